@@ -1,0 +1,143 @@
+"""Pins the CPU oracle (oracle/valle_oracle.py) against vectors frozen from the EXECUTED reference
+(oracle/make_golden.py -> tests/golden/*.npz).  CPU only."""
+import numpy as np
+import torch
+
+from oracle import synth
+from oracle import valle_oracle as vo
+from oracle.valle_oracle import OracleConfig
+
+T = torch.from_numpy
+
+
+def close(a, b, tol=2e-5):
+    a = a if isinstance(a, torch.Tensor) else T(np.asarray(a))
+    b = b if isinstance(b, torch.Tensor) else T(np.asarray(b))
+    assert a.shape == b.shape, (a.shape, b.shape)
+    err = (a - b).abs().max().item()
+    ref = b.abs().max().item() + 1e-12
+    assert err <= tol * max(1.0, ref), f'max err {err} (ref scale {ref})'
+
+
+def test_modules(golden):
+    g = golden('modules')
+    d, H = 64, 4
+    x = T(g['mha_x'])
+    S = x.shape[1]
+    sd = {'a.' + k: v for k, v in synth.synth_state_dict(
+        {'qkv.weight': (3 * d, d), 'out.weight': (d, d), 'out.bias': (d,)}, 7).items()}
+    causal = torch.triu(torch.ones(S, S), diagonal=1)
+    y, (k, v) = vo.multi_head_attention(x, sd, 'a.', H, attn_mask=causal, padding_mask=T(g['mha_pad']),
+                                        use_cache=True)
+    close(y, g['mha_y']); close(k, g['mha_k']); close(v, g['mha_v'])
+    y2, _ = vo.multi_head_attention(x, sd, 'a.', H)
+    close(y2, g['mha_y_nomask'])
+    y1, (k1, _) = vo.multi_head_attention(T(g['mha_x1']), sd, 'a.', H, kv_cache=(k, v), use_cache=True)
+    close(y1, g['mha_y1']); close(k1, g['mha_k1'])
+
+    sdf = {'f.' + k: v for k, v in synth.synth_state_dict(
+        {'linear_1.weight': (4 * d, d), 'linear_1.bias': (4 * d,),
+         'linear_2.weight': (d, 4 * d), 'linear_2.bias': (d,)}, 8).items()}
+    close(vo.feed_forward(x, sdf, 'f.'), g['ffn_y'])
+
+    sda = synth.synth_state_dict({'project_layer.weight': (2 * d, d), 'project_layer.bias': (2 * d,),
+                                  'norm.weight': (d,), 'norm.bias': (d,)}, 9)
+    emb = T(g['ada_emb'])
+    close(vo.adaptive_layer_norm(x, emb, sda['project_layer.weight'], sda['project_layer.bias'],
+                                 sda['norm.weight'], sda['norm.bias']), g['ada_y'])
+    close(vo.add_pe(x, vo.sinusoidal_pe(5000, d)), g['pe_y'], tol=1e-6)
+
+    for norm, tag in (('LayerNorm', 'ln'), ('AdaptiveLayerNorm', 'ada')):
+        oc = OracleConfig(num_layers=2, d_model=d, n_heads=H, dim_feedforward=4 * d, norm=norm)
+        shapes = {}
+        for i in range(2):
+            shapes.update(synth._layer_shapes(oc, f'layers.{i}.'))
+        sdt = synth.synth_state_dict(shapes, 10)
+        e = emb if norm != 'LayerNorm' else None
+        mask = vo.build_attn_mask(2, 4)
+        yf, kv = vo.transformer(x, sdt, oc, prefix='', attn_mask=mask, embedding=e, use_cache=True)
+        ys, kv2 = vo.transformer(torch.cat([x, T(g['mha_x1'])], 1), sdt, oc, prefix='', attn_mask=mask,
+                                 embedding=e, kv_cache=kv, use_cache=True)
+        yp, _ = vo.transformer(x, sdt, oc, prefix='', embedding=e)
+        close(yf, g[f'tr_{tag}_full']); close(ys, g[f'tr_{tag}_step']); close(yp, g[f'tr_{tag}_plain'])
+        close(kv2[-1][0], g[f'tr_{tag}_k_last'])
+
+
+def test_masks_sampling(golden):
+    g = golden('masks_sampling')
+    assert np.array_equal(vo.build_attn_mask(3, 4).numpy(), g['attn_mask_3_4'])
+    assert np.array_equal(vo.build_pad_mask(torch.tensor([4, 2, 3, 1])).numpy(), g['pad_mask'])
+    logits = T(g['samp_logits'])
+    for i, (k, p) in enumerate(g['samp_cases']):
+        f = vo.top_k_top_p_filter(logits, int(k), float(p))
+        ref = T(g[f'samp_filtered_{i}'])
+        assert torch.equal(torch.isinf(f), torch.isinf(ref)), f'case {i}'
+        assert torch.equal(f[~torch.isinf(f)], ref[~torch.isinf(ref)])
+    # log-prob of the reference's own draw under the filtered distribution (utils.py:65-66)
+    tok = T(g['samp_tok'])
+    f = vo.top_k_top_p_filter(logits / 0.7, 10, 0.8)
+    lp = torch.log_softmax(f, -1).gather(1, tok)[:, 0]
+    close(lp, g['samp_logprob'], tol=1e-6)
+    s, lp1 = vo.topk_sampling(logits, 1, 1.0, 1.0)
+    assert np.array_equal(s.numpy(), g['greedy_tok'])
+    close(lp1, g['greedy_logprob'], tol=1e-6)
+    for i, lpn in enumerate((1.0, 0.0, 2.0)):
+        best = vo.get_best_beam(T(g['beam_x']), T(g['beam_slp']), 1024, lpn)
+        assert np.array_equal(best.numpy(), g[f'beam_best_{i}'])
+
+
+def test_injected_uniform_sampling_is_consistent():
+    torch.manual_seed(0)
+    logits = torch.randn(4, 1025) * 2
+    f = vo.top_k_top_p_filter(logits, 20, 0.9)
+    p = torch.softmax(f, -1)
+    for u in (0.0, 0.3, 0.77, 0.999999):
+        s, lp = vo.topk_sampling(logits, 20, 0.9, 1.0, uniforms=torch.full((4,), u))
+        assert (p.gather(1, s) > 0).all()
+        cdf = p.cumsum(-1)
+        hi = cdf.gather(1, s)[:, 0]
+        lo = hi - p.gather(1, s)[:, 0]
+        assert ((lo <= u + 1e-6) & (u < hi + 1e-6)).all()
+        close(lp, torch.log(p.gather(1, s))[:, 0], tol=1e-5)
+
+
+def test_ar_tiny(golden):
+    g = golden('ar_tiny')
+    inp = synth.tiny_inputs(0)
+    for beams in (1, 2):
+        oc = synth.tiny_config('LayerNorm', num_beams=beams)
+        sd = synth.synth_state_dict(synth.ar_state_shapes(oc), 0)
+        codes, trace, _, _ = vo.ar_generate(sd, oc, inp['prompt_tokens'], inp['prompt_codes'],
+                                            inp['target_tokens'], return_trace=True)
+        assert np.array_equal(codes.numpy(), g[f'gen_b{beams}_codes'])
+        close(torch.stack(trace), g[f'gen_b{beams}_logits'])
+    oc = synth.tiny_config('LayerNorm')
+    sd = synth.synth_state_dict(synth.ar_state_shapes(oc), 0)
+    logits, loss = vo.ar_teacher_forced(sd, oc, T(g['tf_tokens']), T(g['tf_codes']),
+                                        T(g['tf_tokens_lens']), T(g['tf_codes_lens']), T(g['tf_target']))
+    close(logits, g['tf_logits']); close(loss, g['tf_loss'], tol=1e-6)
+    # early EOS
+    w = sd['proj.weight'].clone()
+    w[oc.eos_token] = T(g['eos_row'])
+    sd['proj.weight'] = w
+    codes = vo.ar_generate(sd, oc, inp['prompt_tokens'], inp['prompt_codes'], inp['target_tokens'])
+    assert np.array_equal(codes.numpy(), g['gen_eos_codes'])
+    assert 0 < len(codes) <= 10
+
+
+def test_nar_tiny(golden):
+    g = golden('nar_tiny')
+    inp = synth.tiny_inputs(0)
+    oc = synth.tiny_config('AdaptiveLayerNorm')
+    sd = synth.synth_state_dict(synth.nar_state_shapes(oc), 1)
+    codes, trace = vo.nar_generate(sd, oc, inp['prompt_tokens'], inp['prompt_codes'],
+                                   inp['target_tokens'], inp['first_layer'], return_trace=True)
+    assert np.array_equal(codes.numpy(), g['nar_codes'])
+    close(torch.stack(trace), g['nar_logits'])
+    y_emb, prefix_len = vo.nar_prepare_audio_codes(sd, oc, T(g['nar_tf_codes']), int(g['nar_tf_layer']))
+    assert prefix_len == int(g['nar_tf_prefix_len'])
+    close(y_emb, g['nar_tf_yemb'], tol=1e-6)
+    B = g['nar_tf_codes'].shape[0]
+    logits, loss = vo.nar_teacher_forced(sd, oc, T(g['nar_tf_tokens']), T(g['nar_tf_codes']),
+                                         torch.full((B,), 5), torch.full((B,), 12), int(g['nar_tf_layer']))
+    close(logits, g['nar_tf_logits']); close(loss, g['nar_tf_loss'], tol=1e-6)
