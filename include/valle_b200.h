@@ -1,0 +1,163 @@
+/*
+ * valle_b200.h -- C ABI of libvalle_b200.so (hand-written sm_100a kernels for the Valle2 hot path).
+ *
+ * The reference (KubiakJakub01/Valle2) has no FFI: its "operator interface" for this path is the
+ * set of ATen call sites inside valle/models/{modules,utils,valle_ar,valle_nar}.py.  Each entry
+ * point below replaces one (or a fused group) of those call sites; the reference file:line it
+ * stands in for is cited next to it.  The Python host mirror (valle2_b200/models/*.py) binds these
+ * symbols with ctypes (valle2_b200/_lib.py) -- see INTEGRATION.md for the binding stub.
+ *
+ * Conventions
+ *   - plain C: raw device pointers, sizes, scalars, a CUDA stream passed as void* (cudaStream_t).
+ *   - every function returns 0 (VB_OK) or a negative vb_status; vb_last_error_string() explains.
+ *   - the caller owns all memory (weights, KV page pool, block tables, workspaces, outputs).
+ *   - all launches are asynchronous on the given stream; no hidden host synchronisation, so the
+ *     whole decode step can be captured in a CUDA graph.
+ *   - dtype codes: VB_F32 = 0, VB_BF16 = 1.  "fp32 validation mode" = every tensor VB_F32 and the
+ *     SIMT kernels; "bf16 mode" = bf16 weights/activations/KV with fp32 accumulation (tcgen05).
+ */
+#ifndef VALLE_B200_H_
+#define VALLE_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    VB_OK = 0,
+    VB_ERR_BAD_ARG = -1,
+    VB_ERR_UNSUPPORTED = -2,
+    VB_ERR_CUDA = -3
+} vb_status;
+
+enum { VB_F32 = 0, VB_BF16 = 1 };
+
+/* GEMM epilogues (vb_linear). */
+enum {
+    VB_EPI_NONE = 0,          /* y = x W^T                                  modules.py:146 (qkv), valle_ar.py:158 (proj) */
+    VB_EPI_BIAS = 1,          /* y = x W^T + b                              modules.py:171 (out), :94-99 (AdaLN project) */
+    VB_EPI_BIAS_GELU = 2,     /* y = gelu_erf(x W^T + b)                    modules.py:220-221 (linear_1 + nn.GELU)      */
+    VB_EPI_BIAS_RESIDUAL = 3  /* y = res + x W^T + b                        modules.py:277-278 (residual adds)           */
+};
+
+/* Attention mask modes (vb_attention). */
+enum {
+    VB_MASK_NONE = 0,       /* NAR / decode: no mask (valle_nar.py:152-154, modules.py:338); keys >= kv_lens[b] are
+                               still skipped when kv_lens is given (ragged-batch extension)                              */
+    VB_MASK_PREFIX_LM = 1,  /* utils.py:17-43 build_attn_mask(x_len, y_len) OR key padding (valle_ar.py:69-74),
+                               evaluated from (x_lens[b], kv_lens[b]) instead of a materialised (B,H,S,S) tensor        */
+    VB_MASK_EXPLICIT = 2    /* arbitrary uint8 mask, nonzero = masked (modules.py:160-164 after merge_masks :175-207)    */
+};
+
+/* ---- housekeeping ------------------------------------------------------------------------------------------------ */
+int vb_version(void);
+const char* vb_last_error_string(void);
+/* Fails (VB_ERR_UNSUPPORTED) unless the current device is compute capability 10.x. */
+int vb_device_info(int* sm_count, int* cc_major, int* cc_minor, int64_t* smem_optin_bytes);
+
+/* ---- K1/K2: embedding gather (sum over codebooks) + sinusoidal PE ------------------------------------------------ */
+/* out[(b*out_rows_per_batch + out_row_offset + t), :] =
+ *       sum_{j < nq(t)} tables[j][ids[b][t][j]]  (left-to-right fp32 sum)  +  pe[pos(b,t)]
+ *   nq(t) = nq_a for t < t_split else nq_b;  pos(b,t) = (pos_b ? pos_b[b] : pos_offset) + t
+ *   ids: int32 [B][T][Q]; tables: fp32 [Q][V][d]; pe: fp32 [max_len][d]; out: fp32 rows of d.
+ * Replaces modules.py:33-37 (TokenEmbedding), :78-80 (PositionalEncoding), valle_ar.py:128-129,143-144,
+ * valle_nar.py:131-133,144-148,180-185 (codebook sums). */
+int vb_embed_sum_pe(const int32_t* ids, const float* tables, const float* pe, float* out,
+                    int B, int T, int Q, int V, int d, int t_split, int nq_a, int nq_b,
+                    int pos_offset, const int32_t* pos_b, int max_len,
+                    int64_t out_rows_per_batch, int64_t out_row_offset, void* stream);
+
+/* ---- K3: LayerNorm / folded AdaLN, optionally fused with the split-K reduction + bias + residual ----------------- */
+/* if (n_part > 0)  x[r,:] += bias[:] + sum_{s<n_part} part[s*part_stride + r*d + :]   (fixed order, x updated in place)
+ * y[r,:] = (x[r,:] - mean) * rsqrt(var + eps) * gamma + beta           (y may be NULL: residual update only;
+ *                                                                        gamma = beta = NULL: y = cast(x), no norm)
+ * x: fp32 [R][d]; gamma/beta fp32 [d] (AdaLN: pre-folded w*gamma, w*beta+b -- modules.py:93-99); y: y_dtype [R][d].
+ * Replaces nn.LayerNorm at modules.py:89,234-235,271,278 and the residual adds :277-278 on the decode path. */
+int vb_residual_layernorm(float* x, const float* part, int n_part, int64_t part_stride, const float* bias,
+                          const float* gamma, const float* beta, void* y, int y_dtype,
+                          int64_t R, int d, float eps, void* stream);
+
+/* y[r, n] = act(sum_s part[s][r][n] + bias[n]); act = gelu_erf if gelu != 0.  y: y_dtype.  (modules.py:220-221) */
+int vb_reduce_bias_act(const float* part, int n_part, int64_t part_stride, const float* bias, int gelu,
+                       void* y, int y_dtype, int64_t R, int N, void* stream);
+
+/* ---- K4/K7/K8/K9: linear layers --------------------------------------------------------------------------------- */
+/* y[M,N] = epilogue(x[M,K] . w[N,K]^T)   (nn.Linear layout: w is (out,in) row-major)
+ *   fp32 mode : x,w,y VB_F32 -> SIMT fp32 kernel (bit-reproducible, used for the 1e-5 validation mode)
+ *   bf16 mode : x,w VB_BF16 (K % 64 == 0... see vb_linear_query) -> tcgen05/TMEM GEMM fed by TMA, fp32 accumulate;
+ *               y VB_BF16 or VB_F32; bias fp32 [N]; residual fp32 [M][N] (may alias y when y is fp32).
+ * ldx/ldw/ldy are row pitches in elements. */
+int vb_linear(const void* x, int x_dtype, int64_t ldx, const void* w, int w_dtype, int64_t ldw,
+              const float* bias, const float* residual, int64_t ldr, void* y, int y_dtype, int64_t ldy,
+              int64_t M, int64_t N, int64_t K, int epilogue, void* stream);
+
+/* Decode-shape (M <= 256) weight-streaming GEMM, swap-AB on tcgen05 with split-K:
+ *   part[s][m][n] = sum_{k in slice s} x[m,k] w[n,k]      s < n_split, fp32, part_stride = elements between slices.
+ * Deterministic: consumers (vb_residual_layernorm / vb_reduce_bias_act / vb_attn_decode_paged / vb_sample) add the
+ * slices in index order.  x,w bf16.  Returns the split count actually used in *n_split_out (<= max_split). */
+int vb_linear_decode_splits(int64_t N, int64_t K, int max_split);   /* pure query: the split count vb_linear_decode uses */
+int vb_linear_decode(const void* x, int64_t ldx, const void* w, int64_t ldw, float* part, int64_t part_stride,
+                     int64_t M, int64_t N, int64_t K, int max_split, int* n_split_out, void* stream);
+
+/* ---- K5/K6: attention -------------------------------------------------------------------------------------------- */
+/* General attention over strided q/k/v (element strides), fp32 or bf16 I/O, fp32 math (SIMT).
+ *   q: [B][H][Sq][Dh] via (q_sb,q_sh,q_ss); k,v: [B][H][Sk][Dh]; o: [B][Sq][H*Dh] (row pitch o_ss, batch o_sb).
+ *   mask_mode VB_MASK_PREFIX_LM: query i (absolute index i + q_pos0) may attend key j iff
+ *        j < kv_lens[b]  and  (j < x_lens[b]  or  (i + q_pos0 >= x_lens[b] and j <= i + q_pos0))
+ *   mask_mode VB_MASK_EXPLICIT: mask uint8 with strides (m_sb,m_sh,m_sq) and unit key stride, nonzero = masked.
+ * Replaces F.scaled_dot_product_attention at modules.py:167 (scale 1/sqrt(Dh)). */
+int vb_attention(const void* q, const void* k, const void* v, int dtype,
+                 int64_t q_sb, int64_t q_sh, int64_t q_ss, int64_t k_sb, int64_t k_sh, int64_t k_ss,
+                 int64_t v_sb, int64_t v_sh, int64_t v_ss, void* o, int o_dtype, int64_t o_sb, int64_t o_ss,
+                 int B, int H, int Sq, int Sk, int Dh, int mask_mode, int q_pos0,
+                 const int32_t* x_lens, const int32_t* kv_lens,
+                 const uint8_t* mask, int64_t m_sb, int64_t m_sh, int64_t m_sq, void* stream);
+
+/* Flash-style tensor-core attention for prefill / NAR over a packed qkv buffer [B][S][3][H][64] (bf16).
+ * Same mask semantics as vb_attention (NONE / PREFIX_LM).  o: bf16 [B][S][H*64]. */
+int vb_attention_prefill_tc(const void* qkv, void* o, int B, int S, int H, int mask_mode,
+                            const int32_t* x_lens, const int32_t* kv_lens, void* stream);
+
+/* Paged KV pool layout (one pool per layer): [page][2 (K,V)][H][page_size=64][Dh=64], dtype f32 or bf16.
+ * Copy K,V of a packed qkv buffer [B][S][3][H][Dh] (qkv_dtype) into the pool through block_table[B][max_pages];
+ * only positions < kv_lens[b] are written.  Replaces the cache construction at modules.py:151-157. */
+int vb_kv_scatter_paged(const void* qkv, int qkv_dtype, void* pool, int pool_dtype, const int32_t* block_table,
+                        int max_pages, const int32_t* kv_lens, int B, int S, int H, int Dh, void* stream);
+
+/* One decode step of attention for every sequence (modules.py:146-167 at n=1 with a cache):
+ *   q,k,v (new token) = sum_s qkv_part[s][b][3*H*Dh]  (fixed order);  k,v are appended to the pool at position
+ *   seq_lens[b];  o[b] = softmax(q K^T / sqrt(Dh)) V over positions 0..seq_lens[b] (inclusive of the new token).
+ * Split-T (flash-decoding): grid (n_tsplit, H, B); partials in ws (>= vb_attn_decode_ws_bytes), the last CTA of each
+ * (b,h) merges them -- no second launch.  o: o_dtype [B][H*Dh].  Dh must be 64, page_size 64. */
+int64_t vb_attn_decode_ws_bytes(int B, int H, int n_tsplit);
+int vb_attn_decode_paged(const float* qkv_part, int n_part, int64_t part_stride, void* pool, int pool_dtype,
+                         const int32_t* block_table, int max_pages, const int32_t* seq_lens,
+                         void* o, int o_dtype, int B, int H, int Dh, int n_tsplit, void* ws, void* stream);
+
+/* ---- K9-K12: logits -> temperature -> top-k -> top-p -> sample (+ log-prob) --------------------------------------- */
+/* logits[r][:] = sum_s logits_part[s*part_stride + r*row_stride + :], r < R, V <= 4096.
+ * utils.py:59-66 + transformers 4.38.2 top_k_top_p_filtering: /temperature; keep >= k-th largest (ties kept);
+ * ascending cumulative softmax, drop cum <= 1-p, always keep the largest; softmax; draw; log_softmax at the draw.
+ * The draw is inverse-CDF in index order with u = uniforms[r] (if given) else hash(seed, *step_ptr, r);
+ * top_k == 1 picks the lowest-index maximum (greedy).  out_tok int32 [R]; out_logprob fp32 [R] (nullable).
+ * Also serves valle_nar.py:160 (top_k=0, top_p=1 -> plain Categorical; greedy -> argmax). */
+int vb_sample(const float* logits_part, int n_part, int64_t part_stride, int64_t row_stride, int R, int V,
+              float temperature, int top_k, float top_p, const float* uniforms, uint64_t seed,
+              const int32_t* step_ptr, int32_t* out_tok, float* out_logprob, void* stream);
+
+/* K11: device-side beam bookkeeping of valle_ar.py:167-171 for B rows (no host sync):
+ *   sum_logprobs[b] += logprob[b] * (last[b] != eos);  tok = (last[b]==eos) ? eos : sample[b];
+ *   if every tok == eos and *stop_step < 0: *stop_step = *step;   codes_out[b][*step] = tok; last[b] = tok;
+ *   seq_lens[b] += 1; audio_pos[b] += 1; *step += 1.
+ * state: int32 [2] = {step, stop_step}. */
+int vb_ar_bookkeeping(const int32_t* sample, const float* logprob, int32_t* last, float* sum_logprobs,
+                      int32_t* codes_out, int64_t codes_stride, int32_t* seq_lens, int32_t* audio_pos,
+                      int32_t* state, int B, int eos, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VALLE_B200_H_ */

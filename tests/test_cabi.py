@@ -1,0 +1,48 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library builds, loads without a GPU, and exports every
+symbol that include/valle_b200.h declares (no compute calls here)."""
+import ctypes
+import os
+import re
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, 'include', 'valle_b200.h')).read()
+    text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
+    return sorted(set(re.findall(r'\b(vb_[a-z0-9_]+)\s*\(', text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from valle2_b200 import _lib
+    lib = _lib.load()
+    declared = _declared_symbols()
+    assert len(declared) >= 15
+    for name in declared:
+        assert hasattr(lib, name), f'{name} declared in include/valle_b200.h but not exported'
+    assert sorted(_lib.SIGNATURES) == declared, 'ctypes signature table out of sync with the header'
+    assert lib.vb_version() >= 100
+    assert isinstance(lib.vb_last_error_string(), bytes)
+
+
+def test_pure_queries_need_no_gpu():
+    from valle2_b200 import _lib
+    lib = _lib.load()
+    assert lib.vb_attn_decode_ws_bytes(32, 16, 4) > 32 * 16 * 4 * 64 * 4
+    ns = lib.vb_linear_decode_splits(3072, 1024, 32)
+    assert 1 <= ns <= 8
+
+
+def test_bad_arguments_are_reported_not_crashed():
+    from valle2_b200 import _lib
+    lib = _lib.load()
+    rc = lib.vb_sample(None, 1, 0, 0, 1, 10, ctypes.c_float(1.0), 1, ctypes.c_float(1.0), None, 0, None, None, None, None)
+    assert rc == -1 and b'null' in lib.vb_last_error_string()
+
+
+def test_no_cpu_fallback():
+    import pytest
+    import torch
+    from valle2_b200 import ops
+    with pytest.raises(Exception):
+        ops.linear(torch.zeros(4, 64), torch.zeros(8, 64))

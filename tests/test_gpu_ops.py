@@ -1,0 +1,322 @@
+"""Kernel-level parity on a B200: every C-ABI entry point against a plain torch / oracle computation of the
+same op on the same seeded inputs.  Tolerances: fp32 kernels 1e-5 (relative to the output scale), bf16 tensor-core
+kernels 1e-2 (bf16 operands, fp32 accumulate)."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import valle_oracle as vo  # noqa: E402
+
+
+def rel_err(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return ((a - b).abs().max() / (b.abs().max() + 1e-30)).item()
+
+
+@pytest.fixture(scope='module')
+def ops():
+    from valle2_b200 import ops as _ops
+    info = _ops.device_info()
+    assert info['cc'][0] == 10
+    return _ops
+
+
+def test_embed_sum_pe(ops):
+    torch.manual_seed(0)
+    B, T, Q, V, d = 3, 7, 4, 50, 64
+    ids = torch.randint(0, V, (B, T, Q), dtype=torch.int32, device='cuda')
+    tables = torch.randn(Q, V, d, device='cuda')
+    pe = vo.sinusoidal_pe(100, d).cuda()
+    out = torch.zeros(B, T + 2, d, device='cuda')
+    ops.embed_sum_pe(ids, tables, pe, out.view(-1, d), t_split=3, nq_a=Q, nq_b=2, pos_offset=5,
+                     out_rows_per_batch=T + 2, out_row_offset=2)
+    ref = torch.zeros(B, T, d, device='cuda')
+    for t in range(T):
+        nq = Q if t < 3 else 2
+        for j in range(nq):
+            ref[:, t] = ref[:, t] + tables[j][ids[:, t, j].long()]
+        ref[:, t] = ref[:, t] + pe[5 + t]
+    assert torch.equal(out[:, 2:], ref)
+    assert (out[:, :2] == 0).all()
+    pos_b = torch.tensor([0, 10, 20], dtype=torch.int32, device='cuda')
+    out2 = torch.zeros(B, 1, d, device='cuda')
+    ops.embed_sum_pe(ids[:, :1, :1].contiguous(), tables[:1].contiguous(), pe, out2.view(-1, d), pos_b=pos_b)
+    ref2 = tables[0][ids[:, 0, 0].long()] + pe[pos_b.long()]
+    assert torch.equal(out2[:, 0], ref2)
+
+
+@pytest.mark.parametrize('d', [1024, 256, 64, 96])
+@pytest.mark.parametrize('ydt', [torch.float32, torch.bfloat16])
+def test_residual_layernorm(ops, d, ydt):
+    torch.manual_seed(1)
+    R, ns = 37, 3
+    x = torch.randn(R, d, device='cuda') * 2 + 0.5
+    g, b = torch.randn(d, device='cuda'), torch.randn(d, device='cuda')
+    part = torch.randn(ns, R, d, device='cuda')
+    bias = torch.randn(d, device='cuda')
+    y = torch.empty(R, d, device='cuda', dtype=ydt)
+    x1 = x.clone()
+    ops.residual_layernorm(x1, g, b, y, eps=1e-5)
+    ref = vo.layer_norm(x.cpu(), g.cpu(), b.cpu())
+    tol = 1e-5 if ydt == torch.float32 else 8e-3
+    assert rel_err(y.float(), ref) < tol
+    assert torch.equal(x1, x)
+    x2 = x.clone()
+    ops.residual_layernorm(x2, g, b, y, part=part, n_part=ns, part_stride=R * d, bias=bias)
+    xr = x.cpu() + (bias.cpu() + part[0].cpu() + part[1].cpu() + part[2].cpu())
+    assert rel_err(x2, xr) < 1e-6
+    assert rel_err(y.float(), vo.layer_norm(xr, g.cpu(), b.cpu())) < tol
+    # cast-only mode
+    ops.residual_layernorm(x2, None, None, y)
+    assert rel_err(y.float(), x2) < (1e-7 if ydt == torch.float32 else 4e-3)
+
+
+def test_reduce_bias_act(ops):
+    torch.manual_seed(2)
+    R, N, ns = 5, 1024, 4
+    part = torch.randn(ns, R, N, device='cuda')
+    bias = torch.randn(N, device='cuda')
+    y = torch.empty(R, N, device='cuda', dtype=torch.bfloat16)
+    ops.reduce_bias_act(part, ns, R * N, bias, True, y)
+    ref = vo.gelu_erf((part.sum(0) + bias).cpu())
+    assert rel_err(y.float(), ref) < 8e-3
+    y32 = torch.empty(R, N, device='cuda')
+    ops.reduce_bias_act(part, ns, R * N, bias, False, y32)
+    assert rel_err(y32, (part[0] + part[1] + part[2] + part[3] + bias)) < 1e-6
+
+
+EPIS = ['none', 'bias', 'gelu', 'residual']
+
+
+def _ref_linear(x, w, bias, res, epi):
+    y = x.double() @ w.double().t()
+    if epi != 'none':
+        y = y + bias.double()
+    if epi == 'gelu':
+        y = 0.5 * y * (1 + torch.erf(y / math.sqrt(2)))
+    if epi == 'residual':
+        y = y + res.double()
+    return y
+
+
+@pytest.mark.parametrize('M,N,K', [(37, 100, 64), (128, 256, 1024), (5, 1025, 256), (200, 192, 60)])
+@pytest.mark.parametrize('epi', EPIS)
+def test_linear_fp32(ops, M, N, K, epi):
+    torch.manual_seed(3)
+    x, w = torch.randn(M, K, device='cuda'), torch.randn(N, K, device='cuda') / math.sqrt(K)
+    bias, res = torch.randn(N, device='cuda'), torch.randn(M, N, device='cuda')
+    y = ops.linear(x, w, None if epi == 'none' else bias, gelu=(epi == 'gelu'),
+                   residual=res if epi == 'residual' else None)
+    assert rel_err(y, _ref_linear(x, w, bias, res, epi)) < 1e-5
+
+
+@pytest.mark.parametrize('M,N,K', [(128, 256, 64), (256, 512, 128), (300, 1024, 1024), (57, 192, 64),
+                                   (1000, 3072, 1024), (129, 100, 256), (4096, 1024, 4096), (64, 1025, 1024)])
+@pytest.mark.parametrize('epi', EPIS)
+@pytest.mark.parametrize('ydt', [torch.bfloat16, torch.float32])
+def test_linear_bf16_tc(ops, M, N, K, epi, ydt):
+    torch.manual_seed(4)
+    x = torch.randn(M, K, device='cuda').bfloat16()
+    w = (torch.randn(N, K, device='cuda') / math.sqrt(K)).bfloat16()
+    bias, res = torch.randn(N, device='cuda'), torch.randn(M, N, device='cuda')
+    y = ops.linear(x, w, None if epi == 'none' else bias, gelu=(epi == 'gelu'),
+                   residual=res if epi == 'residual' else None, out_dtype=ydt)
+    torch.cuda.synchronize()
+    err = rel_err(y.float(), _ref_linear(x, w, bias, res, epi))
+    assert err < (1e-2 if ydt == torch.bfloat16 else 1e-4), err
+
+
+def test_linear_bf16_inplace_residual(ops):
+    torch.manual_seed(5)
+    M, N, K = 384, 1024, 1024
+    x = torch.randn(M, K, device='cuda').bfloat16()
+    w = (torch.randn(N, K, device='cuda') / math.sqrt(K)).bfloat16()
+    bias, res = torch.randn(N, device='cuda'), torch.randn(M, N, device='cuda')
+    ref = _ref_linear(x, w, bias, res, 'residual')
+    ops.linear(x, w, bias, residual=res, out=res)
+    assert rel_err(res, ref) < 1e-4
+
+
+@pytest.mark.parametrize('M', [1, 5, 16, 32, 33, 64, 200, 256])
+@pytest.mark.parametrize('N,K', [(1025, 1024), (3072, 1024), (1024, 4096), (256, 256), (768, 64)])
+def test_linear_decode(ops, M, N, K):
+    torch.manual_seed(6)
+    x = torch.randn(M, K, device='cuda').bfloat16()
+    w = (torch.randn(N, K, device='cuda') / math.sqrt(K)).bfloat16()
+    ns_max = 32
+    part = torch.full((ns_max, M, N), float('nan'), device='cuda')
+    ns = ops.linear_decode(x, w, part, M * N, ns_max)
+    assert ns == ops.linear_decode_splits(N, K, ns_max) and 1 <= ns <= ns_max
+    torch.cuda.synchronize()
+    y = part[:ns].sum(0)
+    assert not torch.isnan(y).any()
+    assert rel_err(y, x.double() @ w.double().t()) < 1e-4
+
+
+def _dense_attention(q, k, v, allowed):
+    s = (q.double() @ k.double().transpose(-1, -2)) / math.sqrt(q.shape[-1])
+    if allowed is not None:
+        s = s.masked_fill(~allowed, float('-inf'))
+    return torch.softmax(s, -1) @ v.double()
+
+
+@pytest.mark.parametrize('dt', [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize('Dh', [64, 16])
+def test_attention_masks(ops, dt, Dh):
+    torch.manual_seed(7)
+    B, H, S = 3, 4, 45
+    d = H * Dh
+    qkv = torch.randn(B, S, 3, H, Dh, device='cuda').to(dt)
+    q, k, v = (qkv[:, :, i].permute(0, 2, 1, 3) for i in range(3))
+    out = torch.empty(B, S, d, device='cuda', dtype=dt)
+    tol = 1e-5 if dt == torch.float32 else 1e-2
+    # no mask
+    ops.attention(q, k, v, out)
+    ref = _dense_attention(q.float(), k.float(), v.float(), None).permute(0, 2, 1, 3).reshape(B, S, d)
+    assert rel_err(out.float(), ref) < tol
+    # prefix-LM + key padding, evaluated in-kernel from lengths
+    x_lens = torch.tensor([10, 10, 10], dtype=torch.int32, device='cuda')
+    kv_lens = torch.tensor([45, 30, 41], dtype=torch.int32, device='cuda')
+    ops.attention(q, k, v, out, mask_mode=ops.MASK_PREFIX_LM, x_lens=x_lens, kv_lens=kv_lens)
+    m = vo.build_attn_mask(10, S - 10).cuda()[None, None].expand(B, H, S, S).clone()
+    pad = torch.arange(S, device='cuda')[None, :] >= kv_lens[:, None]
+    m = m | pad[:, None, None, :]
+    ref = _dense_attention(q.float(), k.float(), v.float(), ~m).permute(0, 2, 1, 3).reshape(B, S, d)
+    assert rel_err(out.float(), ref) < tol
+    # the same mask, materialised (module-level path)
+    ops.attention(q, k, v, out, mask_mode=ops.MASK_EXPLICIT, mask=m.to(torch.uint8).contiguous())
+    assert rel_err(out.float(), ref) < tol
+
+
+@pytest.mark.parametrize('dt', [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize('n_tsplit', [1, 4])
+def test_attn_decode_paged(ops, dt, n_tsplit):
+    torch.manual_seed(8)
+    B, H, Dh, max_pages = 5, 4, 64, 6
+    d = H * Dh
+    seq = torch.tensor([1, 63, 64, 200, 319], dtype=torch.int32, device='cuda')
+    n_pages = B * max_pages
+    perm = torch.randperm(n_pages, device='cuda').to(torch.int32)
+    bt = perm.view(B, max_pages).contiguous()
+    dense_k = torch.randn(B, H, max_pages * 64, Dh, device='cuda').to(dt)
+    dense_v = torch.randn(B, H, max_pages * 64, Dh, device='cuda').to(dt)
+    pool = torch.zeros(n_pages, 2, H, 64, Dh, device='cuda', dtype=dt)
+    for b in range(B):
+        for p in range(max_pages):
+            pool[bt[b, p], 0] = dense_k[b, :, p * 64:(p + 1) * 64]
+            pool[bt[b, p], 1] = dense_v[b, :, p * 64:(p + 1) * 64]
+    n_part = 3
+    part = torch.randn(n_part, B, 3 * d, device='cuda')
+    out = torch.empty(B, d, device='cuda', dtype=dt)
+    ws = torch.zeros(ops.attn_decode_ws_bytes(B, H, n_tsplit) // 4 + 16, dtype=torch.int32, device='cuda')
+    for rep in range(2):   # second launch checks that the split counters reset themselves
+        pool_run = pool.clone()
+        ops.attn_decode_paged(part, n_part, B * 3 * d, pool_run, bt, seq, out, B, H, Dh, n_tsplit, ws)
+        torch.cuda.synchronize()
+        qkv = (part[0] + part[1] + part[2]).view(B, 3, H, Dh)
+        for b in range(B):
+            n = int(seq[b])
+            knew, vnew = qkv[b, 1].to(dt), qkv[b, 2].to(dt)
+            K = torch.cat([dense_k[b, :, :n], knew[:, None]], 1).float()
+            V = torch.cat([dense_v[b, :, :n], vnew[:, None]], 1).float()
+            ref = _dense_attention(qkv[b, 0][:, None].float(), K, V, None)[:, 0].reshape(d)
+            assert rel_err(out[b].float(), ref) < (1e-5 if dt == torch.float32 else 1e-2), (b, rep)
+            page, slot = int(bt[b, n // 64]), n % 64
+            assert torch.equal(pool_run[page, 0, :, slot], knew) and torch.equal(pool_run[page, 1, :, slot], vnew)
+
+
+def test_kv_scatter(ops):
+    torch.manual_seed(9)
+    B, S, H, Dh = 2, 70, 4, 64
+    d = H * Dh
+    qkv = torch.randn(B * S, 3 * d, device='cuda').bfloat16()
+    bt = torch.tensor([[3, 0], [1, 2]], dtype=torch.int32, device='cuda')
+    lens = torch.tensor([70, 65], dtype=torch.int32, device='cuda')
+    pool = torch.zeros(4, 2, H, 64, Dh, device='cuda', dtype=torch.bfloat16)
+    ops.kv_scatter_paged(qkv, pool, bt, lens, B, S, H, Dh)
+    v = qkv.view(B, S, 3, H, Dh)
+    for b in range(B):
+        for s in range(S):
+            page, slot = int(bt[b, s // 64]), s % 64
+            if s < int(lens[b]):
+                assert torch.equal(pool[page, 0, :, slot], v[b, s, 1]) and torch.equal(pool[page, 1, :, slot], v[b, s, 2])
+            else:
+                assert (pool[page, :, :, slot] == 0).all()
+
+
+@pytest.mark.parametrize('top_k,top_p,temp', [(1, 1.0, 1.0), (50, 1.0, 1.0), (10, 0.8, 0.7), (0, 0.5, 1.0), (0, 1.0, 1.3),
+                                              (5, 0.3, 1.0), (2000, 0.9, 1.0)])
+def test_sample_matches_oracle(ops, top_k, top_p, temp):
+    torch.manual_seed(10)
+    R, V, ns = 12, 1025, 2
+    part = torch.randn(ns, R, V, device='cuda') * 2
+    logits = (part[0] + part[1]).cpu()
+    tok = torch.empty(R, dtype=torch.int32, device='cuda')
+    lp = torch.empty(R, device='cuda')
+    for trial in range(4):
+        u = torch.rand(R, generator=torch.Generator().manual_seed(trial))
+        ops.sample(part, ns, R * V, V, R, V, temperature=temp, top_k=top_k, top_p=top_p, out_tok=tok, out_logprob=lp,
+                   uniforms=u.cuda())
+        s_ref, lp_ref = vo.topk_sampling(logits, top_k, top_p, temp, uniforms=u)
+        filt = vo.top_k_top_p_filter(logits / temp, top_k, top_p)
+        probs = torch.softmax(filt, -1)
+        t = tok.cpu().long()
+        # every draw lands in the oracle's surviving set ...
+        assert (probs.gather(1, t[:, None]) > 0).all()
+        # ... and equals the oracle's inverse-CDF draw unless u sits within rounding of a CDF edge
+        cdf = probs.double().cumsum(-1)
+        same = t == s_ref[:, 0]
+        edge = (cdf - u.double()[:, None]).abs().min(-1).values < 1e-5
+        assert (same | edge).all(), (t, s_ref[:, 0])
+        assert rel_err(lp.cpu()[same], lp_ref[same]) < 1e-5 or same.sum() == 0
+
+
+def test_sample_greedy_ties_and_hash_rng(ops):
+    V = 1025
+    logits = torch.zeros(3, V, device='cuda')
+    logits[0, 7] = 5.0
+    logits[1, [3, 900]] = 2.0
+    logits[2, :] = -1.0
+    tok = torch.empty(3, dtype=torch.int32, device='cuda')
+    lp = torch.empty(3, device='cuda')
+    ops.sample(logits, 1, 0, V, 3, V, temperature=1.0, top_k=1, top_p=1.0, out_tok=tok, out_logprob=lp)
+    assert tok.tolist() == [7, 3, 0]
+    assert (lp.cpu() - torch.tensor([0.0, -math.log(2.0), -math.log(V)])).abs().max() < 1e-5
+    # in-kernel RNG: deterministic per (seed, step, row), different across steps, roughly uniform
+    R = 4096
+    lg = torch.zeros(R, 16, device='cuda')
+    t1 = torch.empty(R, dtype=torch.int32, device='cuda')
+    t2 = torch.empty(R, dtype=torch.int32, device='cuda')
+    step = torch.zeros(1, dtype=torch.int32, device='cuda')
+    ops.sample(lg, 1, 0, 16, R, 16, temperature=1.0, top_k=0, top_p=1.0, out_tok=t1, seed=1234, step_ptr=step)
+    ops.sample(lg, 1, 0, 16, R, 16, temperature=1.0, top_k=0, top_p=1.0, out_tok=t2, seed=1234, step_ptr=step)
+    assert torch.equal(t1, t2)
+    step.fill_(1)
+    ops.sample(lg, 1, 0, 16, R, 16, temperature=1.0, top_k=0, top_p=1.0, out_tok=t2, seed=1234, step_ptr=step)
+    assert not torch.equal(t1, t2)
+    hist = torch.bincount(t1.long(), minlength=16).float() / R
+    assert (hist - 1 / 16).abs().max() < 0.03
+
+
+def test_ar_bookkeeping(ops):
+    B, eos = 4, 1024
+    sample = torch.tensor([5, 1024, 7, 9], dtype=torch.int32, device='cuda')
+    logprob = torch.tensor([-1.0, -2.0, -3.0, -4.0], device='cuda')
+    last = torch.tensor([1, 2, 1024, 3], dtype=torch.int32, device='cuda')
+    slp = torch.zeros(B, device='cuda')
+    codes = torch.zeros(B, 8, dtype=torch.int32, device='cuda')
+    seq = torch.tensor([10, 11, 12, 13], dtype=torch.int32, device='cuda')
+    pos = torch.tensor([3, 3, 3, 3], dtype=torch.int32, device='cuda')
+    state = torch.tensor([2, -1], dtype=torch.int32, device='cuda')
+    ops.ar_bookkeeping(sample, logprob, last, slp, codes, seq, pos, state, eos)
+    assert slp.tolist() == [-1.0, -2.0, 0.0, -4.0]
+    assert codes[:, 2].tolist() == [5, 1024, 1024, 9] and last.tolist() == [5, 1024, 1024, 9]
+    assert seq.tolist() == [11, 12, 13, 14] and pos.tolist() == [4, 4, 4, 4] and state.tolist() == [3, -1]
+    sample.fill_(1024)
+    ops.ar_bookkeeping(sample, logprob, last, slp, codes, seq, pos, state, eos)
+    assert state.tolist() == [4, 3]
+    ops.ar_bookkeeping(sample, logprob, last, slp, codes, seq, pos, state, eos)
+    assert state.tolist() == [5, 3]          # the first all-EOS step is kept

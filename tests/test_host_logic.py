@@ -1,0 +1,97 @@
+"""Host-side logic of the reference-facing API on CPU: the reference's own mask tests
+(tests/test_models_utils.py:7-59, tests/test_modules.py:33-79 of the reference) against our modules, the config
+contract, state_dict key inventory and beam selection."""
+import pytest
+import torch
+
+from oracle import synth
+from oracle.valle_oracle import OracleConfig
+
+
+def test_build_attn_mask_reference_vector():
+    from valle.models.utils import build_attn_mask
+    expected = torch.tensor([[0, 0, 0, 0, 0, 1, 1, 1, 1, 1]] * 5 + [
+        [0, 0, 0, 0, 0, 0, 1, 1, 1, 1], [0, 0, 0, 0, 0, 0, 0, 1, 1, 1], [0, 0, 0, 0, 0, 0, 0, 0, 1, 1],
+        [0, 0, 0, 0, 0, 0, 0, 0, 0, 1], [0, 0, 0, 0, 0, 0, 0, 0, 0, 0]], dtype=torch.bool)
+    mask = build_attn_mask(5, 5, device='cpu')
+    assert mask.shape == expected.shape and torch.equal(mask, expected)
+
+
+@pytest.mark.parametrize('lens,expected', [
+    (torch.tensor([5, 5, 5, 5]), torch.zeros(4, 5, dtype=torch.bool)),
+    (torch.tensor([5, 4, 3, 2]), torch.tensor([[0, 0, 0, 0, 0], [0, 0, 0, 0, 1], [0, 0, 0, 1, 1], [0, 0, 1, 1, 1]],
+                                              dtype=torch.bool)),
+])
+def test_build_pad_mask_reference_vectors(lens, expected):
+    from valle.models.utils import build_pad_mask
+    mask = build_pad_mask(lens, device='cpu')
+    assert mask.shape == expected.shape and torch.equal(mask, expected)
+
+
+@pytest.mark.parametrize('d_model,n_heads,batch_size,seq_len,expected', [
+    (512, 8, 4, 5, [120, 112, 96, 72]),
+    (256, 4, 8, 10, [220, 216, 208, 196, 180, 160, 136, 108]),
+])
+def test_merge_masks_reference_zero_counts(d_model, n_heads, batch_size, seq_len, expected):
+    from valle.models.modules import MultiHeadAttention
+    attention = MultiHeadAttention(d_model=d_model, n_heads=n_heads)
+    pad = (torch.arange(seq_len)[None, :] >= (seq_len - torch.arange(batch_size))[:, None]).long()
+    attn_mask = torch.triu(torch.ones(seq_len, seq_len), diagonal=1)
+    mask = attention.merge_masks(batch_size, attn_mask, pad)
+    assert isinstance(mask, torch.Tensor) and mask.shape == (batch_size, n_heads, seq_len, seq_len)
+    for i, e in enumerate(expected):
+        assert (mask[i] == 0.0).sum().item() == e
+
+
+def test_state_dict_keys_match_reference_inventory(tmp_path):
+    from valle.config import ConfigValle
+    from valle.models import MODEL_DICT, get_model_class
+    assert set(MODEL_DICT) == {'EncodecPip', 'ValleAR', 'ValleNAR'}
+    for kind, norm, shapes_fn in (('ValleAR', 'LayerNorm', synth.ar_state_shapes),
+                                  ('ValleNAR', 'AdaptiveLayerNorm', synth.nar_state_shapes)):
+        oc = OracleConfig(num_layers=2, d_model=64, n_heads=4, dim_feedforward=128, norm=norm)
+        cfg = ConfigValle(num_layers=2, d_model=64, n_heads=4, dim_feedforward=128, norm=norm,
+                          ckpt_path=tmp_path / 'c', log_path=tmp_path / 'l')
+        model = get_model_class(kind)(cfg)
+        sd = model.state_dict()
+        want = shapes_fn(oc)
+        assert list(sd.keys()) == list(want.keys())
+        for k, shape in want.items():
+            assert tuple(sd[k].shape) == tuple(shape), k
+        model.load_state_dict(synth.synth_state_dict(want, 0), strict=True)
+    assert model.eos_token == 1024 and model.bos_token == 1025
+
+
+def test_config_contract(tmp_path):
+    from valle.config import ConfigValle
+    cfg = ConfigValle(ckpt_path=tmp_path / 'a', log_path=tmp_path / 'b')
+    assert (tmp_path / 'a').is_dir() and (tmp_path / 'b').is_dir()
+    assert cfg.quantization_factor == 50 and cfg.bos_token == 1025 and cfg.eos_token == 1024
+    assert cfg.norm == 'AdaptiveLayerNorm' and cfg.num_beams == 4 and cfg.top_k == 50 and cfg.use_kv_cache
+    with pytest.raises(ValueError):
+        ConfigValle(norm='RMSNorm', ckpt_path=tmp_path / 'a', log_path=tmp_path / 'b')
+    with pytest.raises(ValueError):
+        ConfigValle(activation='swish', ckpt_path=tmp_path / 'a', log_path=tmp_path / 'b')
+    (tmp_path / 'h.json').write_text('{"d_model": 128, "ckpt_path": "%s", "log_path": "%s"}' % (tmp_path / 'a', tmp_path / 'b'))
+    assert ConfigValle.from_json(tmp_path / 'h.json').d_model == 128
+
+
+def test_get_best_beam(golden):
+    import numpy as np
+    from valle.models.utils import get_best_beam
+    g = golden('masks_sampling')
+    for i, lp in enumerate((1.0, 0.0, 2.0)):
+        best = get_best_beam(torch.from_numpy(g['beam_x']), torch.from_numpy(g['beam_slp']), 1024, lp)
+        assert np.array_equal(best.numpy(), g[f'beam_best_{i}'])
+
+
+def test_generate_asserts_like_reference(tmp_path):
+    from valle.config import ConfigValle
+    from valle.models import ValleAR
+    cfg = ConfigValle(num_layers=1, d_model=64, n_heads=1, dim_feedforward=64, norm='LayerNorm',
+                      ckpt_path=tmp_path / 'c', log_path=tmp_path / 'l')
+    model = ValleAR(cfg)
+    with pytest.raises(AssertionError):
+        model.generate(torch.zeros(2, 3, dtype=torch.long), torch.zeros(4, 8, dtype=torch.long))
+    with pytest.raises(AssertionError):
+        model.generate(torch.zeros(3, dtype=torch.long), torch.zeros(4, dtype=torch.long))

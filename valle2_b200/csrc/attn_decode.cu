@@ -1,0 +1,307 @@
+// Decode-time attention over the paged KV pool (one new token per sequence) -- the HBM-bound kernel of the AR path.
+//
+//   pool (per layer): [page][2 (K,V)][H][64 tokens][64 dims]   -> for one (b,h) a page is one contiguous 8 KB (bf16)
+//   chunk of K and one of V.  grid = (n_tsplit, H, B): flash-decoding split over the sequence; each CTA streams its
+//   pages with 1D bulk-async copies (cp.async.bulk -> UBLKCP) into a 4-deep shared-memory ring guarded by mbarriers
+//   (one producer warp, four consumer warps), so the bytes in flight do not cost registers.  Consumers read 16-byte
+//   vectors (8 lanes cover one 128-byte K row: coalesced + bank-conflict free), reduce q.k with warp shuffles, keep an
+//   online softmax per warp, and accumulate p.V in registers.  Warps merge through shared memory, splits merge in the
+//   last-arriving CTA of each (b,h) (atomic ticket) -- no second launch.
+//   The new token's q/k/v arrive as split-K partials of the QKV GEMM and are reduced here in fixed order; k/v are
+//   appended to the pool by the CTA that owns the last split.
+// Replaces modules.py:146-167 on the cached path (qkv head split, torch.cat cache growth, SDPA with one query).
+#include <math.h>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int DH = 64;
+constexpr int PAGE = 64;
+constexpr int NSTAGE = 4;
+constexpr int CONSUMER_WARPS = 4;
+constexpr int THREADS = (CONSUMER_WARPS + 1) * 32;
+
+template <typename T> struct PoolTraits;
+template <> struct PoolTraits<__nv_bfloat16> {
+    static constexpr int LPT = 8;   // lanes per token row (128 B / 16 B)
+    static constexpr int EPL = 8;   // elements per lane
+};
+template <> struct PoolTraits<float> {
+    static constexpr int LPT = 16;
+    static constexpr int EPL = 4;
+};
+
+template <typename T, int EPL> __device__ __forceinline__ void load_vec(const uint8_t* smem_ptr, float (&out)[EPL]) {
+    const uint4 raw = *reinterpret_cast<const uint4*>(smem_ptr);
+    if constexpr (sizeof(T) == 2) {
+        out[0] = bf16_lo(raw.x); out[1] = bf16_hi(raw.x); out[2] = bf16_lo(raw.y); out[3] = bf16_hi(raw.y);
+        out[4] = bf16_lo(raw.z); out[5] = bf16_hi(raw.z); out[6] = bf16_lo(raw.w); out[7] = bf16_hi(raw.w);
+    } else {
+        out[0] = __uint_as_float(raw.x); out[1] = __uint_as_float(raw.y);
+        out[2] = __uint_as_float(raw.z); out[3] = __uint_as_float(raw.w);
+    }
+}
+
+template <typename T, typename TO>
+__global__ void __launch_bounds__(THREADS) attn_decode_kernel(const float* __restrict__ qkv_part, int n_part,
+                                                              int64_t part_stride, T* __restrict__ pool,
+                                                              const int32_t* __restrict__ block_table, int max_pages,
+                                                              const int32_t* __restrict__ seq_lens, TO* __restrict__ o,
+                                                              float* __restrict__ ws_o, float* __restrict__ ws_ml,
+                                                              unsigned* __restrict__ counters, int H, int n_tsplit,
+                                                              float scale_log2e) {
+    constexpr int LPT = PoolTraits<T>::LPT, EPL = PoolTraits<T>::EPL;
+    constexpr int TPP = 32 / LPT;                       // tokens per warp pass
+    constexpr int TOK_PER_WARP = PAGE / CONSUMER_WARPS; // 16
+    constexpr int NPASS = TOK_PER_WARP / TPP;
+    constexpr int ROW_BYTES = DH * sizeof(T);
+    constexpr int CHUNK_BYTES = PAGE * ROW_BYTES;       // one (page, K or V, head) chunk
+    constexpr int STAGE_BYTES = 2 * CHUNK_BYTES;
+
+    extern __shared__ __align__(128) uint8_t ring[];
+    __shared__ __align__(8) uint64_t full_bar[NSTAGE];
+    __shared__ __align__(8) uint64_t empty_bar[NSTAGE];
+    __shared__ float q_s[DH], k_s[DH], v_s[DH];
+    __shared__ float w_acc[CONSUMER_WARPS][DH];
+    __shared__ float w_ml[CONSUMER_WARPS][2];
+    __shared__ int is_last;
+
+    const int split = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int d_model = H * DH;
+    const int n_old = seq_lens[b];
+    const int pages_total = (n_old + PAGE - 1) / PAGE;
+    const int pp = (pages_total + n_tsplit - 1) / n_tsplit;
+    const int p0 = min(split * pp, pages_total), p1 = min(p0 + pp, pages_total);
+    const bool owns_new = (split == n_tsplit - 1);
+    const int32_t* bt = block_table + static_cast<int64_t>(b) * max_pages;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NSTAGE; ++s) {
+            mbar_init(smem_u32(&full_bar[s]), 1);
+            mbar_init(smem_u32(&empty_bar[s]), CONSUMER_WARPS);
+        }
+        fence_mbar_init();
+    }
+    // new-token q (and k, v for the owner of the last split): fixed-order reduction of the split-K partials
+    if (threadIdx.x < DH) {
+        const int e = threadIdx.x;
+        const float* src = qkv_part + static_cast<int64_t>(b) * 3 * d_model + h * DH + e;
+        float qv = 0.f, kv = 0.f, vv = 0.f;
+        for (int s = 0; s < n_part; ++s) {
+            qv += src[s * part_stride];
+            if (owns_new) { kv += src[s * part_stride + d_model]; vv += src[s * part_stride + 2 * d_model]; }
+        }
+        q_s[e] = qv * scale_log2e;
+        if (owns_new) {
+            const T kq = from_f32<T>(kv), vq = from_f32<T>(vv);   // the cache precision is what later steps will read
+            k_s[e] = to_f32<T>(kq);
+            v_s[e] = to_f32<T>(vq);
+            const int page = bt[n_old / PAGE], slot = n_old % PAGE;
+            T* kdst = pool + ((static_cast<int64_t>(page) * 2 * H + h) * PAGE + slot) * DH + e;
+            kdst[0] = kq;
+            kdst[static_cast<int64_t>(H) * PAGE * DH] = vq;
+        }
+    }
+    __syncthreads();
+
+    if (warp == CONSUMER_WARPS) {
+        // ---------------- producer ----------------
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int p = p0; p < p1; ++p) {
+                mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+                const uint32_t fb = smem_u32(&full_bar[stage]);
+                mbar_expect_tx(fb, STAGE_BYTES);
+                const int page = bt[p];
+                const T* ksrc = pool + (static_cast<int64_t>(page) * 2 * H + h) * PAGE * DH;
+                const uint32_t dst = smem_u32(ring) + stage * STAGE_BYTES;
+                bulk_load_1d(dst, ksrc, CHUNK_BYTES, fb);
+                bulk_load_1d(dst + CHUNK_BYTES, ksrc + static_cast<int64_t>(H) * PAGE * DH, CHUNK_BYTES, fb);
+                if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+            }
+        }
+        // the producer warp still takes part in the block-level syncs below
+    }
+
+    float m_run = -INFINITY, l_run = 0.f;
+    float acc[EPL];
+#pragma unroll
+    for (int i = 0; i < EPL; ++i) acc[i] = 0.f;
+
+    if (warp < CONSUMER_WARPS) {
+        const int grp = lane / LPT, c = lane % LPT;
+        float qreg[EPL];
+#pragma unroll
+        for (int i = 0; i < EPL; ++i) qreg[i] = q_s[c * EPL + i];
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int p = p0; p < p1; ++p) {
+            mbar_wait(smem_u32(&full_bar[stage]), phase);
+            const uint8_t* ks = ring + stage * STAGE_BYTES;
+            const uint8_t* vs = ks + CHUNK_BYTES;
+            float sc[NPASS];
+            float pmax = -INFINITY;
+#pragma unroll
+            for (int ps = 0; ps < NPASS; ++ps) {
+                const int tok = warp * TOK_PER_WARP + ps * TPP + grp;
+                float kv[EPL];
+                load_vec<T, EPL>(ks + tok * ROW_BYTES + c * 16, kv);
+                float d = 0.f;
+#pragma unroll
+                for (int i = 0; i < EPL; ++i) d = fmaf(qreg[i], kv[i], d);
+#pragma unroll
+                for (int off = 1; off < LPT; off <<= 1) d += __shfl_xor_sync(0xffffffffu, d, off);
+                const bool valid = (p * PAGE + tok) < n_old;
+                sc[ps] = valid ? d : -INFINITY;
+                pmax = fmaxf(pmax, sc[ps]);
+            }
+            pmax = warp_max(pmax);
+            const float m_new = fmaxf(m_run, pmax);
+            if (m_new != -INFINITY) {
+                const float corr = (m_run == -INFINITY) ? 0.f : exp2f(m_run - m_new);
+                l_run *= corr;
+#pragma unroll
+                for (int i = 0; i < EPL; ++i) acc[i] *= corr;
+#pragma unroll
+                for (int ps = 0; ps < NPASS; ++ps) {
+                    const int tok = warp * TOK_PER_WARP + ps * TPP + grp;
+                    const float pj = (sc[ps] == -INFINITY) ? 0.f : exp2f(sc[ps] - m_new);
+                    l_run += pj;
+                    float vv[EPL];
+                    load_vec<T, EPL>(vs + tok * ROW_BYTES + c * 16, vv);
+#pragma unroll
+                    for (int i = 0; i < EPL; ++i) acc[i] = fmaf(pj, vv[i], acc[i]);
+                }
+                m_run = m_new;
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&empty_bar[stage]));
+            if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+        }
+        // the new token (position n_old), handled by lane-group 0 of warp 0 of the last split
+        if (owns_new && warp == 0) {
+            float d = 0.f;
+#pragma unroll
+            for (int i = 0; i < EPL; ++i) d = fmaf(qreg[i], k_s[c * EPL + i], d);
+#pragma unroll
+            for (int off = 1; off < LPT; off <<= 1) d += __shfl_xor_sync(0xffffffffu, d, off);
+            const float s_new = __shfl_sync(0xffffffffu, d, 0);
+            const float m_new = fmaxf(m_run, s_new);
+            const float corr = (m_run == -INFINITY) ? 0.f : exp2f(m_run - m_new);
+            l_run *= corr;
+#pragma unroll
+            for (int i = 0; i < EPL; ++i) acc[i] *= corr;
+            if (grp == 0) {
+                const float pj = exp2f(s_new - m_new);
+                l_run += pj;
+#pragma unroll
+                for (int i = 0; i < EPL; ++i) acc[i] = fmaf(pj, v_s[c * EPL + i], acc[i]);
+            }
+            m_run = m_new;
+        }
+        // merge the lane groups of the warp (all lanes share m_run); l is replicated across the LPT lanes of a group
+#pragma unroll
+        for (int off = LPT; off < 32; off <<= 1) {
+            l_run += __shfl_xor_sync(0xffffffffu, l_run, off);
+#pragma unroll
+            for (int i = 0; i < EPL; ++i) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], off);
+        }
+        if (grp == 0) {
+#pragma unroll
+            for (int i = 0; i < EPL; ++i) w_acc[warp][c * EPL + i] = acc[i];
+        }
+        if (lane == 0) { w_ml[warp][0] = m_run; w_ml[warp][1] = l_run; }
+    }
+    __syncthreads();
+
+    // merge the consumer warps: threads 0..63 own one output dim each
+    float out_acc = 0.f, out_l = 0.f, out_m = -INFINITY;
+    if (threadIdx.x < DH) {
+#pragma unroll
+        for (int w = 0; w < CONSUMER_WARPS; ++w) out_m = fmaxf(out_m, w_ml[w][0]);
+#pragma unroll
+        for (int w = 0; w < CONSUMER_WARPS; ++w) {
+            const float wt = (w_ml[w][0] == -INFINITY) ? 0.f : exp2f(w_ml[w][0] - out_m);
+            out_acc = fmaf(w_acc[w][threadIdx.x], wt, out_acc);
+            out_l = fmaf(w_ml[w][1], wt, out_l);
+        }
+    }
+    TO* orow = o + static_cast<int64_t>(b) * d_model + h * DH;
+    if (n_tsplit == 1) {
+        if (threadIdx.x < DH) orow[threadIdx.x] = from_f32<TO>(out_l > 0.f ? out_acc / out_l : 0.f);
+        return;
+    }
+    const int64_t slot = (static_cast<int64_t>(b) * H + h) * n_tsplit;
+    if (threadIdx.x < DH) {
+        ws_o[(slot + split) * DH + threadIdx.x] = out_acc;
+        if (threadIdx.x == 0) { ws_ml[(slot + split) * 2] = out_m; ws_ml[(slot + split) * 2 + 1] = out_l; }
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned ticket = atomicInc(&counters[b * H + h], static_cast<unsigned>(n_tsplit - 1));
+        is_last = (ticket == static_cast<unsigned>(n_tsplit - 1));
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    if (threadIdx.x < DH) {
+        float M = -INFINITY;
+        for (int s = 0; s < n_tsplit; ++s) M = fmaxf(M, __ldcg(&ws_ml[(slot + s) * 2]));
+        float a = 0.f, l = 0.f;
+        for (int s = 0; s < n_tsplit; ++s) {
+            const float ms = __ldcg(&ws_ml[(slot + s) * 2]);
+            const float wt = (ms == -INFINITY) ? 0.f : exp2f(ms - M);
+            a = fmaf(__ldcg(&ws_o[(slot + s) * DH + threadIdx.x]), wt, a);
+            l = fmaf(__ldcg(&ws_ml[(slot + s) * 2 + 1]), wt, l);
+        }
+        orow[threadIdx.x] = from_f32<TO>(l > 0.f ? a / l : 0.f);
+    }
+}
+
+}  // namespace
+
+extern "C" int64_t vb_attn_decode_ws_bytes(int B, int H, int n_tsplit) {
+    const int64_t bh = static_cast<int64_t>(B) * H;
+    // [counters: bh u32 (rounded to 256 B)] [ws_ml: bh*ns*2 f32] [ws_o: bh*ns*64 f32]
+    return ((bh * 4 + 255) / 256) * 256 + bh * n_tsplit * 2 * 4 + bh * n_tsplit * DH * 4;
+}
+
+extern "C" int vb_attn_decode_paged(const float* qkv_part, int n_part, int64_t part_stride, void* pool, int pool_dtype,
+                                    const int32_t* block_table, int max_pages, const int32_t* seq_lens, void* o,
+                                    int o_dtype, int B, int H, int Dh, int n_tsplit, void* ws, void* stream) {
+    VB_REQUIRE(qkv_part && pool && block_table && seq_lens && o, VB_ERR_BAD_ARG, "vb_attn_decode_paged: null pointer");
+    VB_REQUIRE(Dh == DH, VB_ERR_UNSUPPORTED, "vb_attn_decode_paged: head_dim must be 64 (got %d)", Dh);
+    VB_REQUIRE(B >= 1 && B <= 65535 && H >= 1 && H <= 65535 && n_part >= 1 && n_tsplit >= 1, VB_ERR_BAD_ARG,
+               "vb_attn_decode_paged: bad shape");
+    VB_REQUIRE(n_tsplit == 1 || ws != nullptr, VB_ERR_BAD_ARG, "vb_attn_decode_paged: workspace required for n_tsplit > 1");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int64_t bh = static_cast<int64_t>(B) * H;
+    unsigned* counters = static_cast<unsigned*>(ws);   // must be zero-initialised once; self-resetting afterwards
+    float* ws_ml = ws ? reinterpret_cast<float*>(static_cast<uint8_t*>(ws) + ((bh * 4 + 255) / 256) * 256) : nullptr;
+    float* ws_o = ws ? ws_ml + bh * n_tsplit * 2 : nullptr;
+    const float scale_log2e = 1.4426950408889634f / sqrtf(static_cast<float>(DH));
+    dim3 grid(n_tsplit, H, B);
+#define DEC(T, TO, SMEM)                                                                                              \
+    {                                                                                                                 \
+        auto kern = attn_decode_kernel<T, TO>;                                                                        \
+        static bool configured = false;                                                                               \
+        if (!configured) {                                                                                            \
+            VB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));                   \
+            configured = true;                                                                                        \
+        }                                                                                                             \
+        kern<<<grid, THREADS, SMEM, st>>>(qkv_part, n_part, part_stride, static_cast<T*>(pool), block_table,           \
+                                          max_pages, seq_lens, static_cast<TO*>(o), ws_o, ws_ml, counters, H,         \
+                                          n_tsplit, scale_log2e);                                                     \
+    }
+    if (pool_dtype == VB_BF16 && o_dtype == VB_BF16) DEC(__nv_bfloat16, __nv_bfloat16, NSTAGE * 2 * PAGE * DH * 2)
+    else if (pool_dtype == VB_BF16 && o_dtype == VB_F32) DEC(__nv_bfloat16, float, NSTAGE * 2 * PAGE * DH * 2)
+    else if (pool_dtype == VB_F32 && o_dtype == VB_F32) DEC(float, float, NSTAGE * 2 * PAGE * DH * 4)
+    else VB_REQUIRE(false, VB_ERR_UNSUPPORTED, "vb_attn_decode_paged: dtype combination pool=%d o=%d", pool_dtype, o_dtype);
+#undef DEC
+    VB_LAUNCH_CHECK();
+    return VB_OK;
+}

@@ -1,0 +1,310 @@
+// HBM-bound row kernels of the hot path: embedding-sum + PE (K1/K2), split-K reduce + bias + residual +
+// (Ada)LayerNorm (K3), split-K reduce + bias + erf-GELU (K8), KV scatter into the paged pool (K5), and the
+// device-side beam bookkeeping (K11).  All are coalesced, 16-byte vectorised where the shape allows.
+#include "common.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// K1/K2  embedding sum + sinusoidal PE
+// ------------------------------------------------------------------------------------------------
+__global__ void embed_sum_pe_kernel(const int32_t* __restrict__ ids, const float* __restrict__ tables,
+                                    const float* __restrict__ pe, float* __restrict__ out, int T, int Q, int V, int d,
+                                    int t_split, int nq_a, int nq_b, int pos_offset, const int32_t* __restrict__ pos_b,
+                                    int max_len, int64_t out_rows_per_batch, int64_t out_row_offset) {
+    const int t = blockIdx.x, b = blockIdx.y;
+    const int nq = (t < t_split) ? nq_a : nq_b;
+    int pos = (pos_b ? pos_b[b] : pos_offset) + t;
+    pos = min(max(pos, 0), max_len - 1);
+    const int32_t* id_row = ids + (static_cast<int64_t>(b) * T + t) * Q;
+    float* o = out + (static_cast<int64_t>(b) * out_rows_per_batch + out_row_offset + t) * d;
+    const float* pe_row = pe + static_cast<int64_t>(pos) * d;
+    for (int c = threadIdx.x * 4; c < d; c += blockDim.x * 4) {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int j = 0; j < nq; ++j) {  // left-to-right, same order as the reference's += loop
+            int id = id_row[j];
+            id = min(max(id, 0), V - 1);
+            const float4 e = *reinterpret_cast<const float4*>(tables + (static_cast<int64_t>(j) * V + id) * d + c);
+            acc.x += e.x; acc.y += e.y; acc.z += e.z; acc.w += e.w;
+        }
+        const float4 p = *reinterpret_cast<const float4*>(pe_row + c);
+        acc.x += p.x; acc.y += p.y; acc.z += p.z; acc.w += p.w;
+        *reinterpret_cast<float4*>(o + c) = acc;
+    }
+}
+
+extern "C" int vb_embed_sum_pe(const int32_t* ids, const float* tables, const float* pe, float* out, int B, int T, int Q,
+                               int V, int d, int t_split, int nq_a, int nq_b, int pos_offset, const int32_t* pos_b,
+                               int max_len, int64_t out_rows_per_batch, int64_t out_row_offset, void* stream) {
+    VB_REQUIRE(ids && tables && pe && out, VB_ERR_BAD_ARG, "vb_embed_sum_pe: null pointer");
+    VB_REQUIRE(B >= 0 && T >= 0 && Q >= 1 && d > 0 && d % 4 == 0, VB_ERR_BAD_ARG, "vb_embed_sum_pe: bad shape B=%d T=%d Q=%d d=%d", B, T, Q, d);
+    VB_REQUIRE(nq_a >= 0 && nq_a <= Q && nq_b >= 0 && nq_b <= Q, VB_ERR_BAD_ARG, "vb_embed_sum_pe: nq out of range");
+    if (B == 0 || T == 0) return VB_OK;
+    VB_REQUIRE(B <= 65535, VB_ERR_BAD_ARG, "vb_embed_sum_pe: B too large");
+    int threads = min(256, max(32, d / 4));
+    embed_sum_pe_kernel<<<dim3(T, B), threads, 0, static_cast<cudaStream_t>(stream)>>>(
+        ids, tables, pe, out, T, Q, V, d, t_split, nq_a, nq_b, pos_offset, pos_b, max_len, out_rows_per_batch, out_row_offset);
+    VB_LAUNCH_CHECK();
+    return VB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3  [split-K reduce + bias + residual] + LayerNorm;  one warp per row, row kept in registers
+// ------------------------------------------------------------------------------------------------
+template <typename TY, int NV>  // NV = d / 128 float4 chunks per lane
+__global__ void __launch_bounds__(256) residual_layernorm_kernel(float* __restrict__ x, const float* __restrict__ part,
+                                                                 int n_part, int64_t part_stride,
+                                                                 const float* __restrict__ bias,
+                                                                 const float* __restrict__ gamma,
+                                                                 const float* __restrict__ beta, TY* __restrict__ y,
+                                                                 int64_t R, int d, float eps) {
+    const int lane = threadIdx.x & 31;
+    const int64_t r = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (r >= R) return;
+    float* xr = x + r * d;
+    float4 v[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] = *reinterpret_cast<const float4*>(xr + (i * 32 + lane) * 4);
+    if (n_part > 0) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int c = (i * 32 + lane) * 4;
+            float4 acc = bias ? *reinterpret_cast<const float4*>(bias + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int s = 0; s < n_part; ++s) {
+                const float4 p = *reinterpret_cast<const float4*>(part + s * part_stride + r * d + c);
+                acc.x += p.x; acc.y += p.y; acc.z += p.z; acc.w += p.w;
+            }
+            v[i].x += acc.x; v[i].y += acc.y; v[i].z += acc.z; v[i].w += acc.w;
+            *reinterpret_cast<float4*>(xr + c) = v[i];
+        }
+    }
+    if (y == nullptr) return;
+    if (gamma == nullptr) {   // no norm: y = cast(x)  (the stack has no final LayerNorm, reference K-2)
+        TY* yc = y + r * d;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int c = (i * 32 + lane) * 4;
+            if constexpr (sizeof(TY) == 4) *reinterpret_cast<float4*>(yc + c) = v[i];
+            else *reinterpret_cast<uint2*>(yc + c) = make_uint2(pack_bf16x2(v[i].x, v[i].y), pack_bf16x2(v[i].z, v[i].w));
+        }
+        return;
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    const float mean = warp_sum(s) / d;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, e = v[i].w - mean;
+        q += (a * a + b * b) + (c * c + e * e);
+    }
+    const float rstd = rsqrtf(warp_sum(q) / d + eps);
+    TY* yr = y + r * d;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int c = (i * 32 + lane) * 4;
+        const float4 g = *reinterpret_cast<const float4*>(gamma + c);
+        const float4 bt = *reinterpret_cast<const float4*>(beta + c);
+        const float o0 = (v[i].x - mean) * rstd * g.x + bt.x, o1 = (v[i].y - mean) * rstd * g.y + bt.y;
+        const float o2 = (v[i].z - mean) * rstd * g.z + bt.z, o3 = (v[i].w - mean) * rstd * g.w + bt.w;
+        if constexpr (sizeof(TY) == 4) {
+            *reinterpret_cast<float4*>(yr + c) = make_float4(o0, o1, o2, o3);
+        } else {
+            uint2 pk = make_uint2(pack_bf16x2(o0, o1), pack_bf16x2(o2, o3));
+            *reinterpret_cast<uint2*>(yr + c) = pk;
+        }
+    }
+}
+
+// generic d (any multiple of 1): one warp per row, row re-read from global (L1/L2 resident)
+template <typename TY>
+__global__ void __launch_bounds__(256) residual_layernorm_generic_kernel(float* __restrict__ x, const float* __restrict__ part,
+                                                                         int n_part, int64_t part_stride,
+                                                                         const float* __restrict__ bias,
+                                                                         const float* __restrict__ gamma,
+                                                                         const float* __restrict__ beta, TY* __restrict__ y,
+                                                                         int64_t R, int d, float eps) {
+    const int lane = threadIdx.x & 31;
+    const int64_t r = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (r >= R) return;
+    float* xr = x + r * d;
+    if (n_part > 0) {
+        for (int c = lane; c < d; c += 32) {
+            float acc = bias ? bias[c] : 0.f;
+            for (int s = 0; s < n_part; ++s) acc += part[s * part_stride + r * d + c];
+            xr[c] += acc;
+        }
+        __syncwarp();
+    }
+    if (y == nullptr) return;
+    if (gamma == nullptr) {
+        for (int c = lane; c < d; c += 32) y[r * d + c] = from_f32<TY>(xr[c]);
+        return;
+    }
+    float s = 0.f;
+    for (int c = lane; c < d; c += 32) s += xr[c];
+    const float mean = warp_sum(s) / d;
+    float q = 0.f;
+    for (int c = lane; c < d; c += 32) {
+        const float a = xr[c] - mean;
+        q += a * a;
+    }
+    const float rstd = rsqrtf(warp_sum(q) / d + eps);
+    for (int c = lane; c < d; c += 32) y[r * d + c] = from_f32<TY>((xr[c] - mean) * rstd * gamma[c] + beta[c]);
+}
+
+template <typename TY>
+static int launch_rln(float* x, const float* part, int n_part, int64_t part_stride, const float* bias, const float* gamma,
+                      const float* beta, TY* y, int64_t R, int d, float eps, cudaStream_t st) {
+    const int warps = 8;
+    const dim3 grid(static_cast<unsigned>(vb_ceil_div(R, warps)));
+#define RLN(NV) residual_layernorm_kernel<TY, NV><<<grid, warps * 32, 0, st>>>(x, part, n_part, part_stride, bias, gamma, beta, y, R, d, eps)
+    switch (d) {
+        case 128: RLN(1); break;
+        case 256: RLN(2); break;
+        case 512: RLN(4); break;
+        case 1024: RLN(8); break;
+        default:
+            residual_layernorm_generic_kernel<TY><<<grid, warps * 32, 0, st>>>(x, part, n_part, part_stride, bias, gamma, beta, y, R, d, eps);
+    }
+#undef RLN
+    VB_LAUNCH_CHECK();
+    return VB_OK;
+}
+
+extern "C" int vb_residual_layernorm(float* x, const float* part, int n_part, int64_t part_stride, const float* bias,
+                                     const float* gamma, const float* beta, void* y, int y_dtype, int64_t R, int d,
+                                     float eps, void* stream) {
+    VB_REQUIRE(x != nullptr && R >= 0 && d > 0, VB_ERR_BAD_ARG, "vb_residual_layernorm: bad args");
+    VB_REQUIRE(n_part == 0 || part != nullptr, VB_ERR_BAD_ARG, "vb_residual_layernorm: n_part > 0 needs part");
+    VB_REQUIRE(y == nullptr || (gamma != nullptr) == (beta != nullptr), VB_ERR_BAD_ARG,
+               "vb_residual_layernorm: gamma and beta must both be given (LayerNorm) or both be null (plain cast)");
+    VB_REQUIRE(y_dtype == VB_F32 || y_dtype == VB_BF16, VB_ERR_BAD_ARG, "vb_residual_layernorm: bad y_dtype");
+    if (R == 0) return VB_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (y_dtype == VB_F32)
+        return launch_rln<float>(x, part, n_part, part_stride, bias, gamma, beta, static_cast<float*>(y), R, d, eps, st);
+    return launch_rln<__nv_bfloat16>(x, part, n_part, part_stride, bias, gamma, beta, static_cast<__nv_bfloat16*>(y), R, d, eps, st);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K8  split-K reduce + bias + erf-GELU
+// ------------------------------------------------------------------------------------------------
+template <typename TY>
+__global__ void reduce_bias_act_kernel(const float* __restrict__ part, int n_part, int64_t part_stride,
+                                       const float* __restrict__ bias, int gelu, TY* __restrict__ y, int64_t total4, int N) {
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total4;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int64_t e = i * 4;
+        const int n = static_cast<int>(e % N);
+        float4 acc = bias ? *reinterpret_cast<const float4*>(bias + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int s = 0; s < n_part; ++s) {
+            const float4 p = *reinterpret_cast<const float4*>(part + s * part_stride + e);
+            acc.x += p.x; acc.y += p.y; acc.z += p.z; acc.w += p.w;
+        }
+        if (gelu) { acc.x = gelu_erf(acc.x); acc.y = gelu_erf(acc.y); acc.z = gelu_erf(acc.z); acc.w = gelu_erf(acc.w); }
+        if constexpr (sizeof(TY) == 4) {
+            *reinterpret_cast<float4*>(y + e) = acc;
+        } else {
+            *reinterpret_cast<uint2*>(y + e) = make_uint2(pack_bf16x2(acc.x, acc.y), pack_bf16x2(acc.z, acc.w));
+        }
+    }
+}
+
+extern "C" int vb_reduce_bias_act(const float* part, int n_part, int64_t part_stride, const float* bias, int gelu, void* y,
+                                  int y_dtype, int64_t R, int N, void* stream) {
+    VB_REQUIRE(part && y && n_part >= 1 && N > 0 && N % 4 == 0 && R >= 0, VB_ERR_BAD_ARG, "vb_reduce_bias_act: bad args");
+    if (R == 0) return VB_OK;
+    const int64_t total4 = R * N / 4;
+    const int threads = 256;
+    const int64_t want_blocks = vb_ceil_div(total4, threads), cap_blocks = static_cast<int64_t>(vb_sm_count()) * 8;
+    const int blocks = static_cast<int>(want_blocks < cap_blocks ? want_blocks : cap_blocks);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (y_dtype == VB_F32)
+        reduce_bias_act_kernel<float><<<blocks, threads, 0, st>>>(part, n_part, part_stride, bias, gelu, static_cast<float*>(y), total4, N);
+    else if (y_dtype == VB_BF16)
+        reduce_bias_act_kernel<__nv_bfloat16><<<blocks, threads, 0, st>>>(part, n_part, part_stride, bias, gelu, static_cast<__nv_bfloat16*>(y), total4, N);
+    else
+        VB_REQUIRE(false, VB_ERR_BAD_ARG, "vb_reduce_bias_act: bad y_dtype");
+    VB_LAUNCH_CHECK();
+    return VB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K5  prefill K/V -> paged pool   pool: [page][2][H][64][Dh]
+// ------------------------------------------------------------------------------------------------
+template <typename TS, typename TD>
+__global__ void kv_scatter_kernel(const TS* __restrict__ qkv, TD* __restrict__ pool, const int32_t* __restrict__ block_table,
+                                  int max_pages, const int32_t* __restrict__ kv_lens, int S, int H, int Dh) {
+    const int s = blockIdx.x, b = blockIdx.y;
+    if (s >= kv_lens[b]) return;
+    const int page = block_table[b * max_pages + (s >> 6)];
+    const int slot = s & 63;
+    const int d = H * Dh;
+    const TS* src = qkv + (static_cast<int64_t>(b) * S + s) * 3 * d;
+    for (int c = threadIdx.x; c < 2 * d; c += blockDim.x) {
+        const int kv = c / d, hd = c % d, h = hd / Dh, e = hd % Dh;
+        const float val = to_f32<TS>(src[d + c]);
+        pool[(((static_cast<int64_t>(page) * 2 + kv) * H + h) * 64 + slot) * Dh + e] = from_f32<TD>(val);
+    }
+}
+
+extern "C" int vb_kv_scatter_paged(const void* qkv, int qkv_dtype, void* pool, int pool_dtype, const int32_t* block_table,
+                                   int max_pages, const int32_t* kv_lens, int B, int S, int H, int Dh, void* stream) {
+    VB_REQUIRE(qkv && pool && block_table && kv_lens, VB_ERR_BAD_ARG, "vb_kv_scatter_paged: null pointer");
+    VB_REQUIRE(B >= 0 && S >= 0 && H > 0 && Dh > 0 && B <= 65535, VB_ERR_BAD_ARG, "vb_kv_scatter_paged: bad shape");
+    if (B == 0 || S == 0) return VB_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    dim3 grid(S, B);
+    const int threads = 256;
+#define KVS(TS, TD) kv_scatter_kernel<TS, TD><<<grid, threads, 0, st>>>(static_cast<const TS*>(qkv), static_cast<TD*>(pool), block_table, max_pages, kv_lens, S, H, Dh)
+    if (qkv_dtype == VB_F32 && pool_dtype == VB_F32) KVS(float, float);
+    else if (qkv_dtype == VB_BF16 && pool_dtype == VB_BF16) KVS(__nv_bfloat16, __nv_bfloat16);
+    else if (qkv_dtype == VB_F32 && pool_dtype == VB_BF16) KVS(float, __nv_bfloat16);
+    else VB_REQUIRE(false, VB_ERR_UNSUPPORTED, "vb_kv_scatter_paged: dtype combination %d -> %d", qkv_dtype, pool_dtype);
+#undef KVS
+    VB_LAUNCH_CHECK();
+    return VB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K11  beam bookkeeping (valle_ar.py:167-171) -- one CTA, no host sync
+// ------------------------------------------------------------------------------------------------
+__global__ void ar_bookkeeping_kernel(const int32_t* __restrict__ sample, const float* __restrict__ logprob,
+                                      int32_t* __restrict__ last, float* __restrict__ sum_logprobs,
+                                      int32_t* __restrict__ codes_out, int64_t codes_stride, int32_t* __restrict__ seq_lens,
+                                      int32_t* __restrict__ audio_pos, int32_t* __restrict__ state, int B, int eos) {
+    __shared__ int not_eos;
+    if (threadIdx.x == 0) not_eos = 0;
+    __syncthreads();
+    const int step = state[0];
+    int local = 0;
+    for (int b = threadIdx.x; b < B; b += blockDim.x) {
+        const int prev = last[b];
+        const bool done = (prev == eos);
+        if (!done) sum_logprobs[b] += logprob[b];
+        const int tok = done ? eos : sample[b];
+        if (tok != eos) local = 1;
+        if (step < codes_stride) codes_out[b * codes_stride + step] = tok;
+        last[b] = tok;
+        seq_lens[b] += 1;
+        audio_pos[b] += 1;
+    }
+    if (local) atomicOr(&not_eos, 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (!not_eos && state[1] < 0) state[1] = step;
+        state[0] = step + 1;
+    }
+}
+
+extern "C" int vb_ar_bookkeeping(const int32_t* sample, const float* logprob, int32_t* last, float* sum_logprobs,
+                                 int32_t* codes_out, int64_t codes_stride, int32_t* seq_lens, int32_t* audio_pos,
+                                 int32_t* state, int B, int eos, void* stream) {
+    VB_REQUIRE(sample && logprob && last && sum_logprobs && codes_out && seq_lens && audio_pos && state, VB_ERR_BAD_ARG,
+               "vb_ar_bookkeeping: null pointer");
+    VB_REQUIRE(B > 0, VB_ERR_BAD_ARG, "vb_ar_bookkeeping: B must be > 0");
+    ar_bookkeeping_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(sample, logprob, last, sum_logprobs, codes_out,
+                                                                           codes_stride, seq_lens, audio_pos, state, B, eos);
+    VB_LAUNCH_CHECK();
+    return VB_OK;
+}

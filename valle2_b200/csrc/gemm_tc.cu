@@ -1,0 +1,329 @@
+// bf16 GEMM on the 5th-generation tensor cores: tcgen05.mma (cta_group::1, M=128) with fp32 accumulators in TMEM,
+// operands staged in shared memory by TMA (SWIZZLE_128B), warp-specialised persistent CTAs:
+//   warp 0   TMA producer (one elected lane)         smem ring: full[]/empty[] mbarriers
+//   warp 1   MMA issuer (one elected lane) + TMEM allocator
+//   warp 2-5 epilogue: tcgen05.ld -> bias / erf-GELU / residual -> global, double-buffered TMEM accumulators so the
+//            epilogue of tile i overlaps the main loop of tile i+1.
+// Two orientations share the kernel:
+//   normal : A = x [M][K], B = w [N][K]  ->  y[m][n]           (prefill / NAR / training shapes)
+//   swap-AB: A = w [N][K], B = x [M<=256][K] -> part[s][m][n]  (decode: weight rows fill the 128-row MMA-M, the batch
+//            sits on MMA-N, split-K slices are written as deterministic fp32 partials)
+// Replaces the nn.Linear call sites modules.py:146,171,220-221 and valle_ar.py:158 / valle_nar.py:157.
+#include "common.cuh"
+
+namespace {
+
+constexpr int BM = 128;      // UMMA M (rows of the A operand per tile)
+constexpr int BK = 64;       // k-block: 64 bf16 = one 128-byte swizzle atom row
+constexpr int UMMA_K = 16;
+constexpr int NUM_THREADS = 192;
+
+struct GemmParams {
+    int rows_a, rows_b, K;
+    int tiles_a, tiles_b;      // tiles along A rows / B rows
+    int kb_total, kb_per_split, n_split;
+    int epilogue;
+    const float* bias;
+    const float* residual;
+    int64_t ldr;
+    void* y;
+    int y_bf16;
+    int64_t ldy;
+    float* part;
+    int64_t part_stride;
+    int64_t part_ld;           // N (row pitch of a partial slice)
+};
+
+template <int BN, int STAGES, bool SWAP>
+__global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a,
+                                                                 const __grid_constant__ CUtensorMap tm_b, GemmParams p) {
+    constexpr int A_BYTES = BM * BK * 2;
+    constexpr int B_BYTES = BN * BK * 2;
+    constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+    constexpr uint32_t IDESC = umma_idesc_bf16(BM, BN, 0, 0);
+
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t full_bar[STAGES];
+    __shared__ __align__(8) uint64_t empty_bar[STAGES];
+    __shared__ __align__(8) uint64_t tfull_bar[2];
+    __shared__ __align__(8) uint64_t tempty_bar[2];
+    __shared__ uint32_t tmem_base_slot;
+
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tm_a);
+        tma_prefetch_desc(&tm_b);
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(smem_u32(&full_bar[s]), 1);
+            mbar_init(smem_u32(&empty_bar[s]), 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(smem_u32(&tfull_bar[a]), 1);
+            mbar_init(smem_u32(&tempty_bar[a]), 4);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc<TMEM_COLS>(smem_u32(&tmem_base_slot));
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_slot;
+
+    const int total_tiles = p.tiles_a * p.tiles_b * p.n_split;
+
+    if (warp == 0) {
+        if (elect_one()) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+                int ta, tb, split;
+                if (SWAP) { ta = t % p.tiles_a; split = t / p.tiles_a; tb = 0; }
+                else      { tb = t % p.tiles_b; ta = t / p.tiles_b; split = 0; }
+                const int kb0 = split * p.kb_per_split;
+                const int kb1 = min(kb0 + p.kb_per_split, p.kb_total);
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+                    const uint32_t fb = smem_u32(&full_bar[stage]);
+                    mbar_expect_tx(fb, STAGE_BYTES);
+                    const uint32_t sa = smem_base + stage * STAGE_BYTES;
+                    tma_load_2d(sa, &tm_a, fb, kb * BK, ta * BM);
+                    tma_load_2d(sa + A_BYTES, &tm_b, fb, kb * BK, tb * BN);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (elect_one()) {
+            int stage = 0;
+            uint32_t phase = 0;
+            int local = 0;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++local) {
+                const int split = SWAP ? t / p.tiles_a : 0;
+                const int kb0 = split * p.kb_per_split;
+                const int kb1 = min(kb0 + p.kb_per_split, p.kb_total);
+                const int acc = local & 1;
+                const uint32_t acc_phase = (local >> 1) & 1;
+                mbar_wait(smem_u32(&tempty_bar[acc]), acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BN;
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    mbar_wait(smem_u32(&full_bar[stage]), phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_base + stage * STAGE_BYTES;
+#pragma unroll
+                    for (int kk = 0; kk < BK / UMMA_K; ++kk) {
+                        const uint64_t da = umma_desc_sw128(sa + kk * UMMA_K * 2, 16, 1024);
+                        const uint64_t db = umma_desc_sw128(sa + A_BYTES + kk * UMMA_K * 2, 16, 1024);
+                        umma_f16(d_tmem, da, db, IDESC, (kb > kb0 || kk > 0) ? 1u : 0u);
+                    }
+                    umma_commit(smem_u32(&empty_bar[stage]));
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(smem_u32(&tfull_bar[acc]));
+            }
+        }
+    } else {
+        const int q = warp & 3;  // TMEM lane quadrant this warp may access
+        int local = 0;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++local) {
+            int ta, tb, split;
+            if (SWAP) { ta = t % p.tiles_a; split = t / p.tiles_a; tb = 0; }
+            else      { tb = t % p.tiles_b; ta = t / p.tiles_b; split = 0; }
+            const int kb0 = split * p.kb_per_split;
+            const bool empty_slice = kb0 >= p.kb_total;   // a split past the end of K: contributes zeros
+            const int acc = local & 1;
+            const uint32_t acc_phase = (local >> 1) & 1;
+            mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase);
+            tc_fence_after();
+            const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
+            const int row = ta * BM + q * 32 + lane;  // row of the A operand owned by this thread
+            if (SWAP) {
+                // D[n][m]: this thread owns weight row n; columns are batch rows m.
+                float* dst = p.part + split * p.part_stride + row;
+                constexpr int CH = (BN >= 32) ? 32 : 16;
+#pragma unroll 1
+                for (int c0 = 0; c0 < BN; c0 += CH) {
+                    if (c0 >= p.rows_b) break;
+                    uint32_t v[CH];
+                    if constexpr (CH == 32) tmem_ld_32x32(t_addr + c0, reinterpret_cast<uint32_t(&)[32]>(v));
+                    else tmem_ld_32x16(t_addr + c0, reinterpret_cast<uint32_t(&)[16]>(v));
+                    tmem_ld_wait();
+                    if (row < p.rows_a) {
+#pragma unroll
+                        for (int j = 0; j < CH; ++j) {
+                            const int m = c0 + j;
+                            if (m < p.rows_b) dst[m * p.part_ld] = empty_slice ? 0.f : __uint_as_float(v[j]);
+                        }
+                    }
+                }
+            } else {
+                const int n_base = tb * BN;
+                const bool row_ok = row < p.rows_a;
+#pragma unroll 1
+                for (int c0 = 0; c0 < BN; c0 += 32) {
+                    const int n0 = n_base + c0;
+                    if (n0 >= p.rows_b) break;
+                    uint32_t v[32];
+                    tmem_ld_32x32(t_addr + c0, v);
+                    tmem_ld_wait();
+                    if (!row_ok) continue;
+                    float f[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+                    const bool full = (n0 + 32 <= p.rows_b);
+                    if (p.epilogue != VB_EPI_NONE) {
+                        if (full) {
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4) {
+                                const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
+                                f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
+                            }
+                        } else {
+                            for (int j = 0; j < 32; ++j) if (n0 + j < p.rows_b) f[j] += p.bias[n0 + j];
+                        }
+                    }
+                    if (p.epilogue == VB_EPI_BIAS_GELU) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
+                    }
+                    if (p.epilogue == VB_EPI_BIAS_RESIDUAL) {
+                        const float* rr = p.residual + static_cast<int64_t>(row) * p.ldr + n0;
+                        if (full && (p.ldr & 3) == 0) {
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4) {
+                                const float4 r4 = *reinterpret_cast<const float4*>(rr + j);
+                                f[j] += r4.x; f[j + 1] += r4.y; f[j + 2] += r4.z; f[j + 3] += r4.w;
+                            }
+                        } else {
+                            for (int j = 0; j < 32; ++j) if (n0 + j < p.rows_b) f[j] += rr[j];
+                        }
+                    }
+                    if (p.y_bf16) {
+                        __nv_bfloat16* yr = static_cast<__nv_bfloat16*>(p.y) + static_cast<int64_t>(row) * p.ldy + n0;
+                        if (full && (p.ldy & 7) == 0) {
+#pragma unroll
+                            for (int j = 0; j < 32; j += 8) {
+                                uint4 pk;
+                                pk.x = pack_bf16x2(f[j], f[j + 1]); pk.y = pack_bf16x2(f[j + 2], f[j + 3]);
+                                pk.z = pack_bf16x2(f[j + 4], f[j + 5]); pk.w = pack_bf16x2(f[j + 6], f[j + 7]);
+                                *reinterpret_cast<uint4*>(yr + j) = pk;
+                            }
+                        } else {
+                            for (int j = 0; j < 32; ++j) if (n0 + j < p.rows_b) yr[j] = __float2bfloat16_rn(f[j]);
+                        }
+                    } else {
+                        float* yr = static_cast<float*>(p.y) + static_cast<int64_t>(row) * p.ldy + n0;
+                        if (full && (p.ldy & 3) == 0) {
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4)
+                                *reinterpret_cast<float4*>(yr + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+                        } else {
+                            for (int j = 0; j < 32; ++j) if (n0 + j < p.rows_b) yr[j] = f[j];
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[acc]));
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<TMEM_COLS>(tmem_base);
+    }
+}
+
+template <int BN, int STAGES, bool SWAP>
+int launch_gemm_tc(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
+    constexpr int SMEM = STAGES * (BM * BK * 2 + BN * BK * 2) + 1024;
+    static bool configured = false;
+    auto kern = gemm_tc_kernel<BN, STAGES, SWAP>;
+    if (!configured) {
+        VB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+        configured = true;
+    }
+    const int total = p.tiles_a * p.tiles_b * p.n_split;
+    const int grid = min(total, vb_sm_count());
+    kern<<<grid, NUM_THREADS, SMEM, st>>>(ta, tb, p);
+    VB_LAUNCH_CHECK();
+    return VB_OK;
+}
+
+}  // namespace
+
+// y[M,N] = epi(x . w^T), bf16 operands
+int vb_linear_tc(const void* x, int64_t ldx, const void* w, int64_t ldw, const float* bias, const float* residual,
+                 int64_t ldr, void* y, int y_dtype, int64_t ldy, int64_t M, int64_t N, int64_t K, int epilogue,
+                 cudaStream_t st) {
+    VB_REQUIRE(K % 8 == 0, VB_ERR_UNSUPPORTED, "vb_linear(bf16): K must be a multiple of 8 (got %lld)", (long long)K);
+    CUtensorMap ta, tb;
+    int rc;
+    GemmParams p{};
+    p.rows_a = (int)M; p.rows_b = (int)N; p.K = (int)K;
+    p.tiles_a = (int)vb_ceil_div(M, BM);
+    p.kb_total = (int)vb_ceil_div(K, BK); p.kb_per_split = p.kb_total; p.n_split = 1;
+    p.epilogue = epilogue; p.bias = bias; p.residual = residual; p.ldr = ldr;
+    p.y = y; p.y_bf16 = (y_dtype == VB_BF16); p.ldy = ldy;
+    if ((rc = vb_make_tmap_bf16_2d(&ta, x, M, K, ldx, BM, BK)) != VB_OK) return rc;
+    if (N > 128) {
+        p.tiles_b = (int)vb_ceil_div(N, 256);
+        if ((rc = vb_make_tmap_bf16_2d(&tb, w, N, K, ldw, 256, BK)) != VB_OK) return rc;
+        return launch_gemm_tc<256, 4, false>(ta, tb, p, st);
+    }
+    if (N > 64) {
+        p.tiles_b = 1;
+        if ((rc = vb_make_tmap_bf16_2d(&tb, w, N, K, ldw, 128, BK)) != VB_OK) return rc;
+        return launch_gemm_tc<128, 6, false>(ta, tb, p, st);
+    }
+    p.tiles_b = 1;
+    if ((rc = vb_make_tmap_bf16_2d(&tb, w, N, K, ldw, 64, BK)) != VB_OK) return rc;
+    return launch_gemm_tc<64, 8, false>(ta, tb, p, st);
+}
+
+// split K so that (N/128 slabs) x splits fills the SMs, with at least 2 k-blocks (128 columns of K) per slice
+extern "C" int vb_linear_decode_splits(int64_t N, int64_t K, int max_split) {
+    const int tiles_a = (int)vb_ceil_div(N, BM), kb_total = (int)vb_ceil_div(K, BK);
+    const int want = (int)vb_ceil_div(vb_sm_count(), tiles_a);
+    int n_split = max(1, min(min(want, max_split), max(1, kb_total / 2)));
+    const int kb_per_split = (int)vb_ceil_div(kb_total, n_split);
+    return (int)vb_ceil_div(kb_total, kb_per_split);
+}
+
+extern "C" int vb_linear_decode(const void* x, int64_t ldx, const void* w, int64_t ldw, float* part, int64_t part_stride,
+                                int64_t M, int64_t N, int64_t K, int max_split, int* n_split_out, void* stream) {
+    VB_REQUIRE(x && w && part, VB_ERR_BAD_ARG, "vb_linear_decode: null pointer");
+    VB_REQUIRE(M >= 1 && M <= 256, VB_ERR_UNSUPPORTED, "vb_linear_decode: M must be in [1,256] (got %lld)", (long long)M);
+    VB_REQUIRE(K % 8 == 0 && N >= 1, VB_ERR_UNSUPPORTED, "vb_linear_decode: K %% 8 != 0 or N < 1");
+    VB_REQUIRE(max_split >= 1, VB_ERR_BAD_ARG, "vb_linear_decode: max_split must be >= 1");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    GemmParams p{};
+    p.rows_a = (int)N; p.rows_b = (int)M; p.K = (int)K;
+    p.tiles_a = (int)vb_ceil_div(N, BM); p.tiles_b = 1;
+    p.kb_total = (int)vb_ceil_div(K, BK);
+    const int n_split = vb_linear_decode_splits(N, K, max_split);
+    p.kb_per_split = (int)vb_ceil_div(p.kb_total, n_split);
+    p.n_split = n_split;
+    p.part = part; p.part_stride = part_stride; p.part_ld = N;
+    VB_REQUIRE(n_split == 1 || part_stride >= M * N, VB_ERR_BAD_ARG, "vb_linear_decode: part_stride too small");
+    if (n_split_out) *n_split_out = n_split;
+    CUtensorMap ta, tb;
+    int rc;
+    if ((rc = vb_make_tmap_bf16_2d(&ta, w, N, K, ldw, BM, BK)) != VB_OK) return rc;
+#define DECODE_CASE(BNV, ST)                                                             \
+    {                                                                                    \
+        if ((rc = vb_make_tmap_bf16_2d(&tb, x, M, K, ldx, BNV, BK)) != VB_OK) return rc; \
+        return launch_gemm_tc<BNV, ST, true>(ta, tb, p, st);                             \
+    }
+    if (M <= 16) DECODE_CASE(16, 8)
+    if (M <= 32) DECODE_CASE(32, 8)
+    if (M <= 64) DECODE_CASE(64, 8)
+    if (M <= 128) DECODE_CASE(128, 6)
+    DECODE_CASE(256, 4)
+#undef DECODE_CASE
+}

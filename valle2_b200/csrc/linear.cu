@@ -1,0 +1,28 @@
+// vb_linear: dtype dispatch between the fp32 SIMT GEMM (validation mode) and the tcgen05 bf16 GEMM.
+#include "common.cuh"
+
+int vb_linear_simt(const float* x, int64_t ldx, const float* w, int64_t ldw, const float* bias, const float* residual,
+                   int64_t ldr, void* y, int y_dtype, int64_t ldy, int64_t M, int64_t N, int64_t K, int epilogue,
+                   cudaStream_t st);
+int vb_linear_tc(const void* x, int64_t ldx, const void* w, int64_t ldw, const float* bias, const float* residual,
+                 int64_t ldr, void* y, int y_dtype, int64_t ldy, int64_t M, int64_t N, int64_t K, int epilogue,
+                 cudaStream_t st);
+
+extern "C" int vb_linear(const void* x, int x_dtype, int64_t ldx, const void* w, int w_dtype, int64_t ldw, const float* bias,
+                         const float* residual, int64_t ldr, void* y, int y_dtype, int64_t ldy, int64_t M, int64_t N,
+                         int64_t K, int epilogue, void* stream) {
+    VB_REQUIRE(x && w && y, VB_ERR_BAD_ARG, "vb_linear: null pointer");
+    VB_REQUIRE(M >= 0 && N >= 1 && K >= 1, VB_ERR_BAD_ARG, "vb_linear: bad shape M=%lld N=%lld K=%lld", (long long)M, (long long)N, (long long)K);
+    VB_REQUIRE(epilogue >= VB_EPI_NONE && epilogue <= VB_EPI_BIAS_RESIDUAL, VB_ERR_BAD_ARG, "vb_linear: bad epilogue %d", epilogue);
+    VB_REQUIRE(epilogue == VB_EPI_NONE || bias != nullptr, VB_ERR_BAD_ARG, "vb_linear: epilogue %d needs a bias", epilogue);
+    VB_REQUIRE(epilogue != VB_EPI_BIAS_RESIDUAL || residual != nullptr, VB_ERR_BAD_ARG, "vb_linear: residual is null");
+    VB_REQUIRE(y_dtype == VB_F32 || y_dtype == VB_BF16, VB_ERR_BAD_ARG, "vb_linear: bad y_dtype");
+    if (M == 0) return VB_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (x_dtype == VB_F32 && w_dtype == VB_F32)
+        return vb_linear_simt(static_cast<const float*>(x), ldx, static_cast<const float*>(w), ldw, bias, residual, ldr, y,
+                              y_dtype, ldy, M, N, K, epilogue, st);
+    if (x_dtype == VB_BF16 && w_dtype == VB_BF16)
+        return vb_linear_tc(x, ldx, w, ldw, bias, residual, ldr, y, y_dtype, ldy, M, N, K, epilogue, st);
+    VB_REQUIRE(false, VB_ERR_UNSUPPORTED, "vb_linear: dtype combination x=%d w=%d", x_dtype, w_dtype);
+}

@@ -1,0 +1,363 @@
+"""Execution engines for the hot path: packed weights, KV page pool, workspaces, CUDA-graph decode.
+
+``StackWeights``   per-layer weights of a ``Transformer`` stack in the compute dtype; AdaLN scale/shift
+                   pre-folded per (layer, norm, stage):  (w*gamma) * xhat + (w*beta + b)   (modules.py:93-99).
+``StackRunner``    large-M forward over packed rows (AR prefill, NAR stages, teacher-forced logits).
+``ARDecoder``      batched KV-cached decode (valle_ar.py:92-180): prefill -> CUDA-graph decode steps with
+                   device-side sampling + EOS bookkeeping (no per-step host sync).
+``NARDecoder``     stages 2..Q with full attention and summed codebook embeddings (valle_nar.py:107-165, repaired
+                   per SURVEY Appendix A).
+
+Precision: 'bf16' = bf16 weights / activations / KV, fp32 accumulation and fp32 residual stream (tcgen05 GEMMs);
+'fp32' = validation mode, everything fp32 on the SIMT kernels.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+
+from . import ops
+from .ops import MASK_NONE, MASK_PREFIX_LM, PAGE
+
+
+def _cdtype(precision: str) -> torch.dtype:
+    return torch.bfloat16 if precision == 'bf16' else torch.float32
+
+
+class StackWeights:
+    def __init__(self, transformer, norm: str, precision: str, stage_embs: list[torch.Tensor] | None = None):
+        self.precision = precision
+        cd = _cdtype(precision)
+        self.layers = []
+        for layer in transformer.layers:
+            a, f = layer.self_attn, layer.ffn
+            L = {
+                'wqkv': a.qkv.weight.detach().to(cd).contiguous(),
+                'wo': a.out.weight.detach().to(cd).contiguous(),
+                'bo': a.out.bias.detach().float().contiguous(),
+                'w1': f.linear_1.weight.detach().to(cd).contiguous(),
+                'b1': f.linear_1.bias.detach().float().contiguous(),
+                'w2': f.linear_2.weight.detach().to(cd).contiguous(),
+                'b2': f.linear_2.bias.detach().float().contiguous(),
+            }
+            for name in ('norm1', 'norm2'):
+                nm = getattr(layer, name)
+                if norm == 'LayerNorm':
+                    L[name] = (nm.weight.detach().float().reshape(1, -1).contiguous(),
+                               nm.bias.detach().float().reshape(1, -1).contiguous(), nm.eps)
+                else:
+                    assert stage_embs is not None, 'AdaptiveLayerNorm needs stage embeddings'
+                    d = nm.d_model
+                    e = torch.cat([s.detach().float().reshape(1, d) for s in stage_embs], 0).contiguous()
+                    wb = ops.linear(e, nm.project_layer.weight.detach().float().contiguous(),
+                                    nm.project_layer.bias.detach().float().contiguous())      # (n_stage, 2d) fp32 SIMT
+                    w, b = wb[:, :d], wb[:, d:]
+                    g0, b0 = nm.norm.weight.detach().float(), nm.norm.bias.detach().float()
+                    # the fold is two elementwise products at weight-load time (exact up to 1 ulp)
+                    L[name] = ((w * g0).contiguous(), (w * b0 + b).contiguous(), nm.eps)
+            self.layers.append(L)
+        l0 = self.layers[0]
+        self.d = l0['wo'].shape[0]
+        self.F = l0['w1'].shape[0]
+
+
+class StackRunner:
+    """Large-M forward: x (R,d) fp32 residual stream updated in place."""
+
+    def __init__(self, weights: StackWeights, n_heads: int):
+        self.w = weights
+        self.H = n_heads
+        self.cd = _cdtype(weights.precision)
+        self._ws = {}
+
+    def _buffers(self, R: int, device):
+        key = (R, device)
+        if key not in self._ws:
+            d, F = self.w.d, self.w.F
+            self._ws = {key: {                       # keep only the latest size resident
+                'h': torch.empty(R, d, device=device, dtype=self.cd),
+                'qkv': torch.empty(R, 3 * d, device=device, dtype=self.cd),
+                'o': torch.empty(R, d, device=device, dtype=self.cd),
+                'f': torch.empty(R, F, device=device, dtype=self.cd),
+            }}
+        return self._ws[key]
+
+    def forward(self, x: torch.Tensor, B: int, S: int, *, mask_mode: int, x_lens=None, kv_lens=None, stage: int = 0,
+                kv_pools: torch.Tensor | None = None, block_table: torch.Tensor | None = None,
+                use_tc_attention: bool = False) -> torch.Tensor:
+        R, d = x.shape
+        assert R == B * S
+        buf = self._buffers(R, x.device)
+        h, qkv, o, f = buf['h'], buf['qkv'], buf['o'], buf['f']
+        H, Dh = self.H, d // self.H
+        for li, L in enumerate(self.w.layers):
+            g, b, eps = L['norm1']
+            ops.residual_layernorm(x, g[min(stage, g.shape[0] - 1)], b[min(stage, b.shape[0] - 1)], h, eps=eps)
+            ops.linear(h, L['wqkv'], out=qkv)
+            if kv_pools is not None:
+                ops.kv_scatter_paged(qkv, kv_pools[li], block_table, kv_lens, B, S, H, Dh)
+            ops.attention_packed(qkv, o, B, S, H, mask_mode=mask_mode, x_lens=x_lens, kv_lens=kv_lens,
+                                 use_tc=use_tc_attention)
+            ops.linear(o, L['wo'], L['bo'], residual=x, out=x)
+            g, b, eps = L['norm2']
+            ops.residual_layernorm(x, g[min(stage, g.shape[0] - 1)], b[min(stage, b.shape[0] - 1)], h, eps=eps)
+            ops.linear(h, L['w1'], L['b1'], gelu=True, out=f)
+            ops.linear(f, L['w2'], L['b2'], residual=x, out=x)
+        return x
+
+
+def _i32(t: torch.Tensor, device) -> torch.Tensor:
+    return t.to(device=device, dtype=torch.int32).contiguous()
+
+
+class ARDecoder:
+    def __init__(self, model, precision: str):
+        cfg = model.config
+        assert cfg.norm == 'LayerNorm', 'ValleAR runs only with norm=LayerNorm (reference defect A-10)'
+        self.cfg = cfg
+        self.precision = precision
+        self.cd = _cdtype(precision)
+        self.device = model.device
+        self.H = cfg.n_heads
+        self.d = cfg.d_model
+        self.Dh = self.d // self.H
+        self.V = cfg.num_audio_tokens + 1
+        self.weights = StackWeights(model.transformer, cfg.norm, precision)
+        self.runner = StackRunner(self.weights, self.H)
+        self.tok_table = model.tokens_emb.weight.detach().float().unsqueeze(0).contiguous()
+        self.aud_table = model.audio_emb.weight.detach().float().unsqueeze(0).contiguous()
+        self.pe_t = model.tokens_position_emb.pe.detach().float().reshape(-1, self.d).contiguous()
+        self.pe_a = model.audio_position_emb.pe.detach().float().reshape(-1, self.d).contiguous()
+        self.wproj = model.proj.weight.detach().to(self.cd).contiguous()
+        self._state = None
+        self._graph = None
+
+    # ------------------------------------------------------------------------------------------
+    def _alloc(self, B: int, max_ctx: int, max_new: int):
+        dev, d, F, H, V, L = self.device, self.d, self.weights.F, self.H, self.V, len(self.weights.layers)
+        max_pages = (max_ctx + PAGE - 1) // PAGE + 1
+        st = {'B': B, 'max_pages': max_pages, 'max_new': max_new}
+        st['pools'] = torch.zeros(L, B * max_pages, 2, H, PAGE, self.Dh, device=dev, dtype=self.cd)
+        st['block_table'] = torch.arange(B * max_pages, device=dev, dtype=torch.int32).view(B, max_pages).contiguous()
+        st['seq_lens'] = torch.zeros(B, device=dev, dtype=torch.int32)
+        st['audio_pos'] = torch.zeros(B, device=dev, dtype=torch.int32)
+        st['last'] = torch.zeros(B, device=dev, dtype=torch.int32)
+        st['sum_logprobs'] = torch.zeros(B, device=dev, dtype=torch.float32)
+        st['codes_out'] = torch.zeros(B, max_new, device=dev, dtype=torch.int32)
+        st['state'] = torch.tensor([0, -1], device=dev, dtype=torch.int32)
+        st['sample'] = torch.zeros(B, device=dev, dtype=torch.int32)
+        st['logprob'] = torch.zeros(B, device=dev, dtype=torch.float32)
+        st['x'] = torch.zeros(B, d, device=dev, dtype=torch.float32)
+        if self.precision == 'bf16':
+            ms = 32
+            ns = {k: ops.linear_decode_splits(n, kk, ms) for k, (n, kk) in
+                  {'qkv': (3 * d, d), 'o': (d, d), 'f1': (F, d), 'f2': (d, F), 'lg': (V, d)}.items()}
+            st['ns'] = ns
+            st['h'] = torch.zeros(B, d, device=dev, dtype=self.cd)
+            st['o'] = torch.zeros(B, d, device=dev, dtype=self.cd)
+            st['f'] = torch.zeros(B, F, device=dev, dtype=self.cd)
+            st['p_qkv'] = torch.zeros(ns['qkv'], B, 3 * d, device=dev, dtype=torch.float32)
+            st['p_o'] = torch.zeros(ns['o'], B, d, device=dev, dtype=torch.float32)
+            st['p_f1'] = torch.zeros(ns['f1'], B, F, device=dev, dtype=torch.float32)
+            st['p_f2'] = torch.zeros(ns['f2'], B, d, device=dev, dtype=torch.float32)
+            st['p_lg'] = torch.zeros(ns['lg'], B, V, device=dev, dtype=torch.float32)
+        else:
+            st['h'] = torch.zeros(B, d, device=dev, dtype=torch.float32)
+            st['qkv'] = torch.zeros(B, 3 * d, device=dev, dtype=torch.float32)
+            st['o'] = torch.zeros(B, d, device=dev, dtype=torch.float32)
+            st['f'] = torch.zeros(B, F, device=dev, dtype=torch.float32)
+            st['lg'] = torch.zeros(B, V, device=dev, dtype=torch.float32)
+        # flash-decoding split: enough CTAs to fill the GPU, never more splits than pages
+        sm = ops.device_info()['sm_count']
+        n_ts = max(1, min(16, max_pages, math.ceil(6 * sm / (B * H))))
+        st['n_tsplit'] = n_ts
+        st['attn_ws'] = torch.zeros(ops.attn_decode_ws_bytes(B, H, n_ts) // 4 + 64, device=dev, dtype=torch.int32)
+        self._state = st
+        self._graph = None
+        return st
+
+    # ------------------------------------------------------------------------------------------
+    def _logits_sample_book(self, x_rows: torch.Tensor, samp: dict, uniforms: torch.Tensor | None, eos: int):
+        """x_rows (B,d) fp32 final hidden rows -> logits -> sample -> bookkeeping."""
+        st = self._state
+        B, V = st['B'], self.V
+        if self.precision == 'bf16':
+            ops.residual_layernorm(x_rows, None, None, st['h'])                  # cast to bf16 (no final norm, K-2)
+            ops.linear_decode(st['h'], self.wproj, st['p_lg'], B * V, 32)
+            lg, n_part, pstride = st['p_lg'], st['ns']['lg'], B * V
+        else:
+            ops.linear(x_rows, self.wproj, out=st['lg'])
+            lg, n_part, pstride = st['lg'], 1, 0
+        ops.sample(lg, n_part, pstride, V, B, V, temperature=samp['temperature'], top_k=samp['top_k'],
+                   top_p=samp['top_p'], out_tok=st['sample'], out_logprob=st['logprob'], uniforms=uniforms,
+                   seed=samp['seed'], step_ptr=st['state'])
+        ops.ar_bookkeeping(st['sample'], st['logprob'], st['last'], st['sum_logprobs'], st['codes_out'],
+                           st['seq_lens'], st['audio_pos'], st['state'], eos)
+
+    def _decode_step(self, samp: dict, uniforms: torch.Tensor | None, eos: int):
+        st = self._state
+        B, d, H, Dh = st['B'], self.d, self.H, self.Dh
+        x = st['x']
+        ops.embed_sum_pe(st['last'].view(B, 1, 1), self.aud_table, self.pe_a, x, pos_b=st['audio_pos'])
+        layers = self.weights.layers
+        if self.precision == 'bf16':
+            ns = st['ns']
+            for li, L in enumerate(layers):
+                g, b, eps = L['norm1']
+                if li == 0:
+                    ops.residual_layernorm(x, g[0], b[0], st['h'], eps=eps)
+                else:
+                    ops.residual_layernorm(x, g[0], b[0], st['h'], part=st['p_f2'], n_part=ns['f2'],
+                                           part_stride=B * d, bias=layers[li - 1]['b2'], eps=eps)
+                ops.linear_decode(st['h'], L['wqkv'], st['p_qkv'], B * 3 * d, 32)
+                ops.attn_decode_paged(st['p_qkv'], ns['qkv'], B * 3 * d, st['pools'][li], st['block_table'],
+                                      st['seq_lens'], st['o'], B, H, Dh, st['n_tsplit'], st['attn_ws'])
+                ops.linear_decode(st['o'], L['wo'], st['p_o'], B * d, 32)
+                g, b, eps = L['norm2']
+                ops.residual_layernorm(x, g[0], b[0], st['h'], part=st['p_o'], n_part=ns['o'], part_stride=B * d,
+                                       bias=L['bo'], eps=eps)
+                ops.linear_decode(st['h'], L['w1'], st['p_f1'], B * self.weights.F, 32)
+                ops.reduce_bias_act(st['p_f1'], ns['f1'], B * self.weights.F, L['b1'], True, st['f'])
+                ops.linear_decode(st['f'], L['w2'], st['p_f2'], B * d, 32)
+            ops.residual_layernorm(x, None, None, None, part=st['p_f2'], n_part=ns['f2'], part_stride=B * d,
+                                   bias=layers[-1]['b2'])
+        else:
+            for li, L in enumerate(layers):
+                g, b, eps = L['norm1']
+                ops.residual_layernorm(x, g[0], b[0], st['h'], eps=eps)
+                ops.linear(st['h'], L['wqkv'], out=st['qkv'])
+                ops.attn_decode_paged(st['qkv'], 1, 0, st['pools'][li], st['block_table'], st['seq_lens'], st['o'],
+                                      B, H, Dh, st['n_tsplit'], st['attn_ws'])
+                ops.linear(st['o'], L['wo'], L['bo'], residual=x, out=x)
+                g, b, eps = L['norm2']
+                ops.residual_layernorm(x, g[0], b[0], st['h'], eps=eps)
+                ops.linear(st['h'], L['w1'], L['b1'], gelu=True, out=st['f'])
+                ops.linear(st['f'], L['w2'], L['b2'], residual=x, out=x)
+        self._logits_sample_book(x, samp, uniforms, eos)
+
+    # ------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def prefill(self, tokens: torch.Tensor, codes: torch.Tensor, *, x_lens=None, code_lens=None, max_new: int):
+        """tokens (B,Tx), codes (B,P) incl. BOS.  Lays every sequence out as [text | audio] with the audio part
+        starting at column Tx (the reference's layout, valle_ar.py:147); ragged batches pass x_lens / code_lens
+        (then text padding between x_lens[b] and Tx is attended exactly like the reference does, K-4)."""
+        dev = self.device
+        B, Tx = tokens.shape
+        P = codes.shape[1]
+        S = Tx + P
+        st = self._alloc(B, S + max_new, max_new)
+        tok_i = _i32(tokens, dev).view(B, Tx, 1)
+        cod_i = _i32(codes, dev).view(B, P, 1)
+        x = torch.empty(B * S, self.d, device=dev, dtype=torch.float32)
+        ops.embed_sum_pe(tok_i, self.tok_table, self.pe_t, x, out_rows_per_batch=S, out_row_offset=0)
+        ops.embed_sum_pe(cod_i, self.aud_table, self.pe_a, x, out_rows_per_batch=S, out_row_offset=Tx)
+        xl = torch.full((B,), Tx, device=dev, dtype=torch.int32)
+        cl = torch.full((B,), P, device=dev, dtype=torch.int32) if code_lens is None else _i32(code_lens, dev)
+        kv_lens = (xl + cl).contiguous()
+        self.runner.forward(x, B, S, mask_mode=MASK_PREFIX_LM, x_lens=xl, kv_lens=kv_lens, kv_pools=st['pools'],
+                            block_table=st['block_table'])
+        st['seq_lens'].copy_(kv_lens - 1)
+        st['audio_pos'].copy_(cl - 1)
+        rows = x.view(B, S, self.d)
+        idx = (kv_lens - 1).long()
+        st['x_last'] = rows[torch.arange(B, device=dev), idx].contiguous()
+        st['last'].copy_(cod_i.view(B, P)[torch.arange(B, device=dev), (cl - 1).long()])
+        return st
+
+    @torch.no_grad()
+    def generate(self, tokens: torch.Tensor, codes: torch.Tensor, *, max_new: int, top_k: int, top_p: float,
+                 temperature: float, code_lens=None, uniforms: torch.Tensor | None = None, seed: int = 0,
+                 ignore_eos: bool = False, use_graph: bool = True, poll_every: int = 16):
+        """Returns (codes_out (B,n_steps) int32, sum_logprobs (B,), n_steps).  Semantics: valle_ar.py:141-171."""
+        samp = {'temperature': temperature, 'top_k': top_k, 'top_p': top_p, 'seed': seed}
+        eos = -1 if ignore_eos else self.cfg.num_audio_tokens
+        st = self.prefill(tokens, codes, code_lens=code_lens, max_new=max_new)
+        self._logits_sample_book(st['x_last'], samp, None if uniforms is None else uniforms[0].contiguous(), eos)
+        graph = None
+        step = 1
+        if use_graph and uniforms is None and max_new > 2:
+            self._decode_step(samp, None, eos)          # warm-up (also loads modules, sets func attributes)
+            step += 1
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                self._decode_step(samp, None, eos)
+            # capture does not execute: the captured step still has to be replayed for this position
+        self._graph = graph
+        while step < max_new:
+            if graph is not None:
+                graph.replay()
+            else:
+                self._decode_step(samp, None if uniforms is None else uniforms[step].contiguous(), eos)
+            step += 1
+            if not ignore_eos and (step % poll_every == 0):
+                if int(st['state'][1].item()) >= 0:
+                    break
+        s_now, s_stop = (int(v) for v in st['state'].tolist())
+        n = s_stop if s_stop >= 0 else min(s_now, max_new)
+        return st['codes_out'][:, :n], st['sum_logprobs'].clone(), n
+
+
+class NARDecoder:
+    def __init__(self, model, precision: str):
+        cfg = model.config
+        assert cfg.norm == 'AdaptiveLayerNorm', 'ValleNAR conditions on the stage through AdaptiveLayerNorm'
+        self.cfg = cfg
+        self.precision = precision
+        self.cd = _cdtype(precision)
+        self.device = model.device
+        self.H, self.d, self.Q = cfg.n_heads, cfg.d_model, cfg.num_quantizers
+        stage_embs = [m.weight for m in model.stage_embs]
+        self.weights = StackWeights(model.transformer, cfg.norm, precision, stage_embs)
+        self.runner = StackRunner(self.weights, self.H)
+        self.tok_table = model.tokens_emb.weight.detach().float().unsqueeze(0).contiguous()
+        self.code_tables = torch.stack([m.weight.detach().float() for m in model.codes_embs]).contiguous()
+        self.pe_t = model.tokens_position_emb.pe.detach().float().reshape(-1, self.d).contiguous()
+        self.pe_a = model.audio_position_emb.pe.detach().float().reshape(-1, self.d).contiguous()
+        self.wproj = [m.weight.detach().to(self.cd).contiguous() for m in model.proj_layers]
+
+    @torch.no_grad()
+    def generate(self, prompt_tokens: torch.Tensor, prompt_codes: torch.Tensor, target_tokens: torch.Tensor,
+                 first_layer: torch.Tensor, *, greedy: bool = True, temperature: float = 1.0, seed: int = 0,
+                 return_logits: bool = False, use_tc_attention: bool = False):
+        """Batched stages 2..Q.  prompt_tokens (B,Tp), prompt_codes (B,Tc,Q), target_tokens (B,Tt),
+        first_layer (B,T) -> (B,T,Q) int64."""
+        dev, d, Q = self.device, self.d, self.Q
+        B, Tc, Qc = prompt_codes.shape
+        assert Qc == Q
+        tokens = torch.cat([prompt_tokens, target_tokens], dim=1)
+        Tx, T = tokens.shape[1], first_layer.shape[1]
+        S = Tx + Tc + T
+        tok_i = _i32(tokens, dev).view(B, Tx, 1)
+        ids = torch.zeros(B, Tc + T, Q, device=dev, dtype=torch.int32)
+        ids[:, :Tc] = prompt_codes.to(dev)
+        ids[:, Tc:, 0] = first_layer.to(dev)
+        x = torch.empty(B * S, d, device=dev, dtype=torch.float32)
+        V = self.cfg.num_audio_tokens
+        sampled = torch.empty(B * T, device=dev, dtype=torch.int32)
+        step = torch.zeros(1, device=dev, dtype=torch.int32)
+        trace = []
+        for n in range(1, Q):
+            ops.embed_sum_pe(tok_i, self.tok_table, self.pe_t, x, out_rows_per_batch=S, out_row_offset=0)
+            ops.embed_sum_pe(ids, self.code_tables, self.pe_a, x, t_split=Tc, nq_a=Q, nq_b=n,
+                             out_rows_per_batch=S, out_row_offset=Tx)
+            self.runner.forward(x, B, S, mask_mode=MASK_NONE, stage=n - 1, use_tc_attention=use_tc_attention)
+            tgt = x.view(B, S, d)[:, Tx + Tc:].reshape(B * T, d)          # strided gather (memory plumbing)
+            if self.precision == 'bf16':
+                hb = torch.empty(B * T, d, device=dev, dtype=self.cd)
+                ops.residual_layernorm(tgt, None, None, hb)
+                logits = ops.linear(hb, self.wproj[n - 1], out_dtype=torch.float32)
+            else:
+                logits = ops.linear(tgt, self.wproj[n - 1])
+            if return_logits:
+                trace.append(logits.view(B, T, V).clone())
+            step.fill_(n)
+            if greedy:
+                ops.sample(logits, 1, 0, V, B * T, V, temperature=1.0, top_k=1, top_p=1.0, out_tok=sampled)
+            else:
+                ops.sample(logits, 1, 0, V, B * T, V, temperature=temperature, top_k=0, top_p=1.0, out_tok=sampled,
+                           seed=seed, step_ptr=step)
+            ids[:, Tc:, n] = sampled.view(B, T)
+        out = ids[:, Tc:].long()
+        return (out, trace) if return_logits else out

@@ -1,0 +1,212 @@
+"""Thin torch-tensor wrappers over the C ABI (include/valle_b200.h).
+
+PyTorch is used here only for device memory and streams; every computation below is a kernel of
+libvalle_b200.so launched on ``torch.cuda.current_stream()``.  All wrappers raise on CPU tensors:
+there is no fallback path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import (EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RESIDUAL, EPI_NONE, MASK_EXPLICIT, MASK_NONE,
+                   MASK_PREFIX_LM, VB_BF16, VB_F32, check)
+
+__all__ = ['EPI_NONE', 'EPI_BIAS', 'EPI_BIAS_GELU', 'EPI_BIAS_RESIDUAL', 'MASK_NONE', 'MASK_PREFIX_LM',
+           'MASK_EXPLICIT', 'VB_F32', 'VB_BF16']
+
+PAGE = 64
+
+
+def _L():
+    return _lib.load()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _code(dtype: torch.dtype) -> int:
+    if dtype == torch.float32:
+        return VB_F32
+    if dtype == torch.bfloat16:
+        return VB_BF16
+    raise TypeError(f'unsupported dtype {dtype}; the CUDA path handles float32 and bfloat16')
+
+
+def _ptr(t: torch.Tensor | None) -> int | None:
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise _lib.VBError('valle2_b200 has no CPU path: tensor is not on a CUDA device')
+    return t.data_ptr()
+
+
+def device_info() -> dict:
+    sm, maj, mn, smem = C.c_int(), C.c_int(), C.c_int(), C.c_int64()
+    check(_L().vb_device_info(C.byref(sm), C.byref(maj), C.byref(mn), C.byref(smem)), 'vb_device_info')
+    return {'sm_count': sm.value, 'cc': (maj.value, mn.value), 'smem_optin': smem.value}
+
+
+def embed_sum_pe(ids: torch.Tensor, tables: torch.Tensor, pe: torch.Tensor, out: torch.Tensor, *,
+                 t_split: int = 0, nq_a: int | None = None, nq_b: int | None = None, pos_offset: int = 0,
+                 pos_b: torch.Tensor | None = None, out_rows_per_batch: int | None = None,
+                 out_row_offset: int = 0) -> None:
+    """ids int32 (B,T,Q); tables fp32 (Q,V,d); pe fp32 (max_len,d); out fp32 rows of d."""
+    B, T, Q = ids.shape
+    Qt, V, d = tables.shape
+    assert Qt == Q and ids.dtype == torch.int32 and ids.is_contiguous() and tables.is_contiguous()
+    assert tables.dtype == torch.float32 and pe.dtype == torch.float32 and out.dtype == torch.float32
+    nq_b = Q if nq_b is None else nq_b
+    nq_a = nq_b if nq_a is None else nq_a
+    rows = T if out_rows_per_batch is None else out_rows_per_batch
+    check(_L().vb_embed_sum_pe(_ptr(ids), _ptr(tables), _ptr(pe), _ptr(out), B, T, Q, V, d, t_split, nq_a, nq_b,
+                               pos_offset, _ptr(pos_b), pe.shape[0], rows, out_row_offset, _stream()),
+          'vb_embed_sum_pe')
+
+
+def residual_layernorm(x: torch.Tensor, gamma: torch.Tensor | None, beta: torch.Tensor | None,
+                       y: torch.Tensor | None, *, part: torch.Tensor | None = None, n_part: int = 0,
+                       part_stride: int = 0, bias: torch.Tensor | None = None, eps: float = 1e-5) -> None:
+    """x fp32 (R,d) updated in place when n_part > 0; y = LN(x) (or a plain cast when gamma is None)."""
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    R, d = x.shape
+    check(_L().vb_residual_layernorm(_ptr(x), _ptr(part), n_part, part_stride, _ptr(bias), _ptr(gamma), _ptr(beta),
+                                     _ptr(y), _code(y.dtype) if y is not None else VB_F32, R, d, eps, _stream()),
+          'vb_residual_layernorm')
+
+
+def reduce_bias_act(part: torch.Tensor, n_part: int, part_stride: int, bias: torch.Tensor | None, gelu: bool,
+                    y: torch.Tensor) -> None:
+    R, N = y.shape
+    check(_L().vb_reduce_bias_act(_ptr(part), n_part, part_stride, _ptr(bias), int(gelu), _ptr(y), _code(y.dtype),
+                                  R, N, _stream()), 'vb_reduce_bias_act')
+
+
+def linear(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None = None, *, gelu: bool = False,
+           residual: torch.Tensor | None = None, out: torch.Tensor | None = None,
+           out_dtype: torch.dtype | None = None) -> torch.Tensor:
+    """y = epilogue(x @ w.T); x (M,K), w (N,K) same dtype (fp32 -> SIMT, bf16 -> tcgen05)."""
+    assert x.dim() == 2 and w.dim() == 2 and x.shape[1] == w.shape[1], (x.shape, w.shape)
+    assert x.stride(1) == 1 and w.stride(1) == 1
+    M, K = x.shape
+    N = w.shape[0]
+    if out is None:
+        out = torch.empty(M, N, device=x.device, dtype=out_dtype or x.dtype)
+    assert out.shape == (M, N) and out.stride(1) == 1
+    if residual is not None:
+        assert bias is not None and not gelu and residual.dtype == torch.float32 and residual.stride(1) == 1
+        epi = EPI_BIAS_RESIDUAL
+    elif gelu:
+        assert bias is not None
+        epi = EPI_BIAS_GELU
+    elif bias is not None:
+        epi = EPI_BIAS
+    else:
+        epi = EPI_NONE
+    if bias is not None:
+        assert bias.dtype == torch.float32 and bias.is_contiguous()
+    check(_L().vb_linear(_ptr(x), _code(x.dtype), x.stride(0), _ptr(w), _code(w.dtype), w.stride(0), _ptr(bias),
+                         _ptr(residual), residual.stride(0) if residual is not None else 0, _ptr(out),
+                         _code(out.dtype), out.stride(0), M, N, K, epi, _stream()), 'vb_linear')
+    return out
+
+
+def linear_decode_splits(N: int, K: int, max_split: int) -> int:
+    return int(_L().vb_linear_decode_splits(N, K, max_split))
+
+
+def linear_decode(x: torch.Tensor, w: torch.Tensor, part: torch.Tensor, part_stride: int, max_split: int) -> int:
+    """part[s][m][n] (fp32) = split-K slices of x @ w.T; x (M<=256,K) bf16, w (N,K) bf16.  Returns n_split."""
+    assert x.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and part.dtype == torch.float32
+    M, K = x.shape
+    N = w.shape[0]
+    ns = C.c_int()
+    check(_L().vb_linear_decode(_ptr(x), x.stride(0), _ptr(w), w.stride(0), _ptr(part), part_stride, M, N, K,
+                                max_split, C.byref(ns), _stream()), 'vb_linear_decode')
+    return ns.value
+
+
+def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tensor, *, mask_mode: int = MASK_NONE,
+              q_pos0: int = 0, x_lens: torch.Tensor | None = None, kv_lens: torch.Tensor | None = None,
+              mask: torch.Tensor | None = None) -> torch.Tensor:
+    """q (B,H,Sq,Dh), k/v (B,H,Sk,Dh) strided views with unit last stride; out (B,Sq,H*Dh).
+    mask (explicit mode): uint8, broadcastable to (B,H,Sq,Sk), nonzero = masked."""
+    B, H, Sq, Dh = q.shape
+    Sk = k.shape[2]
+    assert q.stride(3) == 1 and k.stride(3) == 1 and v.stride(3) == 1 and out.stride(2) == 1
+    assert q.dtype == k.dtype == v.dtype
+    m_sb = m_sh = m_sq = 0
+    if mask_mode == MASK_EXPLICIT:
+        assert mask is not None and mask.dtype == torch.uint8 and mask.dim() == 4 and mask.stride(3) == 1
+        assert mask.shape[2] == Sq and mask.shape[3] == Sk
+        m_sb = mask.stride(0) if mask.shape[0] > 1 else 0
+        m_sh = mask.stride(1) if mask.shape[1] > 1 else 0
+        m_sq = mask.stride(2)
+    for t in (x_lens, kv_lens):
+        assert t is None or (t.dtype == torch.int32 and t.is_contiguous())
+    check(_L().vb_attention(_ptr(q), _ptr(k), _ptr(v), _code(q.dtype), q.stride(0), q.stride(1), q.stride(2),
+                            k.stride(0), k.stride(1), k.stride(2), v.stride(0), v.stride(1), v.stride(2),
+                            _ptr(out), _code(out.dtype), out.stride(0), out.stride(1), B, H, Sq, Sk, Dh, mask_mode,
+                            q_pos0, _ptr(x_lens), _ptr(kv_lens), _ptr(mask), m_sb, m_sh, m_sq, _stream()),
+          'vb_attention')
+    return out
+
+
+def attention_packed(qkv: torch.Tensor, out: torch.Tensor, B: int, S: int, H: int, *, mask_mode: int,
+                     x_lens: torch.Tensor | None, kv_lens: torch.Tensor | None, use_tc: bool = False) -> torch.Tensor:
+    """Self-attention over a packed (B*S, 3*H*Dh) qkv buffer; out (B*S, H*Dh)."""
+    d3 = qkv.shape[1]
+    d = d3 // 3
+    Dh = d // H
+    if use_tc:
+        check(_L().vb_attention_prefill_tc(_ptr(qkv), _ptr(out), B, S, H, mask_mode, _ptr(x_lens), _ptr(kv_lens),
+                                           _stream()), 'vb_attention_prefill_tc')
+        return out
+    base = qkv.view(B, S, 3, H, Dh)
+    q = base[:, :, 0].permute(0, 2, 1, 3)
+    k = base[:, :, 1].permute(0, 2, 1, 3)
+    v = base[:, :, 2].permute(0, 2, 1, 3)
+    attention(q, k, v, out.view(B, S, d), mask_mode=mask_mode, x_lens=x_lens, kv_lens=kv_lens)
+    return out
+
+
+def kv_scatter_paged(qkv: torch.Tensor, pool: torch.Tensor, block_table: torch.Tensor, kv_lens: torch.Tensor,
+                     B: int, S: int, H: int, Dh: int) -> None:
+    check(_L().vb_kv_scatter_paged(_ptr(qkv), _code(qkv.dtype), _ptr(pool), _code(pool.dtype), _ptr(block_table),
+                                   block_table.shape[1], _ptr(kv_lens), B, S, H, Dh, _stream()),
+          'vb_kv_scatter_paged')
+
+
+def attn_decode_ws_bytes(B: int, H: int, n_tsplit: int) -> int:
+    return int(_L().vb_attn_decode_ws_bytes(B, H, n_tsplit))
+
+
+def attn_decode_paged(qkv_part: torch.Tensor, n_part: int, part_stride: int, pool: torch.Tensor,
+                      block_table: torch.Tensor, seq_lens: torch.Tensor, out: torch.Tensor, B: int, H: int, Dh: int,
+                      n_tsplit: int, ws: torch.Tensor | None) -> None:
+    check(_L().vb_attn_decode_paged(_ptr(qkv_part), n_part, part_stride, _ptr(pool), _code(pool.dtype),
+                                    _ptr(block_table), block_table.shape[1], _ptr(seq_lens), _ptr(out),
+                                    _code(out.dtype), B, H, Dh, n_tsplit, _ptr(ws), _stream()),
+          'vb_attn_decode_paged')
+
+
+def sample(logits_part: torch.Tensor, n_part: int, part_stride: int, row_stride: int, R: int, V: int, *,
+           temperature: float, top_k: int, top_p: float, out_tok: torch.Tensor,
+           out_logprob: torch.Tensor | None = None, uniforms: torch.Tensor | None = None, seed: int = 0,
+           step_ptr: torch.Tensor | None = None) -> None:
+    assert out_tok.dtype == torch.int32
+    check(_L().vb_sample(_ptr(logits_part), n_part, part_stride, row_stride, R, V, float(temperature), int(top_k),
+                         float(top_p), _ptr(uniforms), seed & (2 ** 64 - 1), _ptr(step_ptr), _ptr(out_tok),
+                         _ptr(out_logprob), _stream()), 'vb_sample')
+
+
+def ar_bookkeeping(sample_tok: torch.Tensor, logprob: torch.Tensor, last: torch.Tensor, sum_logprobs: torch.Tensor,
+                   codes_out: torch.Tensor, seq_lens: torch.Tensor, audio_pos: torch.Tensor, state: torch.Tensor,
+                   eos: int) -> None:
+    B = last.shape[0]
+    check(_L().vb_ar_bookkeeping(_ptr(sample_tok), _ptr(logprob), _ptr(last), _ptr(sum_logprobs), _ptr(codes_out),
+                                 codes_out.stride(0), _ptr(seq_lens), _ptr(audio_pos), _ptr(state), B, eos,
+                                 _stream()), 'vb_ar_bookkeeping')
