@@ -1,8 +1,267 @@
-// Placeholder translation unit for the tcgen05 flash-attention kernel (prefill / NAR); see DESIGN.md.
+// Flash-style attention on the 5th-generation tensor cores for the large-M paths (AR prefill, NAR stages, teacher-forced
+// forward): S = Q K^T and O += P V are tcgen05.mma with accumulators in TMEM, operands staged by TMA (SWIZZLE_128B)
+// straight out of the packed qkv buffer [B*S][3][H][64] written by the QKV GEMM -- no head-split copy, no
+// materialised (B,H,S,S) mask: the prefix-LM / padding predicate is evaluated from (x_len, kv_len) per element.
+//
+// CTA = 128 query rows of one (batch, head); key blocks of 64.
+//   warp 0    TMA producer: Q tile once, then a 3-deep ring of {K block, V block}
+//   warp 1    MMA issuer + TMEM allocator: QK_j (M128 N64 K64), PV_j (M128 N64 K64; V is the MN-major B operand)
+//   warp 2-5  softmax: one thread per query row (tcgen05.ld 32x32b gives a thread its whole row -> no shuffles):
+//             online max/sum in the exp2 domain, P_j written as bf16 into a 128B-swizzled smem tile (the A operand of
+//             PV_j), running output kept in registers and rescaled by exp2(m_old - m_new).
+// Two CTAs are resident per SM (80 KB smem, 128 TMEM columns each) so one CTA's softmax overlaps the other's MMAs.
+// Replaces F.scaled_dot_product_attention + merge_masks on modules.py:160-167 for S > 1.
+#include <math.h>
+
 #include "common.cuh"
+
+namespace {
+
+constexpr int BQ = 128;    // query rows per CTA
+constexpr int BKV = 64;    // keys per block
+constexpr int DH = 64;
+constexpr int KV_STAGES = 3;
+constexpr int THREADS = 192;
+constexpr int Q_BYTES = BQ * DH * 2;          // 16 KB
+constexpr int KV_BYTES = BKV * DH * 2;        // 8 KB each for K and V
+constexpr int P_BYTES = BQ * BKV * 2;         // 16 KB
+constexpr int SMEM_BYTES = Q_BYTES + KV_STAGES * 2 * KV_BYTES + P_BYTES + 1024;
+constexpr int TMEM_COLS = 128;                // S: cols [0,64), PV: cols [64,128)
+
+__device__ __forceinline__ float fast_exp2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+__global__ void __launch_bounds__(THREADS, 2) attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tm_q,
+                                                                     const __grid_constant__ CUtensorMap tm_kv,
+                                                                     __nv_bfloat16* __restrict__ o, int S, int H, int mask_mode,
+                                                                     const int32_t* __restrict__ x_lens,
+                                                                     const int32_t* __restrict__ kv_lens, float scale_log2e) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bar_q, bar_s, bar_sfree, bar_p, bar_o;
+    __shared__ __align__(8) uint64_t kv_full[KV_STAGES], kv_empty[KV_STAGES];
+    __shared__ uint32_t tmem_slot;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+    const int d = H * DH;
+    const int i0 = qt * BQ;
+    const int kv_len = kv_lens ? min(kv_lens[b], S) : S;
+    const int x_len = (mask_mode == VB_MASK_PREFIX_LM) ? x_lens[b] : 0;
+    // keys any row of this tile may attend: everything (no mask) or the text prefix plus the causal part
+    int k_end = kv_len;
+    if (mask_mode == VB_MASK_PREFIX_LM) k_end = min(kv_len, max(x_len, i0 + BQ));
+    const int nb = max(1, (k_end + BKV - 1) / BKV);
+
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t q_smem = base;
+    const uint32_t kv_smem = base + Q_BYTES;
+    const uint32_t p_smem = kv_smem + KV_STAGES * 2 * KV_BYTES;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tm_q);
+        tma_prefetch_desc(&tm_kv);
+        mbar_init(smem_u32(&bar_q), 1);
+        mbar_init(smem_u32(&bar_s), 1);
+        mbar_init(smem_u32(&bar_sfree), 4);
+        mbar_init(smem_u32(&bar_p), 4);
+        mbar_init(smem_u32(&bar_o), 1);
+        for (int s = 0; s < KV_STAGES; ++s) {
+            mbar_init(smem_u32(&kv_full[s]), 1);
+            mbar_init(smem_u32(&kv_empty[s]), 1);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc<TMEM_COLS>(smem_u32(&tmem_slot));
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_slot;
+    const int row0 = b * S;   // first row of this batch in the packed [B*S][3d] matrix
+
+    if (warp == 0) {
+        if (elect_one()) {
+            mbar_expect_tx(smem_u32(&bar_q), Q_BYTES);
+            tma_load_2d(q_smem, &tm_q, smem_u32(&bar_q), h * DH, row0 + i0);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int j = 0; j < nb; ++j) {
+                mbar_wait(smem_u32(&kv_empty[stage]), phase ^ 1);
+                const uint32_t fb = smem_u32(&kv_full[stage]);
+                mbar_expect_tx(fb, 2 * KV_BYTES);
+                const uint32_t dst = kv_smem + stage * 2 * KV_BYTES;
+                tma_load_2d(dst, &tm_kv, fb, d + h * DH, row0 + j * BKV);
+                tma_load_2d(dst + KV_BYTES, &tm_kv, fb, 2 * d + h * DH, row0 + j * BKV);
+                if (++stage == KV_STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        if (elect_one()) {
+            constexpr uint32_t IDESC_QK = umma_idesc_bf16(BQ, BKV, 0, 0);   // A = Q (K-major), B = K block (K-major)
+            constexpr uint32_t IDESC_PV = umma_idesc_bf16(BQ, DH, 0, 1);    // A = P (K-major), B = V block (MN-major)
+            const uint32_t s_tmem = tmem_base, o_tmem = tmem_base + BKV;
+            mbar_wait(smem_u32(&bar_q), 0);
+            int stage = 0;
+            uint32_t phase = 0;
+            auto issue_pv = [&](int jj, int st) {
+                mbar_wait(smem_u32(&bar_p), jj & 1);
+                tc_fence_after();
+                const uint32_t v_s = kv_smem + st * 2 * KV_BYTES + KV_BYTES;
+#pragma unroll
+                for (int kk = 0; kk < BKV / 16; ++kk) {
+                    const uint64_t da = umma_desc_sw128(p_smem + kk * 32, 16, 1024);
+                    const uint64_t db = umma_desc_sw128(v_s + kk * 16 * 128, 1024, 1024);
+                    umma_f16(o_tmem, da, db, IDESC_PV, kk > 0 ? 1u : 0u);
+                }
+                umma_commit(smem_u32(&kv_empty[st]));
+                umma_commit(smem_u32(&bar_o));
+            };
+            int prev_stage = 0;
+            for (int j = 0; j < nb; ++j) {
+                mbar_wait(smem_u32(&kv_full[stage]), phase);
+                mbar_wait(smem_u32(&bar_sfree), (j & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t k_s = kv_smem + stage * 2 * KV_BYTES;
+#pragma unroll
+                for (int kk = 0; kk < DH / 16; ++kk) {
+                    const uint64_t da = umma_desc_sw128(q_smem + kk * 32, 16, 1024);
+                    const uint64_t db = umma_desc_sw128(k_s + kk * 32, 16, 1024);
+                    umma_f16(s_tmem, da, db, IDESC_QK, kk > 0 ? 1u : 0u);
+                }
+                umma_commit(smem_u32(&bar_s));
+                if (j > 0) issue_pv(j - 1, prev_stage);
+                prev_stage = stage;
+                if (++stage == KV_STAGES) { stage = 0; phase ^= 1; }
+            }
+            issue_pv(nb - 1, prev_stage);
+        }
+    } else {
+        const int q = warp & 3;
+        const int r = q * 32 + lane;          // row within the tile == TMEM lane
+        const int i = i0 + r;                 // query index within the sequence
+        const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+        float m_run = -INFINITY, l_run = 0.f;
+        float acc[DH];
+#pragma unroll
+        for (int e = 0; e < DH; ++e) acc[e] = 0.f;
+        const uint32_t p_row = p_smem + r * 128;
+        for (int j = 0; j < nb; ++j) {
+            mbar_wait(smem_u32(&bar_s), j & 1);
+            tc_fence_after();
+            uint32_t sv[BKV];
+            tmem_ld_32x32(lane_addr, reinterpret_cast<uint32_t(&)[32]>(sv[0]));
+            tmem_ld_32x32(lane_addr + 32, reinterpret_cast<uint32_t(&)[32]>(sv[32]));
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&bar_sfree));
+            // scale into the exp2 domain, mask, row max
+            const int kbase = j * BKV;
+            float mx = -INFINITY;
+#pragma unroll
+            for (int c = 0; c < BKV; ++c) {
+                const int kj = kbase + c;
+                bool ok = kj < kv_len;
+                if (mask_mode == VB_MASK_PREFIX_LM) ok = ok && ((kj < x_len) || (i >= x_len && kj <= i));
+                const float s = ok ? __uint_as_float(sv[c]) * scale_log2e : -INFINITY;
+                sv[c] = __float_as_uint(s);
+                mx = fmaxf(mx, s);
+            }
+            const float m_new = fmaxf(m_run, mx);
+            const float m_use = (m_new == -INFINITY) ? 0.f : m_new;     // fully masked so far: p = 0, no NaN
+            const float alpha = (m_run == -INFINITY) ? 0.f : fast_exp2(m_run - m_use);
+            float rs = 0.f;
+            uint32_t pk[BKV / 2];
+#pragma unroll
+            for (int c = 0; c < BKV; c += 2) {
+                const float p0 = fast_exp2(__uint_as_float(sv[c]) - m_use);
+                const float p1 = fast_exp2(__uint_as_float(sv[c + 1]) - m_use);
+                rs += p0 + p1;
+                pk[c >> 1] = pack_bf16x2(p0, p1);
+            }
+            // fold in PV_{j-1} (accumulated relative to the previous max), then rescale to the new max
+            if (j > 0) {
+                mbar_wait(smem_u32(&bar_o), (j - 1) & 1);
+                tc_fence_after();
+                uint32_t ov[32];
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    tmem_ld_32x32(lane_addr + BKV + half * 32, ov);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) acc[half * 32 + e] = (acc[half * 32 + e] + __uint_as_float(ov[e])) * alpha;
+                }
+            }
+            l_run = l_run * alpha + rs;
+            m_run = m_new;
+            // P_j -> smem, K-major 128B-swizzled rows (chunk c of row r lives at chunk c ^ (r & 7))
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const uint32_t addr = p_row + (static_cast<uint32_t>(c ^ (r & 7)) << 4);
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[c * 4]), "r"(pk[c * 4 + 1]),
+                             "r"(pk[c * 4 + 2]), "r"(pk[c * 4 + 3]) : "memory");
+            }
+            fence_proxy_async();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&bar_p));
+        }
+        mbar_wait(smem_u32(&bar_o), (nb - 1) & 1);
+        tc_fence_after();
+        const float inv = (l_run > 0.f) ? 1.f / l_run : 0.f;
+        __nv_bfloat16* orow = o + (static_cast<int64_t>(row0) + i) * d + h * DH;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            uint32_t ov[32];
+            tmem_ld_32x32(lane_addr + BKV + half * 32, ov);
+            tmem_ld_wait();
+            if (i < S) {
+#pragma unroll
+                for (int e = 0; e < 32; e += 8) {
+                    uint4 w;
+                    w.x = pack_bf16x2((acc[half * 32 + e] + __uint_as_float(ov[e])) * inv, (acc[half * 32 + e + 1] + __uint_as_float(ov[e + 1])) * inv);
+                    w.y = pack_bf16x2((acc[half * 32 + e + 2] + __uint_as_float(ov[e + 2])) * inv, (acc[half * 32 + e + 3] + __uint_as_float(ov[e + 3])) * inv);
+                    w.z = pack_bf16x2((acc[half * 32 + e + 4] + __uint_as_float(ov[e + 4])) * inv, (acc[half * 32 + e + 5] + __uint_as_float(ov[e + 5])) * inv);
+                    w.w = pack_bf16x2((acc[half * 32 + e + 6] + __uint_as_float(ov[e + 6])) * inv, (acc[half * 32 + e + 7] + __uint_as_float(ov[e + 7])) * inv);
+                    *reinterpret_cast<uint4*>(orow + half * 32 + e) = w;
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<TMEM_COLS>(tmem_base);
+    }
+}
+
+}  // namespace
 
 extern "C" int vb_attention_prefill_tc(const void* qkv, void* o, int B, int S, int H, int mask_mode, const int32_t* x_lens,
                                        const int32_t* kv_lens, void* stream) {
-    (void)qkv; (void)o; (void)B; (void)S; (void)H; (void)mask_mode; (void)x_lens; (void)kv_lens; (void)stream;
-    VB_REQUIRE(false, VB_ERR_UNSUPPORTED, "vb_attention_prefill_tc: not built in this revision");
+    VB_REQUIRE(qkv && o, VB_ERR_BAD_ARG, "vb_attention_prefill_tc: null pointer");
+    VB_REQUIRE(B >= 1 && S >= 1 && H >= 1 && B <= 65535 && H <= 65535, VB_ERR_BAD_ARG, "vb_attention_prefill_tc: bad shape");
+    VB_REQUIRE(mask_mode == VB_MASK_NONE || mask_mode == VB_MASK_PREFIX_LM, VB_ERR_UNSUPPORTED,
+               "vb_attention_prefill_tc: mask mode %d (use vb_attention for explicit masks)", mask_mode);
+    VB_REQUIRE(mask_mode != VB_MASK_PREFIX_LM || x_lens != nullptr, VB_ERR_BAD_ARG, "vb_attention_prefill_tc: prefix-LM needs x_lens");
+    const int64_t d = static_cast<int64_t>(H) * DH;
+    const int64_t rows = static_cast<int64_t>(B) * S;
+    CUtensorMap tq, tkv;
+    int rc;
+    if ((rc = vb_make_tmap_bf16_2d(&tq, qkv, rows, 3 * d, 3 * d, BQ, DH)) != VB_OK) return rc;
+    if ((rc = vb_make_tmap_bf16_2d(&tkv, qkv, rows, 3 * d, 3 * d, BKV, DH)) != VB_OK) return rc;
+    static bool configured = false;
+    if (!configured) {
+        VB_CUDA(cudaFuncSetAttribute(attn_prefill_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        configured = true;
+    }
+    dim3 grid(static_cast<unsigned>(vb_ceil_div(S, BQ)), H, B);
+    const float scale_log2e = 1.4426950408889634f / sqrtf(static_cast<float>(DH));
+    attn_prefill_tc_kernel<<<grid, THREADS, SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(
+        tq, tkv, static_cast<__nv_bfloat16*>(o), S, H, mask_mode, x_lens, kv_lens, scale_log2e);
+    VB_LAUNCH_CHECK();
+    return VB_OK;
 }

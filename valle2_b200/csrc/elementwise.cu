@@ -152,9 +152,115 @@ __global__ void __launch_bounds__(256) residual_layernorm_generic_kernel(float* 
     for (int c = lane; c < d; c += 32) y[r * d + c] = from_f32<TY>((xr[c] - mean) * rstd * gamma[c] + beta[c]);
 }
 
+// Few rows (decode: R = batch): one 256-thread CTA per row so that the split-K slices are read with many independent
+// 16-byte loads in flight instead of one warp walking them serially.  d <= 4096, d % 4 == 0.
+template <typename TY>
+__global__ void __launch_bounds__(256) residual_layernorm_block_kernel(float* __restrict__ x, const float* __restrict__ part,
+                                                                       int n_part, int64_t part_stride,
+                                                                       const float* __restrict__ bias,
+                                                                       const float* __restrict__ gamma,
+                                                                       const float* __restrict__ beta, TY* __restrict__ y,
+                                                                       int d, float eps) {
+    __shared__ float red[8];
+    const int64_t r = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float* xr = x + r * d;
+    constexpr int MAXC = 4;
+    float4 v[MAXC];
+    const int nchunk = d >> 2;
+#pragma unroll
+    for (int i = 0; i < MAXC; ++i) {
+        const int c4 = tid + i * 256;
+        v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c4 < nchunk) {
+            const int c = c4 * 4;
+            float4 a = *reinterpret_cast<const float4*>(xr + c);
+            if (n_part > 0) {
+                float4 acc = bias ? *reinterpret_cast<const float4*>(bias + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+                const float* pp = part + r * d + c;
+                int s = 0;
+                for (; s + 4 <= n_part; s += 4) {   // four independent loads in flight, summed in slice order
+                    const float4 p0 = *reinterpret_cast<const float4*>(pp + (s + 0) * part_stride);
+                    const float4 p1 = *reinterpret_cast<const float4*>(pp + (s + 1) * part_stride);
+                    const float4 p2 = *reinterpret_cast<const float4*>(pp + (s + 2) * part_stride);
+                    const float4 p3 = *reinterpret_cast<const float4*>(pp + (s + 3) * part_stride);
+                    acc.x += p0.x; acc.y += p0.y; acc.z += p0.z; acc.w += p0.w;
+                    acc.x += p1.x; acc.y += p1.y; acc.z += p1.z; acc.w += p1.w;
+                    acc.x += p2.x; acc.y += p2.y; acc.z += p2.z; acc.w += p2.w;
+                    acc.x += p3.x; acc.y += p3.y; acc.z += p3.z; acc.w += p3.w;
+                }
+                for (; s < n_part; ++s) {
+                    const float4 p0 = *reinterpret_cast<const float4*>(pp + s * part_stride);
+                    acc.x += p0.x; acc.y += p0.y; acc.z += p0.z; acc.w += p0.w;
+                }
+                a.x += acc.x; a.y += acc.y; a.z += acc.z; a.w += acc.w;
+                *reinterpret_cast<float4*>(xr + c) = a;
+            }
+            v[i] = a;
+        }
+    }
+    if (y == nullptr) return;
+    TY* yr = y + r * d;
+    if (gamma == nullptr) {
+#pragma unroll
+        for (int i = 0; i < MAXC; ++i) {
+            const int c4 = tid + i * 256;
+            if (c4 < nchunk) {
+                if constexpr (sizeof(TY) == 4) *reinterpret_cast<float4*>(yr + c4 * 4) = v[i];
+                else *reinterpret_cast<uint2*>(yr + c4 * 4) = make_uint2(pack_bf16x2(v[i].x, v[i].y), pack_bf16x2(v[i].z, v[i].w));
+            }
+        }
+        return;
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXC; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);   // chunks past d hold zeros
+    s = warp_sum(s);
+    if (lane == 0) red[warp] = s;
+    __syncthreads();
+    float tot = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) tot += red[w];
+    const float mean = tot / d;
+    __syncthreads();
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXC; ++i) {
+        if (tid + i * 256 < nchunk) {
+            const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, e = v[i].w - mean;
+            q += (a * a + b * b) + (c * c + e * e);
+        }
+    }
+    q = warp_sum(q);
+    if (lane == 0) red[warp] = q;
+    __syncthreads();
+    float qt = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) qt += red[w];
+    const float rstd = rsqrtf(qt / d + eps);
+#pragma unroll
+    for (int i = 0; i < MAXC; ++i) {
+        const int c4 = tid + i * 256;
+        if (c4 < nchunk) {
+            const int c = c4 * 4;
+            const float4 g = *reinterpret_cast<const float4*>(gamma + c);
+            const float4 bt = *reinterpret_cast<const float4*>(beta + c);
+            const float o0 = (v[i].x - mean) * rstd * g.x + bt.x, o1 = (v[i].y - mean) * rstd * g.y + bt.y;
+            const float o2 = (v[i].z - mean) * rstd * g.z + bt.z, o3 = (v[i].w - mean) * rstd * g.w + bt.w;
+            if constexpr (sizeof(TY) == 4) *reinterpret_cast<float4*>(yr + c) = make_float4(o0, o1, o2, o3);
+            else *reinterpret_cast<uint2*>(yr + c) = make_uint2(pack_bf16x2(o0, o1), pack_bf16x2(o2, o3));
+        }
+    }
+}
+
 template <typename TY>
 static int launch_rln(float* x, const float* part, int n_part, int64_t part_stride, const float* bias, const float* gamma,
                       const float* beta, TY* y, int64_t R, int d, float eps, cudaStream_t st) {
+    if (R <= 1024 && d % 4 == 0 && d <= 4096) {
+        residual_layernorm_block_kernel<TY><<<static_cast<unsigned>(R), 256, 0, st>>>(x, part, n_part, part_stride, bias, gamma, beta, y, d, eps);
+        VB_LAUNCH_CHECK();
+        return VB_OK;
+    }
     const int warps = 8;
     const dim3 grid(static_cast<unsigned>(vb_ceil_div(R, warps)));
 #define RLN(NV) residual_layernorm_kernel<TY, NV><<<grid, warps * 32, 0, st>>>(x, part, n_part, part_stride, bias, gamma, beta, y, R, d, eps)

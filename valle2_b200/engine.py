@@ -14,6 +14,7 @@ Precision: 'bf16' = bf16 weights / activations / KV, fp32 accumulation and fp32 
 from __future__ import annotations
 
 import math
+import os
 
 import torch
 
@@ -85,8 +86,11 @@ class StackRunner:
 
     def forward(self, x: torch.Tensor, B: int, S: int, *, mask_mode: int, x_lens=None, kv_lens=None, stage: int = 0,
                 kv_pools: torch.Tensor | None = None, block_table: torch.Tensor | None = None,
-                use_tc_attention: bool = False) -> torch.Tensor:
+                use_tc_attention: bool | None = None) -> torch.Tensor:
         R, d = x.shape
+        if use_tc_attention is None:    # tcgen05 flash attention whenever the shape allows (bf16, head_dim 64)
+            use_tc_attention = (self.cd == torch.bfloat16 and d // self.H == 64
+                                and os.environ.get('VALLE_B200_TC_ATTN', '1') != '0')
         assert R == B * S
         buf = self._buffers(R, x.device)
         h, qkv, o, f = buf['h'], buf['qkv'], buf['o'], buf['f']
@@ -170,7 +174,7 @@ class ARDecoder:
             st['lg'] = torch.zeros(B, V, device=dev, dtype=torch.float32)
         # flash-decoding split: enough CTAs to fill the GPU, never more splits than pages
         sm = ops.device_info()['sm_count']
-        n_ts = max(1, min(16, max_pages, math.ceil(6 * sm / (B * H))))
+        n_ts = max(1, min(8, max_pages, math.ceil(sm / (B * H))))   # measured: splitting only pays when B*H < #SMs
         st['n_tsplit'] = n_ts
         st['attn_ws'] = torch.zeros(ops.attn_decode_ws_bytes(B, H, n_ts) // 4 + 64, device=dev, dtype=torch.int32)
         self._state = st
@@ -320,7 +324,7 @@ class NARDecoder:
     @torch.no_grad()
     def generate(self, prompt_tokens: torch.Tensor, prompt_codes: torch.Tensor, target_tokens: torch.Tensor,
                  first_layer: torch.Tensor, *, greedy: bool = True, temperature: float = 1.0, seed: int = 0,
-                 return_logits: bool = False, use_tc_attention: bool = False):
+                 return_logits: bool = False, use_tc_attention: bool | None = None):
         """Batched stages 2..Q.  prompt_tokens (B,Tp), prompt_codes (B,Tc,Q), target_tokens (B,Tt),
         first_layer (B,T) -> (B,T,Q) int64."""
         dev, d, Q = self.device, self.d, self.Q

@@ -91,7 +91,7 @@ class ValleNAR(BaseModule):
 
     @torch.inference_mode()
     def generate_batch(self, prompt_tokens, prompt_codes, target_tokens, first_layer, *, greedy: bool = True,
-                       seed: int = 0, use_tc_attention: bool = False) -> torch.Tensor:
+                       seed: int = 0, use_tc_attention: bool | None = None) -> torch.Tensor:
         """Extension: B equal-length utterances at once -> (B, T, Q)."""
         return self._engine().generate(prompt_tokens, prompt_codes, target_tokens, first_layer, greedy=greedy,
                                        temperature=self.config.temperature, seed=seed,
