@@ -99,8 +99,12 @@ int vb_linear(const void* x, int x_dtype, int64_t ldx, const void* w, int w_dtyp
  * Deterministic: consumers (vb_residual_layernorm / vb_reduce_bias_act / vb_attn_decode_paged / vb_sample) add the
  * slices in index order.  x,w bf16.  Returns the split count actually used in *n_split_out (<= max_split). */
 int vb_linear_decode_splits(int64_t N, int64_t K, int max_split);   /* pure query: the split count vb_linear_decode uses */
+/* flags: VB_FLAG_LATE_TRIGGER -- programmatic dependent launch: the kernel lets its successor start only after it has
+ * itself waited for its predecessor, so the successor's pre-wait code may read anything written before this kernel
+ * (used for the QKV GEMM, whose successor vb_attn_decode_paged prefetches KV pages before waiting). */
+enum { VB_FLAG_LATE_TRIGGER = 1, VB_FLAG_PREFETCH_KV = 2 };
 int vb_linear_decode(const void* x, int64_t ldx, const void* w, int64_t ldw, float* part, int64_t part_stride,
-                     int64_t M, int64_t N, int64_t K, int max_split, int* n_split_out, void* stream);
+                     int64_t M, int64_t N, int64_t K, int max_split, int flags, int* n_split_out, void* stream);
 
 /* ---- K5/K6: attention -------------------------------------------------------------------------------------------- */
 /* General attention over strided q/k/v (element strides), fp32 or bf16 I/O, fp32 math (SIMT).
@@ -133,9 +137,12 @@ int vb_kv_scatter_paged(const void* qkv, int qkv_dtype, void* pool, int pool_dty
  * Split-T (flash-decoding): grid (n_tsplit, H, B); partials in ws (>= vb_attn_decode_ws_bytes), the last CTA of each
  * (b,h) merges them -- no second launch.  o: o_dtype [B][H*Dh].  Dh must be 64, page_size 64. */
 int64_t vb_attn_decode_ws_bytes(int B, int H, int n_tsplit);
+/* flags: VB_FLAG_PREFETCH_KV -- the producer warp starts streaming KV pages BEFORE waiting on the predecessor kernel
+ * (PDL).  Only legal when seq_lens / block_table / cached positions were written before the predecessor started
+ * waiting, i.e. the predecessor is vb_linear_decode(..., VB_FLAG_LATE_TRIGGER) or any non-PDL kernel. */
 int vb_attn_decode_paged(const float* qkv_part, int n_part, int64_t part_stride, void* pool, int pool_dtype,
                          const int32_t* block_table, int max_pages, const int32_t* seq_lens,
-                         void* o, int o_dtype, int B, int H, int Dh, int n_tsplit, void* ws, void* stream);
+                         void* o, int o_dtype, int B, int H, int Dh, int n_tsplit, int flags, void* ws, void* stream);
 
 /* ---- K9-K12: logits -> temperature -> top-k -> top-p -> sample (+ log-prob) --------------------------------------- */
 /* logits[r][:] = sum_s logits_part[s*part_stride + r*row_stride + :], r < R, V <= 4096.

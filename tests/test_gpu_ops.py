@@ -148,7 +148,7 @@ def test_linear_decode(ops, M, N, K):
     w = (torch.randn(N, K, device='cuda') / math.sqrt(K)).bfloat16()
     ns_max = 32
     part = torch.full((ns_max, M, N), float('nan'), device='cuda')
-    ns = ops.linear_decode(x, w, part, M * N, ns_max)
+    ns = ops.linear_decode(x, w, part, M * N, ns_max, flags=(M % 2))     # odd M also exercises the late PDL trigger
     assert ns == ops.linear_decode_splits(N, K, ns_max) and 1 <= ns <= ns_max
     torch.cuda.synchronize()
     y = part[:ns].sum(0)
@@ -225,7 +225,8 @@ def test_attention_prefill_tc(ops, B, S, H, mode):
 
 @pytest.mark.parametrize('dt', [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize('n_tsplit', [1, 4])
-def test_attn_decode_paged(ops, dt, n_tsplit):
+@pytest.mark.parametrize('flags', [0, 2])
+def test_attn_decode_paged(ops, dt, n_tsplit, flags):
     torch.manual_seed(8)
     B, H, Dh, max_pages = 5, 4, 64, 6
     d = H * Dh
@@ -246,7 +247,7 @@ def test_attn_decode_paged(ops, dt, n_tsplit):
     ws = torch.zeros(ops.attn_decode_ws_bytes(B, H, n_tsplit) // 4 + 16, dtype=torch.int32, device='cuda')
     for rep in range(2):   # second launch checks that the split counters reset themselves
         pool_run = pool.clone()
-        ops.attn_decode_paged(part, n_part, B * 3 * d, pool_run, bt, seq, out, B, H, Dh, n_tsplit, ws)
+        ops.attn_decode_paged(part, n_part, B * 3 * d, pool_run, bt, seq, out, B, H, Dh, n_tsplit, ws, flags)
         torch.cuda.synchronize()
         qkv = (part[0] + part[1] + part[2]).view(B, 3, H, Dh)
         for b in range(B):

@@ -13,6 +13,7 @@ LIB_PATH = os.path.join(HERE, 'lib', 'libvalle_b200.so')
 VB_F32, VB_BF16 = 0, 1
 EPI_NONE, EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RESIDUAL = 0, 1, 2, 3
 MASK_NONE, MASK_PREFIX_LM, MASK_EXPLICIT = 0, 1, 2
+FLAG_LATE_TRIGGER, FLAG_PREFETCH_KV = 1, 2
 
 _p, _i, _i64, _f, _u64 = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_uint64
 
@@ -26,13 +27,13 @@ SIGNATURES = {
     'vb_reduce_bias_act': (_i, [_p, _i, _i64, _p, _i, _p, _i, _i64, _i, _p]),
     'vb_linear': (_i, [_p, _i, _i64, _p, _i, _i64, _p, _p, _i64, _p, _i, _i64, _i64, _i64, _i64, _i, _p]),
     'vb_linear_decode_splits': (_i, [_i64, _i64, _i]),
-    'vb_linear_decode': (_i, [_p, _i64, _p, _i64, _p, _i64, _i64, _i64, _i64, _i, _p, _p]),
+    'vb_linear_decode': (_i, [_p, _i64, _p, _i64, _p, _i64, _i64, _i64, _i64, _i, _i, _p, _p]),
     'vb_attention': (_i, [_p, _p, _p, _i, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _p, _i, _i64, _i64,
                           _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _i64, _i64, _i64, _p]),
     'vb_attention_prefill_tc': (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _p]),
     'vb_kv_scatter_paged': (_i, [_p, _i, _p, _i, _p, _i, _p, _i, _i, _i, _i, _p]),
     'vb_attn_decode_ws_bytes': (_i64, [_i, _i, _i]),
-    'vb_attn_decode_paged': (_i, [_p, _i, _i64, _p, _i, _p, _i, _p, _p, _i, _i, _i, _i, _i, _p, _p]),
+    'vb_attn_decode_paged': (_i, [_p, _i, _i64, _p, _i, _p, _i, _p, _p, _i, _i, _i, _i, _i, _i, _p, _p]),
     'vb_sample': (_i, [_p, _i, _i64, _i64, _i, _i, _f, _i, _f, _p, _u64, _p, _p, _p, _p]),
     'vb_ar_bookkeeping': (_i, [_p, _p, _p, _p, _p, _i64, _p, _p, _p, _i, _i, _p]),
 }

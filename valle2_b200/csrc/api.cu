@@ -1,5 +1,6 @@
 // Housekeeping entry points of the C ABI: version, error string, device query, TMA descriptor factory.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -27,6 +28,15 @@ int vb_sm_count() {
         cached[dev] = n;
     }
     return cached[dev];
+}
+
+bool vb_pdl_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("VALLE_B200_PDL");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v != 0;
 }
 
 extern "C" int vb_device_info(int* sm_count, int* cc_major, int* cc_minor, int64_t* smem_optin_bytes) {

@@ -50,7 +50,7 @@ __global__ void __launch_bounds__(THREADS) attn_decode_kernel(const float* __res
                                                               const int32_t* __restrict__ seq_lens, TO* __restrict__ o,
                                                               float* __restrict__ ws_o, float* __restrict__ ws_ml,
                                                               unsigned* __restrict__ counters, int H, int n_tsplit,
-                                                              float scale_log2e) {
+                                                              float scale_log2e, int prefetch_kv) {
     constexpr int LPT = PoolTraits<T>::LPT, EPL = PoolTraits<T>::EPL;
     constexpr int TPP = 32 / LPT;                       // tokens per warp pass
     constexpr int TOK_PER_WARP = PAGE / CONSUMER_WARPS; // 16
@@ -70,13 +70,7 @@ __global__ void __launch_bounds__(THREADS) attn_decode_kernel(const float* __res
     const int split = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int d_model = H * DH;
-    const int n_old = seq_lens[b];
-    const int pages_total = (n_old + PAGE - 1) / PAGE;
-    const int pp = (pages_total + n_tsplit - 1) / n_tsplit;
-    const int p0 = min(split * pp, pages_total), p1 = min(p0 + pp, pages_total);
-    const bool owns_new = (split == n_tsplit - 1);
-    const int32_t* bt = block_table + static_cast<int64_t>(b) * max_pages;
-
+    pdl_trigger();
     if (threadIdx.x == 0) {
         for (int s = 0; s < NSTAGE; ++s) {
             mbar_init(smem_u32(&full_bar[s]), 1);
@@ -84,31 +78,18 @@ __global__ void __launch_bounds__(THREADS) attn_decode_kernel(const float* __res
         }
         fence_mbar_init();
     }
-    // new-token q (and k, v for the owner of the last split): fixed-order reduction of the split-K partials
-    if (threadIdx.x < DH) {
-        const int e = threadIdx.x;
-        const float* src = qkv_part + static_cast<int64_t>(b) * 3 * d_model + h * DH + e;
-        float qv = 0.f, kv = 0.f, vv = 0.f;
-        for (int s = 0; s < n_part; ++s) {
-            qv += src[s * part_stride];
-            if (owns_new) { kv += src[s * part_stride + d_model]; vv += src[s * part_stride + 2 * d_model]; }
-        }
-        q_s[e] = qv * scale_log2e;
-        if (owns_new) {
-            const T kq = from_f32<T>(kv), vq = from_f32<T>(vv);   // the cache precision is what later steps will read
-            k_s[e] = to_f32<T>(kq);
-            v_s[e] = to_f32<T>(vq);
-            const int page = bt[n_old / PAGE], slot = n_old % PAGE;
-            T* kdst = pool + ((static_cast<int64_t>(page) * 2 * H + h) * PAGE + slot) * DH + e;
-            kdst[0] = kq;
-            kdst[static_cast<int64_t>(H) * PAGE * DH] = vq;
-        }
-    }
     __syncthreads();
+    const int32_t* bt = block_table + static_cast<int64_t>(b) * max_pages;
+    const bool owns_new = (split == n_tsplit - 1);
 
     if (warp == CONSUMER_WARPS) {
-        // ---------------- producer ----------------
+        // ---------------- producer: starts streaming KV pages as early as the caller allows ----------------
         if (lane == 0) {
+            if (!prefetch_kv) pdl_wait();     // with VB_FLAG_PREFETCH_KV the cached pages are known to be final already
+            const int n_old = seq_lens[b];
+            const int pages_total = (n_old + PAGE - 1) / PAGE;
+            const int pp = (pages_total + n_tsplit - 1) / n_tsplit;
+            const int p0 = min(split * pp, pages_total), p1 = min(p0 + pp, pages_total);
             int stage = 0;
             uint32_t phase = 0;
             for (int p = p0; p < p1; ++p) {
@@ -122,8 +103,39 @@ __global__ void __launch_bounds__(THREADS) attn_decode_kernel(const float* __res
                 bulk_load_1d(dst + CHUNK_BYTES, ksrc + static_cast<int64_t>(H) * PAGE * DH, CHUNK_BYTES, fb);
                 if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
             }
+            if (prefetch_kv) pdl_wait();      // every thread of the CTA passes the dependency before it exits
         }
-        // the producer warp still takes part in the block-level syncs below
+    }
+
+    int n_old = 0, p0 = 0, p1 = 0;
+    if (warp < CONSUMER_WARPS) {
+        pdl_wait();     // q/k/v partials of the new token come from the predecessor (QKV GEMM)
+        n_old = seq_lens[b];
+        const int pages_total = (n_old + PAGE - 1) / PAGE;
+        const int pp = (pages_total + n_tsplit - 1) / n_tsplit;
+        p0 = min(split * pp, pages_total);
+        p1 = min(p0 + pp, pages_total);
+        // new-token q (and k, v for the owner of the last split): fixed-order reduction of the split-K partials
+        if (threadIdx.x < DH) {
+            const int e = threadIdx.x;
+            const float* src = qkv_part + static_cast<int64_t>(b) * 3 * d_model + h * DH + e;
+            float qv = 0.f, kv = 0.f, vv = 0.f;
+            for (int s = 0; s < n_part; ++s) {
+                qv += src[s * part_stride];
+                if (owns_new) { kv += src[s * part_stride + d_model]; vv += src[s * part_stride + 2 * d_model]; }
+            }
+            q_s[e] = qv * scale_log2e;
+            if (owns_new) {
+                const T kq = from_f32<T>(kv), vq = from_f32<T>(vv);   // the cache precision is what later steps will read
+                k_s[e] = to_f32<T>(kq);
+                v_s[e] = to_f32<T>(vq);
+                const int page = bt[n_old / PAGE], slot = n_old % PAGE;
+                T* kdst = pool + ((static_cast<int64_t>(page) * 2 * H + h) * PAGE + slot) * DH + e;
+                kdst[0] = kq;
+                kdst[static_cast<int64_t>(H) * PAGE * DH] = vq;
+            }
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(CONSUMER_WARPS * 32) : "memory");   // consumer warps only
     }
 
     float m_run = -INFINITY, l_run = 0.f;
@@ -272,7 +284,7 @@ extern "C" int64_t vb_attn_decode_ws_bytes(int B, int H, int n_tsplit) {
 
 extern "C" int vb_attn_decode_paged(const float* qkv_part, int n_part, int64_t part_stride, void* pool, int pool_dtype,
                                     const int32_t* block_table, int max_pages, const int32_t* seq_lens, void* o,
-                                    int o_dtype, int B, int H, int Dh, int n_tsplit, void* ws, void* stream) {
+                                    int o_dtype, int B, int H, int Dh, int n_tsplit, int flags, void* ws, void* stream) {
     VB_REQUIRE(qkv_part && pool && block_table && seq_lens && o, VB_ERR_BAD_ARG, "vb_attn_decode_paged: null pointer");
     VB_REQUIRE(Dh == DH, VB_ERR_UNSUPPORTED, "vb_attn_decode_paged: head_dim must be 64 (got %d)", Dh);
     VB_REQUIRE(B >= 1 && B <= 65535 && H >= 1 && H <= 65535 && n_part >= 1 && n_tsplit >= 1, VB_ERR_BAD_ARG,
@@ -293,15 +305,14 @@ extern "C" int vb_attn_decode_paged(const float* qkv_part, int n_part, int64_t p
             VB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));                   \
             configured = true;                                                                                        \
         }                                                                                                             \
-        kern<<<grid, THREADS, SMEM, st>>>(qkv_part, n_part, part_stride, static_cast<T*>(pool), block_table,           \
-                                          max_pages, seq_lens, static_cast<TO*>(o), ws_o, ws_ml, counters, H,         \
-                                          n_tsplit, scale_log2e);                                                     \
+        VB_CUDA(vb_launch(true, kern, grid, dim3(THREADS), SMEM, st, qkv_part, n_part, part_stride, static_cast<T*>(pool),   \
+                          block_table, max_pages, seq_lens, static_cast<TO*>(o), ws_o, ws_ml, counters, H, n_tsplit,  \
+                          scale_log2e, (flags & VB_FLAG_PREFETCH_KV) ? 1 : 0));                                       \
     }
     if (pool_dtype == VB_BF16 && o_dtype == VB_BF16) DEC(__nv_bfloat16, __nv_bfloat16, NSTAGE * 2 * PAGE * DH * 2)
     else if (pool_dtype == VB_BF16 && o_dtype == VB_F32) DEC(__nv_bfloat16, float, NSTAGE * 2 * PAGE * DH * 2)
     else if (pool_dtype == VB_F32 && o_dtype == VB_F32) DEC(float, float, NSTAGE * 2 * PAGE * DH * 4)
     else VB_REQUIRE(false, VB_ERR_UNSUPPORTED, "vb_attn_decode_paged: dtype combination pool=%d o=%d", pool_dtype, o_dtype);
 #undef DEC
-    VB_LAUNCH_CHECK();
     return VB_OK;
 }

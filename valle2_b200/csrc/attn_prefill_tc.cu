@@ -47,13 +47,8 @@ __global__ void __launch_bounds__(THREADS, 2) attn_prefill_tc_kernel(const __gri
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
     const int d = H * DH;
+    pdl_trigger();
     const int i0 = qt * BQ;
-    const int kv_len = kv_lens ? min(kv_lens[b], S) : S;
-    const int x_len = (mask_mode == VB_MASK_PREFIX_LM) ? x_lens[b] : 0;
-    // keys any row of this tile may attend: everything (no mask) or the text prefix plus the causal part
-    int k_end = kv_len;
-    if (mask_mode == VB_MASK_PREFIX_LM) k_end = min(kv_len, max(x_len, i0 + BQ));
-    const int nb = max(1, (k_end + BKV - 1) / BKV);
 
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t q_smem = base;
@@ -80,6 +75,13 @@ __global__ void __launch_bounds__(THREADS, 2) attn_prefill_tc_kernel(const __gri
     tc_fence_after();
     const uint32_t tmem_base = tmem_slot;
     const int row0 = b * S;   // first row of this batch in the packed [B*S][3d] matrix
+    pdl_wait();               // qkv / lens are produced by earlier kernels; the set-up above overlapped their tail
+    const int kv_len = kv_lens ? min(kv_lens[b], S) : S;
+    const int x_len = (mask_mode == VB_MASK_PREFIX_LM) ? x_lens[b] : 0;
+    // keys any row of this tile may attend: everything (no mask) or the text prefix plus the causal part
+    int k_end = kv_len;
+    if (mask_mode == VB_MASK_PREFIX_LM) k_end = min(kv_len, max(x_len, i0 + BQ));
+    const int nb = max(1, (k_end + BKV - 1) / BKV);
 
     if (warp == 0) {
         if (elect_one()) {
@@ -260,8 +262,7 @@ extern "C" int vb_attention_prefill_tc(const void* qkv, void* o, int B, int S, i
     }
     dim3 grid(static_cast<unsigned>(vb_ceil_div(S, BQ)), H, B);
     const float scale_log2e = 1.4426950408889634f / sqrtf(static_cast<float>(DH));
-    attn_prefill_tc_kernel<<<grid, THREADS, SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(
-        tq, tkv, static_cast<__nv_bfloat16*>(o), S, H, mask_mode, x_lens, kv_lens, scale_log2e);
-    VB_LAUNCH_CHECK();
+    VB_CUDA(vb_launch(false, attn_prefill_tc_kernel, grid, dim3(THREADS), SMEM_BYTES, static_cast<cudaStream_t>(stream), tq, tkv,
+                      static_cast<__nv_bfloat16*>(o), S, H, mask_mode, x_lens, kv_lens, scale_log2e));
     return VB_OK;
 }

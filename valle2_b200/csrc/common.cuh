@@ -39,6 +39,23 @@ void vb_set_error(const char* fmt, ...);
 static inline int64_t vb_ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 int vb_sm_count();   // cached cudaDevAttrMultiProcessorCount of the current device
+bool vb_pdl_enabled();   // VALLE_B200_PDL != 0 (default on)
+
+// Kernel launch with the programmatic-dependent-launch attribute (captured as a programmatic edge in CUDA graphs).
+template <typename... Exp, typename... Act>
+static inline cudaError_t vb_launch(bool pdl, void (*kern)(Exp...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Act&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = (pdl && vb_pdl_enabled()) ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<Exp>(args)...);
+}
 
 // ------------------------------------------------------------------------------------------------
 // device: scalar conversion
@@ -111,6 +128,13 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         if (++spins > (1u << 22)) __trap();
     }
 }
+
+// Programmatic dependent launch (PDL): a kernel launched with the programmatic-serialization attribute may start
+// while its predecessor in the stream is still running.  pdl_trigger() lets OUR successor start early; pdl_wait()
+// blocks until the predecessor grid has completed and its writes are visible.  Before pdl_wait() a kernel may only
+// touch immutable data (weights, tensor maps) and its own shared memory / TMEM.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 // TMA: 2D/3D tiled load global -> shared, completion on an mbarrier
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {

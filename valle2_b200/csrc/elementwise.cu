@@ -10,6 +10,8 @@ __global__ void embed_sum_pe_kernel(const int32_t* __restrict__ ids, const float
                                     const float* __restrict__ pe, float* __restrict__ out, int T, int Q, int V, int d,
                                     int t_split, int nq_a, int nq_b, int pos_offset, const int32_t* __restrict__ pos_b,
                                     int max_len, int64_t out_rows_per_batch, int64_t out_row_offset) {
+    pdl_trigger();
+    pdl_wait();
     const int t = blockIdx.x, b = blockIdx.y;
     const int nq = (t < t_split) ? nq_a : nq_b;
     int pos = (pos_b ? pos_b[b] : pos_offset) + t;
@@ -40,9 +42,8 @@ extern "C" int vb_embed_sum_pe(const int32_t* ids, const float* tables, const fl
     if (B == 0 || T == 0) return VB_OK;
     VB_REQUIRE(B <= 65535, VB_ERR_BAD_ARG, "vb_embed_sum_pe: B too large");
     int threads = min(256, max(32, d / 4));
-    embed_sum_pe_kernel<<<dim3(T, B), threads, 0, static_cast<cudaStream_t>(stream)>>>(
-        ids, tables, pe, out, T, Q, V, d, t_split, nq_a, nq_b, pos_offset, pos_b, max_len, out_rows_per_batch, out_row_offset);
-    VB_LAUNCH_CHECK();
+    VB_CUDA(vb_launch(T == 1, embed_sum_pe_kernel, dim3(T, B), dim3(threads), 0, static_cast<cudaStream_t>(stream), ids, tables, pe, out,
+                      T, Q, V, d, t_split, nq_a, nq_b, pos_offset, pos_b, max_len, out_rows_per_batch, out_row_offset));
     return VB_OK;
 }
 
@@ -56,6 +57,8 @@ __global__ void __launch_bounds__(256) residual_layernorm_kernel(float* __restri
                                                                  const float* __restrict__ gamma,
                                                                  const float* __restrict__ beta, TY* __restrict__ y,
                                                                  int64_t R, int d, float eps) {
+    pdl_trigger();
+    pdl_wait();
     const int lane = threadIdx.x & 31;
     const int64_t r = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (r >= R) return;
@@ -123,6 +126,8 @@ __global__ void __launch_bounds__(256) residual_layernorm_generic_kernel(float* 
                                                                          const float* __restrict__ gamma,
                                                                          const float* __restrict__ beta, TY* __restrict__ y,
                                                                          int64_t R, int d, float eps) {
+    pdl_trigger();
+    pdl_wait();
     const int lane = threadIdx.x & 31;
     const int64_t r = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (r >= R) return;
@@ -162,6 +167,8 @@ __global__ void __launch_bounds__(256) residual_layernorm_block_kernel(float* __
                                                                        const float* __restrict__ beta, TY* __restrict__ y,
                                                                        int d, float eps) {
     __shared__ float red[8];
+    pdl_trigger();
+    pdl_wait();
     const int64_t r = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     float* xr = x + r * d;
@@ -257,23 +264,23 @@ template <typename TY>
 static int launch_rln(float* x, const float* part, int n_part, int64_t part_stride, const float* bias, const float* gamma,
                       const float* beta, TY* y, int64_t R, int d, float eps, cudaStream_t st) {
     if (R <= 1024 && d % 4 == 0 && d <= 4096) {
-        residual_layernorm_block_kernel<TY><<<static_cast<unsigned>(R), 256, 0, st>>>(x, part, n_part, part_stride, bias, gamma, beta, y, d, eps);
-        VB_LAUNCH_CHECK();
+        VB_CUDA(vb_launch(true, residual_layernorm_block_kernel<TY>, dim3(static_cast<unsigned>(R)), dim3(256), 0, st, x, part, n_part,
+                          part_stride, bias, gamma, beta, y, d, eps));
         return VB_OK;
     }
     const int warps = 8;
     const dim3 grid(static_cast<unsigned>(vb_ceil_div(R, warps)));
-#define RLN(NV) residual_layernorm_kernel<TY, NV><<<grid, warps * 32, 0, st>>>(x, part, n_part, part_stride, bias, gamma, beta, y, R, d, eps)
+#define RLN(NV) VB_CUDA(vb_launch(false, residual_layernorm_kernel<TY, NV>, grid, dim3(warps * 32), 0, st, x, part, n_part, part_stride, bias, gamma, beta, y, R, d, eps))
     switch (d) {
         case 128: RLN(1); break;
         case 256: RLN(2); break;
         case 512: RLN(4); break;
         case 1024: RLN(8); break;
         default:
-            residual_layernorm_generic_kernel<TY><<<grid, warps * 32, 0, st>>>(x, part, n_part, part_stride, bias, gamma, beta, y, R, d, eps);
+            VB_CUDA(vb_launch(false, residual_layernorm_generic_kernel<TY>, grid, dim3(warps * 32), 0, st, x, part, n_part, part_stride, bias,
+                              gamma, beta, y, R, d, eps));
     }
 #undef RLN
-    VB_LAUNCH_CHECK();
     return VB_OK;
 }
 
@@ -298,6 +305,8 @@ extern "C" int vb_residual_layernorm(float* x, const float* part, int n_part, in
 template <typename TY>
 __global__ void reduce_bias_act_kernel(const float* __restrict__ part, int n_part, int64_t part_stride,
                                        const float* __restrict__ bias, int gelu, TY* __restrict__ y, int64_t total4, int N) {
+    pdl_trigger();
+    pdl_wait();
     for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total4;
          i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
         const int64_t e = i * 4;
@@ -326,12 +335,11 @@ extern "C" int vb_reduce_bias_act(const float* part, int n_part, int64_t part_st
     const int blocks = static_cast<int>(want_blocks < cap_blocks ? want_blocks : cap_blocks);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (y_dtype == VB_F32)
-        reduce_bias_act_kernel<float><<<blocks, threads, 0, st>>>(part, n_part, part_stride, bias, gelu, static_cast<float*>(y), total4, N);
+        VB_CUDA(vb_launch(R <= 1024, reduce_bias_act_kernel<float>, dim3(blocks), dim3(threads), 0, st, part, n_part, part_stride, bias, gelu, static_cast<float*>(y), total4, N));
     else if (y_dtype == VB_BF16)
-        reduce_bias_act_kernel<__nv_bfloat16><<<blocks, threads, 0, st>>>(part, n_part, part_stride, bias, gelu, static_cast<__nv_bfloat16*>(y), total4, N);
+        VB_CUDA(vb_launch(R <= 1024, reduce_bias_act_kernel<__nv_bfloat16>, dim3(blocks), dim3(threads), 0, st, part, n_part, part_stride, bias, gelu, static_cast<__nv_bfloat16*>(y), total4, N));
     else
         VB_REQUIRE(false, VB_ERR_BAD_ARG, "vb_reduce_bias_act: bad y_dtype");
-    VB_LAUNCH_CHECK();
     return VB_OK;
 }
 
@@ -341,6 +349,8 @@ extern "C" int vb_reduce_bias_act(const float* part, int n_part, int64_t part_st
 template <typename TS, typename TD>
 __global__ void kv_scatter_kernel(const TS* __restrict__ qkv, TD* __restrict__ pool, const int32_t* __restrict__ block_table,
                                   int max_pages, const int32_t* __restrict__ kv_lens, int S, int H, int Dh) {
+    pdl_trigger();
+    pdl_wait();
     const int s = blockIdx.x, b = blockIdx.y;
     if (s >= kv_lens[b]) return;
     const int page = block_table[b * max_pages + (s >> 6)];
@@ -362,13 +372,12 @@ extern "C" int vb_kv_scatter_paged(const void* qkv, int qkv_dtype, void* pool, i
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     dim3 grid(S, B);
     const int threads = 256;
-#define KVS(TS, TD) kv_scatter_kernel<TS, TD><<<grid, threads, 0, st>>>(static_cast<const TS*>(qkv), static_cast<TD*>(pool), block_table, max_pages, kv_lens, S, H, Dh)
+#define KVS(TS, TD) VB_CUDA(vb_launch(false, kv_scatter_kernel<TS, TD>, grid, dim3(threads), 0, st, static_cast<const TS*>(qkv), static_cast<TD*>(pool), block_table, max_pages, kv_lens, S, H, Dh))
     if (qkv_dtype == VB_F32 && pool_dtype == VB_F32) KVS(float, float);
     else if (qkv_dtype == VB_BF16 && pool_dtype == VB_BF16) KVS(__nv_bfloat16, __nv_bfloat16);
     else if (qkv_dtype == VB_F32 && pool_dtype == VB_BF16) KVS(float, __nv_bfloat16);
     else VB_REQUIRE(false, VB_ERR_UNSUPPORTED, "vb_kv_scatter_paged: dtype combination %d -> %d", qkv_dtype, pool_dtype);
 #undef KVS
-    VB_LAUNCH_CHECK();
     return VB_OK;
 }
 
@@ -380,6 +389,8 @@ __global__ void ar_bookkeeping_kernel(const int32_t* __restrict__ sample, const 
                                       int32_t* __restrict__ codes_out, int64_t codes_stride, int32_t* __restrict__ seq_lens,
                                       int32_t* __restrict__ audio_pos, int32_t* __restrict__ state, int B, int eos) {
     __shared__ int not_eos;
+    pdl_trigger();
+    pdl_wait();
     if (threadIdx.x == 0) not_eos = 0;
     __syncthreads();
     const int step = state[0];
@@ -409,8 +420,7 @@ extern "C" int vb_ar_bookkeeping(const int32_t* sample, const float* logprob, in
     VB_REQUIRE(sample && logprob && last && sum_logprobs && codes_out && seq_lens && audio_pos && state, VB_ERR_BAD_ARG,
                "vb_ar_bookkeeping: null pointer");
     VB_REQUIRE(B > 0, VB_ERR_BAD_ARG, "vb_ar_bookkeeping: B must be > 0");
-    ar_bookkeeping_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(sample, logprob, last, sum_logprobs, codes_out,
-                                                                           codes_stride, seq_lens, audio_pos, state, B, eos);
-    VB_LAUNCH_CHECK();
+    VB_CUDA(vb_launch(true, ar_bookkeeping_kernel, dim3(1), dim3(256), 0, static_cast<cudaStream_t>(stream), sample, logprob, last,
+                      sum_logprobs, codes_out, codes_stride, seq_lens, audio_pos, state, B, eos));
     return VB_OK;
 }

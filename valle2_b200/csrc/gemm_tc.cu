@@ -32,6 +32,7 @@ struct GemmParams {
     float* part;
     int64_t part_stride;
     int64_t part_ld;           // N (row pitch of a partial slice)
+    int late_trigger;          // release the dependent kernel only after our own pdl_wait (see vb_linear_decode flags)
 };
 
 template <int BN, int STAGES, bool SWAP>
@@ -74,28 +75,58 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
 
     const int total_tiles = p.tiles_a * p.tiles_b * p.n_split;
 
+    if (!p.late_trigger) pdl_trigger();
     if (warp == 0) {
         if (elect_one()) {
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-                int ta, tb, split;
+            // The weight operand (A when SWAP, else B) is immutable, so its tiles are requested BEFORE waiting on the
+            // predecessor kernel (PDL): the weight stream of this GEMM overlaps the tail of whatever runs before it.
+            // The activation operand of the same ring slots is requested after pdl_wait(); each slot's mbarrier
+            // expects the bytes of both tiles.
+            auto tile_of = [&](int t, int& ta, int& tb, int& kb0, int& kb1) {
+                int split;
                 if (SWAP) { ta = t % p.tiles_a; split = t / p.tiles_a; tb = 0; }
                 else      { tb = t % p.tiles_b; ta = t / p.tiles_b; split = 0; }
-                const int kb0 = split * p.kb_per_split;
-                const int kb1 = min(kb0 + p.kb_per_split, p.kb_total);
-                for (int kb = kb0; kb < kb1; ++kb) {
-                    mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
-                    const uint32_t fb = smem_u32(&full_bar[stage]);
+                kb0 = split * p.kb_per_split;
+                kb1 = min(kb0 + p.kb_per_split, p.kb_total);
+            };
+            int pre = 0;   // ring slots already armed with their weight tile
+            for (int t = blockIdx.x; t < total_tiles && pre < STAGES; t += gridDim.x) {
+                int ta, tb, kb0, kb1;
+                tile_of(t, ta, tb, kb0, kb1);
+                for (int kb = kb0; kb < kb1 && pre < STAGES; ++kb, ++pre) {
+                    const uint32_t fb = smem_u32(&full_bar[pre]);
                     mbar_expect_tx(fb, STAGE_BYTES);
+                    const uint32_t sa = smem_base + pre * STAGE_BYTES;
+                    if (SWAP) tma_load_2d(sa, &tm_a, fb, kb * BK, ta * BM);
+                    else      tma_load_2d(sa + A_BYTES, &tm_b, fb, kb * BK, tb * BN);
+                }
+            }
+            pdl_wait();
+            if (p.late_trigger) pdl_trigger();
+            int stage = 0, n = 0;
+            uint32_t phase = 0;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+                int ta, tb, kb0, kb1;
+                tile_of(t, ta, tb, kb0, kb1);
+                for (int kb = kb0; kb < kb1; ++kb, ++n) {
+                    const uint32_t fb = smem_u32(&full_bar[stage]);
                     const uint32_t sa = smem_base + stage * STAGE_BYTES;
-                    tma_load_2d(sa, &tm_a, fb, kb * BK, ta * BM);
-                    tma_load_2d(sa + A_BYTES, &tm_b, fb, kb * BK, tb * BN);
+                    if (n < pre) {      // weight tile already in flight: only the activation tile is missing
+                        if (SWAP) tma_load_2d(sa + A_BYTES, &tm_b, fb, kb * BK, tb * BN);
+                        else      tma_load_2d(sa, &tm_a, fb, kb * BK, ta * BM);
+                    } else {
+                        mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+                        mbar_expect_tx(fb, STAGE_BYTES);
+                        tma_load_2d(sa, &tm_a, fb, kb * BK, ta * BM);
+                        tma_load_2d(sa + A_BYTES, &tm_b, fb, kb * BK, tb * BN);
+                    }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
         }
+        else if (p.late_trigger) { pdl_wait(); pdl_trigger(); }
     } else if (warp == 1) {
+        if (p.late_trigger) { pdl_wait(); pdl_trigger(); }
         if (elect_one()) {
             int stage = 0;
             uint32_t phase = 0;
@@ -128,6 +159,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
     } else {
         const int q = warp & 3;  // TMEM lane quadrant this warp may access
         int local = 0;
+        pdl_wait();              // residual reads / output writes must not overtake the predecessor kernel
+        if (p.late_trigger) pdl_trigger();
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++local) {
             int ta, tb, split;
             if (SWAP) { ta = t % p.tiles_a; split = t / p.tiles_a; tb = 0; }
@@ -250,8 +283,7 @@ int launch_gemm_tc(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParam
     }
     const int total = p.tiles_a * p.tiles_b * p.n_split;
     const int grid = min(total, vb_sm_count());
-    kern<<<grid, NUM_THREADS, SMEM, st>>>(ta, tb, p);
-    VB_LAUNCH_CHECK();
+    VB_CUDA(vb_launch(SWAP, kern, dim3(grid), dim3(NUM_THREADS), SMEM, st, ta, tb, p));
     return VB_OK;
 }
 
@@ -296,7 +328,7 @@ extern "C" int vb_linear_decode_splits(int64_t N, int64_t K, int max_split) {
 }
 
 extern "C" int vb_linear_decode(const void* x, int64_t ldx, const void* w, int64_t ldw, float* part, int64_t part_stride,
-                                int64_t M, int64_t N, int64_t K, int max_split, int* n_split_out, void* stream) {
+                                int64_t M, int64_t N, int64_t K, int max_split, int flags, int* n_split_out, void* stream) {
     VB_REQUIRE(x && w && part, VB_ERR_BAD_ARG, "vb_linear_decode: null pointer");
     VB_REQUIRE(M >= 1 && M <= 256, VB_ERR_UNSUPPORTED, "vb_linear_decode: M must be in [1,256] (got %lld)", (long long)M);
     VB_REQUIRE(K % 8 == 0 && N >= 1, VB_ERR_UNSUPPORTED, "vb_linear_decode: K %% 8 != 0 or N < 1");
@@ -310,6 +342,7 @@ extern "C" int vb_linear_decode(const void* x, int64_t ldx, const void* w, int64
     p.kb_per_split = (int)vb_ceil_div(p.kb_total, n_split);
     p.n_split = n_split;
     p.part = part; p.part_stride = part_stride; p.part_ld = N;
+    p.late_trigger = (flags & VB_FLAG_LATE_TRIGGER) ? 1 : 0;
     VB_REQUIRE(n_split == 1 || part_stride >= M * N, VB_ERR_BAD_ARG, "vb_linear_decode: part_stride too small");
     if (n_split_out) *n_split_out = n_split;
     CUtensorMap ta, tb;
@@ -320,10 +353,10 @@ extern "C" int vb_linear_decode(const void* x, int64_t ldx, const void* w, int64
         if ((rc = vb_make_tmap_bf16_2d(&tb, x, M, K, ldx, BNV, BK)) != VB_OK) return rc; \
         return launch_gemm_tc<BNV, ST, true>(ta, tb, p, st);                             \
     }
-    if (M <= 16) DECODE_CASE(16, 8)
-    if (M <= 32) DECODE_CASE(32, 8)
-    if (M <= 64) DECODE_CASE(64, 8)
-    if (M <= 128) DECODE_CASE(128, 6)
+    if (M <= 16) DECODE_CASE(16, 4)
+    if (M <= 32) DECODE_CASE(32, 4)
+    if (M <= 64) DECODE_CASE(64, 4)
+    if (M <= 128) DECODE_CASE(128, 4)
     DECODE_CASE(256, 4)
 #undef DECODE_CASE
 }

@@ -56,6 +56,8 @@ __global__ void __launch_bounds__(THREADS) sample_kernel(const float* __restrict
     __shared__ int pick;
     __shared__ float warp_tot[THREADS / 32];
 
+    pdl_trigger();
+    pdl_wait();
     const int r = blockIdx.x, tid = threadIdx.x;
     const float* src = logits_part + static_cast<int64_t>(r) * row_stride;
     for (int i = tid; i < V; i += THREADS) {
@@ -217,9 +219,7 @@ extern "C" int vb_sample(const float* logits_part, int n_part, int64_t part_stri
     VB_REQUIRE(V >= 1 && V <= MAX_V, VB_ERR_UNSUPPORTED, "vb_sample: vocabulary %d not in [1,%d]", V, MAX_V);
     VB_REQUIRE(R >= 0 && n_part >= 1 && temperature > 0.f, VB_ERR_BAD_ARG, "vb_sample: bad args");
     if (R == 0) return VB_OK;
-    sample_kernel<<<R, THREADS, 0, static_cast<cudaStream_t>(stream)>>>(logits_part, n_part, part_stride, row_stride, V,
-                                                                       temperature, top_k, top_p, uniforms, seed,
-                                                                       step_ptr, out_tok, out_logprob);
-    VB_LAUNCH_CHECK();
+    VB_CUDA(vb_launch(R <= 1024, sample_kernel, dim3(R), dim3(THREADS), 0, static_cast<cudaStream_t>(stream), logits_part, n_part, part_stride,
+                      row_stride, V, temperature, top_k, top_p, uniforms, seed, step_ptr, out_tok, out_logprob));
     return VB_OK;
 }

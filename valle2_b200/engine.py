@@ -214,9 +214,10 @@ class ARDecoder:
                 else:
                     ops.residual_layernorm(x, g[0], b[0], st['h'], part=st['p_f2'], n_part=ns['f2'],
                                            part_stride=B * d, bias=layers[li - 1]['b2'], eps=eps)
-                ops.linear_decode(st['h'], L['wqkv'], st['p_qkv'], B * 3 * d, 32)
+                ops.linear_decode(st['h'], L['wqkv'], st['p_qkv'], B * 3 * d, 32, ops.FLAG_LATE_TRIGGER)
                 ops.attn_decode_paged(st['p_qkv'], ns['qkv'], B * 3 * d, st['pools'][li], st['block_table'],
-                                      st['seq_lens'], st['o'], B, H, Dh, st['n_tsplit'], st['attn_ws'])
+                                      st['seq_lens'], st['o'], B, H, Dh, st['n_tsplit'], st['attn_ws'],
+                                      ops.FLAG_PREFETCH_KV)
                 ops.linear_decode(st['o'], L['wo'], st['p_o'], B * d, 32)
                 g, b, eps = L['norm2']
                 ops.residual_layernorm(x, g[0], b[0], st['h'], part=st['p_o'], n_part=ns['o'], part_stride=B * d,

@@ -11,7 +11,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import (EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RESIDUAL, EPI_NONE, MASK_EXPLICIT, MASK_NONE,
+from ._lib import (FLAG_LATE_TRIGGER, FLAG_PREFETCH_KV, EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RESIDUAL, EPI_NONE, MASK_EXPLICIT, MASK_NONE,
                    MASK_PREFIX_LM, VB_BF16, VB_F32, check)
 
 __all__ = ['EPI_NONE', 'EPI_BIAS', 'EPI_BIAS_GELU', 'EPI_BIAS_RESIDUAL', 'MASK_NONE', 'MASK_PREFIX_LM',
@@ -118,14 +118,15 @@ def linear_decode_splits(N: int, K: int, max_split: int) -> int:
     return int(_L().vb_linear_decode_splits(N, K, max_split))
 
 
-def linear_decode(x: torch.Tensor, w: torch.Tensor, part: torch.Tensor, part_stride: int, max_split: int) -> int:
+def linear_decode(x: torch.Tensor, w: torch.Tensor, part: torch.Tensor, part_stride: int, max_split: int,
+                  flags: int = 0) -> int:
     """part[s][m][n] (fp32) = split-K slices of x @ w.T; x (M<=256,K) bf16, w (N,K) bf16.  Returns n_split."""
     assert x.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and part.dtype == torch.float32
     M, K = x.shape
     N = w.shape[0]
     ns = C.c_int()
     check(_L().vb_linear_decode(_ptr(x), x.stride(0), _ptr(w), w.stride(0), _ptr(part), part_stride, M, N, K,
-                                max_split, C.byref(ns), _stream()), 'vb_linear_decode')
+                                max_split, flags, C.byref(ns), _stream()), 'vb_linear_decode')
     return ns.value
 
 
@@ -186,10 +187,10 @@ def attn_decode_ws_bytes(B: int, H: int, n_tsplit: int) -> int:
 
 def attn_decode_paged(qkv_part: torch.Tensor, n_part: int, part_stride: int, pool: torch.Tensor,
                       block_table: torch.Tensor, seq_lens: torch.Tensor, out: torch.Tensor, B: int, H: int, Dh: int,
-                      n_tsplit: int, ws: torch.Tensor | None) -> None:
+                      n_tsplit: int, ws: torch.Tensor | None, flags: int = 0) -> None:
     check(_L().vb_attn_decode_paged(_ptr(qkv_part), n_part, part_stride, _ptr(pool), _code(pool.dtype),
                                     _ptr(block_table), block_table.shape[1], _ptr(seq_lens), _ptr(out),
-                                    _code(out.dtype), B, H, Dh, n_tsplit, _ptr(ws), _stream()),
+                                    _code(out.dtype), B, H, Dh, n_tsplit, flags, _ptr(ws), _stream()),
           'vb_attn_decode_paged')
 
 
