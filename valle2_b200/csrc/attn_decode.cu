@@ -18,7 +18,7 @@ namespace {
 
 constexpr int DH = 64;
 constexpr int PAGE = 64;
-constexpr int NSTAGE = 4;
+constexpr int NSTAGE = 3;
 constexpr int CONSUMER_WARPS = 4;
 constexpr int THREADS = (CONSUMER_WARPS + 1) * 32;
 
