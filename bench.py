@@ -395,6 +395,8 @@ def main():
             print(json.dumps(res), flush=True)
         return 0
     if world > 1:
+        if os.environ.get('NCCL_DEBUG', '').upper() == 'VERSION':
+            os.environ['NCCL_DEBUG'] = 'WARN'      # keep stdout to the single JSON line
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         torch.cuda.set_device(local_rank)
         torch.distributed.init_process_group('nccl', device_id=torch.device('cuda', local_rank))

@@ -9,7 +9,8 @@
 //   warp 2-5  softmax: one thread per query row (tcgen05.ld 32x32b gives a thread its whole row -> no shuffles):
 //             online max/sum in the exp2 domain, P_j written as bf16 into a 128B-swizzled smem tile (the A operand of
 //             PV_j), running output kept in registers and rescaled by exp2(m_old - m_new).
-// Two CTAs are resident per SM (80 KB smem, 128 TMEM columns each) so one CTA's softmax overlaps the other's MMAs.
+// Three CTAs are resident per SM (65 KB smem, 128 TMEM columns, <= 112 registers each) so the softmax of one CTA
+// overlaps the MMAs and TMEM loads of the others.
 // Replaces F.scaled_dot_product_attention + merge_masks on modules.py:160-167 for S > 1.
 #include <math.h>
 
@@ -20,7 +21,7 @@ namespace {
 constexpr int BQ = 128;    // query rows per CTA
 constexpr int BKV = 64;    // keys per block
 constexpr int DH = 64;
-constexpr int KV_STAGES = 3;
+constexpr int KV_STAGES = 2;
 constexpr int THREADS = 192;
 constexpr int Q_BYTES = BQ * DH * 2;          // 16 KB
 constexpr int KV_BYTES = BKV * DH * 2;        // 8 KB each for K and V
@@ -34,7 +35,7 @@ __device__ __forceinline__ float fast_exp2(float x) {
     return y;
 }
 
-__global__ void __launch_bounds__(THREADS, 2) attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tm_q,
+__global__ void __launch_bounds__(THREADS, 3) attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tm_q,
                                                                      const __grid_constant__ CUtensorMap tm_kv,
                                                                      __nv_bfloat16* __restrict__ o, int S, int H, int mask_mode,
                                                                      const int32_t* __restrict__ x_lens,
@@ -90,7 +91,7 @@ __global__ void __launch_bounds__(THREADS, 2) attn_prefill_tc_kernel(const __gri
             int stage = 0;
             uint32_t phase = 0;
             for (int j = 0; j < nb; ++j) {
-                mbar_wait(smem_u32(&kv_empty[stage]), phase ^ 1);
+                mbar_wait_relaxed(smem_u32(&kv_empty[stage]), phase ^ 1);
                 const uint32_t fb = smem_u32(&kv_full[stage]);
                 mbar_expect_tx(fb, 2 * KV_BYTES);
                 const uint32_t dst = kv_smem + stage * 2 * KV_BYTES;
@@ -104,26 +105,26 @@ __global__ void __launch_bounds__(THREADS, 2) attn_prefill_tc_kernel(const __gri
             constexpr uint32_t IDESC_QK = umma_idesc_bf16(BQ, BKV, 0, 0);   // A = Q (K-major), B = K block (K-major)
             constexpr uint32_t IDESC_PV = umma_idesc_bf16(BQ, DH, 0, 1);    // A = P (K-major), B = V block (MN-major)
             const uint32_t s_tmem = tmem_base, o_tmem = tmem_base + BKV;
-            mbar_wait(smem_u32(&bar_q), 0);
+            mbar_wait_relaxed(smem_u32(&bar_q), 0);
             int stage = 0;
             uint32_t phase = 0;
             auto issue_pv = [&](int jj, int st) {
-                mbar_wait(smem_u32(&bar_p), jj & 1);
+                mbar_wait_relaxed(smem_u32(&bar_p), jj & 1);
                 tc_fence_after();
                 const uint32_t v_s = kv_smem + st * 2 * KV_BYTES + KV_BYTES;
 #pragma unroll
                 for (int kk = 0; kk < BKV / 16; ++kk) {
                     const uint64_t da = umma_desc_sw128(p_smem + kk * 32, 16, 1024);
                     const uint64_t db = umma_desc_sw128(v_s + kk * 16 * 128, 1024, 1024);
-                    umma_f16(o_tmem, da, db, IDESC_PV, kk > 0 ? 1u : 0u);
+                    umma_f16(o_tmem, da, db, IDESC_PV, (jj > 0 || kk > 0) ? 1u : 0u);
                 }
                 umma_commit(smem_u32(&kv_empty[st]));
                 umma_commit(smem_u32(&bar_o));
             };
             int prev_stage = 0;
             for (int j = 0; j < nb; ++j) {
-                mbar_wait(smem_u32(&kv_full[stage]), phase);
-                mbar_wait(smem_u32(&bar_sfree), (j & 1) ^ 1);
+                mbar_wait_relaxed(smem_u32(&kv_full[stage]), phase);
+                mbar_wait_relaxed(smem_u32(&bar_sfree), (j & 1) ^ 1);
                 tc_fence_after();
                 const uint32_t k_s = kv_smem + stage * 2 * KV_BYTES;
 #pragma unroll
@@ -144,67 +145,111 @@ __global__ void __launch_bounds__(THREADS, 2) attn_prefill_tc_kernel(const __gri
         const int r = q * 32 + lane;          // row within the tile == TMEM lane
         const int i = i0 + r;                 // query index within the sequence
         const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-        float m_run = -INFINITY, l_run = 0.f;
-        float acc[DH];
-#pragma unroll
-        for (int e = 0; e < DH; ++e) acc[e] = 0.f;
+        // O accumulates in TMEM across key blocks (PV MMAs with accumulate = 1).  The softmax reference m_ref is only
+        // raised when the block maximum exceeds it by more than 2^8 ("lazy rescaling"): then O and l are multiplied by
+        // exp2(m_ref - m_new) -- a TMEM load/scale/store done by the whole warp if any of its rows needs it.  Otherwise
+        // p = exp2(s - m_ref) <= 256, which bf16 / fp32 hold comfortably, and no per-block traffic on O is needed.
+        float m_ref = -INFINITY, l_run = 0.f;
         const uint32_t p_row = p_smem + r * 128;
         for (int j = 0; j < nb; ++j) {
             mbar_wait(smem_u32(&bar_s), j & 1);
             tc_fence_after();
-            uint32_t sv[BKV];
-            tmem_ld_32x32(lane_addr, reinterpret_cast<uint32_t(&)[32]>(sv[0]));
-            tmem_ld_32x32(lane_addr + 32, reinterpret_cast<uint32_t(&)[32]>(sv[32]));
-            tmem_ld_wait();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(&bar_sfree));
-            // scale into the exp2 domain, mask, row max
+            // pass 1 over S_j (two 32-column TMEM loads, nothing kept): the row maximum of the raw scores
+            // (scale > 0 commutes with max); masking only where the block needs it.  S_j is read again in pass 2 so
+            // that only 32 scores are live at a time -- 3 CTAs fit per SM (registers) and hide each other's latencies.
             const int kbase = j * BKV;
+            bool need_mask = (kbase + BKV > kv_len);
+            if (mask_mode == VB_MASK_PREFIX_LM)
+                need_mask = need_mask || !((kbase + BKV <= x_len) || (i0 >= x_len && kbase + BKV - 1 <= i0));
             float mx = -INFINITY;
 #pragma unroll
-            for (int c = 0; c < BKV; ++c) {
-                const int kj = kbase + c;
-                bool ok = kj < kv_len;
-                if (mask_mode == VB_MASK_PREFIX_LM) ok = ok && ((kj < x_len) || (i >= x_len && kj <= i));
-                const float s = ok ? __uint_as_float(sv[c]) * scale_log2e : -INFINITY;
-                sv[c] = __float_as_uint(s);
-                mx = fmaxf(mx, s);
-            }
-            const float m_new = fmaxf(m_run, mx);
-            const float m_use = (m_new == -INFINITY) ? 0.f : m_new;     // fully masked so far: p = 0, no NaN
-            const float alpha = (m_run == -INFINITY) ? 0.f : fast_exp2(m_run - m_use);
-            float rs = 0.f;
-            uint32_t pk[BKV / 2];
+            for (int half = 0; half < 2; ++half) {
+                uint32_t sv[32];
+                tmem_ld_32x32(lane_addr + half * 32, sv);
+                tmem_ld_wait();
+                if (need_mask) {
 #pragma unroll
-            for (int c = 0; c < BKV; c += 2) {
-                const float p0 = fast_exp2(__uint_as_float(sv[c]) - m_use);
-                const float p1 = fast_exp2(__uint_as_float(sv[c + 1]) - m_use);
-                rs += p0 + p1;
-                pk[c >> 1] = pack_bf16x2(p0, p1);
-            }
-            // fold in PV_{j-1} (accumulated relative to the previous max), then rescale to the new max
-            if (j > 0) {
-                mbar_wait(smem_u32(&bar_o), (j - 1) & 1);
-                tc_fence_after();
-                uint32_t ov[32];
+                    for (int c = 0; c < 32; ++c) {
+                        const int kj = kbase + half * 32 + c;
+                        bool ok = kj < kv_len;
+                        if (mask_mode == VB_MASK_PREFIX_LM) ok = ok && ((kj < x_len) || (i >= x_len && kj <= i));
+                        if (ok) mx = fmaxf(mx, __uint_as_float(sv[c]));
+                    }
+                } else {
 #pragma unroll
-                for (int half = 0; half < 2; ++half) {
-                    tmem_ld_32x32(lane_addr + BKV + half * 32, ov);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int e = 0; e < 32; ++e) acc[half * 32 + e] = (acc[half * 32 + e] + __uint_as_float(ov[e])) * alpha;
+                    for (int c = 0; c < 32; ++c) mx = fmaxf(mx, __uint_as_float(sv[c]));
                 }
             }
-            l_run = l_run * alpha + rs;
-            m_run = m_new;
-            // P_j -> smem, K-major 128B-swizzled rows (chunk c of row r lives at chunk c ^ (r & 7))
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                const uint32_t addr = p_row + (static_cast<uint32_t>(c ^ (r & 7)) << 4);
-                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[c * 4]), "r"(pk[c * 4 + 1]),
-                             "r"(pk[c * 4 + 2]), "r"(pk[c * 4 + 3]) : "memory");
+            const float m_blk = mx * scale_log2e;
+            const bool grow = m_blk > m_ref + 8.0f;            // also true for the first finite block (m_ref = -inf)
+            float alpha = 1.f;
+            if (grow) {
+                alpha = (m_ref == -INFINITY) ? 0.f : fast_exp2(m_ref - m_blk);
+                m_ref = m_blk;
+                l_run *= alpha;
             }
+            if (j > 0) {
+                // PV_{j-1} must be complete before P is overwritten and before O may be corrected
+                mbar_wait(smem_u32(&bar_o), (j - 1) & 1);
+                tc_fence_after();
+                if (__any_sync(0xffffffffu, grow)) {
+                    const float2 a2 = make_float2(alpha, alpha);
+#pragma unroll
+                    for (int half = 0; half < 2; ++half) {
+                        uint32_t ov[32];
+                        tmem_ld_32x32(lane_addr + BKV + half * 32, ov);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int e = 0; e < 32; e += 2) {
+                            const float2 t = __fmul2_rn(make_float2(__uint_as_float(ov[e]), __uint_as_float(ov[e + 1])), a2);
+                            ov[e] = __float_as_uint(t.x);
+                            ov[e + 1] = __float_as_uint(t.y);
+                        }
+                        tmem_st_32x32(lane_addr + BKV + half * 32, ov);
+                    }
+                    tmem_st_wait();
+                }
+            }
+            const float m_use = (m_ref == -INFINITY) ? 0.f : m_ref;     // fully masked so far: p = 0, no NaN
+            const float2 sc2 = make_float2(scale_log2e, scale_log2e), nm2 = make_float2(-m_use, -m_use);
+            float2 rs2 = make_float2(0.f, 0.f);
+            // pass 2: p = exp2(s * scale - m_ref), row sum, bf16 pack, P_j -> smem as K-major 128B-swizzled rows
+            // (16-byte chunk c of row r lives at chunk c ^ (r & 7)); packed two-wide fp32 math (FFMA2 / FADD2)
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                uint32_t sv[32];
+                tmem_ld_32x32(lane_addr + half * 32, sv);
+                tmem_ld_wait();
+                if (half == 1) {      // S_j fully consumed: the MMA warp may overwrite it with S_{j+1}
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(smem_u32(&bar_sfree));
+                }
+                if (need_mask) {
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) {
+                        const int kj = kbase + half * 32 + c;
+                        bool ok = kj < kv_len;
+                        if (mask_mode == VB_MASK_PREFIX_LM) ok = ok && ((kj < x_len) || (i >= x_len && kj <= i));
+                        if (!ok) sv[c] = 0xff800000u;   // -inf -> p = 0
+                    }
+                }
+                uint32_t pk[16];
+#pragma unroll
+                for (int c = 0; c < 32; c += 2) {
+                    const float2 t = __ffma2_rn(make_float2(__uint_as_float(sv[c]), __uint_as_float(sv[c + 1])), sc2, nm2);
+                    const float2 pp = make_float2(fast_exp2(t.x), fast_exp2(t.y));
+                    rs2 = __fadd2_rn(rs2, pp);
+                    pk[c >> 1] = pack_bf16x2(pp.x, pp.y);
+                }
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const uint32_t addr = p_row + (static_cast<uint32_t>((half * 4 + c) ^ (r & 7)) << 4);
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[c * 4]), "r"(pk[c * 4 + 1]),
+                                 "r"(pk[c * 4 + 2]), "r"(pk[c * 4 + 3]) : "memory");
+                }
+            }
+            l_run += rs2.x + rs2.y;
             fence_proxy_async();
             tc_fence_before();
             __syncwarp();
@@ -223,10 +268,10 @@ __global__ void __launch_bounds__(THREADS, 2) attn_prefill_tc_kernel(const __gri
 #pragma unroll
                 for (int e = 0; e < 32; e += 8) {
                     uint4 w;
-                    w.x = pack_bf16x2((acc[half * 32 + e] + __uint_as_float(ov[e])) * inv, (acc[half * 32 + e + 1] + __uint_as_float(ov[e + 1])) * inv);
-                    w.y = pack_bf16x2((acc[half * 32 + e + 2] + __uint_as_float(ov[e + 2])) * inv, (acc[half * 32 + e + 3] + __uint_as_float(ov[e + 3])) * inv);
-                    w.z = pack_bf16x2((acc[half * 32 + e + 4] + __uint_as_float(ov[e + 4])) * inv, (acc[half * 32 + e + 5] + __uint_as_float(ov[e + 5])) * inv);
-                    w.w = pack_bf16x2((acc[half * 32 + e + 6] + __uint_as_float(ov[e + 6])) * inv, (acc[half * 32 + e + 7] + __uint_as_float(ov[e + 7])) * inv);
+                    w.x = pack_bf16x2(__uint_as_float(ov[e]) * inv, __uint_as_float(ov[e + 1]) * inv);
+                    w.y = pack_bf16x2(__uint_as_float(ov[e + 2]) * inv, __uint_as_float(ov[e + 3]) * inv);
+                    w.z = pack_bf16x2(__uint_as_float(ov[e + 4]) * inv, __uint_as_float(ov[e + 5]) * inv);
+                    w.w = pack_bf16x2(__uint_as_float(ov[e + 6]) * inv, __uint_as_float(ov[e + 7]) * inv);
                     *reinterpret_cast<uint4*>(orow + half * 32 + e) = w;
                 }
             }

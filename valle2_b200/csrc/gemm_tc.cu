@@ -16,7 +16,9 @@ namespace {
 constexpr int BM = 128;      // UMMA M (rows of the A operand per tile)
 constexpr int BK = 64;       // k-block: 64 bf16 = one 128-byte swizzle atom row
 constexpr int UMMA_K = 16;
-constexpr int NUM_THREADS = 192;
+constexpr int epi_warps(bool swap) { return swap ? 4 : 8; }
+constexpr int num_threads(bool swap) { return 64 + 32 * epi_warps(swap); }
+constexpr int STG_BYTES_PER_WARP = 32 * 128;   // epilogue staging: 32 rows x 32 fp32, 128B-swizzled
 
 struct GemmParams {
     int rows_a, rows_b, K;
@@ -35,8 +37,24 @@ struct GemmParams {
     int late_trigger;          // release the dependent kernel only after our own pdl_wait (see vb_linear_decode flags)
 };
 
+// erf-GELU with erf from Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7, far below the bf16 output rounding); two MUFU
+// ops + ~12 FMA-pipe ops instead of the ~30-instruction erff().  The fp32 validation path keeps erff (gemm_simt.cu).
+__device__ __forceinline__ float gelu_erf_fast(float x) {
+    const float z = fabsf(x) * 0.70710678118654752440f;
+    const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
+    float poly = fmaf(1.061405429f, t, -1.453152027f);
+    poly = fmaf(poly, t, 1.421413741f);
+    poly = fmaf(poly, t, -0.284496736f);
+    poly = fmaf(poly, t, 0.254829592f);
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-z * z * 1.4426950408889634f));
+    const float erf_abs = fmaf(-poly * t, e, 1.0f);
+    const float erf_x = copysignf(erf_abs, x);
+    return 0.5f * x * (1.0f + erf_x);
+}
+
 template <int BN, int STAGES, bool SWAP>
-__global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a,
+__global__ void __launch_bounds__(num_threads(SWAP), 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a,
                                                                  const __grid_constant__ CUtensorMap tm_b, GemmParams p) {
     constexpr int A_BYTES = BM * BK * 2;
     constexpr int B_BYTES = BN * BK * 2;
@@ -63,7 +81,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(smem_u32(&tfull_bar[a]), 1);
-            mbar_init(smem_u32(&tempty_bar[a]), 4);
+            mbar_init(smem_u32(&tempty_bar[a]), epi_warps(SWAP));
         }
         fence_mbar_init();
     }
@@ -115,7 +133,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
                         if (SWAP) tma_load_2d(sa + A_BYTES, &tm_b, fb, kb * BK, tb * BN);
                         else      tma_load_2d(sa, &tm_a, fb, kb * BK, ta * BM);
                     } else {
-                        mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+                        if (SWAP) mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+                        else mbar_wait_relaxed(smem_u32(&empty_bar[stage]), phase ^ 1);
                         mbar_expect_tx(fb, STAGE_BYTES);
                         tma_load_2d(sa, &tm_a, fb, kb * BK, ta * BM);
                         tma_load_2d(sa + A_BYTES, &tm_b, fb, kb * BK, tb * BN);
@@ -137,11 +156,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
                 const int kb1 = min(kb0 + p.kb_per_split, p.kb_total);
                 const int acc = local & 1;
                 const uint32_t acc_phase = (local >> 1) & 1;
-                mbar_wait(smem_u32(&tempty_bar[acc]), acc_phase ^ 1);
+                if (SWAP) mbar_wait(smem_u32(&tempty_bar[acc]), acc_phase ^ 1);
+                else mbar_wait_relaxed(smem_u32(&tempty_bar[acc]), acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * BN;
                 for (int kb = kb0; kb < kb1; ++kb) {
-                    mbar_wait(smem_u32(&full_bar[stage]), phase);
+                    if (SWAP) mbar_wait(smem_u32(&full_bar[stage]), phase);
+                    else mbar_wait_relaxed(smem_u32(&full_bar[stage]), phase);
                     tc_fence_after();
                     const uint32_t sa = smem_base + stage * STAGE_BYTES;
 #pragma unroll
@@ -193,70 +214,89 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
                     }
                 }
             } else {
+                // Normal orientation.  Each quadrant is served by two warps (column halves).  A 32-column chunk goes
+                // TMEM -> registers (thread = row) -> a warp-private 128B-swizzled smem tile -> registers again with
+                // lane = (row, 16-byte column group), so that residual loads and output stores are coalesced
+                // (8 lanes cover one 128-byte row segment) instead of 32 scattered rows per instruction.
+                const int ew = warp - 2, half = ew >> 2;
+                const uint32_t stg = smem_base + STAGES * STAGE_BYTES + ew * STG_BYTES_PER_WARP;
                 const int n_base = tb * BN;
-                const bool row_ok = row < p.rows_a;
+                const int row_base = ta * BM + q * 32;
+                const bool vec_ok = ((p.rows_b & 3) == 0) && ((p.ldy & 3) == 0) && (p.epilogue != VB_EPI_BIAS_RESIDUAL || (p.ldr & 3) == 0);
+                const int c4 = lane & 7, rsub = lane >> 3;
 #pragma unroll 1
-                for (int c0 = 0; c0 < BN; c0 += 32) {
+                for (int c0 = half * (BN / 2); c0 < (half + 1) * (BN / 2); c0 += 32) {
                     const int n0 = n_base + c0;
                     if (n0 >= p.rows_b) break;
                     uint32_t v[32];
                     tmem_ld_32x32(t_addr + c0, v);
                     tmem_ld_wait();
-                    if (!row_ok) continue;
-                    float f[32];
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-                    const bool full = (n0 + 32 <= p.rows_b);
+                    for (int j = 0; j < 8; ++j) {
+                        const uint32_t a = stg + lane * 128 + (static_cast<uint32_t>(j ^ (lane & 7)) << 4);
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v[4 * j]), "r"(v[4 * j + 1]),
+                                     "r"(v[4 * j + 2]), "r"(v[4 * j + 3]) : "memory");
+                    }
+                    __syncwarp();
+                    const int gcol = n0 + c4 * 4;
+                    float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (p.epilogue != VB_EPI_NONE) {
-                        if (full) {
+                        if (gcol + 3 < p.rows_b) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + gcol));
+                        else {
+                            if (gcol < p.rows_b) b4.x = p.bias[gcol];
+                            if (gcol + 1 < p.rows_b) b4.y = p.bias[gcol + 1];
+                            if (gcol + 2 < p.rows_b) b4.z = p.bias[gcol + 2];
+                        }
+                    }
+                    // phase A: every shared and global LOAD of the chunk is issued before any store (y may alias the
+                    // residual, so interleaving them would serialise the loads behind the stores)
+                    float4 f[8], r4[8];
+                    const bool col_ok = gcol < p.rows_b;
 #pragma unroll
-                            for (int j = 0; j < 32; j += 4) {
-                                const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
-                                f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
+                    for (int it = 0; it < 8; ++it) {
+                        const int rr = it * 4 + rsub;
+                        const uint32_t a = stg + rr * 128 + (static_cast<uint32_t>(c4 ^ (rr & 7)) << 4);
+                        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(f[it].x), "=f"(f[it].y), "=f"(f[it].z), "=f"(f[it].w) : "r"(a));
+                    }
+                    if (p.epilogue == VB_EPI_BIAS_RESIDUAL && vec_ok) {
+#pragma unroll
+                        for (int it = 0; it < 8; ++it) {
+                            const int grow = row_base + it * 4 + rsub;
+                            r4[it] = (grow < p.rows_a && col_ok)
+                                         ? *reinterpret_cast<const float4*>(p.residual + static_cast<int64_t>(grow) * p.ldr + gcol)
+                                         : make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
+                    }
+                    // phase B: epilogue math + stores
+#pragma unroll
+                    for (int it = 0; it < 8; ++it) {
+                        const int grow = row_base + it * 4 + rsub;
+                        if (grow >= p.rows_a || !col_ok) continue;
+                        float4 v4 = f[it];
+                        v4.x += b4.x; v4.y += b4.y; v4.z += b4.z; v4.w += b4.w;
+                        if (p.epilogue == VB_EPI_BIAS_GELU) {
+                            v4.x = gelu_erf_fast(v4.x); v4.y = gelu_erf_fast(v4.y); v4.z = gelu_erf_fast(v4.z); v4.w = gelu_erf_fast(v4.w);
+                        }
+                        if (vec_ok) {
+                            if (p.epilogue == VB_EPI_BIAS_RESIDUAL) { v4.x += r4[it].x; v4.y += r4[it].y; v4.z += r4[it].z; v4.w += r4[it].w; }
+                            if (p.y_bf16) {
+                                *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(p.y) + static_cast<int64_t>(grow) * p.ldy + gcol) =
+                                    make_uint2(pack_bf16x2(v4.x, v4.y), pack_bf16x2(v4.z, v4.w));
+                            } else {
+                                *reinterpret_cast<float4*>(static_cast<float*>(p.y) + static_cast<int64_t>(grow) * p.ldy + gcol) = v4;
                             }
                         } else {
-                            for (int j = 0; j < 32; ++j) if (n0 + j < p.rows_b) f[j] += p.bias[n0 + j];
-                        }
-                    }
-                    if (p.epilogue == VB_EPI_BIAS_GELU) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
-                    }
-                    if (p.epilogue == VB_EPI_BIAS_RESIDUAL) {
-                        const float* rr = p.residual + static_cast<int64_t>(row) * p.ldr + n0;
-                        if (full && (p.ldr & 3) == 0) {
-#pragma unroll
-                            for (int j = 0; j < 32; j += 4) {
-                                const float4 r4 = *reinterpret_cast<const float4*>(rr + j);
-                                f[j] += r4.x; f[j + 1] += r4.y; f[j + 2] += r4.z; f[j + 3] += r4.w;
+                            const float fv[4] = {v4.x, v4.y, v4.z, v4.w};
+                            for (int e = 0; e < 4; ++e) {
+                                if (gcol + e >= p.rows_b) break;
+                                float val = fv[e];
+                                if (p.epilogue == VB_EPI_BIAS_RESIDUAL) val += p.residual[static_cast<int64_t>(grow) * p.ldr + gcol + e];
+                                if (p.y_bf16) static_cast<__nv_bfloat16*>(p.y)[static_cast<int64_t>(grow) * p.ldy + gcol + e] = __float2bfloat16_rn(val);
+                                else static_cast<float*>(p.y)[static_cast<int64_t>(grow) * p.ldy + gcol + e] = val;
                             }
-                        } else {
-                            for (int j = 0; j < 32; ++j) if (n0 + j < p.rows_b) f[j] += rr[j];
                         }
                     }
-                    if (p.y_bf16) {
-                        __nv_bfloat16* yr = static_cast<__nv_bfloat16*>(p.y) + static_cast<int64_t>(row) * p.ldy + n0;
-                        if (full && (p.ldy & 7) == 0) {
-#pragma unroll
-                            for (int j = 0; j < 32; j += 8) {
-                                uint4 pk;
-                                pk.x = pack_bf16x2(f[j], f[j + 1]); pk.y = pack_bf16x2(f[j + 2], f[j + 3]);
-                                pk.z = pack_bf16x2(f[j + 4], f[j + 5]); pk.w = pack_bf16x2(f[j + 6], f[j + 7]);
-                                *reinterpret_cast<uint4*>(yr + j) = pk;
-                            }
-                        } else {
-                            for (int j = 0; j < 32; ++j) if (n0 + j < p.rows_b) yr[j] = __float2bfloat16_rn(f[j]);
-                        }
-                    } else {
-                        float* yr = static_cast<float*>(p.y) + static_cast<int64_t>(row) * p.ldy + n0;
-                        if (full && (p.ldy & 3) == 0) {
-#pragma unroll
-                            for (int j = 0; j < 32; j += 4)
-                                *reinterpret_cast<float4*>(yr + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-                        } else {
-                            for (int j = 0; j < 32; ++j) if (n0 + j < p.rows_b) yr[j] = f[j];
-                        }
-                    }
+                    __syncwarp();
                 }
             }
             tc_fence_before();
@@ -274,7 +314,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
 
 template <int BN, int STAGES, bool SWAP>
 int launch_gemm_tc(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
-    constexpr int SMEM = STAGES * (BM * BK * 2 + BN * BK * 2) + 1024;
+    constexpr int SMEM = STAGES * (BM * BK * 2 + BN * BK * 2) + 1024 + (SWAP ? 0 : epi_warps(false) * STG_BYTES_PER_WARP);
     static bool configured = false;
     auto kern = gemm_tc_kernel<BN, STAGES, SWAP>;
     if (!configured) {
@@ -283,7 +323,7 @@ int launch_gemm_tc(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParam
     }
     const int total = p.tiles_a * p.tiles_b * p.n_split;
     const int grid = min(total, vb_sm_count());
-    VB_CUDA(vb_launch(SWAP, kern, dim3(grid), dim3(NUM_THREADS), SMEM, st, ta, tb, p));
+    VB_CUDA(vb_launch(SWAP, kern, dim3(grid), dim3(num_threads(SWAP)), SMEM, st, ta, tb, p));
     return VB_OK;
 }
 
