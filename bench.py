@@ -199,9 +199,18 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             torch.cuda.synchronize()
         att_ms = ev[0].elapsed_time(ev[1]) / (reps * 12)
         att_bytes = B * (ctx_r + 1) * 2 * d * 2            # K and V rows of every cached position, bf16
+        traffic = None
+        try:                                                 # DRAM bytes per launch from the committed ncu --set full capture
+            with open(os.path.join(ROOT, 'profiles', 'traffic.json')) as fh:
+                tr = json.load(fh)['attn_decode_kernel<bf16>']
+            # the capture is at B=32, ctx=750; scale linearly to this launch's algorithmic bytes
+            traffic = (tr['dram_bytes_read'] + tr['dram_bytes_write']) * att_bytes / tr['algorithmic_bytes']
+        except Exception:
+            pass
         result['roofline'] = {'bound': 'hbm', 'kernel': 'attn_decode_kernel<bf16>', 'achieved': att_bytes / (att_ms * 1e-3) / 1e9,
                               'peak': pk['hbm_gbs'], 'unit': 'GB/s', 'frac': att_bytes / (att_ms * 1e-3) / 1e9 / pk['hbm_gbs'],
-                              'traffic': None, 'peak_source': pk['_source'] + ' (MEASURED_PEAKS.json hbm_gbs)',
+                              'traffic': traffic, 'traffic_source': 'profiles/traffic.json (ncu --set full, scaled to this launch)',
+                              'peak_source': pk['_source'] + ' (MEASURED_PEAKS.json hbm_gbs)',
                               'bytes_per_launch': att_bytes, 'us_per_launch': att_ms * 1e3,
                               'share_of_step': att_ms * 12 / (ms / K)}
         # weight-streaming GEMMs of one step, same method

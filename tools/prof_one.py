@@ -1,0 +1,54 @@
+#!/usr/bin/env python
+"""Launch ONE kernel configuration a few times (no graphs) -- the target of `ncu --set full` captures.
+usage: python tools/prof_one.py {attn_decode|gemm_decode|gemm_large|attn_prefill}"""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from valle2_b200 import ops  # noqa: E402
+
+what = sys.argv[1]
+d, F, H = 1024, 4096, 16
+if what == 'attn_decode':            # BASELINE config 2 at the mean context: B=32, ctx=750, 12 distinct layer pools
+    B, ctx = 32, 750
+    max_pages = (ctx + 64) // 64 + 1
+    pools = torch.randn(12, B * max_pages, 2, H, 64, 64, device='cuda').bfloat16()
+    bt = torch.arange(B * max_pages, device='cuda', dtype=torch.int32).view(B, max_pages)
+    seq = torch.full((B,), ctx, device='cuda', dtype=torch.int32)
+    part = torch.randn(6, B, 3 * d, device='cuda')
+    o = torch.empty(B, d, device='cuda', dtype=torch.bfloat16)
+    ws = torch.zeros(ops.attn_decode_ws_bytes(B, H, 1) // 4 + 64, device='cuda', dtype=torch.int32)
+    for li in range(12):
+        ops.attn_decode_paged(part, 6, B * 3 * d, pools[li], bt, seq, o, B, H, 64, 1, ws)
+elif what == 'gemm_decode':          # the four weight-streaming GEMMs of one decode layer at B=32
+    B = 32
+    h = torch.randn(B, d, device='cuda').bfloat16()
+    f = torch.randn(B, F, device='cuda').bfloat16()
+    for rep in range(3):
+        for (N, K, x) in [(3 * d, d, h), (d, d, h), (F, d, h), (d, F, f)]:
+            w = (torch.randn(N, K, device='cuda') * 0.02).bfloat16()
+            part = torch.zeros(32, B, N, device='cuda')
+            ops.linear_decode(x, w, part, B * N, 32)
+elif what == 'gemm_large':           # NAR config 3 shapes (M = 64 x 900)
+    M = 57600
+    for (N, K, epi) in [(3072, 1024, 'none'), (1024, 1024, 'residual'), (4096, 1024, 'gelu'), (1024, 4096, 'residual')]:
+        x = torch.randn(M, K, device='cuda').bfloat16()
+        w = torch.randn(N, K, device='cuda').bfloat16()
+        bias = torch.randn(N, device='cuda')
+        if epi == 'residual':
+            y = torch.randn(M, N, device='cuda')
+            ops.linear(x, w, bias, residual=y, out=y)
+        elif epi == 'gelu':
+            ops.linear(x, w, bias, gelu=True)
+        else:
+            ops.linear(x, w)
+elif what == 'attn_prefill':         # NAR config 3 attention: B=64, S=900, 16 heads
+    B, S = 64, 900
+    qkv = torch.randn(B * S, 3 * d, device='cuda').bfloat16()
+    o = torch.empty(B * S, d, device='cuda', dtype=torch.bfloat16)
+    for _ in range(2):
+        ops.attention_packed(qkv, o, B, S, H, mask_mode=ops.MASK_NONE, x_lens=None, kv_lens=None, use_tc=True)
+torch.cuda.synchronize()
+print('done', what)

@@ -136,6 +136,7 @@ class ARDecoder:
         self.wproj = model.proj.weight.detach().to(self.cd).contiguous()
         self._state = None
         self._graph = None
+        self.page_permutation_seed = None      # tests: scatter the logical pages over the pool
 
     # ------------------------------------------------------------------------------------------
     def _alloc(self, B: int, max_ctx: int, max_new: int):
@@ -143,7 +144,11 @@ class ARDecoder:
         max_pages = (max_ctx + PAGE - 1) // PAGE + 1
         st = {'B': B, 'max_pages': max_pages, 'max_new': max_new}
         st['pools'] = torch.zeros(L, B * max_pages, 2, H, PAGE, self.Dh, device=dev, dtype=self.cd)
-        st['block_table'] = torch.arange(B * max_pages, device=dev, dtype=torch.int32).view(B, max_pages).contiguous()
+        if self.page_permutation_seed is None:
+            table = torch.arange(B * max_pages, dtype=torch.int32)
+        else:
+            table = torch.randperm(B * max_pages, generator=torch.Generator().manual_seed(self.page_permutation_seed)).to(torch.int32)
+        st['block_table'] = table.view(B, max_pages).contiguous().to(dev)
         st['seq_lens'] = torch.zeros(B, device=dev, dtype=torch.int32)
         st['audio_pos'] = torch.zeros(B, device=dev, dtype=torch.int32)
         st['last'] = torch.zeros(B, device=dev, dtype=torch.int32)
@@ -325,9 +330,11 @@ class NARDecoder:
     @torch.no_grad()
     def generate(self, prompt_tokens: torch.Tensor, prompt_codes: torch.Tensor, target_tokens: torch.Tensor,
                  first_layer: torch.Tensor, *, greedy: bool = True, temperature: float = 1.0, seed: int = 0,
-                 return_logits: bool = False, use_tc_attention: bool | None = None):
+                 return_logits: bool = False, use_tc_attention: bool | None = None,
+                 target_lens: torch.Tensor | None = None):
         """Batched stages 2..Q.  prompt_tokens (B,Tp), prompt_codes (B,Tc,Q), target_tokens (B,Tt),
-        first_layer (B,T) -> (B,T,Q) int64."""
+        first_layer (B,T) -> (B,T,Q) int64.  ``target_lens`` (B,) marks ragged targets (extension): keys past
+        Tx+Tc+target_lens[b] are not attended and rows past it are padding in the result."""
         dev, d, Q = self.device, self.d, self.Q
         B, Tc, Qc = prompt_codes.shape
         assert Qc == Q
@@ -343,11 +350,15 @@ class NARDecoder:
         sampled = torch.empty(B * T, device=dev, dtype=torch.int32)
         step = torch.zeros(1, device=dev, dtype=torch.int32)
         trace = []
+        kv_lens = None
+        if target_lens is not None:
+            kv_lens = (_i32(target_lens, dev) + (Tx + Tc)).contiguous()
         for n in range(1, Q):
             ops.embed_sum_pe(tok_i, self.tok_table, self.pe_t, x, out_rows_per_batch=S, out_row_offset=0)
             ops.embed_sum_pe(ids, self.code_tables, self.pe_a, x, t_split=Tc, nq_a=Q, nq_b=n,
                              out_rows_per_batch=S, out_row_offset=Tx)
-            self.runner.forward(x, B, S, mask_mode=MASK_NONE, stage=n - 1, use_tc_attention=use_tc_attention)
+            self.runner.forward(x, B, S, mask_mode=MASK_NONE, kv_lens=kv_lens, stage=n - 1,
+                                use_tc_attention=use_tc_attention)
             tgt = x.view(B, S, d)[:, Tx + Tc:].reshape(B * T, d)          # strided gather (memory plumbing)
             if self.precision == 'bf16':
                 hb = torch.empty(B * T, d, device=dev, dtype=self.cd)

@@ -91,11 +91,11 @@ class ValleNAR(BaseModule):
 
     @torch.inference_mode()
     def generate_batch(self, prompt_tokens, prompt_codes, target_tokens, first_layer, *, greedy: bool = True,
-                       seed: int = 0, use_tc_attention: bool | None = None) -> torch.Tensor:
-        """Extension: B equal-length utterances at once -> (B, T, Q)."""
+                       seed: int = 0, use_tc_attention: bool | None = None, target_lens=None) -> torch.Tensor:
+        """Extension: B utterances at once -> (B, T, Q); ragged targets via ``target_lens`` (B,)."""
         return self._engine().generate(prompt_tokens, prompt_codes, target_tokens, first_layer, greedy=greedy,
                                        temperature=self.config.temperature, seed=seed,
-                                       use_tc_attention=use_tc_attention)
+                                       use_tc_attention=use_tc_attention, target_lens=target_lens)
 
     def _prepare_audio_codes(self, codes: torch.Tensor, nar_stage: int) -> tuple[torch.Tensor, int]:
         """(B, T, Q) codes -> (summed embeddings (B, T, d), prefix_len)  (valle_nar.py:167-188): the first
