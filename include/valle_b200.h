@@ -106,6 +106,34 @@ enum { VB_FLAG_LATE_TRIGGER = 1, VB_FLAG_PREFETCH_KV = 2 };
 int vb_linear_decode(const void* x, int64_t ldx, const void* w, int64_t ldw, float* part, int64_t part_stride,
                      int64_t M, int64_t N, int64_t K, int max_split, int flags, int* n_split_out, void* stream);
 
+/* Persistent "chain" kernel for the decode step (batch <= 64): up to 8 phases executed by one launch of #SM CTAs with a
+ * grid barrier between phases -- GEMM (as vb_linear_decode, same split-K slices), LN (as vb_residual_layernorm with a
+ * bf16 y), ACT (as vb_reduce_bias_act with gelu and a bf16 y).  Fuses out-proj -> LN -> FFN1 -> GELU -> FFN2 -> LN -> QKV
+ * of one decoder layer (modules.py:271-278) into one launch; results are bit-identical to the separate kernels.
+ * grid_barrier_counter: one zero-initialised uint32 in device memory (left at zero by every launch).
+ * The kernel uses a late PDL trigger (see VB_FLAG_LATE_TRIGGER). */
+enum { VB_PHASE_GEMM = 0, VB_PHASE_LN = 1, VB_PHASE_ACT = 2 };
+typedef struct vb_chain_phase {
+    int32_t type;
+    int32_t N, K, max_split;          /* GEMM: out / in features, split cap.  ACT: N = row width */
+    const void* x;                    /* GEMM: bf16 activations [B][K] */
+    const void* w;                    /* GEMM: bf16 weights [N][K] */
+    float* out_part;                  /* GEMM: fp32 slices [split][B][N] */
+    int64_t out_part_stride;
+    float* x32;                       /* LN: fp32 residual rows [B][d], updated in place when n_part > 0 */
+    const float* in_part;             /* LN / ACT: slices to reduce */
+    int32_t n_part;
+    int32_t d;                        /* LN: row width */
+    int64_t in_part_stride;
+    const float* bias;
+    const float* gamma;               /* LN: NULL = plain cast */
+    const float* beta;
+    void* y;                          /* LN / ACT: bf16 output rows (LN: may be NULL) */
+    float eps;
+    int32_t reserved;
+} vb_chain_phase;
+int vb_decode_chain(const vb_chain_phase* phases, int n_phase, int B, void* grid_barrier_counter, void* stream);
+
 /* ---- K5/K6: attention -------------------------------------------------------------------------------------------- */
 /* General attention over strided q/k/v (element strides), fp32 or bf16 I/O, fp32 math (SIMT).
  *   q: [B][H][Sq][Dh] via (q_sb,q_sh,q_ss); k,v: [B][H][Sk][Dh]; o: [B][Sq][H*Dh] (row pitch o_ss, batch o_sb).

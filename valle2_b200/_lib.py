@@ -28,6 +28,7 @@ SIGNATURES = {
     'vb_linear': (_i, [_p, _i, _i64, _p, _i, _i64, _p, _p, _i64, _p, _i, _i64, _i64, _i64, _i64, _i, _p]),
     'vb_linear_decode_splits': (_i, [_i64, _i64, _i]),
     'vb_linear_decode': (_i, [_p, _i64, _p, _i64, _p, _i64, _i64, _i64, _i64, _i, _i, _p, _p]),
+    'vb_decode_chain': (_i, [_p, _i, _i, _p, _p]),
     'vb_attention': (_i, [_p, _p, _p, _i, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _p, _i, _i64, _i64,
                           _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _i64, _i64, _i64, _p]),
     'vb_attention_prefill_tc': (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _p]),
@@ -37,6 +38,18 @@ SIGNATURES = {
     'vb_sample': (_i, [_p, _i, _i64, _i64, _i, _i, _f, _i, _f, _p, _u64, _p, _p, _p, _p]),
     'vb_ar_bookkeeping': (_i, [_p, _p, _p, _p, _p, _i64, _p, _p, _p, _i, _i, _p]),
 }
+
+
+PHASE_GEMM, PHASE_LN, PHASE_ACT = 0, 1, 2
+
+
+class ChainPhase(C.Structure):
+    """Mirror of ``vb_chain_phase`` (include/valle_b200.h)."""
+    _fields_ = [('type', C.c_int32), ('N', C.c_int32), ('K', C.c_int32), ('max_split', C.c_int32),
+                ('x', C.c_void_p), ('w', C.c_void_p), ('out_part', C.c_void_p), ('out_part_stride', C.c_int64),
+                ('x32', C.c_void_p), ('in_part', C.c_void_p), ('n_part', C.c_int32), ('d', C.c_int32),
+                ('in_part_stride', C.c_int64), ('bias', C.c_void_p), ('gamma', C.c_void_p), ('beta', C.c_void_p),
+                ('y', C.c_void_p), ('eps', C.c_float), ('reserved', C.c_int32)]
 
 
 class VBError(RuntimeError):

@@ -211,3 +211,34 @@ def ar_bookkeeping(sample_tok: torch.Tensor, logprob: torch.Tensor, last: torch.
     check(_L().vb_ar_bookkeeping(_ptr(sample_tok), _ptr(logprob), _ptr(last), _ptr(sum_logprobs), _ptr(codes_out),
                                  codes_out.stride(0), _ptr(seq_lens), _ptr(audio_pos), _ptr(state), B, eos,
                                  _stream()), 'vb_ar_bookkeeping')
+
+
+# ---- persistent decode chain (csrc/decode_chain.cu) -------------------------------------------------------------------
+def chain_gemm(x: torch.Tensor, w: torch.Tensor, part: torch.Tensor, part_stride: int, max_split: int = 32):
+    assert x.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and x.is_contiguous() and w.is_contiguous()
+    ph = _lib.ChainPhase()
+    ph.type, ph.N, ph.K, ph.max_split = _lib.PHASE_GEMM, w.shape[0], w.shape[1], max_split
+    ph.x, ph.w, ph.out_part, ph.out_part_stride = _ptr(x), _ptr(w), _ptr(part), part_stride
+    return ph
+
+
+def chain_ln(x32: torch.Tensor, gamma, beta, y, *, part=None, n_part: int = 0, part_stride: int = 0, bias=None,
+             eps: float = 1e-5):
+    assert x32.dtype == torch.float32 and (y is None or y.dtype == torch.bfloat16)
+    ph = _lib.ChainPhase()
+    ph.type, ph.d, ph.n_part, ph.in_part_stride, ph.eps = _lib.PHASE_LN, x32.shape[1], n_part, part_stride, eps
+    ph.x32, ph.in_part, ph.bias, ph.gamma, ph.beta, ph.y = _ptr(x32), _ptr(part), _ptr(bias), _ptr(gamma), _ptr(beta), _ptr(y)
+    return ph
+
+
+def chain_act(part: torch.Tensor, n_part: int, part_stride: int, bias, y: torch.Tensor):
+    assert y.dtype == torch.bfloat16
+    ph = _lib.ChainPhase()
+    ph.type, ph.N, ph.n_part, ph.in_part_stride = _lib.PHASE_ACT, y.shape[1], n_part, part_stride
+    ph.in_part, ph.bias, ph.y = _ptr(part), _ptr(bias), _ptr(y)
+    return ph
+
+
+def decode_chain(phases: list, B: int, counter: torch.Tensor) -> None:
+    arr = (_lib.ChainPhase * len(phases))(*phases)
+    check(_L().vb_decode_chain(C.cast(arr, C.c_void_p), len(phases), B, _ptr(counter), _stream()), 'vb_decode_chain')
