@@ -133,12 +133,12 @@ def run_ours(args, rank: int, world: int, local_rank: int):
 
     # ---- device-resident measurement: prefill (untimed), W warm-up steps, K timed graph replays ----
     st = eng.prefill(tokens_h.to(dev), codes_h.to(dev), max_new=total_steps + 2)
-    eng._logits_sample_book(st['x_last'], samp, None, -1)
-    eng._decode_step(samp, None, -1)                       # eager warm-up launch (module load, func attributes)
+    eng.first_token(samp, None, -1)
+    eng.decode_step(samp, None, -1)                        # eager warm-up launch (module load, func attributes)
     torch.cuda.synchronize()
     graph = torch.cuda.CUDAGraph()
     with torch.cuda.graph(graph):
-        eng._decode_step(samp, None, -1)
+        eng.decode_step(samp, None, -1)
     for _ in range(max(W - 1, 0)):
         graph.replay()
     ctx0 = int(st['seq_lens'][0].item())
@@ -164,7 +164,8 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     tok_s = B * world * K / (ms * 1e-3)
     step_bytes = ar_step_bytes(B, mean_ctx)
     pk = peaks()
-    launches_per_step = 1 + 8 * 12 + 1 + 1 + 1 + 1 + 1
+    launches_per_step = eng.launches_per_step()
+    n_sub = len(st['subs'])
 
     result = {
         'metric': 'ar_decode_tokens_per_s', 'value': tok_s, 'unit': 'tokens/s', 'n_gpus': world, 'steps': K, 'warmup': W,
@@ -174,6 +175,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                                f'(BASELINE configs[1]); text {TX}, prompt {P}, ctx {ctx0}->{ctx0 + K} (mean {mean_ctx:.1f})',
                    'batch_per_gpu': B, 'global_batch': B * world, 'parallelism': f'dp{world} (utterance sharding, '
                    'one all-gather of the codes at the end)', 'kv_page': 64,
+                   'sub_batches': n_sub, 'decode_gemm': 'fused' if eng._fused_ok(st['subs'][0]) else ('chain' if eng._chain_ok(st['subs'][0]) else 'split-k'), 'launches_per_step': launches_per_step,
                    'l2_policy': 'inputs larger than L2: every step streams 304 MB of weights + %.0f MB of KV' %
                                 ((step_bytes - ar_step_bytes(0, 0)) / 1e6),
                    'step_hbm_bytes': step_bytes, 'step_hbm_frac_of_measured_peak':
@@ -186,19 +188,37 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         H, Dh, d = 16, 64, 1024
         ctx_r = int(round(mean_ctx))
         st['seq_lens'].fill_(ctx_r)
+        sb = st['subs'][0]                                   # the launch shape the step really uses (one sub-batch)
+        Bs = sb['B']
         torch.cuda.synchronize()
         reps = 5
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-        for it in range(2):                                  # first pass warms up
+        rows = eng._fused_ok(sb)
+        qkv_src, qkv_np, qkv_ps = (sb['qkv32'], 1, 0) if rows else (sb['p_qkv'], sb['ns']['qkv'], Bs * 3 * d)
+
+        def attn_all_layers():
+            for li in range(12):                             # 12 layers x B x ctx KV = > L2, no re-use between launches
+                ops.attn_decode_paged(qkv_src, qkv_np, qkv_ps, st['pools'][li], sb['block_table'], sb['seq_lens'],
+                                      sb['o'], Bs, H, Dh, sb['n_tsplit'], sb['attn_ws'])
+
+        def timed_graph(fn):
+            """Kernel time without host launch overhead: capture fn once, replay it reps times between two events."""
+            fn()
+            torch.cuda.synchronize()
+            gr = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gr):
+                fn()
+            gr.replay()
+            torch.cuda.synchronize()
             ev[0].record()
             for _ in range(reps):
-                for li in range(12):                         # 12 layers x B x ctx KV = > L2, no re-use between launches
-                    ops.attn_decode_paged(st['p_qkv'], st['ns']['qkv'], B * 3 * d, st['pools'][li], st['block_table'],
-                                          st['seq_lens'], st['o'], B, H, Dh, st['n_tsplit'], st['attn_ws'])
+                gr.replay()
             ev[1].record()
             torch.cuda.synchronize()
-        att_ms = ev[0].elapsed_time(ev[1]) / (reps * 12)
-        att_bytes = B * (ctx_r + 1) * 2 * d * 2            # K and V rows of every cached position, bf16
+            return ev[0].elapsed_time(ev[1]) / reps
+
+        att_ms = timed_graph(attn_all_layers) / 12
+        att_bytes = Bs * (ctx_r + 1) * 2 * d * 2           # K and V rows of every cached position, bf16
         traffic = None
         try:                                                 # DRAM bytes per launch from the committed ncu --set full capture
             with open(os.path.join(ROOT, 'profiles', 'traffic.json')) as fh:
@@ -212,21 +232,31 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                               'traffic': traffic, 'traffic_source': 'profiles/traffic.json (ncu --set full, scaled to this launch)',
                               'peak_source': pk['_source'] + ' (MEASURED_PEAKS.json hbm_gbs)',
                               'bytes_per_launch': att_bytes, 'us_per_launch': att_ms * 1e3,
-                              'share_of_step': att_ms * 12 / (ms / K)}
+                              'share_of_step': att_ms * 12 * n_sub / (ms / K), 'rows_per_launch': Bs,
+                              'launches_per_step': 12 * n_sub}
         # weight-streaming GEMMs of one step, same method
-        ev[0].record()
-        for _ in range(reps):
+        def gemms_all_layers():
             for L in eng.weights.layers:
-                ops.linear_decode(st['h'], L['wqkv'], st['p_qkv'], B * 3 * d, 32)
-                ops.linear_decode(st['o'], L['wo'], st['p_o'], B * d, 32)
-                ops.linear_decode(st['h'], L['w1'], st['p_f1'], B * 4096, 32)
-                ops.linear_decode(st['f'], L['w2'], st['p_f2'], B * d, 32)
-        ev[1].record()
-        torch.cuda.synchronize()
-        gemm_ms = ev[0].elapsed_time(ev[1]) / reps
+                if rows:
+                    cl = eng.fused_cluster
+                    g1, b1, _ = L['norm1']
+                    g2, b2, _ = L['norm2']
+                    ops.linear_decode_fused(sb['x'], L['wqkv'], sb['qkv32'], gamma=g1[0], beta=b1[0], cluster_k=cl['qkv'])
+                    ops.linear_decode_fused(sb['o'], L['wo'], sb['x'], bias=L['bo'], residual=True, cluster_k=cl['o'])
+                    ops.linear_decode_fused(sb['x'], L['w1'], sb['f'], bias=L['b1'], gelu=True, gamma=g2[0], beta=b2[0], cluster_k=cl['f1'])
+                    ops.linear_decode_fused(sb['f'], L['w2'], sb['x'], bias=L['b2'], residual=True, cluster_k=cl['f2'])
+                else:
+                    ops.linear_decode(sb['h'], L['wqkv'], sb['p_qkv'], Bs * 3 * d, 32)
+                    ops.linear_decode(sb['o'], L['wo'], sb['p_o'], Bs * d, 32)
+                    ops.linear_decode(sb['h'], L['w1'], sb['p_f1'], Bs * 4096, 32)
+                    ops.linear_decode(sb['f'], L['w2'], sb['p_f2'], Bs * d, 32)
+
+        sb['x'].zero_()
+        gemm_ms = timed_graph(gemms_all_layers)
         wbytes = 2 * 12 * (3 * d * d + d * d + 2 * d * 4096)
         result['gemm_decode'] = {'ms_per_step': gemm_ms, 'achieved_gbs': wbytes / (gemm_ms * 1e-3) / 1e9,
-                                 'frac_of_hbm_peak': wbytes / (gemm_ms * 1e-3) / 1e9 / pk['hbm_gbs'], 'launches': 48}
+                                 'frac_of_hbm_peak': wbytes / (gemm_ms * 1e-3) / 1e9 / pk['hbm_gbs'], 'launches': 48,
+                                 'kernel': 'gemm_decode_fused_kernel (cluster split-K through DSMEM, LN on load, fused epilogues)' if rows else 'gemm_tc_kernel<swap-AB split-K>'}
 
     # ---- end-to-end through the public API from pinned host tensors --------------------------------
     barrier()
@@ -268,12 +298,12 @@ def extras(args, dev, tmp):
     codes = torch.cat([torch.full((1, 1), 1025), torch.randint(0, 1024, (1, P0 - 1), generator=g)], 1).to(dev)
     samp = {'temperature': 1.0, 'top_k': 1, 'top_p': 1.0, 'seed': 0}
     st = eng.prefill(tokens, codes, max_new=N_NEW + 2)
-    eng._logits_sample_book(st['x_last'], samp, None, -1)
-    eng._decode_step(samp, None, -1)
+    eng.first_token(samp, None, -1)
+    eng.decode_step(samp, None, -1)
     torch.cuda.synchronize()
     graph = torch.cuda.CUDAGraph()
     with torch.cuda.graph(graph):
-        eng._decode_step(samp, None, -1)
+        eng.decode_step(samp, None, -1)
     for _ in range(4):
         graph.replay()
     K1 = N_NEW - 8

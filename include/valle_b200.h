@@ -106,6 +106,22 @@ enum { VB_FLAG_LATE_TRIGGER = 1, VB_FLAG_PREFETCH_KV = 2 };
 int vb_linear_decode(const void* x, int64_t ldx, const void* w, int64_t ldw, float* part, int64_t part_stride,
                      int64_t M, int64_t N, int64_t K, int max_split, int flags, int* n_split_out, void* stream);
 
+/* Decode-shape GEMM with the split-K reduction, LayerNorm and epilogue fused in (csrc/gemm_decode_fused.cu), B <= 64:
+ *   y[B][N] = epilogue(A[B][K] . w[N][K]^T).  CTAs that share a 128-row weight slab form a thread-block cluster along K
+ *   and sum their partial accumulators through distributed shared memory in rank order (deterministic, no slices in HBM).
+ *   a_dtype VB_BF16: a = bf16 rows [B][K] (pitch lda).
+ *   a_dtype VB_F32 : a = fp32 rows [B][K] (pitch lda, K % 64 == 0); the kernel normalises them on load:
+ *                    A = LayerNorm(a; gamma, beta, eps) (modules.py:271/276 norm1/norm2; row statistics combined across
+ *                    the cluster), or a plain cast when gamma is NULL.
+ *   epilogue: VB_EPI_NONE / VB_EPI_BIAS / VB_EPI_BIAS_GELU write y (VB_F32 or VB_BF16, pitch ldy);
+ *             VB_EPI_BIAS_RESIDUAL does y += A.w^T + bias in place (y fp32: the residual stream, modules.py:274/278).
+ *   cluster_k: CTAs per cluster along K, 1..8 or 16; 0 = vb_linear_decode_fused_cluster(N, K) (fills the SMs).
+ *   flags: VB_FLAG_LATE_TRIGGER as for vb_linear_decode. */
+int vb_linear_decode_fused_cluster(int N, int K);
+int vb_linear_decode_fused(const void* a, int a_dtype, int64_t lda, const float* gamma, const float* beta, float eps,
+                           const void* w, int64_t ldw, const float* bias, void* y, int y_dtype, int64_t ldy, int B, int N,
+                           int K, int epilogue, int cluster_k, int flags, void* stream);
+
 /* Persistent "chain" kernel for the decode step (batch <= 64): up to 8 phases executed by one launch of #SM CTAs with a
  * grid barrier between phases -- GEMM (as vb_linear_decode, same split-K slices), LN (as vb_residual_layernorm with a
  * bf16 y), ACT (as vb_reduce_bias_act with gelu and a bf16 y).  Fuses out-proj -> LN -> FFN1 -> GELU -> FFN2 -> LN -> QKV
@@ -133,6 +149,9 @@ typedef struct vb_chain_phase {
     int32_t reserved;
 } vb_chain_phase;
 int vb_decode_chain(const vb_chain_phase* phases, int n_phase, int B, void* grid_barrier_counter, void* stream);
+/* Profiling aid: subsequent chain launches write %globaltimer stamps [cta][phase 0..7][start, work done, arrived, released]
+ * (uint64) into buf (device memory, #SM*8*4 entries); NULL switches it off. */
+int vb_decode_chain_set_debug(void* buf);
 
 /* ---- K5/K6: attention -------------------------------------------------------------------------------------------- */
 /* General attention over strided q/k/v (element strides), fp32 or bf16 I/O, fp32 math (SIMT).
@@ -176,12 +195,13 @@ int vb_attn_decode_paged(const float* qkv_part, int n_part, int64_t part_stride,
 /* logits[r][:] = sum_s logits_part[s*part_stride + r*row_stride + :], r < R, V <= 4096.
  * utils.py:59-66 + transformers 4.38.2 top_k_top_p_filtering: /temperature; keep >= k-th largest (ties kept);
  * ascending cumulative softmax, drop cum <= 1-p, always keep the largest; softmax; draw; log_softmax at the draw.
- * The draw is inverse-CDF in index order with u = uniforms[r] (if given) else hash(seed, *step_ptr, r);
+ * The draw is inverse-CDF in index order with u = uniforms[r] (if given) else hash(seed, *step_ptr, r + row_offset)
+ * (row_offset: position of row 0 inside a larger batch, so that a batch decoded in pieces draws the same numbers);
  * top_k == 1 picks the lowest-index maximum (greedy).  out_tok int32 [R]; out_logprob fp32 [R] (nullable).
  * Also serves valle_nar.py:160 (top_k=0, top_p=1 -> plain Categorical; greedy -> argmax). */
 int vb_sample(const float* logits_part, int n_part, int64_t part_stride, int64_t row_stride, int R, int V,
               float temperature, int top_k, float top_p, const float* uniforms, uint64_t seed,
-              const int32_t* step_ptr, int32_t* out_tok, float* out_logprob, void* stream);
+              const int32_t* step_ptr, int row_offset, int32_t* out_tok, float* out_logprob, void* stream);
 
 /* K11: device-side beam bookkeeping of valle_ar.py:167-171 for B rows (no host sync):
  *   sum_logprobs[b] += logprob[b] * (last[b] != eos);  tok = (last[b]==eos) ? eos : sample[b];

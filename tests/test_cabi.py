@@ -36,7 +36,7 @@ def test_pure_queries_need_no_gpu():
 def test_bad_arguments_are_reported_not_crashed():
     from valle2_b200 import _lib
     lib = _lib.load()
-    rc = lib.vb_sample(None, 1, 0, 0, 1, 10, ctypes.c_float(1.0), 1, ctypes.c_float(1.0), None, 0, None, None, None, None)
+    rc = lib.vb_sample(None, 1, 0, 0, 1, 10, ctypes.c_float(1.0), 1, ctypes.c_float(1.0), None, 0, None, 0, None, None, None)
     assert rc == -1 and b'null' in lib.vb_last_error_string()
 
 

@@ -156,6 +156,139 @@ def test_linear_decode(ops, M, N, K):
     assert rel_err(y, x.double() @ w.double().t()) < 1e-4
 
 
+@pytest.mark.parametrize('B', [1, 7, 16, 32, 33, 64])
+@pytest.mark.parametrize('d,F', [(1024, 4096), (256, 1024)])
+def test_decode_chain_matches_separate_kernels(ops, B, d, F):
+    """The persistent chain kernel (out-proj -> LN -> FFN1 -> GELU -> FFN2 -> LN -> QKV, modules.py:271-278) against the
+    same sequence launched as separate kernels: split-K slices bit-identical, LN / GELU rows to fp32 round-off; run
+    three times back to back to exercise the self-resetting grid-barrier counter."""
+    torch.manual_seed(11)
+    dev = 'cuda'
+    bf = torch.bfloat16
+    o = torch.randn(B, d, device=dev).to(bf)
+    x0 = torch.randn(B, d, device=dev)
+    wo, w1 = (torch.randn(d, d, device=dev) / math.sqrt(d)).to(bf), (torch.randn(F, d, device=dev) / math.sqrt(d)).to(bf)
+    w2, wq = (torch.randn(d, F, device=dev) / math.sqrt(F)).to(bf), (torch.randn(3 * d, d, device=dev) / math.sqrt(d)).to(bf)
+    bo, b1, b2 = torch.randn(d, device=dev), torch.randn(F, device=dev), torch.randn(d, device=dev)
+    g2, be2, g1, be1 = (torch.randn(d, device=dev) for _ in range(4))
+    ns = {k: ops.linear_decode_splits(n, kk, 32) for k, (n, kk) in
+          {'qkv': (3 * d, d), 'o': (d, d), 'f1': (F, d), 'f2': (d, F)}.items()}
+
+    def bufs():
+        return {'x': x0.clone(), 'h': torch.zeros(B, d, device=dev, dtype=bf), 'h2': torch.zeros(B, d, device=dev, dtype=bf),
+                'f': torch.zeros(B, F, device=dev, dtype=bf),
+                'p_o': torch.full((ns['o'], B, d), float('nan'), device=dev),
+                'p_f1': torch.full((ns['f1'], B, F), float('nan'), device=dev),
+                'p_f2': torch.full((ns['f2'], B, d), float('nan'), device=dev),
+                'p_qkv': torch.full((ns['qkv'], B, 3 * d), float('nan'), device=dev)}
+
+    r = bufs()
+    ops.linear_decode(o, wo, r['p_o'], B * d, 32)
+    ops.residual_layernorm(r['x'], g2, be2, r['h'], part=r['p_o'], n_part=ns['o'], part_stride=B * d, bias=bo)
+    ops.linear_decode(r['h'], w1, r['p_f1'], B * F, 32)
+    ops.reduce_bias_act(r['p_f1'], ns['f1'], B * F, b1, True, r['f'])
+    ops.linear_decode(r['f'], w2, r['p_f2'], B * d, 32)
+    ops.residual_layernorm(r['x'], g1, be1, r['h2'], part=r['p_f2'], n_part=ns['f2'], part_stride=B * d, bias=b2)
+    ops.linear_decode(r['h2'], wq, r['p_qkv'], B * 3 * d, 32)
+    torch.cuda.synchronize()
+
+    gbar = torch.zeros(64, device=dev, dtype=torch.int32)
+    for rep in range(3):
+        c = bufs()
+        ops.decode_chain([
+            ops.chain_gemm(o, wo, c['p_o'], B * d),
+            ops.chain_ln(c['x'], g2, be2, c['h'], part=c['p_o'], n_part=ns['o'], part_stride=B * d, bias=bo),
+            ops.chain_gemm(c['h'], w1, c['p_f1'], B * F),
+            ops.chain_act(c['p_f1'], ns['f1'], B * F, b1, c['f']),
+            ops.chain_gemm(c['f'], w2, c['p_f2'], B * d),
+            ops.chain_ln(c['x'], g1, be1, c['h2'], part=c['p_f2'], n_part=ns['f2'], part_stride=B * d, bias=b2),
+            ops.chain_gemm(c['h2'], wq, c['p_qkv'], B * 3 * d)], B, gbar)
+        torch.cuda.synchronize()
+        assert int(gbar[0].item()) == 0, 'grid-barrier counter not reset'
+        assert torch.equal(c['p_o'], r['p_o']), 'out-proj slices differ'
+        # downstream stages see LN / GELU rows that may differ by fp32 round-off before the bf16 rounding
+        assert rel_err(c['x'], r['x']) < 2e-3      # after FFN2: bf16 roundings of h / f may flip by one ulp
+        for k in ('h', 'f', 'h2'):
+            assert rel_err(c[k].float(), r[k].float()) < 1e-2, k
+        for k, n in (('p_f1', 'f1'), ('p_f2', 'f2'), ('p_qkv', 'qkv')):
+            assert not torch.isnan(c[k][:ns[n]]).any()
+            assert rel_err(c[k][:ns[n]].sum(0), r[k][:ns[n]].sum(0)) < 2e-2, k
+    # and against fp64 math end to end
+    xr = x0.double() + o.double() @ wo.double().t() + bo.double()
+    assert rel_err(c['p_o'].sum(0) + bo + x0, xr) < 1e-4
+
+
+def test_decode_chain_plain_cast_and_first_layer(ops):
+    """LN phase variants: n_part = 0 (first layer: normalise x as is) and gamma = None (plain bf16 cast)."""
+    torch.manual_seed(12)
+    B, d, N = 5, 1024, 1025
+    dev = 'cuda'
+    x = torch.randn(B, d, device=dev)
+    g, be = torch.randn(d, device=dev), torch.randn(d, device=dev)
+    w = (torch.randn(N, d, device=dev) / math.sqrt(d)).bfloat16()
+    ns = ops.linear_decode_splits(N, d, 32)
+    gbar = torch.zeros(64, device=dev, dtype=torch.int32)
+    for gamma, beta in ((g, be), (None, None)):
+        h = torch.zeros(B, d, device=dev, dtype=torch.bfloat16)
+        part = torch.full((ns, B, N), float('nan'), device=dev)
+        xc = x.clone()
+        ops.decode_chain([ops.chain_ln(xc, gamma, beta, h), ops.chain_gemm(h, w, part, B * N)], B, gbar)
+        torch.cuda.synchronize()
+        assert torch.equal(xc, x)
+        ref_h = torch.nn.functional.layer_norm(x, (d,), g, be) if gamma is not None else x
+        assert rel_err(h.float(), ref_h) < 1e-2
+        assert rel_err(part.sum(0), h.double() @ w.double().t()) < 1e-4
+
+
+@pytest.mark.parametrize('B', [1, 7, 32, 33, 64])
+@pytest.mark.parametrize('N,K,cluster', [(3072, 1024, 0), (3072, 1024, 4), (1024, 1024, 0), (1024, 1024, 8), (4096, 1024, 0),
+                                       (1024, 4096, 0), (1024, 4096, 8), (1025, 1024, 0), (256, 256, 2), (200, 64, 1),
+                                       (1024, 2048, 5), (96, 1536, 3), (384, 512, 1)])
+def test_linear_decode_fused_bf16(ops, B, N, K, cluster):
+    """Cluster split-K decode GEMM (partials reduced through DSMEM) against fp64 math, all epilogues."""
+    torch.manual_seed(21)
+    a = torch.randn(B, K, device='cuda').bfloat16()
+    w = (torch.randn(N, K, device='cuda') / math.sqrt(K)).bfloat16()
+    bias = torch.randn(N, device='cuda')
+    ref = a.double() @ w.double().t()
+    y = torch.full((B, N), float('nan'), device='cuda')
+    ops.linear_decode_fused(a, w, y, cluster_k=cluster, flags=B % 2)
+    assert rel_err(y, ref) < 1e-4
+    y2 = torch.full((B, N), float('nan'), device='cuda')
+    ops.linear_decode_fused(a, w, y2, cluster_k=cluster)
+    assert torch.equal(y, y2), 'not deterministic'
+    yb = torch.zeros(B, N, device='cuda', dtype=torch.bfloat16)
+    ops.linear_decode_fused(a, w, yb, bias=bias, gelu=True, cluster_k=cluster)
+    assert rel_err(yb.float(), torch.nn.functional.gelu(ref + bias.double())) < 1e-2
+    x = torch.randn(B, N, device='cuda')
+    x0 = x.clone()
+    ops.linear_decode_fused(a, w, x, bias=bias, residual=True, cluster_k=cluster)
+    assert rel_err(x, x0.double() + ref + bias.double()) < 1e-4
+
+
+@pytest.mark.parametrize('B', [1, 5, 32, 40, 64])
+@pytest.mark.parametrize('d,N,cluster', [(1024, 4096, 0), (1024, 3072, 0), (1024, 3072, 4), (256, 768, 0), (1024, 1025, 0),
+                                       (1024, 512, 1), (1024, 512, 16), (512, 256, 3)])
+def test_linear_decode_fused_layernorm_on_load(ops, B, d, N, cluster):
+    """A = LayerNorm(x) computed inside the GEMM from the fp32 residual rows, row statistics combined across the cluster
+    (modules.py:271/276), and the plain-cast variant (no final norm before valle_ar.py:158)."""
+    torch.manual_seed(22)
+    x = torch.randn(B, d, device='cuda') * 2 + 0.5
+    g, be = torch.randn(d, device='cuda'), torch.randn(d, device='cuda')
+    w = (torch.randn(N, d, device='cuda') / math.sqrt(d)).bfloat16()
+    bias = torch.randn(N, device='cuda')
+    h = torch.nn.functional.layer_norm(x, (d,), g, be).bfloat16()          # the operand the kernel builds in smem
+    y = torch.full((B, N), float('nan'), device='cuda')
+    ops.linear_decode_fused(x, w, y, gamma=g, beta=be, cluster_k=cluster)
+    assert rel_err(y, h.double() @ w.double().t()) < 3e-3                    # bf16 roundings of LN(x) may flip by an ulp
+    f = torch.zeros(B, N, device='cuda', dtype=torch.bfloat16)
+    ops.linear_decode_fused(x, w, f, bias=bias, gelu=True, gamma=g, beta=be, cluster_k=cluster)
+    assert rel_err(f.float(), torch.nn.functional.gelu(h.double() @ w.double().t() + bias.double())) < 1e-2
+    yc = torch.full((B, N), float('nan'), device='cuda')
+    ops.linear_decode_fused(x, w, yc, cluster_k=cluster)                     # plain cast
+    assert rel_err(yc, x.bfloat16().double() @ w.double().t()) < 1e-4
+
+
 def _dense_attention(q, k, v, allowed):
     s = (q.double() @ k.double().transpose(-1, -2)) / math.sqrt(q.shape[-1])
     if allowed is not None:

@@ -53,8 +53,15 @@ struct ChainParams {
     int n_phase;
     int B;
     unsigned* gbar;
+    unsigned long long* dbg;   // optional: [cta][phase][4] globaltimer stamps (vb_decode_chain_set_debug)
     Phase ph[8];
 };
+
+__device__ __forceinline__ unsigned long long gtimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 
 struct Maps { CUtensorMap m[4]; };
 
@@ -162,6 +169,8 @@ __global__ void __launch_bounds__(THREADS, 1) decode_chain_kernel(const __grid_c
         unsigned bar_count = 0;
         for (int pi = 0; pi < p.n_phase; ++pi) {
             const Phase& ph = p.ph[pi];
+            unsigned long long* dbg = p.dbg ? p.dbg + (static_cast<size_t>(blockIdx.x) * 8 + pi) * 4 : nullptr;
+            if (dbg && threadIdx.x == 32) dbg[0] = gtimer();
             if (ph.type == PH_GEMM) {
                 const int total = ph.tiles_a * ph.n_split, kb_total = (ph.K + BK - 1) / BK;
                 for (int t = blockIdx.x; t < total; t += G, ++local) {
@@ -334,9 +343,14 @@ __global__ void __launch_bounds__(THREADS, 1) decode_chain_kernel(const __grid_c
                     *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(ph.y) + e) = make_uint2(pack_bf16x2(accv.x, accv.y), pack_bf16x2(accv.z, accv.w));
                 }
             }
+            if (dbg && threadIdx.x == 4 * 32) dbg[1] = gtimer();      // an epilogue warp: its part of the phase is done
             if (pi + 1 < p.n_phase) {
                 ++bar_count;
+                __threadfence();
+                worker_sync();
+                if (dbg && threadIdx.x == 32) dbg[2] = gtimer();       // whole CTA arrived
                 grid_barrier(p.gbar, bar_count * G);
+                if (dbg && threadIdx.x == 32) dbg[3] = gtimer();       // barrier released
             }
         }
         // leave the counter at zero for the next launch: the last CTA to check out resets it
@@ -370,6 +384,12 @@ int launch_chain(const Maps& maps, const ChainParams& p, int grid, cudaStream_t 
 
 }  // namespace
 
+static unsigned long long* g_chain_dbg = nullptr;
+extern "C" int vb_decode_chain_set_debug(void* buf) {   /* device buffer of #SM * 8 * 4 uint64, or NULL to switch off */
+    g_chain_dbg = static_cast<unsigned long long*>(buf);
+    return VB_OK;
+}
+
 extern "C" int vb_decode_chain(const vb_chain_phase* phases, int n_phase, int B, void* grid_barrier_counter, void* stream) {
     VB_REQUIRE(phases && grid_barrier_counter, VB_ERR_BAD_ARG, "vb_decode_chain: null pointer");
     VB_REQUIRE(n_phase >= 1 && n_phase <= 8, VB_ERR_BAD_ARG, "vb_decode_chain: 1..8 phases (got %d)", n_phase);
@@ -381,6 +401,7 @@ extern "C" int vb_decode_chain(const vb_chain_phase* phases, int n_phase, int B,
     p.n_phase = n_phase;
     p.B = B;
     p.gbar = static_cast<unsigned*>(grid_barrier_counter);
+    p.dbg = g_chain_dbg;
     int n_maps = 0, rc;
     for (int i = 0; i < n_phase; ++i) {
         const vb_chain_phase& s = phases[i];

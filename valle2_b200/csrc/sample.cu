@@ -45,7 +45,7 @@ __global__ void __launch_bounds__(THREADS) sample_kernel(const float* __restrict
                                                          int64_t part_stride, int64_t row_stride, int V,
                                                          float temperature, int top_k, float top_p,
                                                          const float* __restrict__ uniforms, uint64_t seed,
-                                                         const int32_t* __restrict__ step_ptr,
+                                                         const int32_t* __restrict__ step_ptr, int row_offset,
                                                          int32_t* __restrict__ out_tok, float* __restrict__ out_logprob) {
     __shared__ float val[MAX_V];
     __shared__ uint16_t kept_idx[MAX_V];
@@ -182,7 +182,7 @@ __global__ void __launch_bounds__(THREADS) sample_kernel(const float* __restrict
     float u;
     if (uniforms) u = uniforms[r];
     else {
-        uint64_t z = seed + 0x9E3779B97F4A7C15ull * (static_cast<uint64_t>(step_ptr ? *step_ptr : 0) * 1000003ull + r + 1);
+        uint64_t z = seed + 0x9E3779B97F4A7C15ull * (static_cast<uint64_t>(step_ptr ? *step_ptr : 0) * 1000003ull + (r + row_offset) + 1);
         z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
         z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
         z ^= z >> 31;
@@ -214,12 +214,12 @@ __global__ void __launch_bounds__(THREADS) sample_kernel(const float* __restrict
 
 extern "C" int vb_sample(const float* logits_part, int n_part, int64_t part_stride, int64_t row_stride, int R, int V,
                          float temperature, int top_k, float top_p, const float* uniforms, uint64_t seed,
-                         const int32_t* step_ptr, int32_t* out_tok, float* out_logprob, void* stream) {
+                         const int32_t* step_ptr, int row_offset, int32_t* out_tok, float* out_logprob, void* stream) {
     VB_REQUIRE(logits_part && out_tok, VB_ERR_BAD_ARG, "vb_sample: null pointer");
     VB_REQUIRE(V >= 1 && V <= MAX_V, VB_ERR_UNSUPPORTED, "vb_sample: vocabulary %d not in [1,%d]", V, MAX_V);
     VB_REQUIRE(R >= 0 && n_part >= 1 && temperature > 0.f, VB_ERR_BAD_ARG, "vb_sample: bad args");
     if (R == 0) return VB_OK;
     VB_CUDA(vb_launch(R <= 1024, sample_kernel, dim3(R), dim3(THREADS), 0, static_cast<cudaStream_t>(stream), logits_part, n_part, part_stride,
-                      row_stride, V, temperature, top_k, top_p, uniforms, seed, step_ptr, out_tok, out_logprob));
+                      row_stride, V, temperature, top_k, top_p, uniforms, seed, step_ptr, row_offset, out_tok, out_logprob));
     return VB_OK;
 }

@@ -116,6 +116,11 @@ def _i32(t: torch.Tensor, device) -> torch.Tensor:
 
 
 class ARDecoder:
+    """Batched KV-cached decode.  The batch may be cut into ``n_sub`` independent sub-batches (whole utterances) that run
+    on parallel branches of the step's CUDA graph: while one sub-batch is in its HBM-bound attention kernel the other is in
+    its latency-bound GEMM chain, so the two kinds of kernel overlap on the GPU.  Every sub-batch owns its workspaces;
+    KV pool, block table, counters and outputs are row-slices of the full-batch tensors."""
+
     def __init__(self, model, precision: str):
         cfg = model.config
         assert cfg.norm == 'LayerNorm', 'ValleAR runs only with norm=LayerNorm (reference defect A-10)'
@@ -136,11 +141,78 @@ class ARDecoder:
         self.wproj = model.proj.weight.detach().to(self.cd).contiguous()
         self._state = None
         self._graph = None
+        self._streams = []
         self.page_permutation_seed = None      # tests: scatter the logical pages over the pool
+        # tunables (env overrides are for experiments; the defaults are the measured best)
+        self.use_chain = os.environ.get('VALLE_B200_CHAIN', '0') != '0'
+        self.use_fused = os.environ.get('VALLE_B200_FUSED', '1') != '0'
+        # cluster size along K of the fused decode GEMMs (0 = fill the SMs), csrc/gemm_decode_fused.cu
+        self.fused_cluster = {'qkv': 0, 'o': 0, 'f1': 0, 'f2': 0, 'lg': 0}
+        for k, v in [kv.split('=') for kv in os.environ.get('VALLE_B200_FUSED_CLUSTER', '').split(';') if kv]:
+            self.fused_cluster[k] = int(v)
+        self.n_sub_override = int(os.environ.get('VALLE_B200_SUBBATCH', '0'))
+        self.attn_ctas = int(os.environ.get('VALLE_B200_ATTN_CTAS', '0'))
+        self.n_tsplit_override = 0             # tests: pin the flash-decoding split
 
     # ------------------------------------------------------------------------------------------
+    def _n_sub(self, B: int) -> int:
+        if self.precision != 'bf16':
+            return 1
+        if self.n_sub_override > 0:
+            return max(1, min(self.n_sub_override, B))
+        return 1
+
+    def _chain_ok(self, sub: dict) -> bool:
+        # Concurrent chain kernels (one per sub-batch) spin on grid barriers and cannot share an SM: two of them could
+        # each hold part of the GPU and wait for the rest forever, so the chain runs only when the batch is not split.
+        return (self.precision == 'bf16' and self.use_chain and sub['B'] <= 64 and len(self._state['subs']) == 1)
+
+    def _fused_ok(self, sub: dict) -> bool:
+        return self.precision == 'bf16' and self.use_fused and sub['B'] <= 64 and self.d % 64 == 0
+
+    def _make_sub(self, st: dict, b0: int, b1: int, state: torch.Tensor) -> dict:
+        """Workspaces of one sub-batch (rows b0..b1 of the batch) + row-slice views of the shared decode state."""
+        dev, d, F, H, V = self.device, self.d, self.weights.F, self.H, self.V
+        B = b1 - b0
+        sub = {'B': B, 'b0': b0, 'state': state}
+        for k in ('block_table', 'seq_lens', 'audio_pos', 'last', 'sum_logprobs', 'codes_out'):
+            sub[k] = st[k][b0:b1]
+        sub['sample'] = torch.zeros(B, device=dev, dtype=torch.int32)
+        sub['logprob'] = torch.zeros(B, device=dev, dtype=torch.float32)
+        sub['x'] = torch.zeros(B, d, device=dev, dtype=torch.float32)
+        if self.precision == 'bf16':
+            ms = 32
+            ns = {k: ops.linear_decode_splits(n, kk, ms) for k, (n, kk) in
+                  {'qkv': (3 * d, d), 'o': (d, d), 'f1': (F, d), 'f2': (d, F), 'lg': (V, d)}.items()}
+            sub['ns'] = ns
+            sub['h'] = torch.zeros(B, d, device=dev, dtype=self.cd)
+            sub['o'] = torch.zeros(B, d, device=dev, dtype=self.cd)
+            sub['f'] = torch.zeros(B, F, device=dev, dtype=self.cd)
+            sub['p_qkv'] = torch.zeros(ns['qkv'], B, 3 * d, device=dev, dtype=torch.float32)
+            sub['p_o'] = torch.zeros(ns['o'], B, d, device=dev, dtype=torch.float32)
+            sub['p_f1'] = torch.zeros(ns['f1'], B, F, device=dev, dtype=torch.float32)
+            sub['p_f2'] = torch.zeros(ns['f2'], B, d, device=dev, dtype=torch.float32)
+            sub['p_lg'] = torch.zeros(ns['lg'], B, V, device=dev, dtype=torch.float32)
+            sub['gbar'] = torch.zeros(64, device=dev, dtype=torch.int32)     # grid-barrier counter of the chain kernel
+            sub['qkv32'] = torch.zeros(B, 3 * d, device=dev, dtype=torch.float32)
+            sub['lg'] = torch.zeros(B, V, device=dev, dtype=torch.float32)
+        else:
+            sub['h'] = torch.zeros(B, d, device=dev, dtype=torch.float32)
+            sub['qkv'] = torch.zeros(B, 3 * d, device=dev, dtype=torch.float32)
+            sub['o'] = torch.zeros(B, d, device=dev, dtype=torch.float32)
+            sub['f'] = torch.zeros(B, F, device=dev, dtype=torch.float32)
+            sub['lg'] = torch.zeros(B, V, device=dev, dtype=torch.float32)
+        # flash-decoding split: enough CTAs to fill the GPU, never more splits than pages
+        sm = ops.device_info()['sm_count']
+        # ~3.5 CTAs per SM keep enough pages in flight and enough warps issuing (measured: 512 CTAs at B=32, H=16)
+        want = self.attn_ctas if self.attn_ctas > 0 else int(3.46 * sm)
+        n_ts = self.n_tsplit_override or max(1, min(8, st['max_pages'], math.ceil(want / (B * H))))
+        sub['n_tsplit'] = n_ts
+        sub['attn_ws'] = torch.zeros(ops.attn_decode_ws_bytes(B, H, n_ts) // 4 + 64, device=dev, dtype=torch.int32)
+        return sub
+
     def _alloc(self, B: int, max_ctx: int, max_new: int):
-        dev, d, F, H, V, L = self.device, self.d, self.weights.F, self.H, self.V, len(self.weights.layers)
+        dev, H, L = self.device, self.H, len(self.weights.layers)
         max_pages = (max_ctx + PAGE - 1) // PAGE + 1
         st = {'B': B, 'max_pages': max_pages, 'max_new': max_new}
         st['pools'] = torch.zeros(L, B * max_pages, 2, H, PAGE, self.Dh, device=dev, dtype=self.cd)
@@ -154,97 +226,172 @@ class ARDecoder:
         st['last'] = torch.zeros(B, device=dev, dtype=torch.int32)
         st['sum_logprobs'] = torch.zeros(B, device=dev, dtype=torch.float32)
         st['codes_out'] = torch.zeros(B, max_new, device=dev, dtype=torch.int32)
-        st['state'] = torch.tensor([0, -1], device=dev, dtype=torch.int32)
-        st['sample'] = torch.zeros(B, device=dev, dtype=torch.int32)
-        st['logprob'] = torch.zeros(B, device=dev, dtype=torch.float32)
-        st['x'] = torch.zeros(B, d, device=dev, dtype=torch.float32)
-        if self.precision == 'bf16':
-            ms = 32
-            ns = {k: ops.linear_decode_splits(n, kk, ms) for k, (n, kk) in
-                  {'qkv': (3 * d, d), 'o': (d, d), 'f1': (F, d), 'f2': (d, F), 'lg': (V, d)}.items()}
-            st['ns'] = ns
-            st['h'] = torch.zeros(B, d, device=dev, dtype=self.cd)
-            st['o'] = torch.zeros(B, d, device=dev, dtype=self.cd)
-            st['f'] = torch.zeros(B, F, device=dev, dtype=self.cd)
-            st['p_qkv'] = torch.zeros(ns['qkv'], B, 3 * d, device=dev, dtype=torch.float32)
-            st['p_o'] = torch.zeros(ns['o'], B, d, device=dev, dtype=torch.float32)
-            st['p_f1'] = torch.zeros(ns['f1'], B, F, device=dev, dtype=torch.float32)
-            st['p_f2'] = torch.zeros(ns['f2'], B, d, device=dev, dtype=torch.float32)
-            st['p_lg'] = torch.zeros(ns['lg'], B, V, device=dev, dtype=torch.float32)
-        else:
-            st['h'] = torch.zeros(B, d, device=dev, dtype=torch.float32)
-            st['qkv'] = torch.zeros(B, 3 * d, device=dev, dtype=torch.float32)
-            st['o'] = torch.zeros(B, d, device=dev, dtype=torch.float32)
-            st['f'] = torch.zeros(B, F, device=dev, dtype=torch.float32)
-            st['lg'] = torch.zeros(B, V, device=dev, dtype=torch.float32)
-        # flash-decoding split: enough CTAs to fill the GPU, never more splits than pages
-        sm = ops.device_info()['sm_count']
-        n_ts = max(1, min(8, max_pages, math.ceil(sm / (B * H))))   # measured: splitting only pays when B*H < #SMs
-        st['n_tsplit'] = n_ts
-        st['attn_ws'] = torch.zeros(ops.attn_decode_ws_bytes(B, H, n_ts) // 4 + 64, device=dev, dtype=torch.int32)
+        n_sub = self._n_sub(B)
+        st['state'] = torch.tensor([[0, -1]] * n_sub, device=dev, dtype=torch.int32)     # per sub-batch {step, stop_step}
+        bounds = [(B * i) // n_sub for i in range(n_sub + 1)]
+        st['subs'] = [self._make_sub(st, bounds[i], bounds[i + 1], st['state'][i]) for i in range(n_sub)]
+        while len(self._streams) < n_sub:
+            self._streams.append(torch.cuda.Stream(device=dev))
         self._state = st
         self._graph = None
         return st
 
     # ------------------------------------------------------------------------------------------
-    def _logits_sample_book(self, x_rows: torch.Tensor, samp: dict, uniforms: torch.Tensor | None, eos: int):
-        """x_rows (B,d) fp32 final hidden rows -> logits -> sample -> bookkeeping."""
-        st = self._state
-        B, V = st['B'], self.V
-        if self.precision == 'bf16':
-            ops.residual_layernorm(x_rows, None, None, st['h'])                  # cast to bf16 (no final norm, K-2)
-            ops.linear_decode(st['h'], self.wproj, st['p_lg'], B * V, 32)
-            lg, n_part, pstride = st['p_lg'], st['ns']['lg'], B * V
-        else:
-            ops.linear(x_rows, self.wproj, out=st['lg'])
-            lg, n_part, pstride = st['lg'], 1, 0
-        ops.sample(lg, n_part, pstride, V, B, V, temperature=samp['temperature'], top_k=samp['top_k'],
-                   top_p=samp['top_p'], out_tok=st['sample'], out_logprob=st['logprob'], uniforms=uniforms,
-                   seed=samp['seed'], step_ptr=st['state'])
-        ops.ar_bookkeeping(st['sample'], st['logprob'], st['last'], st['sum_logprobs'], st['codes_out'],
-                           st['seq_lens'], st['audio_pos'], st['state'], eos)
+    def _for_each_sub(self, fn):
+        """Run fn(sub) for every sub-batch; more than one -> parallel streams forked from / joined to the current one
+        (captured as parallel branches when the step is recorded into a CUDA graph)."""
+        subs = self._state['subs']
+        if len(subs) == 1:
+            fn(subs[0])
+            return
+        cur = torch.cuda.current_stream()
+        fork = torch.cuda.Event()
+        fork.record(cur)
+        for sub, s in zip(subs, self._streams):
+            s.wait_event(fork)
+            with torch.cuda.stream(s):
+                fn(sub)
+                done = torch.cuda.Event()
+                done.record(s)
+            cur.wait_event(done)
 
-    def _decode_step(self, samp: dict, uniforms: torch.Tensor | None, eos: int):
+    def _logits_sample_book(self, sub: dict, x_rows: torch.Tensor, samp: dict, uniforms: torch.Tensor | None, eos: int,
+                            logits_done: bool = False):
+        """x_rows (B,d) fp32 final hidden rows of the sub-batch -> logits -> sample -> bookkeeping."""
+        B, V = sub['B'], self.V
+        if self._fused_ok(sub):
+            ops.linear_decode_fused(x_rows, self.wproj, sub['lg'], cluster_k=self.fused_cluster['lg'])   # plain cast on load (no final norm, K-2)
+            lg, n_part, pstride = sub['lg'], 1, 0
+        elif self.precision == 'bf16':
+            if not logits_done:
+                ops.residual_layernorm(x_rows, None, None, sub['h'])                  # cast to bf16 (no final norm, K-2)
+                ops.linear_decode(sub['h'], self.wproj, sub['p_lg'], B * V, 32)
+            lg, n_part, pstride = sub['p_lg'], sub['ns']['lg'], B * V
+        else:
+            ops.linear(x_rows, self.wproj, out=sub['lg'])
+            lg, n_part, pstride = sub['lg'], 1, 0
+        if uniforms is not None:
+            uniforms = uniforms[sub['b0']:sub['b0'] + B].contiguous()
+        ops.sample(lg, n_part, pstride, V, B, V, temperature=samp['temperature'], top_k=samp['top_k'],
+                   top_p=samp['top_p'], out_tok=sub['sample'], out_logprob=sub['logprob'], uniforms=uniforms,
+                   seed=samp['seed'], step_ptr=sub['state'], row_offset=sub['b0'])
+        ops.ar_bookkeeping(sub['sample'], sub['logprob'], sub['last'], sub['sum_logprobs'], sub['codes_out'],
+                           sub['seq_lens'], sub['audio_pos'], sub['state'], eos)
+
+    def first_token(self, samp: dict, uniforms: torch.Tensor | None, eos: int):
+        """Sample the first generated token of every sequence from the prefill's last hidden rows."""
         st = self._state
-        B, d, H, Dh = st['B'], self.d, self.H, self.Dh
-        x = st['x']
-        ops.embed_sum_pe(st['last'].view(B, 1, 1), self.aud_table, self.pe_a, x, pos_b=st['audio_pos'])
+        self._for_each_sub(lambda sub: self._logits_sample_book(
+            sub, st['x_last'][sub['b0']:sub['b0'] + sub['B']], samp, uniforms, eos))
+
+    def decode_step(self, samp: dict, uniforms: torch.Tensor | None, eos: int):
+        """One decode step of the whole batch (all sub-batches)."""
+        self._for_each_sub(lambda sub: self._decode_step(sub, samp, uniforms, eos))
+
+    def _decode_step(self, sub: dict, samp: dict, uniforms: torch.Tensor | None, eos: int):
+        st = self._state
+        B, d, H, Dh, F = sub['B'], self.d, self.H, self.Dh, self.weights.F
+        x = sub['x']
+        ops.embed_sum_pe(sub['last'].view(B, 1, 1), self.aud_table, self.pe_a, x, pos_b=sub['audio_pos'])
         layers = self.weights.layers
+        if self._fused_ok(sub):
+            # five dependent kernels per layer: split-K is reduced inside a thread-block cluster, LayerNorm runs on load
+            # inside the QKV / FFN1 GEMMs, bias + residual / GELU in the epilogues (csrc/gemm_decode_fused.cu)
+            cl = self.fused_cluster
+            for li, L in enumerate(layers):
+                g, b, eps = L['norm1']
+                ops.linear_decode_fused(x, L['wqkv'], sub['qkv32'], gamma=g[0], beta=b[0], eps=eps, cluster_k=cl['qkv'],
+                                        flags=ops.FLAG_LATE_TRIGGER)
+                ops.attn_decode_paged(sub['qkv32'], 1, 0, st['pools'][li], sub['block_table'], sub['seq_lens'], sub['o'],
+                                      B, H, Dh, sub['n_tsplit'], sub['attn_ws'], ops.FLAG_PREFETCH_KV)
+                ops.linear_decode_fused(sub['o'], L['wo'], x, bias=L['bo'], residual=True, cluster_k=cl['o'])
+                g, b, eps = L['norm2']
+                ops.linear_decode_fused(x, L['w1'], sub['f'], bias=L['b1'], gelu=True, gamma=g[0], beta=b[0], eps=eps,
+                                        cluster_k=cl['f1'])
+                ops.linear_decode_fused(sub['f'], L['w2'], x, bias=L['b2'], residual=True, cluster_k=cl['f2'])
+            self._logits_sample_book(sub, x, samp, uniforms, eos)
+            return
+        if self._chain_ok(sub):
+            # persistent chain kernels: everything between two attention kernels is ONE launch (csrc/decode_chain.cu)
+            ns = sub['ns']
+            g, b, eps = layers[0]['norm1']
+            ops.decode_chain([ops.chain_ln(x, g[0], b[0], sub['h'], eps=eps),
+                              ops.chain_gemm(sub['h'], layers[0]['wqkv'], sub['p_qkv'], B * 3 * d)], B, sub['gbar'])
+            for li, L in enumerate(layers):
+                ops.attn_decode_paged(sub['p_qkv'], ns['qkv'], B * 3 * d, st['pools'][li], sub['block_table'],
+                                      sub['seq_lens'], sub['o'], B, H, Dh, sub['n_tsplit'], sub['attn_ws'],
+                                      ops.FLAG_PREFETCH_KV)
+                g2, b2, eps2 = L['norm2']
+                ph = [ops.chain_gemm(sub['o'], L['wo'], sub['p_o'], B * d),
+                      ops.chain_ln(x, g2[0], b2[0], sub['h'], part=sub['p_o'], n_part=ns['o'], part_stride=B * d,
+                                   bias=L['bo'], eps=eps2),
+                      ops.chain_gemm(sub['h'], L['w1'], sub['p_f1'], B * F),
+                      ops.chain_act(sub['p_f1'], ns['f1'], B * F, L['b1'], sub['f']),
+                      ops.chain_gemm(sub['f'], L['w2'], sub['p_f2'], B * d)]
+                if li + 1 < len(layers):
+                    nxt = layers[li + 1]
+                    g1, b1, eps1 = nxt['norm1']
+                    ph += [ops.chain_ln(x, g1[0], b1[0], sub['h'], part=sub['p_f2'], n_part=ns['f2'], part_stride=B * d,
+                                        bias=L['b2'], eps=eps1),
+                           ops.chain_gemm(sub['h'], nxt['wqkv'], sub['p_qkv'], B * 3 * d)]
+                else:       # no final norm (K-2): cast the hidden rows and run the logits projection
+                    ph += [ops.chain_ln(x, None, None, sub['h'], part=sub['p_f2'], n_part=ns['f2'], part_stride=B * d,
+                                        bias=L['b2']),
+                           ops.chain_gemm(sub['h'], self.wproj, sub['p_lg'], B * self.V)]
+                ops.decode_chain(ph, B, sub['gbar'])
+            self._logits_sample_book(sub, x, samp, uniforms, eos, logits_done=True)
+            return
         if self.precision == 'bf16':
-            ns = st['ns']
+            ns = sub['ns']
             for li, L in enumerate(layers):
                 g, b, eps = L['norm1']
                 if li == 0:
-                    ops.residual_layernorm(x, g[0], b[0], st['h'], eps=eps)
+                    ops.residual_layernorm(x, g[0], b[0], sub['h'], eps=eps)
                 else:
-                    ops.residual_layernorm(x, g[0], b[0], st['h'], part=st['p_f2'], n_part=ns['f2'],
+                    ops.residual_layernorm(x, g[0], b[0], sub['h'], part=sub['p_f2'], n_part=ns['f2'],
                                            part_stride=B * d, bias=layers[li - 1]['b2'], eps=eps)
-                ops.linear_decode(st['h'], L['wqkv'], st['p_qkv'], B * 3 * d, 32, ops.FLAG_LATE_TRIGGER)
-                ops.attn_decode_paged(st['p_qkv'], ns['qkv'], B * 3 * d, st['pools'][li], st['block_table'],
-                                      st['seq_lens'], st['o'], B, H, Dh, st['n_tsplit'], st['attn_ws'],
+                ops.linear_decode(sub['h'], L['wqkv'], sub['p_qkv'], B * 3 * d, 32, ops.FLAG_LATE_TRIGGER)
+                ops.attn_decode_paged(sub['p_qkv'], ns['qkv'], B * 3 * d, st['pools'][li], sub['block_table'],
+                                      sub['seq_lens'], sub['o'], B, H, Dh, sub['n_tsplit'], sub['attn_ws'],
                                       ops.FLAG_PREFETCH_KV)
-                ops.linear_decode(st['o'], L['wo'], st['p_o'], B * d, 32)
+                ops.linear_decode(sub['o'], L['wo'], sub['p_o'], B * d, 32)
                 g, b, eps = L['norm2']
-                ops.residual_layernorm(x, g[0], b[0], st['h'], part=st['p_o'], n_part=ns['o'], part_stride=B * d,
+                ops.residual_layernorm(x, g[0], b[0], sub['h'], part=sub['p_o'], n_part=ns['o'], part_stride=B * d,
                                        bias=L['bo'], eps=eps)
-                ops.linear_decode(st['h'], L['w1'], st['p_f1'], B * self.weights.F, 32)
-                ops.reduce_bias_act(st['p_f1'], ns['f1'], B * self.weights.F, L['b1'], True, st['f'])
-                ops.linear_decode(st['f'], L['w2'], st['p_f2'], B * d, 32)
-            ops.residual_layernorm(x, None, None, None, part=st['p_f2'], n_part=ns['f2'], part_stride=B * d,
+                ops.linear_decode(sub['h'], L['w1'], sub['p_f1'], B * F, 32)
+                ops.reduce_bias_act(sub['p_f1'], ns['f1'], B * F, L['b1'], True, sub['f'])
+                ops.linear_decode(sub['f'], L['w2'], sub['p_f2'], B * d, 32)
+            ops.residual_layernorm(x, None, None, None, part=sub['p_f2'], n_part=ns['f2'], part_stride=B * d,
                                    bias=layers[-1]['b2'])
         else:
             for li, L in enumerate(layers):
                 g, b, eps = L['norm1']
-                ops.residual_layernorm(x, g[0], b[0], st['h'], eps=eps)
-                ops.linear(st['h'], L['wqkv'], out=st['qkv'])
-                ops.attn_decode_paged(st['qkv'], 1, 0, st['pools'][li], st['block_table'], st['seq_lens'], st['o'],
-                                      B, H, Dh, st['n_tsplit'], st['attn_ws'])
-                ops.linear(st['o'], L['wo'], L['bo'], residual=x, out=x)
+                ops.residual_layernorm(x, g[0], b[0], sub['h'], eps=eps)
+                ops.linear(sub['h'], L['wqkv'], out=sub['qkv'])
+                ops.attn_decode_paged(sub['qkv'], 1, 0, st['pools'][li], sub['block_table'], sub['seq_lens'], sub['o'],
+                                      B, H, Dh, sub['n_tsplit'], sub['attn_ws'])
+                ops.linear(sub['o'], L['wo'], L['bo'], residual=x, out=x)
                 g, b, eps = L['norm2']
-                ops.residual_layernorm(x, g[0], b[0], st['h'], eps=eps)
-                ops.linear(st['h'], L['w1'], L['b1'], gelu=True, out=st['f'])
-                ops.linear(st['f'], L['w2'], L['b2'], residual=x, out=x)
-        self._logits_sample_book(x, samp, uniforms, eos)
+                ops.residual_layernorm(x, g[0], b[0], sub['h'], eps=eps)
+                ops.linear(sub['h'], L['w1'], L['b1'], gelu=True, out=sub['f'])
+                ops.linear(sub['f'], L['w2'], L['b2'], residual=x, out=x)
+        self._logits_sample_book(sub, x, samp, uniforms, eos)
+
+    def launches_per_step(self) -> int:
+        """Kernel launches of one decode step (all sub-batches) -- the bench's gpu_launches claim."""
+        L = len(self.weights.layers)
+        subs = self._state['subs']
+        total = 0
+        for sub in subs:
+            if self._fused_ok(sub):
+                total += 1 + 5 * L + 1 + 2          # embed, 5 per layer, logits, sample + bookkeeping
+            elif self._chain_ok(sub):
+                total += 1 + 1 + 2 * L + 2          # embed, first chain, (attention + chain) per layer, sample, bookkeeping
+            elif self.precision == 'bf16':
+                total += 1 + 8 * L + 1 + 2 + 2      # embed, 8 per layer, x-update, cast + logits, sample + bookkeeping
+            else:
+                total += 1 + 7 * L + 1 + 2
+        return total
 
     # ------------------------------------------------------------------------------------------
     @torch.no_grad()
@@ -283,28 +430,31 @@ class ARDecoder:
         samp = {'temperature': temperature, 'top_k': top_k, 'top_p': top_p, 'seed': seed}
         eos = -1 if ignore_eos else self.cfg.num_audio_tokens
         st = self.prefill(tokens, codes, code_lens=code_lens, max_new=max_new)
-        self._logits_sample_book(st['x_last'], samp, None if uniforms is None else uniforms[0].contiguous(), eos)
+        self.first_token(samp, None if uniforms is None else uniforms[0], eos)
         graph = None
         step = 1
         if use_graph and uniforms is None and max_new > 2:
-            self._decode_step(samp, None, eos)          # warm-up (also loads modules, sets func attributes)
+            self.decode_step(samp, None, eos)           # warm-up (also loads modules, sets func attributes)
             step += 1
             torch.cuda.synchronize()
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
-                self._decode_step(samp, None, eos)
+                self.decode_step(samp, None, eos)
             # capture does not execute: the captured step still has to be replayed for this position
         self._graph = graph
         while step < max_new:
             if graph is not None:
                 graph.replay()
             else:
-                self._decode_step(samp, None if uniforms is None else uniforms[step].contiguous(), eos)
+                self.decode_step(samp, None if uniforms is None else uniforms[step], eos)
             step += 1
             if not ignore_eos and (step % poll_every == 0):
-                if int(st['state'][1].item()) >= 0:
+                if int(st['state'][:, 1].min().item()) >= 0:      # every sub-batch has seen all of its rows stop
                     break
-        s_now, s_stop = (int(v) for v in st['state'].tolist())
+        state = st['state'].tolist()
+        s_now = state[0][0]
+        stops = [s[1] for s in state]
+        s_stop = max(stops) if min(stops) >= 0 else -1
         n = s_stop if s_stop >= 0 else min(s_now, max_new)
         return st['codes_out'][:, :n], st['sum_logprobs'].clone(), n
 

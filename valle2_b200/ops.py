@@ -130,6 +130,35 @@ def linear_decode(x: torch.Tensor, w: torch.Tensor, part: torch.Tensor, part_str
     return ns.value
 
 
+def linear_decode_fused(a: torch.Tensor, w: torch.Tensor, y: torch.Tensor, *, bias: torch.Tensor | None = None,
+                        gelu: bool = False, residual: bool = False, gamma: torch.Tensor | None = None,
+                        beta: torch.Tensor | None = None, eps: float = 1e-5, cluster_k: int = 0,
+                        flags: int = 0) -> torch.Tensor:
+    """y (B<=64, N) = epilogue(A @ w.T), split-K reduced inside a thread-block cluster (csrc/gemm_decode_fused.cu).
+    a bf16 (B,K): A = a;  a fp32 (B,K): A = LayerNorm(a; gamma, beta) computed on load (plain cast when gamma is None).
+    residual=True: y (fp32) += A @ w.T + bias in place."""
+    assert a.dim() == 2 and w.dim() == 2 and a.shape[1] == w.shape[1] and w.dtype == torch.bfloat16
+    assert a.stride(1) == 1 and w.stride(1) == 1 and y.stride(1) == 1 and y.shape == (a.shape[0], w.shape[0])
+    B, K = a.shape
+    N = w.shape[0]
+    if residual:
+        assert bias is not None and not gelu and y.dtype == torch.float32
+        epi = EPI_BIAS_RESIDUAL
+    elif gelu:
+        assert bias is not None
+        epi = EPI_BIAS_GELU
+    else:
+        epi = EPI_BIAS if bias is not None else EPI_NONE
+    check(_L().vb_linear_decode_fused(_ptr(a), _code(a.dtype), a.stride(0), _ptr(gamma), _ptr(beta), float(eps), _ptr(w),
+                                      w.stride(0), _ptr(bias), _ptr(y), _code(y.dtype), y.stride(0), B, N, K, epi,
+                                      cluster_k, flags, _stream()), 'vb_linear_decode_fused')
+    return y
+
+
+def linear_decode_fused_cluster(N: int, K: int) -> int:
+    return int(_L().vb_linear_decode_fused_cluster(N, K))
+
+
 def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tensor, *, mask_mode: int = MASK_NONE,
               q_pos0: int = 0, x_lens: torch.Tensor | None = None, kv_lens: torch.Tensor | None = None,
               mask: torch.Tensor | None = None) -> torch.Tensor:
@@ -197,10 +226,10 @@ def attn_decode_paged(qkv_part: torch.Tensor, n_part: int, part_stride: int, poo
 def sample(logits_part: torch.Tensor, n_part: int, part_stride: int, row_stride: int, R: int, V: int, *,
            temperature: float, top_k: int, top_p: float, out_tok: torch.Tensor,
            out_logprob: torch.Tensor | None = None, uniforms: torch.Tensor | None = None, seed: int = 0,
-           step_ptr: torch.Tensor | None = None) -> None:
+           step_ptr: torch.Tensor | None = None, row_offset: int = 0) -> None:
     assert out_tok.dtype == torch.int32
     check(_L().vb_sample(_ptr(logits_part), n_part, part_stride, row_stride, R, V, float(temperature), int(top_k),
-                         float(top_p), _ptr(uniforms), seed & (2 ** 64 - 1), _ptr(step_ptr), _ptr(out_tok),
+                         float(top_p), _ptr(uniforms), seed & (2 ** 64 - 1), _ptr(step_ptr), int(row_offset), _ptr(out_tok),
                          _ptr(out_logprob), _stream()), 'vb_sample')
 
 
