@@ -199,7 +199,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         def attn_all_layers():
             for li in range(12):                             # 12 layers x B x ctx KV = > L2, no re-use between launches
                 ops.attn_decode_paged(qkv_src, qkv_np, qkv_ps, st['pools'][li], sb['block_table'], sb['seq_lens'],
-                                      sb['o'], Bs, H, Dh, sb['n_tsplit'], sb['attn_ws'])
+                                      sb['o'], Bs, H, Dh, sb['n_tsplit'], sb['attn_ws'], eng.attn_flags)
 
         def timed_graph(fn):
             """Kernel time without host launch overhead: capture fn once, replay it reps times between two events."""
@@ -222,12 +222,12 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         traffic = None
         try:                                                 # DRAM bytes per launch from the committed ncu --set full capture
             with open(os.path.join(ROOT, 'profiles', 'traffic.json')) as fh:
-                tr = json.load(fh)['attn_decode_kernel<bf16>']
+                tr = json.load(fh)['attn_decode_kernel<bf16>' if eng.attn_flags else 'attn_decode_mma_kernel<bf16>']
             # the capture is at B=32, ctx=750; scale linearly to this launch's algorithmic bytes
             traffic = (tr['dram_bytes_read'] + tr['dram_bytes_write']) * att_bytes / tr['algorithmic_bytes']
         except Exception:
             pass
-        result['roofline'] = {'bound': 'hbm', 'kernel': 'attn_decode_kernel<bf16>', 'achieved': att_bytes / (att_ms * 1e-3) / 1e9,
+        result['roofline'] = {'bound': 'hbm', 'kernel': 'attn_decode_kernel<bf16> (SIMT)' if eng.attn_flags else 'attn_decode_mma_kernel<bf16>', 'achieved': att_bytes / (att_ms * 1e-3) / 1e9,
                               'peak': pk['hbm_gbs'], 'unit': 'GB/s', 'frac': att_bytes / (att_ms * 1e-3) / 1e9 / pk['hbm_gbs'],
                               'traffic': traffic, 'traffic_source': 'profiles/traffic.json (ncu --set full, scaled to this launch)',
                               'peak_source': pk['_source'] + ' (MEASURED_PEAKS.json hbm_gbs)',

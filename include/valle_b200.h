@@ -102,9 +102,14 @@ int vb_linear_decode_splits(int64_t N, int64_t K, int max_split);   /* pure quer
 /* flags: VB_FLAG_LATE_TRIGGER -- programmatic dependent launch: the kernel lets its successor start only after it has
  * itself waited for its predecessor, so the successor's pre-wait code may read anything written before this kernel
  * (used for the QKV GEMM, whose successor vb_attn_decode_paged prefetches KV pages before waiting). */
-enum { VB_FLAG_LATE_TRIGGER = 1, VB_FLAG_PREFETCH_KV = 2 };
+enum { VB_FLAG_LATE_TRIGGER = 1, VB_FLAG_PREFETCH_KV = 2, VB_FLAG_ATTN_SIMT = 4 };
 int vb_linear_decode(const void* x, int64_t ldx, const void* w, int64_t ldw, float* part, int64_t part_stride,
                      int64_t M, int64_t N, int64_t K, int max_split, int flags, int* n_split_out, void* stream);
+
+/* Profiling aid: subsequent vb_linear_decode launches write %globaltimer stamps [cta][8] = {prologue done, weights requested,
+ * dependency resolved, first k-block landed, MMAs issued, accumulator complete, epilogue stores issued} (uint64, device
+ * memory, #SM*8 entries); NULL switches it off. */
+int vb_linear_decode_set_debug(void* buf);
 
 /* Decode-shape GEMM with the split-K reduction, LayerNorm and epilogue fused in (csrc/gemm_decode_fused.cu), B <= 64:
  *   y[B][N] = epilogue(A[B][K] . w[N][K]^T).  CTAs that share a 128-row weight slab form a thread-block cluster along K
@@ -173,6 +178,8 @@ int vb_attention_prefill_tc(const void* qkv, void* o, int B, int S, int H, int m
                             const int32_t* x_lens, const int32_t* kv_lens, void* stream);
 
 /* Paged KV pool layout (one pool per layer): [page][2 (K,V)][H][page_size=64][Dh=64], dtype f32 or bf16.
+ * bf16 pools with Dh = 64 store the eight 16-byte chunks of a token row XOR-swizzled: chunk c of token slot t sits at
+ * chunk c ^ (t & 7) (so that a page copied linearly into shared memory is read by ldmatrix without bank conflicts).
  * Copy K,V of a packed qkv buffer [B][S][3][H][Dh] (qkv_dtype) into the pool through block_table[B][max_pages];
  * only positions < kv_lens[b] are written.  Replaces the cache construction at modules.py:151-157. */
 int vb_kv_scatter_paged(const void* qkv, int qkv_dtype, void* pool, int pool_dtype, const int32_t* block_table,
@@ -190,6 +197,12 @@ int64_t vb_attn_decode_ws_bytes(int B, int H, int n_tsplit);
 int vb_attn_decode_paged(const float* qkv_part, int n_part, int64_t part_stride, void* pool, int pool_dtype,
                          const int32_t* block_table, int max_pages, const int32_t* seq_lens,
                          void* o, int o_dtype, int B, int H, int Dh, int n_tsplit, int flags, void* ws, void* stream);
+
+/* Ask the memory system to pull cached KV pages of one layer's pool into L2 (cp.async.bulk.prefetch.L2; a hint, nothing is
+ * written).  Pages [pages_total * page_lo_pct / 100, pages_total * page_hi_pct / 100) of every sequence are requested.
+ * Launched on a side stream while the latency-bound GEMM chain of the previous layer leaves HBM idle. */
+int vb_kv_prefetch_l2(const void* pool, int pool_dtype, const int32_t* block_table, int max_pages, const int32_t* seq_lens,
+                      int B, int H, int Dh, int page_lo_pct, int page_hi_pct, void* stream);
 
 /* ---- K9-K12: logits -> temperature -> top-k -> top-p -> sample (+ log-prob) --------------------------------------- */
 /* logits[r][:] = sum_s logits_part[s*part_stride + r*row_stride + :], r < R, V <= 4096.

@@ -268,7 +268,7 @@ def test_linear_decode_fused_bf16(ops, B, N, K, cluster):
 
 @pytest.mark.parametrize('B', [1, 5, 32, 40, 64])
 @pytest.mark.parametrize('d,N,cluster', [(1024, 4096, 0), (1024, 3072, 0), (1024, 3072, 4), (256, 768, 0), (1024, 1025, 0),
-                                       (1024, 512, 1), (1024, 512, 16), (512, 256, 3)])
+                                       (512, 512, 1), (1024, 512, 16), (512, 256, 3)])
 def test_linear_decode_fused_layernorm_on_load(ops, B, d, N, cluster):
     """A = LayerNorm(x) computed inside the GEMM from the fp32 residual rows, row statistics combined across the cluster
     (modules.py:271/276), and the plain-cast variant (no final norm before valle_ar.py:158)."""
@@ -287,6 +287,17 @@ def test_linear_decode_fused_layernorm_on_load(ops, B, d, N, cluster):
     yc = torch.full((B, N), float('nan'), device='cuda')
     ops.linear_decode_fused(x, w, yc, cluster_k=cluster)                     # plain cast
     assert rel_err(yc, x.bfloat16().double() @ w.double().t()) < 1e-4
+
+
+def _pool_swizzle(x):
+    """bf16 KV pool rows (64 tokens x 64 dims): 16-byte chunk c of token t is stored at chunk c ^ (t & 7)
+    (include/valle_b200.h, 'Paged KV pool layout').  The permutation is its own inverse."""
+    *lead, T, D = x.shape
+    assert T == 64 and D == 64
+    t = torch.arange(64, device=x.device)[:, None]
+    c = torch.arange(8, device=x.device)[None, :]
+    src = ((c ^ (t & 7)) * 8)[:, :, None] + torch.arange(8, device=x.device)[None, None, :]      # (64, 8, 8)
+    return torch.gather(x, -1, src.reshape(64, 64).expand(*lead, 64, 64))
 
 
 def _dense_attention(q, k, v, allowed):
@@ -358,7 +369,7 @@ def test_attention_prefill_tc(ops, B, S, H, mode):
 
 @pytest.mark.parametrize('dt', [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize('n_tsplit', [1, 4])
-@pytest.mark.parametrize('flags', [0, 2])
+@pytest.mark.parametrize('flags', [0, 2, 4])
 def test_attn_decode_paged(ops, dt, n_tsplit, flags):
     torch.manual_seed(8)
     B, H, Dh, max_pages = 5, 4, 64, 6
@@ -374,6 +385,8 @@ def test_attn_decode_paged(ops, dt, n_tsplit, flags):
         for p in range(max_pages):
             pool[bt[b, p], 0] = dense_k[b, :, p * 64:(p + 1) * 64]
             pool[bt[b, p], 1] = dense_v[b, :, p * 64:(p + 1) * 64]
+    if dt == torch.bfloat16:
+        pool = _pool_swizzle(pool)
     n_part = 3
     part = torch.randn(n_part, B, 3 * d, device='cuda')
     out = torch.empty(B, d, device='cuda', dtype=dt)
@@ -391,7 +404,8 @@ def test_attn_decode_paged(ops, dt, n_tsplit, flags):
             ref = _dense_attention(qkv[b, 0][:, None].float(), K, V, None)[:, 0].reshape(d)
             assert rel_err(out[b].float(), ref) < (1e-5 if dt == torch.float32 else 1e-2), (b, rep)
             page, slot = int(bt[b, n // 64]), n % 64
-            assert torch.equal(pool_run[page, 0, :, slot], knew) and torch.equal(pool_run[page, 1, :, slot], vnew)
+            got = _pool_swizzle(pool_run[page]) if dt == torch.bfloat16 else pool_run[page]
+            assert torch.equal(got[0, :, slot], knew) and torch.equal(got[1, :, slot], vnew)
 
 
 def test_kv_scatter(ops):
@@ -403,6 +417,7 @@ def test_kv_scatter(ops):
     lens = torch.tensor([70, 65], dtype=torch.int32, device='cuda')
     pool = torch.zeros(4, 2, H, 64, Dh, device='cuda', dtype=torch.bfloat16)
     ops.kv_scatter_paged(qkv, pool, bt, lens, B, S, H, Dh)
+    pool = _pool_swizzle(pool)          # back to plain (token, dim) order
     v = qkv.view(B, S, 3, H, Dh)
     for b in range(B):
         for s in range(S):

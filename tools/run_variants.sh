@@ -5,7 +5,7 @@ out=gpurun_out/variants.jsonl
 for cfg in "$@"; do
   set -- $cfg
   echo "== fused=$1 sub=$2 cfg=$3" >> gpurun_out/variants.err
-  VALLE_B200_FUSED=$1 VALLE_B200_SUBBATCH=$2 VALLE_B200_FUSED_CLUSTER="$3" timeout 300 python bench.py --steps 300 --warmup 8 --no-extras >> $out 2>> gpurun_out/variants.err
+  VALLE_B200_FUSED=$1 VALLE_B200_SUBBATCH=$2 VALLE_B200_KV_PREFETCH="$3" timeout 300 python bench.py --steps 300 --warmup 8 --no-extras >> $out 2>> gpurun_out/variants.err
 done
 python - <<'PY'
 import json

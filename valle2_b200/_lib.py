@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(HERE, 'lib', 'libvalle_b200.so')
 VB_F32, VB_BF16 = 0, 1
 EPI_NONE, EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RESIDUAL = 0, 1, 2, 3
 MASK_NONE, MASK_PREFIX_LM, MASK_EXPLICIT = 0, 1, 2
-FLAG_LATE_TRIGGER, FLAG_PREFETCH_KV = 1, 2
+FLAG_LATE_TRIGGER, FLAG_PREFETCH_KV, FLAG_ATTN_SIMT = 1, 2, 4
 
 _p, _i, _i64, _f, _u64 = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_uint64
 
@@ -30,8 +30,10 @@ SIGNATURES = {
     'vb_linear_decode': (_i, [_p, _i64, _p, _i64, _p, _i64, _i64, _i64, _i64, _i, _i, _p, _p]),
     'vb_linear_decode_fused_cluster': (_i, [_i, _i]),
     'vb_linear_decode_fused': (_i, [_p, _i, _i64, _p, _p, _f, _p, _i64, _p, _p, _i, _i64, _i, _i, _i, _i, _i, _i, _p]),
+    'vb_kv_prefetch_l2': (_i, [_p, _i, _p, _i, _p, _i, _i, _i, _i, _i, _p]),
     'vb_decode_chain': (_i, [_p, _i, _i, _p, _p]),
     'vb_decode_chain_set_debug': (_i, [_p]),
+    'vb_linear_decode_set_debug': (_i, [_p]),
     'vb_attention': (_i, [_p, _p, _p, _i, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _p, _i, _i64, _i64,
                           _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _i64, _i64, _i64, _p]),
     'vb_attention_prefill_tc': (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _p]),

@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(THREADS) attn_decode_kernel(const float* __res
                 k_s[e] = to_f32<T>(kq);
                 v_s[e] = to_f32<T>(vq);
                 const int page = bt[n_old / PAGE], slot = n_old % PAGE;
-                T* kdst = pool + ((static_cast<int64_t>(page) * 2 * H + h) * PAGE + slot) * DH + e;
+                T* kdst = pool + ((static_cast<int64_t>(page) * 2 * H + h) * PAGE + slot) * DH + (sizeof(T) == 2 ? vb_pool_col_bf16(slot, e) : e);
                 kdst[0] = kq;
                 kdst[static_cast<int64_t>(H) * PAGE * DH] = vq;
             }
@@ -160,7 +160,7 @@ __global__ void __launch_bounds__(THREADS) attn_decode_kernel(const float* __res
             for (int ps = 0; ps < NPASS; ++ps) {
                 const int tok = warp * TOK_PER_WARP + ps * TPP + grp;
                 float kv[EPL];
-                load_vec<T, EPL>(ks + tok * ROW_BYTES + c * 16, kv);
+                load_vec<T, EPL>(ks + tok * ROW_BYTES + ((sizeof(T) == 2 ? (c ^ (tok & 7)) : c) << 4), kv);
                 float d = 0.f;
 #pragma unroll
                 for (int i = 0; i < EPL; ++i) d = fmaf(qreg[i], kv[i], d);
@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(THREADS) attn_decode_kernel(const float* __res
                     const float pj = (sc[ps] == -INFINITY) ? 0.f : exp2f(sc[ps] - m_new);
                     l_run += pj;
                     float vv[EPL];
-                    load_vec<T, EPL>(vs + tok * ROW_BYTES + c * 16, vv);
+                    load_vec<T, EPL>(vs + tok * ROW_BYTES + ((sizeof(T) == 2 ? (c ^ (tok & 7)) : c) << 4), vv);
 #pragma unroll
                     for (int i = 0; i < EPL; ++i) acc[i] = fmaf(pj, vv[i], acc[i]);
                 }
@@ -274,6 +274,290 @@ __global__ void __launch_bounds__(THREADS) attn_decode_kernel(const float* __res
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// Tensor-core variant for the bf16 pool.  The SIMT kernel above spends ~1200 warp-instructions per 16 KB page pair and
+// its consumers, not HBM, set the pace (ncu: 19 % of the warp samples wait for data, the rest is shuffle/FMA chains).
+// Here ONE warp owns a whole page: S = q.K^T and O += P.V are mma.sync.m16n8k16 (bf16 in, fp32 accumulate) with the
+// single query in row 0 of the 16-row A operand, K and V fragments come from ldmatrix on the XOR-swizzled page rows
+// (conflict-free), the softmax runs on the four lanes that hold row 0.  ~200 warp-instructions per page, and up to
+// NSTAGE pages of a CTA are in different warps at the same time, so ring slots turn over as fast as the copies land.
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+// D(16x8) += A(16x16) . B(16x8); rows 8..15 of A are zero here (a1 = a3 = 0)
+__device__ __forceinline__ void mma_row0(float (&c)[4], uint32_t a0, uint32_t a2, uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a0), "r"(0u), "r"(a2), "r"(0u), "r"(b0), "r"(b1));
+}
+
+constexpr int MAX_PG_SMEM = 64;     // page ids of a split kept in shared memory (longer splits read the table directly)
+// One consumer warp per ring stage: warp w only ever waits on stage w, phase after phase (a warp that could run ahead to
+// a later phase of another stage would alias the mbarrier parity).
+constexpr int MMA_WARPS = NSTAGE;
+constexpr int MMA_THREADS = (MMA_WARPS + 1) * 32;
+
+template <typename TO>
+__global__ void __launch_bounds__(MMA_THREADS, 4) attn_decode_mma_kernel(const float* __restrict__ qkv_part, int n_part,
+                                                                  int64_t part_stride, __nv_bfloat16* __restrict__ pool,
+                                                                  const int32_t* __restrict__ block_table, int max_pages,
+                                                                  const int32_t* __restrict__ seq_lens, TO* __restrict__ o,
+                                                                  float* __restrict__ ws_o, float* __restrict__ ws_ml,
+                                                                  unsigned* __restrict__ counters, int H, int n_tsplit,
+                                                                  float scale_log2e, int prefetch_kv) {
+    typedef __nv_bfloat16 T;
+    constexpr int CHUNK_BYTES = PAGE * DH * 2;          // 8 KB: one (page, K or V, head) chunk
+    constexpr int STAGE_BYTES = 2 * CHUNK_BYTES;
+
+    extern __shared__ __align__(128) uint8_t ring[];
+    __shared__ __align__(8) uint64_t full_bar[NSTAGE];
+    __shared__ __align__(8) uint64_t empty_bar[NSTAGE];
+    __shared__ float q_s[DH], k_s[DH], v_s[DH];
+    __shared__ float w_acc[MMA_WARPS][DH];
+    __shared__ float w_ml[MMA_WARPS][2];
+    __shared__ int pg_s[MAX_PG_SMEM];
+    __shared__ int is_last;
+
+    const int split = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int d_model = H * DH;
+    pdl_trigger();
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NSTAGE; ++s) {
+            mbar_init(smem_u32(&full_bar[s]), 1);
+            mbar_init(smem_u32(&empty_bar[s]), 1);       // one warp consumes a whole stage
+        }
+        fence_mbar_init();
+    }
+    __syncthreads();
+    const int32_t* bt = block_table + static_cast<int64_t>(b) * max_pages;
+    const bool owns_new = (split == n_tsplit - 1);
+
+    if (warp == MMA_WARPS) {
+        // ---------------- producer warp: page ids first (one coalesced read), then the bulk copies ----------------
+        if (!prefetch_kv) pdl_wait();     // with VB_FLAG_PREFETCH_KV the cached pages are known to be final already
+        const int n_old = seq_lens[b];
+        const int pages_total = (n_old + PAGE - 1) / PAGE;
+        const int pp = (pages_total + n_tsplit - 1) / n_tsplit;
+        const int p0 = min(split * pp, pages_total), p1 = min(p0 + pp, pages_total);
+        for (int i = lane; i < min(p1 - p0, MAX_PG_SMEM); i += 32) pg_s[i] = bt[p0 + i];
+        __syncwarp();
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int p = p0; p < p1; ++p) {
+                const int page = (p - p0 < MAX_PG_SMEM) ? pg_s[p - p0] : bt[p];
+                mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+                const uint32_t fb = smem_u32(&full_bar[stage]);
+                mbar_expect_tx(fb, STAGE_BYTES);
+                const T* ksrc = pool + (static_cast<int64_t>(page) * 2 * H + h) * PAGE * DH;
+                const uint32_t dst = smem_u32(ring) + stage * STAGE_BYTES;
+                bulk_load_1d(dst, ksrc, CHUNK_BYTES, fb);
+                bulk_load_1d(dst + CHUNK_BYTES, ksrc + static_cast<int64_t>(H) * PAGE * DH, CHUNK_BYTES, fb);
+                if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+            }
+        }
+        __syncwarp();
+        if (prefetch_kv) pdl_wait();      // every thread of the CTA passes the dependency before it exits
+    }
+
+    float m_run = -INFINITY, l_run = 0.f;
+    float oacc[8][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) oacc[j][i] = 0.f;
+
+    if (warp < MMA_WARPS) {
+        pdl_wait();     // q/k/v partials of the new token come from the predecessor (QKV GEMM)
+        const int n_old = seq_lens[b];
+        const int pages_total = (n_old + PAGE - 1) / PAGE;
+        const int pp = (pages_total + n_tsplit - 1) / n_tsplit;
+        const int p0 = min(split * pp, pages_total), p1 = min(p0 + pp, pages_total);
+        // new-token q, k, v (k, v only in the owner of the last split): threads 0..63 own one dim each; fixed-order reduction
+        // of the split-K partials with every load issued before the first add
+        if (threadIdx.x < DH) {
+            const int e = threadIdx.x;
+            const float* src = qkv_part + static_cast<int64_t>(b) * 3 * d_model + h * DH + e;
+            float tq[8], tk[8], tv[8];
+#pragma unroll
+            for (int s = 0; s < 8; ++s) {
+                tq[s] = (s < n_part) ? __ldcg(src + s * part_stride) : 0.f;
+                tk[s] = (owns_new && s < n_part) ? __ldcg(src + s * part_stride + d_model) : 0.f;
+                tv[s] = (owns_new && s < n_part) ? __ldcg(src + s * part_stride + 2 * d_model) : 0.f;
+            }
+            float aq = 0.f, ak = 0.f, av = 0.f;
+#pragma unroll
+            for (int s = 0; s < 8; ++s) { aq += tq[s]; ak += tk[s]; av += tv[s]; }
+            for (int s = 8; s < n_part; ++s) {
+                aq += __ldcg(src + s * part_stride);
+                if (owns_new) { ak += __ldcg(src + s * part_stride + d_model); av += __ldcg(src + s * part_stride + 2 * d_model); }
+            }
+            q_s[e] = aq * scale_log2e;
+            if (owns_new) {
+                const T kq = __float2bfloat16_rn(ak), vq = __float2bfloat16_rn(av);   // the cache precision is what later steps read
+                k_s[e] = __bfloat162float(kq);
+                v_s[e] = __bfloat162float(vq);
+                const int page = bt[n_old / PAGE], slot = n_old % PAGE;
+                T* kdst = pool + ((static_cast<int64_t>(page) * 2 * H + h) * PAGE + slot) * DH + vb_pool_col_bf16(slot, e);
+                kdst[0] = kq;
+                kdst[static_cast<int64_t>(H) * PAGE * DH] = vq;
+            }
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(MMA_WARPS * 32) : "memory");   // consumer warps only
+
+        const int g = lane >> 2, t = lane & 3;
+        // A fragments of q (row 0 of the 16-row tile): k-step kk covers dims 16kk .. 16kk+15
+        uint32_t qa0[4], qa2[4];
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+            qa0[kk] = (g == 0) ? pack_bf16x2(q_s[16 * kk + 2 * t], q_s[16 * kk + 2 * t + 1]) : 0u;
+            qa2[kk] = (g == 0) ? pack_bf16x2(q_s[16 * kk + 8 + 2 * t], q_s[16 * kk + 9 + 2 * t]) : 0u;
+        }
+        const int lm = lane >> 3, lr = lane & 7;      // ldmatrix: lane supplies row lr of matrix lm
+        for (int ip = warp; ip < p1 - p0; ip += MMA_WARPS) {
+            const int stage = ip % NSTAGE;
+            const uint32_t phase = (ip / NSTAGE) & 1;
+            mbar_wait(smem_u32(&full_bar[stage]), phase);
+            const uint32_t kbase = smem_u32(ring) + stage * STAGE_BYTES;
+            const uint32_t vbase = kbase + CHUNK_BYTES;
+            const int tok0 = (p0 + ip) * PAGE;
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {          // two half pages of 32 tokens: halves the live accumulator registers
+                // ---- S = q . K^T : 4 token tiles x 4 dim steps ----
+                float sacc[4][4];
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+                    const int j = 4 * hf + jj;
+                    sacc[jj][0] = sacc[jj][1] = sacc[jj][2] = sacc[jj][3] = 0.f;
+#pragma unroll
+                    for (int kp = 0; kp < 2; ++kp) {  // two k-steps per ldmatrix.x4: dim chunks 4kp .. 4kp+3
+                        uint32_t r0, r1, r2, r3;
+                        ldsm_x4(kbase + (8 * j + lr) * 128 + (((4 * kp + lm) ^ lr) << 4), r0, r1, r2, r3);
+                        mma_row0(sacc[jj], qa0[2 * kp], qa2[2 * kp], r0, r1);
+                        mma_row0(sacc[jj], qa0[2 * kp + 1], qa2[2 * kp + 1], r2, r3);
+                    }
+                }
+                // ---- online softmax on row 0 (lanes 0..3 hold it; the other lanes carry zeros through the same code) ----
+                float pmax = -INFINITY;
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+                    const int tk = tok0 + 8 * (4 * hf + jj) + 2 * t;
+                    if (tk >= n_old) sacc[jj][0] = -INFINITY;
+                    if (tk + 1 >= n_old) sacc[jj][1] = -INFINITY;
+                    pmax = fmaxf(pmax, fmaxf(sacc[jj][0], sacc[jj][1]));
+                }
+                pmax = fmaxf(pmax, __shfl_xor_sync(0xffffffffu, pmax, 1));
+                pmax = fmaxf(pmax, __shfl_xor_sync(0xffffffffu, pmax, 2));
+                const float m_new = fmaxf(m_run, pmax);          // finite for row 0: token 0 of a page is always cached
+                const float corr = exp2f(m_run - m_new);
+                l_run *= corr;
+                uint32_t pa[4];
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+                    const float p0f = exp2f(sacc[jj][0] - m_new), p1f = exp2f(sacc[jj][1] - m_new);
+                    l_run += p0f + p1f;
+                    pa[jj] = pack_bf16x2(p0f, p1f);
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    oacc[j][0] *= corr;
+                    oacc[j][1] *= corr;
+                }
+                m_run = m_new;
+                // ---- O += P . V : 2 token steps x 8 dim tiles ----
+#pragma unroll
+                for (int k2 = 0; k2 < 2; ++k2) {
+                    const int kk = 2 * hf + k2;
+#pragma unroll
+                    for (int jp = 0; jp < 4; ++jp) {  // two dim tiles per ldmatrix.x4.trans
+                        uint32_t r0, r1, r2, r3;
+                        const int tok = 16 * kk + (lm & 1) * 8 + lr;
+                        ldsm_x4_t(vbase + tok * 128 + (((2 * jp + (lm >> 1)) ^ lr) << 4), r0, r1, r2, r3);
+                        mma_row0(oacc[2 * jp], pa[2 * k2], pa[2 * k2 + 1], r0, r1);
+                        mma_row0(oacc[2 * jp + 1], pa[2 * k2], pa[2 * k2 + 1], r2, r3);
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&empty_bar[stage]));
+        }
+        // row 0 lives in lanes 0..3: dims 8j + 2t, 8j + 2t + 1; l is a per-lane partial sum
+        l_run += __shfl_xor_sync(0xffffffffu, l_run, 1);
+        l_run += __shfl_xor_sync(0xffffffffu, l_run, 2);
+        if (g == 0) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                w_acc[warp][8 * j + 2 * t] = oacc[j][0];
+                w_acc[warp][8 * j + 2 * t + 1] = oacc[j][1];
+            }
+        }
+        if (lane == 0) { w_ml[warp][0] = m_run; w_ml[warp][1] = l_run; }
+    }
+    __syncthreads();
+
+    // merge the consumer warps and (owner of the last split) the new token: threads 0..63 own one output dim each
+    float out_acc = 0.f, out_l = 0.f, out_m = -INFINITY;
+    if (threadIdx.x < DH) {
+        float s_new = -INFINITY;
+        if (owns_new) {
+            s_new = 0.f;
+#pragma unroll 8
+            for (int e = 0; e < DH; ++e) s_new = fmaf(q_s[e], k_s[e], s_new);
+        }
+        out_m = s_new;
+#pragma unroll
+        for (int w = 0; w < MMA_WARPS; ++w) out_m = fmaxf(out_m, w_ml[w][0]);
+#pragma unroll
+        for (int w = 0; w < MMA_WARPS; ++w) {
+            const float wt = (w_ml[w][0] == -INFINITY) ? 0.f : exp2f(w_ml[w][0] - out_m);
+            out_acc = fmaf(w_acc[w][threadIdx.x], wt, out_acc);
+            out_l = fmaf(w_ml[w][1], wt, out_l);
+        }
+        if (owns_new) {
+            const float wt = exp2f(s_new - out_m);
+            out_acc = fmaf(v_s[threadIdx.x], wt, out_acc);
+            out_l += wt;
+        }
+    }
+    TO* orow = o + static_cast<int64_t>(b) * d_model + h * DH;
+    if (n_tsplit == 1) {
+        if (threadIdx.x < DH) orow[threadIdx.x] = from_f32<TO>(out_l > 0.f ? out_acc / out_l : 0.f);
+        return;
+    }
+    const int64_t slot = (static_cast<int64_t>(b) * H + h) * n_tsplit;
+    if (threadIdx.x < DH) {
+        ws_o[(slot + split) * DH + threadIdx.x] = out_acc;
+        if (threadIdx.x == 0) { ws_ml[(slot + split) * 2] = out_m; ws_ml[(slot + split) * 2 + 1] = out_l; }
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned ticket = atomicInc(&counters[b * H + h], static_cast<unsigned>(n_tsplit - 1));
+        is_last = (ticket == static_cast<unsigned>(n_tsplit - 1));
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    if (threadIdx.x < DH) {
+        float M = -INFINITY;
+        for (int s = 0; s < n_tsplit; ++s) M = fmaxf(M, __ldcg(&ws_ml[(slot + s) * 2]));
+        float a = 0.f, l = 0.f;
+        for (int s = 0; s < n_tsplit; ++s) {
+            const float ms = __ldcg(&ws_ml[(slot + s) * 2]);
+            const float wt = (ms == -INFINITY) ? 0.f : exp2f(ms - M);
+            a = fmaf(__ldcg(&ws_o[(slot + s) * DH + threadIdx.x]), wt, a);
+            l = fmaf(__ldcg(&ws_ml[(slot + s) * 2 + 1]), wt, l);
+        }
+        orow[threadIdx.x] = from_f32<TO>(l > 0.f ? a / l : 0.f);
+    }
+}
+
 }  // namespace
 
 extern "C" int64_t vb_attn_decode_ws_bytes(int B, int H, int n_tsplit) {
@@ -309,10 +593,26 @@ extern "C" int vb_attn_decode_paged(const float* qkv_part, int n_part, int64_t p
                           block_table, max_pages, seq_lens, static_cast<TO*>(o), ws_o, ws_ml, counters, H, n_tsplit,  \
                           scale_log2e, (flags & VB_FLAG_PREFETCH_KV) ? 1 : 0));                                       \
     }
-    if (pool_dtype == VB_BF16 && o_dtype == VB_BF16) DEC(__nv_bfloat16, __nv_bfloat16, NSTAGE * 2 * PAGE * DH * 2)
+#define DECM(TO, SMEM)                                                                                                \
+    {                                                                                                                 \
+        auto kern = attn_decode_mma_kernel<TO>;                                                                       \
+        static bool configured = false;                                                                               \
+        if (!configured) {                                                                                            \
+            VB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));                   \
+            configured = true;                                                                                        \
+        }                                                                                                             \
+        VB_CUDA(vb_launch(true, kern, grid, dim3(MMA_THREADS), SMEM, st, qkv_part, n_part, part_stride,               \
+                          static_cast<__nv_bfloat16*>(pool), block_table, max_pages, seq_lens, static_cast<TO*>(o),   \
+                          ws_o, ws_ml, counters, H, n_tsplit, scale_log2e, (flags & VB_FLAG_PREFETCH_KV) ? 1 : 0));   \
+    }
+    const bool simt = (flags & VB_FLAG_ATTN_SIMT) != 0;
+    if (pool_dtype == VB_BF16 && o_dtype == VB_BF16 && !simt) DECM(__nv_bfloat16, NSTAGE * 2 * PAGE * DH * 2)
+    else if (pool_dtype == VB_BF16 && o_dtype == VB_F32 && !simt) DECM(float, NSTAGE * 2 * PAGE * DH * 2)
+    else if (pool_dtype == VB_BF16 && o_dtype == VB_BF16) DEC(__nv_bfloat16, __nv_bfloat16, NSTAGE * 2 * PAGE * DH * 2)
     else if (pool_dtype == VB_BF16 && o_dtype == VB_F32) DEC(__nv_bfloat16, float, NSTAGE * 2 * PAGE * DH * 2)
     else if (pool_dtype == VB_F32 && o_dtype == VB_F32) DEC(float, float, NSTAGE * 2 * PAGE * DH * 4)
     else VB_REQUIRE(false, VB_ERR_UNSUPPORTED, "vb_attn_decode_paged: dtype combination pool=%d o=%d", pool_dtype, o_dtype);
 #undef DEC
+#undef DECM
     return VB_OK;
 }

@@ -105,6 +105,11 @@ __device__ __forceinline__ float warp_max(float v) {
     return v;
 }
 
+// KV pool, bf16, head_dim 64: the eight 16-byte chunks of a token row are stored XOR-swizzled by (token & 7), so that a
+// (page, K|V, head) chunk copied linearly into shared memory can be read with ldmatrix without bank conflicts (eight
+// consecutive token rows hit eight different 16-byte bank groups).  Element (slot, e) of a chunk lives at column:
+__host__ __device__ __forceinline__ int vb_pool_col_bf16(int slot, int e) { return ((((e >> 3) ^ (slot & 7)) << 3) | (e & 7)); }
+
 // ------------------------------------------------------------------------------------------------
 // device: sm_100a PTX wrappers
 // ------------------------------------------------------------------------------------------------

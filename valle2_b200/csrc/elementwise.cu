@@ -360,7 +360,8 @@ __global__ void kv_scatter_kernel(const TS* __restrict__ qkv, TD* __restrict__ p
     for (int c = threadIdx.x; c < 2 * d; c += blockDim.x) {
         const int kv = c / d, hd = c % d, h = hd / Dh, e = hd % Dh;
         const float val = to_f32<TS>(src[d + c]);
-        pool[(((static_cast<int64_t>(page) * 2 + kv) * H + h) * 64 + slot) * Dh + e] = from_f32<TD>(val);
+        const int col = (sizeof(TD) == 2 && Dh == 64) ? vb_pool_col_bf16(slot, e) : e;    // bf16 pool rows are chunk-swizzled
+        pool[(((static_cast<int64_t>(page) * 2 + kv) * H + h) * 64 + slot) * Dh + col] = from_f32<TD>(val);
     }
 }
 
@@ -378,6 +379,41 @@ extern "C" int vb_kv_scatter_paged(const void* qkv, int qkv_dtype, void* pool, i
     else if (qkv_dtype == VB_F32 && pool_dtype == VB_BF16) KVS(float, __nv_bfloat16);
     else VB_REQUIRE(false, VB_ERR_UNSUPPORTED, "vb_kv_scatter_paged: dtype combination %d -> %d", qkv_dtype, pool_dtype);
 #undef KVS
+    return VB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// KV prefetch into L2.  The decode step alternates an HBM-bound kernel (paged attention: ~100 MB of KV per layer at
+// B=32) with a latency-bound chain of small GEMM / row kernels that leaves HBM almost idle.  This kernel is launched on a
+// side stream while that chain runs and asks the memory system to pull the NEXT layer's cached pages into L2
+// (cp.async.bulk.prefetch.L2: no destination, fire and forget), so that the next attention kernel finds part of its
+// pages on chip.  A page is one contiguous [2][H][64][Dh] block; it is requested in pieces of <= 64 KB.
+// ------------------------------------------------------------------------------------------------
+__global__ void kv_prefetch_l2_kernel(const uint8_t* __restrict__ pool, int64_t page_bytes, const int32_t* __restrict__ block_table,
+                                      int max_pages, const int32_t* __restrict__ seq_lens, int page_lo_pct, int page_hi_pct) {
+    const int b = blockIdx.y, p = blockIdx.x;
+    const int pages_total = (seq_lens[b] + 63) / 64;
+    const int lo = pages_total * page_lo_pct / 100, hi = (pages_total * page_hi_pct + 99) / 100;
+    if (p < lo || p >= min(hi, pages_total)) return;
+    const int page = block_table[static_cast<int64_t>(b) * max_pages + p];
+    const int64_t piece = 65536;
+    const int64_t off = static_cast<int64_t>(threadIdx.x) * piece;
+    if (off >= page_bytes) return;
+    const uint32_t bytes = static_cast<uint32_t>(min(piece, page_bytes - off));
+    const uint8_t* src = pool + static_cast<int64_t>(page) * page_bytes + off;
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
+
+extern "C" int vb_kv_prefetch_l2(const void* pool, int pool_dtype, const int32_t* block_table, int max_pages,
+                                 const int32_t* seq_lens, int B, int H, int Dh, int page_lo_pct, int page_hi_pct, void* stream) {
+    VB_REQUIRE(pool && block_table && seq_lens, VB_ERR_BAD_ARG, "vb_kv_prefetch_l2: null pointer");
+    VB_REQUIRE(B >= 1 && B <= 65535 && H >= 1 && Dh >= 1 && max_pages >= 1, VB_ERR_BAD_ARG, "vb_kv_prefetch_l2: bad shape");
+    VB_REQUIRE(page_lo_pct >= 0 && page_hi_pct <= 100 && page_lo_pct <= page_hi_pct, VB_ERR_BAD_ARG, "vb_kv_prefetch_l2: bad page range");
+    const int64_t page_bytes = static_cast<int64_t>(2) * H * 64 * Dh * (pool_dtype == VB_BF16 ? 2 : 4);
+    VB_REQUIRE(page_bytes % 16 == 0 && page_bytes <= 32 * 65536, VB_ERR_UNSUPPORTED, "vb_kv_prefetch_l2: page of %lld bytes", (long long)page_bytes);
+    if (page_lo_pct == page_hi_pct) return VB_OK;
+    VB_CUDA(vb_launch(false, kv_prefetch_l2_kernel, dim3(max_pages, B), dim3(32), 0, static_cast<cudaStream_t>(stream),
+                      static_cast<const uint8_t*>(pool), page_bytes, block_table, max_pages, seq_lens, page_lo_pct, page_hi_pct));
     return VB_OK;
 }
 

@@ -86,6 +86,107 @@ __device__ __forceinline__ void emit(const FusedParams& p, int b, int n, float v
     }
 }
 
+// LayerNorm (or plain cast when gamma == null) of this rank's K-slice [col0, col0 + kcols) of the fp32 rows, written as
+// bf16 into the 128B-swizzled activation tiles.  Worker warp wi owns rows wi, wi + 4, ...; a lane holds NCH float4 chunks of
+// a row (columns (lane + 32 ch) * 4 of the slice).  Rows stay in registers across the cluster exchange of the statistics
+// when they fit (RPG rows); otherwise they are read again from L2.
+template <int NCH>
+__device__ __forceinline__ void ln_on_load(const FusedParams& p, float2* stats, uint8_t* smem_gen, int stage_bytes, int col0,
+                                           int kcols, int wi, int lane, int C, bool ln_exchange) {
+    constexpr int RPG = MAXV / NCH;                       // rows per register group
+    const int rows_w = (p.B - wi + 3) >> 2;
+    const bool single = rows_w <= RPG;
+    const bool norm = p.gamma != nullptr;
+    float4 v[MAXV];
+    auto load_group = [&](int g0) {
+#pragma unroll
+        for (int r = 0; r < RPG; ++r)
+#pragma unroll
+            for (int ch = 0; ch < NCH; ++ch) {
+                const int cs = (lane + 32 * ch) * 4;
+                v[r * NCH + ch] = (g0 + r < rows_w && cs < kcols)
+                    ? __ldcg(reinterpret_cast<const float4*>(p.a32 + static_cast<int64_t>(wi + 4 * (g0 + r)) * p.lda32 + col0 + cs))
+                    : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+    };
+    if (norm) {
+        // pass A: (mean, M2) of the slice, two-pass from registers
+        for (int g0 = 0; g0 < rows_w; g0 += RPG) {
+            load_group(g0);
+#pragma unroll
+            for (int r = 0; r < RPG; ++r) {
+                if (g0 + r >= rows_w) break;
+                float s = 0.f;
+#pragma unroll
+                for (int ch = 0; ch < NCH; ++ch) s += (v[r * NCH + ch].x + v[r * NCH + ch].y) + (v[r * NCH + ch].z + v[r * NCH + ch].w);
+                const float mean = kcols > 0 ? warp_sum(s) / kcols : 0.f;    // a rank past the end of K: count 0
+                float q = 0.f;
+#pragma unroll
+                for (int ch = 0; ch < NCH; ++ch) {
+                    if ((lane + 32 * ch) * 4 < kcols) {
+                        const float4 t = v[r * NCH + ch];
+                        const float a = t.x - mean, b = t.y - mean, c = t.z - mean, e = t.w - mean;
+                        q += (a * a + b * b) + (c * c + e * e);
+                    }
+                }
+                q = warp_sum(q);
+                if (lane == 0) stats[wi + 4 * (g0 + r)] = make_float2(mean, q);
+            }
+        }
+    }
+    __syncwarp();
+    if (ln_exchange) cluster_sync_all();          // every rank's slice statistics are in its shared memory
+    // pass B: combine the ranks' statistics (Chan), normalise, store
+    for (int g0 = 0; g0 < rows_w; g0 += RPG) {
+        if (!single || !norm) load_group(g0);
+        float2 st[RPG];
+        if (norm) {
+#pragma unroll
+            for (int r = 0; r < RPG; ++r) {                  // all remote reads first, then the arithmetic
+                st[r] = make_float2(0.f, 0.f);
+                if (g0 + r < rows_w && lane < C) {
+                    const uint32_t la = smem_u32(&stats[wi + 4 * (g0 + r)]);
+                    st[r] = (C > 1) ? ld_dsmem_f32x2(dsmem_addr(la, lane)) : stats[wi + 4 * (g0 + r)];
+                }
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < RPG; ++r) {
+            if (g0 + r >= rows_w) break;
+            const int row = wi + 4 * (g0 + r);
+            float mean = 0.f, rstd = 1.f;
+            if (norm) {
+                const int slice = p.kb_per_cta * BK;
+                float tot = 0.f;
+                for (int l = 0; l < C; ++l) tot += __shfl_sync(0xffffffffu, st[r].x, l) * max(0, min(slice, p.K - l * slice));
+                mean = tot / p.K;
+                float m2 = 0.f;
+                for (int l = 0; l < C; ++l) {
+                    const float dm = __shfl_sync(0xffffffffu, st[r].x, l) - mean;
+                    m2 += __shfl_sync(0xffffffffu, st[r].y, l) + max(0, min(slice, p.K - l * slice)) * dm * dm;
+                }
+                rstd = rsqrtf(m2 / p.K + p.eps);
+            }
+#pragma unroll
+            for (int ch = 0; ch < NCH; ++ch) {
+                const int cs = (lane + 32 * ch) * 4;
+                if (cs < kcols) {
+                    float4 o = v[r * NCH + ch];
+                    if (norm) {
+                        const float4 g = __ldg(reinterpret_cast<const float4*>(p.gamma + col0 + cs));
+                        const float4 bt = __ldg(reinterpret_cast<const float4*>(p.beta + col0 + cs));
+                        o.x = (o.x - mean) * rstd * g.x + bt.x; o.y = (o.y - mean) * rstd * g.y + bt.y;
+                        o.z = (o.z - mean) * rstd * g.z + bt.z; o.w = (o.w - mean) * rstd * g.w + bt.w;
+                    }
+                    const int kb = cs >> 6, cin = cs & 63;
+                    uint8_t* dst = smem_gen + kb * stage_bytes + W_BYTES + row * 128 + (((cin >> 3) ^ (row & 7)) << 4) + ((cin >> 2) & 1) * 8;
+                    *reinterpret_cast<uint2*>(dst) = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
+                }
+            }
+        }
+    }
+}
+
 template <int BN>
 __global__ void __launch_bounds__(THREADS, 1) gemm_decode_fused_kernel(const __grid_constant__ CUtensorMap tm_a,
                                                                        const __grid_constant__ CUtensorMap tm_w,
@@ -177,104 +278,10 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_decode_fused_kernel(const __g
         pdl_wait();
         if (p.late_trigger) pdl_trigger();
         if (p.a_mode == 1) {
-            // ---------------- LayerNorm (or plain cast) on load: this rank's K-slice of the fp32 rows ----------------
-            const int col0 = kb0 * BK;
-            const int kcols = max(0, min(nkb * BK, p.K - col0));       // K % 64 == 0: whole float4 chunks
-            const int nch = (kcols + 127) >> 7;                         // float4 chunks per lane and row
-            const int rows_w = (p.B - wi + 3) >> 2;                     // rows of this warp: wi, wi + 4, ...
-            const bool single = rows_w * nch <= MAXV;                   // the warp's rows stay in registers throughout
-            const int rpg = nch > 0 ? max(1, MAXV / nch) : 1;           // rows per register group
-            float4 v[MAXV];
-            // pass A: partial statistics of the slice (two-pass, from registers)
-            if (p.gamma != nullptr) {
-                for (int g0 = 0; g0 < rows_w; g0 += rpg) {
-#pragma unroll
-                    for (int j = 0; j < MAXV; ++j) {
-                        const int rr = g0 + j / max(nch, 1), ch = j % max(nch, 1);
-                        const int c4 = lane + 32 * ch;
-                        v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (j < rpg * nch && rr < rows_w && c4 * 4 < kcols)
-                            v[j] = __ldcg(reinterpret_cast<const float4*>(p.a32 + static_cast<int64_t>(wi + 4 * rr) * p.lda32 + col0 + c4 * 4));
-                    }
-                    for (int r = 0; r < rpg && g0 + r < rows_w; ++r) {
-                        float s = 0.f;
-#pragma unroll
-                        for (int j = 0; j < MAXV; ++j)
-                            if (j / max(nch, 1) == r) s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
-                        const float mean = kcols > 0 ? warp_sum(s) / kcols : 0.f;
-                        float q = 0.f;
-#pragma unroll
-                        for (int j = 0; j < MAXV; ++j) {
-                            if (j / max(nch, 1) == r && (lane + 32 * (j % max(nch, 1))) * 4 < kcols) {
-                                const float a = v[j].x - mean, b = v[j].y - mean, c = v[j].z - mean, e = v[j].w - mean;
-                                q += (a * a + b * b) + (c * c + e * e);
-                            }
-                        }
-                        q = warp_sum(q);
-                        if (lane == 0) stats[wi + 4 * (g0 + r)] = make_float2(mean, q);
-                    }
-                }
-            }
-            if (ln_exchange) {
-                __syncwarp();
-                cluster_sync_all();          // every rank's slice statistics are in its shared memory
-            } else {
-                __syncwarp();
-            }
-            // pass B: combine the ranks' statistics (Chan), normalise the slice into the swizzled operand tiles
-            for (int g0 = 0; g0 < rows_w; g0 += rpg) {
-                if (!single || p.gamma == nullptr) {
-#pragma unroll
-                    for (int j = 0; j < MAXV; ++j) {
-                        const int rr = g0 + j / max(nch, 1), ch = j % max(nch, 1);
-                        const int c4 = lane + 32 * ch;
-                        v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (j < rpg * nch && rr < rows_w && c4 * 4 < kcols)
-                            v[j] = __ldcg(reinterpret_cast<const float4*>(p.a32 + static_cast<int64_t>(wi + 4 * rr) * p.lda32 + col0 + c4 * 4));
-                    }
-                }
-                for (int r = 0; r < rpg && g0 + r < rows_w; ++r) {
-                    const int row = wi + 4 * (g0 + r);
-                    float mean = 0.f, rstd = 1.f;
-                    if (p.gamma != nullptr) {
-                        float2 mine = make_float2(0.f, 0.f);
-                        if (lane < C) {
-                            const uint32_t la = smem_u32(&stats[row]);
-                            mine = (C > 1) ? ld_dsmem_f32x2(dsmem_addr(la, lane)) : stats[row];
-                        }
-                        float tot = 0.f;
-                        for (int l = 0; l < C; ++l) {
-                            const int cnt = max(0, min(p.kb_per_cta * BK, p.K - l * p.kb_per_cta * BK));
-                            tot += __shfl_sync(0xffffffffu, mine.x, l) * cnt;
-                        }
-                        mean = tot / p.K;
-                        float m2 = 0.f;
-                        for (int l = 0; l < C; ++l) {
-                            const int cnt = max(0, min(p.kb_per_cta * BK, p.K - l * p.kb_per_cta * BK));
-                            const float dm = __shfl_sync(0xffffffffu, mine.x, l) - mean;
-                            m2 += __shfl_sync(0xffffffffu, mine.y, l) + cnt * dm * dm;
-                        }
-                        rstd = rsqrtf(m2 / p.K + p.eps);
-                    }
-#pragma unroll
-                    for (int j = 0; j < MAXV; ++j) {
-                        const int ch = j % max(nch, 1);
-                        const int cs = (lane + 32 * ch) * 4;            // column inside the slice
-                        if (j / max(nch, 1) == r && cs < kcols) {
-                            float4 o = v[j];
-                            if (p.gamma != nullptr) {
-                                const float4 g = __ldg(reinterpret_cast<const float4*>(p.gamma + col0 + cs));
-                                const float4 bt = __ldg(reinterpret_cast<const float4*>(p.beta + col0 + cs));
-                                o.x = (o.x - mean) * rstd * g.x + bt.x; o.y = (o.y - mean) * rstd * g.y + bt.y;
-                                o.z = (o.z - mean) * rstd * g.z + bt.z; o.w = (o.w - mean) * rstd * g.w + bt.w;
-                            }
-                            const int kb = cs >> 6, cin = cs & 63;
-                            uint8_t* dst = smem_gen + kb * STAGE_BYTES + W_BYTES + row * 128 + (((cin >> 3) ^ (row & 7)) << 4) + ((cin >> 2) & 1) * 8;
-                            *reinterpret_cast<uint2*>(dst) = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
-                        }
-                    }
-                }
-            }
+            const int kcols = max(0, min(nkb * BK, p.K - kb0 * BK));       // K % 64 == 0: whole float4 chunks
+            if (kcols <= 128) ln_on_load<1>(p, stats, smem_gen, STAGE_BYTES, kb0 * BK, kcols, wi, lane, C, ln_exchange);
+            else if (kcols <= 256) ln_on_load<2>(p, stats, smem_gen, STAGE_BYTES, kb0 * BK, kcols, wi, lane, C, ln_exchange);
+            else ln_on_load<4>(p, stats, smem_gen, STAGE_BYTES, kb0 * BK, kcols, wi, lane, C, ln_exchange);
             fence_proxy_async();
             __syncwarp();
             if (lane == 0)
@@ -320,8 +327,12 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_decode_fused_kernel(const __g
                 const int b = e / nr, n = n_lo + (e - b * nr);
                 if (n0 + n >= p.N) continue;
                 const uint32_t la = smem_base + static_cast<uint32_t>(b * BM + n) * 4u;
+                float t[16];
+#pragma unroll
+                for (int r = 0; r < 16; ++r) t[r] = (r < C) ? ld_dsmem_f32(dsmem_addr(la, r)) : 0.f;   // all loads in flight
                 float acc = 0.f;
-                for (int r = 0; r < C; ++r) acc += ld_dsmem_f32(dsmem_addr(la, r));      // fixed rank order
+#pragma unroll
+                for (int r = 0; r < 16; ++r) acc += t[r];                                              // fixed rank order
                 emit(p, b, n0 + n, acc);
             }
         }

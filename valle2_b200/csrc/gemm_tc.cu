@@ -35,7 +35,15 @@ struct GemmParams {
     int64_t part_stride;
     int64_t part_ld;           // N (row pitch of a partial slice)
     int late_trigger;          // release the dependent kernel only after our own pdl_wait (see vb_linear_decode flags)
+    unsigned long long* dbg;   // optional %globaltimer stamps [cta][8] (vb_linear_decode_set_debug)
 };
+
+__device__ __forceinline__ unsigned long long gtimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define DBG_STAMP(i) do { if (p.dbg) p.dbg[blockIdx.x * 8 + (i)] = gtimer(); } while (0)
 
 template <int BN, int STAGES, bool SWAP>
 __global__ void __launch_bounds__(num_threads(SWAP), 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a,
@@ -76,6 +84,7 @@ __global__ void __launch_bounds__(num_threads(SWAP), 1) gemm_tc_kernel(const __g
     const uint32_t tmem_base = tmem_base_slot;
 
     const int total_tiles = p.tiles_a * p.tiles_b * p.n_split;
+    if (threadIdx.x == 0) DBG_STAMP(0);                                   // prologue done
 
     if (!p.late_trigger) pdl_trigger();
     if (warp == 0) {
@@ -103,7 +112,9 @@ __global__ void __launch_bounds__(num_threads(SWAP), 1) gemm_tc_kernel(const __g
                     else      tma_load_2d(sa + A_BYTES, &tm_b, fb, kb * BK, tb * BN);
                 }
             }
+            DBG_STAMP(1);                                                     // weight tiles requested
             pdl_wait();
+            DBG_STAMP(2);                                                     // dependency resolved
             if (p.late_trigger) pdl_trigger();
             int stage = 0, n = 0;
             uint32_t phase = 0;
@@ -147,6 +158,7 @@ __global__ void __launch_bounds__(num_threads(SWAP), 1) gemm_tc_kernel(const __g
                 for (int kb = kb0; kb < kb1; ++kb) {
                     if (SWAP) mbar_wait(smem_u32(&full_bar[stage]), phase);
                     else mbar_wait_relaxed(smem_u32(&full_bar[stage]), phase);
+                    if (kb == kb0) DBG_STAMP(3);                              // first k-block (weights + activations) landed
                     tc_fence_after();
                     const uint32_t sa = smem_base + stage * STAGE_BYTES;
 #pragma unroll
@@ -159,6 +171,7 @@ __global__ void __launch_bounds__(num_threads(SWAP), 1) gemm_tc_kernel(const __g
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
                 umma_commit(smem_u32(&tfull_bar[acc]));
+                DBG_STAMP(4);                                                 // last MMA of the tile issued
             }
         }
     } else {
@@ -175,6 +188,7 @@ __global__ void __launch_bounds__(num_threads(SWAP), 1) gemm_tc_kernel(const __g
             const int acc = local & 1;
             const uint32_t acc_phase = (local >> 1) & 1;
             mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase);
+            if (threadIdx.x == 64) DBG_STAMP(5);                              // accumulator complete
             tc_fence_after();
             const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
             const int row = ta * BM + q * 32 + lane;  // row of the A operand owned by this thread
@@ -286,6 +300,7 @@ __global__ void __launch_bounds__(num_threads(SWAP), 1) gemm_tc_kernel(const __g
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[acc]));
+            if (threadIdx.x == 64) DBG_STAMP(6);                              // epilogue stores issued
         }
     }
     tc_fence_before();
@@ -351,6 +366,12 @@ extern "C" int vb_linear_decode_splits(int64_t N, int64_t K, int max_split) {
     return (int)vb_ceil_div(kb_total, kb_per_split);
 }
 
+static unsigned long long* g_gemm_dbg = nullptr;
+extern "C" int vb_linear_decode_set_debug(void* buf) {   /* device buffer of #SM * 8 uint64 stamps, or NULL */
+    g_gemm_dbg = static_cast<unsigned long long*>(buf);
+    return VB_OK;
+}
+
 extern "C" int vb_linear_decode(const void* x, int64_t ldx, const void* w, int64_t ldw, float* part, int64_t part_stride,
                                 int64_t M, int64_t N, int64_t K, int max_split, int flags, int* n_split_out, void* stream) {
     VB_REQUIRE(x && w && part, VB_ERR_BAD_ARG, "vb_linear_decode: null pointer");
@@ -367,6 +388,7 @@ extern "C" int vb_linear_decode(const void* x, int64_t ldx, const void* w, int64
     p.n_split = n_split;
     p.part = part; p.part_stride = part_stride; p.part_ld = N;
     p.late_trigger = (flags & VB_FLAG_LATE_TRIGGER) ? 1 : 0;
+    p.dbg = g_gemm_dbg;
     VB_REQUIRE(n_split == 1 || part_stride >= M * N, VB_ERR_BAD_ARG, "vb_linear_decode: part_stride too small");
     if (n_split_out) *n_split_out = n_split;
     CUtensorMap ta, tb;

@@ -145,7 +145,7 @@ class ARDecoder:
         self.page_permutation_seed = None      # tests: scatter the logical pages over the pool
         # tunables (env overrides are for experiments; the defaults are the measured best)
         self.use_chain = os.environ.get('VALLE_B200_CHAIN', '0') != '0'
-        self.use_fused = os.environ.get('VALLE_B200_FUSED', '1') != '0'
+        self.use_fused = os.environ.get('VALLE_B200_FUSED', '0') != '0'
         # cluster size along K of the fused decode GEMMs (0 = fill the SMs), csrc/gemm_decode_fused.cu
         self.fused_cluster = {'qkv': 0, 'o': 0, 'f1': 0, 'f2': 0, 'lg': 0}
         for k, v in [kv.split('=') for kv in os.environ.get('VALLE_B200_FUSED_CLUSTER', '').split(';') if kv]:
@@ -153,6 +153,11 @@ class ARDecoder:
         self.n_sub_override = int(os.environ.get('VALLE_B200_SUBBATCH', '0'))
         self.attn_ctas = int(os.environ.get('VALLE_B200_ATTN_CTAS', '0'))
         self.n_tsplit_override = 0             # tests: pin the flash-decoding split
+        # percentage range of every sequence's cached pages of the NEXT layer pulled into L2 while the GEMM chain runs
+        pf = os.environ.get('VALLE_B200_KV_PREFETCH', '0,0').split(',')
+        self.kv_prefetch = (int(pf[0]), int(pf[1]))
+        self._pf_stream = None
+        self.attn_flags = ops.FLAG_ATTN_SIMT if os.environ.get('VALLE_B200_ATTN_SIMT', '0') != '0' else 0
 
     # ------------------------------------------------------------------------------------------
     def _n_sub(self, B: int) -> int:
@@ -303,7 +308,7 @@ class ARDecoder:
                 ops.linear_decode_fused(x, L['wqkv'], sub['qkv32'], gamma=g[0], beta=b[0], eps=eps, cluster_k=cl['qkv'],
                                         flags=ops.FLAG_LATE_TRIGGER)
                 ops.attn_decode_paged(sub['qkv32'], 1, 0, st['pools'][li], sub['block_table'], sub['seq_lens'], sub['o'],
-                                      B, H, Dh, sub['n_tsplit'], sub['attn_ws'], ops.FLAG_PREFETCH_KV)
+                                      B, H, Dh, sub['n_tsplit'], sub['attn_ws'], ops.FLAG_PREFETCH_KV | self.attn_flags)
                 ops.linear_decode_fused(sub['o'], L['wo'], x, bias=L['bo'], residual=True, cluster_k=cl['o'])
                 g, b, eps = L['norm2']
                 ops.linear_decode_fused(x, L['w1'], sub['f'], bias=L['b1'], gelu=True, gamma=g[0], beta=b[0], eps=eps,
@@ -320,7 +325,7 @@ class ARDecoder:
             for li, L in enumerate(layers):
                 ops.attn_decode_paged(sub['p_qkv'], ns['qkv'], B * 3 * d, st['pools'][li], sub['block_table'],
                                       sub['seq_lens'], sub['o'], B, H, Dh, sub['n_tsplit'], sub['attn_ws'],
-                                      ops.FLAG_PREFETCH_KV)
+                                      ops.FLAG_PREFETCH_KV | self.attn_flags)
                 g2, b2, eps2 = L['norm2']
                 ph = [ops.chain_gemm(sub['o'], L['wo'], sub['p_o'], B * d),
                       ops.chain_ln(x, g2[0], b2[0], sub['h'], part=sub['p_o'], n_part=ns['o'], part_stride=B * d,
@@ -353,7 +358,8 @@ class ARDecoder:
                 ops.linear_decode(sub['h'], L['wqkv'], sub['p_qkv'], B * 3 * d, 32, ops.FLAG_LATE_TRIGGER)
                 ops.attn_decode_paged(sub['p_qkv'], ns['qkv'], B * 3 * d, st['pools'][li], sub['block_table'],
                                       sub['seq_lens'], sub['o'], B, H, Dh, sub['n_tsplit'], sub['attn_ws'],
-                                      ops.FLAG_PREFETCH_KV)
+                                      ops.FLAG_PREFETCH_KV | self.attn_flags)
+                self._prefetch_next_kv(sub, li)
                 ops.linear_decode(sub['o'], L['wo'], sub['p_o'], B * d, 32)
                 g, b, eps = L['norm2']
                 ops.residual_layernorm(x, g[0], b[0], sub['h'], part=sub['p_o'], n_part=ns['o'], part_stride=B * d,
@@ -363,6 +369,7 @@ class ARDecoder:
                 ops.linear_decode(sub['f'], L['w2'], sub['p_f2'], B * d, 32)
             ops.residual_layernorm(x, None, None, None, part=sub['p_f2'], n_part=ns['f2'], part_stride=B * d,
                                    bias=layers[-1]['b2'])
+            self._prefetch_join(sub)
         else:
             for li, L in enumerate(layers):
                 g, b, eps = L['norm1']
@@ -377,6 +384,30 @@ class ARDecoder:
                 ops.linear(sub['f'], L['w2'], L['b2'], residual=x, out=x)
         self._logits_sample_book(sub, x, samp, uniforms, eos)
 
+    def _prefetch_next_kv(self, sub: dict, li: int):
+        """After layer li's attention has been launched: on a side stream (ordered after that attention), ask for the
+        next layer's pages (layer 0 of the next step after the last layer).  Joined in _decode_step's caller."""
+        lo, hi = self.kv_prefetch
+        if hi <= lo or self.precision != 'bf16':
+            return
+        st = self._state
+        if self._pf_stream is None:
+            self._pf_stream = torch.cuda.Stream(device=self.device)
+        cur = torch.cuda.current_stream()
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        self._pf_stream.wait_event(ev)
+        nxt = (li + 1) % len(self.weights.layers)
+        with torch.cuda.stream(self._pf_stream):
+            ops.kv_prefetch_l2(st['pools'][nxt], sub['block_table'], sub['seq_lens'], sub['B'], self.H, self.Dh, lo, hi)
+        sub['_pf_used'] = True
+
+    def _prefetch_join(self, sub: dict):
+        if sub.pop('_pf_used', False):
+            ev = torch.cuda.Event()
+            ev.record(self._pf_stream)
+            torch.cuda.current_stream().wait_event(ev)
+
     def launches_per_step(self) -> int:
         """Kernel launches of one decode step (all sub-batches) -- the bench's gpu_launches claim."""
         L = len(self.weights.layers)
@@ -389,6 +420,8 @@ class ARDecoder:
                 total += 1 + 1 + 2 * L + 2          # embed, first chain, (attention + chain) per layer, sample, bookkeeping
             elif self.precision == 'bf16':
                 total += 1 + 8 * L + 1 + 2 + 2      # embed, 8 per layer, x-update, cast + logits, sample + bookkeeping
+                if self.kv_prefetch[1] > self.kv_prefetch[0]:
+                    total += L                      # one L2 prefetch launch per layer (side stream)
             else:
                 total += 1 + 7 * L + 1 + 2
         return total

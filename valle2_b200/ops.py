@@ -11,7 +11,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import (FLAG_LATE_TRIGGER, FLAG_PREFETCH_KV, EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RESIDUAL, EPI_NONE, MASK_EXPLICIT, MASK_NONE,
+from ._lib import (FLAG_ATTN_SIMT, FLAG_LATE_TRIGGER, FLAG_PREFETCH_KV, EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RESIDUAL, EPI_NONE, MASK_EXPLICIT, MASK_NONE,
                    MASK_PREFIX_LM, VB_BF16, VB_F32, check)
 
 __all__ = ['EPI_NONE', 'EPI_BIAS', 'EPI_BIAS_GELU', 'EPI_BIAS_RESIDUAL', 'MASK_NONE', 'MASK_PREFIX_LM',
@@ -221,6 +221,13 @@ def attn_decode_paged(qkv_part: torch.Tensor, n_part: int, part_stride: int, poo
                                     _ptr(block_table), block_table.shape[1], _ptr(seq_lens), _ptr(out),
                                     _code(out.dtype), B, H, Dh, n_tsplit, flags, _ptr(ws), _stream()),
           'vb_attn_decode_paged')
+
+
+def kv_prefetch_l2(pool: torch.Tensor, block_table: torch.Tensor, seq_lens: torch.Tensor, B: int, H: int, Dh: int,
+                   page_lo_pct: int = 0, page_hi_pct: int = 100) -> None:
+    """Hint: pull the cached pages (a percentage range of every sequence's pages) of one layer's pool into L2."""
+    check(_L().vb_kv_prefetch_l2(_ptr(pool), _code(pool.dtype), _ptr(block_table), block_table.shape[1], _ptr(seq_lens),
+                                 B, H, Dh, page_lo_pct, page_hi_pct, _stream()), 'vb_kv_prefetch_l2')
 
 
 def sample(logits_part: torch.Tensor, n_part: int, part_stride: int, row_stride: int, R: int, V: int, *,
