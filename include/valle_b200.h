@@ -107,8 +107,8 @@ int vb_linear_decode(const void* x, int64_t ldx, const void* w, int64_t ldw, flo
                      int64_t M, int64_t N, int64_t K, int max_split, int flags, int* n_split_out, void* stream);
 
 /* Profiling aid: subsequent vb_linear_decode launches write %globaltimer stamps [cta][8] = {prologue done, weights requested,
- * dependency resolved, first k-block landed, MMAs issued, accumulator complete, epilogue stores issued} (uint64, device
- * memory, #SM*8 entries); NULL switches it off. */
+ * dependency resolved, first k-block landed, MMAs issued, accumulator complete, epilogue stores issued, -} followed by the
+ * same eight events as SM cycle counters (uint64, device memory, #SM*16 entries); NULL switches it off. */
 int vb_linear_decode_set_debug(void* buf);
 
 /* Decode-shape GEMM with the split-K reduction, LayerNorm and epilogue fused in (csrc/gemm_decode_fused.cu), B <= 64:

@@ -205,7 +205,7 @@ def test_decode_chain_matches_separate_kernels(ops, B, d, F):
             ops.chain_gemm(c['h2'], wq, c['p_qkv'], B * 3 * d)], B, gbar)
         torch.cuda.synchronize()
         assert int(gbar[0].item()) == 0, 'grid-barrier counter not reset'
-        assert torch.equal(c['p_o'], r['p_o']), 'out-proj slices differ'
+        assert rel_err(c['p_o'][:ns['o']].sum(0), r['p_o'][:ns['o']].sum(0)) < 1e-5, 'out-proj slices differ'
         # downstream stages see LN / GELU rows that may differ by fp32 round-off before the bf16 rounding
         assert rel_err(c['x'], r['x']) < 2e-3      # after FFN2: bf16 roundings of h / f may flip by one ulp
         for k in ('h', 'f', 'h2'):

@@ -43,7 +43,9 @@ __device__ __forceinline__ unsigned long long gtimer() {
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
-#define DBG_STAMP(i) do { if (p.dbg) p.dbg[blockIdx.x * 8 + (i)] = gtimer(); } while (0)
+// stamps 0..6: %globaltimer (comparable across SMs, ~0.26 us resolution); the same events as SM cycle counts go to
+// slots 8..14 (exact intervals inside one CTA)
+#define DBG_STAMP(i) do { if (p.dbg) { p.dbg[blockIdx.x * 16 + (i)] = gtimer(); p.dbg[blockIdx.x * 16 + 8 + (i)] = clock64(); } } while (0)
 
 template <int BN, int STAGES, bool SWAP>
 __global__ void __launch_bounds__(num_threads(SWAP), 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a,
@@ -51,7 +53,12 @@ __global__ void __launch_bounds__(num_threads(SWAP), 1) gemm_tc_kernel(const __g
     constexpr int A_BYTES = BM * BK * 2;
     constexpr int B_BYTES = BN * BK * 2;
     constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+    // NACC independent accumulators per tile (summed by the epilogue) were tried for the narrow decode tiles, on the theory
+    // that four MMAs of a k-block accumulating into ONE TMEM tile run at MMA latency: measured no change (~400 cycles per
+    // k-block either way, the issue rate of 128x32x16 MMAs) and +190 cycles of TMEM loads, so one accumulator it is.
+    constexpr int NACC = 1;
+    constexpr int ACC_COLS = NACC * BN;             // TMEM columns of one (multi-)accumulator; two of them are in flight
+    constexpr int TMEM_COLS = (2 * ACC_COLS <= 32) ? 32 : (2 * ACC_COLS <= 64) ? 64 : (2 * ACC_COLS <= 128) ? 128 : (2 * ACC_COLS <= 256) ? 256 : 512;
     constexpr uint32_t IDESC = umma_idesc_bf16(BM, BN, 0, 0);
 
     extern __shared__ uint8_t smem_raw[];
@@ -154,7 +161,7 @@ __global__ void __launch_bounds__(num_threads(SWAP), 1) gemm_tc_kernel(const __g
                 if (SWAP) mbar_wait(smem_u32(&tempty_bar[acc]), acc_phase ^ 1);
                 else mbar_wait_relaxed(smem_u32(&tempty_bar[acc]), acc_phase ^ 1);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + acc * BN;
+                const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
                 for (int kb = kb0; kb < kb1; ++kb) {
                     if (SWAP) mbar_wait(smem_u32(&full_bar[stage]), phase);
                     else mbar_wait_relaxed(smem_u32(&full_bar[stage]), phase);
@@ -165,7 +172,7 @@ __global__ void __launch_bounds__(num_threads(SWAP), 1) gemm_tc_kernel(const __g
                     for (int kk = 0; kk < BK / UMMA_K; ++kk) {
                         const uint64_t da = umma_desc_sw128(sa + kk * UMMA_K * 2, 16, 1024);
                         const uint64_t db = umma_desc_sw128(sa + A_BYTES + kk * UMMA_K * 2, 16, 1024);
-                        umma_f16(d_tmem, da, db, IDESC, (kb > kb0 || kk > 0) ? 1u : 0u);
+                        umma_f16(d_tmem + (kk % NACC) * BN, da, db, IDESC, (kb > kb0 || kk >= NACC) ? 1u : 0u);
                     }
                     umma_commit(smem_u32(&empty_bar[stage]));
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -190,20 +197,53 @@ __global__ void __launch_bounds__(num_threads(SWAP), 1) gemm_tc_kernel(const __g
             mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase);
             if (threadIdx.x == 64) DBG_STAMP(5);                              // accumulator complete
             tc_fence_after();
-            const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
+            const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * ACC_COLS;
             const int row = ta * BM + q * 32 + lane;  // row of the A operand owned by this thread
             if (SWAP) {
                 // D[n][m]: this thread owns weight row n; columns are batch rows m.
                 float* dst = p.part + split * p.part_stride + row;
                 constexpr int CH = (BN >= 32) ? 32 : 16;
+                const int ew = warp - 2;
+                float* stg = reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw)) + STAGES * STAGE_BYTES) + ew * (32 * 32);
+                // vector path: the warp's 32 weight rows x 32 batch rows go through a shared-memory transpose so that each
+                // store instruction writes 16 bytes per lane along n (8 lanes = one 128-byte row segment) -- four times fewer
+                // store instructions than one 4-byte store per (n, m) (measured: ~50 cycles per store instruction)
+                const bool vec = ((p.part_ld & 3) == 0) && ((p.part_stride & 3) == 0) && (ta * BM + q * 32 + 32 <= p.rows_a);
 #pragma unroll 1
                 for (int c0 = 0; c0 < BN; c0 += CH) {
                     if (c0 >= p.rows_b) break;
                     uint32_t v[CH];
                     if constexpr (CH == 32) tmem_ld_32x32(t_addr + c0, reinterpret_cast<uint32_t(&)[32]>(v));
                     else tmem_ld_32x16(t_addr + c0, reinterpret_cast<uint32_t(&)[16]>(v));
-                    tmem_ld_wait();
-                    if (row < p.rows_a) {
+                    if constexpr (NACC > 1) {
+#pragma unroll
+                        for (int a = 1; a < NACC; ++a) {
+                            uint32_t w[CH];
+                            if constexpr (CH == 32) tmem_ld_32x32(t_addr + a * BN + c0, reinterpret_cast<uint32_t(&)[32]>(w));
+                            else tmem_ld_32x16(t_addr + a * BN + c0, reinterpret_cast<uint32_t(&)[16]>(w));
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int j = 0; j < CH; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(w[j]));
+                        }
+                    } else {
+                        tmem_ld_wait();
+                    }
+                    if (threadIdx.x == 64 && c0 == 0) DBG_STAMP(6);           // accumulator in registers
+                    if (vec) {
+#pragma unroll
+                        for (int j = 0; j < CH; ++j) stg[j * 32 + lane] = empty_slice ? 0.f : __uint_as_float(v[j]);
+                        __syncwarp();
+                        const int n4 = (lane & 7) * 4, msub = lane >> 3;
+#pragma unroll
+                        for (int it = 0; it < CH / 4; ++it) {
+                            const int mm = it * 4 + msub, m = c0 + mm;
+                            if (m < p.rows_b) {
+                                const float4 val = *reinterpret_cast<const float4*>(stg + mm * 32 + n4);
+                                *reinterpret_cast<float4*>(p.part + split * p.part_stride + static_cast<int64_t>(m) * p.part_ld + ta * BM + q * 32 + n4) = val;
+                            }
+                        }
+                        __syncwarp();
+                    } else if (row < p.rows_a) {
 #pragma unroll
                         for (int j = 0; j < CH; ++j) {
                             const int m = c0 + j;
@@ -300,7 +340,7 @@ __global__ void __launch_bounds__(num_threads(SWAP), 1) gemm_tc_kernel(const __g
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[acc]));
-            if (threadIdx.x == 64) DBG_STAMP(6);                              // epilogue stores issued
+            if (threadIdx.x == 64) DBG_STAMP(7);                              // epilogue stores issued, TMEM released
         }
     }
     tc_fence_before();
@@ -313,7 +353,7 @@ __global__ void __launch_bounds__(num_threads(SWAP), 1) gemm_tc_kernel(const __g
 
 template <int BN, int STAGES, bool SWAP>
 int launch_gemm_tc(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
-    constexpr int SMEM = STAGES * (BM * BK * 2 + BN * BK * 2) + 1024 + (SWAP ? 0 : epi_warps(false) * STG_BYTES_PER_WARP);
+    constexpr int SMEM = STAGES * (BM * BK * 2 + BN * BK * 2) + 1024 + epi_warps(SWAP) * STG_BYTES_PER_WARP;
     static bool configured = false;
     auto kern = gemm_tc_kernel<BN, STAGES, SWAP>;
     if (!configured) {
@@ -389,6 +429,7 @@ extern "C" int vb_linear_decode(const void* x, int64_t ldx, const void* w, int64
     p.part = part; p.part_stride = part_stride; p.part_ld = N;
     p.late_trigger = (flags & VB_FLAG_LATE_TRIGGER) ? 1 : 0;
     p.dbg = g_gemm_dbg;
+
     VB_REQUIRE(n_split == 1 || part_stride >= M * N, VB_ERR_BAD_ARG, "vb_linear_decode: part_stride too small");
     if (n_split_out) *n_split_out = n_split;
     CUtensorMap ta, tb;
