@@ -204,6 +204,32 @@ int vb_attn_decode_paged(const float* qkv_part, int n_part, int64_t part_stride,
 int vb_kv_prefetch_l2(const void* pool, int pool_dtype, const int32_t* block_table, int max_pages, const int32_t* seq_lens,
                       int B, int H, int Dh, int page_lo_pct, int page_hi_pct, void* stream);
 
+/* ---- training step, backward pass (csrc/train.cu) ------------------------------------------------------------------ */
+/* The backward GEMMs (dgrad = dY.W, wgrad = dY^T.X) are vb_linear calls on transposed operands; these are the rest.
+ * Replaces torch autograd under ValleAR.training_step (valle_ar.py:43-90) / ValleNAR.training_step (valle_nar.py:53-105). */
+int vb_transpose(const void* src, int dtype, int64_t rows, int64_t cols, int64_t lds, void* dst, int64_t ldd, void* stream);
+/* out[n] (+)= scale * sum_r x[r][n], deterministic */
+int vb_colsum(const void* x, int dtype, int64_t R, int N, int64_t ldx, float* out, int accumulate, float scale, void* stream);
+/* y = gelu_erf(pre);  dpre = dy * gelu_erf'(pre)   (modules.py:216) */
+int vb_gelu_fwd(const void* pre, int dtype, void* y, int64_t n, void* stream);
+int vb_gelu_bwd(const void* pre, const void* dy, int dtype, void* dpre, int64_t n, void* stream);
+/* LayerNorm backward: dx[R][d] (fp32) += d/dx of LN(x; gamma, beta) applied to dy; dgamma_part / dbeta_part receive
+ * vb_layernorm_bwd_blocks(R) partial rows of d floats (reduce them with vb_colsum).  gamma == NULL: the forward was a plain
+ * cast, dx += dy. */
+int vb_layernorm_bwd_blocks(int64_t R);
+int vb_layernorm_bwd(const float* x, const float* gamma, const void* dy, int dy_dtype, float* dx, float* dgamma_part,
+                     float* dbeta_part, int64_t R, int d, float eps, void* stream);
+/* Attention backward over packed qkv rows [B*S][3][H][64] (dtype f32/bf16): dqkv from dO, o; lse/delta are fp32 [B][H][S]
+ * work buffers.  mask_mode VB_MASK_NONE or VB_MASK_PREFIX_LM with the forward's predicate (x_lens, kv_lens). */
+int vb_attention_bwd(const void* qkv, const void* o, const void* dO, void* dqkv, int dtype, float* lse, float* delta, int B,
+                     int S, int H, int Dh, int mask_mode, const int32_t* x_lens, const int32_t* kv_lens, void* stream);
+/* loss_rows[r] = logsumexp(logits[r]) - logits[r][target[r]];  dlogits[r] = (softmax(logits[r]) - onehot) * scale (nullable) */
+int vb_cross_entropy(const float* logits, int64_t ld, const int32_t* target, int64_t R, int V, float* loss_rows,
+                     float* dlogits, int64_t ldd, float scale, void* stream);
+/* grad_tables[j][ids[b][t][j]][:] += dx[row(b,t)][:] for j < nq(t): the transpose of vb_embed_sum_pe (PE has no gradient) */
+int vb_embed_bwd(const int32_t* ids, const float* dx, float* grad_tables, int B, int T, int Q, int V, int d, int t_split,
+                 int nq_a, int nq_b, int64_t rows_per_batch, int64_t row_offset, void* stream);
+
 /* ---- K9-K12: logits -> temperature -> top-k -> top-p -> sample (+ log-prob) --------------------------------------- */
 /* logits[r][:] = sum_s logits_part[s*part_stride + r*row_stride + :], r < R, V <= 4096.
  * utils.py:59-66 + transformers 4.38.2 top_k_top_p_filtering: /temperature; keep >= k-th largest (ties kept);

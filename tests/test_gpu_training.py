@@ -1,0 +1,218 @@
+"""Training step: loss and EVERY parameter gradient of ValleAR.training_step / ValleNAR.training_step computed
+by the CUDA stack (valle2_b200/train.py + csrc/train.cu) against torch autograd over the CPU oracle's restatement of the
+same step, plus kernel-level checks of the backward kernels.  fp32 validation mode: 1e-4; bf16: 3e-2 of the gradient's
+scale (bf16 operands, fp32 accumulation)."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+import valle2_b200  # noqa: E402
+from oracle import synth  # noqa: E402
+from oracle import valle_oracle as vo  # noqa: E402
+from test_gpu_models import build, rel_err  # noqa: E402
+
+
+@pytest.fixture(autouse=True)
+def _restore_precision():
+    prev = valle2_b200.get_precision()
+    yield
+    valle2_b200.set_precision(prev)
+
+
+@pytest.fixture(scope='module')
+def ops():
+    from valle2_b200 import ops as _ops
+    return _ops
+
+
+def _oracle_grads(sd, loss_fn):
+    sdg = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and not k.endswith('.pe') else v) for k, v in sd.items()}
+    loss = loss_fn(sdg)
+    loss.backward()
+    return loss.detach(), {k: v.grad for k, v in sdg.items() if getattr(v, 'grad', None) is not None}
+
+
+def _ar_batch(oc, B, Tx, Ty, seed, ragged=True):
+    g = torch.Generator().manual_seed(seed)
+    tokens = torch.randint(0, 256, (B, Tx), generator=g)
+    codes = torch.randint(0, 1024, (B, Ty), generator=g)
+    codes[:, 0] = oc.bos_token
+    target = torch.randint(0, 1025, (B, Ty), generator=g)
+    tl = torch.full((B,), Tx)
+    cl = torch.full((B,), Ty)
+    if ragged and B > 1:
+        tl[1:] = torch.randint(max(1, Tx // 2), Tx + 1, (B - 1,), generator=g)
+        cl[1:] = torch.randint(max(2, Ty // 2), Ty + 1, (B - 1,), generator=g)
+    return {'tokens': tokens, 'codes': codes, 'target': target, 'tokens_lens': tl, 'codes_lens': cl}
+
+
+@pytest.mark.parametrize('precision,tol', [('fp32', 1e-4), ('bf16', 3e-2)])
+@pytest.mark.parametrize('B,Tx,Ty', [(2, 7, 11), (3, 20, 70)])
+def test_ar_training_step_gradients_vs_oracle_autograd(tmp_path, precision, tol, B, Tx, Ty):
+    valle2_b200.set_precision(precision)
+    oc = synth.tiny_config('LayerNorm')
+    model, sd = build('ValleAR', oc, tmp_path, 3)
+    model.train()
+    batch = _ar_batch(oc, B, Tx, Ty, 5)
+    ref_loss, ref = _oracle_grads(sd, lambda s: vo.ar_teacher_forced(s, oc, batch['tokens'], batch['codes'], batch['tokens_lens'],
+                                                                     batch['codes_lens'], batch['target'])[1])
+    loss = model.training_step(batch)
+    assert loss.requires_grad
+    loss.backward()
+    assert abs(loss.item() - ref_loss.item()) < (1e-4 if precision == 'fp32' else 5e-2)
+    checked = 0
+    for name, p in model.named_parameters():
+        assert name in ref, name
+        assert p.grad is not None, name
+        scale = ref[name].abs().max().item() + 1e-12
+        err = (p.grad.cpu().double() - ref[name].double()).abs().max().item() / scale
+        assert err < tol, (name, err)
+        checked += 1
+    assert checked == len(ref)
+
+
+@pytest.mark.parametrize('precision,tol', [('fp32', 1e-4), ('bf16', 3e-2)])
+@pytest.mark.parametrize('layer', [1, 4, 7])
+def test_nar_training_step_gradients_vs_oracle_autograd(tmp_path, precision, tol, layer):
+    valle2_b200.set_precision(precision)
+    oc = synth.tiny_config('AdaptiveLayerNorm')
+    model, sd = build('ValleNAR', oc, tmp_path, 4)
+    model.train()
+    g = torch.Generator().manual_seed(6)
+    B, Tx, T = 2, 6, 13
+    batch = {'tokens': torch.randint(0, 256, (B, Tx), generator=g), 'codes': torch.randint(0, 1024, (B, T, 8), generator=g),
+             'tokens_lens': torch.full((B,), Tx), 'codes_lens': torch.full((B,), T)}
+    ref_loss, ref = _oracle_grads(sd, lambda s: vo.nar_teacher_forced(s, oc, batch['tokens'], batch['codes'], batch['tokens_lens'],
+                                                                      batch['codes_lens'], layer)[1])
+    loss = model.training_step(batch, layer=layer)
+    loss.backward()
+    assert abs(loss.item() - ref_loss.item()) < (1e-4 if precision == 'fp32' else 5e-2)
+    n_checked = 0
+    for name, p in model.named_parameters():
+        if name not in ref:          # parameters of other stages: no gradient on either side
+            assert p.grad is None or float(p.grad.abs().max()) == 0.0, name
+            continue
+        assert p.grad is not None, name
+        scale = ref[name].abs().max().item() + 1e-12
+        err = (p.grad.cpu().double() - ref[name].double()).abs().max().item() / scale
+        assert err < tol, (name, err)
+        n_checked += 1
+    assert n_checked >= 12 * 2 + 4
+
+
+def test_training_step_drives_an_optimizer(tmp_path):
+    """configure_optimizers + three AdamW steps on a fixed batch lower the loss (the loop Lightning would run,
+    train_model.py:28-35)."""
+    valle2_b200.set_precision('fp32')
+    oc = synth.tiny_config('LayerNorm')
+    model, _ = build('ValleAR', oc, tmp_path, 8)
+    model.train()
+    batch = _ar_batch(oc, 2, 6, 12, 9, ragged=False)
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-3)
+    losses = []
+    for _ in range(4):
+        opt.zero_grad()
+        loss = model.training_step(batch)
+        loss.backward()
+        opt.step()
+        losses.append(loss.item())
+    assert losses[-1] < losses[0] - 0.05, losses
+
+
+# ---- kernel-level checks -------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('dt', [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize('mode', ['none', 'prefix', 'ragged'])
+@pytest.mark.parametrize('B,S,H', [(2, 70, 2), (1, 200, 3), (3, 64, 1)])
+def test_attention_bwd_vs_autograd(ops, dt, mode, B, S, H):
+    torch.manual_seed(31)
+    Dh, d = 64, H * 64
+    qkv = (torch.randn(B * S, 3 * d, device='cuda') * 0.5).to(dt)
+    do = torch.randn(B * S, d, device='cuda').to(dt)
+    x_lens = kv_lens = None
+    mask_mode = ops.MASK_NONE
+    if mode != 'none':
+        mask_mode = ops.MASK_PREFIX_LM
+        x_lens = torch.full((B,), S // 3, dtype=torch.int32, device='cuda')
+        kv_lens = torch.full((B,), S, dtype=torch.int32, device='cuda')
+        if mode == 'ragged':
+            kv_lens = torch.randint(S // 2, S + 1, (B,), dtype=torch.int32, device='cuda')
+    # reference: dense attention in fp64 with the same predicate
+    q64 = qkv.double().view(B, S, 3, H, Dh).requires_grad_(True)
+    q, k, v = (q64[:, :, i].permute(0, 2, 1, 3) for i in range(3))
+    s = q @ k.transpose(-1, -2) / math.sqrt(Dh)
+    i = torch.arange(S, device='cuda')[:, None]
+    j = torch.arange(S, device='cuda')[None, :]
+    ok = torch.ones(B, 1, S, S, dtype=torch.bool, device='cuda')
+    if mode != 'none':
+        xl = x_lens.view(B, 1, 1, 1).long()
+        ok = ((j < xl) | ((i >= xl) & (j <= i))) & (j < kv_lens.view(B, 1, 1, 1).long())
+    s = s.masked_fill(~ok, float('-inf'))
+    p = torch.softmax(s, -1)
+    p = torch.nan_to_num(p, nan=0.0)
+    o_ref = (p @ v).permute(0, 2, 1, 3).reshape(B * S, d)
+    o_ref.backward(do.double())
+    ref = q64.grad.reshape(B * S, 3 * d)
+    o = o_ref.detach().to(dt)
+    dqkv = torch.full((B * S, 3 * d), float('nan'), device='cuda').to(dt)
+    ops.attention_bwd(qkv, o, do, dqkv, B, S, H, mask_mode=mask_mode, x_lens=x_lens, kv_lens=kv_lens)
+    assert rel_err(dqkv.float(), ref) < (1e-4 if dt == torch.float32 else 2e-2)
+
+
+@pytest.mark.parametrize('dt', [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize('R,d', [(37, 256), (300, 1024), (5, 128)])
+def test_layernorm_bwd_vs_autograd(ops, dt, R, d):
+    torch.manual_seed(32)
+    x = (torch.randn(R, d, device='cuda') * 1.5 + 0.3).requires_grad_(True)
+    g = torch.randn(d, device='cuda', requires_grad=True)
+    b = torch.randn(d, device='cuda', requires_grad=True)
+    dy = torch.randn(R, d, device='cuda').to(dt)
+    y = torch.nn.functional.layer_norm(x.double(), (d,), g.double(), b.double())
+    y.backward(dy.double())
+    dx = torch.randn(R, d, device='cuda')
+    dx0 = dx.clone()
+    dg, db = ops.layernorm_bwd(x.detach(), g.detach(), dy, dx)
+    tol = 1e-4 if dt == torch.float32 else 1e-2
+    assert rel_err(dx - dx0, x.grad) < tol and rel_err(dg, g.grad) < tol and rel_err(db, b.grad) < tol
+    dx2 = dx0.clone()
+    assert ops.layernorm_bwd(x.detach(), None, dy, dx2) == (None, None)
+    assert rel_err(dx2 - dx0, dy.float()) < 1e-6
+
+
+def test_small_backward_kernels(ops):
+    torch.manual_seed(33)
+    for dt in (torch.float32, torch.bfloat16):
+        a = torch.randn(70, 45, device='cuda').to(dt)
+        assert torch.equal(ops.transpose(a), a.t().contiguous())
+        pre = torch.randn(1000, device='cuda').to(dt)
+        dy = torch.randn(1000, device='cuda').to(dt)
+        y = torch.empty_like(pre)
+        ops.gelu_fwd(pre, y)
+        assert rel_err(y.float(), torch.nn.functional.gelu(pre.double())) < (1e-6 if dt == torch.float32 else 1e-2)
+        pg = pre.double().requires_grad_(True)
+        torch.nn.functional.gelu(pg).backward(dy.double())
+        out = torch.empty_like(pre)
+        ops.gelu_bwd(pre, dy, out)
+        assert rel_err(out.float(), pg.grad) < (1e-5 if dt == torch.float32 else 1e-2)
+        x = torch.randn(333, 70, device='cuda').to(dt)
+        assert rel_err(ops.colsum(x, scale=0.5), 0.5 * x.double().sum(0)) < 1e-5
+    logits = torch.randn(19, 1032, device='cuda') * 3
+    tgt = torch.randint(0, 1025, (19,), dtype=torch.int32, device='cuda')
+    dl = torch.zeros(19, 1032, device='cuda')
+    rows = ops.cross_entropy(logits, tgt, 1025, dlogits=dl, scale=1 / 19)
+    lg = logits[:, :1025].double().requires_grad_(True)
+    ref = torch.nn.functional.cross_entropy(lg, tgt.long(), reduction='none')
+    ref.mean().backward()
+    assert rel_err(rows, ref) < 1e-5 and rel_err(dl[:, :1025], lg.grad) < 1e-5 and float(dl[:, 1025:].abs().max()) == 0.0
+    ids = torch.randint(0, 50, (3, 9, 4), dtype=torch.int32, device='cuda')
+    dx = torch.randn(3 * 11, 64, device='cuda')
+    gt = torch.zeros(4, 50, 64, device='cuda')
+    ops.embed_bwd(ids, dx, gt, t_split=3, nq_a=4, nq_b=2, rows_per_batch=11, row_offset=2)
+    ref = torch.zeros(4, 50, 64, device='cuda', dtype=torch.float64)
+    for b in range(3):
+        for t in range(9):
+            for j in range(4 if t < 3 else 2):
+                ref[j, ids[b, t, j]] += dx[b * 11 + 2 + t].double()
+    assert rel_err(gt, ref) < 1e-5

@@ -31,6 +31,15 @@ SIGNATURES = {
     'vb_linear_decode_fused_cluster': (_i, [_i, _i]),
     'vb_linear_decode_fused': (_i, [_p, _i, _i64, _p, _p, _f, _p, _i64, _p, _p, _i, _i64, _i, _i, _i, _i, _i, _i, _p]),
     'vb_kv_prefetch_l2': (_i, [_p, _i, _p, _i, _p, _i, _i, _i, _i, _i, _p]),
+    'vb_transpose': (_i, [_p, _i, _i64, _i64, _i64, _p, _i64, _p]),
+    'vb_colsum': (_i, [_p, _i, _i64, _i, _i64, _p, _i, _f, _p]),
+    'vb_gelu_fwd': (_i, [_p, _i, _p, _i64, _p]),
+    'vb_gelu_bwd': (_i, [_p, _p, _i, _p, _i64, _p]),
+    'vb_layernorm_bwd_blocks': (_i, [_i64]),
+    'vb_layernorm_bwd': (_i, [_p, _p, _p, _i, _p, _p, _p, _i64, _i, _f, _p]),
+    'vb_attention_bwd': (_i, [_p, _p, _p, _p, _i, _p, _p, _i, _i, _i, _i, _i, _p, _p, _p]),
+    'vb_cross_entropy': (_i, [_p, _i64, _p, _i64, _i, _p, _p, _i64, _f, _p]),
+    'vb_embed_bwd': (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i64, _i64, _p]),
     'vb_decode_chain': (_i, [_p, _i, _i, _p, _p]),
     'vb_decode_chain_set_debug': (_i, [_p]),
     'vb_linear_decode_set_debug': (_i, [_p]),

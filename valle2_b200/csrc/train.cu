@@ -1,0 +1,638 @@
+// Backward-pass kernels of the teacher-forced training step (ValleAR.training_step valle_ar.py:43-90, ValleNAR.training_step
+// valle_nar.py:53-105 as repaired in SURVEY App. A).  The large GEMMs of the backward pass (dgrad = dY.W, wgrad = dY^T.X) reuse
+// the forward GEMM kernels (vb_linear: tcgen05 for bf16, SIMT for the fp32 validation mode) on transposed operands; this
+// file holds everything else:
+//   vb_transpose            2-D transpose (operands of the wgrad / dgrad GEMMs)
+//   vb_colsum               deterministic column sums (bias gradients, reduction of per-CTA partials)
+//   vb_gelu_fwd / _bwd      erf-GELU kept separate from the GEMM epilogue so that the pre-activation is available
+//   vb_layernorm_bwd        dx (+= into the residual gradient), per-CTA partial dgamma / dbeta
+//   vb_attention_bwd        tiled SIMT flash-attention backward (fp32 math, prefix-LM / padding predicate as the forward)
+//   vb_cross_entropy        mean CE over all rows (no ignore_index, K-5) + dlogits
+//   vb_embed_bwd            scatter-add of the residual gradient into the embedding tables
+// First functional revision: correctness first (checked against torch autograd of the CPU oracle), tensor-core attention
+// backward is the next step.
+#include <math.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------------------------
+// transpose: dst[c][r] = src[r][c]
+// ------------------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void transpose_kernel(const T* __restrict__ src, int64_t lds, T* __restrict__ dst, int64_t ldd, int rows, int cols) {
+    __shared__ T tile[32][33];
+    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int r = r0 + i, c = c0 + threadIdx.x;
+        if (r < rows && c < cols) tile[i][threadIdx.x] = src[static_cast<int64_t>(r) * lds + c];
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int c = c0 + i, r = r0 + threadIdx.x;
+        if (r < rows && c < cols) dst[static_cast<int64_t>(c) * ldd + r] = tile[threadIdx.x][i];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// column sums: out[n] (+)= scale * sum_r x[r][n]; one CTA per 32 columns, 8 warps stride the rows, fixed-order merge
+// ------------------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, int64_t ldx, int64_t R, int N, float* __restrict__ out,
+                                                     int accumulate, float scale) {
+    __shared__ float red[8][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n = blockIdx.x * 32 + lane;
+    float acc = 0.f;
+    if (n < N)
+        for (int64_t r = warp; r < R; r += 8) acc += to_f32<T>(x[r * ldx + n]);
+    red[warp][lane] = acc;
+    __syncthreads();
+    if (warp == 0 && n < N) {
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += red[w][lane];
+        t *= scale;
+        out[n] = accumulate ? out[n] + t : t;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// erf-GELU forward / backward on a separate pre-activation buffer (modules.py:216 nn.GELU())
+// ------------------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void gelu_fwd_kernel(const T* __restrict__ pre, T* __restrict__ y, int64_t n) {
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+        y[i] = from_f32<T>(gelu_erf(to_f32<T>(pre[i])));
+}
+template <typename T>
+__global__ void gelu_bwd_kernel(const T* __restrict__ pre, const T* __restrict__ dy, T* __restrict__ dpre, int64_t n) {
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const float x = to_f32<T>(pre[i]);
+        const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
+        const float pdf = 0.39894228040143267794f * expf(-0.5f * x * x);
+        dpre[i] = from_f32<T>(to_f32<T>(dy[i]) * (cdf + x * pdf));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// LayerNorm backward.  y = (x - mean) * rstd * gamma + beta  (gamma == null: gamma = 1, plain normalisation is not used
+// on this path -- null means "no LayerNorm", i.e. y = cast(x): dx += dy).
+//   g = dy * gamma;  dx += rstd * (g - mean(g) - xhat * mean(g * xhat));  dgamma = sum_rows dy * xhat;  dbeta = sum_rows dy
+// One warp per row; a CTA (8 warps) walks rows blockIdx.x, +gridDim.x, ... and writes ONE partial row of dgamma / dbeta.
+// ------------------------------------------------------------------------------------------------------------------
+template <typename TY, int NV>
+__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                            const TY* __restrict__ dy, float* __restrict__ dx,
+                                                            float* __restrict__ dgamma_part, float* __restrict__ dbeta_part,
+                                                            int64_t R, int d, float eps) {
+    __shared__ float sg[NV * 128], sb[NV * 128];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float4 ag[NV], ab[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) ag[i] = ab[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int64_t r = static_cast<int64_t>(blockIdx.x) * 8 + warp; r < R; r += static_cast<int64_t>(gridDim.x) * 8) {
+        const float* xr = x + r * d;
+        const TY* dyr = dy + r * d;
+        float4 xv[NV], gv[NV], dv[NV];
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int c = (lane + 32 * i) * 4;
+            xv[i] = *reinterpret_cast<const float4*>(xr + c);
+            dv[i] = make_float4(to_f32<TY>(dyr[c]), to_f32<TY>(dyr[c + 1]), to_f32<TY>(dyr[c + 2]), to_f32<TY>(dyr[c + 3]));
+            s += (xv[i].x + xv[i].y) + (xv[i].z + xv[i].w);
+        }
+        const float mean = warp_sum(s) / d;
+        float q = 0.f;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const float a = xv[i].x - mean, b = xv[i].y - mean, c = xv[i].z - mean, e = xv[i].w - mean;
+            q += (a * a + b * b) + (c * c + e * e);
+        }
+        const float rstd = rsqrtf(warp_sum(q) / d + eps);
+        float sg1 = 0.f, sg2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int c = (lane + 32 * i) * 4;
+            const float4 gm = *reinterpret_cast<const float4*>(gamma + c);
+            xv[i].x = (xv[i].x - mean) * rstd; xv[i].y = (xv[i].y - mean) * rstd;     // xhat
+            xv[i].z = (xv[i].z - mean) * rstd; xv[i].w = (xv[i].w - mean) * rstd;
+            gv[i] = make_float4(dv[i].x * gm.x, dv[i].y * gm.y, dv[i].z * gm.z, dv[i].w * gm.w);
+            sg1 += (gv[i].x + gv[i].y) + (gv[i].z + gv[i].w);
+            sg2 += (gv[i].x * xv[i].x + gv[i].y * xv[i].y) + (gv[i].z * xv[i].z + gv[i].w * xv[i].w);
+            ag[i].x += dv[i].x * xv[i].x; ag[i].y += dv[i].y * xv[i].y; ag[i].z += dv[i].z * xv[i].z; ag[i].w += dv[i].w * xv[i].w;
+            ab[i].x += dv[i].x; ab[i].y += dv[i].y; ab[i].z += dv[i].z; ab[i].w += dv[i].w;
+        }
+        const float m1 = warp_sum(sg1) / d, m2 = warp_sum(sg2) / d;
+        float* dxr = dx + r * d;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int c = (lane + 32 * i) * 4;
+            float4 o = *reinterpret_cast<const float4*>(dxr + c);
+            o.x += rstd * (gv[i].x - m1 - xv[i].x * m2); o.y += rstd * (gv[i].y - m1 - xv[i].y * m2);
+            o.z += rstd * (gv[i].z - m1 - xv[i].z * m2); o.w += rstd * (gv[i].w - m1 - xv[i].w * m2);
+            *reinterpret_cast<float4*>(dxr + c) = o;
+        }
+    }
+    // merge the eight warps' column sums in warp order (deterministic), one partial row per CTA
+    for (int w = 0; w < 8; ++w) {
+        if (warp == w) {
+#pragma unroll
+            for (int i = 0; i < NV; ++i) {
+                const int c = (lane + 32 * i) * 4;
+                float4 g = ag[i], b = ab[i];
+                if (w > 0) {
+                    const float4 pg = *reinterpret_cast<const float4*>(&sg[c]), pb = *reinterpret_cast<const float4*>(&sb[c]);
+                    g.x += pg.x; g.y += pg.y; g.z += pg.z; g.w += pg.w;
+                    b.x += pb.x; b.y += pb.y; b.z += pb.z; b.w += pb.w;
+                }
+                *reinterpret_cast<float4*>(&sg[c]) = g;
+                *reinterpret_cast<float4*>(&sb[c]) = b;
+            }
+        }
+        __syncthreads();
+    }
+    for (int c = threadIdx.x; c < d; c += 256) {
+        dgamma_part[static_cast<int64_t>(blockIdx.x) * d + c] = sg[c];
+        dbeta_part[static_cast<int64_t>(blockIdx.x) * d + c] = sb[c];
+    }
+}
+
+// dx += dy (the "no LayerNorm, plain cast" case: valle_ar.py:158 has no final norm, K-2)
+template <typename TY>
+__global__ void add_cast_kernel(const TY* __restrict__ dy, float* __restrict__ dx, int64_t n) {
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+        dx[i] += to_f32<TY>(dy[i]);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// attention backward, head_dim 64, packed qkv rows [B*S][3][H][64].  64x64 tiles in shared memory (pitch 68 floats),
+// 256 threads, thread (ty, tx) owns a 4x4 block of every 64x64 product.
+//   kernel 1 (query tile): row statistics (m, l) -> lse, delta = rowsum(dO * O), dQ
+//   kernel 2 (key tile)  : dK, dV
+// allowed(i, j) is the forward's predicate: j < kv_len, and under the prefix-LM mask (j < x_len) || (i >= x_len && j <= i).
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int TS = 64, PITCH = 68;
+
+template <typename T>
+__device__ __forceinline__ void load_tile(float* dst, const T* __restrict__ src, int64_t row_pitch, int row0, int n_rows) {
+    // dst[r][e] = src[(row0 + r) * row_pitch + e], r < 64, e < 64; rows past n_rows are zero
+    for (int idx = threadIdx.x; idx < TS * 16; idx += 256) {
+        const int r = idx >> 4, e4 = (idx & 15) * 4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (row0 + r < n_rows) {
+            const T* p = src + static_cast<int64_t>(row0 + r) * row_pitch + e4;
+            v = make_float4(to_f32<T>(p[0]), to_f32<T>(p[1]), to_f32<T>(p[2]), to_f32<T>(p[3]));
+        }
+        *reinterpret_cast<float4*>(dst + r * PITCH + e4) = v;
+    }
+}
+
+// c[a][b] = sum_e A[4*ty + a][e] * B[4*tx + b][e]   (both operands row-major over e)
+__device__ __forceinline__ void tile_abt(const float* A, const float* Bm, int ty, int tx, float (&c)[4][4]) {
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) c[a][b] = 0.f;
+#pragma unroll 4
+    for (int e = 0; e < TS; e += 4) {
+        float4 av[4], bv[4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) av[a] = *reinterpret_cast<const float4*>(A + (4 * ty + a) * PITCH + e);
+#pragma unroll
+        for (int b = 0; b < 4; ++b) bv[b] = *reinterpret_cast<const float4*>(Bm + (4 * tx + b) * PITCH + e);
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b)
+                c[a][b] += av[a].x * bv[b].x + av[a].y * bv[b].y + av[a].z * bv[b].z + av[a].w * bv[b].w;
+    }
+}
+
+// c[a][b] += sum_j A[4*ty + a][j] * Bm[j][4*tx + b]   (A row-major over j, Bm row-major over the output column)
+__device__ __forceinline__ void tile_ab_acc(const float* A, const float* Bm, int ty, int tx, float (&c)[4][4]) {
+#pragma unroll 4
+    for (int j = 0; j < TS; ++j) {
+        const float4 bv = *reinterpret_cast<const float4*>(Bm + j * PITCH + 4 * tx);
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            const float av = A[(4 * ty + a) * PITCH + j];
+            c[a][0] += av * bv.x; c[a][1] += av * bv.y; c[a][2] += av * bv.z; c[a][3] += av * bv.w;
+        }
+    }
+}
+
+// c[a][b] += sum_i A[i][4*ty + a] * Bm[i][4*tx + b]   (A^T . Bm)
+__device__ __forceinline__ void tile_atb_acc(const float* A, const float* Bm, int ty, int tx, float (&c)[4][4]) {
+#pragma unroll 4
+    for (int i = 0; i < TS; ++i) {
+        const float4 av = *reinterpret_cast<const float4*>(A + i * PITCH + 4 * ty);
+        const float4 bv = *reinterpret_cast<const float4*>(Bm + i * PITCH + 4 * tx);
+        const float aa[4] = {av.x, av.y, av.z, av.w};
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            c[a][0] += aa[a] * bv.x; c[a][1] += aa[a] * bv.y; c[a][2] += aa[a] * bv.z; c[a][3] += aa[a] * bv.w;
+        }
+    }
+}
+
+__device__ __forceinline__ bool allowed(int i, int j, int kv_len, int x_len, int mask_mode) {
+    if (j >= kv_len) return false;
+    if (mask_mode == VB_MASK_PREFIX_LM) return (j < x_len) || (i >= x_len && j <= i);
+    return true;
+}
+__device__ __forceinline__ float half_sum16(float v) {   // sum over the 16 lanes that share ty
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float half_max16(float v) {
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) attn_bwd_dq_kernel(const T* __restrict__ qkv, const T* __restrict__ o, const T* __restrict__ dO,
+                                                          T* __restrict__ dqkv, float* __restrict__ lse, float* __restrict__ delta,
+                                                          int S, int H, int mask_mode, const int32_t* __restrict__ x_lens,
+                                                          const int32_t* __restrict__ kv_lens, float scale) {
+    extern __shared__ float sm[];
+    float* Qs = sm;                  // 64 x 68
+    float* dOs = Qs + TS * PITCH;
+    float* Ks = dOs + TS * PITCH;
+    float* Vs = Ks + TS * PITCH;
+    float* Ss = Vs + TS * PITCH;     // dS tile
+    const int it = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+    const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+    const int d = H * TS;
+    const int64_t rp = 3 * static_cast<int64_t>(d);
+    const int kv_len = kv_lens ? min(kv_lens[b], S) : S;
+    const int x_len = x_lens ? x_lens[b] : 0;
+    const int i0 = it * TS;
+    const T* qb = qkv + static_cast<int64_t>(b) * S * rp + h * TS;
+    load_tile<T>(Qs, qb, rp, i0, S);
+    load_tile<T>(dOs, dO + static_cast<int64_t>(b) * S * d + h * TS, d, i0, S);
+    load_tile<T>(Ks, o + static_cast<int64_t>(b) * S * d + h * TS, d, i0, S);     // O tile, temporarily in Ks
+    __syncthreads();
+    // delta_i = sum_e dO[i][e] * O[i][e]
+    float dl[4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        const float4 x1 = *reinterpret_cast<const float4*>(dOs + (4 * ty + a) * PITCH + 4 * tx);
+        const float4 x2 = *reinterpret_cast<const float4*>(Ks + (4 * ty + a) * PITCH + 4 * tx);
+        dl[a] = half_sum16(x1.x * x2.x + x1.y * x2.y + x1.z * x2.z + x1.w * x2.w);
+    }
+    __syncthreads();
+    const int i_max = min(i0 + TS, S) - 1;
+    int j_end = kv_len;                                      // keys this query tile can see
+    if (mask_mode == VB_MASK_PREFIX_LM) j_end = min(kv_len, max(x_len, i_max + 1));
+    // pass 1: row max / sum
+    float m[4], l[4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) { m[a] = -INFINITY; l[a] = 0.f; }
+    for (int j0 = 0; j0 < j_end; j0 += TS) {
+        load_tile<T>(Ks, qb + d, rp, j0, S);
+        __syncthreads();
+        float s[4][4];
+        tile_abt(Qs, Ks, ty, tx, s);
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            float mx = -INFINITY;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                s[a][c] = allowed(i0 + 4 * ty + a, j0 + 4 * tx + c, kv_len, x_len, mask_mode) ? s[a][c] * scale : -INFINITY;
+                mx = fmaxf(mx, s[a][c]);
+            }
+            mx = half_max16(mx);
+            const float m_new = fmaxf(m[a], mx);
+            if (m_new != -INFINITY) {
+                float ps = 0.f;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) ps += (s[a][c] == -INFINITY) ? 0.f : expf(s[a][c] - m_new);
+                ps = half_sum16(ps);
+                l[a] = l[a] * ((m[a] == -INFINITY) ? 0.f : expf(m[a] - m_new)) + ps;
+                m[a] = m_new;
+            }
+        }
+        __syncthreads();
+    }
+    float ls[4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        ls[a] = (l[a] > 0.f) ? m[a] + logf(l[a]) : INFINITY;      // +inf: the row attends to nothing, P = 0
+        const int i = i0 + 4 * ty + a;
+        if (tx == 0 && i < S) {
+            lse[(static_cast<int64_t>(b) * H + h) * S + i] = ls[a];
+            delta[(static_cast<int64_t>(b) * H + h) * S + i] = dl[a];
+        }
+    }
+    // pass 2: dQ = sum_j dS[i][j] K[j],  dS = P * (dP - delta) * scale
+    float dq[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) dq[a][c] = 0.f;
+    for (int j0 = 0; j0 < j_end; j0 += TS) {
+        load_tile<T>(Ks, qb + d, rp, j0, S);
+        load_tile<T>(Vs, qb + 2 * d, rp, j0, S);
+        __syncthreads();
+        float s[4][4], dp[4][4];
+        tile_abt(Qs, Ks, ty, tx, s);
+        tile_abt(dOs, Vs, ty, tx, dp);
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const bool ok = allowed(i0 + 4 * ty + a, j0 + 4 * tx + c, kv_len, x_len, mask_mode) && ls[a] != INFINITY;
+                const float p = ok ? expf(s[a][c] * scale - ls[a]) : 0.f;
+                Ss[(4 * ty + a) * PITCH + 4 * tx + c] = p * (dp[a][c] - dl[a]) * scale;
+            }
+        __syncthreads();
+        tile_ab_acc(Ss, Ks, ty, tx, dq);
+        __syncthreads();
+    }
+    T* dqb = dqkv + static_cast<int64_t>(b) * S * rp + h * TS;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        const int i = i0 + 4 * ty + a;
+        if (i < S)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) dqb[static_cast<int64_t>(i) * rp + 4 * tx + c] = from_f32<T>(dq[a][c]);
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) attn_bwd_dkv_kernel(const T* __restrict__ qkv, const T* __restrict__ dO, T* __restrict__ dqkv,
+                                                           const float* __restrict__ lse, const float* __restrict__ delta, int S,
+                                                           int H, int mask_mode, const int32_t* __restrict__ x_lens,
+                                                           const int32_t* __restrict__ kv_lens, float scale) {
+    extern __shared__ float sm[];
+    float* Ks = sm;
+    float* Vs = Ks + TS * PITCH;
+    float* Qs = Vs + TS * PITCH;
+    float* dOs = Qs + TS * PITCH;
+    float* Ps = dOs + TS * PITCH;
+    float* dSs = Ps + TS * PITCH;
+    __shared__ float lse_s[TS], dl_s[TS];
+    const int jt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+    const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+    const int d = H * TS;
+    const int64_t rp = 3 * static_cast<int64_t>(d);
+    const int kv_len = kv_lens ? min(kv_lens[b], S) : S;
+    const int x_len = x_lens ? x_lens[b] : 0;
+    const int j0 = jt * TS;
+    const T* qb = qkv + static_cast<int64_t>(b) * S * rp + h * TS;
+    T* dkb = dqkv + static_cast<int64_t>(b) * S * rp + h * TS + d;
+    float dk[4][4], dv[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) dk[a][c] = dv[a][c] = 0.f;
+    if (j0 < kv_len) {
+        load_tile<T>(Ks, qb + d, rp, j0, S);
+        load_tile<T>(Vs, qb + 2 * d, rp, j0, S);
+        // queries that can see this key tile: all (no mask), or under prefix-LM: text keys are seen by every row,
+        // audio keys only by rows i >= j
+        int i_begin = 0;
+        if (mask_mode == VB_MASK_PREFIX_LM && j0 >= x_len) i_begin = (j0 / TS) * TS;
+        for (int i0 = i_begin; i0 < S; i0 += TS) {
+            __syncthreads();
+            load_tile<T>(Qs, qb, rp, i0, S);
+            load_tile<T>(dOs, dO + static_cast<int64_t>(b) * S * d + h * TS, d, i0, S);
+            if (threadIdx.x < TS) {
+                const int i = i0 + threadIdx.x;
+                lse_s[threadIdx.x] = (i < S) ? lse[(static_cast<int64_t>(b) * H + h) * S + i] : INFINITY;
+                dl_s[threadIdx.x] = (i < S) ? delta[(static_cast<int64_t>(b) * H + h) * S + i] : 0.f;
+            }
+            __syncthreads();
+            float s[4][4], dp[4][4];
+            tile_abt(Qs, Ks, ty, tx, s);         // s[a][c]: query 4ty+a, key 4tx+c
+            tile_abt(dOs, Vs, ty, tx, dp);
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const int i = i0 + 4 * ty + a;
+                    const float li = lse_s[4 * ty + a];
+                    const bool ok = i < S && li != INFINITY && allowed(i, j0 + 4 * tx + c, kv_len, x_len, mask_mode);
+                    const float p = ok ? expf(s[a][c] * scale - li) : 0.f;
+                    Ps[(4 * ty + a) * PITCH + 4 * tx + c] = p;
+                    dSs[(4 * ty + a) * PITCH + 4 * tx + c] = p * (dp[a][c] - dl_s[4 * ty + a]) * scale;
+                }
+            __syncthreads();
+            tile_atb_acc(Ps, dOs, ty, tx, dv);    // dV[j][e] += sum_i P[i][j] dO[i][e]
+            tile_atb_acc(dSs, Qs, ty, tx, dk);    // dK[j][e] += sum_i dS[i][j] Q[i][e]
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        const int j = j0 + 4 * ty + a;
+        if (j < S)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                dkb[static_cast<int64_t>(j) * rp + 4 * tx + c] = from_f32<T>(dk[a][c]);
+                dkb[static_cast<int64_t>(j) * rp + d + 4 * tx + c] = from_f32<T>(dv[a][c]);
+            }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// cross entropy: loss_rows[r] = lse(logits[r]) - logits[r][target[r]];  dlogits[r] = (softmax - onehot) * scale
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) cross_entropy_kernel(const float* __restrict__ logits, int64_t ld, const int32_t* __restrict__ target,
+                                                            int V, float* __restrict__ loss_rows, float* __restrict__ dlogits,
+                                                            int64_t ldd, float scale) {
+    __shared__ float red[8];
+    const int64_t r = blockIdx.x;
+    const float* row = logits + r * ld;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float mx = -INFINITY;
+    for (int c = threadIdx.x; c < V; c += 256) mx = fmaxf(mx, row[c]);
+    mx = warp_max(mx);
+    if (lane == 0) red[warp] = mx;
+    __syncthreads();
+    mx = red[0];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) mx = fmaxf(mx, red[w]);
+    __syncthreads();
+    float se = 0.f;
+    for (int c = threadIdx.x; c < V; c += 256) se += expf(row[c] - mx);
+    se = warp_sum(se);
+    if (lane == 0) red[warp] = se;
+    __syncthreads();
+    se = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) se += red[w];
+    const float lse = mx + logf(se);
+    const int t = min(max(target[r], 0), V - 1);
+    if (threadIdx.x == 0) loss_rows[r] = lse - row[t];
+    if (dlogits) {
+        float* drow = dlogits + r * ldd;
+        for (int c = threadIdx.x; c < V; c += 256) drow[c] = (expf(row[c] - lse) - (c == t ? 1.f : 0.f)) * scale;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// embedding backward: grad_tables[j][ids[b][t][j]][:] += dx[row(b, t)][:]   for j < nq(t)   (mirror of vb_embed_sum_pe)
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void embed_bwd_kernel(const int32_t* __restrict__ ids, const float* __restrict__ dx, float* __restrict__ grad_tables, int T,
+                                 int Q, int V, int d, int t_split, int nq_a, int nq_b, int64_t rows_per_batch, int64_t row_offset) {
+    const int t = blockIdx.x, b = blockIdx.y;
+    const int nq = (t < t_split) ? nq_a : nq_b;
+    const int32_t* id_row = ids + (static_cast<int64_t>(b) * T + t) * Q;
+    const float* g = dx + (static_cast<int64_t>(b) * rows_per_batch + row_offset + t) * d;
+    for (int j = 0; j < nq; ++j) {
+        const int id = min(max(id_row[j], 0), V - 1);
+        float* dst = grad_tables + (static_cast<int64_t>(j) * V + id) * d;
+        for (int c = threadIdx.x; c < d; c += blockDim.x) atomicAdd(dst + c, g[c]);
+    }
+}
+
+}  // namespace
+
+// ==================================================================================================================
+extern "C" int vb_transpose(const void* src, int dtype, int64_t rows, int64_t cols, int64_t lds, void* dst, int64_t ldd, void* stream) {
+    VB_REQUIRE(src && dst && rows >= 0 && cols >= 0, VB_ERR_BAD_ARG, "vb_transpose: bad args");
+    if (rows == 0 || cols == 0) return VB_OK;
+    dim3 grid(static_cast<unsigned>(vb_ceil_div(cols, 32)), static_cast<unsigned>(vb_ceil_div(rows, 32)));
+    VB_REQUIRE(grid.y <= 65535, VB_ERR_UNSUPPORTED, "vb_transpose: too many rows (%lld)", (long long)rows);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (dtype == VB_F32) transpose_kernel<float><<<grid, dim3(32, 8), 0, st>>>(static_cast<const float*>(src), lds, static_cast<float*>(dst), ldd, (int)rows, (int)cols);
+    else if (dtype == VB_BF16) transpose_kernel<__nv_bfloat16><<<grid, dim3(32, 8), 0, st>>>(static_cast<const __nv_bfloat16*>(src), lds, static_cast<__nv_bfloat16*>(dst), ldd, (int)rows, (int)cols);
+    else VB_REQUIRE(false, VB_ERR_BAD_ARG, "vb_transpose: bad dtype");
+    VB_LAUNCH_CHECK();
+    return VB_OK;
+}
+
+extern "C" int vb_colsum(const void* x, int dtype, int64_t R, int N, int64_t ldx, float* out, int accumulate, float scale, void* stream) {
+    VB_REQUIRE(x && out && R >= 0 && N >= 1, VB_ERR_BAD_ARG, "vb_colsum: bad args");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int blocks = (N + 31) / 32;
+    if (dtype == VB_F32) colsum_kernel<float><<<blocks, 256, 0, st>>>(static_cast<const float*>(x), ldx, R, N, out, accumulate, scale);
+    else if (dtype == VB_BF16) colsum_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), ldx, R, N, out, accumulate, scale);
+    else VB_REQUIRE(false, VB_ERR_BAD_ARG, "vb_colsum: bad dtype");
+    VB_LAUNCH_CHECK();
+    return VB_OK;
+}
+
+extern "C" int vb_gelu_fwd(const void* pre, int dtype, void* y, int64_t n, void* stream) {
+    VB_REQUIRE(pre && y && n >= 0, VB_ERR_BAD_ARG, "vb_gelu_fwd: bad args");
+    if (n == 0) return VB_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int blocks = (int)std::min<int64_t>(vb_ceil_div(n, 256), static_cast<int64_t>(vb_sm_count()) * 16);
+    if (dtype == VB_F32) gelu_fwd_kernel<float><<<blocks, 256, 0, st>>>(static_cast<const float*>(pre), static_cast<float*>(y), n);
+    else if (dtype == VB_BF16) gelu_fwd_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(pre), static_cast<__nv_bfloat16*>(y), n);
+    else VB_REQUIRE(false, VB_ERR_BAD_ARG, "vb_gelu_fwd: bad dtype");
+    VB_LAUNCH_CHECK();
+    return VB_OK;
+}
+
+extern "C" int vb_gelu_bwd(const void* pre, const void* dy, int dtype, void* dpre, int64_t n, void* stream) {
+    VB_REQUIRE(pre && dy && dpre && n >= 0, VB_ERR_BAD_ARG, "vb_gelu_bwd: bad args");
+    if (n == 0) return VB_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int blocks = (int)std::min<int64_t>(vb_ceil_div(n, 256), static_cast<int64_t>(vb_sm_count()) * 16);
+    if (dtype == VB_F32) gelu_bwd_kernel<float><<<blocks, 256, 0, st>>>(static_cast<const float*>(pre), static_cast<const float*>(dy), static_cast<float*>(dpre), n);
+    else if (dtype == VB_BF16) gelu_bwd_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(pre), static_cast<const __nv_bfloat16*>(dy), static_cast<__nv_bfloat16*>(dpre), n);
+    else VB_REQUIRE(false, VB_ERR_BAD_ARG, "vb_gelu_bwd: bad dtype");
+    VB_LAUNCH_CHECK();
+    return VB_OK;
+}
+
+extern "C" int vb_layernorm_bwd_blocks(int64_t R) { return (int)std::min<int64_t>(vb_ceil_div(R, 8), static_cast<int64_t>(vb_sm_count()) * 2); }
+
+extern "C" int vb_layernorm_bwd(const float* x, const float* gamma, const void* dy, int dy_dtype, float* dx, float* dgamma_part,
+                                float* dbeta_part, int64_t R, int d, float eps, void* stream) {
+    VB_REQUIRE(x && dy && dx && R >= 0, VB_ERR_BAD_ARG, "vb_layernorm_bwd: null pointer");
+    if (R == 0) return VB_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (gamma == nullptr) {   // no LayerNorm on the forward path (plain cast): dx += dy
+        const int64_t n = R * d;
+        const int blocks = (int)std::min<int64_t>(vb_ceil_div(n, 256), static_cast<int64_t>(vb_sm_count()) * 16);
+        if (dy_dtype == VB_F32) add_cast_kernel<float><<<blocks, 256, 0, st>>>(static_cast<const float*>(dy), dx, n);
+        else add_cast_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(dy), dx, n);
+        VB_LAUNCH_CHECK();
+        return VB_OK;
+    }
+    VB_REQUIRE(dgamma_part && dbeta_part, VB_ERR_BAD_ARG, "vb_layernorm_bwd: partial buffers are null");
+    VB_REQUIRE(d % 128 == 0 && d <= 1024, VB_ERR_UNSUPPORTED, "vb_layernorm_bwd: d must be a multiple of 128 up to 1024 (got %d)", d);
+    const int blocks = vb_layernorm_bwd_blocks(R);
+#define LNB(TY, NV) layernorm_bwd_kernel<TY, NV><<<blocks, 256, 0, st>>>(x, gamma, static_cast<const TY*>(dy), dx, dgamma_part, dbeta_part, R, d, eps)
+#define LNB_D(TY)                                          \
+    switch (d / 128) {                                     \
+        case 1: LNB(TY, 1); break;                         \
+        case 2: LNB(TY, 2); break;                         \
+        case 3: LNB(TY, 3); break;                         \
+        case 4: LNB(TY, 4); break;                         \
+        case 5: LNB(TY, 5); break;                         \
+        case 6: LNB(TY, 6); break;                         \
+        case 7: LNB(TY, 7); break;                         \
+        default: LNB(TY, 8); break;                        \
+    }
+    if (dy_dtype == VB_F32) { LNB_D(float) } else if (dy_dtype == VB_BF16) { LNB_D(__nv_bfloat16) }
+    else VB_REQUIRE(false, VB_ERR_BAD_ARG, "vb_layernorm_bwd: bad dy dtype");
+#undef LNB_D
+#undef LNB
+    VB_LAUNCH_CHECK();
+    return VB_OK;
+}
+
+extern "C" int vb_attention_bwd(const void* qkv, const void* o, const void* dO, void* dqkv, int dtype, float* lse, float* delta, int B,
+                                int S, int H, int Dh, int mask_mode, const int32_t* x_lens, const int32_t* kv_lens, void* stream) {
+    VB_REQUIRE(qkv && o && dO && dqkv && lse && delta, VB_ERR_BAD_ARG, "vb_attention_bwd: null pointer");
+    VB_REQUIRE(Dh == 64, VB_ERR_UNSUPPORTED, "vb_attention_bwd: head_dim must be 64 (got %d)", Dh);
+    VB_REQUIRE(mask_mode == VB_MASK_NONE || mask_mode == VB_MASK_PREFIX_LM, VB_ERR_UNSUPPORTED, "vb_attention_bwd: mask mode %d", mask_mode);
+    VB_REQUIRE(mask_mode != VB_MASK_PREFIX_LM || x_lens != nullptr, VB_ERR_BAD_ARG, "vb_attention_bwd: prefix-LM needs x_lens");
+    VB_REQUIRE(B >= 0 && S >= 0 && H >= 1 && H <= 65535 && B <= 65535, VB_ERR_BAD_ARG, "vb_attention_bwd: bad shape");
+    if (B == 0 || S == 0) return VB_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const float scale = 1.0f / sqrtf(64.0f);
+    dim3 grid(static_cast<unsigned>(vb_ceil_div(S, TS)), H, B);
+    const int smem1 = 5 * TS * PITCH * 4, smem2 = 6 * TS * PITCH * 4;
+#define ABW(T)                                                                                                             \
+    {                                                                                                                      \
+        static bool configured = false;                                                                                    \
+        if (!configured) {                                                                                                 \
+            VB_CUDA(cudaFuncSetAttribute(attn_bwd_dq_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1));      \
+            VB_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));     \
+            configured = true;                                                                                             \
+        }                                                                                                                  \
+        attn_bwd_dq_kernel<T><<<grid, 256, smem1, st>>>(static_cast<const T*>(qkv), static_cast<const T*>(o),              \
+            static_cast<const T*>(dO), static_cast<T*>(dqkv), lse, delta, S, H, mask_mode, x_lens, kv_lens, scale);        \
+        attn_bwd_dkv_kernel<T><<<grid, 256, smem2, st>>>(static_cast<const T*>(qkv), static_cast<const T*>(dO),            \
+            static_cast<T*>(dqkv), lse, delta, S, H, mask_mode, x_lens, kv_lens, scale);                                   \
+    }
+    if (dtype == VB_F32) ABW(float)
+    else if (dtype == VB_BF16) ABW(__nv_bfloat16)
+    else VB_REQUIRE(false, VB_ERR_BAD_ARG, "vb_attention_bwd: bad dtype");
+#undef ABW
+    VB_LAUNCH_CHECK();
+    return VB_OK;
+}
+
+extern "C" int vb_cross_entropy(const float* logits, int64_t ld, const int32_t* target, int64_t R, int V, float* loss_rows,
+                                float* dlogits, int64_t ldd, float scale, void* stream) {
+    VB_REQUIRE(logits && target && loss_rows && R >= 0 && V >= 1, VB_ERR_BAD_ARG, "vb_cross_entropy: bad args");
+    if (R == 0) return VB_OK;
+    VB_REQUIRE(R <= 2147483647LL, VB_ERR_UNSUPPORTED, "vb_cross_entropy: too many rows");
+    cross_entropy_kernel<<<static_cast<unsigned>(R), 256, 0, static_cast<cudaStream_t>(stream)>>>(logits, ld, target, V, loss_rows, dlogits, ldd, scale);
+    VB_LAUNCH_CHECK();
+    return VB_OK;
+}
+
+extern "C" int vb_embed_bwd(const int32_t* ids, const float* dx, float* grad_tables, int B, int T, int Q, int V, int d, int t_split,
+                            int nq_a, int nq_b, int64_t rows_per_batch, int64_t row_offset, void* stream) {
+    VB_REQUIRE(ids && dx && grad_tables, VB_ERR_BAD_ARG, "vb_embed_bwd: null pointer");
+    VB_REQUIRE(B >= 0 && T >= 0 && Q >= 1 && d > 0 && B <= 65535, VB_ERR_BAD_ARG, "vb_embed_bwd: bad shape");
+    VB_REQUIRE(nq_a >= 0 && nq_a <= Q && nq_b >= 0 && nq_b <= Q, VB_ERR_BAD_ARG, "vb_embed_bwd: nq out of range");
+    if (B == 0 || T == 0) return VB_OK;
+    embed_bwd_kernel<<<dim3(T, B), 256, 0, static_cast<cudaStream_t>(stream)>>>(ids, dx, grad_tables, T, Q, V, d, t_split, nq_a, nq_b,
+                                                                                 rows_per_batch, row_offset);
+    VB_LAUNCH_CHECK();
+    return VB_OK;
+}

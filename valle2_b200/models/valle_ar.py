@@ -84,11 +84,12 @@ class ValleAR(BaseModule):
         return logits.view(B, Ty, -1)
 
     def training_step(self, batch: dict[str, torch.Tensor], **kwargs) -> torch.Tensor:
-        """Forward loss of valle_ar.py:43-90 (mean CE over all positions incl. padding, K-5).
-        The CUDA stack is forward-only in this revision: the returned loss carries no autograd graph."""
-        logits = self.forward_logits(batch)
-        target = batch['target'].to(self.device)[:, : logits.shape[1]]
-        loss = F.cross_entropy(logits.permute(0, 2, 1), target)
+        """valle_ar.py:43-90: mean CE over all positions incl. padding (K-5).  Forward AND backward run on the CUDA stack
+        (valle2_b200/train.py); the returned loss is attached to the parameters through one autograd Function, so
+        ``loss.backward()`` / Lightning's optimisation loop work as with the reference."""
+        from .. import train
+        precision = valle2_b200.get_precision()
+        loss = train.step_loss(self, lambda: train.ar_loss_and_grads(self, batch, precision))
         self.log('train/loss', loss)
         return loss
 

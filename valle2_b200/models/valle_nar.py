@@ -74,10 +74,12 @@ class ValleNAR(BaseModule):
         return logits.view(B, T - prefix_len, -1), prefix_len
 
     def training_step(self, batch: dict[str, torch.Tensor], **kwargs) -> torch.Tensor:
+        """valle_nar.py:53-105 (repairs A-1..A-3, A-4 kept): random stage (:76), CE on that codebook.  Forward and backward
+        on the CUDA stack (valle2_b200/train.py); ``loss.backward()`` fills the parameter gradients."""
+        from .. import train
         layer = kwargs.get('layer') or random.randint(1, self.config.num_quantizers - 1)   # :76
-        logits, prefix_len = self.forward_logits(batch, layer)
-        target = batch['codes'].to(self.device)[:, prefix_len:, layer]
-        return F.cross_entropy(logits.permute(0, 2, 1), target)
+        precision = valle2_b200.get_precision()
+        return train.step_loss(self, lambda: train.nar_loss_and_grads(self, batch, layer, precision))
 
     @torch.inference_mode()
     def generate(self, prompt_tokens: torch.Tensor, prompt_codes: torch.Tensor, target_tokens: torch.Tensor,

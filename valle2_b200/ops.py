@@ -278,3 +278,91 @@ def chain_act(part: torch.Tensor, n_part: int, part_stride: int, bias, y: torch.
 def decode_chain(phases: list, B: int, counter: torch.Tensor) -> None:
     arr = (_lib.ChainPhase * len(phases))(*phases)
     check(_L().vb_decode_chain(C.cast(arr, C.c_void_p), len(phases), B, _ptr(counter), _stream()), 'vb_decode_chain')
+
+
+# ---- training step, backward pass (csrc/train.cu) -----------------------------------------------------------------------
+def transpose(src: torch.Tensor, dst: torch.Tensor | None = None) -> torch.Tensor:
+    """dst (cols, rows) = src (rows, cols)^T; both with unit inner stride."""
+    rows, cols = src.shape
+    if dst is None:
+        dst = torch.empty(cols, rows, device=src.device, dtype=src.dtype)
+    assert src.stride(1) == 1 and dst.stride(1) == 1 and dst.shape == (cols, rows) and dst.dtype == src.dtype
+    check(_L().vb_transpose(_ptr(src), _code(src.dtype), rows, cols, src.stride(0), _ptr(dst), dst.stride(0), _stream()),
+          'vb_transpose')
+    return dst
+
+
+def colsum(x: torch.Tensor, out: torch.Tensor | None = None, *, accumulate: bool = False, scale: float = 1.0) -> torch.Tensor:
+    R, N = x.shape
+    if out is None:
+        out = torch.zeros(N, device=x.device, dtype=torch.float32)
+    assert x.stride(1) == 1 and out.dtype == torch.float32 and out.numel() == N
+    check(_L().vb_colsum(_ptr(x), _code(x.dtype), R, N, x.stride(0), _ptr(out), int(accumulate), float(scale), _stream()),
+          'vb_colsum')
+    return out
+
+
+def gelu_fwd(pre: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+    assert pre.is_contiguous() and y.is_contiguous() and pre.dtype == y.dtype and pre.numel() == y.numel()
+    check(_L().vb_gelu_fwd(_ptr(pre), _code(pre.dtype), _ptr(y), pre.numel(), _stream()), 'vb_gelu_fwd')
+    return y
+
+
+def gelu_bwd(pre: torch.Tensor, dy: torch.Tensor, dpre: torch.Tensor) -> torch.Tensor:
+    assert pre.is_contiguous() and dy.is_contiguous() and dpre.is_contiguous() and pre.dtype == dy.dtype == dpre.dtype
+    check(_L().vb_gelu_bwd(_ptr(pre), _ptr(dy), _code(pre.dtype), _ptr(dpre), pre.numel(), _stream()), 'vb_gelu_bwd')
+    return dpre
+
+
+def layernorm_bwd(x: torch.Tensor, gamma: torch.Tensor | None, dy: torch.Tensor, dx: torch.Tensor, eps: float = 1e-5):
+    """dx (fp32, R x d) += LN backward of dy; returns (dgamma, dbeta) fp32 [d] (None, None when gamma is None = plain cast)."""
+    R, d = x.shape
+    assert x.dtype == torch.float32 and dx.dtype == torch.float32 and x.is_contiguous() and dx.is_contiguous() and dy.is_contiguous()
+    if gamma is None:
+        check(_L().vb_layernorm_bwd(_ptr(x), None, _ptr(dy), _code(dy.dtype), _ptr(dx), None, None, R, d, eps, _stream()),
+              'vb_layernorm_bwd')
+        return None, None
+    nb = int(_L().vb_layernorm_bwd_blocks(R))
+    pg = torch.empty(nb, d, device=x.device, dtype=torch.float32)
+    pb = torch.empty(nb, d, device=x.device, dtype=torch.float32)
+    check(_L().vb_layernorm_bwd(_ptr(x), _ptr(gamma), _ptr(dy), _code(dy.dtype), _ptr(dx), _ptr(pg), _ptr(pb), R, d, eps,
+                                _stream()), 'vb_layernorm_bwd')
+    return colsum(pg), colsum(pb)
+
+
+def attention_bwd(qkv: torch.Tensor, o: torch.Tensor, do: torch.Tensor, dqkv: torch.Tensor, B: int, S: int, H: int, *,
+                  mask_mode: int, x_lens: torch.Tensor | None, kv_lens: torch.Tensor | None) -> torch.Tensor:
+    """Packed rows: qkv / dqkv (B*S, 3*H*64), o / do (B*S, H*64), all the same dtype."""
+    d = o.shape[1]
+    assert qkv.dtype == o.dtype == do.dtype == dqkv.dtype and qkv.is_contiguous() and o.is_contiguous() and do.is_contiguous()
+    assert dqkv.is_contiguous() and qkv.shape[1] == 3 * d
+    lse = torch.empty(B, H, S, device=qkv.device, dtype=torch.float32)
+    delta = torch.empty(B, H, S, device=qkv.device, dtype=torch.float32)
+    check(_L().vb_attention_bwd(_ptr(qkv), _ptr(o), _ptr(do), _ptr(dqkv), _code(qkv.dtype), _ptr(lse), _ptr(delta), B, S, H,
+                                d // H, mask_mode, _ptr(x_lens), _ptr(kv_lens), _stream()), 'vb_attention_bwd')
+    return dqkv
+
+
+def cross_entropy(logits: torch.Tensor, target: torch.Tensor, V: int, *, dlogits: torch.Tensor | None = None,
+                  scale: float = 1.0) -> torch.Tensor:
+    """Per-row losses (fp32 [R]) over the first V columns of logits (R, >=V); dlogits = (softmax - onehot) * scale."""
+    R = logits.shape[0]
+    assert logits.dtype == torch.float32 and logits.stride(1) == 1 and target.dtype == torch.int32 and target.numel() == R
+    loss_rows = torch.empty(R, device=logits.device, dtype=torch.float32)
+    check(_L().vb_cross_entropy(_ptr(logits), logits.stride(0), _ptr(target), R, V, _ptr(loss_rows), _ptr(dlogits),
+                                dlogits.stride(0) if dlogits is not None else 0, float(scale), _stream()), 'vb_cross_entropy')
+    return loss_rows
+
+
+def embed_bwd(ids: torch.Tensor, dx: torch.Tensor, grad_tables: torch.Tensor, *, t_split: int = 0,
+              nq_a: int | None = None, nq_b: int | None = None, rows_per_batch: int | None = None, row_offset: int = 0) -> None:
+    """grad_tables (Q,V,d) fp32 += scatter of dx rows (transpose of embed_sum_pe)."""
+    B, T, Q = ids.shape
+    Qt, V, d = grad_tables.shape
+    assert Qt == Q and ids.dtype == torch.int32 and ids.is_contiguous() and grad_tables.is_contiguous()
+    assert dx.dtype == torch.float32 and grad_tables.dtype == torch.float32 and dx.is_contiguous()
+    nq_b = Q if nq_b is None else nq_b
+    nq_a = nq_b if nq_a is None else nq_a
+    rows = T if rows_per_batch is None else rows_per_batch
+    check(_L().vb_embed_bwd(_ptr(ids), _ptr(dx), _ptr(grad_tables), B, T, Q, V, d, t_split, nq_a, nq_b, rows, row_offset,
+                            _stream()), 'vb_embed_bwd')

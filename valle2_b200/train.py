@@ -1,0 +1,342 @@
+"""Teacher-forced training step on the CUDA stack: forward with saved activations + hand-written backward.
+
+``ValleAR.training_step`` (valle_ar.py:43-90) and ``ValleNAR.training_step`` (valle_nar.py:53-105, repaired per SURVEY
+App. A) return a loss that Lightning back-propagates with torch autograd.  Here the whole step -- embeddings, the
+pre-norm transformer stack, logits, mean cross entropy, and every gradient -- runs on the kernels of libvalle_b200.so;
+``step_loss`` hands the result to autograd through one ``torch.autograd.Function`` whose inputs are the model's parameters,
+so ``loss.backward()`` / an optimizer step work exactly as with the reference.
+
+GEMMs: forward and backward use ``ops.linear`` (tcgen05 for bf16, SIMT fp32 in validation mode).  For y = x W^T:
+    dgrad  dx (R,K) = dy (R,N) . W (N,K)        = linear(dy, W^T)            W^T (K,N) materialised per step
+    wgrad  dW (N,K) = dy^T (N,R) . x (R,K)      = linear(dy^T, x^T)          activations transposed by vb_transpose
+R (= B*S rows) is padded to a multiple of 8 with zero rows (TMA pitch rule of the bf16 GEMM).
+Everything else (LayerNorm / GELU / attention backward, cross entropy, embedding scatter, bias column sums) is csrc/train.cu.
+
+Precision: 'bf16' = bf16 operands, fp32 accumulation, fp32 residual stream and fp32 gradients of the residual stream and
+of all parameters; 'fp32' = validation mode (gradients within 1e-4 of torch autograd on the CPU oracle).
+Dropout is not applied (the parity configuration: ``dropout=0`` and PE dropout zeroed, SURVEY K-3).
+"""
+from __future__ import annotations
+
+import torch
+
+from . import ops
+from .ops import MASK_NONE, MASK_PREFIX_LM
+
+
+def _cd(precision: str) -> torch.dtype:
+    return torch.bfloat16 if precision == 'bf16' else torch.float32
+
+
+def _pad8(n: int) -> int:
+    return (n + 7) // 8 * 8
+
+
+def _i32(t: torch.Tensor, device) -> torch.Tensor:
+    return t.to(device=device, dtype=torch.int32).contiguous()
+
+
+class _Lin:
+    """One nn.Linear in the compute dtype: W (N,K), its transpose for dgrad, fp32 bias."""
+
+    def __init__(self, weight: torch.Tensor, bias: torch.Tensor | None, cd: torch.dtype, pad_n: bool = False):
+        w = weight.detach().to(cd)
+        self.N = w.shape[0]
+        if pad_n and self.N % 8:                      # logits head (V = 1025): zero rows so that the dgrad K is aligned
+            w = torch.cat([w, torch.zeros(_pad8(self.N) - self.N, w.shape[1], device=w.device, dtype=cd)], 0)
+        self.w = w.contiguous()
+        self.wt = ops.transpose(self.w)               # (K, Npad)
+        self.b = None if bias is None else bias.detach().float().contiguous()
+
+
+def _linear_fwd(x: torch.Tensor, lin: _Lin, *, residual: torch.Tensor | None = None, out: torch.Tensor | None = None,
+                out_dtype: torch.dtype | None = None) -> torch.Tensor:
+    return ops.linear(x, lin.w, lin.b, residual=residual, out=out, out_dtype=out_dtype)
+
+
+def _wgrad(dy_t: torch.Tensor, x_t: torch.Tensor) -> torch.Tensor:
+    """dW (N,K) fp32 = dy^T (N,Rp) . x (Rp,K), both operands given transposed (row = feature, Rp contiguous)."""
+    return ops.linear(dy_t, x_t, out_dtype=torch.float32)
+
+
+class StackTrainer:
+    """Forward (saving what the backward needs) and backward of a ``Transformer`` stack over packed rows."""
+
+    def __init__(self, transformer, n_heads: int, precision: str, norm: str, stage_embs=None):
+        self.cd = _cd(precision)
+        self.H = n_heads
+        self.norm = norm
+        self.layers = []
+        for layer in transformer.layers:
+            a, f = layer.self_attn, layer.ffn
+            L = {'qkv': _Lin(a.qkv.weight, None, self.cd), 'o': _Lin(a.out.weight, a.out.bias, self.cd),
+                 'f1': _Lin(f.linear_1.weight, f.linear_1.bias, self.cd), 'f2': _Lin(f.linear_2.weight, f.linear_2.bias, self.cd)}
+            for name in ('norm1', 'norm2'):
+                nm = getattr(layer, name)
+                if norm == 'LayerNorm':
+                    L[name] = {'g': nm.weight.detach().float().contiguous(), 'b': nm.bias.detach().float().contiguous(), 'eps': nm.eps}
+                else:
+                    L[name] = {'mod': nm, 'eps': nm.eps}
+            self.layers.append(L)
+        self.stage_embs = stage_embs
+        self.d = self.layers[0]['o'].N
+        self.F = self.layers[0]['f1'].N
+
+    # -- stage-conditioned AdaLN folded into one affine LayerNorm per (layer, norm): modules.py:93-99 -------------------
+    def _affine(self, L: dict, name: str, stage: int):
+        nrm = L[name]
+        if self.norm == 'LayerNorm':
+            return nrm['g'], nrm['b'], None
+        nm = nrm['mod']
+        d = self.d
+        e = self.stage_embs[stage].detach().float().reshape(1, d).contiguous()
+        wb = ops.linear(e, nm.project_layer.weight.detach().float().contiguous(), nm.project_layer.bias.detach().float().contiguous())
+        w, b = wb[0, :d], wb[0, d:]
+        g0, b0 = nm.norm.weight.detach().float(), nm.norm.bias.detach().float()
+        return (w * g0).contiguous(), (w * b0 + b).contiguous(), {'w': w, 'e': e, 'g0': g0, 'b0': b0}
+
+    def forward(self, x: torch.Tensor, B: int, S: int, *, mask_mode: int, x_lens, kv_lens, stage: int = 0):
+        """x (Rp, d) fp32 residual stream (rows >= B*S are zero padding), updated in place.  Returns the cache."""
+        Rp, d = x.shape
+        R = B * S
+        cd, H, F = self.cd, self.H, self.F
+        dev = x.device
+        use_tc = cd == torch.bfloat16 and d // H == 64
+        cache = []
+        for L in self.layers:
+            c = {}
+            g1, b1, c['fold1'] = self._affine(L, 'norm1', stage)
+            c['g1'] = g1
+            c['x_in'] = x.clone()
+            c['h1'] = torch.zeros(Rp, d, device=dev, dtype=cd)
+            ops.residual_layernorm(x[:R], g1, b1, c['h1'][:R], eps=L['norm1']['eps'])
+            c['qkv'] = torch.zeros(Rp, 3 * d, device=dev, dtype=cd)
+            _linear_fwd(c['h1'][:R], L['qkv'], out=c['qkv'][:R])
+            c['o'] = torch.zeros(Rp, d, device=dev, dtype=cd)
+            ops.attention_packed(c['qkv'][:R], c['o'][:R], B, S, H, mask_mode=mask_mode, x_lens=x_lens, kv_lens=kv_lens, use_tc=use_tc)
+            _linear_fwd(c['o'][:R], L['o'], residual=x[:R], out=x[:R])
+            g2, b2, c['fold2'] = self._affine(L, 'norm2', stage)
+            c['g2'] = g2
+            c['x_mid'] = x.clone()
+            c['h2'] = torch.zeros(Rp, d, device=dev, dtype=cd)
+            ops.residual_layernorm(x[:R], g2, b2, c['h2'][:R], eps=L['norm2']['eps'])
+            c['f_pre'] = torch.zeros(Rp, F, device=dev, dtype=cd)
+            _linear_fwd(c['h2'][:R], L['f1'], out=c['f_pre'][:R])
+            c['f'] = torch.zeros(Rp, F, device=dev, dtype=cd)
+            ops.gelu_fwd(c['f_pre'], c['f'])
+            _linear_fwd(c['f'][:R], L['f2'], residual=x[:R], out=x[:R])
+            cache.append(c)
+        return cache
+
+    def backward(self, dx: torch.Tensor, cache: list, B: int, S: int, *, mask_mode: int, x_lens, kv_lens) -> list[dict]:
+        """dx (Rp, d) fp32: gradient wrt the stack output, turned in place into the gradient wrt the stack input.
+        Returns per-layer parameter gradients (fp32)."""
+        Rp, d = dx.shape
+        R = B * S
+        cd, H = self.cd, self.H
+        dev = dx.device
+        grads = [None] * len(self.layers)
+        dxb = torch.zeros(Rp, d, device=dev, dtype=cd)
+        for li in range(len(self.layers) - 1, -1, -1):
+            L, c = self.layers[li], cache[li]
+            g = {}
+            # ---- x_out = x_mid + f W2^T + b2 ----
+            ops.residual_layernorm(dx[:R], None, None, dxb[:R])                    # cast of the residual gradient
+            dxb_t = ops.transpose(dxb)                                             # (d, Rp)
+            g['f2.b'] = ops.colsum(dx[:R])
+            g['f2.w'] = _wgrad(dxb_t, ops.transpose(c['f']))                       # (d, F)
+            df = torch.zeros(Rp, self.F, device=dev, dtype=cd)
+            ops.linear(dxb[:R], L['f2'].wt, out=df[:R])                            # (R, F)
+            dpre = ops.gelu_bwd(c['f_pre'], df, df)                                # in place
+            g['f1.b'] = ops.colsum(dpre[:R])
+            g['f1.w'] = _wgrad(ops.transpose(dpre), ops.transpose(c['h2']))        # (F, d)
+            dh = torch.zeros(Rp, d, device=dev, dtype=cd)
+            ops.linear(dpre[:R], L['f1'].wt, out=dh[:R])
+            g['n2.g'], g['n2.b'] = ops.layernorm_bwd(c['x_mid'][:R], c['g2'], dh[:R], dx[:R], L['norm2']['eps'])
+            # ---- x_mid = x_in + o Wo^T + bo ----
+            ops.residual_layernorm(dx[:R], None, None, dxb[:R])
+            dxb_t = ops.transpose(dxb)
+            g['o.b'] = ops.colsum(dx[:R])
+            g['o.w'] = _wgrad(dxb_t, ops.transpose(c['o']))                        # (d, d)
+            do = torch.zeros(Rp, d, device=dev, dtype=cd)
+            ops.linear(dxb[:R], L['o'].wt, out=do[:R])
+            dqkv = torch.zeros(Rp, 3 * d, device=dev, dtype=cd)
+            ops.attention_bwd(c['qkv'][:R], c['o'][:R], do[:R], dqkv[:R], B, S, H, mask_mode=mask_mode, x_lens=x_lens, kv_lens=kv_lens)
+            g['qkv.w'] = _wgrad(ops.transpose(dqkv), ops.transpose(c['h1']))       # (3d, d)
+            ops.linear(dqkv[:R], L['qkv'].wt, out=dh[:R])
+            g['n1.g'], g['n1.b'] = ops.layernorm_bwd(c['x_in'][:R], c['g1'], dh[:R], dx[:R], L['norm1']['eps'])
+            g['fold1'], g['fold2'] = c['fold1'], c['fold2']
+            grads[li] = g
+            cache[li] = None                                                        # release the layer's activations
+        return grads
+
+
+def _layer_param_grads(prefix: str, layer_mod, g: dict, norm: str, out: dict, stage_key: str | None):
+    """Map one layer's gradient dict onto the reference's parameter names (state_dict keys)."""
+    out[prefix + 'self_attn.qkv.weight'] = g['qkv.w']
+    out[prefix + 'self_attn.out.weight'] = g['o.w']
+    out[prefix + 'self_attn.out.bias'] = g['o.b']
+    out[prefix + 'ffn.linear_1.weight'] = g['f1.w']
+    out[prefix + 'ffn.linear_1.bias'] = g['f1.b']
+    out[prefix + 'ffn.linear_2.weight'] = g['f2.w']
+    out[prefix + 'ffn.linear_2.bias'] = g['f2.b']
+    for name, key in (('norm1', 'n1'), ('norm2', 'n2')):
+        dgp, dbp = g[key + '.g'], g[key + '.b']                   # gradients of the folded gamma', beta'
+        if norm == 'LayerNorm':
+            out[prefix + name + '.weight'] = dgp
+            out[prefix + name + '.bias'] = dbp
+            continue
+        # AdaLN (modules.py:93-99): gamma' = w * g0, beta' = w * b0 + b with [w, b] = project_layer(e_stage).
+        # The chain through these d-sized vectors is host-side glue on tiny tensors.
+        fold = g['fold1' if name == 'norm1' else 'fold2']
+        w, e, g0, b0 = fold['w'], fold['e'], fold['g0'], fold['b0']
+        dw = dgp * g0 + dbp * b0
+        dwb = torch.cat([dw, dbp])                                # gradient of the project_layer output (2d)
+        nm = getattr(layer_mod, name)
+        out[prefix + name + '.norm.weight'] = dgp * w
+        out[prefix + name + '.norm.bias'] = dbp * w
+        out[prefix + name + '.project_layer.weight'] = torch.outer(dwb, e[0])
+        out[prefix + name + '.project_layer.bias'] = dwb
+        de = dwb @ nm.project_layer.weight.detach().float()
+        out[stage_key] = out.get(stage_key, 0) + de.reshape(1, -1)
+
+
+@torch.no_grad()
+def ar_loss_and_grads(model, batch: dict, precision: str):
+    """ValleAR.training_step (valle_ar.py:43-90): returns (loss scalar tensor, {param name: grad})."""
+    cfg, dev = model.config, model.device
+    cd = _cd(precision)
+    tokens, codes = batch['tokens'].to(dev), batch['codes'].to(dev)
+    tokens_lens, codes_lens = batch['tokens_lens'], batch['codes_lens']
+    B = tokens.shape[0]
+    Tx, Ty = int(tokens_lens.max()), int(codes_lens.max())
+    tokens, codes = tokens[:, :Tx], codes[:, :Ty]
+    S, d, V = Tx + Ty, cfg.d_model, cfg.num_audio_tokens + 1
+    R, Rp = B * S, _pad8(B * S)
+    tr = StackTrainer(model.transformer, cfg.n_heads, precision, cfg.norm)
+    tok_table = model.tokens_emb.weight.detach().float().unsqueeze(0).contiguous()
+    aud_table = model.audio_emb.weight.detach().float().unsqueeze(0).contiguous()
+    pe_t = model.tokens_position_emb.pe.detach().float().reshape(-1, d).contiguous()
+    pe_a = model.audio_position_emb.pe.detach().float().reshape(-1, d).contiguous()
+    tok_i, cod_i = _i32(tokens, dev).view(B, Tx, 1), _i32(codes, dev).view(B, Ty, 1)
+    x = torch.zeros(Rp, d, device=dev, dtype=torch.float32)
+    ops.embed_sum_pe(tok_i, tok_table, pe_t, x, out_rows_per_batch=S)
+    ops.embed_sum_pe(cod_i, aud_table, pe_a, x, out_rows_per_batch=S, out_row_offset=Tx)
+    xl = torch.full((B,), Tx, device=dev, dtype=torch.int32)
+    kv_lens = (xl + _i32(codes_lens, dev)).contiguous()
+    cache = tr.forward(x, B, S, mask_mode=MASK_PREFIX_LM, x_lens=xl, kv_lens=kv_lens)
+    # logits over the audio rows (valle_ar.py:80-83), mean CE over every position incl. padding (K-5)
+    Ra, Rap = B * Ty, _pad8(B * Ty)
+    rows = x[:R].view(B, S, d)[:, Tx:].reshape(Ra, d).contiguous()
+    proj = _Lin(model.proj.weight, None, cd, pad_n=True)
+    Vp = proj.w.shape[0]
+    hb = torch.zeros(Rap, d, device=dev, dtype=cd)
+    ops.residual_layernorm(rows, None, None, hb[:Ra])                              # no final norm (K-2): plain cast
+    logits = torch.zeros(Rap, Vp, device=dev, dtype=torch.float32)
+    ops.linear(hb[:Ra], proj.w, out=logits[:Ra])
+    target = _i32(batch['target'].to(dev)[:, :Ty], dev).reshape(-1)
+    dlogits = torch.zeros(Rap, Vp, device=dev, dtype=torch.float32)
+    loss_rows = ops.cross_entropy(logits[:Ra], target, V, dlogits=dlogits[:Ra], scale=1.0 / Ra)
+    loss = ops.colsum(loss_rows.view(Ra, 1), scale=1.0 / Ra)[0]
+    grads = {}
+    dl = torch.zeros(Rap, Vp, device=dev, dtype=cd)
+    ops.residual_layernorm(dlogits[:Ra], None, None, dl[:Ra])
+    grads['proj.weight'] = _wgrad(ops.transpose(dl), ops.transpose(hb))[:V]        # (V, d)
+    dh = torch.zeros(Rap, d, device=dev, dtype=cd)
+    ops.linear(dl[:Ra], proj.wt, out=dh[:Ra])
+    dx = torch.zeros(Rp, d, device=dev, dtype=torch.float32)
+    dx[:R].view(B, S, d)[:, Tx:] = dh[:Ra].view(B, Ty, d).float()                   # scatter into the audio rows (plumbing)
+    lg = tr.backward(dx, cache, B, S, mask_mode=MASK_PREFIX_LM, x_lens=xl, kv_lens=kv_lens)
+    for li, g in enumerate(lg):
+        _layer_param_grads(f'transformer.layers.{li}.', model.transformer.layers[li], g, cfg.norm, grads, None)
+    gt = torch.zeros_like(tok_table)
+    ga = torch.zeros_like(aud_table)
+    ops.embed_bwd(tok_i, dx, gt, rows_per_batch=S)
+    ops.embed_bwd(cod_i, dx, ga, rows_per_batch=S, row_offset=Tx)
+    grads['tokens_emb.word_embeddings.weight'] = gt[0]
+    grads['audio_emb.word_embeddings.weight'] = ga[0]
+    return loss, grads
+
+
+@torch.no_grad()
+def nar_loss_and_grads(model, batch: dict, layer: int, precision: str):
+    """ValleNAR.training_step for a fixed stage ``layer`` (valle_nar.py:53-105 with repairs A-1..A-3, A-4 kept)."""
+    cfg, dev = model.config, model.device
+    cd = _cd(precision)
+    codes, tokens = batch['codes'].to(dev), batch['tokens'].to(dev)
+    B, T, Q = codes.shape
+    Tx = int(batch['tokens_lens'].max())
+    tokens = tokens[:, :Tx]
+    prefix_len = min(T // 3, 3 * cfg.quantization_factor)
+    S, d, V = Tx + T, cfg.d_model, cfg.num_audio_tokens
+    R, Rp = B * S, _pad8(B * S)
+    stage_embs = [m.weight for m in model.stage_embs]
+    tr = StackTrainer(model.transformer, cfg.n_heads, precision, cfg.norm, stage_embs)
+    tok_table = model.tokens_emb.weight.detach().float().unsqueeze(0).contiguous()
+    code_tables = torch.stack([m.weight.detach().float() for m in model.codes_embs]).contiguous()
+    pe_t = model.tokens_position_emb.pe.detach().float().reshape(-1, d).contiguous()
+    pe_a = model.audio_position_emb.pe.detach().float().reshape(-1, d).contiguous()
+    tok_i, cod_i = _i32(tokens, dev).view(B, Tx, 1), _i32(codes, dev)
+    x = torch.zeros(Rp, d, device=dev, dtype=torch.float32)
+    ops.embed_sum_pe(tok_i, tok_table, pe_t, x, out_rows_per_batch=S)
+    ops.embed_sum_pe(cod_i, code_tables, pe_a, x, t_split=prefix_len, nq_a=Q, nq_b=layer, out_rows_per_batch=S, out_row_offset=Tx)
+    cache = tr.forward(x, B, S, mask_mode=MASK_NONE, x_lens=None, kv_lens=None, stage=layer - 1)   # padding ignored (A-4)
+    Tt = T - prefix_len
+    Ra, Rap = B * Tt, _pad8(B * Tt)
+    rows = x[:R].view(B, S, d)[:, Tx + prefix_len:].reshape(Ra, d).contiguous()
+    proj = _Lin(model.proj_layers[layer - 1].weight, None, cd, pad_n=True)
+    Vp = proj.w.shape[0]
+    hb = torch.zeros(Rap, d, device=dev, dtype=cd)
+    ops.residual_layernorm(rows, None, None, hb[:Ra])
+    logits = torch.zeros(Rap, Vp, device=dev, dtype=torch.float32)
+    ops.linear(hb[:Ra], proj.w, out=logits[:Ra])
+    target = _i32(codes[:, prefix_len:, layer], dev).reshape(-1)
+    dlogits = torch.zeros(Rap, Vp, device=dev, dtype=torch.float32)
+    loss_rows = ops.cross_entropy(logits[:Ra], target, V, dlogits=dlogits[:Ra], scale=1.0 / Ra)
+    loss = ops.colsum(loss_rows.view(Ra, 1), scale=1.0 / Ra)[0]
+    grads = {}
+    dl = torch.zeros(Rap, Vp, device=dev, dtype=cd)
+    ops.residual_layernorm(dlogits[:Ra], None, None, dl[:Ra])
+    grads[f'proj_layers.{layer - 1}.weight'] = _wgrad(ops.transpose(dl), ops.transpose(hb))[:V]
+    dh = torch.zeros(Rap, d, device=dev, dtype=cd)
+    ops.linear(dl[:Ra], proj.wt, out=dh[:Ra])
+    dx = torch.zeros(Rp, d, device=dev, dtype=torch.float32)
+    dx[:R].view(B, S, d)[:, Tx + prefix_len:] = dh[:Ra].view(B, Tt, d).float()
+    lg = tr.backward(dx, cache, B, S, mask_mode=MASK_NONE, x_lens=None, kv_lens=None)
+    stage_key = f'stage_embs.{layer - 1}.word_embeddings.weight'
+    for li, g in enumerate(lg):
+        _layer_param_grads(f'transformer.layers.{li}.', model.transformer.layers[li], g, cfg.norm, grads, stage_key)
+    gt = torch.zeros_like(tok_table)
+    gc = torch.zeros_like(code_tables)
+    ops.embed_bwd(tok_i, dx, gt, rows_per_batch=S)
+    ops.embed_bwd(cod_i, dx, gc, t_split=prefix_len, nq_a=Q, nq_b=layer, rows_per_batch=S, row_offset=Tx)
+    grads['tokens_emb.word_embeddings.weight'] = gt[0]
+    for q in range(Q):
+        grads[f'codes_embs.{q}.word_embeddings.weight'] = gc[q]
+    return loss, grads
+
+
+class _StepFn(torch.autograd.Function):
+    """loss = f(parameters): forward AND gradients are computed by the CUDA stack in ``forward``; ``backward`` hands the
+    stored gradients (times the incoming scalar) to autograd, so ``loss.backward()`` fills ``param.grad``."""
+
+    @staticmethod
+    def forward(ctx, fn, names, *params):
+        loss, grads = fn()
+        ctx.grads = [grads.get(n) for n in names]
+        ctx.shapes = [p.shape for p in params]
+        return loss.clone()
+
+    @staticmethod
+    def backward(ctx, gout):
+        outs = []
+        for g, shp in zip(ctx.grads, ctx.shapes):
+            outs.append(None if g is None else (g.reshape(shp) * gout))
+        return (None, None, *outs)
+
+
+def step_loss(model, fn):
+    """Differentiable loss of one training step: ``fn() -> (loss, {name: grad})`` runs on the CUDA stack."""
+    named = [(n, p) for n, p in model.named_parameters() if p.requires_grad]
+    names = [n for n, _ in named]
+    return _StepFn.apply(fn, names, *[p for _, p in named])
