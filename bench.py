@@ -345,6 +345,37 @@ def extras(args, dev, tmp):
                       'attention': 'tcgen05' if use_tc else 'simt'}
     except Exception as e:  # report, do not hide
         out['nar'] = {'error': repr(e)}
+    # Training step (BASELINE config 5, per-GPU share): teacher-forced AR, 16 clips of 15 s (Ty = 1126, Tx = 225), bf16
+    # operands / fp32 accumulation, forward + backward on the CUDA stack (valle2_b200/train.py)
+    try:
+        del nar
+        torch.cuda.empty_cache()
+        torch.manual_seed(2)
+        ar = ValleAR(large_cfg('LayerNorm', tmp)).train().to(dev)
+        Bt, Txt, Tyt = args.train_batch, 225, 1126
+        batch = {'tokens': torch.randint(0, 256, (Bt, Txt), generator=g), 'tokens_lens': torch.full((Bt,), Txt),
+                 'codes': torch.randint(0, 1024, (Bt, Tyt), generator=g), 'codes_lens': torch.full((Bt,), Tyt),
+                 'target': torch.randint(0, 1025, (Bt, Tyt), generator=g)}
+        for it in range(3):
+            if it == 1:
+                torch.cuda.synchronize()
+                e0.record()
+            for p_ in ar.parameters():
+                p_.grad = None
+            loss = ar.training_step(batch)
+            loss.backward()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 2
+        S, d, F, L = Txt + Tyt, 1024, 4096, 12
+        fwd = Bt * (L * (S * 2 * (4 * d * d + 2 * d * F) + 4 * S * S * d) + 2 * Tyt * d * 1025)
+        out['train_step'] = {'batch': Bt, 'seq': S, 'ms_per_step': ms, 'clips_per_s': Bt / (ms * 1e-3), 'loss': float(loss),
+                             'model_tflops': 3 * fwd / (ms * 1e-3) / 1e12,
+                             'frac_of_bf16_sustained_peak': 3 * fwd / (ms * 1e-3) / 1e12 / pk['bf16_tflops_sustained'],
+                             'note': 'forward + backward, no optimizer step; flops = 3 x dense forward (no causal discount)',
+                             'peak_mem_gb': torch.cuda.max_memory_allocated() / 1e9}
+    except Exception as e:  # report, do not hide
+        out['train_step'] = {'error': repr(e)}
     return out
 
 
@@ -422,6 +453,7 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--batch', type=int, default=32)
     ap.add_argument('--nar-batch', type=int, default=64)
+    ap.add_argument('--train-batch', type=int, default=16)
     ap.add_argument('--no-extras', action='store_true')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup

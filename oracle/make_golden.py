@@ -243,6 +243,27 @@ def golden_nar(valle, tmp):
     np.savez_compressed(os.path.join(OUT, 'nar_tiny.npz'), **out)
 
 
+def golden_ar_grads(valle, tmp):
+    """Gradients of the reference's own ``ValleAR.training_step`` (autograd through the unmodified modules, eval mode so
+    that the hard-wired PE dropout is inactive, K-3) on the ragged teacher-forced batch of ``ar_tiny.npz``.  Stored as
+    per-parameter summaries (L2 norm, sum, abs-max, first 16 values) to keep the fixture small."""
+    g = np.load(os.path.join(OUT, 'ar_tiny.npz'))
+    oc = synth.tiny_config('LayerNorm')
+    cfg = _ref_config(valle, oc, tmp)
+    model = valle.models.ValleAR(cfg).eval()
+    sd = synth.synth_state_dict(synth.ar_state_shapes(oc), 0)
+    model.load_state_dict(sd, strict=True)
+    batch = {k[3:]: torch.from_numpy(g[k]) for k in g.files if k.startswith('tf_') and k not in ('tf_logits', 'tf_loss')}
+    loss = model.training_step(batch)
+    loss.backward()
+    out = {'loss': _np(loss)}
+    for name, p in model.named_parameters():
+        gr = p.grad.detach().double().flatten()
+        out['stats.' + name] = np.array([float(gr.norm()), float(gr.sum()), float(gr.abs().max())])
+        out['head.' + name] = gr[:16].numpy()
+    np.savez_compressed(os.path.join(OUT, 'ar_tiny_grads.npz'), **out)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     tmp = tempfile.mkdtemp(prefix='valle_golden_')
@@ -255,6 +276,7 @@ def main():
         golden_masks_sampling(valle)
         golden_ar(valle, tmp)
         golden_nar(valle, tmp)
+        golden_ar_grads(valle, tmp)
     finally:
         os.chdir(cwd)
     for f in sorted(os.listdir(OUT)):

@@ -216,3 +216,26 @@ def test_small_backward_kernels(ops):
             for j in range(4 if t < 3 else 2):
                 ref[j, ids[b, t, j]] += dx[b * 11 + 2 + t].double()
     assert rel_err(gt, ref) < 1e-5
+
+
+def test_ar_training_gradients_vs_reference_golden(tmp_path):
+    """fp32 mode against the gradients of the EXECUTED reference (tests/golden/ar_tiny_grads.npz: autograd through the
+    reference's own ValleAR.training_step on the ragged batch of ar_tiny.npz)."""
+    import os
+
+    import numpy as np
+    valle2_b200.set_precision('fp32')
+    gdir = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+    g, gg = np.load(os.path.join(gdir, 'ar_tiny.npz')), np.load(os.path.join(gdir, 'ar_tiny_grads.npz'))
+    oc = synth.tiny_config('LayerNorm')
+    model, _ = build('ValleAR', oc, tmp_path, 0)
+    batch = {k[3:]: torch.from_numpy(g[k]) for k in g.files if k.startswith('tf_') and k not in ('tf_logits', 'tf_loss')}
+    loss = model.training_step(batch)
+    loss.backward()
+    assert abs(loss.item() - float(gg['loss'])) < 1e-4
+    for name, p in model.named_parameters():
+        gr = p.grad.detach().cpu().double().flatten()
+        ref_stats, ref_head = gg['stats.' + name], gg['head.' + name]
+        scale = ref_stats[2] + 1e-12
+        assert abs(float(gr.norm()) - ref_stats[0]) / (ref_stats[0] + 1e-12) < 1e-4, name
+        assert np.abs(gr[:16].numpy() - ref_head).max() / scale < 1e-4, name

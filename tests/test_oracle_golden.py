@@ -141,3 +141,25 @@ def test_nar_tiny(golden):
     logits, loss = vo.nar_teacher_forced(sd, oc, T(g['nar_tf_tokens']), T(g['nar_tf_codes']),
                                          torch.full((B,), 5), torch.full((B,), 12), int(g['nar_tf_layer']))
     close(logits, g['nar_tf_logits']); close(loss, g['nar_tf_loss'], tol=1e-6)
+
+
+def test_ar_training_gradients_match_the_executed_reference(golden):
+    """torch autograd over the oracle's restatement of ValleAR.training_step == autograd through the reference's own
+    modules (per-parameter summaries frozen by oracle/make_golden.py:golden_ar_grads).  This pins the gradient oracle
+    used by tests/test_gpu_training.py."""
+    g, gg = golden('ar_tiny'), golden('ar_tiny_grads')
+    oc = synth.tiny_config('LayerNorm')
+    sd = synth.synth_state_dict(synth.ar_state_shapes(oc), 0)
+    sdg = {k: (v.clone().requires_grad_(True) if not k.endswith('.pe') else v) for k, v in sd.items()}
+    _, loss = vo.ar_teacher_forced(sdg, oc, T(g['tf_tokens']), T(g['tf_codes']), T(g['tf_tokens_lens']),
+                                   T(g['tf_codes_lens']), T(g['tf_target']))
+    loss.backward()
+    close(loss.detach(), gg['loss'], tol=1e-6)
+    names = [k[6:] for k in gg if k.startswith('stats.')]
+    assert len(names) == 2 + 2 * 11 + 1          # two embedding tables, 11 tensors per layer, proj
+    for name in names:
+        gr = sdg[name].grad.double().flatten()
+        stats = np.array([float(gr.norm()), float(gr.sum()), float(gr.abs().max())])
+        scale = gg['stats.' + name][2] + 1e-12
+        assert np.abs(stats - gg['stats.' + name]).max() / max(scale, gg['stats.' + name][0]) < 1e-4, name
+        assert np.abs(gr[:16].numpy() - gg['head.' + name]).max() / scale < 1e-4, name

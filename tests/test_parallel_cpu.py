@@ -47,3 +47,42 @@ def test_sharded_generation_matches_single_process(tmp_path):
             n = int(ref_lens[i])
             assert torch.equal(rows[i, :n], ref_rows[i, :n])
             assert (rows[i, n:] == -1).all()
+
+
+def _grad_worker(rank, world_size, port, out_dir):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world_size)
+    from valle2_b200 import parallel
+    torch.manual_seed(0)
+    model = torch.nn.Sequential(torch.nn.Linear(5, 7), torch.nn.Linear(7, 3), torch.nn.Linear(3, 2))
+    x = torch.arange(20, dtype=torch.float32).view(4, 5) / 10
+    part = parallel.shard_batch({'x': x, 'meta': 'kept'}, rank, world_size)
+    assert part['meta'] == 'kept' and part['x'].shape[0] == 2
+    # rank-local loss: the MEAN over the local rows; the last layer gets a gradient on rank 0 only
+    h = model[1](model[0](part['x']))
+    loss = h.pow(2).mean() + (model[2](h).sum() if rank == 0 else 0.0)
+    loss.backward()
+    n_buckets = parallel.allreduce_gradients(model, bucket_bytes=128)
+    assert n_buckets >= 2
+    torch.save({n: p.grad.clone() for n, p in model.named_parameters()}, os.path.join(out_dir, f'g{rank}.pt'))
+    dist.destroy_process_group()
+
+
+def test_gradient_allreduce_matches_full_batch(tmp_path):
+    """World-size-2 gloo: per-rank gradients of the sharded batch, averaged by allreduce_gradients, equal the gradients of
+    the mean loss over the whole batch (the data-parallel training step, BASELINE config 5)."""
+    with socket.socket() as s:
+        s.bind(('127.0.0.1', 0))
+        port = s.getsockname()[1]
+    mp.spawn(_grad_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    torch.manual_seed(0)
+    model = torch.nn.Sequential(torch.nn.Linear(5, 7), torch.nn.Linear(7, 3), torch.nn.Linear(3, 2))
+    x = torch.arange(20, dtype=torch.float32).view(4, 5) / 10
+    h0, h1 = model[1](model[0](x[:2])), model[1](model[0](x[2:]))
+    loss = 0.5 * (h0.pow(2).mean() + model[2](h0).sum()) + 0.5 * h1.pow(2).mean()
+    loss.backward()
+    g0, g1 = torch.load(os.path.join(tmp_path, 'g0.pt')), torch.load(os.path.join(tmp_path, 'g1.pt'))
+    for n, p in model.named_parameters():
+        assert torch.allclose(g0[n], p.grad, atol=1e-6), n
+        assert torch.equal(g0[n], g1[n]), n

@@ -73,3 +73,47 @@ def generate_sharded(decode_fn: Callable[[list[int]], tuple[torch.Tensor, torch.
     idx = shard_indices(n_items, rank, ws)
     rows, lens = decode_fn(idx)
     return gather_ragged(rows, lens, n_items, pad_value)
+
+
+# ---- training: batch-sharded data parallelism (BASELINE config 5) -------------------------------------------
+def allreduce_gradients(model: torch.nn.Module, bucket_bytes: int = 64 << 20) -> int:
+    """Average ``param.grad`` over the ranks: the ONE exchange step of the batch-sharded training step.
+
+    Gradients are flattened into buckets of ~``bucket_bytes`` (fp32) and summed with ``all_reduce`` (NCCL over
+    NVLink/NVSwitch on GPUs -- bucket size picked for launch latency, not link count -- gloo in the CPU tests), then
+    divided by the world size; parameters without a gradient on this rank (e.g. other NAR stages) contribute zeros so that
+    every rank issues the same collectives.  Returns the number of buckets reduced."""
+    rank, ws = world()
+    params = [p for _, p in sorted(model.named_parameters(), key=lambda kv: kv[0]) if p.requires_grad]
+    if ws == 1 or not params:
+        return 0
+    buckets, cur, cur_bytes = [], [], 0
+    for p in params:
+        cur.append(p)
+        cur_bytes += p.numel() * 4
+        if cur_bytes >= bucket_bytes:
+            buckets.append(cur)
+            cur, cur_bytes = [], 0
+    if cur:
+        buckets.append(cur)
+    for bucket in buckets:
+        flat = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1).float() for p in bucket])
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+        flat.div_(ws)
+        off = 0
+        for p in bucket:
+            n = p.numel()
+            g = flat[off:off + n].view_as(p).to(p.dtype)
+            if p.grad is None:
+                p.grad = g.clone()
+            else:
+                p.grad.copy_(g)
+            off += n
+    return len(buckets)
+
+
+def shard_batch(batch: dict, rank: int, world_size: int) -> dict:
+    """Contiguous per-rank slice of a teacher-forced batch dict (tensors whose first dim is the batch)."""
+    B = next(v.shape[0] for v in batch.values() if torch.is_tensor(v) and v.dim() >= 1)
+    lo, hi = (B * rank) // world_size, (B * (rank + 1)) // world_size
+    return {k: (v[lo:hi] if torch.is_tensor(v) and v.dim() >= 1 and v.shape[0] == B else v) for k, v in batch.items()}
