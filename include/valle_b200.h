@@ -210,6 +210,8 @@ int vb_kv_prefetch_l2(const void* pool, int pool_dtype, const int32_t* block_tab
 int vb_transpose(const void* src, int dtype, int64_t rows, int64_t cols, int64_t lds, void* dst, int64_t ldd, void* stream);
 /* out[n] (+)= scale * sum_r x[r][n], deterministic */
 int vb_colsum(const void* x, int dtype, int64_t R, int N, int64_t ldx, float* out, int accumulate, float scale, void* stream);
+/* first level of a two-level column sum over long matrices: part[row_blocks][N]; reduce part with vb_colsum */
+int vb_colsum_blocks(const void* x, int dtype, int64_t R, int N, int64_t ldx, float* part, int row_blocks, void* stream);
 /* y = gelu_erf(pre);  dpre = dy * gelu_erf'(pre)   (modules.py:216) */
 int vb_gelu_fwd(const void* pre, int dtype, void* y, int64_t n, void* stream);
 int vb_gelu_bwd(const void* pre, const void* dy, int dtype, void* dpre, int64_t n, void* stream);

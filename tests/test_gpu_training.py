@@ -198,6 +198,9 @@ def test_small_backward_kernels(ops):
         assert rel_err(out.float(), pg.grad) < (1e-5 if dt == torch.float32 else 1e-2)
         x = torch.randn(333, 70, device='cuda').to(dt)
         assert rel_err(ops.colsum(x, scale=0.5), 0.5 * x.double().sum(0)) < 1e-5
+        xl = torch.randn(5000, 130, device='cuda').to(dt)            # two-level path
+        assert rel_err(ops.colsum(xl), xl.double().sum(0)) < 1e-5
+        assert torch.equal(ops.colsum(xl), ops.colsum(xl))
     logits = torch.randn(19, 1032, device='cuda') * 3
     tgt = torch.randint(0, 1025, (19,), dtype=torch.int32, device='cuda')
     dl = torch.zeros(19, 1032, device='cuda')

@@ -33,6 +33,7 @@ SIGNATURES = {
     'vb_kv_prefetch_l2': (_i, [_p, _i, _p, _i, _p, _i, _i, _i, _i, _i, _p]),
     'vb_transpose': (_i, [_p, _i, _i64, _i64, _i64, _p, _i64, _p]),
     'vb_colsum': (_i, [_p, _i, _i64, _i, _i64, _p, _i, _f, _p]),
+    'vb_colsum_blocks': (_i, [_p, _i, _i64, _i, _i64, _p, _i, _p]),
     'vb_gelu_fwd': (_i, [_p, _i, _p, _i64, _p]),
     'vb_gelu_bwd': (_i, [_p, _p, _i, _p, _i64, _p]),
     'vb_layernorm_bwd_blocks': (_i, [_i64]),

@@ -12,6 +12,7 @@
 // First functional revision: correctness first (checked against torch autograd of the CPU oracle), tensor-core attention
 // backward is the next step.
 #include <math.h>
+#include <stdlib.h>
 
 #include <algorithm>
 
@@ -43,12 +44,17 @@ __global__ void transpose_kernel(const T* __restrict__ src, int64_t lds, T* __re
 template <typename T>
 __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, int64_t ldx, int64_t R, int N, float* __restrict__ out,
                                                      int accumulate, float scale) {
+    // blockIdx.y = row block (rows [y * rows_per_block, ...)), writing its own output row: long matrices are reduced in
+    // two deterministic levels (vb_colsum calls itself on the partial rows)
     __shared__ float red[8][32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int n = blockIdx.x * 32 + lane;
+    const int64_t rows_per_block = (R + gridDim.y - 1) / gridDim.y;
+    const int64_t r_lo = blockIdx.y * rows_per_block, r_hi = min(R, r_lo + rows_per_block);
+    out += static_cast<int64_t>(blockIdx.y) * N;
     float acc = 0.f;
     if (n < N)
-        for (int64_t r = warp; r < R; r += 8) acc += to_f32<T>(x[r * ldx + n]);
+        for (int64_t r = r_lo + warp; r < r_hi; r += 8) acc += to_f32<T>(x[r * ldx + n]);
     red[warp][lane] = acc;
     __syncthreads();
     if (warp == 0 && n < N) {
@@ -442,6 +448,279 @@ __global__ void __launch_bounds__(256) attn_bwd_dkv_kernel(const T* __restrict__
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// attention backward on tensor cores (bf16 operands, fp32 accumulate): the same two-kernel tiling as above, 4 warps per CTA,
+// each warp owns 16 rows of the CTA's 64-row tile and runs every product as mma.sync.m16n8k16 with ldmatrix fragments
+// from 128-byte-row shared-memory tiles whose 16-byte chunks are XOR-swizzled by (row & 7) (conflict-free, as the KV pool).
+// P and dS are rounded to bf16 between the two GEMMs of each product chain, as in the forward.
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void ldsm4(uint32_t addr, uint32_t (&r)[4]) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm4t(uint32_t addr, uint32_t (&r)[4]) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// 64 x 64 bf16 tile: global rows [row0, row0 + 64) x 64 columns (pitch in elements) -> swizzled shared memory; rows past
+// n_rows are zero
+__device__ __forceinline__ void load_tile_bf16(uint32_t dst, const __nv_bfloat16* __restrict__ src, int64_t pitch, int row0, int n_rows) {
+    for (int idx = threadIdx.x; idx < 512; idx += 128) {
+        const int r = idx >> 3, ch = idx & 7;
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (row0 + r < n_rows) v = *reinterpret_cast<const uint4*>(src + static_cast<int64_t>(row0 + r) * pitch + ch * 8);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + r * 128 + ((ch ^ (r & 7)) << 4)), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+    }
+}
+// A fragments (4 k-steps of 16) of rows [r0, r0 + 16) of a tile
+__device__ __forceinline__ void load_a_frags(uint32_t tile, int r0, int lane, uint32_t (&a)[4][4]) {
+    const int row = r0 + (lane & 15);
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) ldsm4(tile + row * 128 + (((2 * kk + (lane >> 4)) ^ (row & 7)) << 4), a[kk]);
+}
+// c[j] (16 x 8, j = 0..7) = A (16 x 64, fragments a) . T^T, T = tile [64 rows = n][64 = k]
+__device__ __forceinline__ void mma_a_tt(float (&c)[8][4], const uint32_t (&a)[4][4], uint32_t tile, int lane) {
+    const int lr = lane & 7, lm = lane >> 3;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        c[j][0] = c[j][1] = c[j][2] = c[j][3] = 0.f;
+#pragma unroll
+        for (int kp = 0; kp < 2; ++kp) {
+            uint32_t r[4];
+            ldsm4(tile + (8 * j + lr) * 128 + (((4 * kp + lm) ^ lr) << 4), r);
+            mma16816(c[j], a[2 * kp], r[0], r[1]);
+            mma16816(c[j], a[2 * kp + 1], r[2], r[3]);
+        }
+    }
+}
+// c[j] (16 x 8 output columns 8j.., j = 0..7) += A (16 x 64 over the tile's ROWS, fragments a) . T, T = tile [64 rows = k][64 = n]
+__device__ __forceinline__ void mma_a_t_acc(float (&c)[8][4], const uint32_t (&a)[4][4], uint32_t tile, int lane) {
+    const int lr = lane & 7, lm = lane >> 3;
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+        for (int jp = 0; jp < 4; ++jp) {
+            uint32_t r[4];
+            const int row = 16 * kk + (lm & 1) * 8 + lr;
+            ldsm4t(tile + row * 128 + (((2 * jp + (lm >> 1)) ^ lr) << 4), r);
+            mma16816(c[2 * jp], a[kk], r[0], r[1]);
+            mma16816(c[2 * jp + 1], a[kk], r[2], r[3]);
+        }
+    }
+}
+// accumulator layout (rows g, g+8; columns 8j + 2t, +1) -> A fragments of the next product (k = those columns)
+__device__ __forceinline__ void acc_to_a(const float (&c)[8][4], uint32_t (&a)[4][4]) {
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+        a[kk][0] = pack_bf16x2(c[2 * kk][0], c[2 * kk][1]);
+        a[kk][1] = pack_bf16x2(c[2 * kk][2], c[2 * kk][3]);
+        a[kk][2] = pack_bf16x2(c[2 * kk + 1][0], c[2 * kk + 1][1]);
+        a[kk][3] = pack_bf16x2(c[2 * kk + 1][2], c[2 * kk + 1][3]);
+    }
+}
+
+__global__ void __launch_bounds__(128) attn_bwd_dq_mma_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ o,
+                                                              const __nv_bfloat16* __restrict__ dO, __nv_bfloat16* __restrict__ dqkv,
+                                                              float* __restrict__ lse, float* __restrict__ delta, int S, int H,
+                                                              int mask_mode, const int32_t* __restrict__ x_lens,
+                                                              const int32_t* __restrict__ kv_lens, float scale) {
+    __shared__ __align__(128) uint8_t tiles[4][TS * 128];      // Q, dO, K, V
+    __shared__ float delta_s[TS];
+    const uint32_t Qs = smem_u32(tiles[0]), dOs = smem_u32(tiles[1]), Ks = smem_u32(tiles[2]), Vs = smem_u32(tiles[3]);
+    const int it = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const int d = H * TS;
+    const int64_t rp = 3 * static_cast<int64_t>(d);
+    const int kv_len = kv_lens ? min(kv_lens[b], S) : S;
+    const int x_len = x_lens ? x_lens[b] : 0;
+    const int i0 = it * TS;
+    const __nv_bfloat16* qb = qkv + static_cast<int64_t>(b) * S * rp + h * TS;
+    const __nv_bfloat16* ob = o + static_cast<int64_t>(b) * S * d + h * TS;
+    const __nv_bfloat16* dob = dO + static_cast<int64_t>(b) * S * d + h * TS;
+    load_tile_bf16(Qs, qb, rp, i0, S);
+    load_tile_bf16(dOs, dob, d, i0, S);
+    {   // delta_i = sum_e dO[i][e] * O[i][e]: two threads per row
+        const int r = threadIdx.x >> 1, half = threadIdx.x & 1;
+        float acc = 0.f;
+        if (i0 + r < S) {
+            const __nv_bfloat16* p1 = dob + static_cast<int64_t>(i0 + r) * d + half * 32;
+            const __nv_bfloat16* p2 = ob + static_cast<int64_t>(i0 + r) * d + half * 32;
+#pragma unroll 8
+            for (int e = 0; e < 32; ++e) acc += __bfloat162float(p1[e]) * __bfloat162float(p2[e]);
+        }
+        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+        if (half == 0) {
+            delta_s[r] = acc;
+            if (i0 + r < S) delta[(static_cast<int64_t>(b) * H + h) * S + i0 + r] = acc;
+        }
+    }
+    __syncthreads();
+    uint32_t qa[4][4], doa[4][4];
+    load_a_frags(Qs, 16 * warp, lane, qa);
+    load_a_frags(dOs, 16 * warp, lane, doa);
+    const int ra = i0 + 16 * warp + g, rb = ra + 8;          // the two query rows of this thread
+    const float dla = delta_s[16 * warp + g], dlb = delta_s[16 * warp + g + 8];
+    const int i_max = min(i0 + TS, S) - 1;
+    int j_end = kv_len;
+    if (mask_mode == VB_MASK_PREFIX_LM) j_end = min(kv_len, max(x_len, i_max + 1));
+    // pass 1: row max / sum
+    float ma = -INFINITY, mb = -INFINITY, la = 0.f, lb = 0.f;
+    for (int j0 = 0; j0 < j_end; j0 += TS) {
+        __syncthreads();
+        load_tile_bf16(Ks, qb + d, rp, j0, S);
+        __syncthreads();
+        float s[8][4];
+        mma_a_tt(s, qa, Ks, lane);
+        float mxa = -INFINITY, mxb = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                const int col = j0 + 8 * j + 2 * t + c;
+                s[j][c] = allowed(ra, col, kv_len, x_len, mask_mode) ? s[j][c] * scale : -INFINITY;
+                s[j][2 + c] = allowed(rb, col, kv_len, x_len, mask_mode) ? s[j][2 + c] * scale : -INFINITY;
+                mxa = fmaxf(mxa, s[j][c]);
+                mxb = fmaxf(mxb, s[j][2 + c]);
+            }
+        mxa = fmaxf(mxa, __shfl_xor_sync(0xffffffffu, mxa, 1)); mxa = fmaxf(mxa, __shfl_xor_sync(0xffffffffu, mxa, 2));
+        mxb = fmaxf(mxb, __shfl_xor_sync(0xffffffffu, mxb, 1)); mxb = fmaxf(mxb, __shfl_xor_sync(0xffffffffu, mxb, 2));
+        const float na = fmaxf(ma, mxa), nb = fmaxf(mb, mxb);
+        float pa = 0.f, pb = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                pa += (s[j][c] == -INFINITY) ? 0.f : expf(s[j][c] - na);
+                pb += (s[j][2 + c] == -INFINITY) ? 0.f : expf(s[j][2 + c] - nb);
+            }
+        pa += __shfl_xor_sync(0xffffffffu, pa, 1); pa += __shfl_xor_sync(0xffffffffu, pa, 2);
+        pb += __shfl_xor_sync(0xffffffffu, pb, 1); pb += __shfl_xor_sync(0xffffffffu, pb, 2);
+        if (na != -INFINITY) { la = la * ((ma == -INFINITY) ? 0.f : expf(ma - na)) + pa; ma = na; }
+        if (nb != -INFINITY) { lb = lb * ((mb == -INFINITY) ? 0.f : expf(mb - nb)) + pb; mb = nb; }
+    }
+    const float lsa = (la > 0.f) ? ma + logf(la) : INFINITY, lsb = (lb > 0.f) ? mb + logf(lb) : INFINITY;
+    if (t == 0) {
+        if (ra < S) lse[(static_cast<int64_t>(b) * H + h) * S + ra] = lsa;
+        if (rb < S) lse[(static_cast<int64_t>(b) * H + h) * S + rb] = lsb;
+    }
+    // pass 2: dQ
+    float dq[8][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) dq[j][0] = dq[j][1] = dq[j][2] = dq[j][3] = 0.f;
+    for (int j0 = 0; j0 < j_end; j0 += TS) {
+        __syncthreads();
+        load_tile_bf16(Ks, qb + d, rp, j0, S);
+        load_tile_bf16(Vs, qb + 2 * d, rp, j0, S);
+        __syncthreads();
+        float s[8][4], dp[8][4];
+        mma_a_tt(s, qa, Ks, lane);
+        mma_a_tt(dp, doa, Vs, lane);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                const int col = j0 + 8 * j + 2 * t + c;
+                const float p0 = (lsa != INFINITY && allowed(ra, col, kv_len, x_len, mask_mode)) ? expf(s[j][c] * scale - lsa) : 0.f;
+                const float p1 = (lsb != INFINITY && allowed(rb, col, kv_len, x_len, mask_mode)) ? expf(s[j][2 + c] * scale - lsb) : 0.f;
+                s[j][c] = p0 * (dp[j][c] - dla) * scale;            // dS
+                s[j][2 + c] = p1 * (dp[j][2 + c] - dlb) * scale;
+            }
+        uint32_t dsa[4][4];
+        acc_to_a(s, dsa);
+        mma_a_t_acc(dq, dsa, Ks, lane);
+    }
+    __nv_bfloat16* dqb = dqkv + static_cast<int64_t>(b) * S * rp + h * TS;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int col = 8 * j + 2 * t;
+        if (ra < S) *reinterpret_cast<uint32_t*>(dqb + static_cast<int64_t>(ra) * rp + col) = pack_bf16x2(dq[j][0], dq[j][1]);
+        if (rb < S) *reinterpret_cast<uint32_t*>(dqb + static_cast<int64_t>(rb) * rp + col) = pack_bf16x2(dq[j][2], dq[j][3]);
+    }
+}
+
+__global__ void __launch_bounds__(128) attn_bwd_dkv_mma_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ dO,
+                                                               __nv_bfloat16* __restrict__ dqkv, const float* __restrict__ lse,
+                                                               const float* __restrict__ delta, int S, int H, int mask_mode,
+                                                               const int32_t* __restrict__ x_lens, const int32_t* __restrict__ kv_lens,
+                                                               float scale) {
+    __shared__ __align__(128) uint8_t tiles[4][TS * 128];      // K, V, Q, dO
+    __shared__ float lse_s[TS], dl_s[TS];
+    const uint32_t Ks = smem_u32(tiles[0]), Vs = smem_u32(tiles[1]), Qs = smem_u32(tiles[2]), dOs = smem_u32(tiles[3]);
+    const int jt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const int d = H * TS;
+    const int64_t rp = 3 * static_cast<int64_t>(d);
+    const int kv_len = kv_lens ? min(kv_lens[b], S) : S;
+    const int x_len = x_lens ? x_lens[b] : 0;
+    const int j0 = jt * TS;
+    const __nv_bfloat16* qb = qkv + static_cast<int64_t>(b) * S * rp + h * TS;
+    const __nv_bfloat16* dob = dO + static_cast<int64_t>(b) * S * d + h * TS;
+    float dk[8][4], dv[8][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) dk[j][0] = dk[j][1] = dk[j][2] = dk[j][3] = dv[j][0] = dv[j][1] = dv[j][2] = dv[j][3] = 0.f;
+    const int ka_row = j0 + 16 * warp + g, kb_row = ka_row + 8;        // the two key rows of this thread
+    if (j0 < kv_len) {
+        load_tile_bf16(Ks, qb + d, rp, j0, S);
+        load_tile_bf16(Vs, qb + 2 * d, rp, j0, S);
+        __syncthreads();
+        uint32_t ka[4][4], va[4][4];
+        load_a_frags(Ks, 16 * warp, lane, ka);
+        load_a_frags(Vs, 16 * warp, lane, va);
+        int i_begin = 0;
+        if (mask_mode == VB_MASK_PREFIX_LM && j0 >= x_len) i_begin = j0;
+        for (int i0 = i_begin; i0 < S; i0 += TS) {
+            __syncthreads();
+            load_tile_bf16(Qs, qb, rp, i0, S);
+            load_tile_bf16(dOs, dob, d, i0, S);
+            if (threadIdx.x < TS) {
+                const int i = i0 + threadIdx.x;
+                lse_s[threadIdx.x] = (i < S) ? lse[(static_cast<int64_t>(b) * H + h) * S + i] : INFINITY;
+                dl_s[threadIdx.x] = (i < S) ? delta[(static_cast<int64_t>(b) * H + h) * S + i] : 0.f;
+            }
+            __syncthreads();
+            float st[8][4], dpt[8][4];                     // S^T and dP^T: rows = keys, columns = queries
+            mma_a_tt(st, ka, Qs, lane);
+            mma_a_tt(dpt, va, dOs, lane);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    const int qi = 8 * j + 2 * t + c, i = i0 + qi;
+                    const float li = lse_s[qi], di = dl_s[qi];
+                    const bool oka = i < S && li != INFINITY && allowed(i, ka_row, kv_len, x_len, mask_mode);
+                    const bool okb = i < S && li != INFINITY && allowed(i, kb_row, kv_len, x_len, mask_mode);
+                    const float p0 = oka ? expf(st[j][c] * scale - li) : 0.f;
+                    const float p1 = okb ? expf(st[j][2 + c] * scale - li) : 0.f;
+                    st[j][c] = p0; st[j][2 + c] = p1;                              // P^T
+                    dpt[j][c] = p0 * (dpt[j][c] - di) * scale;                     // dS^T
+                    dpt[j][2 + c] = p1 * (dpt[j][2 + c] - di) * scale;
+                }
+            uint32_t pa[4][4];
+            acc_to_a(st, pa);
+            mma_a_t_acc(dv, pa, dOs, lane);       // dV[key][e] += sum_i P^T[key][i] dO[i][e]
+            acc_to_a(dpt, pa);
+            mma_a_t_acc(dk, pa, Qs, lane);        // dK[key][e] += sum_i dS^T[key][i] Q[i][e]
+        }
+    }
+    __nv_bfloat16* dkb = dqkv + static_cast<int64_t>(b) * S * rp + h * TS + d;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int col = 8 * j + 2 * t;
+        if (ka_row < S) {
+            *reinterpret_cast<uint32_t*>(dkb + static_cast<int64_t>(ka_row) * rp + col) = pack_bf16x2(dk[j][0], dk[j][1]);
+            *reinterpret_cast<uint32_t*>(dkb + static_cast<int64_t>(ka_row) * rp + d + col) = pack_bf16x2(dv[j][0], dv[j][1]);
+        }
+        if (kb_row < S) {
+            *reinterpret_cast<uint32_t*>(dkb + static_cast<int64_t>(kb_row) * rp + col) = pack_bf16x2(dk[j][2], dk[j][3]);
+            *reinterpret_cast<uint32_t*>(dkb + static_cast<int64_t>(kb_row) * rp + d + col) = pack_bf16x2(dv[j][2], dv[j][3]);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // cross entropy: loss_rows[r] = lse(logits[r]) - logits[r][target[r]];  dlogits[r] = (softmax - onehot) * scale
 // ------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) cross_entropy_kernel(const float* __restrict__ logits, int64_t ld, const int32_t* __restrict__ target,
@@ -516,6 +795,19 @@ extern "C" int vb_colsum(const void* x, int dtype, int64_t R, int N, int64_t ldx
     if (dtype == VB_F32) colsum_kernel<float><<<blocks, 256, 0, st>>>(static_cast<const float*>(x), ldx, R, N, out, accumulate, scale);
     else if (dtype == VB_BF16) colsum_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), ldx, R, N, out, accumulate, scale);
     else VB_REQUIRE(false, VB_ERR_BAD_ARG, "vb_colsum: bad dtype");
+    VB_LAUNCH_CHECK();
+    return VB_OK;
+}
+
+/* First level of a two-level column sum: part[y][n] = sum over row block y (row_blocks of them) of x[r][n]; reduce part
+ * with vb_colsum.  Fills the GPU when R is long and N narrow (bias / LayerNorm gradients over B*S rows). */
+extern "C" int vb_colsum_blocks(const void* x, int dtype, int64_t R, int N, int64_t ldx, float* part, int row_blocks, void* stream) {
+    VB_REQUIRE(x && part && R >= 0 && N >= 1 && row_blocks >= 1 && row_blocks <= 65535, VB_ERR_BAD_ARG, "vb_colsum_blocks: bad args");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    dim3 grid((N + 31) / 32, row_blocks);
+    if (dtype == VB_F32) colsum_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(x), ldx, R, N, part, 0, 1.0f);
+    else if (dtype == VB_BF16) colsum_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), ldx, R, N, part, 0, 1.0f);
+    else VB_REQUIRE(false, VB_ERR_BAD_ARG, "vb_colsum_blocks: bad dtype");
     VB_LAUNCH_CHECK();
     return VB_OK;
 }
@@ -607,8 +899,19 @@ extern "C" int vb_attention_bwd(const void* qkv, const void* o, const void* dO, 
         attn_bwd_dkv_kernel<T><<<grid, 256, smem2, st>>>(static_cast<const T*>(qkv), static_cast<const T*>(dO),            \
             static_cast<T*>(dqkv), lse, delta, S, H, mask_mode, x_lens, kv_lens, scale);                                   \
     }
+    static const bool force_simt = (getenv("VALLE_B200_ATTN_BWD_SIMT") != nullptr && getenv("VALLE_B200_ATTN_BWD_SIMT")[0] == '1');
     if (dtype == VB_F32) ABW(float)
-    else if (dtype == VB_BF16) ABW(__nv_bfloat16)
+    else if (dtype == VB_BF16 && force_simt) ABW(__nv_bfloat16)
+    else if (dtype == VB_BF16) {
+        VB_REQUIRE((reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(o) & 15) == 0 &&
+                   (reinterpret_cast<uintptr_t>(dO) & 15) == 0 && (reinterpret_cast<uintptr_t>(dqkv) & 3) == 0,
+                   VB_ERR_BAD_ARG, "vb_attention_bwd: bf16 operands must be 16-byte aligned");
+        const __nv_bfloat16* q16 = static_cast<const __nv_bfloat16*>(qkv);
+        attn_bwd_dq_mma_kernel<<<grid, 128, 0, st>>>(q16, static_cast<const __nv_bfloat16*>(o), static_cast<const __nv_bfloat16*>(dO),
+                                                     static_cast<__nv_bfloat16*>(dqkv), lse, delta, S, H, mask_mode, x_lens, kv_lens, scale);
+        attn_bwd_dkv_mma_kernel<<<grid, 128, 0, st>>>(q16, static_cast<const __nv_bfloat16*>(dO), static_cast<__nv_bfloat16*>(dqkv), lse,
+                                                      delta, S, H, mask_mode, x_lens, kv_lens, scale);
+    }
     else VB_REQUIRE(false, VB_ERR_BAD_ARG, "vb_attention_bwd: bad dtype");
 #undef ABW
     VB_LAUNCH_CHECK();
