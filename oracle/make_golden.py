@@ -264,6 +264,29 @@ def golden_ar_grads(valle, tmp):
     np.savez_compressed(os.path.join(OUT, 'ar_tiny_grads.npz'), **out)
 
 
+def golden_collate(valle, tmp):
+    """The reference's own ``ValleARCollate`` on three ragged items (collate.py:19-46), and the proof that its
+    ``ValleNARCollate`` raises on ragged lengths (SURVEY A-13) -- the repaired layout is pinned by construction instead."""
+    from valle import collate as C
+    oc = synth.tiny_config('LayerNorm')
+    cfg = _ref_config(valle, oc, tmp)
+    g = torch.Generator().manual_seed(41)
+    items = []
+    for T_, Tx_ in ((11, 4), (7, 5), (9, 3)):
+        items.append({'codes': torch.randint(0, 1024, (8, T_), generator=g), 'tokens': torch.randint(1, 256, (Tx_,), generator=g)})
+    out = {}
+    for i, it in enumerate(items):
+        out[f'item{i}_codes'], out[f'item{i}_tokens'] = _np(it['codes']), _np(it['tokens'])
+    for k, v in C.ValleARCollate(cfg)(items).items():
+        out['ar_' + k] = _np(v)
+    try:
+        C.ValleNARCollate(cfg)(items)
+        out['nar_upstream_raises'] = np.array(0)
+    except Exception:
+        out['nar_upstream_raises'] = np.array(1)
+    np.savez_compressed(os.path.join(OUT, 'collate.npz'), **out)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     tmp = tempfile.mkdtemp(prefix='valle_golden_')
@@ -277,6 +300,7 @@ def main():
         golden_ar(valle, tmp)
         golden_nar(valle, tmp)
         golden_ar_grads(valle, tmp)
+        golden_collate(valle, tmp)
     finally:
         os.chdir(cwd)
     for f in sorted(os.listdir(OUT)):

@@ -242,3 +242,21 @@ def test_ar_training_gradients_vs_reference_golden(tmp_path):
         scale = ref_stats[2] + 1e-12
         assert abs(float(gr.norm()) - ref_stats[0]) / (ref_stats[0] + 1e-12) < 1e-4, name
         assert np.abs(gr[:16].numpy() - ref_head).max() / scale < 1e-4, name
+
+
+def test_collated_batch_feeds_training_step(tmp_path):
+    """N2 -> a13: the reference's own collated batch (tests/golden/collate.npz, produced by the executed upstream
+    ValleARCollate) goes through ValleAR.training_step; loss equals the oracle's teacher-forced loss on the same dict."""
+    import os
+    import numpy as np
+    from valle.collate import ValleARCollate
+    valle2_b200.set_precision('fp32')
+    oc = synth.tiny_config('LayerNorm')
+    z = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'collate.npz'))
+    items = [{'codes': torch.from_numpy(z[f'item{i}_codes']), 'tokens': torch.from_numpy(z[f'item{i}_tokens'])} for i in range(3)]
+    batch = ValleARCollate(oc)(items)
+    model, sd = build('ValleAR', oc, tmp_path, 3)
+    model.train()
+    ref = vo.ar_teacher_forced(sd, oc, batch['tokens'], batch['codes'], batch['tokens_lens'], batch['codes_lens'], batch['target'])[1]
+    loss = model.training_step(batch)
+    assert abs(loss.item() - ref.item()) < 1e-4

@@ -95,3 +95,57 @@ def test_generate_asserts_like_reference(tmp_path):
         model.generate(torch.zeros(2, 3, dtype=torch.long), torch.zeros(4, 8, dtype=torch.long))
     with pytest.raises(AssertionError):
         model.generate(torch.zeros(3, dtype=torch.long), torch.zeros(4, dtype=torch.long))
+
+
+# ---- batch-dict contract: valle.collate against the executed reference (tests/golden/collate.npz) --------
+
+def _collate_items():
+    import numpy as np, os
+    z = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'collate.npz'))
+    items = [{'codes': torch.from_numpy(z[f'item{i}_codes']), 'tokens': torch.from_numpy(z[f'item{i}_tokens'])} for i in range(3)]
+    return z, items
+
+
+def test_ar_collate_matches_reference_golden():
+    from valle.collate import ValleARCollate, get_collate
+    assert get_collate('ValleAR') is ValleARCollate
+    z, items = _collate_items()
+    out = ValleARCollate(synth.tiny_config('LayerNorm'))(items)
+    assert set(out) == {'codes', 'codes_lens', 'target', 'tokens', 'tokens_lens'}
+    for k, v in out.items():
+        ref = torch.from_numpy(z['ar_' + k])
+        assert v.dtype == ref.dtype and torch.equal(v, ref), k
+    # the shift by one: codes = BOS + c, target = c + EOS (collate.py:27-29)
+    cfg = synth.tiny_config('LayerNorm')
+    assert int(out['codes'][0, 0]) == cfg.bos_token and int(out['target'][0, 11]) == cfg.eos_token
+    assert torch.equal(out['codes'][0, 1:12], out['target'][0, :11])
+
+
+def test_nar_collate_repaired_layout():
+    """Upstream ValleNARCollate raises on ragged (Q, T) items (SURVEY A-13, recorded in the golden file); the repaired
+    collate yields the (B, T_max, Q) layout that ValleNAR.training_step indexes (valle_nar.py:81, :177-186)."""
+    from valle.collate import ValleNARCollate, get_collate
+    assert get_collate('ValleNAR') is ValleNARCollate
+    z, items = _collate_items()
+    assert int(z['nar_upstream_raises']) == 1
+    out = ValleNARCollate(synth.tiny_config('AdaptiveLayerNorm'))(items)
+    assert out['codes'].shape == (3, 11, 8) and out['codes_lens'].tolist() == [11, 7, 9]
+    for i, it in enumerate(items):
+        T = it['codes'].shape[1]
+        assert torch.equal(out['codes'][i, :T], it['codes'].T) and int(out['codes'][i, T:].abs().sum()) == 0
+    assert out['tokens'].shape == (3, 5) and out['tokens_lens'].tolist() == [4, 5, 3]
+
+
+def test_collate_asserts_more_frames_than_phonemes():
+    from valle.collate import ValleARCollate
+    items = [{'codes': torch.zeros(8, 3, dtype=torch.int64), 'tokens': torch.ones(6, dtype=torch.int64)}]
+    with pytest.raises(AssertionError, match='Codes length must be greater'):
+        ValleARCollate(synth.tiny_config('LayerNorm'))(items)
+
+
+def test_collate_empty_and_single():
+    from valle.collate import collate_list
+    x, lens = collate_list([torch.arange(4)])
+    assert x.shape == (1, 4) and lens.tolist() == [4]
+    x, lens = collate_list([])
+    assert x.numel() == 0 and lens.numel() == 0

@@ -4,6 +4,7 @@ unchanged.  See INTEGRATION.md."""
 import sys
 
 import valle2_b200
+import valle2_b200.collate
 import valle2_b200.config
 import valle2_b200.models
 import valle2_b200.models.modules
@@ -12,6 +13,7 @@ import valle2_b200.models.valle_ar
 import valle2_b200.models.valle_nar
 
 _alias = {
+    'valle.collate': valle2_b200.collate,
     'valle.config': valle2_b200.config,
     'valle.models': valle2_b200.models,
     'valle.models.modules': valle2_b200.models.modules,
@@ -20,5 +22,6 @@ _alias = {
     'valle.models.valle_nar': valle2_b200.models.valle_nar,
 }
 sys.modules.update(_alias)
+collate = valle2_b200.collate
 config = valle2_b200.config
 models = valle2_b200.models
