@@ -175,7 +175,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                                f'(BASELINE configs[1]); text {TX}, prompt {P}, ctx {ctx0}->{ctx0 + K} (mean {mean_ctx:.1f})',
                    'batch_per_gpu': B, 'global_batch': B * world, 'parallelism': f'dp{world} (utterance sharding, '
                    'one all-gather of the codes at the end)', 'kv_page': 64,
-                   'sub_batches': n_sub, 'decode_gemm': 'fused' if eng._fused_ok(st['subs'][0]) else ('chain' if eng._chain_ok(st['subs'][0]) else 'split-k'), 'launches_per_step': launches_per_step,
+                   'sub_batches': n_sub, 'decode_gemm': 'lean (rows kernels, LN on load, 5 per layer)' if eng._lean_ok(st['subs'][0]) else ('mix qkv,o,f1,f2,lg=' + ''.join(eng._mix(st['subs'][0]).values())) if eng._rows_ok(st['subs'][0]) else 'fused' if eng._fused_ok(st['subs'][0]) else ('chain' if eng._chain_ok(st['subs'][0]) else 'split-k'), 'launches_per_step': launches_per_step,
                    'l2_policy': 'inputs larger than L2: every step streams 304 MB of weights + %.0f MB of KV' %
                                 ((step_bytes - ar_step_bytes(0, 0)) / 1e6),
                    'step_hbm_bytes': step_bytes, 'step_hbm_frac_of_measured_peak':
@@ -194,7 +194,16 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         reps = 5
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
         rows = eng._fused_ok(sb)
-        qkv_src, qkv_np, qkv_ps = (sb['qkv32'], 1, 0) if rows else (sb['p_qkv'], sb['ns']['qkv'], Bs * 3 * d)
+        mma_rows = eng._rows_ok(sb)
+        lean = eng._lean_ok(sb)
+        if lean:
+            qkv_src, qkv_np, qkv_ps = sb['r_qkv'], 1, 0
+        elif mma_rows and eng._mix(sb)['qkv'] == 'r':
+            qkv_src, qkv_np, qkv_ps = sb['r_qkv'], sb['nr']['qkv'], Bs * 3 * d
+        elif mma_rows:
+            qkv_src, qkv_np, qkv_ps = sb['p_qkv'], sb['ns']['qkv'], Bs * 3 * d
+        else:
+            qkv_src, qkv_np, qkv_ps = (sb['qkv32'], 1, 0) if rows else (sb['p_qkv'], sb['ns']['qkv'], Bs * 3 * d)
 
         def attn_all_layers():
             for li in range(12):                             # 12 layers x B x ctx KV = > L2, no re-use between launches
@@ -237,7 +246,33 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         # weight-streaming GEMMs of one step, same method
         def gemms_all_layers():
             for L in eng.weights.layers:
-                if rows:
+                if lean:
+                    g1, b1, _ = L['norm1']
+                    g2, b2, _ = L['norm2']
+                    ops.linear_decode_rows_ln(sb['x'], L['wqkv'], sb['r_qkv'][0], gamma=g1[0], beta=b1[0])
+                    ops.linear_decode_rows(sb['o'], L['wo'], sb['x'], bias=L['bo'], residual=True)
+                    ops.linear_decode_rows_ln(sb['x'], L['w1'], sb['f'], gamma=g2[0], beta=b2[0], bias=L['b1'], gelu=True)
+                    ops.linear_decode_rows(sb['f'], L['w2'], sb['x'], bias=L['b2'], residual=True, want_split=0)
+                elif mma_rows:
+                    mix = eng._mix(sb)
+                    if mix['qkv'] == 'r':
+                        ops.linear_decode_rows(sb['h'], L['wqkv'], sb['r_qkv'] if sb['nr']['qkv'] > 1 else sb['r_qkv'][0],
+                                               want_split=eng.rows_qkv_split)
+                    else:
+                        ops.linear_decode(sb['h'], L['wqkv'], sb['p_qkv'], Bs * 3 * d, 32)
+                    if mix['o'] == 'r':
+                        ops.linear_decode_rows(sb['o'], L['wo'], sb['x'], bias=L['bo'], residual=True)
+                    else:
+                        ops.linear_decode(sb['o'], L['wo'], sb['p_o'], Bs * d, 32)
+                    if mix['f1'] == 'r':
+                        ops.linear_decode_rows(sb['h'], L['w1'], sb['f'], bias=L['b1'], gelu=True)
+                    else:
+                        ops.linear_decode(sb['h'], L['w1'], sb['p_f1'], Bs * 4096, 32)
+                    if mix['f2'] == 'r':
+                        ops.linear_decode_rows(sb['f'], L['w2'], sb['r_f2'])
+                    else:
+                        ops.linear_decode(sb['f'], L['w2'], sb['p_f2'], Bs * d, 32)
+                elif rows:
                     cl = eng.fused_cluster
                     g1, b1, _ = L['norm1']
                     g2, b2, _ = L['norm2']
@@ -256,7 +291,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         wbytes = 2 * 12 * (3 * d * d + d * d + 2 * d * 4096)
         result['gemm_decode'] = {'ms_per_step': gemm_ms, 'achieved_gbs': wbytes / (gemm_ms * 1e-3) / 1e9,
                                  'frac_of_hbm_peak': wbytes / (gemm_ms * 1e-3) / 1e9 / pk['hbm_gbs'], 'launches': 48,
-                                 'kernel': 'gemm_decode_fused_kernel (cluster split-K through DSMEM, LN on load, fused epilogues)' if rows else 'gemm_tc_kernel<swap-AB split-K>'}
+                                 'kernel': 'linear_decode_rows_kernel (mma.sync, full K per CTA, LN on load, fused epilogues)' if lean else 'linear_decode_rows_kernel (mma.sync, full K per CTA, fused epilogues) / gemm_tc_kernel<swap-AB split-K> per config.decode_gemm' if mma_rows else 'gemm_decode_fused_kernel (cluster split-K through DSMEM, LN on load, fused epilogues)' if rows else 'gemm_tc_kernel<swap-AB split-K>'}
 
     # ---- end-to-end through the public API from pinned host tensors --------------------------------
     barrier()

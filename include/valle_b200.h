@@ -106,6 +106,37 @@ enum { VB_FLAG_LATE_TRIGGER = 1, VB_FLAG_PREFETCH_KV = 2, VB_FLAG_ATTN_SIMT = 4 
 int vb_linear_decode(const void* x, int64_t ldx, const void* w, int64_t ldw, float* part, int64_t part_stride,
                      int64_t M, int64_t N, int64_t K, int max_split, int flags, int* n_split_out, void* stream);
 
+/* Decode-shape linear layer in "rows" form (csrc/gemm_decode_mma.cu), M <= 32, K % 256 == 0, x and w bf16:
+ *   y[M][N] = epilogue(x[M][K] . w[N][K]^T)   -- the whole K of an output element stays inside one CTA when K <= 1024, so
+ *   bias / erf-GELU / the residual add run in the epilogue and no reduce kernel follows (modules.py:146, :171+:274,
+ *   :220-221, :278; valle_ar.py:158).  Weights stream HBM -> registers in mma.sync fragment order before the kernel waits
+ *   on its predecessor (PDL); activations are bulk-copied into shared memory; eight warps split K and are summed in warp
+ *   order (deterministic).
+ *   epilogue VB_EPI_NONE / VB_EPI_BIAS / VB_EPI_BIAS_GELU: y is VB_F32 or VB_BF16 [M][N] (pitch ldy);
+ *   VB_EPI_BIAS_RESIDUAL: y (fp32) += x.w^T + bias in place (the residual stream).
+ *   K > 1024 (or want_split > 1): split-K over vb_linear_decode_rows_splits(M, K, want_split) CTAs; then epilogue must be
+ *   VB_EPI_NONE and y receives fp32 slices [split][M][N] (split_stride elements apart) for vb_residual_layernorm /
+ *   vb_attn_decode_paged / vb_sample to add in index order.  want_split == 0: keep the whole K (<= 4096) in one CTA
+ *   whenever the M activation rows fit in shared memory (K = 4096: M <= 8), so that K > 1024 gets an epilogue too.
+ *   flags: VB_FLAG_LATE_TRIGGER as for vb_linear_decode. */
+int vb_linear_decode_rows_splits(int M, int64_t K, int want_split);   /* pure query; 0 = K unsupported */
+int vb_linear_decode_rows(const void* x, int64_t ldx, const void* w, int64_t ldw, const float* bias, void* y, int y_dtype,
+                          int64_t ldy, int64_t split_stride, int M, int64_t N, int64_t K, int epilogue, int want_split,
+                          int flags, int* n_split_out, void* stream);
+
+/* Same kernel with LayerNorm ON LOAD (M <= 8, K in {256, 512, 1024}): x is the fp32 residual stream [M][K]; every CTA
+ * normalises the rows itself, y = epilogue(LayerNorm(x; gamma, beta, eps) . w^T), so the separate LayerNorm kernel of
+ * modules.py:271 / :276 (norm1 / norm2) and its dependent launch disappear; gamma = beta = NULL: plain bf16 cast (the AR
+ * logits projection, valle_ar.py:158 -- no final norm).  One slice only (no split-K). */
+int vb_linear_decode_rows_ln(const float* x, int64_t ldx, const float* gamma, const float* beta, float eps, const void* w,
+                             int64_t ldw, const float* bias, void* y, int y_dtype, int64_t ldy, int M, int64_t N, int64_t K,
+                             int epilogue, int flags, void* stream);
+
+/* Profiling aid: subsequent vb_linear_decode_rows launches write per-CTA stamps [cta][16]: events {kernel start, weights
+ * requested, dependency resolved, activations landed, MMAs done, k-slices summed, stores issued, -} as %globaltimer, then
+ * the same events as SM cycle counters (uint64, device memory, grid * 16 entries); NULL switches it off. */
+int vb_linear_decode_rows_set_debug(void* buf);
+
 /* Profiling aid: subsequent vb_linear_decode launches write %globaltimer stamps [cta][8] = {prologue done, weights requested,
  * dependency resolved, first k-block landed, MMAs issued, accumulator complete, epilogue stores issued, -} followed by the
  * same eight events as SM cycle counters (uint64, device memory, #SM*16 entries); NULL switches it off. */

@@ -156,6 +156,108 @@ def test_linear_decode(ops, M, N, K):
     assert rel_err(y, x.double() @ w.double().t()) < 1e-4
 
 
+@pytest.mark.parametrize('M', [1, 5, 16, 17, 32])
+@pytest.mark.parametrize('N,K,epi,ydt,split', [
+    (3072, 1024, 'none', torch.float32, 1), (3072, 1024, 'none', torch.float32, 2), (1024, 1024, 'residual', torch.float32, 1),
+    (4096, 1024, 'gelu', torch.bfloat16, 1), (1024, 4096, 'none', torch.float32, 1), (1025, 1024, 'none', torch.float32, 1),
+    (768, 256, 'none', torch.float32, 1), (256, 256, 'residual', torch.float32, 1), (1024, 256, 'gelu', torch.bfloat16, 1),
+    (256, 1024, 'bias', torch.bfloat16, 1), (1025, 256, 'none', torch.float32, 1), (520, 512, 'bias', torch.float32, 1),
+    (8192, 1024, 'gelu', torch.bfloat16, 1), (104, 768, 'none', torch.float32, 1)])
+def test_linear_decode_rows(ops, M, N, K, epi, ydt, split):
+    """csrc/gemm_decode_mma.cu against a float64 matmul of the same bf16 operands: every epilogue, ragged N (1025 = the AR
+    logits), split-K slices (K = 4096 -> 4 slices; want_split = 2), M across both m16 tile counts; late PDL trigger on odd M."""
+    torch.manual_seed(6)
+    x = torch.randn(M, K, device='cuda').bfloat16()
+    w = (torch.randn(N, K, device='cuda') / math.sqrt(K)).bfloat16()
+    bias = torch.randn(N, device='cuda') if epi != 'none' else None
+    ref = x.double() @ w.double().t()
+    ns = ops.linear_decode_rows_splits(K, split, M)
+    assert ns == {768: 3}.get(K, max(split, K // 1024, 1))
+    if ns > 1:
+        y = torch.full((ns, M, N), float('nan'), device='cuda')
+        got_ns = ops.linear_decode_rows(x, w, y, want_split=split, flags=(M % 2))
+        assert got_ns == ns
+        torch.cuda.synchronize()
+        out = y.sum(0)
+    else:
+        res = torch.randn(M, N, device='cuda')
+        y = res.clone() if epi == 'residual' else torch.full((M, N), float('nan'), device='cuda').to(ydt)
+        ops.linear_decode_rows(x, w, y, bias=bias, gelu=(epi == 'gelu'), residual=(epi == 'residual'), flags=(M % 2))
+        torch.cuda.synchronize()
+        out = y
+        if epi != 'none':
+            ref = ref + bias.double()
+        if epi == 'gelu':
+            ref = torch.nn.functional.gelu(ref)
+        if epi == 'residual':
+            ref = ref + res.double()
+    assert not torch.isnan(out.float()).any()
+    assert rel_err(out, ref) < (1e-4 if ydt == torch.float32 else 6e-3)
+
+
+@pytest.mark.parametrize('M', [1, 3, 8])
+@pytest.mark.parametrize('N,K,epi,ydt,norm', [
+    (3072, 1024, 'none', torch.float32, True), (4096, 1024, 'gelu', torch.bfloat16, True), (1025, 1024, 'none', torch.float32, False),
+    (768, 256, 'none', torch.float32, True), (1024, 256, 'gelu', torch.bfloat16, True), (1025, 256, 'none', torch.float32, False),
+    (512, 512, 'bias', torch.float32, True), (256, 1024, 'residual', torch.float32, True)])
+def test_linear_decode_rows_layernorm_on_load(ops, M, N, K, epi, ydt, norm):
+    """vb_linear_decode_rows_ln: y = epilogue(LN(x) @ w.T) against the oracle's layer_norm (modules.py:271/276) followed by a
+    float64 matmul of the bf16-rounded rows; rows with a large common offset check the two-level (Chan) variance."""
+    torch.manual_seed(8)
+    x = torch.randn(M, K, device='cuda') * 2 + 3.0
+    x[0] += 50.0
+    w = (torch.randn(N, K, device='cuda') / math.sqrt(K)).bfloat16()
+    gamma, beta = (torch.randn(K, device='cuda'), torch.randn(K, device='cuda')) if norm else (None, None)
+    bias = torch.randn(N, device='cuda') if epi != 'none' else None
+    hn = vo.layer_norm(x.cpu(), gamma.cpu(), beta.cpu()) if norm else x.cpu()
+    ref = hn.bfloat16().double() @ w.cpu().double().t()
+    res = torch.randn(M, N, device='cuda')
+    y = res.clone() if epi == 'residual' else torch.full((M, N), float('nan'), device='cuda').to(ydt)
+    ops.linear_decode_rows_ln(x, w, y, gamma=gamma, beta=beta, bias=bias, gelu=(epi == 'gelu'), residual=(epi == 'residual'),
+                              flags=(M % 2))
+    torch.cuda.synchronize()
+    if epi != 'none':
+        ref = ref + bias.cpu().double()
+    if epi == 'gelu':
+        ref = torch.nn.functional.gelu(ref)
+    if epi == 'residual':
+        ref = ref + res.cpu().double()
+    assert not torch.isnan(y.float()).any()
+    # LN output is rounded to bf16 before the MMA on both sides; a 1-ulp flip of a few elements is the remaining noise
+    assert rel_err(y.float().cpu(), ref) < (2e-3 if ydt == torch.float32 else 6e-3)
+
+
+@pytest.mark.parametrize('M', [1, 8])
+def test_linear_decode_rows_whole_k_4096(ops, M):
+    """want_split=0: FFN2 (K = 4096) inside one CTA with the residual epilogue (modules.py:278), small batches only."""
+    torch.manual_seed(9)
+    N, K = 1024, 4096
+    assert ops.linear_decode_rows_splits(K, 0, M) == 1 and ops.linear_decode_rows_splits(K, 0, 32) == 4
+    x = torch.randn(M, K, device='cuda').bfloat16()
+    w = (torch.randn(N, K, device='cuda') / math.sqrt(K)).bfloat16()
+    bias, res = torch.randn(N, device='cuda'), torch.randn(M, N, device='cuda')
+    y = res.clone()
+    assert ops.linear_decode_rows(x, w, y, bias=bias, residual=True, want_split=0) == 1
+    torch.cuda.synchronize()
+    assert rel_err(y, x.double() @ w.double().t() + bias.double() + res.double()) < 1e-4
+
+
+def test_linear_decode_rows_is_deterministic_and_rejects_bad_shapes(ops):
+    torch.manual_seed(7)
+    x = torch.randn(32, 1024, device='cuda').bfloat16()
+    w = (torch.randn(3072, 1024, device='cuda') / 32).bfloat16()
+    a, b = torch.empty(32, 3072, device='cuda'), torch.empty(32, 3072, device='cuda')
+    ops.linear_decode_rows(x, w, a)
+    ops.linear_decode_rows(x, w, b)
+    torch.cuda.synchronize()
+    assert torch.equal(a, b)
+    with pytest.raises(RuntimeError, match='M = 33'):
+        ops.linear_decode_rows(torch.zeros(33, 1024, device='cuda').bfloat16(), w, torch.empty(33, 3072, device='cuda'))
+    assert ops.linear_decode_rows_splits(1000) == 0
+    with pytest.raises(RuntimeError, match='M = 9'):
+        ops.linear_decode_rows_ln(torch.zeros(9, 1024, device='cuda'), w, torch.empty(9, 3072, device='cuda'))
+
+
 @pytest.mark.parametrize('B', [1, 7, 16, 32, 33, 64])
 @pytest.mark.parametrize('d,F', [(1024, 4096), (256, 1024)])
 def test_decode_chain_matches_separate_kernels(ops, B, d, F):

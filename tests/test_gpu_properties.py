@@ -73,16 +73,30 @@ def test_sub_batches_and_chain_kernel_do_not_change_tokens(tmp_path):
     cod = torch.cat([torch.full((B, 1), oc.bos_token), torch.randint(0, 1024, (B, 40), generator=g)], 1).cuda()
     eng = model._engine()
     results = {}
+    gemm_form = eng.decode_gemm
     try:
+        # one GEMM form for every sub-batch size ('auto' would move sub-batches of <= 8 rows to the lean rows kernels,
+        # whose fp32 summation order differs)
+        eng.decode_gemm = 'splitk'
         for chain, n_sub in ((False, 1), (False, 2), (False, 3), (True, 1)):
             if True:
                 eng.use_chain, eng.n_sub_override, eng.n_tsplit_override = chain, n_sub, 2
                 out, lp, n = eng.generate(tok, cod, max_new=24, top_k=50, top_p=1.0, temperature=1.0, seed=3)
                 assert len(eng._state['subs']) == n_sub
                 results[(chain, n_sub)] = (out.clone(), lp.clone(), n)
+        # the other GEMM forms on the same batch: rows kernels (any batch <= 32) and the lean path (sub-batches of 6)
+        eng.use_chain, eng.n_tsplit_override = False, 2
+        for form, n_sub in (('rows', 1), ('lean', 3)):
+            eng.decode_gemm, eng.n_sub_override = form, n_sub
+            out, lp, n = eng.generate(tok, cod, max_new=24, top_k=50, top_p=1.0, temperature=1.0, seed=3)
+            assert (eng._lean_ok if form == 'lean' else eng._rows_ok)(eng._state['subs'][0])
+            results[form] = (out.clone(), lp.clone(), n)
     finally:
-        eng.use_chain, eng.n_sub_override, eng.n_tsplit_override = True, 0, 0
+        eng.use_chain, eng.n_sub_override, eng.n_tsplit_override, eng.decode_gemm = False, 0, 0, gemm_form
     ref = results[(False, 1)]
+    for form in ('rows', 'lean'):       # different fp32 summation order: a sampled row may flip on a near-tie of the CDF
+        same = (results[form][0][:, :2] == ref[0][:, :2]).float().mean().item()
+        assert same >= 0.85, (form, same)
     for n_sub in (2, 3):
         got = results[(False, n_sub)]
         assert got[2] == ref[2]

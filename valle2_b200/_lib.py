@@ -28,6 +28,9 @@ SIGNATURES = {
     'vb_linear': (_i, [_p, _i, _i64, _p, _i, _i64, _p, _p, _i64, _p, _i, _i64, _i64, _i64, _i64, _i, _p]),
     'vb_linear_decode_splits': (_i, [_i64, _i64, _i]),
     'vb_linear_decode': (_i, [_p, _i64, _p, _i64, _p, _i64, _i64, _i64, _i64, _i, _i, _p, _p]),
+    'vb_linear_decode_rows_splits': (_i, [_i, _i64, _i]),
+    'vb_linear_decode_rows_ln': (_i, [_p, _i64, _p, _p, _f, _p, _i64, _p, _p, _i, _i64, _i, _i64, _i64, _i, _i, _p]),
+    'vb_linear_decode_rows': (_i, [_p, _i64, _p, _i64, _p, _p, _i, _i64, _i64, _i, _i64, _i64, _i, _i, _i, _p, _p]),
     'vb_linear_decode_fused_cluster': (_i, [_i, _i]),
     'vb_linear_decode_fused': (_i, [_p, _i, _i64, _p, _p, _f, _p, _i64, _p, _p, _i, _i64, _i, _i, _i, _i, _i, _i, _p]),
     'vb_kv_prefetch_l2': (_i, [_p, _i, _p, _i, _p, _i, _i, _i, _i, _i, _p]),
@@ -44,6 +47,7 @@ SIGNATURES = {
     'vb_decode_chain': (_i, [_p, _i, _i, _p, _p]),
     'vb_decode_chain_set_debug': (_i, [_p]),
     'vb_linear_decode_set_debug': (_i, [_p]),
+    'vb_linear_decode_rows_set_debug': (_i, [_p]),
     'vb_attention': (_i, [_p, _p, _p, _i, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _p, _i, _i64, _i64,
                           _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _i64, _i64, _i64, _p]),
     'vb_attention_prefill_tc': (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _p]),

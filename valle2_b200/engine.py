@@ -150,6 +150,11 @@ class ARDecoder:
         self.fused_cluster = {'qkv': 0, 'o': 0, 'f1': 0, 'f2': 0, 'lg': 0}
         for k, v in [kv.split('=') for kv in os.environ.get('VALLE_B200_FUSED_CLUSTER', '').split(';') if kv]:
             self.fused_cluster[k] = int(v)
+        # decode GEMM form: 'rows' = full-K mma.sync kernel with fused epilogues (csrc/gemm_decode_mma.cu, sub-batches of
+        # <= 32 sequences), 'splitk' = tcgen05 swap-AB slices + reduce kernels (csrc/gemm_tc.cu), 'auto' = by batch size,
+        # or five letters [rs] for qkv, out-proj, FFN1, FFN2, logits (see _mix)
+        self.decode_gemm = os.environ.get('VALLE_B200_DECODE_GEMM', 'auto')
+        self.rows_qkv_split = int(os.environ.get('VALLE_B200_ROWS_QKV_SPLIT', '1'))
         self.n_sub_override = int(os.environ.get('VALLE_B200_SUBBATCH', '0'))
         self.attn_ctas = int(os.environ.get('VALLE_B200_ATTN_CTAS', '0'))
         self.n_tsplit_override = 0             # tests: pin the flash-decoding split
@@ -171,6 +176,36 @@ class ARDecoder:
         # Concurrent chain kernels (one per sub-batch) spin on grid barriers and cannot share an SM: two of them could
         # each hold part of the GPU and wait for the rest forever, so the chain runs only when the batch is not split.
         return (self.precision == 'bf16' and self.use_chain and sub['B'] <= 64 and len(self._state['subs']) == 1)
+
+    def _mix(self, sub: dict) -> dict:
+        """Form of each decode GEMM for this sub-batch: 'r' rows (mma.sync, full K per CTA), 's' tcgen05 split-K slices.
+        In the rows form every CTA reads the whole (B, K) activation matrix from L2 -- 0.3 us at B = 1, 1.4 us at B = 32
+        (tools/rows_timeline.py) -- so 'auto' uses it (as the lean path) up to 8 sequences and slices above; every mix
+        was measured with tools/layer_chain.py and tools/ab_mix.sh."""
+        dg = self.decode_gemm
+        if dg in ('auto', 'lean'):      # small batches take the lean path (_lean_ok) before this is consulted
+            dg = 'splitk'
+        if dg == 'rows':
+            dg = 'rrrrr'
+        elif dg == 'splitk':
+            dg = 'sssss'
+        assert len(dg) == 5 and set(dg) <= {'r', 's'}, 'VALLE_B200_DECODE_GEMM: auto | rows | splitk | 5 x [rs] (qkv,o,f1,f2,logits)'
+        return dict(zip(('qkv', 'o', 'f1', 'f2', 'lg'), dg))
+
+    def _lean_ok(self, sub: dict) -> bool:
+        """Five kernels per layer (small batch): LayerNorm on load inside the QKV / FFN1 GEMMs, residual adds and GELU in
+        the epilogues, FFN2 with its whole K = F in one CTA (csrc/gemm_decode_mma.cu).  Every CTA reads the whole fp32
+        residual matrix, which is what limits it to <= 8 sequences."""
+        dg = self.decode_gemm
+        if dg not in ('auto', 'lean') or self.precision != 'bf16' or self.use_fused or self.use_chain:
+            return False
+        return (sub['B'] <= 8 and self.d in (256, 512, 1024) and self.weights.F % 256 == 0
+                and ops.linear_decode_rows_splits(self.weights.F, 0, sub['B']) == 1)
+
+    def _rows_ok(self, sub: dict) -> bool:
+        """The mixed decode path (any GEMM in rows form) applies to this sub-batch."""
+        return (self.precision == 'bf16' and not self.use_fused and not self.use_chain and 'nr' in sub
+                and 'r' in self._mix(sub).values())
 
     def _fused_ok(self, sub: dict) -> bool:
         return self.precision == 'bf16' and self.use_fused and sub['B'] <= 64 and self.d % 64 == 0
@@ -200,6 +235,11 @@ class ARDecoder:
             sub['p_lg'] = torch.zeros(ns['lg'], B, V, device=dev, dtype=torch.float32)
             sub['gbar'] = torch.zeros(64, device=dev, dtype=torch.int32)     # grid-barrier counter of the chain kernel
             sub['qkv32'] = torch.zeros(B, 3 * d, device=dev, dtype=torch.float32)
+            if self.d % 256 == 0 and F % 256 == 0 and B <= 32:
+                nr = {'qkv': ops.linear_decode_rows_splits(d, self.rows_qkv_split, B), 'f2': ops.linear_decode_rows_splits(F, 1, B)}
+                sub['nr'] = nr
+                sub['r_qkv'] = torch.zeros(nr['qkv'], B, 3 * d, device=dev, dtype=torch.float32)
+                sub['r_f2'] = torch.zeros(nr['f2'], B, d, device=dev, dtype=torch.float32)
             sub['lg'] = torch.zeros(B, V, device=dev, dtype=torch.float32)
         else:
             sub['h'] = torch.zeros(B, d, device=dev, dtype=torch.float32)
@@ -264,7 +304,19 @@ class ARDecoder:
                             logits_done: bool = False):
         """x_rows (B,d) fp32 final hidden rows of the sub-batch -> logits -> sample -> bookkeeping."""
         B, V = sub['B'], self.V
-        if self._fused_ok(sub):
+        if self._lean_ok(sub):
+            ops.linear_decode_rows_ln(x_rows, self.wproj, sub['lg'])                  # plain cast on load (no final norm, K-2)
+            lg, n_part, pstride = sub['lg'], 1, 0
+        elif self._rows_ok(sub):
+            if not logits_done:
+                ops.residual_layernorm(x_rows, None, None, sub['h'])                  # cast to bf16 (no final norm, K-2)
+            if self._mix(sub)['lg'] == 'r':
+                ops.linear_decode_rows(sub['h'], self.wproj, sub['lg'])
+                lg, n_part, pstride = sub['lg'], 1, 0
+            else:
+                ops.linear_decode(sub['h'], self.wproj, sub['p_lg'], B * V, 32)
+                lg, n_part, pstride = sub['p_lg'], sub['ns']['lg'], B * V
+        elif self._fused_ok(sub):
             ops.linear_decode_fused(x_rows, self.wproj, sub['lg'], cluster_k=self.fused_cluster['lg'])   # plain cast on load (no final norm, K-2)
             lg, n_part, pstride = sub['lg'], 1, 0
         elif self.precision == 'bf16':
@@ -299,6 +351,73 @@ class ARDecoder:
         x = sub['x']
         ops.embed_sum_pe(sub['last'].view(B, 1, 1), self.aud_table, self.pe_a, x, pos_b=sub['audio_pos'])
         layers = self.weights.layers
+        if self._lean_ok(sub):
+            qkv32 = sub['r_qkv'][0]
+            for li, L in enumerate(layers):
+                g, b, eps = L['norm1']
+                ops.linear_decode_rows_ln(x, L['wqkv'], qkv32, gamma=g[0], beta=b[0], eps=eps, flags=ops.FLAG_LATE_TRIGGER)
+                ops.attn_decode_paged(qkv32, 1, 0, st['pools'][li], sub['block_table'], sub['seq_lens'], sub['o'],
+                                      B, H, Dh, sub['n_tsplit'], sub['attn_ws'], ops.FLAG_PREFETCH_KV | self.attn_flags)
+                ops.linear_decode_rows(sub['o'], L['wo'], x, bias=L['bo'], residual=True)
+                g, b, eps = L['norm2']
+                ops.linear_decode_rows_ln(x, L['w1'], sub['f'], gamma=g[0], beta=b[0], eps=eps, bias=L['b1'], gelu=True)
+                ops.linear_decode_rows(sub['f'], L['w2'], x, bias=L['b2'], residual=True, want_split=0)
+            self._logits_sample_book(sub, x, samp, uniforms, eos)
+            return
+        if self._rows_ok(sub):
+            # Per GEMM one of two forms (self._mix(sub)): 'r' = rows kernel (csrc/gemm_decode_mma.cu: whole K inside one CTA,
+            # so out-proj adds into the residual stream and FFN1 applies bias + GELU in the epilogue -- no reduce kernel; only
+            # FFN2, K = F > 1024, leaves slices); 's' = tcgen05 swap-AB split-K slices (csrc/gemm_tc.cu) that the next
+            # LayerNorm / GELU-reduce / attention kernel adds in index order.
+            mix, nr, ns = self._mix(sub), sub['nr'], sub['ns']
+            f2_direct = mix['f2'] == 'r' and nr['f2'] == 1
+            if mix['f2'] == 'r':
+                f2_part, f2_n = sub['r_f2'], nr['f2']
+            else:
+                f2_part, f2_n = sub['p_f2'], ns['f2']
+            for li, L in enumerate(layers):
+                g, b, eps = L['norm1']
+                if li == 0 or f2_direct:
+                    ops.residual_layernorm(x, g[0], b[0], sub['h'], eps=eps)
+                else:
+                    ops.residual_layernorm(x, g[0], b[0], sub['h'], part=f2_part, n_part=f2_n, part_stride=B * d,
+                                           bias=layers[li - 1]['b2'], eps=eps)
+                if mix['qkv'] == 'r':
+                    ops.linear_decode_rows(sub['h'], L['wqkv'], sub['r_qkv'] if nr['qkv'] > 1 else sub['r_qkv'][0],
+                                           want_split=self.rows_qkv_split, flags=ops.FLAG_LATE_TRIGGER)
+                    qkv_part, qkv_n = sub['r_qkv'], nr['qkv']
+                else:
+                    ops.linear_decode(sub['h'], L['wqkv'], sub['p_qkv'], B * 3 * d, 32, ops.FLAG_LATE_TRIGGER)
+                    qkv_part, qkv_n = sub['p_qkv'], ns['qkv']
+                ops.attn_decode_paged(qkv_part, qkv_n, B * 3 * d, st['pools'][li], sub['block_table'],
+                                      sub['seq_lens'], sub['o'], B, H, Dh, sub['n_tsplit'], sub['attn_ws'],
+                                      ops.FLAG_PREFETCH_KV | self.attn_flags)
+                g, b, eps = L['norm2']
+                if mix['o'] == 'r':
+                    ops.linear_decode_rows(sub['o'], L['wo'], x, bias=L['bo'], residual=True)
+                    ops.residual_layernorm(x, g[0], b[0], sub['h'], eps=eps)
+                else:
+                    ops.linear_decode(sub['o'], L['wo'], sub['p_o'], B * d, 32)
+                    ops.residual_layernorm(x, g[0], b[0], sub['h'], part=sub['p_o'], n_part=ns['o'], part_stride=B * d,
+                                           bias=L['bo'], eps=eps)
+                if mix['f1'] == 'r':
+                    ops.linear_decode_rows(sub['h'], L['w1'], sub['f'], bias=L['b1'], gelu=True)
+                else:
+                    ops.linear_decode(sub['h'], L['w1'], sub['p_f1'], B * F, 32)
+                    ops.reduce_bias_act(sub['p_f1'], ns['f1'], B * F, L['b1'], True, sub['f'])
+                if f2_direct:
+                    ops.linear_decode_rows(sub['f'], L['w2'], x, bias=L['b2'], residual=True)
+                elif mix['f2'] == 'r':
+                    ops.linear_decode_rows(sub['f'], L['w2'], sub['r_f2'])
+                else:
+                    ops.linear_decode(sub['f'], L['w2'], sub['p_f2'], B * d, 32)
+            if f2_direct:
+                ops.residual_layernorm(x, None, None, sub['h'])
+            else:       # last FFN2 slices + bias into the residual stream, and the bf16 cast for the logits projection
+                ops.residual_layernorm(x, None, None, sub['h'], part=f2_part, n_part=f2_n, part_stride=B * d,
+                                       bias=layers[-1]['b2'])
+            self._logits_sample_book(sub, x, samp, uniforms, eos, logits_done=True)
+            return
         if self._fused_ok(sub):
             # five dependent kernels per layer: split-K is reduced inside a thread-block cluster, LayerNorm runs on load
             # inside the QKV / FFN1 GEMMs, bias + residual / GELU in the epilogues (csrc/gemm_decode_fused.cu)
@@ -414,7 +533,12 @@ class ARDecoder:
         subs = self._state['subs']
         total = 0
         for sub in subs:
-            if self._fused_ok(sub):
+            if self._lean_ok(sub):
+                total += 1 + 5 * L + 1 + 2          # embed, 5 per layer, logits, sample + bookkeeping
+            elif self._rows_ok(sub):
+                # embed, 7 per layer (+1 GELU-reduce when FFN1 leaves slices), final reduce + cast, logits, sample + bookkeeping
+                total += 1 + (7 + (self._mix(sub)['f1'] == 's')) * L + 1 + 1 + 2
+            elif self._fused_ok(sub):
                 total += 1 + 5 * L + 1 + 2          # embed, 5 per layer, logits, sample + bookkeeping
             elif self._chain_ok(sub):
                 total += 1 + 1 + 2 * L + 2          # embed, first chain, (attention + chain) per layer, sample, bookkeeping

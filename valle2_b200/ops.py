@@ -130,6 +130,61 @@ def linear_decode(x: torch.Tensor, w: torch.Tensor, part: torch.Tensor, part_str
     return ns.value
 
 
+def linear_decode_rows_splits(K: int, want_split: int = 1, M: int = 32) -> int:
+    """Split count vb_linear_decode_rows uses for this K and batch (0: K unsupported).  want_split=0: whole K in one CTA
+    when the M activation rows fit in shared memory (K <= 4096)."""
+    return int(_L().vb_linear_decode_rows_splits(M, K, want_split))
+
+
+def _rows_epilogue(bias, gelu, residual, y):
+    if residual:
+        assert bias is not None and not gelu and y.dtype == torch.float32
+        return EPI_BIAS_RESIDUAL
+    if gelu:
+        assert bias is not None
+        return EPI_BIAS_GELU
+    return EPI_BIAS if bias is not None else EPI_NONE
+
+
+def linear_decode_rows(x: torch.Tensor, w: torch.Tensor, y: torch.Tensor, *, bias: torch.Tensor | None = None,
+                       gelu: bool = False, residual: bool = False, want_split: int = 1, flags: int = 0) -> int:
+    """Decode-shape linear layer, "rows" form (csrc/gemm_decode_mma.cu): x (M<=32, K) bf16, w (N, K) bf16.
+    One slice: y (M, N) fp32/bf16 = epilogue(x @ w.T); residual=True: y (fp32) += x @ w.T + bias in place.
+    Several slices (K > 1024 or want_split > 1): y (n_split, M, N) fp32 slices, no epilogue.  Returns n_split."""
+    assert x.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and x.stride(1) == 1 and w.stride(1) == 1
+    M, K = x.shape
+    N = w.shape[0]
+    epi = _rows_epilogue(bias, gelu, residual, y)
+    if y.dim() == 3:
+        assert y.shape[1:] == (M, N) and y.dtype == torch.float32 and y.stride(2) == 1
+        ldy, sstride = y.stride(1), y.stride(0)
+        assert y.shape[0] >= linear_decode_rows_splits(K, want_split, M)
+    else:
+        assert y.shape == (M, N) and y.stride(1) == 1
+        ldy, sstride = y.stride(0), 0
+        assert linear_decode_rows_splits(K, want_split, M) == 1, 'split-K output needs a (n_split, M, N) fp32 buffer'
+    ns = C.c_int()
+    check(_L().vb_linear_decode_rows(_ptr(x), x.stride(0), _ptr(w), w.stride(0), _ptr(bias), _ptr(y), _code(y.dtype), ldy,
+                                     sstride, M, N, K, epi, want_split, flags, C.byref(ns), _stream()), 'vb_linear_decode_rows')
+    return ns.value
+
+
+def linear_decode_rows_ln(x: torch.Tensor, w: torch.Tensor, y: torch.Tensor, *, gamma: torch.Tensor | None = None,
+                          beta: torch.Tensor | None = None, eps: float = 1e-5, bias: torch.Tensor | None = None,
+                          gelu: bool = False, residual: bool = False, flags: int = 0) -> torch.Tensor:
+    """y (M<=8, N) = epilogue(LayerNorm(x; gamma, beta) @ w.T) with the LayerNorm computed on load inside the GEMM kernel;
+    x (M, K) fp32 residual rows, K in {256, 512, 1024}; gamma=None: plain bf16 cast of x."""
+    assert x.dtype == torch.float32 and w.dtype == torch.bfloat16 and x.stride(1) == 1 and w.stride(1) == 1
+    M, K = x.shape
+    N = w.shape[0]
+    assert y.shape == (M, N) and y.stride(1) == 1
+    epi = _rows_epilogue(bias, gelu, residual, y)
+    check(_L().vb_linear_decode_rows_ln(_ptr(x), x.stride(0), _ptr(gamma), _ptr(beta), float(eps), _ptr(w), w.stride(0),
+                                        _ptr(bias), _ptr(y), _code(y.dtype), y.stride(0), M, N, K, epi, flags, _stream()),
+          'vb_linear_decode_rows_ln')
+    return y
+
+
 def linear_decode_fused(a: torch.Tensor, w: torch.Tensor, y: torch.Tensor, *, bias: torch.Tensor | None = None,
                         gelu: bool = False, residual: bool = False, gamma: torch.Tensor | None = None,
                         beta: torch.Tensor | None = None, eps: float = 1e-5, cluster_k: int = 0,
