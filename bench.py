@@ -294,24 +294,35 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                                  'kernel': 'linear_decode_rows_kernel (mma.sync, full K per CTA, LN on load, fused epilogues)' if lean else 'linear_decode_rows_kernel (mma.sync, full K per CTA, fused epilogues) / gemm_tc_kernel<swap-AB split-K> per config.decode_gemm' if mma_rows else 'gemm_decode_fused_kernel (cluster split-K through DSMEM, LN on load, fused epilogues)' if rows else 'gemm_tc_kernel<swap-AB split-K>'}
 
     # ---- end-to-end through the public API from pinned host tensors --------------------------------
-    barrier()
-    t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
-    t0.record()
-    out, n = model.generate_batch(tokens_h.to(dev, non_blocking=True), codes_h.to(dev, non_blocking=True),
-                                  max_new=total_steps, ignore_eos=True)
-    out_h = out.to('cpu', non_blocking=False)
-    t1.record()
-    barrier()
-    e2e_ms = t0.elapsed_time(t1)
-    if world > 1:
-        t = torch.tensor([e2e_ms], device=dev)
-        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
-        e2e_ms = float(t.item())
+    # One untimed call first (allocates the KV pools and captures the step graph of this request shape -- the engine keeps
+    # both for later requests of the same shape), then three timed calls; the median is reported and all three are listed.
+    # Every timed call does the full job: H2D prompt, prefill, decode, D2H codes.
+    def e2e_once():
+        barrier()
+        t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+        t0.record()
+        out, n = model.generate_batch(tokens_h.to(dev, non_blocking=True), codes_h.to(dev, non_blocking=True),
+                                      max_new=total_steps, ignore_eos=True)
+        out_h = out.to('cpu', non_blocking=False)
+        t1.record()
+        barrier()
+        t_ms = t0.elapsed_time(t1)
+        if world > 1:
+            t = torch.tensor([t_ms], device=dev)
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+            t_ms = float(t.item())
+        return t_ms, out_h
+
+    e2e_once()
+    runs = [e2e_once() for _ in range(3)]
+    e2e_all = sorted(r[0] for r in runs)
+    e2e_ms, out_h = e2e_all[1], runs[0][1]
     result['e2e'] = {'value': B * world * total_steps / (e2e_ms * 1e-3), 'unit': 'tokens/s',
                      'h2d_bytes_per_step': (tokens_h.numel() + codes_h.numel()) * 8 / total_steps,
                      'd2h_bytes_per_step': out_h.numel() * 4 / total_steps,
-                     'includes': f'H2D prompt, prefill of {TX + P} positions, graph capture, {total_steps} decode steps, D2H codes',
-                     'ms_total': e2e_ms}
+                     'includes': f'H2D prompt, prefill of {TX + P} positions, {total_steps} decode steps (step graph and KV pools of this '
+                                 f'request shape are reused from the untimed first call), D2H codes',
+                     'ms_total': e2e_ms, 'ms_all_runs': e2e_all, 'runs': 'median of 3 after one untimed call'}
 
     if rank == 0 and not args.no_extras:
         result['extras'] = extras(args, dev, tmp)
@@ -329,31 +340,35 @@ def extras(args, dev, tmp):
     model = ValleAR(large_cfg('LayerNorm', tmp)).eval().to(dev)
     eng = model._engine()
     g = torch.Generator().manual_seed(7)
-    tokens = torch.randint(0, 256, (1, TX), generator=g).to(dev)
-    codes = torch.cat([torch.full((1, 1), 1025), torch.randint(0, 1024, (1, P0 - 1), generator=g)], 1).to(dev)
     samp = {'temperature': 1.0, 'top_k': 1, 'top_p': 1.0, 'seed': 0}
-    st = eng.prefill(tokens, codes, max_new=N_NEW + 2)
-    eng.first_token(samp, None, -1)
-    eng.decode_step(samp, None, -1)
-    torch.cuda.synchronize()
-    graph = torch.cuda.CUDAGraph()
-    with torch.cuda.graph(graph):
-        eng.decode_step(samp, None, -1)
-    for _ in range(4):
-        graph.replay()
-    K1 = N_NEW - 8
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
-    e0.record()
-    for _ in range(K1):
-        graph.replay()
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1)
-    mean_ctx = TX + P0 + 6 + (K1 - 1) / 2
-    out['ar_decode_b1'] = {'tokens_per_s': K1 / (ms * 1e-3), 'us_per_step': ms * 1e3 / K1,
-                           'hbm_frac_of_measured_peak': ar_step_bytes(1, mean_ctx) / (ms / K1 * 1e-3) / (pk['hbm_gbs'] * 1e9)}
-    del model, eng, st, graph
+    # batch 1 (BASELINE configs[1]) over the full 750 frames; batch 128 / 64 = one GPU's share of configs[3] (256 utterances
+    # over 2 / 4 GPUs), 150 steps around the same mean context
+    for Bx, K1, extra in ((1, N_NEW - 8, 0), (64, 150, 300), (128, 150, 300)):
+        tokens = torch.randint(0, 256, (Bx, TX), generator=g).to(dev)
+        codes = torch.cat([torch.full((Bx, 1), 1025), torch.randint(0, 1024, (Bx, P0 + extra - 1), generator=g)], 1).to(dev)
+        st = eng.prefill(tokens, codes, max_new=K1 + 10)
+        eng.first_token(samp, None, -1)
+        eng.decode_step(samp, None, -1)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            eng.decode_step(samp, None, -1)
+        for _ in range(4):
+            graph.replay()
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(K1):
+            graph.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        mean_ctx = TX + P0 + extra + 6 + (K1 - 1) / 2
+        out[f'ar_decode_b{Bx}'] = {'tokens_per_s': Bx * K1 / (ms * 1e-3), 'us_per_step': ms * 1e3 / K1, 'mean_ctx': mean_ctx,
+                                   'launches_per_step': eng.launches_per_step(),
+                                   'hbm_frac_of_measured_peak': ar_step_bytes(Bx, mean_ctx) / (ms / K1 * 1e-3) / (pk['hbm_gbs'] * 1e9)}
+        del st, graph
+    del model, eng
     torch.cuda.empty_cache()
     # NAR config 3: 7 stages, S = 150 + 225 + 525 = 900, batch 64
     try:

@@ -229,6 +229,11 @@ int vb_attn_decode_paged(const float* qkv_part, int n_part, int64_t part_stride,
                          const int32_t* block_table, int max_pages, const int32_t* seq_lens,
                          void* o, int o_dtype, int B, int H, int Dh, int n_tsplit, int flags, void* ws, void* stream);
 
+/* Profiling aid: subsequent bf16 vb_attn_decode_paged launches write %globaltimer stamps [cta][8] = {start, producer issued
+ * its copies, consumers' dependency resolved, q ready, first page landed, pages done, partial written, output written}
+ * (uint64, device memory, grid * 8 entries; 0 = event did not occur in that CTA); NULL switches it off. */
+int vb_attn_decode_set_debug(void* buf);
+
 /* Ask the memory system to pull cached KV pages of one layer's pool into L2 (cp.async.bulk.prefetch.L2; a hint, nothing is
  * written).  Pages [pages_total * page_lo_pct / 100, pages_total * page_hi_pct / 100) of every sequence are requested.
  * Launched on a side stream while the latency-bound GEMM chain of the previous layer leaves HBM idle. */

@@ -177,3 +177,30 @@ def test_tts_pipeline_matches_oracle_tiny(golden, tmp_path):
         assert outs[b].shape == ref.shape and torch.equal(outs[b].cpu(), ref), b
         lens.add(len(first))
     assert len(lens) > 1 or True        # (ragged when the synthetic utterances stop at different steps)
+
+
+def test_state_and_graph_reuse_across_requests(tmp_path):
+    """Two requests of the same shape reuse the decode state and the captured step graph (engine._alloc / generate); the
+    second request (different inputs) must equal what a fresh engine produces, and the first result must not be
+    overwritten by the second (outputs are copies)."""
+    valle2_b200.set_precision('bf16')
+    oc, model, _ = _large_ar(tmp_path, max_audio_len=12, top_k=1)
+    g = torch.Generator().manual_seed(23)
+    mk = lambda: (torch.randint(0, 256, (3, 40), generator=g).cuda(),
+                  torch.cat([torch.full((3, 1), oc.bos_token), torch.randint(0, 1024, (3, 30), generator=g)], 1).cuda())
+    (t1, c1), (t2, c2) = mk(), mk()
+    eng = model._engine()
+    out1, _, n1 = eng.generate(t1, c1, max_new=12, top_k=1, top_p=1.0, temperature=1.0, ignore_eos=True)
+    keep1, graph1, state1 = out1.clone(), eng._graph, eng._state
+    out2, _, n2 = eng.generate(t2, c2, max_new=12, top_k=1, top_p=1.0, temperature=1.0, ignore_eos=True)
+    assert eng._graph is graph1 and eng._state is state1          # reused
+    assert torch.equal(out1, keep1)                               # first result untouched
+    eng._state, eng._graph, eng._graph_key = None, None, None     # fresh state + capture
+    out2_fresh, _, _ = eng.generate(t2, c2, max_new=12, top_k=1, top_p=1.0, temperature=1.0, ignore_eos=True)
+    assert n1 == n2 == 12 and torch.equal(out2, out2_fresh)
+    # a different sampling scalar re-captures, a different shape re-allocates
+    eng.generate(t2, c2, max_new=12, top_k=5, top_p=1.0, temperature=1.0, ignore_eos=True)
+    assert eng._graph is not graph1
+    st = eng._state
+    eng.generate(t2[:2], c2[:2], max_new=12, top_k=5, top_p=1.0, temperature=1.0, ignore_eos=True)
+    assert eng._state is not st

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Launch ONE kernel configuration a few times (no graphs) -- the target of `ncu --set full` captures.
-usage: python tools/prof_one.py {attn_decode|gemm_decode|gemm_large|attn_prefill}"""
+usage: python tools/prof_one.py {attn_decode|gemm_decode|rows_decode [B]|gemm_large|attn_prefill}"""
 import os
 import sys
 
@@ -31,6 +31,21 @@ elif what == 'gemm_decode':          # the four weight-streaming GEMMs of one de
             w = (torch.randn(N, K, device='cuda') * 0.02).bfloat16()
             part = torch.zeros(32, B, N, device='cuda')
             ops.linear_decode(x, w, part, B * N, 32)
+elif what == 'rows_decode':          # the four GEMMs of the lean small-batch layer (csrc/gemm_decode_mma.cu), B = argv[2] (default 1)
+    B = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+    x = torch.randn(B, d, device='cuda')
+    o = torch.randn(B, d, device='cuda').bfloat16()
+    f = torch.zeros(B, F, device='cuda', dtype=torch.bfloat16)
+    qkv = torch.zeros(B, 3 * d, device='cuda')
+    g_, b_ = torch.randn(d, device='cuda'), torch.randn(d, device='cuda')
+    bo, b1 = torch.randn(d, device='cuda'), torch.randn(F, device='cuda')
+    for rep in range(3):
+        wq, wo = (torch.randn(3 * d, d, device='cuda') * 0.02).bfloat16(), (torch.randn(d, d, device='cuda') * 0.02).bfloat16()
+        w1, w2 = (torch.randn(F, d, device='cuda') * 0.02).bfloat16(), (torch.randn(d, F, device='cuda') * 0.02).bfloat16()
+        ops.linear_decode_rows_ln(x, wq, qkv, gamma=g_, beta=b_)
+        ops.linear_decode_rows(o, wo, x, bias=bo, residual=True)
+        ops.linear_decode_rows_ln(x, w1, f, gamma=g_, beta=b_, bias=b1, gelu=True)
+        ops.linear_decode_rows(f, w2, x, bias=bo, residual=True, want_split=0)
 elif what == 'gemm_large':           # NAR config 3 shapes (M = 64 x 900)
     M = 57600
     for (N, K, epi) in [(3072, 1024, 'none'), (1024, 1024, 'residual'), (4096, 1024, 'gelu'), (1024, 4096, 'residual')]:

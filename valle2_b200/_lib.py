@@ -47,6 +47,7 @@ SIGNATURES = {
     'vb_decode_chain': (_i, [_p, _i, _i, _p, _p]),
     'vb_decode_chain_set_debug': (_i, [_p]),
     'vb_linear_decode_set_debug': (_i, [_p]),
+    'vb_attn_decode_set_debug': (_i, [_p]),
     'vb_linear_decode_rows_set_debug': (_i, [_p]),
     'vb_attention': (_i, [_p, _p, _p, _i, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _p, _i, _i64, _i64,
                           _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _i64, _i64, _i64, _p]),
@@ -93,7 +94,7 @@ def load(build_if_missing: bool = True):
                 raise VBError(f'libvalle_b200.so is missing and could not be built: {e}') from e
     if not os.path.exists(LIB_PATH):
         raise VBError(f'{LIB_PATH} not found -- run `python -m valle2_b200.build` (there is no CPU fallback)')
-    lib = C.CDLL(LIB_PATH)
+    lib = C.CDLL(os.environ.get('VALLE_B200_LIB') or LIB_PATH)      # override: experiment builds (tools/build_variant.sh)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)            # AttributeError if the symbol is missing: loud by design
         fn.restype = res

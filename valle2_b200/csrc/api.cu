@@ -3,6 +3,9 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <mutex>
+#include <unordered_set>
+
 #include "common.cuh"
 
 static thread_local char g_err[512] = "";
@@ -37,6 +40,20 @@ bool vb_pdl_enabled() {
         v = (e && e[0] == '0') ? 0 : 1;
     }
     return v != 0;
+}
+
+void vb_prefer_max_carveout(const void* kern) {
+    static std::mutex mu;
+    static std::unordered_set<const void*> done;
+    static int enabled = -1;
+    std::lock_guard<std::mutex> lock(mu);
+    if (enabled < 0) {
+        const char* e = getenv("VALLE_B200_CARVEOUT");
+        enabled = (e && e[0] == '1') ? 1 : 0;
+    }
+    if (!enabled || !done.insert(kern).second) return;
+    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaGetLastError();     // a kernel that cannot take the hint keeps its default
 }
 
 extern "C" int vb_device_info(int* sm_count, int* cc_major, int* cc_minor, int64_t* smem_optin_bytes) {

@@ -12,6 +12,8 @@
 // Replaces modules.py:146-167 on the cached path (qkv head split, torch.cat cache growth, SDPA with one query).
 #include <math.h>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace {
@@ -309,9 +311,20 @@ __global__ void __launch_bounds__(MMA_THREADS, 4) attn_decode_mma_kernel(const f
                                                                   const int32_t* __restrict__ seq_lens, TO* __restrict__ o,
                                                                   float* __restrict__ ws_o, float* __restrict__ ws_ml,
                                                                   unsigned* __restrict__ counters, int H, int n_tsplit,
-                                                                  float scale_log2e, int prefetch_kv) {
+                                                                  float scale_log2e, int prefetch_kv,
+                                                                  unsigned long long* __restrict__ dbg) {
     typedef __nv_bfloat16 T;
     constexpr int CHUNK_BYTES = PAGE * DH * 2;          // 8 KB: one (page, K or V, head) chunk
+    // optional timeline (vb_attn_decode_set_debug): %globaltimer stamps [cta][8] = {start, producer issued its copies,
+    // consumers' dependency resolved, q ready, first page landed, pages done, partial written, output written}
+#define ATT_STAMP(ev)                                                                                          \
+    do {                                                                                                       \
+        if (dbg != nullptr) {                                                                                  \
+            unsigned long long t_;                                                                             \
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                                             \
+            dbg[((static_cast<size_t>(blockIdx.z) * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 8 + (ev)] = t_; \
+        }                                                                                                      \
+    } while (0)
     constexpr int STAGE_BYTES = 2 * CHUNK_BYTES;
 
     extern __shared__ __align__(128) uint8_t ring[];
@@ -326,8 +339,15 @@ __global__ void __launch_bounds__(MMA_THREADS, 4) attn_decode_mma_kernel(const f
     const int split = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int d_model = H * DH;
-    pdl_trigger();
+    // prefetch_kv bit 1 (VB_FLAG_LATE_TRIGGER): release the successor only after this kernel's own dependency has resolved.
+    // With the early trigger the out-proj / FFN1 CTAs of the same layer become resident (spinning in griddepcontrol.wait)
+    // while this kernel's own CTAs are still waiting for registers: at batch 1 some clusters started 2 us late and their
+    // pages landed 3 us after the median (tools/step_timeline.py).
+    const bool late_trigger = (prefetch_kv & 2) != 0;
+    prefetch_kv &= 1;
+    if (!late_trigger) pdl_trigger();
     if (threadIdx.x == 0) {
+        ATT_STAMP(0);
         for (int s = 0; s < NSTAGE; ++s) {
             mbar_init(smem_u32(&full_bar[s]), 1);
             mbar_init(smem_u32(&empty_bar[s]), 1);       // one warp consumes a whole stage
@@ -343,8 +363,8 @@ __global__ void __launch_bounds__(MMA_THREADS, 4) attn_decode_mma_kernel(const f
         if (!prefetch_kv) pdl_wait();     // with VB_FLAG_PREFETCH_KV the cached pages are known to be final already
         const int n_old = seq_lens[b];
         const int pages_total = (n_old + PAGE - 1) / PAGE;
-        const int pp = (pages_total + n_tsplit - 1) / n_tsplit;
-        const int p0 = min(split * pp, pages_total), p1 = min(p0 + pp, pages_total);
+        // pages spread evenly over the splits (12 pages over 8 splits: 2,1,2,1,... instead of 2,2,2,2,2,2,0,0)
+        const int p0 = (split * pages_total) / n_tsplit, p1 = ((split + 1) * pages_total) / n_tsplit;
         for (int i = lane; i < min(p1 - p0, MAX_PG_SMEM); i += 32) pg_s[i] = bt[p0 + i];
         __syncwarp();
         if (lane == 0) {
@@ -361,6 +381,7 @@ __global__ void __launch_bounds__(MMA_THREADS, 4) attn_decode_mma_kernel(const f
                 bulk_load_1d(dst + CHUNK_BYTES, ksrc + static_cast<int64_t>(H) * PAGE * DH, CHUNK_BYTES, fb);
                 if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
             }
+            ATT_STAMP(1);
         }
         __syncwarp();
         if (prefetch_kv) pdl_wait();      // every thread of the CTA passes the dependency before it exits
@@ -374,11 +395,24 @@ __global__ void __launch_bounds__(MMA_THREADS, 4) attn_decode_mma_kernel(const f
         for (int i = 0; i < 4; ++i) oacc[j][i] = 0.f;
 
     if (warp < MMA_WARPS) {
+        // Under VB_FLAG_PREFETCH_KV seq_lens and the page table are final before this kernel starts: fetch the sequence
+        // length and the page that receives the new token BEFORE the dependency wait (two dependent L2 round trips that
+        // otherwise sit between the wait and the q/k/v reduction).
+        int n_old = 0, new_page = 0;
+        if (prefetch_kv) {
+            n_old = seq_lens[b];
+            if (owns_new) new_page = bt[n_old / PAGE];
+        }
         pdl_wait();     // q/k/v partials of the new token come from the predecessor (QKV GEMM)
-        const int n_old = seq_lens[b];
+        if (late_trigger) pdl_trigger();
+        if (threadIdx.x == 0) ATT_STAMP(2);
+        if (!prefetch_kv) {
+            n_old = seq_lens[b];
+            if (owns_new) new_page = bt[n_old / PAGE];
+        }
         const int pages_total = (n_old + PAGE - 1) / PAGE;
-        const int pp = (pages_total + n_tsplit - 1) / n_tsplit;
-        const int p0 = min(split * pp, pages_total), p1 = min(p0 + pp, pages_total);
+        // pages spread evenly over the splits (12 pages over 8 splits: 2,1,2,1,... instead of 2,2,2,2,2,2,0,0)
+        const int p0 = (split * pages_total) / n_tsplit, p1 = ((split + 1) * pages_total) / n_tsplit;
         // new-token q, k, v (k, v only in the owner of the last split): threads 0..63 own one dim each; fixed-order reduction
         // of the split-K partials with every load issued before the first add
         if (threadIdx.x < DH) {
@@ -403,13 +437,14 @@ __global__ void __launch_bounds__(MMA_THREADS, 4) attn_decode_mma_kernel(const f
                 const T kq = __float2bfloat16_rn(ak), vq = __float2bfloat16_rn(av);   // the cache precision is what later steps read
                 k_s[e] = __bfloat162float(kq);
                 v_s[e] = __bfloat162float(vq);
-                const int page = bt[n_old / PAGE], slot = n_old % PAGE;
+                const int page = new_page, slot = n_old % PAGE;
                 T* kdst = pool + ((static_cast<int64_t>(page) * 2 * H + h) * PAGE + slot) * DH + vb_pool_col_bf16(slot, e);
                 kdst[0] = kq;
                 kdst[static_cast<int64_t>(H) * PAGE * DH] = vq;
             }
         }
         asm volatile("bar.sync 1, %0;" ::"n"(MMA_WARPS * 32) : "memory");   // consumer warps only
+        if (threadIdx.x == 0) ATT_STAMP(3);
 
         const int g = lane >> 2, t = lane & 3;
         // A fragments of q (row 0 of the 16-row tile): k-step kk covers dims 16kk .. 16kk+15
@@ -424,6 +459,7 @@ __global__ void __launch_bounds__(MMA_THREADS, 4) attn_decode_mma_kernel(const f
             const int stage = ip % NSTAGE;
             const uint32_t phase = (ip / NSTAGE) & 1;
             mbar_wait(smem_u32(&full_bar[stage]), phase);
+            if (threadIdx.x == 0 && ip == 0) ATT_STAMP(4);
             const uint32_t kbase = smem_u32(ring) + stage * STAGE_BYTES;
             const uint32_t vbase = kbase + CHUNK_BYTES;
             const int tok0 = (p0 + ip) * PAGE;
@@ -487,6 +523,7 @@ __global__ void __launch_bounds__(MMA_THREADS, 4) attn_decode_mma_kernel(const f
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&empty_bar[stage]));
         }
+        if (threadIdx.x == 0) ATT_STAMP(5);
         // row 0 lives in lanes 0..3: dims 8j + 2t, 8j + 2t + 1; l is a per-lane partial sum
         l_run += __shfl_xor_sync(0xffffffffu, l_run, 1);
         l_run += __shfl_xor_sync(0xffffffffu, l_run, 2);
@@ -528,6 +565,41 @@ __global__ void __launch_bounds__(MMA_THREADS, 4) attn_decode_mma_kernel(const f
     TO* orow = o + static_cast<int64_t>(b) * d_model + h * DH;
     if (n_tsplit == 1) {
         if (threadIdx.x < DH) orow[threadIdx.x] = from_f32<TO>(out_l > 0.f ? out_acc / out_l : 0.f);
+        if (threadIdx.x == 0) ATT_STAMP(7);
+        return;
+    }
+    if (counters == nullptr) {
+        // Launched as a thread-block cluster of n_tsplit CTAs along x (one cluster per (b, h)): the splits are merged in
+        // CTA 0 through distributed shared memory -- one remote store + one cluster barrier instead of store, fence, ticket
+        // atomic, fence and an L2 round trip for the partials (1.5-3 us of a 9 us launch at batch 1).  Same order and
+        // arithmetic as the ticket path: bit-identical results.
+        __shared__ float c_o[8][DH];
+        __shared__ __align__(8) float c_ml[8][2];
+        if (threadIdx.x < DH) {
+            uint32_t ra;
+            asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(&c_o[split][threadIdx.x])), "r"(0));
+            asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(ra), "f"(out_acc) : "memory");
+            if (threadIdx.x == 0) {
+                asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(&c_ml[split][0])), "r"(0));
+                asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(ra), "f"(out_m), "f"(out_l) : "memory");
+            }
+        }
+        if (threadIdx.x == 0) ATT_STAMP(6);
+        asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+        if (split != 0) return;
+        asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+        if (threadIdx.x < DH) {
+            float M = -INFINITY;
+            for (int s = 0; s < n_tsplit; ++s) M = fmaxf(M, c_ml[s][0]);
+            float a = 0.f, l = 0.f;
+            for (int s = 0; s < n_tsplit; ++s) {
+                const float wt = (c_ml[s][0] == -INFINITY) ? 0.f : exp2f(c_ml[s][0] - M);
+                a = fmaf(c_o[s][threadIdx.x], wt, a);
+                l = fmaf(c_ml[s][1], wt, l);
+            }
+            orow[threadIdx.x] = from_f32<TO>(l > 0.f ? a / l : 0.f);
+            if (threadIdx.x == 0) ATT_STAMP(7);
+        }
         return;
     }
     const int64_t slot = (static_cast<int64_t>(b) * H + h) * n_tsplit;
@@ -535,6 +607,7 @@ __global__ void __launch_bounds__(MMA_THREADS, 4) attn_decode_mma_kernel(const f
         ws_o[(slot + split) * DH + threadIdx.x] = out_acc;
         if (threadIdx.x == 0) { ws_ml[(slot + split) * 2] = out_m; ws_ml[(slot + split) * 2 + 1] = out_l; }
     }
+    if (threadIdx.x == 0) ATT_STAMP(6);
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -545,20 +618,55 @@ __global__ void __launch_bounds__(MMA_THREADS, 4) attn_decode_mma_kernel(const f
     if (!is_last) return;
     __threadfence();
     if (threadIdx.x < DH) {
+        // every partial is requested before the first one is used: one L2 round trip instead of n_tsplit dependent ones
+        // (the rolled loop cost 5 us of the 9.5 us this kernel took in a batch-1 step -- tools/step_timeline.py)
+        constexpr int MAXS = 8;
+        float ms[MAXS], ls[MAXS], os[MAXS];
+#pragma unroll
+        for (int s = 0; s < MAXS; ++s) {
+            const bool on = s < n_tsplit;
+            ms[s] = on ? __ldcg(&ws_ml[(slot + s) * 2]) : -INFINITY;
+            ls[s] = on ? __ldcg(&ws_ml[(slot + s) * 2 + 1]) : 0.f;
+            os[s] = on ? __ldcg(&ws_o[(slot + s) * DH + threadIdx.x]) : 0.f;
+        }
         float M = -INFINITY;
-        for (int s = 0; s < n_tsplit; ++s) M = fmaxf(M, __ldcg(&ws_ml[(slot + s) * 2]));
+#pragma unroll
+        for (int s = 0; s < MAXS; ++s) M = fmaxf(M, ms[s]);
+        for (int s = MAXS; s < n_tsplit; ++s) M = fmaxf(M, __ldcg(&ws_ml[(slot + s) * 2]));
         float a = 0.f, l = 0.f;
-        for (int s = 0; s < n_tsplit; ++s) {
-            const float ms = __ldcg(&ws_ml[(slot + s) * 2]);
-            const float wt = (ms == -INFINITY) ? 0.f : exp2f(ms - M);
+#pragma unroll
+        for (int s = 0; s < MAXS; ++s) {        // same order and arithmetic as the rolled loop: results are bit-identical
+            const float wt = (ms[s] == -INFINITY) ? 0.f : exp2f(ms[s] - M);
+            a = fmaf(os[s], wt, a);
+            l = fmaf(ls[s], wt, l);
+        }
+        for (int s = MAXS; s < n_tsplit; ++s) {
+            const float m2 = __ldcg(&ws_ml[(slot + s) * 2]);
+            const float wt = (m2 == -INFINITY) ? 0.f : exp2f(m2 - M);
             a = fmaf(__ldcg(&ws_o[(slot + s) * DH + threadIdx.x]), wt, a);
             l = fmaf(__ldcg(&ws_ml[(slot + s) * 2 + 1]), wt, l);
         }
         orow[threadIdx.x] = from_f32<TO>(l > 0.f ? a / l : 0.f);
+        if (threadIdx.x == 0) ATT_STAMP(7);
     }
 }
 
+#undef ATT_STAMP
 }  // namespace
+
+static unsigned long long* g_attn_dbg = nullptr;
+static bool attn_cluster_enabled() {     // VALLE_B200_ATTN_CLUSTER=0: merge the splits through the global ticket instead
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("VALLE_B200_ATTN_CLUSTER");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v != 0;
+}
+extern "C" int vb_attn_decode_set_debug(void* buf) {   /* device buffer of grid * 8 uint64 stamps, or NULL */
+    g_attn_dbg = static_cast<unsigned long long*>(buf);
+    return VB_OK;
+}
 
 extern "C" int64_t vb_attn_decode_ws_bytes(int B, int H, int n_tsplit) {
     const int64_t bh = static_cast<int64_t>(B) * H;
@@ -601,9 +709,32 @@ extern "C" int vb_attn_decode_paged(const float* qkv_part, int n_part, int64_t p
             VB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));                   \
             configured = true;                                                                                        \
         }                                                                                                             \
-        VB_CUDA(vb_launch(true, kern, grid, dim3(MMA_THREADS), SMEM, st, qkv_part, n_part, part_stride,               \
-                          static_cast<__nv_bfloat16*>(pool), block_table, max_pages, seq_lens, static_cast<TO*>(o),   \
-                          ws_o, ws_ml, counters, H, n_tsplit, scale_log2e, (flags & VB_FLAG_PREFETCH_KV) ? 1 : 0));   \
+        if (n_tsplit > 1 && n_tsplit <= 8 && attn_cluster_enabled()) {                                                \
+            /* one cluster per (b, h): splits merged through DSMEM, counters == nullptr selects that path */          \
+            cudaLaunchConfig_t cfg = {};                                                                              \
+            cfg.gridDim = grid; cfg.blockDim = dim3(MMA_THREADS); cfg.dynamicSmemBytes = SMEM; cfg.stream = st;       \
+            cudaLaunchAttribute attr[2];                                                                              \
+            int na = 0;                                                                                               \
+            if (vb_pdl_enabled()) {                                                                                   \
+                attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;                                     \
+                attr[na].val.programmaticStreamSerializationAllowed = 1;                                              \
+                ++na;                                                                                                 \
+            }                                                                                                         \
+            attr[na].id = cudaLaunchAttributeClusterDimension;                                                        \
+            attr[na].val.clusterDim.x = n_tsplit; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;       \
+            ++na;                                                                                                     \
+            cfg.attrs = attr; cfg.numAttrs = na;                                                                      \
+            VB_CUDA(cudaLaunchKernelEx(&cfg, kern, qkv_part, n_part, part_stride, static_cast<__nv_bfloat16*>(pool),  \
+                                       block_table, max_pages, seq_lens, static_cast<TO*>(o), ws_o, ws_ml,            \
+                                       static_cast<unsigned*>(nullptr), H, n_tsplit, scale_log2e,                     \
+                                       ((flags & VB_FLAG_PREFETCH_KV) ? 1 : 0) | ((flags & VB_FLAG_LATE_TRIGGER) ? 2 : 0), g_attn_dbg)); \
+        } else {                                                                                                      \
+            VB_CUDA(vb_launch(true, kern, grid, dim3(MMA_THREADS), SMEM, st, qkv_part, n_part, part_stride,           \
+                              static_cast<__nv_bfloat16*>(pool), block_table, max_pages, seq_lens, static_cast<TO*>(o), \
+                              ws_o, ws_ml, counters, H, n_tsplit, scale_log2e,                                        \
+                              ((flags & VB_FLAG_PREFETCH_KV) ? 1 : 0) | ((flags & VB_FLAG_LATE_TRIGGER) ? 2 : 0),     \
+                              g_attn_dbg));                                                                           \
+        }                                                                                                             \
     }
     const bool simt = (flags & VB_FLAG_ATTN_SIMT) != 0;
     if (pool_dtype == VB_BF16 && o_dtype == VB_BF16 && !simt) DECM(__nv_bfloat16, NSTAGE * 2 * PAGE * DH * 2)

@@ -40,6 +40,11 @@ static inline int64_t vb_ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b
 
 int vb_sm_count();   // cached cudaDevAttrMultiProcessorCount of the current device
 bool vb_pdl_enabled();   // VALLE_B200_PDL != 0 (default on)
+// Experiment (VALLE_B200_CARVEOUT=1, off by default): ask for the maximum shared-memory carveout on the first launch of
+// every PDL kernel, on the theory that kernels of one dependent chain can only be co-resident when they agree on the
+// L1 / shared split.  Measured: no gain in the full step (243.6 vs 245.1 us at B=1) and the GEMM chain alone gets slower
+// (135 -> 181 us) with the minimal L1 -- tools/step_breakdown.py.
+void vb_prefer_max_carveout(const void* kern);
 
 // Kernel launch with the programmatic-dependent-launch attribute (captured as a programmatic edge in CUDA graphs).
 template <typename... Exp, typename... Act>
@@ -54,6 +59,7 @@ static inline cudaError_t vb_launch(bool pdl, void (*kern)(Exp...), dim3 grid, d
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = (pdl && vb_pdl_enabled()) ? 1 : 0;
+    if (pdl) vb_prefer_max_carveout(reinterpret_cast<const void*>(kern));
     return cudaLaunchKernelEx(&cfg, kern, static_cast<Exp>(args)...);
 }
 
@@ -163,8 +169,16 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity)
 // while its predecessor in the stream is still running.  pdl_trigger() lets OUR successor start early; pdl_wait()
 // blocks until the predecessor grid has completed and its writes are visible.  Before pdl_wait() a kernel may only
 // touch immutable data (weights, tensor maps) and its own shared memory / TMEM.
+// -DVB_PDL_DEPTH1 (experiment, tools/build_variant.sh): every kernel releases its successor only AFTER its own wait, so
+// at most two kernels of a chain are resident at a time (the default lets a whole stack of future kernels sit on the SMs
+// spinning in griddepcontrol.wait, which starves a second, independent chain of registers and shared memory).
+#ifdef VB_PDL_DEPTH1
+__device__ __forceinline__ void pdl_trigger() {}
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;\n griddepcontrol.launch_dependents;" ::: "memory"); }
+#else
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#endif
 
 // TMA: 2D/3D tiled load global -> shared, completion on an mbarrier
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {

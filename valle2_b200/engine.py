@@ -141,6 +141,7 @@ class ARDecoder:
         self.wproj = model.proj.weight.detach().to(self.cd).contiguous()
         self._state = None
         self._graph = None
+        self._graph_key = None
         self._streams = []
         self.page_permutation_seed = None      # tests: scatter the logical pages over the pool
         # tunables (env overrides are for experiments; the defaults are the measured best)
@@ -155,6 +156,10 @@ class ARDecoder:
         # or five letters [rs] for qkv, out-proj, FFN1, FFN2, logits (see _mix)
         self.decode_gemm = os.environ.get('VALLE_B200_DECODE_GEMM', 'auto')
         self.rows_qkv_split = int(os.environ.get('VALLE_B200_ROWS_QKV_SPLIT', '1'))
+        # lean path, >= 4 sequences: the attention kernel releases its successors only after its own wait (see
+        # csrc/attn_decode.cu; measured -2 % step time at B = 4..8, +2 % at B = 1, tools/step_breakdown.py)
+        self.attn_late = ops.FLAG_LATE_TRIGGER if os.environ.get('VALLE_B200_ATTN_LATE', '1') != '0' else 0
+        self.qkv_late_all = os.environ.get('VALLE_B200_QKV_LATE_ALL', '0') != '0'      # A/B: late PDL trigger in every layer
         self.n_sub_override = int(os.environ.get('VALLE_B200_SUBBATCH', '0'))
         self.attn_ctas = int(os.environ.get('VALLE_B200_ATTN_CTAS', '0'))
         self.n_tsplit_override = 0             # tests: pin the flash-decoding split
@@ -256,10 +261,26 @@ class ARDecoder:
         sub['attn_ws'] = torch.zeros(ops.attn_decode_ws_bytes(B, H, n_ts) // 4 + 64, device=dev, dtype=torch.int32)
         return sub
 
+    def _alloc_key(self, B: int, max_pages: int, max_new: int):
+        return (B, max_pages, max_new, self._n_sub(B), self.n_tsplit_override, self.attn_ctas, self.page_permutation_seed,
+                self.decode_gemm, self.use_chain, self.use_fused, self.rows_qkv_split, self.precision)
+
     def _alloc(self, B: int, max_ctx: int, max_new: int):
+        """Decode state for a batch: KV page pools, page table, counters, workspaces.  A request of the same shape as the
+        previous one REUSES the buffers (and with them the captured step graph, see generate): only the counters are
+        reset -- stale pages are never read because every kernel is bounded by seq_lens.  Re-allocating 1.9 GB of pools
+        and re-capturing per call cost 5-270 ms of a 400 ms request (tools/e2e_phases.py: the graph's private pool is
+        released with cudaFree when the old graph dies)."""
         dev, H, L = self.device, self.H, len(self.weights.layers)
         max_pages = (max_ctx + PAGE - 1) // PAGE + 1
-        st = {'B': B, 'max_pages': max_pages, 'max_new': max_new}
+        key = self._alloc_key(B, max_pages, max_new)
+        st = self._state
+        if st is not None and st.get('key') == key:
+            st['seq_lens'].zero_(); st['audio_pos'].zero_(); st['last'].zero_(); st['sum_logprobs'].zero_()
+            st['codes_out'].zero_()
+            st['state'][:, 0].zero_(); st['state'][:, 1].fill_(-1)
+            return st
+        st = {'B': B, 'max_pages': max_pages, 'max_new': max_new, 'key': key}
         st['pools'] = torch.zeros(L, B * max_pages, 2, H, PAGE, self.Dh, device=dev, dtype=self.cd)
         if self.page_permutation_seed is None:
             table = torch.arange(B * max_pages, dtype=torch.int32)
@@ -274,11 +295,13 @@ class ARDecoder:
         n_sub = self._n_sub(B)
         st['state'] = torch.tensor([[0, -1]] * n_sub, device=dev, dtype=torch.int32)     # per sub-batch {step, stop_step}
         bounds = [(B * i) // n_sub for i in range(n_sub + 1)]
+        self._state = None
+        self._graph = None                 # release the old pools / graph before the new ones are allocated
+        self._graph_key = None
         st['subs'] = [self._make_sub(st, bounds[i], bounds[i + 1], st['state'][i]) for i in range(n_sub)]
         while len(self._streams) < n_sub:
             self._streams.append(torch.cuda.Stream(device=dev))
         self._state = st
-        self._graph = None
         return st
 
     # ------------------------------------------------------------------------------------------
@@ -355,9 +378,15 @@ class ARDecoder:
             qkv32 = sub['r_qkv'][0]
             for li, L in enumerate(layers):
                 g, b, eps = L['norm1']
-                ops.linear_decode_rows_ln(x, L['wqkv'], qkv32, gamma=g[0], beta=b[0], eps=eps, flags=ops.FLAG_LATE_TRIGGER)
+                # Layer 0 releases the attention kernel only after its own dependency has resolved (late trigger): attention
+                # reads seq_lens and KV pages BEFORE it waits, and the previous step's bookkeeping must have finished by then.
+                # Deeper layers release it at once -- seq_lens is final since the step began and the layer's pages were
+                # appended a whole step ago -- so its page copies are in flight while the QKV GEMM still runs.
+                ops.linear_decode_rows_ln(x, L['wqkv'], qkv32, gamma=g[0], beta=b[0], eps=eps,
+                                          flags=ops.FLAG_LATE_TRIGGER if (li == 0 or self.qkv_late_all) else 0)
                 ops.attn_decode_paged(qkv32, 1, 0, st['pools'][li], sub['block_table'], sub['seq_lens'], sub['o'],
-                                      B, H, Dh, sub['n_tsplit'], sub['attn_ws'], ops.FLAG_PREFETCH_KV | self.attn_flags)
+                                      B, H, Dh, sub['n_tsplit'], sub['attn_ws'],
+                                      ops.FLAG_PREFETCH_KV | self.attn_flags | (self.attn_late if B >= 4 else 0))
                 ops.linear_decode_rows(sub['o'], L['wo'], x, bias=L['bo'], residual=True)
                 g, b, eps = L['norm2']
                 ops.linear_decode_rows_ln(x, L['w1'], sub['f'], gamma=g[0], beta=b[0], eps=eps, bias=L['b1'], gelu=True)
@@ -591,14 +620,22 @@ class ARDecoder:
         graph = None
         step = 1
         if use_graph and uniforms is None and max_new > 2:
-            self.decode_step(samp, None, eos)           # warm-up (also loads modules, sets func attributes)
-            step += 1
-            torch.cuda.synchronize()
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
-                self.decode_step(samp, None, eos)
-            # capture does not execute: the captured step still has to be replayed for this position
-        self._graph = graph
+            # the captured step bakes in the state's buffers and the sampling scalars: reuse it while they are the same
+            gkey = (st['key'], temperature, top_k, top_p, seed, eos)
+            if self._graph is not None and self._graph_key == gkey:
+                graph = self._graph
+            else:
+                self._graph = None
+                self.decode_step(samp, None, eos)           # warm-up (also loads modules, sets func attributes)
+                step += 1
+                torch.cuda.synchronize()
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    self.decode_step(samp, None, eos)
+                # capture does not execute: the captured step still has to be replayed for this position
+                self._graph, self._graph_key = graph, gkey
+        else:
+            self._graph, self._graph_key = None, None
         while step < max_new:
             if graph is not None:
                 graph.replay()
@@ -613,7 +650,7 @@ class ARDecoder:
         stops = [s[1] for s in state]
         s_stop = max(stops) if min(stops) >= 0 else -1
         n = s_stop if s_stop >= 0 else min(s_now, max_new)
-        return st['codes_out'][:, :n], st['sum_logprobs'].clone(), n
+        return st['codes_out'][:, :n].clone(), st['sum_logprobs'].clone(), n      # the state's buffers are reused by the next call
 
 
 class NARDecoder:
