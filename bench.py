@@ -406,8 +406,8 @@ def extras(args, dev, tmp):
         batch = {'tokens': torch.randint(0, 256, (Bt, Txt), generator=g), 'tokens_lens': torch.full((Bt,), Txt),
                  'codes': torch.randint(0, 1024, (Bt, Tyt), generator=g), 'codes_lens': torch.full((Bt,), Tyt),
                  'target': torch.randint(0, 1025, (Bt, Tyt), generator=g)}
-        for it in range(3):
-            if it == 1:
+        for it in range(6):             # three warm-up steps (allocator growth, first-use kernel loads), three timed
+            if it == 3:
                 torch.cuda.synchronize()
                 e0.record()
             for p_ in ar.parameters():
@@ -416,7 +416,7 @@ def extras(args, dev, tmp):
             loss.backward()
         e1.record()
         torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / 2
+        ms = e0.elapsed_time(e1) / 3
         S, d, F, L = Txt + Tyt, 1024, 4096, 12
         fwd = Bt * (L * (S * 2 * (4 * d * d + 2 * d * F) + 4 * S * S * d) + 2 * Tyt * d * 1025)
         out['train_step'] = {'batch': Bt, 'seq': S, 'ms_per_step': ms, 'clips_per_s': Bt / (ms * 1e-3), 'loss': float(loss),
