@@ -204,9 +204,11 @@ int vb_attention(const void* q, const void* k, const void* v, int dtype,
                  const uint8_t* mask, int64_t m_sb, int64_t m_sh, int64_t m_sq, void* stream);
 
 /* Flash-style tensor-core attention for prefill / NAR over a packed qkv buffer [B][S][3][H][64] (bf16).
- * Same mask semantics as vb_attention (NONE / PREFIX_LM).  o: bf16 [B][S][H*64]. */
+ * Same mask semantics as vb_attention (NONE / PREFIX_LM).  o: bf16 [B][S][H*64].
+ * lse (nullable): fp32 [B][H][S] receives the log-sum-exp of every query row's scaled scores (+inf for a row that attends
+ * nothing) -- saved by the training forward so that vb_attention_bwd does not recompute it. */
 int vb_attention_prefill_tc(const void* qkv, void* o, int B, int S, int H, int mask_mode,
-                            const int32_t* x_lens, const int32_t* kv_lens, void* stream);
+                            const int32_t* x_lens, const int32_t* kv_lens, float* lse, void* stream);
 
 /* Paged KV pool layout (one pool per layer): [page][2 (K,V)][H][page_size=64][Dh=64], dtype f32 or bf16.
  * bf16 pools with Dh = 64 store the eight 16-byte chunks of a token row XOR-swizzled: chunk c of token slot t sits at
@@ -258,9 +260,11 @@ int vb_layernorm_bwd_blocks(int64_t R);
 int vb_layernorm_bwd(const float* x, const float* gamma, const void* dy, int dy_dtype, float* dx, float* dgamma_part,
                      float* dbeta_part, int64_t R, int d, float eps, void* stream);
 /* Attention backward over packed qkv rows [B*S][3][H][64] (dtype f32/bf16): dqkv from dO, o; lse/delta are fp32 [B][H][S]
- * work buffers.  mask_mode VB_MASK_NONE or VB_MASK_PREFIX_LM with the forward's predicate (x_lens, kv_lens). */
+ * work buffers.  mask_mode VB_MASK_NONE or VB_MASK_PREFIX_LM with the forward's predicate (x_lens, kv_lens).
+ * lse_is_input != 0 (bf16 only): lse already holds the forward's log-sum-exp (vb_attention_prefill_tc) and is not recomputed. */
 int vb_attention_bwd(const void* qkv, const void* o, const void* dO, void* dqkv, int dtype, float* lse, float* delta, int B,
-                     int S, int H, int Dh, int mask_mode, const int32_t* x_lens, const int32_t* kv_lens, void* stream);
+                     int S, int H, int Dh, int mask_mode, const int32_t* x_lens, const int32_t* kv_lens, int lse_is_input,
+                     void* stream);
 /* loss_rows[r] = logsumexp(logits[r]) - logits[r][target[r]];  dlogits[r] = (softmax(logits[r]) - onehot) * scale (nullable) */
 int vb_cross_entropy(const float* logits, int64_t ld, const int32_t* target, int64_t R, int V, float* loss_rows,
                      float* dlogits, int64_t ldd, float scale, void* stream);

@@ -260,3 +260,37 @@ def test_collated_batch_feeds_training_step(tmp_path):
     ref = vo.ar_teacher_forced(sd, oc, batch['tokens'], batch['codes'], batch['tokens_lens'], batch['codes_lens'], batch['target'])[1]
     loss = model.training_step(batch)
     assert abs(loss.item() - ref.item()) < 1e-4
+
+
+@pytest.mark.parametrize('mode', ['none', 'prefix'])
+def test_forward_lse_feeds_attention_backward(ops, mode):
+    """The tensor-core forward's log-sum-exp (vb_attention_prefill_tc lse output) against a float64 softmax of the same
+    bf16 q, k, and attention_bwd with that lse against attention_bwd recomputing it: same gradients to bf16 round-off."""
+    torch.manual_seed(31)
+    B, S, H, Dh = 2, 200, 4, 64
+    d = H * Dh
+    qkv = (torch.randn(B * S, 3 * d, device='cuda') * 0.7).bfloat16()
+    o = torch.empty(B * S, d, device='cuda', dtype=torch.bfloat16)
+    lse = torch.full((B, H, S), float('nan'), device='cuda')
+    x_lens = torch.tensor([37, 90], device='cuda', dtype=torch.int32) if mode == 'prefix' else None
+    kv_lens = torch.tensor([200, 161], device='cuda', dtype=torch.int32)
+    mm = ops.MASK_PREFIX_LM if mode == 'prefix' else ops.MASK_NONE
+    ops.attention_packed(qkv, o, B, S, H, mask_mode=mm, x_lens=x_lens, kv_lens=kv_lens, use_tc=True, lse=lse)
+    q, k = qkv.view(B, S, 3, H, Dh)[:, :, 0].double(), qkv.view(B, S, 3, H, Dh)[:, :, 1].double()
+    s = torch.einsum('bihd,bjhd->bhij', q, k) / math.sqrt(Dh)
+    i, j = torch.arange(S, device='cuda')[:, None], torch.arange(S, device='cuda')[None, :]
+    for b in range(B):
+        ok = j < int(kv_lens[b])
+        if mode == 'prefix':
+            xl = int(x_lens[b])
+            ok = ok & ((j < xl) | ((i >= xl) & (j <= i)))
+        s[b].masked_fill_(~ok[None], float('-inf'))
+    ref = torch.logsumexp(s, dim=-1)
+    assert not torch.isnan(lse).any()
+    assert (lse.double() - ref).abs().max().item() < 2e-3
+    do = (torch.randn(B * S, d, device='cuda') * 0.5).bfloat16()
+    g_saved, g_recomp = torch.zeros_like(qkv), torch.zeros_like(qkv)
+    ops.attention_bwd(qkv, o, do, g_saved, B, S, H, mask_mode=mm, x_lens=x_lens, kv_lens=kv_lens, lse=lse)
+    ops.attention_bwd(qkv, o, do, g_recomp, B, S, H, mask_mode=mm, x_lens=x_lens, kv_lens=kv_lens)
+    scale = g_recomp.float().abs().max().item()
+    assert (g_saved.float() - g_recomp.float()).abs().max().item() < 2e-2 * scale

@@ -41,7 +41,7 @@ SIGNATURES = {
     'vb_gelu_bwd': (_i, [_p, _p, _i, _p, _i64, _p]),
     'vb_layernorm_bwd_blocks': (_i, [_i64]),
     'vb_layernorm_bwd': (_i, [_p, _p, _p, _i, _p, _p, _p, _i64, _i, _f, _p]),
-    'vb_attention_bwd': (_i, [_p, _p, _p, _p, _i, _p, _p, _i, _i, _i, _i, _i, _p, _p, _p]),
+    'vb_attention_bwd': (_i, [_p, _p, _p, _p, _i, _p, _p, _i, _i, _i, _i, _i, _p, _p, _i, _p]),
     'vb_cross_entropy': (_i, [_p, _i64, _p, _i64, _i, _p, _p, _i64, _f, _p]),
     'vb_embed_bwd': (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i64, _i64, _p]),
     'vb_decode_chain': (_i, [_p, _i, _i, _p, _p]),
@@ -51,7 +51,7 @@ SIGNATURES = {
     'vb_linear_decode_rows_set_debug': (_i, [_p]),
     'vb_attention': (_i, [_p, _p, _p, _i, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _p, _i, _i64, _i64,
                           _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _i64, _i64, _i64, _p]),
-    'vb_attention_prefill_tc': (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _p]),
+    'vb_attention_prefill_tc': (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _p, _p]),
     'vb_kv_scatter_paged': (_i, [_p, _i, _p, _i, _p, _i, _p, _i, _i, _i, _i, _p]),
     'vb_attn_decode_ws_bytes': (_i64, [_i, _i, _i]),
     'vb_attn_decode_paged': (_i, [_p, _i, _i64, _p, _i, _p, _i, _p, _p, _i, _i, _i, _i, _i, _i, _p, _p]),

@@ -39,7 +39,8 @@ __global__ void __launch_bounds__(THREADS, 3) attn_prefill_tc_kernel(const __gri
                                                                      const __grid_constant__ CUtensorMap tm_kv,
                                                                      __nv_bfloat16* __restrict__ o, int S, int H, int mask_mode,
                                                                      const int32_t* __restrict__ x_lens,
-                                                                     const int32_t* __restrict__ kv_lens, float scale_log2e) {
+                                                                     const int32_t* __restrict__ kv_lens, float scale_log2e,
+                                                                     float* __restrict__ lse) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bar_q, bar_s, bar_sfree, bar_p, bar_o;
     __shared__ __align__(8) uint64_t kv_full[KV_STAGES], kv_empty[KV_STAGES];
@@ -258,6 +259,10 @@ __global__ void __launch_bounds__(THREADS, 3) attn_prefill_tc_kernel(const __gri
         mbar_wait(smem_u32(&bar_o), (nb - 1) & 1);
         tc_fence_after();
         const float inv = (l_run > 0.f) ? 1.f / l_run : 0.f;
+        // optional: log-sum-exp of the scaled scores (natural log) for the backward pass -- any reference m_ref gives the
+        // same value, so the lazy rescaling does not matter; +inf marks a row that attends nothing
+        if (lse != nullptr && i < S)
+            lse[(static_cast<int64_t>(b) * H + h) * S + i] = (l_run > 0.f) ? (m_ref + log2f(l_run)) * 0.69314718055994531f : INFINITY;
         __nv_bfloat16* orow = o + (static_cast<int64_t>(row0) + i) * d + h * DH;
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
@@ -288,7 +293,7 @@ __global__ void __launch_bounds__(THREADS, 3) attn_prefill_tc_kernel(const __gri
 }  // namespace
 
 extern "C" int vb_attention_prefill_tc(const void* qkv, void* o, int B, int S, int H, int mask_mode, const int32_t* x_lens,
-                                       const int32_t* kv_lens, void* stream) {
+                                       const int32_t* kv_lens, float* lse, void* stream) {
     VB_REQUIRE(qkv && o, VB_ERR_BAD_ARG, "vb_attention_prefill_tc: null pointer");
     VB_REQUIRE(B >= 1 && S >= 1 && H >= 1 && B <= 65535 && H <= 65535, VB_ERR_BAD_ARG, "vb_attention_prefill_tc: bad shape");
     VB_REQUIRE(mask_mode == VB_MASK_NONE || mask_mode == VB_MASK_PREFIX_LM, VB_ERR_UNSUPPORTED,
@@ -308,6 +313,6 @@ extern "C" int vb_attention_prefill_tc(const void* qkv, void* o, int B, int S, i
     dim3 grid(static_cast<unsigned>(vb_ceil_div(S, BQ)), H, B);
     const float scale_log2e = 1.4426950408889634f / sqrtf(static_cast<float>(DH));
     VB_CUDA(vb_launch(false, attn_prefill_tc_kernel, grid, dim3(THREADS), SMEM_BYTES, static_cast<cudaStream_t>(stream), tq, tkv,
-                      static_cast<__nv_bfloat16*>(o), S, H, mask_mode, x_lens, kv_lens, scale_log2e));
+                      static_cast<__nv_bfloat16*>(o), S, H, mask_mode, x_lens, kv_lens, scale_log2e, lse));
     return VB_OK;
 }

@@ -526,7 +526,7 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_mma_kernel(const __nv_bfloat1
                                                               const __nv_bfloat16* __restrict__ dO, __nv_bfloat16* __restrict__ dqkv,
                                                               float* __restrict__ lse, float* __restrict__ delta, int S, int H,
                                                               int mask_mode, const int32_t* __restrict__ x_lens,
-                                                              const int32_t* __restrict__ kv_lens, float scale) {
+                                                              const int32_t* __restrict__ kv_lens, float scale, int lse_in) {
     __shared__ __align__(128) uint8_t tiles[4][TS * 128];      // Q, dO, K, V
     __shared__ float delta_s[TS];
     const uint32_t Qs = smem_u32(tiles[0]), dOs = smem_u32(tiles[1]), Ks = smem_u32(tiles[2]), Vs = smem_u32(tiles[3]);
@@ -566,45 +566,53 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_mma_kernel(const __nv_bfloat1
     const int i_max = min(i0 + TS, S) - 1;
     int j_end = kv_len;
     if (mask_mode == VB_MASK_PREFIX_LM) j_end = min(kv_len, max(x_len, i_max + 1));
-    // pass 1: row max / sum
-    float ma = -INFINITY, mb = -INFINITY, la = 0.f, lb = 0.f;
-    for (int j0 = 0; j0 < j_end; j0 += TS) {
-        __syncthreads();
-        load_tile_bf16(Ks, qb + d, rp, j0, S);
-        __syncthreads();
-        float s[8][4];
-        mma_a_tt(s, qa, Ks, lane);
-        float mxa = -INFINITY, mxb = -INFINITY;
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                const int col = j0 + 8 * j + 2 * t + c;
-                s[j][c] = allowed(ra, col, kv_len, x_len, mask_mode) ? s[j][c] * scale : -INFINITY;
-                s[j][2 + c] = allowed(rb, col, kv_len, x_len, mask_mode) ? s[j][2 + c] * scale : -INFINITY;
-                mxa = fmaxf(mxa, s[j][c]);
-                mxb = fmaxf(mxb, s[j][2 + c]);
-            }
-        mxa = fmaxf(mxa, __shfl_xor_sync(0xffffffffu, mxa, 1)); mxa = fmaxf(mxa, __shfl_xor_sync(0xffffffffu, mxa, 2));
-        mxb = fmaxf(mxb, __shfl_xor_sync(0xffffffffu, mxb, 1)); mxb = fmaxf(mxb, __shfl_xor_sync(0xffffffffu, mxb, 2));
-        const float na = fmaxf(ma, mxa), nb = fmaxf(mb, mxb);
-        float pa = 0.f, pb = 0.f;
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                pa += (s[j][c] == -INFINITY) ? 0.f : expf(s[j][c] - na);
-                pb += (s[j][2 + c] == -INFINITY) ? 0.f : expf(s[j][2 + c] - nb);
-            }
-        pa += __shfl_xor_sync(0xffffffffu, pa, 1); pa += __shfl_xor_sync(0xffffffffu, pa, 2);
-        pb += __shfl_xor_sync(0xffffffffu, pb, 1); pb += __shfl_xor_sync(0xffffffffu, pb, 2);
-        if (na != -INFINITY) { la = la * ((ma == -INFINITY) ? 0.f : expf(ma - na)) + pa; ma = na; }
-        if (nb != -INFINITY) { lb = lb * ((mb == -INFINITY) ? 0.f : expf(mb - nb)) + pb; mb = nb; }
-    }
-    const float lsa = (la > 0.f) ? ma + logf(la) : INFINITY, lsb = (lb > 0.f) ? mb + logf(lb) : INFINITY;
-    if (t == 0) {
-        if (ra < S) lse[(static_cast<int64_t>(b) * H + h) * S + ra] = lsa;
-        if (rb < S) lse[(static_cast<int64_t>(b) * H + h) * S + rb] = lsb;
+    // pass 1: row max / sum -- skipped when the forward pass saved the log-sum-exp (lse_in): one of the four tile products
+    // and an exp per score less
+    float lsa, lsb;
+    if (lse_in) {
+        lsa = (ra < S) ? lse[(static_cast<int64_t>(b) * H + h) * S + ra] : INFINITY;
+        lsb = (rb < S) ? lse[(static_cast<int64_t>(b) * H + h) * S + rb] : INFINITY;
+    } else {
+        float ma = -INFINITY, mb = -INFINITY, la = 0.f, lb = 0.f;
+        for (int j0 = 0; j0 < j_end; j0 += TS) {
+            __syncthreads();
+            load_tile_bf16(Ks, qb + d, rp, j0, S);
+            __syncthreads();
+            float s[8][4];
+            mma_a_tt(s, qa, Ks, lane);
+            float mxa = -INFINITY, mxb = -INFINITY;
+    #pragma unroll
+            for (int j = 0; j < 8; ++j)
+    #pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    const int col = j0 + 8 * j + 2 * t + c;
+                    s[j][c] = allowed(ra, col, kv_len, x_len, mask_mode) ? s[j][c] * scale : -INFINITY;
+                    s[j][2 + c] = allowed(rb, col, kv_len, x_len, mask_mode) ? s[j][2 + c] * scale : -INFINITY;
+                    mxa = fmaxf(mxa, s[j][c]);
+                    mxb = fmaxf(mxb, s[j][2 + c]);
+                }
+            mxa = fmaxf(mxa, __shfl_xor_sync(0xffffffffu, mxa, 1)); mxa = fmaxf(mxa, __shfl_xor_sync(0xffffffffu, mxa, 2));
+            mxb = fmaxf(mxb, __shfl_xor_sync(0xffffffffu, mxb, 1)); mxb = fmaxf(mxb, __shfl_xor_sync(0xffffffffu, mxb, 2));
+            const float na = fmaxf(ma, mxa), nb = fmaxf(mb, mxb);
+            float pa = 0.f, pb = 0.f;
+    #pragma unroll
+            for (int j = 0; j < 8; ++j)
+    #pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    pa += (s[j][c] == -INFINITY) ? 0.f : expf(s[j][c] - na);
+                    pb += (s[j][2 + c] == -INFINITY) ? 0.f : expf(s[j][2 + c] - nb);
+                }
+            pa += __shfl_xor_sync(0xffffffffu, pa, 1); pa += __shfl_xor_sync(0xffffffffu, pa, 2);
+            pb += __shfl_xor_sync(0xffffffffu, pb, 1); pb += __shfl_xor_sync(0xffffffffu, pb, 2);
+            if (na != -INFINITY) { la = la * ((ma == -INFINITY) ? 0.f : expf(ma - na)) + pa; ma = na; }
+            if (nb != -INFINITY) { lb = lb * ((mb == -INFINITY) ? 0.f : expf(mb - nb)) + pb; mb = nb; }
+        }
+        lsa = (la > 0.f) ? ma + logf(la) : INFINITY;
+        lsb = (lb > 0.f) ? mb + logf(lb) : INFINITY;
+        if (t == 0) {
+            if (ra < S) lse[(static_cast<int64_t>(b) * H + h) * S + ra] = lsa;
+            if (rb < S) lse[(static_cast<int64_t>(b) * H + h) * S + rb] = lsb;
+        }
     }
     // pass 2: dQ
     float dq[8][4];
@@ -875,7 +883,8 @@ extern "C" int vb_layernorm_bwd(const float* x, const float* gamma, const void* 
 }
 
 extern "C" int vb_attention_bwd(const void* qkv, const void* o, const void* dO, void* dqkv, int dtype, float* lse, float* delta, int B,
-                                int S, int H, int Dh, int mask_mode, const int32_t* x_lens, const int32_t* kv_lens, void* stream) {
+                                int S, int H, int Dh, int mask_mode, const int32_t* x_lens, const int32_t* kv_lens, int lse_is_input,
+                                void* stream) {
     VB_REQUIRE(qkv && o && dO && dqkv && lse && delta, VB_ERR_BAD_ARG, "vb_attention_bwd: null pointer");
     VB_REQUIRE(Dh == 64, VB_ERR_UNSUPPORTED, "vb_attention_bwd: head_dim must be 64 (got %d)", Dh);
     VB_REQUIRE(mask_mode == VB_MASK_NONE || mask_mode == VB_MASK_PREFIX_LM, VB_ERR_UNSUPPORTED, "vb_attention_bwd: mask mode %d", mask_mode);
@@ -900,6 +909,8 @@ extern "C" int vb_attention_bwd(const void* qkv, const void* o, const void* dO, 
             static_cast<T*>(dqkv), lse, delta, S, H, mask_mode, x_lens, kv_lens, scale);                                   \
     }
     static const bool force_simt = (getenv("VALLE_B200_ATTN_BWD_SIMT") != nullptr && getenv("VALLE_B200_ATTN_BWD_SIMT")[0] == '1');
+    VB_REQUIRE(!lse_is_input || (dtype == VB_BF16 && !force_simt), VB_ERR_UNSUPPORTED,
+               "vb_attention_bwd: a saved lse is only taken by the bf16 tensor-core kernels");
     if (dtype == VB_F32) ABW(float)
     else if (dtype == VB_BF16 && force_simt) ABW(__nv_bfloat16)
     else if (dtype == VB_BF16) {
@@ -908,7 +919,7 @@ extern "C" int vb_attention_bwd(const void* qkv, const void* o, const void* dO, 
                    VB_ERR_BAD_ARG, "vb_attention_bwd: bf16 operands must be 16-byte aligned");
         const __nv_bfloat16* q16 = static_cast<const __nv_bfloat16*>(qkv);
         attn_bwd_dq_mma_kernel<<<grid, 128, 0, st>>>(q16, static_cast<const __nv_bfloat16*>(o), static_cast<const __nv_bfloat16*>(dO),
-                                                     static_cast<__nv_bfloat16*>(dqkv), lse, delta, S, H, mask_mode, x_lens, kv_lens, scale);
+                                                     static_cast<__nv_bfloat16*>(dqkv), lse, delta, S, H, mask_mode, x_lens, kv_lens, scale, lse_is_input);
         attn_bwd_dkv_mma_kernel<<<grid, 128, 0, st>>>(q16, static_cast<const __nv_bfloat16*>(dO), static_cast<__nv_bfloat16*>(dqkv), lse,
                                                       delta, S, H, mask_mode, x_lens, kv_lens, scale);
     }

@@ -241,15 +241,19 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tens
 
 
 def attention_packed(qkv: torch.Tensor, out: torch.Tensor, B: int, S: int, H: int, *, mask_mode: int,
-                     x_lens: torch.Tensor | None, kv_lens: torch.Tensor | None, use_tc: bool = False) -> torch.Tensor:
-    """Self-attention over a packed (B*S, 3*H*Dh) qkv buffer; out (B*S, H*Dh)."""
+                     x_lens: torch.Tensor | None, kv_lens: torch.Tensor | None, use_tc: bool = False,
+                     lse: torch.Tensor | None = None) -> torch.Tensor:
+    """Self-attention over a packed (B*S, 3*H*Dh) qkv buffer; out (B*S, H*Dh).  lse (B, H, S) fp32, tensor-core path only:
+    receives the rows' log-sum-exp for attention_bwd."""
     d3 = qkv.shape[1]
     d = d3 // 3
     Dh = d // H
     if use_tc:
+        assert lse is None or (lse.dtype == torch.float32 and lse.is_contiguous() and lse.numel() == B * H * S)
         check(_L().vb_attention_prefill_tc(_ptr(qkv), _ptr(out), B, S, H, mask_mode, _ptr(x_lens), _ptr(kv_lens),
-                                           _stream()), 'vb_attention_prefill_tc')
+                                           _ptr(lse), _stream()), 'vb_attention_prefill_tc')
         return out
+    assert lse is None, 'lse is produced by the tensor-core attention only'
     base = qkv.view(B, S, 3, H, Dh)
     q = base[:, :, 0].permute(0, 2, 1, 3)
     k = base[:, :, 1].permute(0, 2, 1, 3)
@@ -391,15 +395,20 @@ def layernorm_bwd(x: torch.Tensor, gamma: torch.Tensor | None, dy: torch.Tensor,
 
 
 def attention_bwd(qkv: torch.Tensor, o: torch.Tensor, do: torch.Tensor, dqkv: torch.Tensor, B: int, S: int, H: int, *,
-                  mask_mode: int, x_lens: torch.Tensor | None, kv_lens: torch.Tensor | None) -> torch.Tensor:
-    """Packed rows: qkv / dqkv (B*S, 3*H*64), o / do (B*S, H*64), all the same dtype."""
+                  mask_mode: int, x_lens: torch.Tensor | None, kv_lens: torch.Tensor | None,
+                  lse: torch.Tensor | None = None) -> torch.Tensor:
+    """Packed rows: qkv / dqkv (B*S, 3*H*64), o / do (B*S, H*64), all the same dtype.  lse (B, H, S) fp32: the forward's
+    log-sum-exp (attention_packed(..., lse=)); without it the backward recomputes it."""
     d = o.shape[1]
     assert qkv.dtype == o.dtype == do.dtype == dqkv.dtype and qkv.is_contiguous() and o.is_contiguous() and do.is_contiguous()
     assert dqkv.is_contiguous() and qkv.shape[1] == 3 * d
-    lse = torch.empty(B, H, S, device=qkv.device, dtype=torch.float32)
+    lse_in = lse is not None
+    if lse is None:
+        lse = torch.empty(B, H, S, device=qkv.device, dtype=torch.float32)
+    assert lse.dtype == torch.float32 and lse.is_contiguous() and lse.numel() == B * H * S
     delta = torch.empty(B, H, S, device=qkv.device, dtype=torch.float32)
     check(_L().vb_attention_bwd(_ptr(qkv), _ptr(o), _ptr(do), _ptr(dqkv), _code(qkv.dtype), _ptr(lse), _ptr(delta), B, S, H,
-                                d // H, mask_mode, _ptr(x_lens), _ptr(kv_lens), _stream()), 'vb_attention_bwd')
+                                d // H, mask_mode, _ptr(x_lens), _ptr(kv_lens), int(lse_in), _stream()), 'vb_attention_bwd')
     return dqkv
 
 

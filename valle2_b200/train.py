@@ -18,6 +18,8 @@ Dropout is not applied (the parity configuration: ``dropout=0`` and PE dropout z
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import ops
@@ -66,6 +68,9 @@ class StackTrainer:
         self.cd = _cd(precision)
         self.H = n_heads
         self.norm = norm
+        # the tensor-core forward hands its log-sum-exp to the backward kernels (VALLE_B200_SAVE_LSE=0: recompute it there;
+        # the SIMT backward of VALLE_B200_ATTN_BWD_SIMT=1 always recomputes)
+        self.save_lse = (os.environ.get('VALLE_B200_SAVE_LSE', '1') != '0' and os.environ.get('VALLE_B200_ATTN_BWD_SIMT', '0') != '1')
         self.layers = []
         for layer in transformer.layers:
             a, f = layer.self_attn, layer.ffn
@@ -113,7 +118,10 @@ class StackTrainer:
             c['qkv'] = torch.zeros(Rp, 3 * d, device=dev, dtype=cd)
             _linear_fwd(c['h1'][:R], L['qkv'], out=c['qkv'][:R])
             c['o'] = torch.zeros(Rp, d, device=dev, dtype=cd)
-            ops.attention_packed(c['qkv'][:R], c['o'][:R], B, S, H, mask_mode=mask_mode, x_lens=x_lens, kv_lens=kv_lens, use_tc=use_tc)
+            # the tensor-core forward also leaves the rows' log-sum-exp for the backward pass (5.5 KB per head and sequence)
+            c['lse'] = torch.empty(B, H, S, device=dev, dtype=torch.float32) if (use_tc and self.save_lse) else None
+            ops.attention_packed(c['qkv'][:R], c['o'][:R], B, S, H, mask_mode=mask_mode, x_lens=x_lens, kv_lens=kv_lens, use_tc=use_tc,
+                                 lse=c['lse'])
             _linear_fwd(c['o'][:R], L['o'], residual=x[:R], out=x[:R])
             g2, b2, c['fold2'] = self._affine(L, 'norm2', stage)
             c['g2'] = g2
@@ -161,7 +169,8 @@ class StackTrainer:
             do = torch.zeros(Rp, d, device=dev, dtype=cd)
             ops.linear(dxb[:R], L['o'].wt, out=do[:R])
             dqkv = torch.zeros(Rp, 3 * d, device=dev, dtype=cd)
-            ops.attention_bwd(c['qkv'][:R], c['o'][:R], do[:R], dqkv[:R], B, S, H, mask_mode=mask_mode, x_lens=x_lens, kv_lens=kv_lens)
+            ops.attention_bwd(c['qkv'][:R], c['o'][:R], do[:R], dqkv[:R], B, S, H, mask_mode=mask_mode, x_lens=x_lens, kv_lens=kv_lens,
+                              lse=c.get('lse'))
             g['qkv.w'] = _wgrad(ops.transpose(dqkv), ops.transpose(c['h1']))       # (3d, d)
             ops.linear(dqkv[:R], L['qkv'].wt, out=dh[:R])
             g['n1.g'], g['n1.b'] = ops.layernorm_bwd(c['x_in'][:R], c['g1'], dh[:R], dx[:R], L['norm1']['eps'])
