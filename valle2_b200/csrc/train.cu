@@ -475,6 +475,19 @@ __device__ __forceinline__ void load_tile_bf16(uint32_t dst, const __nv_bfloat16
         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + r * 128 + ((ch ^ (r & 7)) << 4)), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
     }
 }
+// the same tile, asynchronously (cp.async, 16 bytes per request, zero fill past n_rows): issue, commit a group, and wait
+// for it one loop iteration later, so that the next key / query tile is in flight while the current one is multiplied
+__device__ __forceinline__ void issue_tile_bf16(uint32_t dst, const __nv_bfloat16* __restrict__ src, int64_t pitch, int row0, int n_rows) {
+    for (int idx = threadIdx.x; idx < 512; idx += 128) {
+        const int r = idx >> 3, ch = idx & 7;
+        const bool in = row0 + r < n_rows;
+        const __nv_bfloat16* p = src + static_cast<int64_t>(in ? row0 + r : 0) * pitch + ch * 8;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + r * 128 + ((ch ^ (r & 7)) << 4)), "l"(p), "r"(in ? 16 : 0) : "memory");
+    }
+}
+__device__ __forceinline__ void async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 // A fragments (4 k-steps of 16) of rows [r0, r0 + 16) of a tile
 __device__ __forceinline__ void load_a_frags(uint32_t tile, int r0, int lane, uint32_t (&a)[4][4]) {
     const int row = r0 + (lane & 15);
@@ -614,18 +627,30 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_mma_kernel(const __nv_bfloat1
             if (rb < S) lse[(static_cast<int64_t>(b) * H + h) * S + rb] = lsb;
         }
     }
-    // pass 2: dQ
+    // pass 2: dQ.  K and V tiles are double-buffered: the Q / dO tiles are dead once their fragments sit in registers, so
+    // tiles[0..1] serve as the second buffer and the copy of block j+1 (cp.async) overlaps the three products of block j.
     float dq[8][4];
 #pragma unroll
     for (int j = 0; j < 8; ++j) dq[j][0] = dq[j][1] = dq[j][2] = dq[j][3] = 0.f;
-    for (int j0 = 0; j0 < j_end; j0 += TS) {
-        __syncthreads();
-        load_tile_bf16(Ks, qb + d, rp, j0, S);
-        load_tile_bf16(Vs, qb + 2 * d, rp, j0, S);
-        __syncthreads();
+    __syncthreads();                                   // every warp holds its Q / dO fragments (and pass 1 is over)
+    if (j_end > 0) {
+        issue_tile_bf16(Ks, qb + d, rp, 0, S);
+        issue_tile_bf16(Vs, qb + 2 * d, rp, 0, S);
+        async_commit();
+    }
+    int buf = 0;
+    for (int j0 = 0; j0 < j_end; j0 += TS, buf ^= 1) {
+        const uint32_t Kc = buf ? Qs : Ks, Vc = buf ? dOs : Vs;
+        async_wait_all();
+        __syncthreads();                               // block j0 landed for everyone; everyone is done with block j0 - TS
+        if (j0 + TS < j_end) {
+            issue_tile_bf16(buf ? Ks : Qs, qb + d, rp, j0 + TS, S);
+            issue_tile_bf16(buf ? Vs : dOs, qb + 2 * d, rp, j0 + TS, S);
+            async_commit();
+        }
         float s[8][4], dp[8][4];
-        mma_a_tt(s, qa, Ks, lane);
-        mma_a_tt(dp, doa, Vs, lane);
+        mma_a_tt(s, qa, Kc, lane);
+        mma_a_tt(dp, doa, Vc, lane);
 #pragma unroll
         for (int j = 0; j < 8; ++j)
 #pragma unroll
@@ -638,7 +663,7 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_mma_kernel(const __nv_bfloat1
             }
         uint32_t dsa[4][4];
         acc_to_a(s, dsa);
-        mma_a_t_acc(dq, dsa, Ks, lane);
+        mma_a_t_acc(dq, dsa, Kc, lane);
     }
     __nv_bfloat16* dqb = dqkv + static_cast<int64_t>(b) * S * rp + h * TS;
 #pragma unroll
@@ -655,7 +680,7 @@ __global__ void __launch_bounds__(128) attn_bwd_dkv_mma_kernel(const __nv_bfloat
                                                                const int32_t* __restrict__ x_lens, const int32_t* __restrict__ kv_lens,
                                                                float scale) {
     __shared__ __align__(128) uint8_t tiles[4][TS * 128];      // K, V, Q, dO
-    __shared__ float lse_s[TS], dl_s[TS];
+    __shared__ float lse_s[2][TS], dl_s[2][TS];
     const uint32_t Ks = smem_u32(tiles[0]), Vs = smem_u32(tiles[1]), Qs = smem_u32(tiles[2]), dOs = smem_u32(tiles[3]);
     const int jt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
@@ -679,25 +704,42 @@ __global__ void __launch_bounds__(128) attn_bwd_dkv_mma_kernel(const __nv_bfloat
         load_a_frags(Vs, 16 * warp, lane, va);
         int i_begin = 0;
         if (mask_mode == VB_MASK_PREFIX_LM && j0 >= x_len) i_begin = j0;
-        for (int i0 = i_begin; i0 < S; i0 += TS) {
-            __syncthreads();
-            load_tile_bf16(Qs, qb, rp, i0, S);
-            load_tile_bf16(dOs, dob, d, i0, S);
+        // Q / dO tiles are double-buffered (cp.async): the K / V tiles are dead once their fragments sit in registers, so
+        // tiles[0..1] serve as the second buffer; lse / delta rows of the tile ride along in lse_s / dl_s [2][TS]
+        auto stage_rows = [&](int bsel, int i0) {
             if (threadIdx.x < TS) {
                 const int i = i0 + threadIdx.x;
-                lse_s[threadIdx.x] = (i < S) ? lse[(static_cast<int64_t>(b) * H + h) * S + i] : INFINITY;
-                dl_s[threadIdx.x] = (i < S) ? delta[(static_cast<int64_t>(b) * H + h) * S + i] : 0.f;
+                lse_s[bsel][threadIdx.x] = (i < S) ? lse[(static_cast<int64_t>(b) * H + h) * S + i] : INFINITY;
+                dl_s[bsel][threadIdx.x] = (i < S) ? delta[(static_cast<int64_t>(b) * H + h) * S + i] : 0.f;
             }
-            __syncthreads();
+        };
+        __syncthreads();                               // every warp holds its K / V fragments
+        if (i_begin < S) {
+            issue_tile_bf16(Qs, qb, rp, i_begin, S);
+            issue_tile_bf16(dOs, dob, d, i_begin, S);
+            async_commit();
+            stage_rows(0, i_begin);
+        }
+        int buf = 0;
+        for (int i0 = i_begin; i0 < S; i0 += TS, buf ^= 1) {
+            const uint32_t Qc = buf ? Ks : Qs, dOc = buf ? Vs : dOs;
+            async_wait_all();
+            __syncthreads();                           // tile i0 landed for everyone; everyone is done with tile i0 - TS
+            if (i0 + TS < S) {
+                issue_tile_bf16(buf ? Qs : Ks, qb, rp, i0 + TS, S);
+                issue_tile_bf16(buf ? dOs : Vs, dob, d, i0 + TS, S);
+                async_commit();
+                stage_rows(buf ^ 1, i0 + TS);
+            }
             float st[8][4], dpt[8][4];                     // S^T and dP^T: rows = keys, columns = queries
-            mma_a_tt(st, ka, Qs, lane);
-            mma_a_tt(dpt, va, dOs, lane);
+            mma_a_tt(st, ka, Qc, lane);
+            mma_a_tt(dpt, va, dOc, lane);
 #pragma unroll
             for (int j = 0; j < 8; ++j)
 #pragma unroll
                 for (int c = 0; c < 2; ++c) {
                     const int qi = 8 * j + 2 * t + c, i = i0 + qi;
-                    const float li = lse_s[qi], di = dl_s[qi];
+                    const float li = lse_s[buf][qi], di = dl_s[buf][qi];
                     const bool oka = i < S && li != INFINITY && allowed(i, ka_row, kv_len, x_len, mask_mode);
                     const bool okb = i < S && li != INFINITY && allowed(i, kb_row, kv_len, x_len, mask_mode);
                     const float p0 = oka ? expf(st[j][c] * scale - li) : 0.f;
@@ -708,9 +750,9 @@ __global__ void __launch_bounds__(128) attn_bwd_dkv_mma_kernel(const __nv_bfloat
                 }
             uint32_t pa[4][4];
             acc_to_a(st, pa);
-            mma_a_t_acc(dv, pa, dOs, lane);       // dV[key][e] += sum_i P^T[key][i] dO[i][e]
+            mma_a_t_acc(dv, pa, dOc, lane);       // dV[key][e] += sum_i P^T[key][i] dO[i][e]
             acc_to_a(dpt, pa);
-            mma_a_t_acc(dk, pa, Qs, lane);        // dK[key][e] += sum_i dS^T[key][i] Q[i][e]
+            mma_a_t_acc(dk, pa, Qc, lane);        // dK[key][e] += sum_i dS^T[key][i] Q[i][e]
         }
     }
     __nv_bfloat16* dkb = dqkv + static_cast<int64_t>(b) * S * rp + h * TS + d;
