@@ -94,6 +94,15 @@ int vb_linear(const void* x, int x_dtype, int64_t ldx, const void* w, int w_dtyp
               const float* bias, const float* residual, int64_t ldr, void* y, int y_dtype, int64_t ldy,
               int64_t M, int64_t N, int64_t K, int epilogue, void* stream);
 
+/* The same bf16 tcgen05 GEMM with operands optionally given TRANSPOSED in memory (MN-major MMA operands, no copy):
+ *   x_transposed: x is [K][M] row-major (pitch ldx) instead of [M][K];  w_transposed: w is [K][N] (pitch ldw) instead of [N][K].
+ *   y[M,N] = epilogue(X . W^T) as for vb_linear.  Serves the backward pass of every nn.Linear of the path without a
+ *   transpose kernel: dgrad dx = dy . W reads W (N,K) as the transposed "w" of an (M,K_out=K) product, wgrad
+ *   dW = dy^T . x reads dy (R,N) and x (R,K) as transposed "x" and "w" of an (N,K) product over R.  N > 128, pitches % 8 == 0. */
+int vb_linear_t(const void* x, int64_t ldx, int x_transposed, const void* w, int64_t ldw, int w_transposed, const float* bias,
+                const float* residual, int64_t ldr, void* y, int y_dtype, int64_t ldy, int64_t M, int64_t N, int64_t K,
+                int epilogue, void* stream);
+
 /* Decode-shape (M <= 256) weight-streaming GEMM, swap-AB on tcgen05 with split-K:
  *   part[s][m][n] = sum_{k in slice s} x[m,k] w[n,k]      s < n_split, fp32, part_stride = elements between slices.
  * Deterministic: consumers (vb_residual_layernorm / vb_reduce_bias_act / vb_attn_decode_paged / vb_sample) add the

@@ -603,3 +603,23 @@ def test_ar_bookkeeping(ops):
     assert state.tolist() == [4, 3]
     ops.ar_bookkeeping(sample, logprob, last, slp, codes, seq, pos, state, eos)
     assert state.tolist() == [5, 3]          # the first all-EOS step is kept
+
+
+@pytest.mark.parametrize('x_t,w_t', [(False, True), (True, True), (True, False)])
+@pytest.mark.parametrize('M,N,K', [(304, 1024, 512), (1024, 4096, 21616), (1040, 1024, 21616), (3072, 1024, 700), (136, 256, 64)])
+def test_linear_transposed_operands(ops, x_t, w_t, M, N, K):
+    """vb_linear_t: MN-major MMA operands read straight from the row-major matrices the backward pass has (dgrad: W (N,K) as
+    transposed w; wgrad: dy (R,N) and x (R,K) as transposed x and w, contraction over R = 21 616 rows, ragged last k block)."""
+    torch.manual_seed(12)
+    K8 = (K + 7) // 8 * 8
+    X = (torch.randn(M, K, device='cuda') / math.sqrt(K)).bfloat16()
+    W = torch.randn(N, K, device='cuda').bfloat16()
+    x = X.t().contiguous() if x_t else X
+    w = W.t().contiguous() if w_t else W
+    if not x_t and K % 8:
+        pytest.skip('K-major operand needs K % 8 == 0')
+    if not w_t and K % 8:
+        pytest.skip('K-major operand needs K % 8 == 0')
+    y = ops.linear_t(x, w, x_t=x_t, w_t=w_t, out_dtype=torch.float32)
+    torch.cuda.synchronize()
+    assert rel_err(y, X.double() @ W.double().t()) < 1e-4

@@ -47,7 +47,11 @@ __device__ __forceinline__ unsigned long long gtimer() {
 // slots 8..14 (exact intervals inside one CTA)
 #define DBG_STAMP(i) do { if (p.dbg) { p.dbg[blockIdx.x * 16 + (i)] = gtimer(); p.dbg[blockIdx.x * 16 + 8 + (i)] = clock64(); } } while (0)
 
-template <int BN, int STAGES, bool SWAP>
+// A_MN / B_MN: the operand is given TRANSPOSED in memory -- [K][rows] row-major, i.e. MN-major for the MMA (the backward
+// GEMMs: dgrad reads W (N,K) as the MN-major B operand of dy.W, wgrad reads dy and x as MN-major A and B of dy^T.x, so no
+// operand is transposed in HBM first).  Tile = 64-wide MN atoms of [64 k rows][64 columns], 8 KB each, 128B-swizzled by
+// TMA; UMMA descriptor: start advances 2 KB per 16 k rows, LBO = atom pitch (8 KB), SBO = 8-row group pitch (1 KB).
+template <int BN, int STAGES, bool SWAP, bool A_MN = false, bool B_MN = false>
 __global__ void __launch_bounds__(num_threads(SWAP), 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a,
                                                                  const __grid_constant__ CUtensorMap tm_b, GemmParams p) {
     constexpr int A_BYTES = BM * BK * 2;
@@ -59,7 +63,8 @@ __global__ void __launch_bounds__(num_threads(SWAP), 1) gemm_tc_kernel(const __g
     constexpr int NACC = 1;
     constexpr int ACC_COLS = NACC * BN;             // TMEM columns of one (multi-)accumulator; two of them are in flight
     constexpr int TMEM_COLS = (2 * ACC_COLS <= 32) ? 32 : (2 * ACC_COLS <= 64) ? 64 : (2 * ACC_COLS <= 128) ? 128 : (2 * ACC_COLS <= 256) ? 256 : 512;
-    constexpr uint32_t IDESC = umma_idesc_bf16(BM, BN, 0, 0);
+    static_assert(!(SWAP && (A_MN || B_MN)), "MN-major operands are for the large-M orientation");
+    constexpr uint32_t IDESC = umma_idesc_bf16(BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
 
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[STAGES];
@@ -107,6 +112,22 @@ __global__ void __launch_bounds__(num_threads(SWAP), 1) gemm_tc_kernel(const __g
                 kb0 = split * p.kb_per_split;
                 kb1 = min(kb0 + p.kb_per_split, p.kb_total);
             };
+            auto load_a = [&](uint32_t dst, uint32_t fb, int kb, int ta) {
+                if constexpr (A_MN) {
+#pragma unroll
+                    for (int i = 0; i < BM / 64; ++i) tma_load_2d(dst + i * 8192, &tm_a, fb, ta * BM + i * 64, kb * BK);
+                } else {
+                    tma_load_2d(dst, &tm_a, fb, kb * BK, ta * BM);
+                }
+            };
+            auto load_b = [&](uint32_t dst, uint32_t fb, int kb, int tb) {
+                if constexpr (B_MN) {
+#pragma unroll
+                    for (int i = 0; i < BN / 64; ++i) tma_load_2d(dst + i * 8192, &tm_b, fb, tb * BN + i * 64, kb * BK);
+                } else {
+                    tma_load_2d(dst, &tm_b, fb, kb * BK, tb * BN);
+                }
+            };
             int pre = 0;   // ring slots already armed with their weight tile
             for (int t = blockIdx.x; t < total_tiles && pre < STAGES; t += gridDim.x) {
                 int ta, tb, kb0, kb1;
@@ -115,8 +136,8 @@ __global__ void __launch_bounds__(num_threads(SWAP), 1) gemm_tc_kernel(const __g
                     const uint32_t fb = smem_u32(&full_bar[pre]);
                     mbar_expect_tx(fb, STAGE_BYTES);
                     const uint32_t sa = smem_base + pre * STAGE_BYTES;
-                    if (SWAP) tma_load_2d(sa, &tm_a, fb, kb * BK, ta * BM);
-                    else      tma_load_2d(sa + A_BYTES, &tm_b, fb, kb * BK, tb * BN);
+                    if (SWAP) load_a(sa, fb, kb, ta);
+                    else      load_b(sa + A_BYTES, fb, kb, tb);
                 }
             }
             DBG_STAMP(1);                                                     // weight tiles requested
@@ -132,14 +153,14 @@ __global__ void __launch_bounds__(num_threads(SWAP), 1) gemm_tc_kernel(const __g
                     const uint32_t fb = smem_u32(&full_bar[stage]);
                     const uint32_t sa = smem_base + stage * STAGE_BYTES;
                     if (n < pre) {      // weight tile already in flight: only the activation tile is missing
-                        if (SWAP) tma_load_2d(sa + A_BYTES, &tm_b, fb, kb * BK, tb * BN);
-                        else      tma_load_2d(sa, &tm_a, fb, kb * BK, ta * BM);
+                        if (SWAP) load_b(sa + A_BYTES, fb, kb, tb);
+                        else      load_a(sa, fb, kb, ta);
                     } else {
                         if (SWAP) mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
                         else mbar_wait_relaxed(smem_u32(&empty_bar[stage]), phase ^ 1);
                         mbar_expect_tx(fb, STAGE_BYTES);
-                        tma_load_2d(sa, &tm_a, fb, kb * BK, ta * BM);
-                        tma_load_2d(sa + A_BYTES, &tm_b, fb, kb * BK, tb * BN);
+                        load_a(sa, fb, kb, ta);
+                        load_b(sa + A_BYTES, fb, kb, tb);
                     }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -170,8 +191,10 @@ __global__ void __launch_bounds__(num_threads(SWAP), 1) gemm_tc_kernel(const __g
                     const uint32_t sa = smem_base + stage * STAGE_BYTES;
 #pragma unroll
                     for (int kk = 0; kk < BK / UMMA_K; ++kk) {
-                        const uint64_t da = umma_desc_sw128(sa + kk * UMMA_K * 2, 16, 1024);
-                        const uint64_t db = umma_desc_sw128(sa + A_BYTES + kk * UMMA_K * 2, 16, 1024);
+                        const uint64_t da = A_MN ? umma_desc_sw128(sa + kk * UMMA_K * 128, 8192, 1024)
+                                                 : umma_desc_sw128(sa + kk * UMMA_K * 2, 16, 1024);
+                        const uint64_t db = B_MN ? umma_desc_sw128(sa + A_BYTES + kk * UMMA_K * 128, 8192, 1024)
+                                                 : umma_desc_sw128(sa + A_BYTES + kk * UMMA_K * 2, 16, 1024);
                         umma_f16(d_tmem + (kk % NACC) * BN, da, db, IDESC, (kb > kb0 || kk >= NACC) ? 1u : 0u);
                     }
                     umma_commit(smem_u32(&empty_bar[stage]));
@@ -372,11 +395,11 @@ __global__ void __launch_bounds__(num_threads(SWAP), 1) gemm_tc_kernel(const __g
     }
 }
 
-template <int BN, int STAGES, bool SWAP>
+template <int BN, int STAGES, bool SWAP, bool A_MN = false, bool B_MN = false>
 int launch_gemm_tc(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
     constexpr int SMEM = STAGES * (BM * BK * 2 + BN * BK * 2) + 1024 + epi_warps(SWAP) * STG_BYTES_PER_WARP;
     static bool configured = false;
-    auto kern = gemm_tc_kernel<BN, STAGES, SWAP>;
+    auto kern = gemm_tc_kernel<BN, STAGES, SWAP, A_MN, B_MN>;
     if (!configured) {
         VB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
         configured = true;
@@ -416,6 +439,33 @@ int vb_linear_tc(const void* x, int64_t ldx, const void* w, int64_t ldw, const f
     p.tiles_b = 1;
     if ((rc = vb_make_tmap_bf16_2d(&tb, w, N, K, ldw, 64, BK)) != VB_OK) return rc;
     return launch_gemm_tc<64, 8, false>(ta, tb, p, st);
+}
+
+// y[M,N] = epi(X . W^T) with operands optionally given transposed: x_mn: x is [K][M] (pitch ldx), w_mn: w is [K][N] (pitch ldw)
+int vb_linear_tc_t(const void* x, int64_t ldx, int x_mn, const void* w, int64_t ldw, int w_mn, const float* bias,
+                   const float* residual, int64_t ldr, void* y, int y_dtype, int64_t ldy, int64_t M, int64_t N, int64_t K,
+                   int epilogue, cudaStream_t st) {
+    if (!x_mn && !w_mn) return vb_linear_tc(x, ldx, w, ldw, bias, residual, ldr, y, y_dtype, ldy, M, N, K, epilogue, st);
+    VB_REQUIRE(ldx % 8 == 0 && ldw % 8 == 0, VB_ERR_UNSUPPORTED, "vb_linear_t: operand pitches must be multiples of 8");
+    CUtensorMap ta, tb;
+    int rc;
+    GemmParams p{};
+    p.rows_a = (int)M; p.rows_b = (int)N; p.K = (int)K;
+    p.tiles_a = (int)vb_ceil_div(M, BM);
+    p.tiles_b = (int)vb_ceil_div(N, 256);
+    p.kb_total = (int)vb_ceil_div(K, BK); p.kb_per_split = p.kb_total; p.n_split = 1;
+    p.epilogue = epilogue; p.bias = bias; p.residual = residual; p.ldr = ldr;
+    p.y = y; p.y_bf16 = (y_dtype == VB_BF16); p.ldy = ldy;
+    // MN-major operand: the tensor map runs over the [K][rows] matrix, boxes of 64 k rows x 64 columns
+    if (x_mn) rc = vb_make_tmap_bf16_2d(&ta, x, K, M, ldx, BK, 64);
+    else rc = vb_make_tmap_bf16_2d(&ta, x, M, K, ldx, BM, BK);
+    if (rc != VB_OK) return rc;
+    if (w_mn) rc = vb_make_tmap_bf16_2d(&tb, w, K, N, ldw, BK, 64);
+    else rc = vb_make_tmap_bf16_2d(&tb, w, N, K, ldw, 256, BK);
+    if (rc != VB_OK) return rc;
+    if (x_mn && w_mn) return launch_gemm_tc<256, 4, false, true, true>(ta, tb, p, st);
+    if (w_mn) return launch_gemm_tc<256, 4, false, false, true>(ta, tb, p, st);
+    return launch_gemm_tc<256, 4, false, true, false>(ta, tb, p, st);
 }
 
 // split K so that (N/128 slabs) x splits fills the SMs, with at least 2 k-blocks (128 columns of K) per slice

@@ -8,6 +8,25 @@ int vb_linear_tc(const void* x, int64_t ldx, const void* w, int64_t ldw, const f
                  int64_t ldr, void* y, int y_dtype, int64_t ldy, int64_t M, int64_t N, int64_t K, int epilogue,
                  cudaStream_t st);
 
+int vb_linear_tc_t(const void* x, int64_t ldx, int x_mn, const void* w, int64_t ldw, int w_mn, const float* bias,
+                   const float* residual, int64_t ldr, void* y, int y_dtype, int64_t ldy, int64_t M, int64_t N, int64_t K,
+                   int epilogue, cudaStream_t st);
+
+extern "C" int vb_linear_t(const void* x, int64_t ldx, int x_transposed, const void* w, int64_t ldw, int w_transposed,
+                           const float* bias, const float* residual, int64_t ldr, void* y, int y_dtype, int64_t ldy, int64_t M,
+                           int64_t N, int64_t K, int epilogue, void* stream) {
+    VB_REQUIRE(x && w && y, VB_ERR_BAD_ARG, "vb_linear_t: null pointer");
+    VB_REQUIRE(M >= 0 && N >= 1 && K >= 1, VB_ERR_BAD_ARG, "vb_linear_t: bad shape M=%lld N=%lld K=%lld", (long long)M, (long long)N, (long long)K);
+    VB_REQUIRE(epilogue >= VB_EPI_NONE && epilogue <= VB_EPI_BIAS_RESIDUAL, VB_ERR_BAD_ARG, "vb_linear_t: bad epilogue %d", epilogue);
+    VB_REQUIRE(epilogue == VB_EPI_NONE || bias != nullptr, VB_ERR_BAD_ARG, "vb_linear_t: epilogue %d needs a bias", epilogue);
+    VB_REQUIRE(epilogue != VB_EPI_BIAS_RESIDUAL || residual != nullptr, VB_ERR_BAD_ARG, "vb_linear_t: residual is null");
+    VB_REQUIRE(y_dtype == VB_F32 || y_dtype == VB_BF16, VB_ERR_BAD_ARG, "vb_linear_t: bad y_dtype");
+    VB_REQUIRE((x_transposed || w_transposed) ? N > 128 : true, VB_ERR_UNSUPPORTED, "vb_linear_t: transposed operands need N > 128 (got %lld)", (long long)N);
+    if (M == 0) return VB_OK;
+    return vb_linear_tc_t(x, ldx, x_transposed, w, ldw, w_transposed, bias, residual, ldr, y, y_dtype, ldy, M, N, K, epilogue,
+                          static_cast<cudaStream_t>(stream));
+}
+
 extern "C" int vb_linear(const void* x, int x_dtype, int64_t ldx, const void* w, int w_dtype, int64_t ldw, const float* bias,
                          const float* residual, int64_t ldr, void* y, int y_dtype, int64_t ldy, int64_t M, int64_t N,
                          int64_t K, int epilogue, void* stream) {

@@ -114,6 +114,23 @@ def linear(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None = None, *
     return out
 
 
+def linear_t(x: torch.Tensor, w: torch.Tensor, *, x_t: bool = False, w_t: bool = False, bias: torch.Tensor | None = None,
+             out: torch.Tensor | None = None, out_dtype: torch.dtype | None = None) -> torch.Tensor:
+    """y (M, N) = X @ W.T (+ bias) on the tcgen05 GEMM with operands optionally stored transposed (no transpose kernel):
+    x_t: x is (K, M) instead of (M, K); w_t: w is (K, N) instead of (N, K).  bf16 operands, N > 128."""
+    assert x.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and x.stride(1) == 1 and w.stride(1) == 1
+    K, M = (x.shape[0], x.shape[1]) if x_t else (x.shape[1], x.shape[0])
+    Kw, N = (w.shape[0], w.shape[1]) if w_t else (w.shape[1], w.shape[0])
+    assert K == Kw, (x.shape, w.shape, x_t, w_t)
+    if out is None:
+        out = torch.empty(M, N, device=x.device, dtype=out_dtype or x.dtype)
+    assert out.shape == (M, N) and out.stride(1) == 1
+    check(_L().vb_linear_t(_ptr(x), x.stride(0), int(x_t), _ptr(w), w.stride(0), int(w_t), _ptr(bias), None, 0, _ptr(out),
+                           _code(out.dtype), out.stride(0), M, N, K, EPI_BIAS if bias is not None else EPI_NONE, _stream()),
+          'vb_linear_t')
+    return out
+
+
 def linear_decode_splits(N: int, K: int, max_split: int) -> int:
     return int(_L().vb_linear_decode_splits(N, K, max_split))
 

@@ -6,9 +6,11 @@ pre-norm transformer stack, logits, mean cross entropy, and every gradient -- ru
 ``step_loss`` hands the result to autograd through one ``torch.autograd.Function`` whose inputs are the model's parameters,
 so ``loss.backward()`` / an optimizer step work exactly as with the reference.
 
-GEMMs: forward and backward use ``ops.linear`` (tcgen05 for bf16, SIMT fp32 in validation mode).  For y = x W^T:
-    dgrad  dx (R,K) = dy (R,N) . W (N,K)        = linear(dy, W^T)            W^T (K,N) materialised per step
-    wgrad  dW (N,K) = dy^T (N,R) . x (R,K)      = linear(dy^T, x^T)          activations transposed by vb_transpose
+GEMMs: forward and backward run on the tcgen05 GEMM (bf16) or the SIMT fp32 GEMM (validation mode).  For y = x W^T:
+    dgrad  dx (R,K) = dy (R,N) . W (N,K)        bf16: ``ops.linear_t(dy, W, w_t=True)`` -- W itself is the MN-major B operand
+    wgrad  dW (N,K) = dy^T (N,R) . x (R,K)      bf16: ``ops.linear_t(dy, x, x_t=True, w_t=True)`` -- dy and x are read in place
+so no operand is transposed in HBM (147 transpose launches, 9.6 ms of a 70 ms step, are gone); the fp32 validation mode keeps
+the explicit transposes (``vb_transpose``) in front of ``ops.linear``.
 R (= B*S rows) is padded to a multiple of 8 with zero rows (TMA pitch rule of the bf16 GEMM).
 Everything else (LayerNorm / GELU / attention backward, cross entropy, embedding scatter, bias column sums) is csrc/train.cu.
 
@@ -47,8 +49,15 @@ class _Lin:
         if pad_n and self.N % 8:                      # logits head (V = 1025): zero rows so that the dgrad K is aligned
             w = torch.cat([w, torch.zeros(_pad8(self.N) - self.N, w.shape[1], device=w.device, dtype=cd)], 0)
         self.w = w.contiguous()
-        self.wt = ops.transpose(self.w)               # (K, Npad)
+        self._wt = None
         self.b = None if bias is None else bias.detach().float().contiguous()
+
+    @property
+    def wt(self) -> torch.Tensor:
+        """(K, Npad) copy for the dgrad of the fp32 validation mode; the bf16 path reads W itself as an MN-major operand."""
+        if self._wt is None:
+            self._wt = ops.transpose(self.w)
+        return self._wt
 
 
 def _linear_fwd(x: torch.Tensor, lin: _Lin, *, residual: torch.Tensor | None = None, out: torch.Tensor | None = None,
@@ -56,9 +65,24 @@ def _linear_fwd(x: torch.Tensor, lin: _Lin, *, residual: torch.Tensor | None = N
     return ops.linear(x, lin.w, lin.b, residual=residual, out=out, out_dtype=out_dtype)
 
 
-def _wgrad(dy_t: torch.Tensor, x_t: torch.Tensor) -> torch.Tensor:
-    """dW (N,K) fp32 = dy^T (N,Rp) . x (Rp,K), both operands given transposed (row = feature, Rp contiguous)."""
-    return ops.linear(dy_t, x_t, out_dtype=torch.float32)
+def _mn_ok(*ts: torch.Tensor) -> bool:
+    """The tcgen05 GEMM can read these row-major matrices as MN-major operands (csrc/gemm_tc.cu, vb_linear_t)."""
+    return all(t.dtype == torch.bfloat16 and t.stride(0) % 8 == 0 for t in ts)
+
+
+def _wgrad(dy: torch.Tensor, x: torch.Tensor, R: int) -> torch.Tensor:
+    """dW (N,K) fp32 = dy^T . x over the first R rows of dy (Rp,N) and x (Rp,K).  bf16: both matrices are read in place as
+    MN-major MMA operands; fp32 validation mode: transposed copies (zero rows past R) + the SIMT GEMM."""
+    if _mn_ok(dy, x) and x.shape[1] > 128:
+        return ops.linear_t(dy[:R], x[:R], x_t=True, w_t=True, out_dtype=torch.float32)
+    return ops.linear(ops.transpose(dy), ops.transpose(x), out_dtype=torch.float32)
+
+
+def _dgrad(dy: torch.Tensor, lin: _Lin, out: torch.Tensor) -> torch.Tensor:
+    """dx (R,K) = dy (R,N) . W (N,K): W is the MN-major B operand (bf16) or its transposed copy (fp32 mode)."""
+    if _mn_ok(dy, lin.w) and lin.w.shape[1] > 128:
+        return ops.linear_t(dy, lin.w, w_t=True, out=out)
+    return ops.linear(dy, lin.wt, out=out)
 
 
 class StackTrainer:
@@ -150,29 +174,27 @@ class StackTrainer:
             g = {}
             # ---- x_out = x_mid + f W2^T + b2 ----
             ops.residual_layernorm(dx[:R], None, None, dxb[:R])                    # cast of the residual gradient
-            dxb_t = ops.transpose(dxb)                                             # (d, Rp)
             g['f2.b'] = ops.colsum(dx[:R])
-            g['f2.w'] = _wgrad(dxb_t, ops.transpose(c['f']))                       # (d, F)
+            g['f2.w'] = _wgrad(dxb, c['f'], R)                                     # (d, F)
             df = torch.zeros(Rp, self.F, device=dev, dtype=cd)
-            ops.linear(dxb[:R], L['f2'].wt, out=df[:R])                            # (R, F)
+            _dgrad(dxb[:R], L['f2'], df[:R])                                       # (R, F)
             dpre = ops.gelu_bwd(c['f_pre'], df, df)                                # in place
             g['f1.b'] = ops.colsum(dpre[:R])
-            g['f1.w'] = _wgrad(ops.transpose(dpre), ops.transpose(c['h2']))        # (F, d)
+            g['f1.w'] = _wgrad(dpre, c['h2'], R)                                   # (F, d)
             dh = torch.zeros(Rp, d, device=dev, dtype=cd)
-            ops.linear(dpre[:R], L['f1'].wt, out=dh[:R])
+            _dgrad(dpre[:R], L['f1'], dh[:R])
             g['n2.g'], g['n2.b'] = ops.layernorm_bwd(c['x_mid'][:R], c['g2'], dh[:R], dx[:R], L['norm2']['eps'])
             # ---- x_mid = x_in + o Wo^T + bo ----
             ops.residual_layernorm(dx[:R], None, None, dxb[:R])
-            dxb_t = ops.transpose(dxb)
             g['o.b'] = ops.colsum(dx[:R])
-            g['o.w'] = _wgrad(dxb_t, ops.transpose(c['o']))                        # (d, d)
+            g['o.w'] = _wgrad(dxb, c['o'], R)                                      # (d, d)
             do = torch.zeros(Rp, d, device=dev, dtype=cd)
-            ops.linear(dxb[:R], L['o'].wt, out=do[:R])
+            _dgrad(dxb[:R], L['o'], do[:R])
             dqkv = torch.zeros(Rp, 3 * d, device=dev, dtype=cd)
             ops.attention_bwd(c['qkv'][:R], c['o'][:R], do[:R], dqkv[:R], B, S, H, mask_mode=mask_mode, x_lens=x_lens, kv_lens=kv_lens,
                               lse=c.get('lse'))
-            g['qkv.w'] = _wgrad(ops.transpose(dqkv), ops.transpose(c['h1']))       # (3d, d)
-            ops.linear(dqkv[:R], L['qkv'].wt, out=dh[:R])
+            g['qkv.w'] = _wgrad(dqkv, c['h1'], R)                                  # (3d, d)
+            _dgrad(dqkv[:R], L['qkv'], dh[:R])
             g['n1.g'], g['n1.b'] = ops.layernorm_bwd(c['x_in'][:R], c['g1'], dh[:R], dx[:R], L['norm1']['eps'])
             g['fold1'], g['fold2'] = c['fold1'], c['fold2']
             grads[li] = g
@@ -250,9 +272,9 @@ def ar_loss_and_grads(model, batch: dict, precision: str):
     grads = {}
     dl = torch.zeros(Rap, Vp, device=dev, dtype=cd)
     ops.residual_layernorm(dlogits[:Ra], None, None, dl[:Ra])
-    grads['proj.weight'] = _wgrad(ops.transpose(dl), ops.transpose(hb))[:V]        # (V, d)
+    grads['proj.weight'] = _wgrad(dl, hb, Ra)[:V]                                  # (V, d)
     dh = torch.zeros(Rap, d, device=dev, dtype=cd)
-    ops.linear(dl[:Ra], proj.wt, out=dh[:Ra])
+    _dgrad(dl[:Ra], proj, dh[:Ra])
     dx = torch.zeros(Rp, d, device=dev, dtype=torch.float32)
     dx[:R].view(B, S, d)[:, Tx:] = dh[:Ra].view(B, Ty, d).float()                   # scatter into the audio rows (plumbing)
     lg = tr.backward(dx, cache, B, S, mask_mode=MASK_PREFIX_LM, x_lens=xl, kv_lens=kv_lens)
@@ -306,9 +328,9 @@ def nar_loss_and_grads(model, batch: dict, layer: int, precision: str):
     grads = {}
     dl = torch.zeros(Rap, Vp, device=dev, dtype=cd)
     ops.residual_layernorm(dlogits[:Ra], None, None, dl[:Ra])
-    grads[f'proj_layers.{layer - 1}.weight'] = _wgrad(ops.transpose(dl), ops.transpose(hb))[:V]
+    grads[f'proj_layers.{layer - 1}.weight'] = _wgrad(dl, hb, Ra)[:V]
     dh = torch.zeros(Rap, d, device=dev, dtype=cd)
-    ops.linear(dl[:Ra], proj.wt, out=dh[:Ra])
+    _dgrad(dl[:Ra], proj, dh[:Ra])
     dx = torch.zeros(Rp, d, device=dev, dtype=torch.float32)
     dx[:R].view(B, S, d)[:, Tx + prefix_len:] = dh[:Ra].view(B, Tt, d).float()
     lg = tr.backward(dx, cache, B, S, mask_mode=MASK_NONE, x_lens=None, kv_lens=None)
