@@ -53,8 +53,15 @@ __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, in
     const int64_t r_lo = blockIdx.y * rows_per_block, r_hi = min(R, r_lo + rows_per_block);
     out += static_cast<int64_t>(blockIdx.y) * N;
     float acc = 0.f;
-    if (n < N)
-        for (int64_t r = r_lo + warp; r < r_hi; r += 8) acc += to_f32<T>(x[r * ldx + n]);
+    if (n < N) {
+        int64_t r = r_lo + warp;
+        for (; r + 24 < r_hi; r += 32) {        // four independent loads in flight per lane, fixed summation order
+            const float v0 = to_f32<T>(x[r * ldx + n]), v1 = to_f32<T>(x[(r + 8) * ldx + n]);
+            const float v2 = to_f32<T>(x[(r + 16) * ldx + n]), v3 = to_f32<T>(x[(r + 24) * ldx + n]);
+            acc += (v0 + v1) + (v2 + v3);
+        }
+        for (; r < r_hi; r += 8) acc += to_f32<T>(x[r * ldx + n]);
+    }
     red[warp][lane] = acc;
     __syncthreads();
     if (warp == 0 && n < N) {

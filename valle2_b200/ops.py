@@ -374,7 +374,7 @@ def colsum(x: torch.Tensor, out: torch.Tensor | None = None, *, accumulate: bool
         out = torch.zeros(N, device=x.device, dtype=torch.float32)
     assert x.stride(1) == 1 and out.dtype == torch.float32 and out.numel() == N
     if R >= 4096:       # long and narrow: two deterministic levels so that the first one fills the GPU
-        rb = int(min(64, max(2, (148 * 32) // max(N, 32))))
+        rb = int(min(64, max(2, -(-R // 512))))     # <= 512 rows per CTA (64 per warp): enough CTAs to keep HBM busy
         part = torch.empty(rb, N, device=x.device, dtype=torch.float32)
         check(_L().vb_colsum_blocks(_ptr(x), _code(x.dtype), R, N, x.stride(0), _ptr(part), rb, _stream()), 'vb_colsum_blocks')
         x, R = part, rb

@@ -65,6 +65,18 @@ def _linear_fwd(x: torch.Tensor, lin: _Lin, *, residual: torch.Tensor | None = N
     return ops.linear(x, lin.w, lin.b, residual=residual, out=out, out_dtype=out_dtype)
 
 
+def _rows(Rp: int, n: int, R: int, device, dtype: torch.dtype) -> torch.Tensor:
+    """Activation / gradient buffer of Rp rows of which R are live.  bf16: uninitialised, only the <= 7 pad rows are zeroed
+    (the kernels write every live row; the GEMMs read rows [:R] or zero-fill past them) -- a full memset of these buffers
+    was ~12 GB of HBM writes per step.  fp32 validation mode: zero-filled (its transposed wgrad copies read the pad rows)."""
+    if dtype != torch.bfloat16:
+        return torch.zeros(Rp, n, device=device, dtype=dtype)
+    t = torch.empty(Rp, n, device=device, dtype=dtype)
+    if Rp > R:
+        t[R:].zero_()
+    return t
+
+
 def _mn_ok(*ts: torch.Tensor) -> bool:
     """The tcgen05 GEMM can read these row-major matrices as MN-major operands (csrc/gemm_tc.cu, vb_linear_t)."""
     return all(t.dtype == torch.bfloat16 and t.stride(0) % 8 == 0 for t in ts)
@@ -137,11 +149,11 @@ class StackTrainer:
             g1, b1, c['fold1'] = self._affine(L, 'norm1', stage)
             c['g1'] = g1
             c['x_in'] = x.clone()
-            c['h1'] = torch.zeros(Rp, d, device=dev, dtype=cd)
+            c['h1'] = _rows(Rp, d, R, dev, cd)
             ops.residual_layernorm(x[:R], g1, b1, c['h1'][:R], eps=L['norm1']['eps'])
-            c['qkv'] = torch.zeros(Rp, 3 * d, device=dev, dtype=cd)
+            c['qkv'] = _rows(Rp, 3 * d, R, dev, cd)
             _linear_fwd(c['h1'][:R], L['qkv'], out=c['qkv'][:R])
-            c['o'] = torch.zeros(Rp, d, device=dev, dtype=cd)
+            c['o'] = _rows(Rp, d, R, dev, cd)
             # the tensor-core forward also leaves the rows' log-sum-exp for the backward pass (5.5 KB per head and sequence)
             c['lse'] = torch.empty(B, H, S, device=dev, dtype=torch.float32) if (use_tc and self.save_lse) else None
             ops.attention_packed(c['qkv'][:R], c['o'][:R], B, S, H, mask_mode=mask_mode, x_lens=x_lens, kv_lens=kv_lens, use_tc=use_tc,
@@ -150,11 +162,11 @@ class StackTrainer:
             g2, b2, c['fold2'] = self._affine(L, 'norm2', stage)
             c['g2'] = g2
             c['x_mid'] = x.clone()
-            c['h2'] = torch.zeros(Rp, d, device=dev, dtype=cd)
+            c['h2'] = _rows(Rp, d, R, dev, cd)
             ops.residual_layernorm(x[:R], g2, b2, c['h2'][:R], eps=L['norm2']['eps'])
-            c['f_pre'] = torch.zeros(Rp, F, device=dev, dtype=cd)
+            c['f_pre'] = _rows(Rp, F, R, dev, cd)
             _linear_fwd(c['h2'][:R], L['f1'], out=c['f_pre'][:R])
-            c['f'] = torch.zeros(Rp, F, device=dev, dtype=cd)
+            c['f'] = _rows(Rp, F, R, dev, cd)
             ops.gelu_fwd(c['f_pre'], c['f'])
             _linear_fwd(c['f'][:R], L['f2'], residual=x[:R], out=x[:R])
             cache.append(c)
@@ -168,7 +180,7 @@ class StackTrainer:
         cd, H = self.cd, self.H
         dev = dx.device
         grads = [None] * len(self.layers)
-        dxb = torch.zeros(Rp, d, device=dev, dtype=cd)
+        dxb = _rows(Rp, d, R, dev, cd)
         for li in range(len(self.layers) - 1, -1, -1):
             L, c = self.layers[li], cache[li]
             g = {}
@@ -176,21 +188,21 @@ class StackTrainer:
             ops.residual_layernorm(dx[:R], None, None, dxb[:R])                    # cast of the residual gradient
             g['f2.b'] = ops.colsum(dx[:R])
             g['f2.w'] = _wgrad(dxb, c['f'], R)                                     # (d, F)
-            df = torch.zeros(Rp, self.F, device=dev, dtype=cd)
+            df = _rows(Rp, self.F, R, dev, cd)
             _dgrad(dxb[:R], L['f2'], df[:R])                                       # (R, F)
             dpre = ops.gelu_bwd(c['f_pre'], df, df)                                # in place
             g['f1.b'] = ops.colsum(dpre[:R])
             g['f1.w'] = _wgrad(dpre, c['h2'], R)                                   # (F, d)
-            dh = torch.zeros(Rp, d, device=dev, dtype=cd)
+            dh = _rows(Rp, d, R, dev, cd)
             _dgrad(dpre[:R], L['f1'], dh[:R])
             g['n2.g'], g['n2.b'] = ops.layernorm_bwd(c['x_mid'][:R], c['g2'], dh[:R], dx[:R], L['norm2']['eps'])
             # ---- x_mid = x_in + o Wo^T + bo ----
             ops.residual_layernorm(dx[:R], None, None, dxb[:R])
             g['o.b'] = ops.colsum(dx[:R])
             g['o.w'] = _wgrad(dxb, c['o'], R)                                      # (d, d)
-            do = torch.zeros(Rp, d, device=dev, dtype=cd)
+            do = _rows(Rp, d, R, dev, cd)
             _dgrad(dxb[:R], L['o'], do[:R])
-            dqkv = torch.zeros(Rp, 3 * d, device=dev, dtype=cd)
+            dqkv = _rows(Rp, 3 * d, R, dev, cd)
             ops.attention_bwd(c['qkv'][:R], c['o'][:R], do[:R], dqkv[:R], B, S, H, mask_mode=mask_mode, x_lens=x_lens, kv_lens=kv_lens,
                               lse=c.get('lse'))
             g['qkv.w'] = _wgrad(dqkv, c['h1'], R)                                  # (3d, d)
