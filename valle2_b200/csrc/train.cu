@@ -81,6 +81,37 @@ __global__ void gelu_fwd_kernel(const T* __restrict__ pre, T* __restrict__ y, in
     for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * blockDim.x)
         y[i] = from_f32<T>(gelu_erf(to_f32<T>(pre[i])));
 }
+// bf16, 8 elements (16 bytes) per thread and iteration: the scalar kernels above moved 2 bytes per load instruction and ran
+// at 40 % of the HBM rate on the (B*S, 4096) FFN buffers
+__device__ __forceinline__ float gelu_grad(float x, float dy) {
+    const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
+    const float pdf = 0.39894228040143267794f * expf(-0.5f * x * x);
+    return dy * (cdf + x * pdf);
+}
+__global__ void __launch_bounds__(256) gelu_fwd_bf16x8_kernel(const uint4* __restrict__ pre, uint4* __restrict__ y, int64_t n8) {
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n8; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const uint4 p = pre[i];
+        uint4 r;
+        r.x = pack_bf16x2(gelu_erf(bf16_lo(p.x)), gelu_erf(bf16_hi(p.x)));
+        r.y = pack_bf16x2(gelu_erf(bf16_lo(p.y)), gelu_erf(bf16_hi(p.y)));
+        r.z = pack_bf16x2(gelu_erf(bf16_lo(p.z)), gelu_erf(bf16_hi(p.z)));
+        r.w = pack_bf16x2(gelu_erf(bf16_lo(p.w)), gelu_erf(bf16_hi(p.w)));
+        y[i] = r;
+    }
+}
+__global__ void __launch_bounds__(256) gelu_bwd_bf16x8_kernel(const uint4* __restrict__ pre, const uint4* __restrict__ dy,
+                                                              uint4* __restrict__ dpre, int64_t n8) {
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n8; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const uint4 p = pre[i], g = dy[i];
+        uint4 r;
+        r.x = pack_bf16x2(gelu_grad(bf16_lo(p.x), bf16_lo(g.x)), gelu_grad(bf16_hi(p.x), bf16_hi(g.x)));
+        r.y = pack_bf16x2(gelu_grad(bf16_lo(p.y), bf16_lo(g.y)), gelu_grad(bf16_hi(p.y), bf16_hi(g.y)));
+        r.z = pack_bf16x2(gelu_grad(bf16_lo(p.z), bf16_lo(g.z)), gelu_grad(bf16_hi(p.z), bf16_hi(g.z)));
+        r.w = pack_bf16x2(gelu_grad(bf16_lo(p.w), bf16_lo(g.w)), gelu_grad(bf16_hi(p.w), bf16_hi(g.w)));
+        dpre[i] = r;
+    }
+}
+
 template <typename T>
 __global__ void gelu_bwd_kernel(const T* __restrict__ pre, const T* __restrict__ dy, T* __restrict__ dpre, int64_t n) {
     for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
@@ -874,7 +905,12 @@ extern "C" int vb_gelu_fwd(const void* pre, int dtype, void* y, int64_t n, void*
     if (n == 0) return VB_OK;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int blocks = (int)std::min<int64_t>(vb_ceil_div(n, 256), static_cast<int64_t>(vb_sm_count()) * 16);
-    if (dtype == VB_F32) gelu_fwd_kernel<float><<<blocks, 256, 0, st>>>(static_cast<const float*>(pre), static_cast<float*>(y), n);
+    const bool vec8 = dtype == VB_BF16 && n % 8 == 0 && ((reinterpret_cast<uintptr_t>(pre) | reinterpret_cast<uintptr_t>(y)) & 15) == 0;
+    if (vec8) {
+        const int b8 = (int)std::min<int64_t>(vb_ceil_div(n / 8, 256), static_cast<int64_t>(vb_sm_count()) * 16);
+        gelu_fwd_bf16x8_kernel<<<b8, 256, 0, st>>>(static_cast<const uint4*>(pre), static_cast<uint4*>(y), n / 8);
+    }
+    else if (dtype == VB_F32) gelu_fwd_kernel<float><<<blocks, 256, 0, st>>>(static_cast<const float*>(pre), static_cast<float*>(y), n);
     else if (dtype == VB_BF16) gelu_fwd_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(pre), static_cast<__nv_bfloat16*>(y), n);
     else VB_REQUIRE(false, VB_ERR_BAD_ARG, "vb_gelu_fwd: bad dtype");
     VB_LAUNCH_CHECK();
@@ -886,7 +922,13 @@ extern "C" int vb_gelu_bwd(const void* pre, const void* dy, int dtype, void* dpr
     if (n == 0) return VB_OK;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int blocks = (int)std::min<int64_t>(vb_ceil_div(n, 256), static_cast<int64_t>(vb_sm_count()) * 16);
-    if (dtype == VB_F32) gelu_bwd_kernel<float><<<blocks, 256, 0, st>>>(static_cast<const float*>(pre), static_cast<const float*>(dy), static_cast<float*>(dpre), n);
+    const bool vec8 = dtype == VB_BF16 && n % 8 == 0 &&
+                      ((reinterpret_cast<uintptr_t>(pre) | reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dpre)) & 15) == 0;
+    if (vec8) {
+        const int b8 = (int)std::min<int64_t>(vb_ceil_div(n / 8, 256), static_cast<int64_t>(vb_sm_count()) * 16);
+        gelu_bwd_bf16x8_kernel<<<b8, 256, 0, st>>>(static_cast<const uint4*>(pre), static_cast<const uint4*>(dy), static_cast<uint4*>(dpre), n / 8);
+    }
+    else if (dtype == VB_F32) gelu_bwd_kernel<float><<<blocks, 256, 0, st>>>(static_cast<const float*>(pre), static_cast<const float*>(dy), static_cast<float*>(dpre), n);
     else if (dtype == VB_BF16) gelu_bwd_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(pre), static_cast<const __nv_bfloat16*>(dy), static_cast<__nv_bfloat16*>(dpre), n);
     else VB_REQUIRE(false, VB_ERR_BAD_ARG, "vb_gelu_bwd: bad dtype");
     VB_LAUNCH_CHECK();
