@@ -974,6 +974,8 @@ extern "C" int vb_layernorm_bwd(const float* x, const float* gamma, const void* 
 }
 
 bool vb_attention_bwd_tc_enabled();
+int vb_attention_bwd_dkv_tc(const void* qkv, const void* dO, void* dqkv, const float* lse, const float* delta, int B, int S, int H,
+                            int mask_mode, const int32_t* x_lens, const int32_t* kv_lens, cudaStream_t st);
 int vb_attention_bwd_dq_tc(const void* qkv, const void* o, const void* dO, void* dqkv, const float* lse, float* delta, int B, int S,
                            int H, int mask_mode, const int32_t* x_lens, const int32_t* kv_lens, cudaStream_t st);
 
@@ -1013,9 +1015,16 @@ extern "C" int vb_attention_bwd(const void* qkv, const void* o, const void* dO, 
                    (reinterpret_cast<uintptr_t>(dO) & 15) == 0 && (reinterpret_cast<uintptr_t>(dqkv) & 3) == 0,
                    VB_ERR_BAD_ARG, "vb_attention_bwd: bf16 operands must be 16-byte aligned");
         const __nv_bfloat16* q16 = static_cast<const __nv_bfloat16*>(qkv);
-        if (lse_is_input && vb_attention_bwd_tc_enabled()) {      // dQ on tcgen05 (attn_bwd_tc.cu); needs the forward's lse
-            const int rc = vb_attention_bwd_dq_tc(qkv, o, dO, dqkv, lse, delta, B, S, H, mask_mode, x_lens, kv_lens, st);
+        if (lse_is_input && vb_attention_bwd_tc_enabled()) {      // tcgen05 kernels (attn_bwd_tc.cu); they need the forward's lse
+            int rc = vb_attention_bwd_dq_tc(qkv, o, dO, dqkv, lse, delta, B, S, H, mask_mode, x_lens, kv_lens, st);
             if (rc != VB_OK) return rc;
+            static const bool dkv_tc = !(getenv("VALLE_B200_ATTN_BWD_DKV_TC") != nullptr && getenv("VALLE_B200_ATTN_BWD_DKV_TC")[0] == '0');
+            if (dkv_tc) {
+                rc = vb_attention_bwd_dkv_tc(qkv, dO, dqkv, lse, delta, B, S, H, mask_mode, x_lens, kv_lens, st);
+                if (rc != VB_OK) return rc;
+                VB_LAUNCH_CHECK();
+                return VB_OK;
+            }
         } else
         attn_bwd_dq_mma_kernel<<<grid, 128, 0, st>>>(q16, static_cast<const __nv_bfloat16*>(o), static_cast<const __nv_bfloat16*>(dO),
                                                      static_cast<__nv_bfloat16*>(dqkv), lse, delta, S, H, mask_mode, x_lens, kv_lens, scale, lse_is_input);
