@@ -80,6 +80,10 @@ int vb_residual_layernorm(float* x, const float* part, int n_part, int64_t part_
                           const float* gamma, const float* beta, void* y, int y_dtype,
                           int64_t R, int d, float eps, void* stream);
 
+/* Profiling aid: decode-shape (R <= 1024) vb_residual_layernorm launches write %globaltimer stamps [row][4] = {start,
+ * dependency resolved, row loaded (slices added), stored}; NULL switches it off. */
+int vb_residual_layernorm_set_debug(void* buf);
+
 /* y[r, n] = act(sum_s part[s][r][n] + bias[n]); act = gelu_erf if gelu != 0.  y: y_dtype.  (modules.py:220-221) */
 int vb_reduce_bias_act(const float* part, int n_part, int64_t part_stride, const float* bias, int gelu,
                        void* y, int y_dtype, int64_t R, int N, void* stream);

@@ -64,6 +64,42 @@ def attn_wrap(*a, **k):
     return r
 
 
+real_ld = ops.linear_decode
+gpool = [torch.zeros(512, 16, device=dev, dtype=torch.int64) for _ in range(64)]
+gused = []
+
+
+def ld_wrap(x, w, part, part_stride, max_split, flags=0):
+    buf = gpool[len(gused)]
+    gused.append(buf)
+    bufs.append(buf)
+    names.append(f'tc-splitK N={w.shape[0]} K={w.shape[1]}')
+    _lib.check(lib.vb_linear_decode_set_debug(buf.data_ptr()), 'dbg')
+    r = real_ld(x, w, part, part_stride, max_split, flags)
+    _lib.check(lib.vb_linear_decode_set_debug(None), 'dbg')
+    return r
+
+
+real_ln = ops.residual_layernorm
+lpool = [torch.zeros(64, 4, device=dev, dtype=torch.int64) for _ in range(64)]
+lused = []
+
+
+def ln_wrap(x, *a, **k):
+    if x.shape[0] > 64:
+        return real_ln(x, *a, **k)
+    buf = lpool[len(lused)]
+    lused.append(buf)
+    bufs.append(buf)
+    names.append(f'LN n_part={k.get("n_part", 0)}')
+    _lib.check(lib.vb_residual_layernorm_set_debug(buf.data_ptr()), 'dbg')
+    r = real_ln(x, *a, **k)
+    _lib.check(lib.vb_residual_layernorm_set_debug(None), 'dbg')
+    return r
+
+
+ops.residual_layernorm = ln_wrap
+ops.linear_decode = ld_wrap
 ops.attn_decode_paged = attn_wrap
 ops.linear_decode_rows, ops.linear_decode_rows_ln = wrap(real_rows, 'rows'), wrap(real_ln, 'rows+LN')
 graph = torch.cuda.CUDAGraph()
@@ -71,6 +107,8 @@ with torch.cuda.graph(graph):
     eng.decode_step(samp, None, -1)
 ops.linear_decode_rows, ops.linear_decode_rows_ln = real_rows, real_ln
 ops.attn_decode_paged = real_attn
+ops.linear_decode = real_ld
+ops.residual_layernorm = real_ln
 for _ in range(3):
     graph.replay()
 torch.cuda.synchronize()
@@ -98,6 +136,23 @@ for nm, t in zip(names, T):
                 c = tt[:, sp]
                 print(f'      split {sp}: copies issued {(np.median(c[:, 1]) - t0) / 1e3:6.2f}  1st page {(np.median(c[:, 4][c[:, 4] > 0]) - t0) / 1e3 if (c[:, 4] > 0).any() else float("nan"):6.2f}'
                       f'  pages done {(np.median(c[:, 5]) - t0) / 1e3:6.2f}  partial out {(np.median(c[:, 6]) - t0) / 1e3:6.2f}')
+        prev_end = t[:, 7].max()
+        continue
+    if nm.startswith('LN'):
+        t = t[t[:, 0] > 0]
+        if t0 is None:
+            t0 = t[:, 0].min()
+        gap = (np.median(t[:, 1]) - prev_end) if prev_end is not None else 0.0
+        print(f'  {nm:24s} start {(t[:, 0].min() - t0) / 1e3:8.2f}  dep {(np.median(t[:, 1]) - t0) / 1e3:8.2f}  loaded {(np.median(t[:, 2]) - t0) / 1e3:8.2f}..{(t[:, 2].max() - t0) / 1e3:.2f}  end {(t[:, 3].max() - t0) / 1e3:8.2f}   dep - prev end {gap / 1e3:6.2f}')
+        prev_end = t[:, 3].max()
+        continue
+    if nm.startswith('tc-splitK'):      # stamps: 0 prologue, 1 weights requested, 2 dep resolved, 3 first k-block, 4 MMAs issued, 5 acc done, 6 acc in regs, 7 stores
+        t = t[t[:, 0] > 0]
+        if t0 is None:
+            t0 = t[:, 0].min()
+        dep, end = np.median(t[:, 2]) - t0, t[:, 7].max() - t0
+        gap = (np.median(t[:, 2]) - prev_end) if prev_end is not None else 0.0
+        print(f'  {nm:24s} start {(t[:, 0].min() - t0) / 1e3:8.2f}  dep {dep / 1e3:8.2f}  1st kblock {(np.median(t[:, 3]) - t0) / 1e3:8.2f}  acc done {(np.median(t[:, 5]) - t0) / 1e3:8.2f}  end {end / 1e3:8.2f}   dep - prev end {gap / 1e3:6.2f}   run {(end - dep) / 1e3:5.2f}')
         prev_end = t[:, 7].max()
         continue
     live = t[:, 0] > 0

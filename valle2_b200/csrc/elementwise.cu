@@ -165,14 +165,33 @@ __global__ void __launch_bounds__(256) residual_layernorm_block_kernel(float* __
                                                                        const float* __restrict__ bias,
                                                                        const float* __restrict__ gamma,
                                                                        const float* __restrict__ beta, TY* __restrict__ y,
-                                                                       int d, float eps) {
+                                                                       int d, float eps, unsigned long long* __restrict__ dbg) {
     __shared__ float red[8];
+    // optional timeline (vb_residual_layernorm_set_debug): %globaltimer [row][4] = {start, dependency resolved, row loaded, stored}
+#define LN_STAMP(ev) do { if (dbg != nullptr && threadIdx.x == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); dbg[blockIdx.x * 4 + (ev)] = t_; } } while (0)
+    LN_STAMP(0);
     pdl_trigger();
-    pdl_wait();
     const int64_t r = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     float* xr = x + r * d;
     constexpr int MAXC = 4;
+    // gamma / beta / bias are weights: fetched BEFORE the dependency resolves (they used to be read after the two block
+    // reductions -- one more L2 round trip on the critical path of every decode-step LayerNorm)
+    float4 g4[MAXC], b4[MAXC], bias4[MAXC];
+#pragma unroll
+    for (int i = 0; i < MAXC; ++i) {
+        const int c4 = tid + i * 256;
+        g4[i] = b4[i] = bias4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c4 < (d >> 2)) {
+            if (gamma != nullptr && y != nullptr) {
+                g4[i] = *reinterpret_cast<const float4*>(gamma + c4 * 4);
+                b4[i] = *reinterpret_cast<const float4*>(beta + c4 * 4);
+            }
+            if (n_part > 0 && bias != nullptr) bias4[i] = *reinterpret_cast<const float4*>(bias + c4 * 4);
+        }
+    }
+    pdl_wait();
+    LN_STAMP(1);
     float4 v[MAXC];
     const int nchunk = d >> 2;
 #pragma unroll
@@ -183,9 +202,30 @@ __global__ void __launch_bounds__(256) residual_layernorm_block_kernel(float* __
             const int c = c4 * 4;
             float4 a = *reinterpret_cast<const float4*>(xr + c);
             if (n_part > 0) {
-                float4 acc = bias ? *reinterpret_cast<const float4*>(bias + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+                float4 acc = bias4[i];
                 const float* pp = part + r * d + c;
                 int s = 0;
+                // Sixteen / eight slices at a time with EVERY load issued before the first add (summed in slice order).  The
+                // empty asm consumes all loaded registers at once: without it ptxas interleaves load and add to save
+                // registers and the slices arrive as a chain of dependent L2 round trips (3.6 us for this kernel in a B=32
+                // step with 16 slices -- tools/step_timeline.py).
+                for (; s + 16 <= n_part; s += 16) {
+                    float4 p[16];
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) p[k] = __ldcg(reinterpret_cast<const float4*>(pp + (s + k) * part_stride));
+                    asm volatile("" ::"f"(p[0].x), "f"(p[1].x), "f"(p[2].x), "f"(p[3].x), "f"(p[4].x), "f"(p[5].x), "f"(p[6].x), "f"(p[7].x),
+                                 "f"(p[8].x), "f"(p[9].x), "f"(p[10].x), "f"(p[11].x), "f"(p[12].x), "f"(p[13].x), "f"(p[14].x), "f"(p[15].x));
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) { acc.x += p[k].x; acc.y += p[k].y; acc.z += p[k].z; acc.w += p[k].w; }
+                }
+                for (; s + 8 <= n_part; s += 8) {
+                    float4 p[8];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) p[k] = __ldcg(reinterpret_cast<const float4*>(pp + (s + k) * part_stride));
+                    asm volatile("" ::"f"(p[0].x), "f"(p[1].x), "f"(p[2].x), "f"(p[3].x), "f"(p[4].x), "f"(p[5].x), "f"(p[6].x), "f"(p[7].x));
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) { acc.x += p[k].x; acc.y += p[k].y; acc.z += p[k].z; acc.w += p[k].w; }
+                }
                 for (; s + 4 <= n_part; s += 4) {   // four independent loads in flight, summed in slice order
                     const float4 p0 = *reinterpret_cast<const float4*>(pp + (s + 0) * part_stride);
                     const float4 p1 = *reinterpret_cast<const float4*>(pp + (s + 1) * part_stride);
@@ -206,6 +246,7 @@ __global__ void __launch_bounds__(256) residual_layernorm_block_kernel(float* __
             v[i] = a;
         }
     }
+    LN_STAMP(2);
     if (y == nullptr) return;
     TY* yr = y + r * d;
     if (gamma == nullptr) {
@@ -250,14 +291,22 @@ __global__ void __launch_bounds__(256) residual_layernorm_block_kernel(float* __
         const int c4 = tid + i * 256;
         if (c4 < nchunk) {
             const int c = c4 * 4;
-            const float4 g = *reinterpret_cast<const float4*>(gamma + c);
-            const float4 bt = *reinterpret_cast<const float4*>(beta + c);
+            const float4 g = g4[i];
+            const float4 bt = b4[i];
             const float o0 = (v[i].x - mean) * rstd * g.x + bt.x, o1 = (v[i].y - mean) * rstd * g.y + bt.y;
             const float o2 = (v[i].z - mean) * rstd * g.z + bt.z, o3 = (v[i].w - mean) * rstd * g.w + bt.w;
             if constexpr (sizeof(TY) == 4) *reinterpret_cast<float4*>(yr + c) = make_float4(o0, o1, o2, o3);
             else *reinterpret_cast<uint2*>(yr + c) = make_uint2(pack_bf16x2(o0, o1), pack_bf16x2(o2, o3));
         }
     }
+    LN_STAMP(3);
+#undef LN_STAMP
+}
+
+static unsigned long long* g_ln_dbg = nullptr;
+extern "C" int vb_residual_layernorm_set_debug(void* buf) {   /* device buffer of R * 4 uint64 stamps (decode-shape launches), or NULL */
+    g_ln_dbg = static_cast<unsigned long long*>(buf);
+    return VB_OK;
 }
 
 template <typename TY>
@@ -265,7 +314,7 @@ static int launch_rln(float* x, const float* part, int n_part, int64_t part_stri
                       const float* beta, TY* y, int64_t R, int d, float eps, cudaStream_t st) {
     if (R <= 1024 && d % 4 == 0 && d <= 4096) {
         VB_CUDA(vb_launch(true, residual_layernorm_block_kernel<TY>, dim3(static_cast<unsigned>(R)), dim3(256), 0, st, x, part, n_part,
-                          part_stride, bias, gamma, beta, y, d, eps));
+                          part_stride, bias, gamma, beta, y, d, eps, g_ln_dbg));
         return VB_OK;
     }
     const int warps = 8;
@@ -306,17 +355,36 @@ template <typename TY>
 __global__ void reduce_bias_act_kernel(const float* __restrict__ part, int n_part, int64_t part_stride,
                                        const float* __restrict__ bias, int gelu, TY* __restrict__ y, int64_t total4, int N) {
     pdl_trigger();
+    // the bias of this thread's first element is a weight: fetched before the dependency resolves
+    const int64_t i_first = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    float4 bias_first = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (bias && i_first < total4) bias_first = *reinterpret_cast<const float4*>(bias + static_cast<int>((i_first * 4) % N));
     pdl_wait();
-    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total4;
-         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    for (int64_t i = i_first; i < total4; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
         const int64_t e = i * 4;
         const int n = static_cast<int>(e % N);
-        float4 acc = bias ? *reinterpret_cast<const float4*>(bias + n) : make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int s = 0; s < n_part; ++s) {
+        float4 acc = (i == i_first) ? bias_first : (bias ? *reinterpret_cast<const float4*>(bias + n) : make_float4(0.f, 0.f, 0.f, 0.f));
+        int s = 0;
+        for (; s + 4 <= n_part; s += 4) {       // four slices with every load issued before the first add (see the LayerNorm kernel)
+            float4 p[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) p[k] = __ldcg(reinterpret_cast<const float4*>(part + (s + k) * part_stride + e));
+            asm volatile("" ::"f"(p[0].x), "f"(p[1].x), "f"(p[2].x), "f"(p[3].x));
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { acc.x += p[k].x; acc.y += p[k].y; acc.z += p[k].z; acc.w += p[k].w; }
+        }
+        for (; s < n_part; ++s) {
             const float4 p = *reinterpret_cast<const float4*>(part + s * part_stride + e);
             acc.x += p.x; acc.y += p.y; acc.z += p.z; acc.w += p.w;
         }
-        if (gelu) { acc.x = gelu_erf(acc.x); acc.y = gelu_erf(acc.y); acc.z = gelu_erf(acc.z); acc.w = gelu_erf(acc.w); }
+        if (gelu) {     // bf16 output: the 1.5e-7 erf approximation is far below its rounding; fp32 output keeps erff
+            if constexpr (sizeof(TY) == 2) {
+                const float2 g01 = gelu_erf_fast2(make_float2(acc.x, acc.y)), g23 = gelu_erf_fast2(make_float2(acc.z, acc.w));
+                acc = make_float4(g01.x, g01.y, g23.x, g23.y);
+            } else {
+                acc.x = gelu_erf(acc.x); acc.y = gelu_erf(acc.y); acc.z = gelu_erf(acc.z); acc.w = gelu_erf(acc.w);
+            }
+        }
         if constexpr (sizeof(TY) == 4) {
             *reinterpret_cast<float4*>(y + e) = acc;
         } else {
