@@ -425,6 +425,11 @@ __global__ void __launch_bounds__(MMA_THREADS, 4) attn_decode_mma_kernel(const f
                 tk[s] = (owns_new && s < n_part) ? __ldcg(src + s * part_stride + d_model) : 0.f;
                 tv[s] = (owns_new && s < n_part) ? __ldcg(src + s * part_stride + 2 * d_model) : 0.f;
             }
+            // consume all 24 registers at once: keeps ptxas from interleaving load and add (a chain of dependent L2 round
+            // trips: q was ready 1.5-2.0 us after the dependency resolved in a B=32 step with 6 slices)
+            asm volatile("" ::"f"(tq[0]), "f"(tq[1]), "f"(tq[2]), "f"(tq[3]), "f"(tq[4]), "f"(tq[5]), "f"(tq[6]), "f"(tq[7]),
+                         "f"(tk[0]), "f"(tk[1]), "f"(tk[2]), "f"(tk[3]), "f"(tk[4]), "f"(tk[5]), "f"(tk[6]), "f"(tk[7]),
+                         "f"(tv[0]), "f"(tv[1]), "f"(tv[2]), "f"(tv[3]), "f"(tv[4]), "f"(tv[5]), "f"(tv[6]), "f"(tv[7]));
             float aq = 0.f, ak = 0.f, av = 0.f;
 #pragma unroll
             for (int s = 0; s < 8; ++s) { aq += tq[s]; ak += tk[s]; av += tv[s]; }

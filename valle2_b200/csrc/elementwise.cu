@@ -1,6 +1,8 @@
 // HBM-bound row kernels of the hot path: embedding-sum + PE (K1/K2), split-K reduce + bias + residual +
 // (Ada)LayerNorm (K3), split-K reduce + bias + erf-GELU (K8), KV scatter into the paged pool (K5), and the
 // device-side beam bookkeeping (K11).  All are coalesced, 16-byte vectorised where the shape allows.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 // ------------------------------------------------------------------------------------------------
@@ -303,6 +305,107 @@ __global__ void __launch_bounds__(256) residual_layernorm_block_kernel(float* __
 #undef LN_STAMP
 }
 
+// Decode rows with many split-K slices: one row spread over a CLUSTER of four CTAs (a quarter of the columns each), so that
+// the 36-68 KB of slices of a row arrive through four SMs' L2 ports instead of one (the one-CTA-per-row kernel spends
+// 1.3-2.0 us of its ~3 us waiting for them -- tools/step_timeline.py).  Inside a CTA the slices are split over 256 / nch
+// thread groups (nch = d / 16 float4 chunks per CTA), summed per group in slice order and then across groups in group order
+// (deterministic); the row statistics (mean, M2 of a quarter row) are exchanged through distributed shared memory and
+// combined with Chan's equal-count formula.  d in {256, 512, 1024}.
+template <typename TY>
+__global__ void __launch_bounds__(256) residual_layernorm_cluster_kernel(float* __restrict__ x, const float* __restrict__ part,
+                                                                         int n_part, int64_t part_stride,
+                                                                         const float* __restrict__ bias,
+                                                                         const float* __restrict__ gamma,
+                                                                         const float* __restrict__ beta, TY* __restrict__ y,
+                                                                         int d, float eps) {
+    __shared__ float4 gsum[256];
+    __shared__ float wred[2][4];
+    __shared__ __align__(8) float2 cstat[4];          // (mean, M2) of each CTA's quarter row, written by every rank
+    const int rank = blockIdx.x;                      // cluster rank == blockIdx.x (cluster = 4 x 1 x 1)
+    const int64_t r = blockIdx.y;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nch = d >> 4;                           // float4 chunks of this CTA's quarter row: 64, 32 or 16
+    const int ng = 256 / nch;                         // slice groups
+    const int chunk = tid % nch, grp = tid / nch;
+    const int c = rank * (d >> 2) + chunk * 4;        // first column of this thread's chunk
+    pdl_trigger();
+    float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f), b4 = g4, bias4 = g4;
+    if (grp == 0) {                                   // weights: before the dependency resolves
+        if (gamma != nullptr && y != nullptr) {
+            g4 = *reinterpret_cast<const float4*>(gamma + c);
+            b4 = *reinterpret_cast<const float4*>(beta + c);
+        }
+        if (bias != nullptr) bias4 = *reinterpret_cast<const float4*>(bias + c);
+    }
+    pdl_wait();
+    float* xr = x + r * d;
+    const float* pp = part + r * d + c;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 xv = acc;
+    if (grp == 0) xv = *reinterpret_cast<const float4*>(xr + c);
+    {
+        float4 p[4];                                  // up to four slices of this group in flight (16 slices, 4 groups)
+        int s = grp;
+        for (; s + 3 * ng < n_part; s += 4 * ng) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) p[k] = __ldcg(reinterpret_cast<const float4*>(pp + static_cast<int64_t>(s + k * ng) * part_stride));
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { acc.x += p[k].x; acc.y += p[k].y; acc.z += p[k].z; acc.w += p[k].w; }
+        }
+        for (; s < n_part; s += ng) {
+            const float4 q = __ldcg(reinterpret_cast<const float4*>(pp + static_cast<int64_t>(s) * part_stride));
+            acc.x += q.x; acc.y += q.y; acc.z += q.z; acc.w += q.w;
+        }
+    }
+    gsum[tid] = acc;
+    __syncthreads();
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (grp == 0) {                                   // nch threads (1/2, 1 or 2 warps) finish the row quarter
+        float4 t = bias4;
+        for (int g = 0; g < ng; ++g) { const float4 q = gsum[g * nch + chunk]; t.x += q.x; t.y += q.y; t.z += q.z; t.w += q.w; }
+        a = make_float4(xv.x + t.x, xv.y + t.y, xv.z + t.z, xv.w + t.w);
+        *reinterpret_cast<float4*>(xr + c) = a;
+    }
+    if (y == nullptr) return;                         // uniform: residual update only
+    TY* yr = y + r * d;
+    if (gamma == nullptr) {                           // plain cast
+        if (grp == 0) {
+            if constexpr (sizeof(TY) == 4) *reinterpret_cast<float4*>(yr + c) = a;
+            else *reinterpret_cast<uint2*>(yr + c) = make_uint2(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w));
+        }
+        return;
+    }
+    // quarter-row statistics: the first nch threads hold the values (whole warps: nch is 16, 32 or 64)
+    const int nw = (nch + 31) >> 5;                   // warps that hold data: 1 or 2
+    const float cnt = static_cast<float>(d >> 2);
+    float sm = (grp == 0) ? (a.x + a.y) + (a.z + a.w) : 0.f;
+    if (warp < nw) { sm = warp_sum(sm); if (lane == 0) wred[0][warp] = sm; }
+    __syncthreads();
+    const float mean_c = ((nw == 2) ? wred[0][0] + wred[0][1] : wred[0][0]) / cnt;
+    float m2 = 0.f;
+    if (grp == 0) { const float e0 = a.x - mean_c, e1 = a.y - mean_c, e2 = a.z - mean_c, e3 = a.w - mean_c; m2 = (e0 * e0 + e1 * e1) + (e2 * e2 + e3 * e3); }
+    if (warp < nw) { m2 = warp_sum(m2); if (lane == 0) wred[1][warp] = m2; }
+    __syncthreads();
+    if (tid < 4) {                                    // thread t publishes this CTA's (mean, M2) into rank t's cstat[rank]
+        const float m2_c = (nw == 2) ? wred[1][0] + wred[1][1] : wred[1][0];
+        uint32_t ra;
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(&cstat[rank])), "r"(tid));
+        asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(ra), "f"(mean_c), "f"(m2_c) : "memory");
+    }
+    asm volatile("barrier.cluster.arrive.release.aligned;\n barrier.cluster.wait.acquire.aligned;" ::: "memory");
+    if (grp == 0) {
+        const float2 s0 = cstat[0], s1 = cstat[1], s2 = cstat[2], s3 = cstat[3];
+        const float mean = ((s0.x + s1.x) + (s2.x + s3.x)) * 0.25f;
+        const float dev = ((s0.x - mean) * (s0.x - mean) + (s1.x - mean) * (s1.x - mean)) + ((s2.x - mean) * (s2.x - mean) + (s3.x - mean) * (s3.x - mean));
+        const float var = (((s0.y + s1.y) + (s2.y + s3.y)) + cnt * dev) / static_cast<float>(d);
+        const float rstd = rsqrtf(var + eps);
+        const float o0 = (a.x - mean) * rstd * g4.x + b4.x, o1 = (a.y - mean) * rstd * g4.y + b4.y;
+        const float o2 = (a.z - mean) * rstd * g4.z + b4.z, o3 = (a.w - mean) * rstd * g4.w + b4.w;
+        if constexpr (sizeof(TY) == 4) *reinterpret_cast<float4*>(yr + c) = make_float4(o0, o1, o2, o3);
+        else *reinterpret_cast<uint2*>(yr + c) = make_uint2(pack_bf16x2(o0, o1), pack_bf16x2(o2, o3));
+    }
+}
+
 static unsigned long long* g_ln_dbg = nullptr;
 extern "C" int vb_residual_layernorm_set_debug(void* buf) {   /* device buffer of R * 4 uint64 stamps (decode-shape launches), or NULL */
     g_ln_dbg = static_cast<unsigned long long*>(buf);
@@ -312,6 +415,28 @@ extern "C" int vb_residual_layernorm_set_debug(void* buf) {   /* device buffer o
 template <typename TY>
 static int launch_rln(float* x, const float* part, int n_part, int64_t part_stride, const float* bias, const float* gamma,
                       const float* beta, TY* y, int64_t R, int d, float eps, cudaStream_t st) {
+    static const bool ln_cluster = !(getenv("VALLE_B200_LN_CLUSTER") != nullptr && getenv("VALLE_B200_LN_CLUSTER")[0] == '0');
+    if (ln_cluster && g_ln_dbg == nullptr && R <= 1024 && n_part >= 4 && (d == 256 || d == 512 || d == 1024)) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(4, static_cast<unsigned>(R));
+        cfg.blockDim = dim3(256);
+        cfg.dynamicSmemBytes = 0;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[2];
+        int na = 0;
+        if (vb_pdl_enabled()) {
+            attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            attr[na].val.programmaticStreamSerializationAllowed = 1;
+            ++na;
+        }
+        attr[na].id = cudaLaunchAttributeClusterDimension;
+        attr[na].val.clusterDim.x = 4; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+        ++na;
+        cfg.attrs = attr;
+        cfg.numAttrs = na;
+        VB_CUDA(cudaLaunchKernelEx(&cfg, residual_layernorm_cluster_kernel<TY>, x, part, n_part, part_stride, bias, gamma, beta, y, d, eps));
+        return VB_OK;
+    }
     if (R <= 1024 && d % 4 == 0 && d <= 4096) {
         VB_CUDA(vb_launch(true, residual_layernorm_block_kernel<TY>, dim3(static_cast<unsigned>(R)), dim3(256), 0, st, x, part, n_part,
                           part_stride, bias, gamma, beta, y, d, eps, g_ln_dbg));

@@ -159,6 +159,7 @@ class ARDecoder:
         # lean path, >= 4 sequences: the attention kernel releases its successors only after its own wait (see
         # csrc/attn_decode.cu; measured -2 % step time at B = 4..8, +2 % at B = 1, tools/step_breakdown.py)
         self.attn_late = ops.FLAG_LATE_TRIGGER if os.environ.get('VALLE_B200_ATTN_LATE', '1') != '0' else 0
+        self.attn_late_splitk = ops.FLAG_LATE_TRIGGER if os.environ.get('VALLE_B200_ATTN_LATE_SPLITK', '0') != '0' else 0   # A/B
         self.qkv_late_all = os.environ.get('VALLE_B200_QKV_LATE_ALL', '0') != '0'      # A/B: late PDL trigger in every layer
         self.n_sub_override = int(os.environ.get('VALLE_B200_SUBBATCH', '0'))
         self.attn_ctas = int(os.environ.get('VALLE_B200_ATTN_CTAS', '0'))
@@ -420,7 +421,7 @@ class ARDecoder:
                     qkv_part, qkv_n = sub['p_qkv'], ns['qkv']
                 ops.attn_decode_paged(qkv_part, qkv_n, B * 3 * d, st['pools'][li], sub['block_table'],
                                       sub['seq_lens'], sub['o'], B, H, Dh, sub['n_tsplit'], sub['attn_ws'],
-                                      ops.FLAG_PREFETCH_KV | self.attn_flags)
+                                      ops.FLAG_PREFETCH_KV | self.attn_flags | self.attn_late_splitk)
                 g, b, eps = L['norm2']
                 if mix['o'] == 'r':
                     ops.linear_decode_rows(sub['o'], L['wo'], x, bias=L['bo'], residual=True)
@@ -456,7 +457,7 @@ class ARDecoder:
                 ops.linear_decode_fused(x, L['wqkv'], sub['qkv32'], gamma=g[0], beta=b[0], eps=eps, cluster_k=cl['qkv'],
                                         flags=ops.FLAG_LATE_TRIGGER)
                 ops.attn_decode_paged(sub['qkv32'], 1, 0, st['pools'][li], sub['block_table'], sub['seq_lens'], sub['o'],
-                                      B, H, Dh, sub['n_tsplit'], sub['attn_ws'], ops.FLAG_PREFETCH_KV | self.attn_flags)
+                                      B, H, Dh, sub['n_tsplit'], sub['attn_ws'], ops.FLAG_PREFETCH_KV | self.attn_flags | self.attn_late_splitk)
                 ops.linear_decode_fused(sub['o'], L['wo'], x, bias=L['bo'], residual=True, cluster_k=cl['o'])
                 g, b, eps = L['norm2']
                 ops.linear_decode_fused(x, L['w1'], sub['f'], bias=L['b1'], gelu=True, gamma=g[0], beta=b[0], eps=eps,
@@ -473,7 +474,7 @@ class ARDecoder:
             for li, L in enumerate(layers):
                 ops.attn_decode_paged(sub['p_qkv'], ns['qkv'], B * 3 * d, st['pools'][li], sub['block_table'],
                                       sub['seq_lens'], sub['o'], B, H, Dh, sub['n_tsplit'], sub['attn_ws'],
-                                      ops.FLAG_PREFETCH_KV | self.attn_flags)
+                                      ops.FLAG_PREFETCH_KV | self.attn_flags | self.attn_late_splitk)
                 g2, b2, eps2 = L['norm2']
                 ph = [ops.chain_gemm(sub['o'], L['wo'], sub['p_o'], B * d),
                       ops.chain_ln(x, g2[0], b2[0], sub['h'], part=sub['p_o'], n_part=ns['o'], part_stride=B * d,
@@ -506,7 +507,7 @@ class ARDecoder:
                 ops.linear_decode(sub['h'], L['wqkv'], sub['p_qkv'], B * 3 * d, 32, ops.FLAG_LATE_TRIGGER)
                 ops.attn_decode_paged(sub['p_qkv'], ns['qkv'], B * 3 * d, st['pools'][li], sub['block_table'],
                                       sub['seq_lens'], sub['o'], B, H, Dh, sub['n_tsplit'], sub['attn_ws'],
-                                      ops.FLAG_PREFETCH_KV | self.attn_flags)
+                                      ops.FLAG_PREFETCH_KV | self.attn_flags | self.attn_late_splitk)
                 self._prefetch_next_kv(sub, li)
                 ops.linear_decode(sub['o'], L['wo'], sub['p_o'], B * d, 32)
                 g, b, eps = L['norm2']
