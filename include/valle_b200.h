@@ -75,7 +75,8 @@ int vb_embed_sum_pe(const int32_t* ids, const float* tables, const float* pe, fl
  * y[r,:] = (x[r,:] - mean) * rsqrt(var + eps) * gamma + beta           (y may be NULL: residual update only;
  *                                                                        gamma = beta = NULL: y = cast(x), no norm)
  * x: fp32 [R][d]; gamma/beta fp32 [d] (AdaLN: pre-folded w*gamma, w*beta+b -- modules.py:93-99); y: y_dtype [R][d].
- * Replaces nn.LayerNorm at modules.py:89,234-235,271,278 and the residual adds :277-278 on the decode path. */
+ * Replaces nn.LayerNorm at modules.py:89,234-235,271,278 and the residual adds :277-278 on the decode path.
+ * Decode rows (R <= 1024) with n_part >= 4 and d in {256, 512, 1024} run one row over a cluster of four CTAs. */
 int vb_residual_layernorm(float* x, const float* part, int n_part, int64_t part_stride, const float* bias,
                           const float* gamma, const float* beta, void* y, int y_dtype,
                           int64_t R, int d, float eps, void* stream);
