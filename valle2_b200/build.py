@@ -9,6 +9,7 @@ GPU-less host too (symbols only -- no compute without a device).
 from __future__ import annotations
 
 import concurrent.futures
+import fcntl
 import os
 import subprocess
 import sys
@@ -29,16 +30,28 @@ def sources() -> list[str]:
     return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith('.cu'))
 
 
-def _newest(paths) -> float:
-    return max(os.path.getmtime(p) for p in paths)
+HASH = os.path.join(LIBDIR, 'libvalle_b200.srchash')
+
+
+def _source_hash() -> str:
+    """Content hash of everything the library is built from (file times do not survive a copy of the tree to a GPU box)."""
+    import hashlib
+    h = hashlib.sha256()
+    deps = sources() + sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith('.cuh'))
+    deps.append(os.path.join(os.path.dirname(HERE), 'include', 'valle_b200.h'))
+    for path in deps:
+        h.update(os.path.basename(path).encode())
+        with open(path, 'rb') as fh:
+            h.update(fh.read())
+    h.update(' '.join(NVCC_FLAGS).encode())
+    return h.hexdigest()
 
 
 def needs_build() -> bool:
-    if not os.path.exists(LIB):
+    if not os.path.exists(LIB) or not os.path.exists(HASH):
         return True
-    deps = sources() + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith('.cuh')]
-    deps.append(os.path.join(os.path.dirname(HERE), 'include', 'valle_b200.h'))
-    return _newest(deps) > os.path.getmtime(LIB)
+    with open(HASH) as fh:
+        return fh.read().strip() != _source_hash()
 
 
 def _compile(src: str) -> str:
@@ -51,16 +64,31 @@ def _compile(src: str) -> str:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile + link if the library is missing or older than its sources.  Safe under concurrency (one process per GPU
+    under torchrun, all importing at once): an exclusive file lock serialises the builders, the check is repeated under
+    the lock, and the library is linked to a temporary name and renamed into place atomically."""
     if not force and not needs_build():
         return LIB
     os.makedirs(LIBDIR, exist_ok=True)
     os.makedirs(OBJDIR, exist_ok=True)
-    with concurrent.futures.ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
-        objs = list(ex.map(_compile, sources()))
-    cmd = ['nvcc', '-shared', '-gencode', 'arch=compute_100a,code=sm_100a', '-o', LIB, *objs, '-cudart', 'static']
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    if r.returncode != 0:
-        raise RuntimeError(f'link failed:\n{r.stdout}\n{r.stderr}')
+    with open(os.path.join(LIBDIR, '.build.lock'), 'w') as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not needs_build():        # another process built it while we waited
+                return LIB
+            with concurrent.futures.ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
+                objs = list(ex.map(_compile, sources()))
+            tmp = f'{LIB}.tmp.{os.getpid()}'
+            cmd = ['nvcc', '-shared', '-gencode', 'arch=compute_100a,code=sm_100a', '-o', tmp, *objs, '-cudart', 'static']
+            r = subprocess.run(cmd, capture_output=True, text=True)
+            if r.returncode != 0:
+                raise RuntimeError(f'link failed:\n{r.stdout}\n{r.stderr}')
+            os.replace(tmp, LIB)
+            with open(HASH + '.tmp', 'w') as fh:
+                fh.write(_source_hash())
+            os.replace(HASH + '.tmp', HASH)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     if verbose:
         print('built', LIB)
     return LIB
