@@ -48,9 +48,9 @@ def test_embed_sum_pe(ops):
     assert torch.equal(out2[:, 0], ref2)
 
 
-@pytest.mark.parametrize('d', [1024, 256, 64, 96])
+@pytest.mark.parametrize('d', [1024, 512, 256, 64, 96])
 @pytest.mark.parametrize('ydt', [torch.float32, torch.bfloat16])
-@pytest.mark.parametrize('R,ns', [(37, 3), (1500, 5), (3, 16)])
+@pytest.mark.parametrize('R,ns', [(37, 3), (1500, 5), (3, 16), (32, 8), (1, 4), (32, 6)])      # ns >= 4, R <= 1024, d in {256,512,1024}: 4-CTA cluster kernel
 def test_residual_layernorm(ops, d, ydt, R, ns):
     torch.manual_seed(1)
     x = torch.randn(R, d, device='cuda') * 2 + 0.5
@@ -69,6 +69,14 @@ def test_residual_layernorm(ops, d, ydt, R, ns):
     xr = x.cpu() + (bias.cpu() + part.cpu().sum(0))
     assert rel_err(x2, xr) < 2e-6
     assert rel_err(y.float(), vo.layer_norm(xr, g.cpu(), b.cpu())) < tol
+    # residual update only (y = None) and slices + plain cast (the last decode LayerNorm call of a step, K-2)
+    x3 = x.clone()
+    ops.residual_layernorm(x3, None, None, None, part=part, n_part=ns, part_stride=R * d, bias=bias)
+    assert rel_err(x3, xr) < 2e-6
+    x4 = x.clone()
+    ops.residual_layernorm(x4, None, None, y, part=part, n_part=ns, part_stride=R * d, bias=bias)
+    assert rel_err(x4, xr) < 2e-6
+    assert torch.equal(y, x4) if ydt == torch.float32 else rel_err(y.float(), x4) < 4e-3     # y = cast(updated x)
     # cast-only mode
     ops.residual_layernorm(x2, None, None, y)
     assert rel_err(y.float(), x2) < (1e-7 if ydt == torch.float32 else 4e-3)
