@@ -1,3 +1,5 @@
+# sub-batch overlap on the depth-1 PDL build vs the product build (tools/ab_sub.sh "gemm sub attn_ctas")
 export VALLE_B200_LIB=$PWD/valle2_b200/lib/libvalle_b200_depth1.so
-tools/ab_sub.sh "rows 2 128" "rows 2 192" "rows 2 320" "srrrs 2 256" "rrrrs 2 256" "srrss 2 256" "rsrrr 2 256" "rrsrr 2 256" "rrrsr 2 256"
-VALLE_B200_ROWS_QKV_SPLIT=2 tools/ab_sub.sh "rows 2 256" | tail -1
+tools/ab_sub.sh "splitk 1 0" "rsrrr 2 256" "rows 2 256" "splitk 2 256" "srsss 2 256"
+unset VALLE_B200_LIB
+tools/ab_sub.sh "splitk 1 0" "rsrrr 2 256" "splitk 2 256"
