@@ -149,3 +149,21 @@ def test_collate_empty_and_single():
     assert x.shape == (1, 4) and lens.tolist() == [4]
     x, lens = collate_list([])
     assert x.numel() == 0 and lens.numel() == 0
+
+
+def test_train_model_host_side_sharding_and_items(tmp_path):
+    """valle.train_model host logic (no GPU): synthetic items obey the collate's contract (more frames than phonemes), and the
+    per-rank batches of one step partition the global batch without overlap."""
+    from valle.collate import get_collate
+    from valle.train_model import batches, synthetic_items
+    cfg = synth.tiny_config('LayerNorm')
+    items = synthetic_items(cfg, 24, seed=3)
+    assert len(items) == 24 and all(it['codes'].shape[0] == cfg.num_quantizers and it['codes'].shape[1] > it['tokens'].numel() for it in items)
+    collate_fn = get_collate('ValleAR')(cfg)
+    world, bs = 3, 2
+    per_rank = [list(batches(items, bs, collate_fn, r, world)) for r in range(world)]
+    assert all(len(b) == 24 // (bs * world) for b in per_rank)
+    step0 = torch.cat([per_rank[r][0]['tokens_lens'] for r in range(world)])
+    expect = torch.tensor([items[i]['tokens'].numel() for i in range(bs * world)])
+    assert torch.equal(step0, expect)
+    assert per_rank[0][0]['codes'].shape[0] == bs and int(per_rank[0][0]['codes'][0, 0]) == cfg.bos_token
