@@ -297,7 +297,7 @@ def test_forward_lse_feeds_attention_backward(ops, mode):
 
 
 def test_train_model_driver_end_to_end(tmp_path):
-    """N3: the reference's training entry point (valle/train_model.py:13-44, CLI repaired per A-12) on synthetic items of the
+    """N3: the reference's training entry point (valle/train_model.py:13-44, CLI repaired per A-11) on synthetic items of the
     wire format: collate -> training_step -> backward -> clip -> AdamW + scheduler, gradient accumulation; the loss falls."""
     import json
     from valle import train_model as tm

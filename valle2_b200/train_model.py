@@ -1,7 +1,7 @@
 """Training driver: the caller of ``training_step``, mirroring ``valle/train_model.py:13-44``.
 
     python -m valle.train_model -c cfg.json -m ValleAR                      # reference CLI (``args.config``: upstream reads a
-                                                                            # non-existent ``args.hparams`` -- defect A-12)
+                                                                            # non-existent ``args.hparams`` -- defect A-11)
     torchrun --nproc-per-node 8 -m valle.train_model -c cfg.json -m ValleAR --synthetic 64
 
 ``train(hparams_fp, model_name)`` keeps the reference's signature and order of operations: config from JSON, seed, model from
@@ -120,7 +120,7 @@ def main(argv=None):
     import os
     if int(os.environ.get('WORLD_SIZE', '1')) > 1 and not torch.distributed.is_initialized():
         torch.distributed.init_process_group('nccl' if torch.cuda.is_available() else 'gloo')
-    train(args.config, args.model, synthetic=args.synthetic, max_steps=args.max_steps)      # upstream: args.hparams (A-12)
+    train(args.config, args.model, synthetic=args.synthetic, max_steps=args.max_steps)      # upstream: args.hparams (A-11)
 
 
 if __name__ == '__main__':
