@@ -118,9 +118,17 @@ def main(argv=None):
     parser.add_argument('--max-steps', type=int, default=None)
     args = parser.parse_args(argv)
     import os
+    started = False
     if int(os.environ.get('WORLD_SIZE', '1')) > 1 and not torch.distributed.is_initialized():
+        if torch.cuda.is_available():
+            torch.cuda.set_device(int(os.environ.get('LOCAL_RANK', '0')))
         torch.distributed.init_process_group('nccl' if torch.cuda.is_available() else 'gloo')
-    train(args.config, args.model, synthetic=args.synthetic, max_steps=args.max_steps)      # upstream: args.hparams (A-11)
+        started = True
+    try:
+        train(args.config, args.model, synthetic=args.synthetic, max_steps=args.max_steps)  # upstream: args.hparams (A-11)
+    finally:
+        if started:
+            torch.distributed.destroy_process_group()
 
 
 if __name__ == '__main__':
