@@ -311,7 +311,7 @@ def test_train_model_driver_end_to_end(tmp_path):
     losses = tm.train(fp, 'ValleAR', synthetic=8, log=lines.append)
     assert len(losses) == 6 and all(math.isfinite(v) for v in losses)
     assert losses[-1] < losses[0] - 0.5, losses          # 8 items seen repeatedly: the model starts to memorise them
-    assert any('ms/step' in ln for ln in lines)
+    assert any('ms/step' in ln and 'this step' in ln for ln in lines)
     with pytest.raises(RuntimeError, match='out of scope'):
         tm.train(fp, 'ValleAR')
     # the CLI parses the reference's flags

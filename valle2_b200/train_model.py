@@ -59,6 +59,7 @@ def fit(model, loader, config: ConfigValle, *, max_steps: int | None = None, log
     max_steps = config.max_steps if max_steps is None else max_steps
     accum = max(1, int(config.grad_accum))
     losses, micro, t0 = [], 0, time.time()
+    t_prev = t0
     model.train()
     optimizer.zero_grad(set_to_none=True)
     while len(losses) < max_steps:
@@ -78,9 +79,12 @@ def fit(model, loader, config: ConfigValle, *, max_steps: int | None = None, log
             if scheduler is not None:
                 scheduler.step()
             optimizer.zero_grad(set_to_none=True)
-            losses.append(float(loss.detach()))
+            losses.append(float(loss.detach()))                      # the step's one host sync
+            t_now = time.time()
             if rank == 0 and (len(losses) % max(1, int(config.log_every_n_steps)) == 0 or len(losses) == max_steps):
-                log(f'step {len(losses)}  loss {losses[-1]:.4f}  {(time.time() - t0) / len(losses) * 1e3:.1f} ms/step')
+                log(f'step {len(losses)}  loss {losses[-1]:.4f}  this step {(t_now - t_prev) * 1e3:.1f} ms  '
+                    f'(mean {(t_now - t0) / len(losses) * 1e3:.1f} ms/step)')
+            t_prev = t_now
             if len(losses) >= max_steps:
                 break
         if not progressed:
@@ -89,7 +93,7 @@ def fit(model, loader, config: ConfigValle, *, max_steps: int | None = None, log
 
 
 def train(hparams_fp: Path, model_name: str, *, loaders=None, synthetic: int = 0, max_steps: int | None = None,
-          device: str | None = None, log=print) -> list[float]:
+          device: str | None = None, log=print, frames: tuple[int, int] = (60, 150)) -> list[float]:
     """``valle/train_model.py:13-36`` with the loop written out.  ``loaders`` = a callable returning an iterable of batch
     dicts (e.g. a ``DataLoader`` with ``collate_fn=get_collate(model_name)(config)``); ``synthetic`` > 0 builds one."""
     config = ConfigValle.from_json(hparams_fp)
@@ -102,7 +106,7 @@ def train(hparams_fp: Path, model_name: str, *, loaders=None, synthetic: int = 0
     if loaders is None:
         if synthetic <= 0:
             raise RuntimeError('valle.data (HF datasets + EnCodec + g2p) is out of scope of valle2_b200: pass loaders= or --synthetic N')
-        items = synthetic_items(config, synthetic, config.seed)
+        items = synthetic_items(config, synthetic, config.seed, min_frames=frames[0], max_frames=frames[1])
         collate_fn = get_collate(model_name)(config)
         loaders = lambda: batches(items, config.batch_size, collate_fn, rank, world_size)   # noqa: E731
     if rank == 0:
@@ -116,6 +120,7 @@ def main(argv=None):
     parser.add_argument('-m', '--model', type=str, choices=['ValleAR', 'ValleNAR'], required=True)
     parser.add_argument('--synthetic', type=int, default=0, help='train on N random items instead of valle.data')
     parser.add_argument('--max-steps', type=int, default=None)
+    parser.add_argument('--frames', type=int, nargs=2, default=(60, 150), help='frame range of the synthetic clips (75 frames = 1 s)')
     args = parser.parse_args(argv)
     import os
     started = False
@@ -125,7 +130,8 @@ def main(argv=None):
         torch.distributed.init_process_group('nccl' if torch.cuda.is_available() else 'gloo')
         started = True
     try:
-        train(args.config, args.model, synthetic=args.synthetic, max_steps=args.max_steps)  # upstream: args.hparams (A-11)
+        train(args.config, args.model, synthetic=args.synthetic, max_steps=args.max_steps,       # upstream: args.hparams (A-11)
+              frames=tuple(args.frames))
     finally:
         if started:
             torch.distributed.destroy_process_group()
