@@ -326,7 +326,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
 
     if rank == 0 and not args.no_extras:
         result['extras'] = extras(args, dev, tmp)
-        result['cpu_baseline'] = cpu_baseline(model, B, budget_s=20.0)
+        result['cpu_baseline'] = cpu_baseline(model, B, budget_s=12.0)
     return result
 
 
@@ -486,9 +486,9 @@ def cpu_baseline(model, B: int, budget_s: float):
     torch.set_num_threads(os.cpu_count() or 1)
     oc = OracleConfig.from_any(model.config)
     sd = {k: v.detach().float().cpu() for k, v in model.state_dict().items()}
-    ctx = TX + P0
-    rate1, t1 = _cpu_decode_rate(sd, oc, B, 1, ctx, warm=1)
-    n = max(2, min(32, int(budget_s / max(t1, 1e-3))))
+    rate1, t1 = _cpu_decode_rate(sd, oc, B, 1, int(MEAN_CTX), warm=1)
+    n = max(2, min(160, int(budget_s / max(t1, 1e-3))))          # bounded sample: ~budget_s seconds of CPU work
+    ctx = int(MEAN_CTX - n / 2)                                   # centred on the GPU workload's mean context
     rate, total = _cpu_decode_rate(sd, oc, B, n, ctx, warm=0)
     return {'value': rate, 'unit': 'tokens/s', 'cores': torch.get_num_threads(), 'kind': 'port',
             'sample': f'oracle port (fp32, torch CPU ops, reference algorithm incl. torch.cat KV growth): {n} decode steps at batch '
