@@ -175,6 +175,9 @@ __global__ void __launch_bounds__(THREADS, 2) attn_bwd_dq_tc_kernel(const __grid
             lse2 = (l == INFINITY) ? INFINITY : l * 1.4426950408889634f;
         }
         const float scale_log2e = scale * 1.4426950408889634f;
+        // lse2 = +inf (row attends nothing, or i >= S): -inf - inf stays -inf for a masked score, p = 0, dS = 0 * finite = 0
+        const float2 sc2 = make_float2(scale_log2e, scale_log2e), nl2 = make_float2(-lse2, -lse2);
+        const float2 ss2 = make_float2(scale, scale), nd2 = make_float2(-dl * scale, -dl * scale);
         const uint32_t ds_row = ds_smem + r * 128;
         for (int j = 0; j < nb; ++j) {
             mbar_wait(smem_u32(&bar_s), j & 1);
@@ -209,12 +212,11 @@ __global__ void __launch_bounds__(THREADS, 2) attn_bwd_dq_tc_kernel(const __grid
                 }
                 uint32_t pk[16];
 #pragma unroll
-                for (int c = 0; c < 32; c += 2) {
-                    const float p0 = ex2(fmaf(__uint_as_float(sv[c]), scale_log2e, -lse2));
-                    const float p1 = ex2(fmaf(__uint_as_float(sv[c + 1]), scale_log2e, -lse2));
-                    const float d0 = p0 * (__uint_as_float(dv[c]) - dl) * scale;
-                    const float d1 = p1 * (__uint_as_float(dv[c + 1]) - dl) * scale;
-                    pk[c >> 1] = pack_bf16x2(d0, d1);
+                for (int c = 0; c < 32; c += 2) {      // packed fp32x2: t = s scale log2e - lse2, g = dp scale - delta scale, dS = p g
+                    const float2 t = __ffma2_rn(make_float2(__uint_as_float(sv[c]), __uint_as_float(sv[c + 1])), sc2, nl2);
+                    const float2 g2 = __ffma2_rn(make_float2(__uint_as_float(dv[c]), __uint_as_float(dv[c + 1])), ss2, nd2);
+                    const float2 ds2 = __fmul2_rn(make_float2(ex2(t.x), ex2(t.y)), g2);
+                    pk[c >> 1] = pack_bf16x2(ds2.x, ds2.y);
                 }
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
@@ -407,16 +409,17 @@ __global__ void __launch_bounds__(THREADS, 2) attn_bwd_dkv_tc_kernel(const __gri
         const int64_t bh = static_cast<int64_t>(b) * H + h;
         const float scale_log2e = scale * 1.4426950408889634f;
         const bool key_ok = kj < kv_len;
+        const float2 sc2 = make_float2(scale_log2e, scale_log2e), ss2 = make_float2(scale, scale);
         const uint32_t pt_row = pt_smem + r * 128, dst_row = dst_smem + r * 128;
         for (int ib = 0; ib < nb; ++ib) {
             const int i0 = i_begin + ib * BI;
             {   // lse (log2 units) and delta of this block's queries: threads 0..63 / 64..127 fetch one value each
                 const int qi = i0 + (sid & 63);
-                if (sid < 64) {
+                if (sid < 64) {      // staged as the addends of the two fused multiply-adds: -lse log2e and -delta scale
                     const float l = (qi < S) ? lse[bh * S + qi] : INFINITY;
-                    lse_s[ib & 1][sid] = (l == INFINITY) ? INFINITY : l * 1.4426950408889634f;
+                    lse_s[ib & 1][sid] = (l == INFINITY) ? -INFINITY : -l * 1.4426950408889634f;
                 } else {
-                    dl_s[ib & 1][sid - 64] = (qi < S) ? delta[bh * S + qi] : 0.f;
+                    dl_s[ib & 1][sid - 64] = (qi < S) ? -delta[bh * S + qi] * scale : 0.f;
                 }
             }
             asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -447,20 +450,26 @@ __global__ void __launch_bounds__(THREADS, 2) attn_bwd_dkv_tc_kernel(const __gri
                 for (int c = 0; c < 32; c += 4) {
                     const float4 l4 = *reinterpret_cast<const float4*>(ls + half * 32 + c);
                     const float4 d4 = *reinterpret_cast<const float4*>(ds_ + half * 32 + c);
-                    const float lq[4] = {l4.x, l4.y, l4.z, l4.w}, dq_[4] = {d4.x, d4.y, d4.z, d4.w};
-                    float p[4], g[4];
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const int qi = i0 + half * 32 + c + e;
-                        bool ok = key_ok;
-                        if (need_mask) ok = ok && ((kj < x_len) || (qi >= x_len && kj <= qi));
-                        p[e] = ok ? ex2(fmaf(__uint_as_float(sv[c + e]), scale_log2e, -lq[e])) : 0.f;
-                        g[e] = p[e] * (__uint_as_float(dv[c + e]) - dq_[e]) * scale;
+                    // packed fp32x2: t = s scale log2e + (-lse2_q), g = dp scale + (-delta_q scale), dS^T = p g
+                    float2 t01 = __ffma2_rn(make_float2(__uint_as_float(sv[c]), __uint_as_float(sv[c + 1])), sc2, make_float2(l4.x, l4.y));
+                    float2 t23 = __ffma2_rn(make_float2(__uint_as_float(sv[c + 2]), __uint_as_float(sv[c + 3])), sc2, make_float2(l4.z, l4.w));
+                    const float2 g01 = __ffma2_rn(make_float2(__uint_as_float(dv[c]), __uint_as_float(dv[c + 1])), ss2, make_float2(d4.x, d4.y));
+                    const float2 g23 = __ffma2_rn(make_float2(__uint_as_float(dv[c + 2]), __uint_as_float(dv[c + 3])), ss2, make_float2(d4.z, d4.w));
+                    if (!key_ok) { t01 = make_float2(-INFINITY, -INFINITY); t23 = t01; }
+                    else if (need_mask) {
+                        const int qi = i0 + half * 32 + c;
+                        const bool pre = kj < x_len;
+                        if (!(pre || (qi >= x_len && kj <= qi))) t01.x = -INFINITY;
+                        if (!(pre || (qi + 1 >= x_len && kj <= qi + 1))) t01.y = -INFINITY;
+                        if (!(pre || (qi + 2 >= x_len && kj <= qi + 2))) t23.x = -INFINITY;
+                        if (!(pre || (qi + 3 >= x_len && kj <= qi + 3))) t23.y = -INFINITY;
                     }
-                    pk[c >> 1] = pack_bf16x2(p[0], p[1]);
-                    pk[(c >> 1) + 1] = pack_bf16x2(p[2], p[3]);
-                    dk_[c >> 1] = pack_bf16x2(g[0], g[1]);
-                    dk_[(c >> 1) + 1] = pack_bf16x2(g[2], g[3]);
+                    const float2 p01 = make_float2(ex2(t01.x), ex2(t01.y)), p23 = make_float2(ex2(t23.x), ex2(t23.y));
+                    const float2 s01 = __fmul2_rn(p01, g01), s23 = __fmul2_rn(p23, g23);
+                    pk[c >> 1] = pack_bf16x2(p01.x, p01.y);
+                    pk[(c >> 1) + 1] = pack_bf16x2(p23.x, p23.y);
+                    dk_[c >> 1] = pack_bf16x2(s01.x, s01.y);
+                    dk_[(c >> 1) + 1] = pack_bf16x2(s23.x, s23.y);
                 }
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
