@@ -29,6 +29,13 @@ constexpr int P_BYTES = BQ * BKV * 2;         // 16 KB
 constexpr int SMEM_BYTES = Q_BYTES + KV_STAGES * 2 * KV_BYTES + P_BYTES + 1024;
 constexpr int TMEM_COLS = 128;                // S: cols [0,64), PV: cols [64,128)
 
+// three-input maximum (FMNMX3 on sm_100): the row-maximum pass needs 32 instead of 64 instructions per 64-key block
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+    float r;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
+}
+
 __device__ __forceinline__ float fast_exp2(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -178,7 +185,7 @@ __global__ void __launch_bounds__(THREADS, 3) attn_prefill_tc_kernel(const __gri
                     }
                 } else {
 #pragma unroll
-                    for (int c = 0; c < 32; ++c) mx = fmaxf(mx, __uint_as_float(sv[c]));
+                    for (int c = 0; c < 32; c += 2) mx = fmax3(mx, __uint_as_float(sv[c]), __uint_as_float(sv[c + 1]));
                 }
             }
             const float m_blk = mx * scale_log2e;
