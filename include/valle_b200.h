@@ -224,6 +224,10 @@ int vb_attention(const void* q, const void* k, const void* v, int dtype,
 int vb_attention_prefill_tc(const void* qkv, void* o, int B, int S, int H, int mask_mode,
                             const int32_t* x_lens, const int32_t* kv_lens, float* lse, void* stream);
 
+/* Profiling aid: subsequent vb_attention_prefill_tc launches write SM cycle stamps of one row thread per CTA,
+ * [cta][key block < 32][4] = {S ready, row maximum known, previous PV done, P written} (int64); NULL switches it off. */
+int vb_attention_prefill_set_debug(void* buf);
+
 /* Paged KV pool layout (one pool per layer): [page][2 (K,V)][H][page_size=64][Dh=64], dtype f32 or bf16.
  * bf16 pools with Dh = 64 store the eight 16-byte chunks of a token row XOR-swizzled: chunk c of token slot t sits at
  * chunk c ^ (t & 7) (so that a page copied linearly into shared memory is read by ldmatrix without bank conflicts).

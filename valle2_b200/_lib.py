@@ -49,6 +49,7 @@ SIGNATURES = {
     'vb_decode_chain_set_debug': (_i, [_p]),
     'vb_linear_decode_set_debug': (_i, [_p]),
     'vb_attn_decode_set_debug': (_i, [_p]),
+    'vb_attention_prefill_set_debug': (_i, [_p]),
     'vb_residual_layernorm_set_debug': (_i, [_p]),
     'vb_linear_decode_rows_set_debug': (_i, [_p]),
     'vb_attention': (_i, [_p, _p, _p, _i, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _p, _i, _i64, _i64,

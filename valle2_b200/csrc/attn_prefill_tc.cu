@@ -47,10 +47,13 @@ __global__ void __launch_bounds__(THREADS, 3) attn_prefill_tc_kernel(const __gri
                                                                      __nv_bfloat16* __restrict__ o, int S, int H, int mask_mode,
                                                                      const int32_t* __restrict__ x_lens,
                                                                      const int32_t* __restrict__ kv_lens, float scale_log2e,
-                                                                     float* __restrict__ lse) {
+                                                                     float* __restrict__ lse, long long* __restrict__ dbg) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bar_q, bar_s, bar_sfree, bar_p, bar_o;
-    __shared__ __align__(8) uint64_t kv_full[KV_STAGES], kv_empty[KV_STAGES];
+    // K and V blocks travel in SEPARATE two-stage rings: a K stage is free as soon as Q K_j^T has completed, a V stage only
+    // after P_j V_j.  With one {K, V} stage per block the next K could not be requested before P V of two blocks earlier had
+    // finished, and S_j was ready 520 cycles after the row threads had finished block j-1 (tools/fwd_attn_timeline.py).
+    __shared__ __align__(8) uint64_t k_full[KV_STAGES], k_empty[KV_STAGES], v_full[KV_STAGES], v_empty[KV_STAGES];
     __shared__ uint32_t tmem_slot;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -58,6 +61,14 @@ __global__ void __launch_bounds__(THREADS, 3) attn_prefill_tc_kernel(const __gri
     const int d = H * DH;
     pdl_trigger();
     const int i0 = qt * BQ;
+    if (dbg != nullptr && threadIdx.x == 64) {      // kernel entry of this CTA: %globaltimer and the SM it runs on
+        long long* dc = dbg + (static_cast<int64_t>(blockIdx.z) * gridDim.y * gridDim.x + blockIdx.y * gridDim.x + blockIdx.x) * 32 * 4;
+        unsigned long long gt; unsigned sm;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
+        dc[30 * 4 + 0] = static_cast<long long>(gt);
+        dc[30 * 4 + 1] = sm;
+    }
 
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t q_smem = base;
@@ -73,8 +84,10 @@ __global__ void __launch_bounds__(THREADS, 3) attn_prefill_tc_kernel(const __gri
         mbar_init(smem_u32(&bar_p), 4);
         mbar_init(smem_u32(&bar_o), 1);
         for (int s = 0; s < KV_STAGES; ++s) {
-            mbar_init(smem_u32(&kv_full[s]), 1);
-            mbar_init(smem_u32(&kv_empty[s]), 1);
+            mbar_init(smem_u32(&k_full[s]), 1);
+            mbar_init(smem_u32(&k_empty[s]), 1);
+            mbar_init(smem_u32(&v_full[s]), 1);
+            mbar_init(smem_u32(&v_empty[s]), 1);
         }
         fence_mbar_init();
     }
@@ -98,13 +111,13 @@ __global__ void __launch_bounds__(THREADS, 3) attn_prefill_tc_kernel(const __gri
             tma_load_2d(q_smem, &tm_q, smem_u32(&bar_q), h * DH, row0 + i0);
             int stage = 0;
             uint32_t phase = 0;
-            for (int j = 0; j < nb; ++j) {
-                mbar_wait_relaxed(smem_u32(&kv_empty[stage]), phase ^ 1);
-                const uint32_t fb = smem_u32(&kv_full[stage]);
-                mbar_expect_tx(fb, 2 * KV_BYTES);
-                const uint32_t dst = kv_smem + stage * 2 * KV_BYTES;
-                tma_load_2d(dst, &tm_kv, fb, d + h * DH, row0 + j * BKV);
-                tma_load_2d(dst + KV_BYTES, &tm_kv, fb, 2 * d + h * DH, row0 + j * BKV);
+            for (int j = 0; j < nb; ++j) {      // K stages at kv_smem + s * KV_BYTES, V stages behind them
+                mbar_wait_relaxed(smem_u32(&k_empty[stage]), phase ^ 1);
+                mbar_expect_tx(smem_u32(&k_full[stage]), KV_BYTES);
+                tma_load_2d(kv_smem + stage * KV_BYTES, &tm_kv, smem_u32(&k_full[stage]), d + h * DH, row0 + j * BKV);
+                mbar_wait_relaxed(smem_u32(&v_empty[stage]), phase ^ 1);
+                mbar_expect_tx(smem_u32(&v_full[stage]), KV_BYTES);
+                tma_load_2d(kv_smem + (KV_STAGES + stage) * KV_BYTES, &tm_kv, smem_u32(&v_full[stage]), 2 * d + h * DH, row0 + j * BKV);
                 if (++stage == KV_STAGES) { stage = 0; phase ^= 1; }
             }
         }
@@ -118,23 +131,24 @@ __global__ void __launch_bounds__(THREADS, 3) attn_prefill_tc_kernel(const __gri
             uint32_t phase = 0;
             auto issue_pv = [&](int jj, int st) {
                 mbar_wait_relaxed(smem_u32(&bar_p), jj & 1);
+                mbar_wait_relaxed(smem_u32(&v_full[st]), (jj / KV_STAGES) & 1);
                 tc_fence_after();
-                const uint32_t v_s = kv_smem + st * 2 * KV_BYTES + KV_BYTES;
+                const uint32_t v_s = kv_smem + (KV_STAGES + st) * KV_BYTES;
 #pragma unroll
                 for (int kk = 0; kk < BKV / 16; ++kk) {
                     const uint64_t da = umma_desc_sw128(p_smem + kk * 32, 16, 1024);
                     const uint64_t db = umma_desc_sw128(v_s + kk * 16 * 128, 1024, 1024);
                     umma_f16(o_tmem, da, db, IDESC_PV, (jj > 0 || kk > 0) ? 1u : 0u);
                 }
-                umma_commit(smem_u32(&kv_empty[st]));
+                umma_commit(smem_u32(&v_empty[st]));
                 umma_commit(smem_u32(&bar_o));
             };
             int prev_stage = 0;
             for (int j = 0; j < nb; ++j) {
-                mbar_wait_relaxed(smem_u32(&kv_full[stage]), phase);
+                mbar_wait_relaxed(smem_u32(&k_full[stage]), phase);
                 mbar_wait_relaxed(smem_u32(&bar_sfree), (j & 1) ^ 1);
                 tc_fence_after();
-                const uint32_t k_s = kv_smem + stage * 2 * KV_BYTES;
+                const uint32_t k_s = kv_smem + stage * KV_BYTES;
 #pragma unroll
                 for (int kk = 0; kk < DH / 16; ++kk) {
                     const uint64_t da = umma_desc_sw128(q_smem + kk * 32, 16, 1024);
@@ -142,6 +156,7 @@ __global__ void __launch_bounds__(THREADS, 3) attn_prefill_tc_kernel(const __gri
                     umma_f16(s_tmem, da, db, IDESC_QK, kk > 0 ? 1u : 0u);
                 }
                 umma_commit(smem_u32(&bar_s));
+                umma_commit(smem_u32(&k_empty[stage]));      // the K stage is free once Q K_j^T has completed
                 if (j > 0) issue_pv(j - 1, prev_stage);
                 prev_stage = stage;
                 if (++stage == KV_STAGES) { stage = 0; phase ^= 1; }
@@ -159,9 +174,15 @@ __global__ void __launch_bounds__(THREADS, 3) attn_prefill_tc_kernel(const __gri
         // p = exp2(s - m_ref) <= 256, which bf16 / fp32 hold comfortably, and no per-block traffic on O is needed.
         float m_ref = -INFINITY, l_run = 0.f;
         const uint32_t p_row = p_smem + r * 128;
+        // optional per-block cycle stamps of ONE row thread of every CTA (vb_attention_prefill_set_debug): [cta][block][4] =
+        // {S ready, row maximum known, previous PV done, P written}
+        const long long t_entry = clock64();
+        const bool stamp = dbg != nullptr && threadIdx.x == 64;
+        long long* dbg_cta = dbg + (static_cast<int64_t>(blockIdx.z) * gridDim.y * gridDim.x + blockIdx.y * gridDim.x + blockIdx.x) * 32 * 4;
         for (int j = 0; j < nb; ++j) {
             mbar_wait(smem_u32(&bar_s), j & 1);
             tc_fence_after();
+            if (stamp && j < 32) dbg_cta[j * 4 + 0] = clock64();
             // pass 1 over S_j (two 32-column TMEM loads, nothing kept): the row maximum of the raw scores
             // (scale > 0 commutes with max); masking only where the block needs it.  S_j is read again in pass 2 so
             // that only 32 scores are live at a time -- 3 CTAs fit per SM (registers) and hide each other's latencies.
@@ -188,6 +209,7 @@ __global__ void __launch_bounds__(THREADS, 3) attn_prefill_tc_kernel(const __gri
                     for (int c = 0; c < 32; c += 2) mx = fmax3(mx, __uint_as_float(sv[c]), __uint_as_float(sv[c + 1]));
                 }
             }
+            if (stamp && j < 32) dbg_cta[j * 4 + 1] = clock64();
             const float m_blk = mx * scale_log2e;
             const bool grow = m_blk > m_ref + 8.0f;            // also true for the first finite block (m_ref = -inf)
             float alpha = 1.f;
@@ -200,6 +222,7 @@ __global__ void __launch_bounds__(THREADS, 3) attn_prefill_tc_kernel(const __gri
                 // PV_{j-1} must be complete before P is overwritten and before O may be corrected
                 mbar_wait(smem_u32(&bar_o), (j - 1) & 1);
                 tc_fence_after();
+                if (stamp && j < 32) dbg_cta[j * 4 + 2] = clock64();
                 if (__any_sync(0xffffffffu, grow)) {
                     const float2 a2 = make_float2(alpha, alpha);
 #pragma unroll
@@ -262,9 +285,11 @@ __global__ void __launch_bounds__(THREADS, 3) attn_prefill_tc_kernel(const __gri
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&bar_p));
+            if (stamp && j < 32) dbg_cta[j * 4 + 3] = clock64();
         }
         mbar_wait(smem_u32(&bar_o), (nb - 1) & 1);
         tc_fence_after();
+        if (stamp) { dbg_cta[31 * 4 + 0] = t_entry; dbg_cta[31 * 4 + 1] = clock64(); }     // row-thread entry, last PV done
         const float inv = (l_run > 0.f) ? 1.f / l_run : 0.f;
         // optional: log-sum-exp of the scaled scores (natural log) for the backward pass -- any reference m_ref gives the
         // same value, so the lazy rescaling does not matter; +inf marks a row that attends nothing
@@ -289,6 +314,13 @@ __global__ void __launch_bounds__(THREADS, 3) attn_prefill_tc_kernel(const __gri
             }
         }
     }
+    if (dbg != nullptr && threadIdx.x == 64) {      // output stored
+        long long* dbg_cta = dbg + (static_cast<int64_t>(blockIdx.z) * gridDim.y * gridDim.x + blockIdx.y * gridDim.x + blockIdx.x) * 32 * 4;
+        dbg_cta[31 * 4 + 2] = clock64();
+        unsigned long long gt;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        dbg_cta[30 * 4 + 2] = static_cast<long long>(gt);      // output stored, %globaltimer
+    }
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {
@@ -298,6 +330,12 @@ __global__ void __launch_bounds__(THREADS, 3) attn_prefill_tc_kernel(const __gri
 }
 
 }  // namespace
+
+static long long* g_fwd_dbg = nullptr;
+extern "C" int vb_attention_prefill_set_debug(void* buf) {   /* device buffer of grid * 32 * 4 int64 cycle stamps, or NULL */
+    g_fwd_dbg = static_cast<long long*>(buf);
+    return VB_OK;
+}
 
 extern "C" int vb_attention_prefill_tc(const void* qkv, void* o, int B, int S, int H, int mask_mode, const int32_t* x_lens,
                                        const int32_t* kv_lens, float* lse, void* stream) {
@@ -320,6 +358,6 @@ extern "C" int vb_attention_prefill_tc(const void* qkv, void* o, int B, int S, i
     dim3 grid(static_cast<unsigned>(vb_ceil_div(S, BQ)), H, B);
     const float scale_log2e = 1.4426950408889634f / sqrtf(static_cast<float>(DH));
     VB_CUDA(vb_launch(false, attn_prefill_tc_kernel, grid, dim3(THREADS), SMEM_BYTES, static_cast<cudaStream_t>(stream), tq, tkv,
-                      static_cast<__nv_bfloat16*>(o), S, H, mask_mode, x_lens, kv_lens, scale_log2e, lse));
+                      static_cast<__nv_bfloat16*>(o), S, H, mask_mode, x_lens, kv_lens, scale_log2e, lse, g_fwd_dbg));
     return VB_OK;
 }
