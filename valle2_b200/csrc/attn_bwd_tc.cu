@@ -27,7 +27,9 @@ constexpr int THREADS = 192;
 constexpr int Q_BYTES = BQ * DH * 2;          // 16 KB (Q tile, dO tile)
 constexpr int KV_BYTES = BKV * DH * 2;        // 8 KB each for K and V
 constexpr int DS_BYTES = BQ * BKV * 2;        // 16 KB
-constexpr int SMEM_BYTES = 2 * Q_BYTES + KV_STAGES * 2 * KV_BYTES + DS_BYTES + 1024;
+constexpr int DQ_STAGES = 3;                  // {K, V} ring of the dQ kernel: a stage is only free after dQ += dS K of its block, so two
+                                              // stages stall the next S / dP behind it; three still leave two CTAs per SM (97 KB each)
+constexpr int SMEM_BYTES = 2 * Q_BYTES + DQ_STAGES * 2 * KV_BYTES + DS_BYTES + 1024;
 constexpr int TMEM_COLS = 256;
 
 __device__ __forceinline__ float ex2(float x) {
@@ -47,7 +49,7 @@ __global__ void __launch_bounds__(THREADS, 2) attn_bwd_dq_tc_kernel(const __grid
                                                                     const int32_t* __restrict__ kv_lens, float scale) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bar_q, bar_s, bar_sfree, bar_p, bar_o;
-    __shared__ __align__(8) uint64_t kv_full[KV_STAGES], kv_empty[KV_STAGES];
+    __shared__ __align__(8) uint64_t kv_full[DQ_STAGES], kv_empty[DQ_STAGES];
     __shared__ uint32_t tmem_slot;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -59,7 +61,7 @@ __global__ void __launch_bounds__(THREADS, 2) attn_bwd_dq_tc_kernel(const __grid
     const uint32_t q_smem = base;
     const uint32_t do_smem = base + Q_BYTES;
     const uint32_t kv_smem = do_smem + Q_BYTES;
-    const uint32_t ds_smem = kv_smem + KV_STAGES * 2 * KV_BYTES;
+    const uint32_t ds_smem = kv_smem + DQ_STAGES * 2 * KV_BYTES;
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tm_q);
@@ -70,7 +72,7 @@ __global__ void __launch_bounds__(THREADS, 2) attn_bwd_dq_tc_kernel(const __grid
         mbar_init(smem_u32(&bar_sfree), 4);
         mbar_init(smem_u32(&bar_p), 4);
         mbar_init(smem_u32(&bar_o), 1);
-        for (int s = 0; s < KV_STAGES; ++s) {
+        for (int s = 0; s < DQ_STAGES; ++s) {
             mbar_init(smem_u32(&kv_full[s]), 1);
             mbar_init(smem_u32(&kv_empty[s]), 1);
         }
@@ -102,7 +104,7 @@ __global__ void __launch_bounds__(THREADS, 2) attn_bwd_dq_tc_kernel(const __grid
                 const uint32_t dst = kv_smem + stage * 2 * KV_BYTES;
                 tma_load_2d(dst, &tm_kv, fb, d + h * DH, row0 + j * BKV);
                 tma_load_2d(dst + KV_BYTES, &tm_kv, fb, 2 * d + h * DH, row0 + j * BKV);
-                if (++stage == KV_STAGES) { stage = 0; phase ^= 1; }
+                if (++stage == DQ_STAGES) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1) {
@@ -147,7 +149,7 @@ __global__ void __launch_bounds__(THREADS, 2) attn_bwd_dq_tc_kernel(const __grid
                 umma_commit(smem_u32(&bar_s));
                 if (j > 0) issue_dq(j - 1, prev_stage);
                 prev_stage = stage;
-                if (++stage == KV_STAGES) { stage = 0; phase ^= 1; }
+                if (++stage == DQ_STAGES) { stage = 0; phase ^= 1; }
             }
             issue_dq(nb - 1, prev_stage);
         }
