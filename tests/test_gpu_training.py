@@ -125,7 +125,7 @@ def test_training_step_drives_an_optimizer(tmp_path):
 # ---- kernel-level checks -------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize('dt', [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize('mode', ['none', 'prefix', 'ragged'])
-@pytest.mark.parametrize('B,S,H', [(2, 70, 2), (1, 200, 3), (3, 64, 1)])
+@pytest.mark.parametrize('B,S,H', [(2, 70, 2), (1, 200, 3), (3, 64, 1), (2, 333, 2)])
 def test_attention_bwd_vs_autograd(ops, dt, mode, B, S, H):
     torch.manual_seed(31)
     Dh, d = 64, H * 64
@@ -159,6 +159,13 @@ def test_attention_bwd_vs_autograd(ops, dt, mode, B, S, H):
     dqkv = torch.full((B * S, 3 * d), float('nan'), device='cuda').to(dt)
     ops.attention_bwd(qkv, o, do, dqkv, B, S, H, mask_mode=mask_mode, x_lens=x_lens, kv_lens=kv_lens)
     assert rel_err(dqkv.float(), ref) < (1e-4 if dt == torch.float32 else 2e-2)
+    if dt == torch.bfloat16:
+        # the same gradients from the tcgen05 kernels (csrc/attn_bwd_tc.cu), which take the rows' log-sum-exp as an input
+        lse = torch.logsumexp(s.detach(), dim=-1).float().contiguous()                   # (B, H, S); -inf rows do not occur here
+        dq2 = torch.full((B * S, 3 * d), float('nan'), device='cuda').to(dt)
+        ops.attention_bwd(qkv, o, do, dq2, B, S, H, mask_mode=mask_mode, x_lens=x_lens, kv_lens=kv_lens, lse=lse)
+        assert not torch.isnan(dq2.float()).any()
+        assert rel_err(dq2.float(), ref) < 2e-2
 
 
 @pytest.mark.parametrize('dt', [torch.float32, torch.bfloat16])
