@@ -42,6 +42,13 @@ __device__ __forceinline__ float fast_exp2(float x) {
     return y;
 }
 
+// MMA-issuer waits: -DVB_FWD_MMA_SPIN polls without the 32 ns sleep (experiment)
+#ifdef VB_FWD_MMA_SPIN
+#define MMA_WAIT mbar_wait
+#else
+#define MMA_WAIT mbar_wait_relaxed
+#endif
+
 __global__ void __launch_bounds__(THREADS, 3) attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tm_q,
                                                                      const __grid_constant__ CUtensorMap tm_kv,
                                                                      __nv_bfloat16* __restrict__ o, int S, int H, int mask_mode,
@@ -126,12 +133,12 @@ __global__ void __launch_bounds__(THREADS, 3) attn_prefill_tc_kernel(const __gri
             constexpr uint32_t IDESC_QK = umma_idesc_bf16(BQ, BKV, 0, 0);   // A = Q (K-major), B = K block (K-major)
             constexpr uint32_t IDESC_PV = umma_idesc_bf16(BQ, DH, 0, 1);    // A = P (K-major), B = V block (MN-major)
             const uint32_t s_tmem = tmem_base, o_tmem = tmem_base + BKV;
-            mbar_wait_relaxed(smem_u32(&bar_q), 0);
+            MMA_WAIT(smem_u32(&bar_q), 0);
             int stage = 0;
             uint32_t phase = 0;
             auto issue_pv = [&](int jj, int st) {
-                mbar_wait_relaxed(smem_u32(&bar_p), jj & 1);
-                mbar_wait_relaxed(smem_u32(&v_full[st]), (jj / KV_STAGES) & 1);
+                MMA_WAIT(smem_u32(&bar_p), jj & 1);
+                MMA_WAIT(smem_u32(&v_full[st]), (jj / KV_STAGES) & 1);
                 tc_fence_after();
                 const uint32_t v_s = kv_smem + (KV_STAGES + st) * KV_BYTES;
 #pragma unroll
@@ -145,8 +152,8 @@ __global__ void __launch_bounds__(THREADS, 3) attn_prefill_tc_kernel(const __gri
             };
             int prev_stage = 0;
             for (int j = 0; j < nb; ++j) {
-                mbar_wait_relaxed(smem_u32(&k_full[stage]), phase);
-                mbar_wait_relaxed(smem_u32(&bar_sfree), (j & 1) ^ 1);
+                MMA_WAIT(smem_u32(&k_full[stage]), phase);
+                MMA_WAIT(smem_u32(&bar_sfree), (j & 1) ^ 1);
                 tc_fence_after();
                 const uint32_t k_s = kv_smem + stage * KV_BYTES;
 #pragma unroll
