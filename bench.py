@@ -449,11 +449,36 @@ def extras(args, dev, tmp):
         ms = e0.elapsed_time(e1) / 3
         S, d, F, L = Txt + Tyt, 1024, 4096, 12
         fwd = Bt * (L * (S * 2 * (4 * d * d + 2 * d * F) + 4 * S * S * d) + 2 * Tyt * d * 1025)
-        out['train_step'] = {'batch': Bt, 'seq': S, 'ms_per_step': ms, 'clips_per_s': Bt / (ms * 1e-3), 'loss': float(loss),
+        out['train_step'] = {'batch': Bt, 'seq': S, 'ms_per_step': ms, 'clips_per_s': Bt / (ms * 1e-3), 'loss': float(loss.detach()),
                              'model_tflops': 3 * fwd / (ms * 1e-3) / 1e12,
                              'frac_of_bf16_sustained_peak': 3 * fwd / (ms * 1e-3) / 1e12 / pk['bf16_tflops_sustained'],
                              'note': 'forward + backward, no optimizer step; flops = 3 x dense forward (no causal discount)',
                              'peak_mem_gb': torch.cuda.max_memory_allocated() / 1e9}
+        # the NAR half of configs[4]: same clips, all 8 codebooks, stage drawn by training_step (valle_nar.py:76)
+        del ar
+        torch.cuda.empty_cache()
+        torch.manual_seed(3)
+        nar_t = ValleNAR(large_cfg('AdaptiveLayerNorm', tmp)).train().to(dev)
+        nbatch = {'tokens': batch['tokens'], 'tokens_lens': batch['tokens_lens'],
+                  'codes': torch.randint(0, 1024, (Bt, Tyt - 1, 8), generator=g), 'codes_lens': torch.full((Bt,), Tyt - 1)}
+        for it in range(6):
+            if it == 3:
+                torch.cuda.synchronize()
+                e0.record()
+            for p_ in nar_t.parameters():
+                p_.grad = None
+            nloss = nar_t.training_step(nbatch)
+            nloss.backward()
+        e1.record()
+        torch.cuda.synchronize()
+        nms = e0.elapsed_time(e1) / 3
+        Sn = Txt + Tyt - 1
+        nfwd = Bt * (L * (Sn * 2 * (4 * d * d + 2 * d * F) + 4 * Sn * Sn * d))
+        out['train_step_nar'] = {'batch': Bt, 'seq': Sn, 'ms_per_step': nms, 'clips_per_s': Bt / (nms * 1e-3), 'loss': float(nloss.detach()),
+                                 'model_tflops': 3 * nfwd / (nms * 1e-3) / 1e12,
+                                 'frac_of_bf16_sustained_peak': 3 * nfwd / (nms * 1e-3) / 1e12 / pk['bf16_tflops_sustained'],
+                                 'note': 'ValleNAR.training_step forward + backward (full attention, AdaLN), stage drawn per step'}
+        del nar_t
     except Exception as e:  # report, do not hide
         out['train_step'] = {'error': repr(e)}
     return out
