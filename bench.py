@@ -96,6 +96,15 @@ def large_cfg(norm: str, tmp: str, **kw):
     return ConfigValle(**base)
 
 
+def decode_form(eng, sub) -> str:
+    if eng._lean_ok(sub):
+        return 'lean: linear_decode_rows_kernel (mma.sync, full K per CTA, LayerNorm on load, fused epilogues), 5 launches per layer'
+    if eng._tc_ok(sub):
+        return ('tc: decode_gemm_kernel (tcgen05 swap-AB, split-K reduced inside the launch, LayerNorm folded, fused epilogues), '
+                '5 launches per layer')
+    return 'splitk: gemm_tc_kernel<swap-AB split-K> slices + LayerNorm / GELU-reduce kernels, 8 launches per layer'
+
+
 def ar_step_bytes(B: int, ctx: float, L=12, d=1024, F=4096, V=1025) -> float:
     """Algorithmic HBM bytes of one decode step: all weights once + K/V of every cached position."""
     w = 2 * (L * (3 * d * d + d * d + 2 * d * F) + V * d)
@@ -175,7 +184,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                                f'(BASELINE configs[1]); text {TX}, prompt {P}, ctx {ctx0}->{ctx0 + K} (mean {mean_ctx:.1f})',
                    'batch_per_gpu': B, 'global_batch': B * world, 'parallelism': f'dp{world} (utterance sharding, '
                    'one all-gather of the codes at the end)', 'kv_page': 64,
-                   'sub_batches': n_sub, 'decode_gemm': 'lean (rows kernels, LN on load, 5 per layer)' if eng._lean_ok(st['subs'][0]) else ('mix qkv,o,f1,f2,lg=' + ''.join(eng._mix(st['subs'][0]).values())) if eng._rows_ok(st['subs'][0]) else 'fused' if eng._fused_ok(st['subs'][0]) else ('chain' if eng._chain_ok(st['subs'][0]) else 'split-k'), 'launches_per_step': launches_per_step,
+                   'sub_batches': n_sub, 'decode_gemm': decode_form(eng, st['subs'][0]), 'launches_per_step': launches_per_step,
                    'l2_policy': 'inputs larger than L2: every step streams 304 MB of weights + %.0f MB of KV' %
                                 ((step_bytes - ar_step_bytes(0, 0)) / 1e6),
                    'step_hbm_bytes': step_bytes, 'step_hbm_frac_of_measured_peak':
@@ -193,17 +202,13 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         torch.cuda.synchronize()
         reps = 5
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-        rows = eng._fused_ok(sb)
-        mma_rows = eng._rows_ok(sb)
-        lean = eng._lean_ok(sb)
+        lean, tc = eng._lean_ok(sb), eng._tc_ok(sb)
         if lean:
             qkv_src, qkv_np, qkv_ps = sb['r_qkv'], 1, 0
-        elif mma_rows and eng._mix(sb)['qkv'] == 'r':
-            qkv_src, qkv_np, qkv_ps = sb['r_qkv'], sb['nr']['qkv'], Bs * 3 * d
-        elif mma_rows:
-            qkv_src, qkv_np, qkv_ps = sb['p_qkv'], sb['ns']['qkv'], Bs * 3 * d
+        elif tc:
+            qkv_src, qkv_np, qkv_ps = sb['qkv32'], 1, 0
         else:
-            qkv_src, qkv_np, qkv_ps = (sb['qkv32'], 1, 0) if rows else (sb['p_qkv'], sb['ns']['qkv'], Bs * 3 * d)
+            qkv_src, qkv_np, qkv_ps = sb['p_qkv'], sb['ns']['qkv'], Bs * 3 * d
 
         def attn_all_layers():
             for li in range(12):                             # 12 layers x B x ctx KV = > L2, no re-use between launches
@@ -243,7 +248,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                               'bytes_per_launch': att_bytes, 'us_per_launch': att_ms * 1e3,
                               'share_of_step': att_ms * 12 * n_sub / (ms / K), 'rows_per_launch': Bs,
                               'launches_per_step': 12 * n_sub}
-        # weight-streaming GEMMs of one step, same method
+        # weight-streaming GEMMs of one step (incl. their fused reductions / epilogues), same method
         def gemms_all_layers():
             for L in eng.weights.layers:
                 if lean:
@@ -253,33 +258,15 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                     ops.linear_decode_rows(sb['o'], L['wo'], sb['x'], bias=L['bo'], residual=True)
                     ops.linear_decode_rows_ln(sb['x'], L['w1'], sb['f'], gamma=g2[0], beta=b2[0], bias=L['b1'], gelu=True)
                     ops.linear_decode_rows(sb['f'], L['w2'], sb['x'], bias=L['b2'], residual=True, want_split=0)
-                elif mma_rows:
-                    mix = eng._mix(sb)
-                    if mix['qkv'] == 'r':
-                        ops.linear_decode_rows(sb['h'], L['wqkv'], sb['r_qkv'] if sb['nr']['qkv'] > 1 else sb['r_qkv'][0],
-                                               want_split=eng.rows_qkv_split)
-                    else:
-                        ops.linear_decode(sb['h'], L['wqkv'], sb['p_qkv'], Bs * 3 * d, 32)
-                    if mix['o'] == 'r':
-                        ops.linear_decode_rows(sb['o'], L['wo'], sb['x'], bias=L['bo'], residual=True)
-                    else:
-                        ops.linear_decode(sb['o'], L['wo'], sb['p_o'], Bs * d, 32)
-                    if mix['f1'] == 'r':
-                        ops.linear_decode_rows(sb['h'], L['w1'], sb['f'], bias=L['b1'], gelu=True)
-                    else:
-                        ops.linear_decode(sb['h'], L['w1'], sb['p_f1'], Bs * 4096, 32)
-                    if mix['f2'] == 'r':
-                        ops.linear_decode_rows(sb['f'], L['w2'], sb['r_f2'])
-                    else:
-                        ops.linear_decode(sb['f'], L['w2'], sb['p_f2'], Bs * d, 32)
-                elif rows:
-                    cl = eng.fused_cluster
-                    g1, b1, _ = L['norm1']
-                    g2, b2, _ = L['norm2']
-                    ops.linear_decode_fused(sb['x'], L['wqkv'], sb['qkv32'], gamma=g1[0], beta=b1[0], cluster_k=cl['qkv'])
-                    ops.linear_decode_fused(sb['o'], L['wo'], sb['x'], bias=L['bo'], residual=True, cluster_k=cl['o'])
-                    ops.linear_decode_fused(sb['x'], L['w1'], sb['f'], bias=L['b1'], gelu=True, gamma=g2[0], beta=b2[0], cluster_k=cl['f1'])
-                    ops.linear_decode_fused(sb['f'], L['w2'], sb['x'], bias=L['b2'], residual=True, cluster_k=cl['f2'])
+                elif tc:
+                    dg = sb['dg']
+                    ch_o, ch_f2 = dg['o']['tiles'], dg['f2']['tiles']
+                    eng._dg(sb, 'qkv', sb['xb'], L['wqkv_s'], ops.DG_LN, bias=L['b_qkv'], colsum=L['c_qkv'], stats_in=sb['stats'],
+                            n_chunks_in=ch_f2, y32=sb['qkv32'])
+                    eng._dg(sb, 'o', sb['o'], L['wo'], ops.DG_RESIDUAL, bias=L['bo'], xres=sb['x'], y16=sb['xb'], stats_out=sb['stats'])
+                    eng._dg(sb, 'f1', sb['xb'], L['w1_s'], ops.DG_LN_GELU, bias=L['b_1'], colsum=L['c_1'], stats_in=sb['stats'],
+                            n_chunks_in=ch_o, y16=sb['f'])
+                    eng._dg(sb, 'f2', sb['f'], L['w2'], ops.DG_RESIDUAL, bias=L['b2'], xres=sb['x'], y16=sb['xb'], stats_out=sb['stats'])
                 else:
                     ops.linear_decode(sb['h'], L['wqkv'], sb['p_qkv'], Bs * 3 * d, 32)
                     ops.linear_decode(sb['o'], L['wo'], sb['p_o'], Bs * d, 32)
@@ -291,7 +278,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         wbytes = 2 * 12 * (3 * d * d + d * d + 2 * d * 4096)
         result['gemm_decode'] = {'ms_per_step': gemm_ms, 'achieved_gbs': wbytes / (gemm_ms * 1e-3) / 1e9,
                                  'frac_of_hbm_peak': wbytes / (gemm_ms * 1e-3) / 1e9 / pk['hbm_gbs'], 'launches': 48,
-                                 'kernel': 'linear_decode_rows_kernel (mma.sync, full K per CTA, LN on load, fused epilogues)' if lean else 'linear_decode_rows_kernel (mma.sync, full K per CTA, fused epilogues) / gemm_tc_kernel<swap-AB split-K> per config.decode_gemm' if mma_rows else 'gemm_decode_fused_kernel (cluster split-K through DSMEM, LN on load, fused epilogues)' if rows else 'gemm_tc_kernel<swap-AB split-K>'}
+                                 'kernel': decode_form(eng, sb)}
 
     # ---- end-to-end through the public API from pinned host tensors --------------------------------
     # One untimed call first (allocates the KV pools and captures the step graph of this request shape -- the engine keeps

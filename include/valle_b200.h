@@ -116,7 +116,7 @@ int vb_linear_decode_splits(int64_t N, int64_t K, int max_split);   /* pure quer
 /* flags: VB_FLAG_LATE_TRIGGER -- programmatic dependent launch: the kernel lets its successor start only after it has
  * itself waited for its predecessor, so the successor's pre-wait code may read anything written before this kernel
  * (used for the QKV GEMM, whose successor vb_attn_decode_paged prefetches KV pages before waiting). */
-enum { VB_FLAG_LATE_TRIGGER = 1, VB_FLAG_PREFETCH_KV = 2, VB_FLAG_ATTN_SIMT = 4 };
+enum { VB_FLAG_LATE_TRIGGER = 1, VB_FLAG_PREFETCH_KV = 2, VB_FLAG_ATTN_SIMT = 4, VB_FLAG_ATTN_TICKET = 8, VB_FLAG_DG_GLOBAL = 16 };
 int vb_linear_decode(const void* x, int64_t ldx, const void* w, int64_t ldw, float* part, int64_t part_stride,
                      int64_t M, int64_t N, int64_t K, int max_split, int flags, int* n_split_out, void* stream);
 
@@ -156,52 +156,35 @@ int vb_linear_decode_rows_set_debug(void* buf);
  * same eight events as SM cycle counters (uint64, device memory, #SM*16 entries); NULL switches it off. */
 int vb_linear_decode_set_debug(void* buf);
 
-/* Decode-shape GEMM with the split-K reduction, LayerNorm and epilogue fused in (csrc/gemm_decode_fused.cu), B <= 64:
- *   y[B][N] = epilogue(A[B][K] . w[N][K]^T).  CTAs that share a 128-row weight slab form a thread-block cluster along K
- *   and sum their partial accumulators through distributed shared memory in rank order (deterministic, no slices in HBM).
- *   a_dtype VB_BF16: a = bf16 rows [B][K] (pitch lda).
- *   a_dtype VB_F32 : a = fp32 rows [B][K] (pitch lda, K % 64 == 0); the kernel normalises them on load:
- *                    A = LayerNorm(a; gamma, beta, eps) (modules.py:271/276 norm1/norm2; row statistics combined across
- *                    the cluster), or a plain cast when gamma is NULL.
- *   epilogue: VB_EPI_NONE / VB_EPI_BIAS / VB_EPI_BIAS_GELU write y (VB_F32 or VB_BF16, pitch ldy);
- *             VB_EPI_BIAS_RESIDUAL does y += A.w^T + bias in place (y fp32: the residual stream, modules.py:274/278).
- *   cluster_k: CTAs per cluster along K, 1..8 or 16; 0 = vb_linear_decode_fused_cluster(N, K) (fills the SMs).
- *   flags: VB_FLAG_LATE_TRIGGER as for vb_linear_decode. */
-int vb_linear_decode_fused_cluster(int N, int K);
-int vb_linear_decode_fused(const void* a, int a_dtype, int64_t lda, const float* gamma, const float* beta, float eps,
-                           const void* w, int64_t ldw, const float* bias, void* y, int y_dtype, int64_t ldy, int B, int N,
-                           int K, int epilogue, int cluster_k, int flags, void* stream);
-
-/* Persistent "chain" kernel for the decode step (batch <= 64): up to 8 phases executed by one launch of #SM CTAs with a
- * grid barrier between phases -- GEMM (as vb_linear_decode, same split-K slices), LN (as vb_residual_layernorm with a
- * bf16 y), ACT (as vb_reduce_bias_act with gelu and a bf16 y).  Fuses out-proj -> LN -> FFN1 -> GELU -> FFN2 -> LN -> QKV
- * of one decoder layer (modules.py:271-278) into one launch; results are bit-identical to the separate kernels.
- * grid_barrier_counter: one zero-initialised uint32 in device memory (left at zero by every launch).
- * The kernel uses a late PDL trigger (see VB_FLAG_LATE_TRIGGER). */
-enum { VB_PHASE_GEMM = 0, VB_PHASE_LN = 1, VB_PHASE_ACT = 2 };
-typedef struct vb_chain_phase {
-    int32_t type;
-    int32_t N, K, max_split;          /* GEMM: out / in features, split cap.  ACT: N = row width */
-    const void* x;                    /* GEMM: bf16 activations [B][K] */
-    const void* w;                    /* GEMM: bf16 weights [N][K] */
-    float* out_part;                  /* GEMM: fp32 slices [split][B][N] */
-    int64_t out_part_stride;
-    float* x32;                       /* LN: fp32 residual rows [B][d], updated in place when n_part > 0 */
-    const float* in_part;             /* LN / ACT: slices to reduce */
-    int32_t n_part;
-    int32_t d;                        /* LN: row width */
-    int64_t in_part_stride;
-    const float* bias;
-    const float* gamma;               /* LN: NULL = plain cast */
-    const float* beta;
-    void* y;                          /* LN / ACT: bf16 output rows (LN: may be NULL) */
-    float eps;
-    int32_t reserved;
-} vb_chain_phase;
-int vb_decode_chain(const vb_chain_phase* phases, int n_phase, int B, void* grid_barrier_counter, void* stream);
-/* Profiling aid: subsequent chain launches write %globaltimer stamps [cta][phase 0..7][start, work done, arrived, released]
- * (uint64) into buf (device memory, #SM*8*4 entries); NULL switches it off. */
-int vb_decode_chain_set_debug(void* buf);
+/* Decode-shape linear layer that finishes inside one launch (csrc/gemm_decode_tc.cu), M <= 256, x and w bf16:
+ * swap-AB tcgen05 GEMM with split-K over CTAs, the split-K partials exchanged through an L2-resident workspace and reduced
+ * in split order by the same CTAs (deterministic), and the layer's arithmetic in the epilogue.  With it a decoder layer of the
+ * batched AR step is QKV -> attention -> out-proj -> FFN1 -> FFN2: five dependent launches, no LayerNorm / reduce kernels.
+ *   VB_DG_PLAIN    y32[m][n] = x.w^T (+ bias)                                            valle_ar.py:158 (logits)
+ *   VB_DG_LN       y32[m][n] = rstd_m (x.w^T - mean_m colsum[n]) + bias[n]               modules.py:271 + :146 (norm1 + qkv)
+ *   VB_DG_LN_GELU  y16[m][n] = gelu_erf(rstd_m (x.w^T - mean_m colsum[n]) + bias[n])     modules.py:278 + :220-221
+ *   VB_DG_RESIDUAL xres[m][n] += x.w^T + bias[n]; y16 = bf16(xres) (nullable);           modules.py:171+:274, :221+:278
+ *                  stats_out[m][t] = (sum, sum of squares) of xres over the 128 columns of tile t (tiles = ceil(N / 128))
+ * LN modes implement LayerNorm(x; gamma, beta) . W^T algebraically: the caller passes w = bf16(gamma (.) W) (columns scaled),
+ * colsum[n] = sum_k w[n][k], bias = beta . W^T (+ the layer's bias), x = the RAW residual rows in bf16, and stats_in
+ * [M][n_chunks_in] (sum, sum of squares) partials of those rows over K (written by the producing VB_DG_RESIDUAL launch or by
+ * vb_ar_step_tail); mean_m / rstd_m are derived from them with eps.
+ * Exchange: for M <= 64 and 2 <= n_split <= 16 the tile's splits run as one thread-block cluster and push their partials into
+ * the owners' shared memory (DSMEM) + one cluster barrier; otherwise (or with VB_FLAG_DG_GLOBAL) through ws_part + counters.
+ * Both sum the partials in split order: bit-identical results.
+ *   ws_part:  >= ws_bytes of vb_decode_gemm_plan (shared by all launches of one stream-ordered chain);
+ *   counters: >= tiles uint32, zeroed once; a counter array must only ever serve launches of ONE (N, K) shape (arrivals are
+ *             counted modulo that shape's n_split);  flags: VB_FLAG_LATE_TRIGGER as for vb_linear_decode. */
+enum { VB_DG_PLAIN = 0, VB_DG_LN = 1, VB_DG_LN_GELU = 2, VB_DG_RESIDUAL = 3 };
+int vb_decode_gemm_plan(int M, int64_t N, int64_t K, int* tiles, int* n_split, int64_t* ws_bytes);   /* pure query */
+int vb_decode_gemm(const void* x, int64_t ldx, const void* w, int64_t ldw, int M, int64_t N, int64_t K, int mode,
+                   const float* bias, const float* colsum, const float* stats_in, int n_chunks_in, float eps,
+                   float* y32, int64_t ldy32, void* y16, int64_t ldy16, float* xres, int64_t ldxres, float* stats_out,
+                   void* ws_part, void* counters, int flags, void* stream);
+/* Profiling aid: subsequent vb_decode_gemm launches write %globaltimer stamps [cta][16] = {prologue done, weights requested,
+ * dependency resolved, first k-block landed, MMAs issued, accumulator complete, tile's splits all arrived, outputs stored,
+ * partial stored, arrived on the counter, ...} (uint64, device memory, grid * 16 entries); NULL switches it off. */
+int vb_decode_gemm_set_debug(void* buf);
 
 /* ---- K5/K6: attention -------------------------------------------------------------------------------------------- */
 /* General attention over strided q/k/v (element strides), fp32 or bf16 I/O, fp32 math (SIMT).
@@ -244,7 +227,9 @@ int vb_kv_scatter_paged(const void* qkv, int qkv_dtype, void* pool, int pool_dty
 int64_t vb_attn_decode_ws_bytes(int B, int H, int n_tsplit);
 /* flags: VB_FLAG_PREFETCH_KV -- the producer warp starts streaming KV pages BEFORE waiting on the predecessor kernel
  * (PDL).  Only legal when seq_lens / block_table / cached positions were written before the predecessor started
- * waiting, i.e. the predecessor is vb_linear_decode(..., VB_FLAG_LATE_TRIGGER) or any non-PDL kernel. */
+ * waiting, i.e. the predecessor is vb_linear_decode(..., VB_FLAG_LATE_TRIGGER) or any non-PDL kernel.
+ * VB_FLAG_ATTN_TICKET -- merge the n_tsplit partials through the global-memory ticket even where the thread-block
+ * cluster (DSMEM) merge applies (2 <= n_tsplit <= 8); both merges add the partials in split order. */
 int vb_attn_decode_paged(const float* qkv_part, int n_part, int64_t part_stride, void* pool, int pool_dtype,
                          const int32_t* block_table, int max_pages, const int32_t* seq_lens,
                          void* o, int o_dtype, int B, int H, int Dh, int n_tsplit, int flags, void* ws, void* stream);
@@ -310,6 +295,18 @@ int vb_sample(const float* logits_part, int n_part, int64_t part_stride, int64_t
 int vb_ar_bookkeeping(const int32_t* sample, const float* logprob, int32_t* last, float* sum_logprobs,
                       int32_t* codes_out, int64_t codes_stride, int32_t* seq_lens, int32_t* audio_pos,
                       int32_t* state, int B, int eos, void* stream);
+
+/* End of a batched decode step in ONE launch, one CTA per sequence (valle_ar.py:158-171 + :143-144 of the next iteration):
+ *   tok, logprob = vb_sample's draw from logits[b][0..V)  (u = uniforms[b] if given, else hash(*seed_ptr, step, b + row_offset));
+ *   the row's bookkeeping as in vb_ar_bookkeeping; the last CTA to arrive advances step / stop_step;
+ *   x[b] = table[tok] + pe[audio_pos[b]] -- the next step's input: fp32 residual row, x_bf16 its bf16 copy, stats[b] its
+ *   (sum, sum of squares) for the LayerNorm folded into the QKV GEMM (vb_decode_gemm, n_chunks_in = 1).
+ * state: int32 [4] = {step, stop_step, 0, 0} (the last two are scratch, left at zero).  The seed is read from device memory
+ * so that a captured step graph serves every seed. */
+int vb_ar_step_tail(const float* logits, int64_t row_stride, int V, float temperature, int top_k, float top_p,
+                    const float* uniforms, const uint64_t* seed_ptr, int row_offset, int32_t* last, float* sum_logprobs,
+                    int32_t* codes_out, int64_t codes_stride, int32_t* seq_lens, int32_t* audio_pos, int32_t* state, int B,
+                    int eos, const float* table, const float* pe, int d, float* x, void* x_bf16, float* stats, void* stream);
 
 #ifdef __cplusplus
 }

@@ -39,6 +39,23 @@ def build(kind, oc, tmp_path, seed):
     return model.cuda(), sd
 
 
+def oracle_nar_stage_logits(sd, oc, tokens, prompt_codes, columns, n):
+    """Stage-n logits (T, 1024) of the repaired NAR loop (oracle.nar_generate, valle_nar.py:131-157) with the first n
+    codebooks of the target GIVEN (columns (T, >=n)) instead of sampled stage by stage."""
+    d = oc.d_model
+    Tc, Q = prompt_codes.shape
+    emb_prompt = torch.zeros(Tc, d)
+    for j in range(Q):
+        emb_prompt = emb_prompt + sd[f'codes_embs.{j}.word_embeddings.weight'][prompt_codes[:, j]]
+    emb_out = torch.zeros(columns.shape[0], d)
+    for j in range(n):
+        emb_out = emb_out + sd[f'codes_embs.{j}.word_embeddings.weight'][columns[:, j]]
+    x_tok = vo.add_pe(vo.embed(sd['tokens_emb.word_embeddings.weight'], tokens[None]), vo._pe_for(sd, 'tokens_position_emb.pe', d))
+    x_aud = vo.add_pe(torch.cat([emb_prompt, emb_out], 0)[None], vo._pe_for(sd, 'audio_position_emb.pe', d))
+    h, _ = vo.transformer(torch.cat([x_tok, x_aud], 1), sd, oc, embedding=sd[f'stage_embs.{n - 1}.word_embeddings.weight'])
+    return h[0, tokens.shape[0] + Tc:] @ sd[f'proj_layers.{n - 1}.weight'].t()
+
+
 @pytest.fixture(autouse=True)
 def _restore_precision():
     prev = valle2_b200.get_precision()
@@ -46,7 +63,7 @@ def _restore_precision():
     valle2_b200.set_precision(prev)
 
 
-@pytest.mark.parametrize('precision,tol', [('fp32', 2e-5), ('bf16', 1.5e-2)])
+@pytest.mark.parametrize('precision,tol', [('fp32', 2e-5), ('bf16', 1e-2)])
 def test_modules_vs_reference_vectors(golden, precision, tol, tmp_path):
     from valle.models.modules import (AdaptiveLayerNorm, FeedForward, MultiHeadAttention, PositionalEncoding,
                                       Transformer)
@@ -196,7 +213,19 @@ def test_nar_tiny(golden, precision, tol, tmp_path):
     if precision == 'fp32':
         assert torch.equal(out.cpu(), ref)
     else:
-        assert torch.equal(out.cpu()[:, :2], ref[:, :2]) or (out.cpu() == ref).float().mean() > 0.8
+        # bf16: a stage's input is the previous stages' OUTPUT, so after the first near-tie the two runs see different
+        # inputs.  Checked per stage against the oracle driven with the codebooks this run produced: logits within tol,
+        # and the arg-max equal wherever the oracle's top-1/top-2 margin is outside that tolerance.
+        assert torch.equal(out.cpu()[:, 0], ref[:, 0])
+        n_clear = 0
+        for n in range(1, 8):
+            lg = oracle_nar_stage_logits(sd, oc, torch.cat([inp['prompt_tokens'], inp['target_tokens']]), inp['prompt_codes'],
+                                         out.cpu(), n)
+            top2 = lg.topk(2, dim=-1).values
+            clear = (top2[:, 0] - top2[:, 1]) > 2 * tol * lg.abs().max()
+            n_clear += int(clear.sum())
+            assert (out.cpu()[clear, n] == lg.argmax(-1)[clear]).all(), n
+        assert n_clear >= 7 * 11 // 2
     # stage logits with the reference's codes as context (teacher forcing inside generate is not exposed; use
     # the batched engine with return_logits on the reference's own first column -> stage 1 logits are comparable)
     eng = model._engine()
@@ -258,4 +287,4 @@ def test_ar_large_short_decode_vs_oracle(precision, tmp_path):
     assert rel_err(logits, ref_logits[0]) < (1e-5 if precision == 'fp32' else 1e-2)
     # the last len(ref) rows of the teacher-forced logits are the decode-step logits (cached == uncached invariant)
     for s in range(len(ref)):
-        assert rel_err(logits[70 + s], trace[s][0]) < (2e-5 if precision == 'fp32' else 1.5e-2)
+        assert rel_err(logits[70 + s], trace[s][0]) < (2e-5 if precision == 'fp32' else 1e-2)

@@ -266,137 +266,183 @@ def test_linear_decode_rows_is_deterministic_and_rejects_bad_shapes(ops):
         ops.linear_decode_rows_ln(torch.zeros(9, 1024, device='cuda'), w, torch.empty(9, 3072, device='cuda'))
 
 
-@pytest.mark.parametrize('B', [1, 7, 16, 32, 33, 64])
-@pytest.mark.parametrize('d,F', [(1024, 4096), (256, 1024)])
-def test_decode_chain_matches_separate_kernels(ops, B, d, F):
-    """The persistent chain kernel (out-proj -> LN -> FFN1 -> GELU -> FFN2 -> LN -> QKV, modules.py:271-278) against the
-    same sequence launched as separate kernels: split-K slices bit-identical, LN / GELU rows to fp32 round-off; run
-    three times back to back to exercise the self-resetting grid-barrier counter."""
-    torch.manual_seed(11)
-    dev = 'cuda'
-    bf = torch.bfloat16
-    o = torch.randn(B, d, device=dev).to(bf)
-    x0 = torch.randn(B, d, device=dev)
-    wo, w1 = (torch.randn(d, d, device=dev) / math.sqrt(d)).to(bf), (torch.randn(F, d, device=dev) / math.sqrt(d)).to(bf)
-    w2, wq = (torch.randn(d, F, device=dev) / math.sqrt(F)).to(bf), (torch.randn(3 * d, d, device=dev) / math.sqrt(d)).to(bf)
-    bo, b1, b2 = torch.randn(d, device=dev), torch.randn(F, device=dev), torch.randn(d, device=dev)
-    g2, be2, g1, be1 = (torch.randn(d, device=dev) for _ in range(4))
-    ns = {k: ops.linear_decode_splits(n, kk, 32) for k, (n, kk) in
-          {'qkv': (3 * d, d), 'o': (d, d), 'f1': (F, d), 'f2': (d, F)}.items()}
-
-    def bufs():
-        return {'x': x0.clone(), 'h': torch.zeros(B, d, device=dev, dtype=bf), 'h2': torch.zeros(B, d, device=dev, dtype=bf),
-                'f': torch.zeros(B, F, device=dev, dtype=bf),
-                'p_o': torch.full((ns['o'], B, d), float('nan'), device=dev),
-                'p_f1': torch.full((ns['f1'], B, F), float('nan'), device=dev),
-                'p_f2': torch.full((ns['f2'], B, d), float('nan'), device=dev),
-                'p_qkv': torch.full((ns['qkv'], B, 3 * d), float('nan'), device=dev)}
-
-    r = bufs()
-    ops.linear_decode(o, wo, r['p_o'], B * d, 32)
-    ops.residual_layernorm(r['x'], g2, be2, r['h'], part=r['p_o'], n_part=ns['o'], part_stride=B * d, bias=bo)
-    ops.linear_decode(r['h'], w1, r['p_f1'], B * F, 32)
-    ops.reduce_bias_act(r['p_f1'], ns['f1'], B * F, b1, True, r['f'])
-    ops.linear_decode(r['f'], w2, r['p_f2'], B * d, 32)
-    ops.residual_layernorm(r['x'], g1, be1, r['h2'], part=r['p_f2'], n_part=ns['f2'], part_stride=B * d, bias=b2)
-    ops.linear_decode(r['h2'], wq, r['p_qkv'], B * 3 * d, 32)
-    torch.cuda.synchronize()
-
-    gbar = torch.zeros(64, device=dev, dtype=torch.int32)
-    for rep in range(3):
-        c = bufs()
-        ops.decode_chain([
-            ops.chain_gemm(o, wo, c['p_o'], B * d),
-            ops.chain_ln(c['x'], g2, be2, c['h'], part=c['p_o'], n_part=ns['o'], part_stride=B * d, bias=bo),
-            ops.chain_gemm(c['h'], w1, c['p_f1'], B * F),
-            ops.chain_act(c['p_f1'], ns['f1'], B * F, b1, c['f']),
-            ops.chain_gemm(c['f'], w2, c['p_f2'], B * d),
-            ops.chain_ln(c['x'], g1, be1, c['h2'], part=c['p_f2'], n_part=ns['f2'], part_stride=B * d, bias=b2),
-            ops.chain_gemm(c['h2'], wq, c['p_qkv'], B * 3 * d)], B, gbar)
-        torch.cuda.synchronize()
-        assert int(gbar[0].item()) == 0, 'grid-barrier counter not reset'
-        assert rel_err(c['p_o'][:ns['o']].sum(0), r['p_o'][:ns['o']].sum(0)) < 1e-5, 'out-proj slices differ'
-        # downstream stages see LN / GELU rows that may differ by fp32 round-off before the bf16 rounding
-        assert rel_err(c['x'], r['x']) < 2e-3      # after FFN2: bf16 roundings of h / f may flip by one ulp
-        for k in ('h', 'f', 'h2'):
-            assert rel_err(c[k].float(), r[k].float()) < 1e-2, k
-        for k, n in (('p_f1', 'f1'), ('p_f2', 'f2'), ('p_qkv', 'qkv')):
-            assert not torch.isnan(c[k][:ns[n]]).any()
-            assert rel_err(c[k][:ns[n]].sum(0), r[k][:ns[n]].sum(0)) < 2e-2, k
-    # and against fp64 math end to end
-    xr = x0.double() + o.double() @ wo.double().t() + bo.double()
-    assert rel_err(c['p_o'].sum(0) + bo + x0, xr) < 1e-4
+def _dg_buffers(ops, M, N, K):
+    plan = ops.decode_gemm_plan(M, N, K)
+    ws = torch.full((plan['ws_bytes'] // 4,), float('nan'), device='cuda')
+    ctr = torch.zeros(256, dtype=torch.int32, device='cuda')
+    return plan, ws, ctr
 
 
-def test_decode_chain_plain_cast_and_first_layer(ops):
-    """LN phase variants: n_part = 0 (first layer: normalise x as is) and gamma = None (plain bf16 cast)."""
-    torch.manual_seed(12)
-    B, d, N = 5, 1024, 1025
-    dev = 'cuda'
-    x = torch.randn(B, d, device=dev)
-    g, be = torch.randn(d, device=dev), torch.randn(d, device=dev)
-    w = (torch.randn(N, d, device=dev) / math.sqrt(d)).bfloat16()
-    ns = ops.linear_decode_splits(N, d, 32)
-    gbar = torch.zeros(64, device=dev, dtype=torch.int32)
-    for gamma, beta in ((g, be), (None, None)):
-        h = torch.zeros(B, d, device=dev, dtype=torch.bfloat16)
-        part = torch.full((ns, B, N), float('nan'), device=dev)
-        xc = x.clone()
-        ops.decode_chain([ops.chain_ln(xc, gamma, beta, h), ops.chain_gemm(h, w, part, B * N)], B, gbar)
-        torch.cuda.synchronize()
-        assert torch.equal(xc, x)
-        ref_h = torch.nn.functional.layer_norm(x, (d,), g, be) if gamma is not None else x
-        assert rel_err(h.float(), ref_h) < 1e-2
-        assert rel_err(part.sum(0), h.double() @ w.double().t()) < 1e-4
-
-
-@pytest.mark.parametrize('B', [1, 7, 32, 33, 64])
-@pytest.mark.parametrize('N,K,cluster', [(3072, 1024, 0), (3072, 1024, 4), (1024, 1024, 0), (1024, 1024, 8), (4096, 1024, 0),
-                                       (1024, 4096, 0), (1024, 4096, 8), (1025, 1024, 0), (256, 256, 2), (200, 64, 1),
-                                       (1024, 2048, 5), (96, 1536, 3), (384, 512, 1)])
-def test_linear_decode_fused_bf16(ops, B, N, K, cluster):
-    """Cluster split-K decode GEMM (partials reduced through DSMEM) against fp64 math, all epilogues."""
-    torch.manual_seed(21)
-    a = torch.randn(B, K, device='cuda').bfloat16()
+@pytest.mark.parametrize('M', [1, 9, 16, 20, 32, 33, 64, 100, 128, 256])
+@pytest.mark.parametrize('N,K', [(3072, 1024), (1024, 1024), (4096, 1024), (1024, 4096), (1025, 1024), (768, 256), (256, 1024)])
+def test_decode_gemm_modes(ops, M, N, K):
+    """vb_decode_gemm (tcgen05 swap-AB, in-kernel split-K reduction), PLAIN and RESIDUAL epilogues, against float64
+    references computed from the same bf16 operands; repeated launches on the same counters (monotonic arrival counters)
+    and bit-identical results between launches (deterministic reduction order)."""
+    torch.manual_seed(M * 7 + N + K)
+    x = torch.randn(M, K, device='cuda').bfloat16()
     w = (torch.randn(N, K, device='cuda') / math.sqrt(K)).bfloat16()
     bias = torch.randn(N, device='cuda')
-    ref = a.double() @ w.double().t()
-    y = torch.full((B, N), float('nan'), device='cuda')
-    ops.linear_decode_fused(a, w, y, cluster_k=cluster, flags=B % 2)
-    assert rel_err(y, ref) < 1e-4
-    y2 = torch.full((B, N), float('nan'), device='cuda')
-    ops.linear_decode_fused(a, w, y2, cluster_k=cluster)
-    assert torch.equal(y, y2), 'not deterministic'
-    yb = torch.zeros(B, N, device='cuda', dtype=torch.bfloat16)
-    ops.linear_decode_fused(a, w, yb, bias=bias, gelu=True, cluster_k=cluster)
-    assert rel_err(yb.float(), torch.nn.functional.gelu(ref + bias.double())) < 1e-2
-    x = torch.randn(B, N, device='cuda')
-    x0 = x.clone()
-    ops.linear_decode_fused(a, w, x, bias=bias, residual=True, cluster_k=cluster)
-    assert rel_err(x, x0.double() + ref + bias.double()) < 1e-4
+    plan, ws, ctr = _dg_buffers(ops, M, N, K)
+    ref = x.double() @ w.double().t()
+    y = torch.full((M, N), float('nan'), device='cuda')
+    ops.decode_gemm(x, w, ops.DG_PLAIN, ws=ws, counters=ctr, y32=y)
+    y2 = torch.full((M, N), float('nan'), device='cuda')
+    ops.decode_gemm(x, w, ops.DG_PLAIN, ws=ws, counters=ctr, y32=y2, flags=ops.FLAG_LATE_TRIGGER)
+    torch.cuda.synchronize()
+    assert rel_err(y, ref) < 2e-5 and torch.equal(y, y2)
+    ops.decode_gemm(x, w, ops.DG_PLAIN, ws=ws, counters=ctr, y32=y, bias=bias)
+    assert rel_err(y, ref + bias.double()) < 2e-5
+    # the two exchange paths (thread-block cluster / DSMEM where it applies, L2 buffer + counters) sum in the same order
+    yg = torch.full((M, N), float('nan'), device='cuda')
+    ops.decode_gemm(x, w, ops.DG_PLAIN, ws=ws, counters=ctr, y32=yg, bias=bias, flags=ops.FLAG_DG_GLOBAL)
+    torch.cuda.synchronize()
+    assert torch.equal(y, yg)
+    # RESIDUAL: x += acc + bias, bf16 copy, row statistics chunks
+    xres0 = torch.randn(M, N, device='cuda')
+    xres = xres0.clone()
+    xb = torch.zeros(M, N, device='cuda', dtype=torch.bfloat16)
+    chunks = plan['tiles']
+    stats = torch.full((M, chunks, 2), float('nan'), device='cuda')
+    ops.decode_gemm(x, w, ops.DG_RESIDUAL, ws=ws, counters=ctr, bias=bias, xres=xres, y16=xb, stats_out=stats.view(-1))
+    torch.cuda.synchronize()
+    want = xres0.double() + ref + bias.double()
+    assert rel_err(xres, want) < 2e-5
+    assert torch.equal(xb, xres.bfloat16())
+    assert torch.isfinite(stats).all()
+    assert rel_err(stats[:, :, 0].sum(1), xres.double().sum(1)) < 1e-4
+    assert rel_err(stats[:, :, 1].sum(1), (xres.double() ** 2).sum(1)) < 1e-4
 
 
-@pytest.mark.parametrize('B', [1, 5, 32, 40, 64])
-@pytest.mark.parametrize('d,N,cluster', [(1024, 4096, 0), (1024, 3072, 0), (1024, 3072, 4), (256, 768, 0), (1024, 1025, 0),
-                                       (512, 512, 1), (1024, 512, 16), (512, 256, 3)])
-def test_linear_decode_fused_layernorm_on_load(ops, B, d, N, cluster):
-    """A = LayerNorm(x) computed inside the GEMM from the fp32 residual rows, row statistics combined across the cluster
-    (modules.py:271/276), and the plain-cast variant (no final norm before valle_ar.py:158)."""
-    torch.manual_seed(22)
-    x = torch.randn(B, d, device='cuda') * 2 + 0.5
-    g, be = torch.randn(d, device='cuda'), torch.randn(d, device='cuda')
-    w = (torch.randn(N, d, device='cuda') / math.sqrt(d)).bfloat16()
-    bias = torch.randn(N, device='cuda')
-    h = torch.nn.functional.layer_norm(x, (d,), g, be).bfloat16()          # the operand the kernel builds in smem
-    y = torch.full((B, N), float('nan'), device='cuda')
-    ops.linear_decode_fused(x, w, y, gamma=g, beta=be, cluster_k=cluster)
-    assert rel_err(y, h.double() @ w.double().t()) < 3e-3                    # bf16 roundings of LN(x) may flip by an ulp
-    f = torch.zeros(B, N, device='cuda', dtype=torch.bfloat16)
-    ops.linear_decode_fused(x, w, f, bias=bias, gelu=True, gamma=g, beta=be, cluster_k=cluster)
-    assert rel_err(f.float(), torch.nn.functional.gelu(h.double() @ w.double().t() + bias.double())) < 1e-2
-    yc = torch.full((B, N), float('nan'), device='cuda')
-    ops.linear_decode_fused(x, w, yc, cluster_k=cluster)                     # plain cast
-    assert rel_err(yc, x.bfloat16().double() @ w.double().t()) < 1e-4
+@pytest.mark.parametrize('M', [1, 12, 32, 48, 256])
+@pytest.mark.parametrize('d,N,n_chunks', [(1024, 3072, 1), (1024, 4096, 8), (1024, 3072, 8), (256, 768, 2), (1024, 1025, 16)])
+def test_decode_gemm_folded_layernorm(ops, M, d, N, n_chunks):
+    """LN / LN_GELU modes: LayerNorm(x; gamma, beta) . W^T (+ bias, erf-GELU) through the algebraic fold (scaled weights,
+    column sums, folded bias, (sum, sum of squares) partials of the raw rows) against the plain formula in float64."""
+    torch.manual_seed(M + d + N + n_chunks)
+    x32 = torch.randn(M, d, device='cuda') * 1.7 + 0.3
+    gamma, beta = 1 + 0.2 * torch.randn(d, device='cuda'), 0.1 * torch.randn(d, device='cuda')
+    w32 = torch.randn(N, d, device='cuda') / math.sqrt(d)
+    bias = torch.randn(N, device='cuda') * 0.1
+    ws_w = (w32 * gamma[None]).bfloat16().contiguous()
+    colsum = ws_w.float().sum(1).contiguous()
+    bfold = ((w32 * beta[None]).sum(1) + bias).contiguous()
+    xb = x32.bfloat16()
+    # statistics of the fp32 rows split into n_chunks column chunks, as a producing RESIDUAL launch writes them
+    xc = x32.view(M, n_chunks, d // n_chunks)
+    stats = torch.stack([xc.sum(-1), (xc * xc).sum(-1)], -1).contiguous()
+    plan, ws, ctr = _dg_buffers(ops, M, N, d)
+    ln = torch.nn.functional.layer_norm(x32.double(), (d,), gamma.double(), beta.double(), 1e-5)
+    ref = ln @ w32.double().t() + bias.double()
+    y = torch.full((M, N), float('nan'), device='cuda')
+    ops.decode_gemm(xb, ws_w, ops.DG_LN, ws=ws, counters=ctr, bias=bfold, colsum=colsum, stats_in=stats.view(-1),
+                    n_chunks_in=n_chunks, eps=1e-5, y32=y)
+    torch.cuda.synchronize()
+    assert rel_err(y, ref) < 1e-2
+    f = torch.zeros(M, N, device='cuda', dtype=torch.bfloat16)
+    ops.decode_gemm(xb, ws_w, ops.DG_LN_GELU, ws=ws, counters=ctr, bias=bfold, colsum=colsum, stats_in=stats.view(-1),
+                    n_chunks_in=n_chunks, eps=1e-5, y16=f)
+    torch.cuda.synchronize()
+    assert rel_err(f.float(), torch.nn.functional.gelu(ref)) < 1e-2
+    fg = torch.zeros(M, N, device='cuda', dtype=torch.bfloat16)
+    ops.decode_gemm(xb, ws_w, ops.DG_LN_GELU, ws=ws, counters=ctr, bias=bfold, colsum=colsum, stats_in=stats.view(-1),
+                    n_chunks_in=n_chunks, eps=1e-5, y16=fg, flags=ops.FLAG_DG_GLOBAL)
+    torch.cuda.synchronize()
+    assert torch.equal(f, fg)
+
+
+def test_decode_gemm_layer_chain_matches_reference(ops):
+    """out-proj -> FFN1 -> FFN2 -> QKV of one decoder layer on the fused launches (modules.py:271-278), full-size shapes,
+    B = 32, inside one PDL chain, against the float64 formulas; also replayed from a CUDA graph (counters keep counting)."""
+    torch.manual_seed(5)
+    B, d, F = 32, 1024, 4096
+    mk = lambda n, k: (torch.randn(n, k, device='cuda') / math.sqrt(k))
+    wo32, w1_32, w2_32, wq32 = mk(d, d), mk(F, d), mk(d, F), mk(3 * d, d)
+    bo, b1, b2 = (torch.randn(n, device='cuda') * 0.1 for n in (d, F, d))
+    g1, be1, g2, be2 = (1 + 0.1 * torch.randn(d, device='cuda'), 0.1 * torch.randn(d, device='cuda'),
+                        1 + 0.1 * torch.randn(d, device='cuda'), 0.1 * torch.randn(d, device='cuda'))
+    o = torch.randn(B, d, device='cuda').bfloat16()
+    x0 = torch.randn(B, d, device='cuda')
+    wo, w2 = wo32.bfloat16(), w2_32.bfloat16()
+    w1s, wqs = (w1_32 * g2[None]).bfloat16().contiguous(), (wq32 * g1[None]).bfloat16().contiguous()
+    c1, cq = w1s.float().sum(1).contiguous(), wqs.float().sum(1).contiguous()
+    bf1, bfq = ((w1_32 * be2[None]).sum(1) + b1).contiguous(), (wq32 * be1[None]).sum(1).contiguous()
+    plans = {k: ops.decode_gemm_plan(B, n, kk) for k, (n, kk) in {'o': (d, d), 'f1': (F, d), 'f2': (d, F), 'qkv': (3 * d, d)}.items()}
+    ws = torch.zeros(max(p['ws_bytes'] for p in plans.values()) // 4, device='cuda')
+    ctr = torch.zeros(4, 256, dtype=torch.int32, device='cuda')
+    ch_o, ch_f2 = plans['o']['tiles'], plans['f2']['tiles']
+    stats = torch.zeros(B * max(ch_o, ch_f2) * 2, device='cuda')
+    x, xb = x0.clone(), torch.zeros(B, d, device='cuda', dtype=torch.bfloat16)
+    f = torch.zeros(B, F, device='cuda', dtype=torch.bfloat16)
+    qkv = torch.zeros(B, 3 * d, device='cuda')
+
+    def chain():
+        ops.decode_gemm(o, wo, ops.DG_RESIDUAL, ws=ws, counters=ctr[0], bias=bo, xres=x, y16=xb, stats_out=stats)
+        ops.decode_gemm(xb, w1s, ops.DG_LN_GELU, ws=ws, counters=ctr[1], bias=bf1, colsum=c1, stats_in=stats, n_chunks_in=ch_o, y16=f)
+        ops.decode_gemm(f, w2, ops.DG_RESIDUAL, ws=ws, counters=ctr[2], bias=b2, xres=x, y16=xb, stats_out=stats)
+        ops.decode_gemm(xb, wqs, ops.DG_LN, ws=ws, counters=ctr[3], bias=bfq, colsum=cq, stats_in=stats, n_chunks_in=ch_f2, y32=qkv)
+
+    # float64 reference of the same chain (bf16 roundings only where the kernels round: o, weights, f)
+    D = torch.double
+    x1 = x0.to(D) + o.to(D) @ wo.to(D).t() + bo.to(D)
+    h2 = torch.nn.functional.layer_norm(x1, (d,), g2.to(D), be2.to(D), 1e-5)
+    f_ref = torch.nn.functional.gelu(h2 @ w1_32.to(D).t() + b1.to(D))
+    x2 = x1 + f_ref.bfloat16().to(D) @ w2.to(D).t() + b2.to(D)
+    q_ref = torch.nn.functional.layer_norm(x2, (d,), g1.to(D), be1.to(D), 1e-5) @ wq32.to(D).t()
+    chain()
+    torch.cuda.synchronize()
+    assert rel_err(f.float(), f_ref) < 1e-2 and rel_err(x, x2) < 1e-2 and rel_err(qkv, q_ref) < 1e-2
+    first = (x.clone(), qkv.clone(), f.clone())
+    g = torch.cuda.CUDAGraph()
+    x.copy_(x0)
+    torch.cuda.synchronize()
+    with torch.cuda.graph(g):
+        chain()
+    for _ in range(3):
+        x.copy_(x0)
+        g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(x, first[0]) and torch.equal(qkv, first[1]) and torch.equal(f, first[2])
+
+
+@pytest.mark.parametrize('top_k,top_p,temp', [(1, 1.0, 1.0), (50, 1.0, 1.0), (10, 0.8, 0.7)])
+def test_ar_step_tail_matches_separate_kernels(ops, top_k, top_p, temp):
+    """vb_ar_step_tail == vb_sample + vb_ar_bookkeeping + vb_embed_sum_pe (bit for bit), incl. finished rows and the stop
+    detection, over several steps; the row statistics are those of the embedded row."""
+    torch.manual_seed(3)
+    B, V, d, eos, max_new = 6, 1025, 256, 1024, 5
+    table = torch.randn(V + 1, d, device='cuda')
+    pe = torch.randn(64, d, device='cuda')
+    mk_state = lambda: dict(last=torch.tensor([5, eos, 7, 8, 9, 10], dtype=torch.int32, device='cuda'),
+                            slp=torch.zeros(B, device='cuda'), codes=torch.zeros(B, max_new, dtype=torch.int32, device='cuda'),
+                            seq=torch.full((B,), 11, dtype=torch.int32, device='cuda'),
+                            pos=torch.arange(B, dtype=torch.int32, device='cuda'))
+    a, b = mk_state(), mk_state()
+    st_a = torch.tensor([0, -1, 0, 0], dtype=torch.int32, device='cuda')
+    st_b = torch.tensor([0, -1], dtype=torch.int32, device='cuda')
+    seed = torch.tensor([1234], dtype=torch.int64, device='cuda')
+    x, xb, stats = torch.zeros(B, d, device='cuda'), torch.zeros(B, d, device='cuda', dtype=torch.bfloat16), torch.zeros(2 * B, device='cuda')
+    x_ref = torch.zeros(B, d, device='cuda')
+    tok, lp = torch.zeros(B, dtype=torch.int32, device='cuda'), torch.zeros(B, device='cuda')
+    for step in range(max_new):
+        logits = torch.randn(B, V, device='cuda') * 3
+        if step == 3:
+            logits[:, eos] += 100.0                              # every running row draws EOS -> stop_step = 3
+        ops.ar_step_tail(logits, V, temperature=temp, top_k=top_k, top_p=top_p, uniforms=None, seed=seed, row_offset=4,
+                         last=a['last'], sum_logprobs=a['slp'], codes_out=a['codes'], seq_lens=a['seq'], audio_pos=a['pos'],
+                         state=st_a, eos=eos, table=table, pe=pe, x=x, xb=xb, stats=stats)
+        ops.sample(logits, 1, 0, V, B, V, temperature=temp, top_k=top_k, top_p=top_p, out_tok=tok, out_logprob=lp,
+                   seed=1234, step_ptr=st_b, row_offset=4)
+        ops.ar_bookkeeping(tok, lp, b['last'], b['slp'], b['codes'], b['seq'], b['pos'], st_b, eos)
+        ops.embed_sum_pe(b['last'].view(B, 1, 1), table[None].contiguous(), pe, x_ref, pos_b=b['pos'])
+        torch.cuda.synchronize()
+        for k in a:
+            assert torch.equal(a[k], b[k]), (k, step)
+        assert st_a.tolist()[:2] == st_b.tolist() and st_a.tolist()[2:] == [0, 0]
+        assert torch.equal(x, x_ref) and torch.equal(xb, x_ref.bfloat16())
+        s2 = stats.view(B, 2)
+        assert rel_err(s2[:, 0], x_ref.double().sum(1)) < 1e-5 and rel_err(s2[:, 1], (x_ref.double() ** 2).sum(1)) < 1e-5
+    assert st_a.tolist()[1] == 3
 
 
 def _pool_swizzle(x):
@@ -474,7 +520,7 @@ def test_attention_prefill_tc(ops, B, S, H, mode):
     for b in range(B):        # query rows beyond kv_len are padding: not compared
         n = int(kl[b])
         assert torch.isfinite(got[b, :n]).all()
-        assert rel_err(got[b, :n], ref[b, :n]) < 1.5e-2, (b, rel_err(got[b, :n], ref[b, :n]))
+        assert rel_err(got[b, :n], ref[b, :n]) < 1e-2, (b, rel_err(got[b, :n], ref[b, :n]))
 
 
 @pytest.mark.parametrize('dt', [torch.float32, torch.bfloat16])

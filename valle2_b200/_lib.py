@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(HERE, 'lib', 'libvalle_b200.so')
 VB_F32, VB_BF16 = 0, 1
 EPI_NONE, EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RESIDUAL = 0, 1, 2, 3
 MASK_NONE, MASK_PREFIX_LM, MASK_EXPLICIT = 0, 1, 2
-FLAG_LATE_TRIGGER, FLAG_PREFETCH_KV, FLAG_ATTN_SIMT = 1, 2, 4
+FLAG_LATE_TRIGGER, FLAG_PREFETCH_KV, FLAG_ATTN_SIMT, FLAG_ATTN_TICKET, FLAG_DG_GLOBAL = 1, 2, 4, 8, 16
 
 _p, _i, _i64, _f, _u64 = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_uint64
 
@@ -32,8 +32,12 @@ SIGNATURES = {
     'vb_linear_decode_rows_splits': (_i, [_i, _i64, _i]),
     'vb_linear_decode_rows_ln': (_i, [_p, _i64, _p, _p, _f, _p, _i64, _p, _p, _i, _i64, _i, _i64, _i64, _i, _i, _p]),
     'vb_linear_decode_rows': (_i, [_p, _i64, _p, _i64, _p, _p, _i, _i64, _i64, _i, _i64, _i64, _i, _i, _i, _p, _p]),
-    'vb_linear_decode_fused_cluster': (_i, [_i, _i]),
-    'vb_linear_decode_fused': (_i, [_p, _i, _i64, _p, _p, _f, _p, _i64, _p, _p, _i, _i64, _i, _i, _i, _i, _i, _i, _p]),
+    'vb_decode_gemm_plan': (_i, [_i, _i64, _i64, _p, _p, _p]),
+    'vb_decode_gemm': (_i, [_p, _i64, _p, _i64, _i, _i64, _i64, _i, _p, _p, _p, _i, _f, _p, _i64, _p, _i64, _p, _i64, _p, _p, _p,
+                            _i, _p]),
+    'vb_decode_gemm_set_debug': (_i, [_p]),
+    'vb_ar_step_tail': (_i, [_p, _i64, _i, _f, _i, _f, _p, _p, _i, _p, _p, _p, _i64, _p, _p, _p, _i, _i, _p, _p, _i, _p, _p, _p,
+                             _p]),
     'vb_kv_prefetch_l2': (_i, [_p, _i, _p, _i, _p, _i, _i, _i, _i, _i, _p]),
     'vb_transpose': (_i, [_p, _i, _i64, _i64, _i64, _p, _i64, _p]),
     'vb_colsum': (_i, [_p, _i, _i64, _i, _i64, _p, _i, _f, _p]),
@@ -45,8 +49,6 @@ SIGNATURES = {
     'vb_attention_bwd': (_i, [_p, _p, _p, _p, _i, _p, _p, _i, _i, _i, _i, _i, _p, _p, _i, _p]),
     'vb_cross_entropy': (_i, [_p, _i64, _p, _i64, _i, _p, _p, _i64, _f, _p]),
     'vb_embed_bwd': (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i64, _i64, _p]),
-    'vb_decode_chain': (_i, [_p, _i, _i, _p, _p]),
-    'vb_decode_chain_set_debug': (_i, [_p]),
     'vb_linear_decode_set_debug': (_i, [_p]),
     'vb_attn_decode_set_debug': (_i, [_p]),
     'vb_attention_prefill_set_debug': (_i, [_p]),
@@ -61,18 +63,6 @@ SIGNATURES = {
     'vb_sample': (_i, [_p, _i, _i64, _i64, _i, _i, _f, _i, _f, _p, _u64, _p, _i, _p, _p, _p]),
     'vb_ar_bookkeeping': (_i, [_p, _p, _p, _p, _p, _i64, _p, _p, _p, _i, _i, _p]),
 }
-
-
-PHASE_GEMM, PHASE_LN, PHASE_ACT = 0, 1, 2
-
-
-class ChainPhase(C.Structure):
-    """Mirror of ``vb_chain_phase`` (include/valle_b200.h)."""
-    _fields_ = [('type', C.c_int32), ('N', C.c_int32), ('K', C.c_int32), ('max_split', C.c_int32),
-                ('x', C.c_void_p), ('w', C.c_void_p), ('out_part', C.c_void_p), ('out_part_stride', C.c_int64),
-                ('x32', C.c_void_p), ('in_part', C.c_void_p), ('n_part', C.c_int32), ('d', C.c_int32),
-                ('in_part_stride', C.c_int64), ('bias', C.c_void_p), ('gamma', C.c_void_p), ('beta', C.c_void_p),
-                ('y', C.c_void_p), ('eps', C.c_float), ('reserved', C.c_int32)]
 
 
 class VBError(RuntimeError):

@@ -714,7 +714,7 @@ extern "C" int vb_attn_decode_paged(const float* qkv_part, int n_part, int64_t p
             VB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));                   \
             configured = true;                                                                                        \
         }                                                                                                             \
-        if (n_tsplit > 1 && n_tsplit <= 8 && attn_cluster_enabled()) {                                                \
+        if (n_tsplit > 1 && n_tsplit <= 8 && attn_cluster_enabled() && !(flags & VB_FLAG_ATTN_TICKET)) {                                                \
             /* one cluster per (b, h): splits merged through DSMEM, counters == nullptr selects that path */          \
             cudaLaunchConfig_t cfg = {};                                                                              \
             cfg.gridDim = grid; cfg.blockDim = dim3(MMA_THREADS); cfg.dynamicSmemBytes = SMEM; cfg.stream = st;       \

@@ -111,6 +111,12 @@ class StackRunner:
         return x
 
 
+def _as_i64(seed: int) -> int:
+    """The 64 seed bits as a signed int64 (what a torch.int64 tensor stores)."""
+    seed &= (1 << 64) - 1
+    return seed - (1 << 64) if seed >= (1 << 63) else seed
+
+
 def _i32(t: torch.Tensor, device) -> torch.Tensor:
     return t.to(device=device, dtype=torch.int32).contiguous()
 
@@ -143,19 +149,16 @@ class ARDecoder:
         self._graph = None
         self._graph_key = None
         self._streams = []
+        self._seed_dev = torch.zeros(1, device=self.device, dtype=torch.int64)     # read by vb_ar_step_tail: graphs are seed-independent
+        if precision == 'bf16':
+            self._fold_layernorm(model)
         self.page_permutation_seed = None      # tests: scatter the logical pages over the pool
         # tunables (env overrides are for experiments; the defaults are the measured best)
-        self.use_chain = os.environ.get('VALLE_B200_CHAIN', '0') != '0'
-        self.use_fused = os.environ.get('VALLE_B200_FUSED', '0') != '0'
-        # cluster size along K of the fused decode GEMMs (0 = fill the SMs), csrc/gemm_decode_fused.cu
-        self.fused_cluster = {'qkv': 0, 'o': 0, 'f1': 0, 'f2': 0, 'lg': 0}
-        for k, v in [kv.split('=') for kv in os.environ.get('VALLE_B200_FUSED_CLUSTER', '').split(';') if kv]:
-            self.fused_cluster[k] = int(v)
-        # decode GEMM form: 'rows' = full-K mma.sync kernel with fused epilogues (csrc/gemm_decode_mma.cu, sub-batches of
-        # <= 32 sequences), 'splitk' = tcgen05 swap-AB slices + reduce kernels (csrc/gemm_tc.cu), 'auto' = by batch size,
-        # or five letters [rs] for qkv, out-proj, FFN1, FFN2, logits (see _mix)
+        # decode GEMM form: 'lean' = full-K mma.sync rows kernels with LayerNorm on load (csrc/gemm_decode_mma.cu, <= 8
+        # sequences), 'tc' = tcgen05 swap-AB GEMMs with the split-K reduction + folded LayerNorm + epilogues inside the launch
+        # (csrc/gemm_decode_tc.cu, 5 launches per layer), 'splitk' = the round-1 form: tcgen05 split-K slices + LayerNorm /
+        # GELU-reduce kernels (8 launches per layer; kept as the A/B reference), 'auto' = lean up to 8 sequences, tc above.
         self.decode_gemm = os.environ.get('VALLE_B200_DECODE_GEMM', 'auto')
-        self.rows_qkv_split = int(os.environ.get('VALLE_B200_ROWS_QKV_SPLIT', '1'))
         # lean path, >= 4 sequences: the attention kernel releases its successors only after its own wait (see
         # csrc/attn_decode.cu; measured -2 % step time at B = 4..8, +2 % at B = 1, tools/step_breakdown.py)
         self.attn_late = ops.FLAG_LATE_TRIGGER if os.environ.get('VALLE_B200_ATTN_LATE', '1') != '0' else 0
@@ -164,11 +167,23 @@ class ARDecoder:
         self.n_sub_override = int(os.environ.get('VALLE_B200_SUBBATCH', '0'))
         self.attn_ctas = int(os.environ.get('VALLE_B200_ATTN_CTAS', '0'))
         self.n_tsplit_override = 0             # tests: pin the flash-decoding split
-        # percentage range of every sequence's cached pages of the NEXT layer pulled into L2 while the GEMM chain runs
-        pf = os.environ.get('VALLE_B200_KV_PREFETCH', '0,0').split(',')
-        self.kv_prefetch = (int(pf[0]), int(pf[1]))
-        self._pf_stream = None
         self.attn_flags = ops.FLAG_ATTN_SIMT if os.environ.get('VALLE_B200_ATTN_SIMT', '0') != '0' else 0
+
+    def _fold_layernorm(self, model):
+        """Weight-load-time fold of norm1 / norm2 into the QKV / FFN1 GEMMs of the decode path (csrc/gemm_decode_tc.cu):
+            LN(x) . W^T = rstd (x . (gamma (.) W)^T - mean c) + beta . W^T,    c[n] = sum_k bf16(gamma[k] W[n][k])
+        The scaled weights are rounded to bf16 ONCE from the fp32 master weights; c is summed from the rounded values (what
+        the MMA multiplies); beta . W^T (+ the layer's bias) stays fp32.  Elementwise products and row sums only."""
+        for L, layer in zip(self.weights.layers, model.transformer.layers):
+            for wkey, lin, nkey, bkey, out in (('wqkv_s', layer.self_attn.qkv, 'norm1', None, ('c_qkv', 'b_qkv')),
+                                               ('w1_s', layer.ffn.linear_1, 'norm2', 'b1', ('c_1', 'b_1'))):
+                g, b, _ = L[nkey]
+                w32 = lin.weight.detach().float()
+                ws = (w32 * g[0][None, :]).to(self.cd).contiguous()
+                L[wkey] = ws
+                L[out[0]] = ws.float().sum(dim=1).contiguous()
+                fold_b = (w32 * b[0][None, :]).sum(dim=1)
+                L[out[1]] = (fold_b + L[bkey] if bkey else fold_b).contiguous()
 
     # ------------------------------------------------------------------------------------------
     def _n_sub(self, B: int) -> int:
@@ -178,43 +193,19 @@ class ARDecoder:
             return max(1, min(self.n_sub_override, B))
         return 1
 
-    def _chain_ok(self, sub: dict) -> bool:
-        # Concurrent chain kernels (one per sub-batch) spin on grid barriers and cannot share an SM: two of them could
-        # each hold part of the GPU and wait for the rest forever, so the chain runs only when the batch is not split.
-        return (self.precision == 'bf16' and self.use_chain and sub['B'] <= 64 and len(self._state['subs']) == 1)
-
-    def _mix(self, sub: dict) -> dict:
-        """Form of each decode GEMM for this sub-batch: 'r' rows (mma.sync, full K per CTA), 's' tcgen05 split-K slices.
-        In the rows form every CTA reads the whole (B, K) activation matrix from L2 -- 0.3 us at B = 1, 1.4 us at B = 32
-        (tools/rows_timeline.py) -- so 'auto' uses it (as the lean path) up to 8 sequences and slices above; every mix
-        was measured with tools/layer_chain.py and tools/ab_mix.sh."""
-        dg = self.decode_gemm
-        if dg in ('auto', 'lean'):      # small batches take the lean path (_lean_ok) before this is consulted
-            dg = 'splitk'
-        if dg == 'rows':
-            dg = 'rrrrr'
-        elif dg == 'splitk':
-            dg = 'sssss'
-        assert len(dg) == 5 and set(dg) <= {'r', 's'}, 'VALLE_B200_DECODE_GEMM: auto | rows | splitk | 5 x [rs] (qkv,o,f1,f2,logits)'
-        return dict(zip(('qkv', 'o', 'f1', 'f2', 'lg'), dg))
-
     def _lean_ok(self, sub: dict) -> bool:
         """Five kernels per layer (small batch): LayerNorm on load inside the QKV / FFN1 GEMMs, residual adds and GELU in
         the epilogues, FFN2 with its whole K = F in one CTA (csrc/gemm_decode_mma.cu).  Every CTA reads the whole fp32
         residual matrix, which is what limits it to <= 8 sequences."""
-        dg = self.decode_gemm
-        if dg not in ('auto', 'lean') or self.precision != 'bf16' or self.use_fused or self.use_chain:
+        if self.decode_gemm not in ('auto', 'lean') or self.precision != 'bf16':
             return False
         return (sub['B'] <= 8 and self.d in (256, 512, 1024) and self.weights.F % 256 == 0
                 and ops.linear_decode_rows_splits(self.weights.F, 0, sub['B']) == 1)
 
-    def _rows_ok(self, sub: dict) -> bool:
-        """The mixed decode path (any GEMM in rows form) applies to this sub-batch."""
-        return (self.precision == 'bf16' and not self.use_fused and not self.use_chain and 'nr' in sub
-                and 'r' in self._mix(sub).values())
-
-    def _fused_ok(self, sub: dict) -> bool:
-        return self.precision == 'bf16' and self.use_fused and sub['B'] <= 64 and self.d % 64 == 0
+    def _tc_ok(self, sub: dict) -> bool:
+        """Five launches per layer on the tcgen05 decode GEMM with in-kernel split-K reduction (csrc/gemm_decode_tc.cu)."""
+        return (self.precision == 'bf16' and self.decode_gemm in ('auto', 'tc') and not self._lean_ok(sub)
+                and sub['B'] <= 256 and self.d % 8 == 0 and self.weights.F % 8 == 0 and 'dg' in sub)
 
     def _make_sub(self, st: dict, b0: int, b1: int, state: torch.Tensor) -> dict:
         """Workspaces of one sub-batch (rows b0..b1 of the batch) + row-slice views of the shared decode state."""
@@ -226,33 +217,41 @@ class ARDecoder:
         sub['sample'] = torch.zeros(B, device=dev, dtype=torch.int32)
         sub['logprob'] = torch.zeros(B, device=dev, dtype=torch.float32)
         sub['x'] = torch.zeros(B, d, device=dev, dtype=torch.float32)
+        sub['lg'] = torch.zeros(B, V, device=dev, dtype=torch.float32)
         if self.precision == 'bf16':
-            ms = 32
-            ns = {k: ops.linear_decode_splits(n, kk, ms) for k, (n, kk) in
-                  {'qkv': (3 * d, d), 'o': (d, d), 'f1': (F, d), 'f2': (d, F), 'lg': (V, d)}.items()}
-            sub['ns'] = ns
             sub['h'] = torch.zeros(B, d, device=dev, dtype=self.cd)
             sub['o'] = torch.zeros(B, d, device=dev, dtype=self.cd)
             sub['f'] = torch.zeros(B, F, device=dev, dtype=self.cd)
-            sub['p_qkv'] = torch.zeros(ns['qkv'], B, 3 * d, device=dev, dtype=torch.float32)
-            sub['p_o'] = torch.zeros(ns['o'], B, d, device=dev, dtype=torch.float32)
-            sub['p_f1'] = torch.zeros(ns['f1'], B, F, device=dev, dtype=torch.float32)
-            sub['p_f2'] = torch.zeros(ns['f2'], B, d, device=dev, dtype=torch.float32)
-            sub['p_lg'] = torch.zeros(ns['lg'], B, V, device=dev, dtype=torch.float32)
-            sub['gbar'] = torch.zeros(64, device=dev, dtype=torch.int32)     # grid-barrier counter of the chain kernel
+            sub['xb'] = torch.zeros(B, d, device=dev, dtype=self.cd)          # bf16 copy of the residual rows (tc path)
             sub['qkv32'] = torch.zeros(B, 3 * d, device=dev, dtype=torch.float32)
-            if self.d % 256 == 0 and F % 256 == 0 and B <= 32:
-                nr = {'qkv': ops.linear_decode_rows_splits(d, self.rows_qkv_split, B), 'f2': ops.linear_decode_rows_splits(F, 1, B)}
-                sub['nr'] = nr
-                sub['r_qkv'] = torch.zeros(nr['qkv'], B, 3 * d, device=dev, dtype=torch.float32)
-                sub['r_f2'] = torch.zeros(nr['f2'], B, d, device=dev, dtype=torch.float32)
-            sub['lg'] = torch.zeros(B, V, device=dev, dtype=torch.float32)
+            if self.decode_gemm == 'splitk':
+                ms = 32
+                ns = {k: ops.linear_decode_splits(n, kk, ms) for k, (n, kk) in
+                      {'qkv': (3 * d, d), 'o': (d, d), 'f1': (F, d), 'f2': (d, F), 'lg': (V, d)}.items()}
+                sub['ns'] = ns
+                sub['p_qkv'] = torch.zeros(ns['qkv'], B, 3 * d, device=dev, dtype=torch.float32)
+                sub['p_o'] = torch.zeros(ns['o'], B, d, device=dev, dtype=torch.float32)
+                sub['p_f1'] = torch.zeros(ns['f1'], B, F, device=dev, dtype=torch.float32)
+                sub['p_f2'] = torch.zeros(ns['f2'], B, d, device=dev, dtype=torch.float32)
+                sub['p_lg'] = torch.zeros(ns['lg'], B, V, device=dev, dtype=torch.float32)
+            elif B <= 256:
+                # tc path: plan of every GEMM shape (tiles, n_split), the shared exchange buffer, one counter array per shape
+                dg = {k: ops.decode_gemm_plan(B, n, kk) for k, (n, kk) in
+                      {'qkv': (3 * d, d), 'o': (d, d), 'f1': (F, d), 'f2': (d, F), 'lg': (V, d)}.items()}
+                sub['dg'] = dg
+                sub['dg_ws'] = torch.zeros(max(v['ws_bytes'] for v in dg.values()) // 4, device=dev, dtype=torch.float32)
+                sub['dg_ctr'] = torch.zeros(len(dg), 256, device=dev, dtype=torch.int32)
+                chunks = max(dg['o']['tiles'], dg['f2']['tiles'], 1)
+                sub['stats'] = torch.zeros(B * chunks * 2, device=dev, dtype=torch.float32)
+            if self.d % 256 == 0 and F % 256 == 0 and B <= 8:
+                sub['r_qkv'] = torch.zeros(1, B, 3 * d, device=dev, dtype=torch.float32)
+            if 'stats' not in sub:
+                sub['stats'] = torch.zeros(B * 2, device=dev, dtype=torch.float32)
         else:
             sub['h'] = torch.zeros(B, d, device=dev, dtype=torch.float32)
             sub['qkv'] = torch.zeros(B, 3 * d, device=dev, dtype=torch.float32)
             sub['o'] = torch.zeros(B, d, device=dev, dtype=torch.float32)
             sub['f'] = torch.zeros(B, F, device=dev, dtype=torch.float32)
-            sub['lg'] = torch.zeros(B, V, device=dev, dtype=torch.float32)
         # flash-decoding split: enough CTAs to fill the GPU, never more splits than pages
         sm = ops.device_info()['sm_count']
         # ~3.5 CTAs per SM keep enough pages in flight and enough warps issuing (measured: 512 CTAs at B=32, H=16)
@@ -264,7 +263,7 @@ class ARDecoder:
 
     def _alloc_key(self, B: int, max_pages: int, max_new: int):
         return (B, max_pages, max_new, self._n_sub(B), self.n_tsplit_override, self.attn_ctas, self.page_permutation_seed,
-                self.decode_gemm, self.use_chain, self.use_fused, self.rows_qkv_split, self.precision)
+                self.decode_gemm, self.precision)
 
     def _alloc(self, B: int, max_ctx: int, max_new: int):
         """Decode state for a batch: KV page pools, page table, counters, workspaces.  A request of the same shape as the
@@ -279,7 +278,10 @@ class ARDecoder:
         if st is not None and st.get('key') == key:
             st['seq_lens'].zero_(); st['audio_pos'].zero_(); st['last'].zero_(); st['sum_logprobs'].zero_()
             st['codes_out'].zero_()
-            st['state'][:, 0].zero_(); st['state'][:, 1].fill_(-1)
+            st['state'].zero_(); st['state'][:, 1].fill_(-1)
+            for sub in st['subs']:
+                if 'dg_ctr' in sub:
+                    sub['dg_ctr'].zero_()
             return st
         st = {'B': B, 'max_pages': max_pages, 'max_new': max_new, 'key': key}
         st['pools'] = torch.zeros(L, B * max_pages, 2, H, PAGE, self.Dh, device=dev, dtype=self.cd)
@@ -294,7 +296,8 @@ class ARDecoder:
         st['sum_logprobs'] = torch.zeros(B, device=dev, dtype=torch.float32)
         st['codes_out'] = torch.zeros(B, max_new, device=dev, dtype=torch.int32)
         n_sub = self._n_sub(B)
-        st['state'] = torch.tensor([[0, -1]] * n_sub, device=dev, dtype=torch.int32)     # per sub-batch {step, stop_step}
+        # per sub-batch {step, stop_step, arrivals, any row running} (the last two: scratch of vb_ar_step_tail)
+        st['state'] = torch.tensor([[0, -1, 0, 0]] * n_sub, device=dev, dtype=torch.int32)
         bounds = [(B * i) // n_sub for i in range(n_sub + 1)]
         self._state = None
         self._graph = None                 # release the old pools / graph before the new ones are allocated
@@ -324,26 +327,37 @@ class ARDecoder:
                 done.record(s)
             cur.wait_event(done)
 
+    def _dg(self, sub: dict, kind: str, x: torch.Tensor, w: torch.Tensor, mode: int, **kw):
+        """One vb_decode_gemm launch of the tc path; kind picks the counter array (one per GEMM shape)."""
+        idx = ('qkv', 'o', 'f1', 'f2', 'lg').index(kind)
+        ops.decode_gemm(x, w, mode, ws=sub['dg_ws'], counters=sub['dg_ctr'][idx], **kw)
+
+    def _tail(self, sub: dict, samp: dict, uniforms: torch.Tensor | None, eos: int):
+        """sample -> bookkeeping -> next step's input row (fp32, bf16 copy, row statistics) in one launch."""
+        B = sub['B']
+        if uniforms is not None:
+            uniforms = uniforms[sub['b0']:sub['b0'] + B].contiguous()
+        ops.ar_step_tail(sub['lg'], self.V, temperature=samp['temperature'], top_k=samp['top_k'], top_p=samp['top_p'],
+                         uniforms=uniforms, seed=self._seed_dev, row_offset=sub['b0'], last=sub['last'],
+                         sum_logprobs=sub['sum_logprobs'], codes_out=sub['codes_out'], seq_lens=sub['seq_lens'],
+                         audio_pos=sub['audio_pos'], state=sub['state'], eos=eos, table=self.aud_table[0], pe=self.pe_a,
+                         x=sub['x'], xb=sub['xb'], stats=sub['stats'])
+
     def _logits_sample_book(self, sub: dict, x_rows: torch.Tensor, samp: dict, uniforms: torch.Tensor | None, eos: int,
                             logits_done: bool = False):
-        """x_rows (B,d) fp32 final hidden rows of the sub-batch -> logits -> sample -> bookkeeping."""
+        """x_rows (B,d) fp32 final hidden rows of the sub-batch -> logits -> sample -> bookkeeping (-> next input row)."""
         B, V = sub['B'], self.V
         if self._lean_ok(sub):
             ops.linear_decode_rows_ln(x_rows, self.wproj, sub['lg'])                  # plain cast on load (no final norm, K-2)
-            lg, n_part, pstride = sub['lg'], 1, 0
-        elif self._rows_ok(sub):
-            if not logits_done:
-                ops.residual_layernorm(x_rows, None, None, sub['h'])                  # cast to bf16 (no final norm, K-2)
-            if self._mix(sub)['lg'] == 'r':
-                ops.linear_decode_rows(sub['h'], self.wproj, sub['lg'])
-                lg, n_part, pstride = sub['lg'], 1, 0
-            else:
-                ops.linear_decode(sub['h'], self.wproj, sub['p_lg'], B * V, 32)
-                lg, n_part, pstride = sub['p_lg'], sub['ns']['lg'], B * V
-        elif self._fused_ok(sub):
-            ops.linear_decode_fused(x_rows, self.wproj, sub['lg'], cluster_k=self.fused_cluster['lg'])   # plain cast on load (no final norm, K-2)
-            lg, n_part, pstride = sub['lg'], 1, 0
-        elif self.precision == 'bf16':
+            self._tail(sub, samp, uniforms, eos)
+            return
+        if self._tc_ok(sub):
+            if not logits_done:                 # first token: the prefill's last hidden rows, cast to bf16
+                ops.residual_layernorm(x_rows, None, None, sub['h'])
+                self._dg(sub, 'lg', sub['h'], self.wproj, ops.DG_PLAIN, y32=sub['lg'])
+            self._tail(sub, samp, uniforms, eos)
+            return
+        if self.precision == 'bf16':
             if not logits_done:
                 ops.residual_layernorm(x_rows, None, None, sub['h'])                  # cast to bf16 (no final norm, K-2)
                 ops.linear_decode(sub['h'], self.wproj, sub['p_lg'], B * V, 32)
@@ -362,6 +376,7 @@ class ARDecoder:
     def first_token(self, samp: dict, uniforms: torch.Tensor | None, eos: int):
         """Sample the first generated token of every sequence from the prefill's last hidden rows."""
         st = self._state
+        self._seed_dev.fill_(_as_i64(samp['seed']))
         self._for_each_sub(lambda sub: self._logits_sample_book(
             sub, st['x_last'][sub['b0']:sub['b0'] + sub['B']], samp, uniforms, eos))
 
@@ -373,9 +388,9 @@ class ARDecoder:
         st = self._state
         B, d, H, Dh, F = sub['B'], self.d, self.H, self.Dh, self.weights.F
         x = sub['x']
-        ops.embed_sum_pe(sub['last'].view(B, 1, 1), self.aud_table, self.pe_a, x, pos_b=sub['audio_pos'])
         layers = self.weights.layers
         if self._lean_ok(sub):
+            # the step's input row x was written by the previous launch of vb_ar_step_tail (first_token or the last step)
             qkv32 = sub['r_qkv'][0]
             for li, L in enumerate(layers):
                 g, b, eps = L['norm1']
@@ -394,107 +409,28 @@ class ARDecoder:
                 ops.linear_decode_rows(sub['f'], L['w2'], x, bias=L['b2'], residual=True, want_split=0)
             self._logits_sample_book(sub, x, samp, uniforms, eos)
             return
-        if self._rows_ok(sub):
-            # Per GEMM one of two forms (self._mix(sub)): 'r' = rows kernel (csrc/gemm_decode_mma.cu: whole K inside one CTA,
-            # so out-proj adds into the residual stream and FFN1 applies bias + GELU in the epilogue -- no reduce kernel; only
-            # FFN2, K = F > 1024, leaves slices); 's' = tcgen05 swap-AB split-K slices (csrc/gemm_tc.cu) that the next
-            # LayerNorm / GELU-reduce / attention kernel adds in index order.
-            mix, nr, ns = self._mix(sub), sub['nr'], sub['ns']
-            f2_direct = mix['f2'] == 'r' and nr['f2'] == 1
-            if mix['f2'] == 'r':
-                f2_part, f2_n = sub['r_f2'], nr['f2']
-            else:
-                f2_part, f2_n = sub['p_f2'], ns['f2']
+        if self._tc_ok(sub):
+            # Five launches per layer (csrc/gemm_decode_tc.cu): every GEMM reduces its split-K partials itself; norm1 / norm2
+            # are folded into the QKV / FFN1 GEMMs (pre-scaled weights + row statistics written by the producer of the rows);
+            # out-proj and FFN2 add into the fp32 residual stream and leave its bf16 copy + statistics for the next GEMM.
+            dg, xb, stats = sub['dg'], sub['xb'], sub['stats']
+            ch_o, ch_f2 = dg['o']['tiles'], dg['f2']['tiles']
             for li, L in enumerate(layers):
-                g, b, eps = L['norm1']
-                if li == 0 or f2_direct:
-                    ops.residual_layernorm(x, g[0], b[0], sub['h'], eps=eps)
-                else:
-                    ops.residual_layernorm(x, g[0], b[0], sub['h'], part=f2_part, n_part=f2_n, part_stride=B * d,
-                                           bias=layers[li - 1]['b2'], eps=eps)
-                if mix['qkv'] == 'r':
-                    ops.linear_decode_rows(sub['h'], L['wqkv'], sub['r_qkv'] if nr['qkv'] > 1 else sub['r_qkv'][0],
-                                           want_split=self.rows_qkv_split, flags=ops.FLAG_LATE_TRIGGER)
-                    qkv_part, qkv_n = sub['r_qkv'], nr['qkv']
-                else:
-                    ops.linear_decode(sub['h'], L['wqkv'], sub['p_qkv'], B * 3 * d, 32, ops.FLAG_LATE_TRIGGER)
-                    qkv_part, qkv_n = sub['p_qkv'], ns['qkv']
-                ops.attn_decode_paged(qkv_part, qkv_n, B * 3 * d, st['pools'][li], sub['block_table'],
-                                      sub['seq_lens'], sub['o'], B, H, Dh, sub['n_tsplit'], sub['attn_ws'],
-                                      ops.FLAG_PREFETCH_KV | self.attn_flags | self.attn_late_splitk)
-                g, b, eps = L['norm2']
-                if mix['o'] == 'r':
-                    ops.linear_decode_rows(sub['o'], L['wo'], x, bias=L['bo'], residual=True)
-                    ops.residual_layernorm(x, g[0], b[0], sub['h'], eps=eps)
-                else:
-                    ops.linear_decode(sub['o'], L['wo'], sub['p_o'], B * d, 32)
-                    ops.residual_layernorm(x, g[0], b[0], sub['h'], part=sub['p_o'], n_part=ns['o'], part_stride=B * d,
-                                           bias=L['bo'], eps=eps)
-                if mix['f1'] == 'r':
-                    ops.linear_decode_rows(sub['h'], L['w1'], sub['f'], bias=L['b1'], gelu=True)
-                else:
-                    ops.linear_decode(sub['h'], L['w1'], sub['p_f1'], B * F, 32)
-                    ops.reduce_bias_act(sub['p_f1'], ns['f1'], B * F, L['b1'], True, sub['f'])
-                if f2_direct:
-                    ops.linear_decode_rows(sub['f'], L['w2'], x, bias=L['b2'], residual=True)
-                elif mix['f2'] == 'r':
-                    ops.linear_decode_rows(sub['f'], L['w2'], sub['r_f2'])
-                else:
-                    ops.linear_decode(sub['f'], L['w2'], sub['p_f2'], B * d, 32)
-            if f2_direct:
-                ops.residual_layernorm(x, None, None, sub['h'])
-            else:       # last FFN2 slices + bias into the residual stream, and the bf16 cast for the logits projection
-                ops.residual_layernorm(x, None, None, sub['h'], part=f2_part, n_part=f2_n, part_stride=B * d,
-                                       bias=layers[-1]['b2'])
-            self._logits_sample_book(sub, x, samp, uniforms, eos, logits_done=True)
-            return
-        if self._fused_ok(sub):
-            # five dependent kernels per layer: split-K is reduced inside a thread-block cluster, LayerNorm runs on load
-            # inside the QKV / FFN1 GEMMs, bias + residual / GELU in the epilogues (csrc/gemm_decode_fused.cu)
-            cl = self.fused_cluster
-            for li, L in enumerate(layers):
-                g, b, eps = L['norm1']
-                ops.linear_decode_fused(x, L['wqkv'], sub['qkv32'], gamma=g[0], beta=b[0], eps=eps, cluster_k=cl['qkv'],
-                                        flags=ops.FLAG_LATE_TRIGGER)
+                eps1, eps2 = L['norm1'][2], L['norm2'][2]
+                self._dg(sub, 'qkv', xb, L['wqkv_s'], ops.DG_LN, bias=L['b_qkv'], colsum=L['c_qkv'], stats_in=stats,
+                         n_chunks_in=1 if li == 0 else ch_f2, eps=eps1, y32=sub['qkv32'],
+                         flags=ops.FLAG_LATE_TRIGGER if (li == 0 or self.qkv_late_all) else 0)
                 ops.attn_decode_paged(sub['qkv32'], 1, 0, st['pools'][li], sub['block_table'], sub['seq_lens'], sub['o'],
-                                      B, H, Dh, sub['n_tsplit'], sub['attn_ws'], ops.FLAG_PREFETCH_KV | self.attn_flags | self.attn_late_splitk)
-                ops.linear_decode_fused(sub['o'], L['wo'], x, bias=L['bo'], residual=True, cluster_k=cl['o'])
-                g, b, eps = L['norm2']
-                ops.linear_decode_fused(x, L['w1'], sub['f'], bias=L['b1'], gelu=True, gamma=g[0], beta=b[0], eps=eps,
-                                        cluster_k=cl['f1'])
-                ops.linear_decode_fused(sub['f'], L['w2'], x, bias=L['b2'], residual=True, cluster_k=cl['f2'])
-            self._logits_sample_book(sub, x, samp, uniforms, eos)
-            return
-        if self._chain_ok(sub):
-            # persistent chain kernels: everything between two attention kernels is ONE launch (csrc/decode_chain.cu)
-            ns = sub['ns']
-            g, b, eps = layers[0]['norm1']
-            ops.decode_chain([ops.chain_ln(x, g[0], b[0], sub['h'], eps=eps),
-                              ops.chain_gemm(sub['h'], layers[0]['wqkv'], sub['p_qkv'], B * 3 * d)], B, sub['gbar'])
-            for li, L in enumerate(layers):
-                ops.attn_decode_paged(sub['p_qkv'], ns['qkv'], B * 3 * d, st['pools'][li], sub['block_table'],
-                                      sub['seq_lens'], sub['o'], B, H, Dh, sub['n_tsplit'], sub['attn_ws'],
+                                      B, H, Dh, sub['n_tsplit'], sub['attn_ws'],
                                       ops.FLAG_PREFETCH_KV | self.attn_flags | self.attn_late_splitk)
-                g2, b2, eps2 = L['norm2']
-                ph = [ops.chain_gemm(sub['o'], L['wo'], sub['p_o'], B * d),
-                      ops.chain_ln(x, g2[0], b2[0], sub['h'], part=sub['p_o'], n_part=ns['o'], part_stride=B * d,
-                                   bias=L['bo'], eps=eps2),
-                      ops.chain_gemm(sub['h'], L['w1'], sub['p_f1'], B * F),
-                      ops.chain_act(sub['p_f1'], ns['f1'], B * F, L['b1'], sub['f']),
-                      ops.chain_gemm(sub['f'], L['w2'], sub['p_f2'], B * d)]
-                if li + 1 < len(layers):
-                    nxt = layers[li + 1]
-                    g1, b1, eps1 = nxt['norm1']
-                    ph += [ops.chain_ln(x, g1[0], b1[0], sub['h'], part=sub['p_f2'], n_part=ns['f2'], part_stride=B * d,
-                                        bias=L['b2'], eps=eps1),
-                           ops.chain_gemm(sub['h'], nxt['wqkv'], sub['p_qkv'], B * 3 * d)]
-                else:       # no final norm (K-2): cast the hidden rows and run the logits projection
-                    ph += [ops.chain_ln(x, None, None, sub['h'], part=sub['p_f2'], n_part=ns['f2'], part_stride=B * d,
-                                        bias=L['b2']),
-                           ops.chain_gemm(sub['h'], self.wproj, sub['p_lg'], B * self.V)]
-                ops.decode_chain(ph, B, sub['gbar'])
+                self._dg(sub, 'o', sub['o'], L['wo'], ops.DG_RESIDUAL, bias=L['bo'], xres=x, y16=xb, stats_out=stats)
+                self._dg(sub, 'f1', xb, L['w1_s'], ops.DG_LN_GELU, bias=L['b_1'], colsum=L['c_1'], stats_in=stats,
+                         n_chunks_in=ch_o, eps=eps2, y16=sub['f'])
+                self._dg(sub, 'f2', sub['f'], L['w2'], ops.DG_RESIDUAL, bias=L['b2'], xres=x, y16=xb, stats_out=stats)
+            self._dg(sub, 'lg', xb, self.wproj, ops.DG_PLAIN, y32=sub['lg'])            # no final norm (K-2)
             self._logits_sample_book(sub, x, samp, uniforms, eos, logits_done=True)
             return
+        ops.embed_sum_pe(sub['last'].view(B, 1, 1), self.aud_table, self.pe_a, x, pos_b=sub['audio_pos'])
         if self.precision == 'bf16':
             ns = sub['ns']
             for li, L in enumerate(layers):
@@ -508,7 +444,6 @@ class ARDecoder:
                 ops.attn_decode_paged(sub['p_qkv'], ns['qkv'], B * 3 * d, st['pools'][li], sub['block_table'],
                                       sub['seq_lens'], sub['o'], B, H, Dh, sub['n_tsplit'], sub['attn_ws'],
                                       ops.FLAG_PREFETCH_KV | self.attn_flags | self.attn_late_splitk)
-                self._prefetch_next_kv(sub, li)
                 ops.linear_decode(sub['o'], L['wo'], sub['p_o'], B * d, 32)
                 g, b, eps = L['norm2']
                 ops.residual_layernorm(x, g[0], b[0], sub['h'], part=sub['p_o'], n_part=ns['o'], part_stride=B * d,
@@ -518,7 +453,6 @@ class ARDecoder:
                 ops.linear_decode(sub['f'], L['w2'], sub['p_f2'], B * d, 32)
             ops.residual_layernorm(x, None, None, None, part=sub['p_f2'], n_part=ns['f2'], part_stride=B * d,
                                    bias=layers[-1]['b2'])
-            self._prefetch_join(sub)
         else:
             for li, L in enumerate(layers):
                 g, b, eps = L['norm1']
@@ -533,49 +467,29 @@ class ARDecoder:
                 ops.linear(sub['f'], L['w2'], L['b2'], residual=x, out=x)
         self._logits_sample_book(sub, x, samp, uniforms, eos)
 
-    def _prefetch_next_kv(self, sub: dict, li: int):
-        """After layer li's attention has been launched: on a side stream (ordered after that attention), ask for the
-        next layer's pages (layer 0 of the next step after the last layer).  Joined in _decode_step's caller."""
-        lo, hi = self.kv_prefetch
-        if hi <= lo or self.precision != 'bf16':
-            return
-        st = self._state
-        if self._pf_stream is None:
-            self._pf_stream = torch.cuda.Stream(device=self.device)
-        cur = torch.cuda.current_stream()
-        ev = torch.cuda.Event()
-        ev.record(cur)
-        self._pf_stream.wait_event(ev)
-        nxt = (li + 1) % len(self.weights.layers)
-        with torch.cuda.stream(self._pf_stream):
-            ops.kv_prefetch_l2(st['pools'][nxt], sub['block_table'], sub['seq_lens'], sub['B'], self.H, self.Dh, lo, hi)
-        sub['_pf_used'] = True
-
-    def _prefetch_join(self, sub: dict):
-        if sub.pop('_pf_used', False):
-            ev = torch.cuda.Event()
-            ev.record(self._pf_stream)
-            torch.cuda.current_stream().wait_event(ev)
+    def step_logits(self) -> torch.Tensor:
+        """(B, V) fp32 logits of the most recent first_token / decode_step, for parity tests: where the logits GEMM leaves
+        split-K slices they are summed in index order, exactly as the sampling kernel does."""
+        rows = []
+        for sub in self._state['subs']:
+            if 'ns' not in sub or self._lean_ok(sub):
+                rows.append(sub['lg'].clone())
+            else:
+                acc = sub['p_lg'][0].clone()
+                for s in range(1, sub['ns']['lg']):
+                    acc += sub['p_lg'][s]
+                rows.append(acc)
+        return torch.cat(rows, 0)
 
     def launches_per_step(self) -> int:
         """Kernel launches of one decode step (all sub-batches) -- the bench's gpu_launches claim."""
         L = len(self.weights.layers)
-        subs = self._state['subs']
         total = 0
-        for sub in subs:
-            if self._lean_ok(sub):
-                total += 1 + 5 * L + 1 + 2          # embed, 5 per layer, logits, sample + bookkeeping
-            elif self._rows_ok(sub):
-                # embed, 7 per layer (+1 GELU-reduce when FFN1 leaves slices), final reduce + cast, logits, sample + bookkeeping
-                total += 1 + (7 + (self._mix(sub)['f1'] == 's')) * L + 1 + 1 + 2
-            elif self._fused_ok(sub):
-                total += 1 + 5 * L + 1 + 2          # embed, 5 per layer, logits, sample + bookkeeping
-            elif self._chain_ok(sub):
-                total += 1 + 1 + 2 * L + 2          # embed, first chain, (attention + chain) per layer, sample, bookkeeping
+        for sub in self._state['subs']:
+            if self._lean_ok(sub) or self._tc_ok(sub):
+                total += 5 * L + 1 + 1              # 5 per layer, logits, sample + bookkeeping + next input row
             elif self.precision == 'bf16':
                 total += 1 + 8 * L + 1 + 2 + 2      # embed, 8 per layer, x-update, cast + logits, sample + bookkeeping
-                if self.kv_prefetch[1] > self.kv_prefetch[0]:
-                    total += L                      # one L2 prefetch launch per layer (side stream)
             else:
                 total += 1 + 7 * L + 1 + 2
         return total
@@ -622,7 +536,7 @@ class ARDecoder:
         step = 1
         if use_graph and uniforms is None and max_new > 2:
             # the captured step bakes in the state's buffers and the sampling scalars: reuse it while they are the same
-            gkey = (st['key'], temperature, top_k, top_p, seed, eos)
+            gkey = (st['key'], temperature, top_k, top_p, seed if self.decode_gemm == 'splitk' or self.precision != 'bf16' else None, eos)
             if self._graph is not None and self._graph_key == gkey:
                 graph = self._graph
             else:

@@ -11,7 +11,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import (FLAG_ATTN_SIMT, FLAG_LATE_TRIGGER, FLAG_PREFETCH_KV, EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RESIDUAL, EPI_NONE, MASK_EXPLICIT, MASK_NONE,
+from ._lib import (FLAG_ATTN_SIMT, FLAG_ATTN_TICKET, FLAG_DG_GLOBAL, FLAG_LATE_TRIGGER, FLAG_PREFETCH_KV, EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RESIDUAL, EPI_NONE, MASK_EXPLICIT, MASK_NONE,
                    MASK_PREFIX_LM, VB_BF16, VB_F32, check)
 
 __all__ = ['EPI_NONE', 'EPI_BIAS', 'EPI_BIAS_GELU', 'EPI_BIAS_RESIDUAL', 'MASK_NONE', 'MASK_PREFIX_LM',
@@ -202,33 +202,56 @@ def linear_decode_rows_ln(x: torch.Tensor, w: torch.Tensor, y: torch.Tensor, *, 
     return y
 
 
-def linear_decode_fused(a: torch.Tensor, w: torch.Tensor, y: torch.Tensor, *, bias: torch.Tensor | None = None,
-                        gelu: bool = False, residual: bool = False, gamma: torch.Tensor | None = None,
-                        beta: torch.Tensor | None = None, eps: float = 1e-5, cluster_k: int = 0,
-                        flags: int = 0) -> torch.Tensor:
-    """y (B<=64, N) = epilogue(A @ w.T), split-K reduced inside a thread-block cluster (csrc/gemm_decode_fused.cu).
-    a bf16 (B,K): A = a;  a fp32 (B,K): A = LayerNorm(a; gamma, beta) computed on load (plain cast when gamma is None).
-    residual=True: y (fp32) += A @ w.T + bias in place."""
-    assert a.dim() == 2 and w.dim() == 2 and a.shape[1] == w.shape[1] and w.dtype == torch.bfloat16
-    assert a.stride(1) == 1 and w.stride(1) == 1 and y.stride(1) == 1 and y.shape == (a.shape[0], w.shape[0])
-    B, K = a.shape
+DG_PLAIN, DG_LN, DG_LN_GELU, DG_RESIDUAL = 0, 1, 2, 3
+
+
+def decode_gemm_plan(M: int, N: int, K: int) -> dict:
+    """Grid of vb_decode_gemm for this shape: {'tiles', 'n_split', 'ws_bytes'}; RESIDUAL launches write `tiles` statistics
+    chunks per row."""
+    t, ns, ws = C.c_int(), C.c_int(), C.c_int64()
+    check(_L().vb_decode_gemm_plan(M, N, K, C.byref(t), C.byref(ns), C.byref(ws)), 'vb_decode_gemm_plan')
+    return {'tiles': t.value, 'n_split': ns.value, 'ws_bytes': ws.value}
+
+
+def decode_gemm(x: torch.Tensor, w: torch.Tensor, mode: int, *, ws: torch.Tensor, counters: torch.Tensor,
+                bias: torch.Tensor | None = None, colsum: torch.Tensor | None = None, stats_in: torch.Tensor | None = None,
+                n_chunks_in: int = 0, eps: float = 1e-5, y32: torch.Tensor | None = None, y16: torch.Tensor | None = None,
+                xres: torch.Tensor | None = None, stats_out: torch.Tensor | None = None, flags: int = 0) -> None:
+    """Decode-shape linear layer finished inside one launch (include/valle_b200.h, vb_decode_gemm): x (M<=256, K) bf16,
+    w (N, K) bf16; mode DG_PLAIN / DG_LN / DG_LN_GELU / DG_RESIDUAL."""
+    assert x.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and x.stride(1) == 1 and w.stride(1) == 1
+    M, K = x.shape
     N = w.shape[0]
-    if residual:
-        assert bias is not None and not gelu and y.dtype == torch.float32
-        epi = EPI_BIAS_RESIDUAL
-    elif gelu:
-        assert bias is not None
-        epi = EPI_BIAS_GELU
-    else:
-        epi = EPI_BIAS if bias is not None else EPI_NONE
-    check(_L().vb_linear_decode_fused(_ptr(a), _code(a.dtype), a.stride(0), _ptr(gamma), _ptr(beta), float(eps), _ptr(w),
-                                      w.stride(0), _ptr(bias), _ptr(y), _code(y.dtype), y.stride(0), B, N, K, epi,
-                                      cluster_k, flags, _stream()), 'vb_linear_decode_fused')
-    return y
+    assert w.shape[1] == K and ws.dtype == torch.float32 and counters.dtype == torch.int32
+    assert ws.numel() * 4 >= decode_gemm_plan(M, N, K)['ws_bytes'], 'exchange workspace too small'
+    for t in (bias, colsum, stats_in, stats_out, y32, xres):
+        assert t is None or (t.dtype == torch.float32 and t.is_cuda)
+    assert y16 is None or y16.dtype == torch.bfloat16
+    for t in (y32, y16, xres):
+        assert t is None or (t.shape == (M, N) and t.stride(1) == 1)
+    check(_L().vb_decode_gemm(_ptr(x), x.stride(0), _ptr(w), w.stride(0), M, N, K, mode, _ptr(bias), _ptr(colsum),
+                              _ptr(stats_in), n_chunks_in, float(eps), _ptr(y32), y32.stride(0) if y32 is not None else 0,
+                              _ptr(y16), y16.stride(0) if y16 is not None else 0, _ptr(xres),
+                              xres.stride(0) if xres is not None else 0, _ptr(stats_out), _ptr(ws), _ptr(counters), flags,
+                              _stream()), 'vb_decode_gemm')
 
 
-def linear_decode_fused_cluster(N: int, K: int) -> int:
-    return int(_L().vb_linear_decode_fused_cluster(N, K))
+def ar_step_tail(logits: torch.Tensor, V: int, *, temperature: float, top_k: int, top_p: float,
+                 uniforms: torch.Tensor | None, seed: torch.Tensor, row_offset: int, last: torch.Tensor,
+                 sum_logprobs: torch.Tensor, codes_out: torch.Tensor, seq_lens: torch.Tensor, audio_pos: torch.Tensor,
+                 state: torch.Tensor, eos: int, table: torch.Tensor, pe: torch.Tensor, x: torch.Tensor, xb: torch.Tensor,
+                 stats: torch.Tensor) -> None:
+    """sample + bookkeeping + next step's input row in one launch (include/valle_b200.h, vb_ar_step_tail).
+    logits fp32 (B, >=V); seed: int64 tensor [1] on the device; state int32 [4]; table fp32 (rows, d); pe fp32 (max_len, d)."""
+    B, d = x.shape
+    assert logits.dtype == torch.float32 and logits.stride(1) == 1 and seed.dtype == torch.int64 and state.numel() >= 4
+    assert state.dtype == torch.int32 and table.dtype == torch.float32 and pe.dtype == torch.float32 and table.shape[1] == d
+    assert x.dtype == torch.float32 and xb.dtype == torch.bfloat16 and x.is_contiguous() and xb.is_contiguous()
+    assert stats.dtype == torch.float32 and stats.numel() >= 2 * B and table.is_contiguous() and pe.is_contiguous()
+    check(_L().vb_ar_step_tail(_ptr(logits), logits.stride(0), V, float(temperature), int(top_k), float(top_p), _ptr(uniforms),
+                               _ptr(seed), int(row_offset), _ptr(last), _ptr(sum_logprobs), _ptr(codes_out), codes_out.stride(0),
+                               _ptr(seq_lens), _ptr(audio_pos), _ptr(state), B, eos, _ptr(table), _ptr(pe), d, _ptr(x), _ptr(xb),
+                               _ptr(stats), _stream()), 'vb_ar_step_tail')
 
 
 def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tensor, *, mask_mode: int = MASK_NONE,
@@ -323,37 +346,6 @@ def ar_bookkeeping(sample_tok: torch.Tensor, logprob: torch.Tensor, last: torch.
     check(_L().vb_ar_bookkeeping(_ptr(sample_tok), _ptr(logprob), _ptr(last), _ptr(sum_logprobs), _ptr(codes_out),
                                  codes_out.stride(0), _ptr(seq_lens), _ptr(audio_pos), _ptr(state), B, eos,
                                  _stream()), 'vb_ar_bookkeeping')
-
-
-# ---- persistent decode chain (csrc/decode_chain.cu) -------------------------------------------------------------------
-def chain_gemm(x: torch.Tensor, w: torch.Tensor, part: torch.Tensor, part_stride: int, max_split: int = 32):
-    assert x.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and x.is_contiguous() and w.is_contiguous()
-    ph = _lib.ChainPhase()
-    ph.type, ph.N, ph.K, ph.max_split = _lib.PHASE_GEMM, w.shape[0], w.shape[1], max_split
-    ph.x, ph.w, ph.out_part, ph.out_part_stride = _ptr(x), _ptr(w), _ptr(part), part_stride
-    return ph
-
-
-def chain_ln(x32: torch.Tensor, gamma, beta, y, *, part=None, n_part: int = 0, part_stride: int = 0, bias=None,
-             eps: float = 1e-5):
-    assert x32.dtype == torch.float32 and (y is None or y.dtype == torch.bfloat16)
-    ph = _lib.ChainPhase()
-    ph.type, ph.d, ph.n_part, ph.in_part_stride, ph.eps = _lib.PHASE_LN, x32.shape[1], n_part, part_stride, eps
-    ph.x32, ph.in_part, ph.bias, ph.gamma, ph.beta, ph.y = _ptr(x32), _ptr(part), _ptr(bias), _ptr(gamma), _ptr(beta), _ptr(y)
-    return ph
-
-
-def chain_act(part: torch.Tensor, n_part: int, part_stride: int, bias, y: torch.Tensor):
-    assert y.dtype == torch.bfloat16
-    ph = _lib.ChainPhase()
-    ph.type, ph.N, ph.n_part, ph.in_part_stride = _lib.PHASE_ACT, y.shape[1], n_part, part_stride
-    ph.in_part, ph.bias, ph.y = _ptr(part), _ptr(bias), _ptr(y)
-    return ph
-
-
-def decode_chain(phases: list, B: int, counter: torch.Tensor) -> None:
-    arr = (_lib.ChainPhase * len(phases))(*phases)
-    check(_L().vb_decode_chain(C.cast(arr, C.c_void_p), len(phases), B, _ptr(counter), _stream()), 'vb_decode_chain')
 
 
 # ---- training step, backward pass (csrc/train.cu) -----------------------------------------------------------------------
