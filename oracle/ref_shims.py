@@ -6,9 +6,10 @@ that transformers 5.x no longer ships (``transformers.generation.utils.top_k_top
 pinned at 4.38.2 by the reference's poetry.lock:3600).  This module registers minimal stand-ins in
 ``sys.modules`` *before* ``valle`` is imported, then imports the unmodified reference modules.
 
-Only usable where ``/root/reference`` exists (the authoring container).  It is used by
-``oracle/make_golden.py`` to generate ``tests/golden/*.npz`` and by the optional test
-``tests/test_oracle_vs_reference.py``; nothing that runs on the GPU box imports it.
+The reference is executed from ``/root/reference`` where that exists (the authoring container) and otherwise from
+``oracle/_ref`` (the unmodified package installed by ``oracle/build_ref.py``; git-ignored, shipped to the GPU box with the
+repo snapshot).  Users: ``oracle/make_golden.py`` (golden vectors), ``bench.py --impl reference`` and its ``cpu_baseline``
+leg (the executed reference timed on the host cores).  The product path never imports this module.
 """
 from __future__ import annotations
 
@@ -18,7 +19,9 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get('VALLE_REFERENCE_ROOT', '/root/reference')
+_INSTALLED = os.path.join(os.path.dirname(os.path.abspath(__file__)), '_ref')     # oracle/build_ref.py (travels to the GPU box)
+REFERENCE_ROOT = os.environ.get('VALLE_REFERENCE_ROOT') or (
+    '/root/reference' if os.path.isdir('/root/reference/valle/models') else _INSTALLED)
 
 
 def reference_available() -> bool:

@@ -21,7 +21,7 @@ from valle2_b200 import _lib, ops  # noqa: E402
 
 EVENTS = [(0, 'prologue done'), (1, 'weights requested'), (2, 'dependency resolved'), (3, 'first k-block landed'),
           (4, 'MMAs issued'), (5, 'accumulator complete'), (8, 'partial stored'), (9, 'arrived'), (6, 'all splits arrived'),
-          (7, 'outputs stored')]
+          (10, 'first item reduced'), (11, 'its operands ready'), (7, 'outputs stored')]
 
 
 def main():

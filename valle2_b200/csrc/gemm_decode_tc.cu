@@ -340,6 +340,7 @@ __global__ void __launch_bounds__(THREADS, 1) decode_gemm_kernel(const __grid_co
                     a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
                 }
             }
+            if (et == 0 && slot == 0) DG_STAMP(10);
             const bool full4 = live && (n + 3 < p.N);
             float av[4] = {a.x, a.y, a.z, a.w};
             float bv[4] = {0.f, 0.f, 0.f, 0.f}, cv[4] = {0.f, 0.f, 0.f, 0.f}, xo[4] = {0.f, 0.f, 0.f, 0.f};
@@ -368,6 +369,7 @@ __global__ void __launch_bounds__(THREADS, 1) decode_gemm_kernel(const __grid_co
                     }
                 }
             }
+            if (et == 0 && slot == 0) DG_STAMP(11);
             if (IS_RES) {
                 float sum = 0.f, sq = 0.f;
                 if (live) {

@@ -164,6 +164,9 @@ class ARDecoder:
         self.attn_late = ops.FLAG_LATE_TRIGGER if os.environ.get('VALLE_B200_ATTN_LATE', '1') != '0' else 0
         self.attn_late_splitk = ops.FLAG_LATE_TRIGGER if os.environ.get('VALLE_B200_ATTN_LATE_SPLITK', '0') != '0' else 0   # A/B
         self.qkv_late_all = os.environ.get('VALLE_B200_QKV_LATE_ALL', '0') != '0'      # A/B: late PDL trigger in every layer
+        # tc path, bit mask over (out-proj, FFN1, FFN2): release the successor only after the own dependency wait, so that at
+        # most two kernels of the chain are resident at a time (their CTAs then all find a slot before their predecessor ends)
+        self.dg_late = int(os.environ.get('VALLE_B200_DG_LATE', '0'))
         self.n_sub_override = int(os.environ.get('VALLE_B200_SUBBATCH', '0'))
         self.attn_ctas = int(os.environ.get('VALLE_B200_ATTN_CTAS', '0'))
         self.n_tsplit_override = 0             # tests: pin the flash-decoding split
@@ -199,13 +202,21 @@ class ARDecoder:
         residual matrix, which is what limits it to <= 8 sequences."""
         if self.decode_gemm not in ('auto', 'lean') or self.precision != 'bf16':
             return False
-        return (sub['B'] <= 8 and self.d in (256, 512, 1024) and self.weights.F % 256 == 0
+        if sub['B'] > (8 if self.decode_gemm == 'lean' else 7):
+            return False
+        return (self.d in (256, 512, 1024) and self.weights.F % 256 == 0
                 and ops.linear_decode_rows_splits(self.weights.F, 0, sub['B']) == 1)
 
     def _tc_ok(self, sub: dict) -> bool:
-        """Five launches per layer on the tcgen05 decode GEMM with in-kernel split-K reduction (csrc/gemm_decode_tc.cu)."""
-        return (self.precision == 'bf16' and self.decode_gemm in ('auto', 'tc') and not self._lean_ok(sub)
-                and sub['B'] <= 256 and self.d % 8 == 0 and self.weights.F % 8 == 0 and 'dg' in sub)
+        """Five launches per layer on the tcgen05 decode GEMM with in-kernel split-K reduction (csrc/gemm_decode_tc.cu).
+        'auto' takes it for 8..32 sequences (measured, tools/ab_r02_batches.sh: B=8 0.305 vs 0.316 ms lean, B=16 0.355 vs
+        0.384 ms split-K, B=32 0.46 vs 0.505; above 32 rows the exchange + epilogue inside the launch grow with the batch
+        and the separate reduce kernels win: B=64 0.85 vs 0.75 ms, B=256 2.63 vs 2.16)."""
+        if self.precision != 'bf16' or 'dg' not in sub or self._lean_ok(sub):
+            return False
+        if self.decode_gemm == 'tc':
+            return sub['B'] <= 256
+        return self.decode_gemm == 'auto' and sub['B'] <= 32
 
     def _make_sub(self, st: dict, b0: int, b1: int, state: torch.Tensor) -> dict:
         """Workspaces of one sub-batch (rows b0..b1 of the batch) + row-slice views of the shared decode state."""
@@ -224,7 +235,7 @@ class ARDecoder:
             sub['f'] = torch.zeros(B, F, device=dev, dtype=self.cd)
             sub['xb'] = torch.zeros(B, d, device=dev, dtype=self.cd)          # bf16 copy of the residual rows (tc path)
             sub['qkv32'] = torch.zeros(B, 3 * d, device=dev, dtype=torch.float32)
-            if self.decode_gemm == 'splitk':
+            if self.decode_gemm == 'splitk' or (self.decode_gemm == 'auto' and B > 32) or B > 256:
                 ms = 32
                 ns = {k: ops.linear_decode_splits(n, kk, ms) for k, (n, kk) in
                       {'qkv': (3 * d, d), 'o': (d, d), 'f1': (F, d), 'f2': (d, F), 'lg': (V, d)}.items()}
@@ -234,7 +245,7 @@ class ARDecoder:
                 sub['p_f1'] = torch.zeros(ns['f1'], B, F, device=dev, dtype=torch.float32)
                 sub['p_f2'] = torch.zeros(ns['f2'], B, d, device=dev, dtype=torch.float32)
                 sub['p_lg'] = torch.zeros(ns['lg'], B, V, device=dev, dtype=torch.float32)
-            elif B <= 256:
+            else:
                 # tc path: plan of every GEMM shape (tiles, n_split), the shared exchange buffer, one counter array per shape
                 dg = {k: ops.decode_gemm_plan(B, n, kk) for k, (n, kk) in
                       {'qkv': (3 * d, d), 'o': (d, d), 'f1': (F, d), 'f2': (d, F), 'lg': (V, d)}.items()}
@@ -423,10 +434,12 @@ class ARDecoder:
                 ops.attn_decode_paged(sub['qkv32'], 1, 0, st['pools'][li], sub['block_table'], sub['seq_lens'], sub['o'],
                                       B, H, Dh, sub['n_tsplit'], sub['attn_ws'],
                                       ops.FLAG_PREFETCH_KV | self.attn_flags | self.attn_late_splitk)
-                self._dg(sub, 'o', sub['o'], L['wo'], ops.DG_RESIDUAL, bias=L['bo'], xres=x, y16=xb, stats_out=stats)
+                self._dg(sub, 'o', sub['o'], L['wo'], ops.DG_RESIDUAL, bias=L['bo'], xres=x, y16=xb, stats_out=stats,
+                         flags=ops.FLAG_LATE_TRIGGER if self.dg_late & 1 else 0)
                 self._dg(sub, 'f1', xb, L['w1_s'], ops.DG_LN_GELU, bias=L['b_1'], colsum=L['c_1'], stats_in=stats,
-                         n_chunks_in=ch_o, eps=eps2, y16=sub['f'])
-                self._dg(sub, 'f2', sub['f'], L['w2'], ops.DG_RESIDUAL, bias=L['b2'], xres=x, y16=xb, stats_out=stats)
+                         n_chunks_in=ch_o, eps=eps2, y16=sub['f'], flags=ops.FLAG_LATE_TRIGGER if self.dg_late & 2 else 0)
+                self._dg(sub, 'f2', sub['f'], L['w2'], ops.DG_RESIDUAL, bias=L['b2'], xres=x, y16=xb, stats_out=stats,
+                         flags=ops.FLAG_LATE_TRIGGER if self.dg_late & 4 else 0)
             self._dg(sub, 'lg', xb, self.wproj, ops.DG_PLAIN, y32=sub['lg'])            # no final norm (K-2)
             self._logits_sample_book(sub, x, samp, uniforms, eos, logits_done=True)
             return
@@ -536,7 +549,9 @@ class ARDecoder:
         step = 1
         if use_graph and uniforms is None and max_new > 2:
             # the captured step bakes in the state's buffers and the sampling scalars: reuse it while they are the same
-            gkey = (st['key'], temperature, top_k, top_p, seed if self.decode_gemm == 'splitk' or self.precision != 'bf16' else None, eos)
+            # (the seed too where the separate sampling kernel takes it as a launch argument; vb_ar_step_tail reads it from memory)
+            baked_seed = any(not (self._lean_ok(s_) or self._tc_ok(s_)) for s_ in st['subs'])
+            gkey = (st['key'], temperature, top_k, top_p, seed if baked_seed else None, eos)
             if self._graph is not None and self._graph_key == gkey:
                 graph = self._graph
             else:
