@@ -1,17 +1,25 @@
 #!/usr/bin/env python
-"""Benchmark of the Valle2 hot path on B200 (contract: see the task statement / DESIGN.md section "Measurement").
+"""Benchmark of the Valle2 hot path on B200 (contract: task statement / DESIGN.md section "Measurement").
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B] [--no-extras]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--utterances G] [--no-extras]
 
-Workload (BASELINE.json configs[1]): default VALL-E AR decoder (12 layers, d=1024, 16 heads, F=4096), KV-cached greedy
-decode, batch 32 per GPU, text 150 phonemes, 3 s prompt (225 frames + BOS), 750 generated frames; bf16 weights / KV
-with fp32 accumulation.  One "step" = one decode step of the whole batch (B new codec tokens).  When K < 750 the
-prompt is lengthened so that the mean context over the K timed steps equals the config's mean (750.5 positions).
+Workload = BASELINE.json configs[3], the one configuration that is defined at 1, 2, 4 and 8 GPUs: full TTS inference for
+G = 256 utterances (text 150 phonemes = 50 prompt + 100 target, 3 s prompt = 225 frames x 8 codebooks, 750 generated frames =
+10 s): AR prefill + KV-cached greedy decode of the first codebook + NAR stages 2..8, bf16 weights / KV with fp32
+accumulation.  The utterances are SHARDED over the N ranks (strong scaling: G is fixed), every rank decodes its shard
+independently and the codes are all-gathered with NCCL at the end -- inside the timed region.  One "step" = one whole job
+through `valle2_b200.parallel.generate_sharded` + `valle2_b200.tts.synthesize_batch`.
 
-Prints ONE JSON line on rank 0.  `value` = tokens/s with everything resident in HBM (CUDA-graph replay of the step);
-`e2e` = the same metric through ValleAR.generate_batch from pinned HOST tensors (H2D of the prompt, prefill, K+W
-decode steps, D2H of the codes all inside the timed region).  `roofline` is measured live with CUDA events on the
-dominant kernel (paged decode attention).  `cpu_baseline` times the oracle port on the host cores (bounded sample).
+Prints ONE JSON line on rank 0:
+  value     codec frames/s (1 frame = 1 AR token + 7 NAR tokens) with the inputs resident in HBM, CUDA events between
+            barriers, max over ranks;  utterances/s = value / 750
+  e2e       the same job from pinned HOST tensors: H2D of the shard, job, gather, D2H of the gathered codes
+  roofline  the dominant kernel (paged decode attention) at this run's per-GPU batch, timed live with CUDA events
+  extras    ar_decode_weak: BASELINE configs[1] (AR decode, batch 32 PER GPU, 750 frames; tokens/s, weak scaling, with the
+            step's HBM roofline fraction); on one GPU also batch 1, NAR configs[2], the training steps of configs[4] and the
+            torch-eager reference on the same GPU
+  cpu_baseline  the EXECUTED reference (oracle/_ref, unmodified) on the host cores, bounded sample (N = 1 only)
+`--impl reference` times that executed reference alone (rank 0), same metric / unit / config.workload.
 """
 from __future__ import annotations
 
@@ -28,8 +36,17 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-TX, P0, N_NEW = 150, 226, 750           # phonemes, BOS + 225 prompt frames, generated frames
+TP, TT, TC, N_NEW = 50, 100, 225, 750   # prompt phonemes, target phonemes, prompt frames, generated frames
+TX, P0 = TP + TT, TC + 1                # text length, BOS + prompt
 MEAN_CTX = TX + P0 + (N_NEW - 1) / 2.0  # 750.5
+Q = 8
+
+
+def workload_string(G: int) -> str:
+    """Identical in both arms (the driver compares it)."""
+    return (f'full TTS inference (BASELINE configs[3]): {G} utterances, text {TX} phonemes ({TP} prompt + {TT} target), '
+            f'{TC}-frame prompt x {Q} codebooks, {N_NEW} generated frames: default VALL-E AR decoder (12L d1024 h16 F4096) prefill + '
+            f'KV-cached greedy decode + NAR stages 2-{Q}; utterances sharded over the GPUs, codes all-gathered at the end')
 
 
 def peaks() -> dict:
@@ -44,9 +61,9 @@ def peaks() -> dict:
 
 class ClockSampler:
     """nvidia-smi sampled DURING the timed region (B200_PROFILING.md recipe)."""
-    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
-         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
-         'clocks_event_reasons.sw_power_cap')
+    QUERY = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+             'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+             'clocks_event_reasons.sw_power_cap')
 
     def __init__(self, gpu_index: int):
         self.proc = None
@@ -54,7 +71,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.idx), f'--query-gpu={self.Q}',
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.idx), f'--query-gpu={self.QUERY}',
                                           '--format=csv,noheader,nounits', '-lms', '100'],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
@@ -100,8 +117,8 @@ def decode_form(eng, sub) -> str:
     if eng._lean_ok(sub):
         return 'lean: linear_decode_rows_kernel (mma.sync, full K per CTA, LayerNorm on load, fused epilogues), 5 launches per layer'
     if eng._tc_ok(sub):
-        return ('tc: decode_gemm_kernel (tcgen05 swap-AB, split-K reduced inside the launch, LayerNorm folded, fused epilogues), '
-                '5 launches per layer')
+        return ('tc: decode_gemm_kernel (tcgen05 swap-AB, split-K exchanged through DSMEM inside the launch, LayerNorm folded, fused '
+                'epilogues), 5 launches per layer')
     return 'splitk: gemm_tc_kernel<swap-AB split-K> slices + LayerNorm / GELU-reduce kernels, 8 launches per layer'
 
 
@@ -112,313 +129,316 @@ def ar_step_bytes(B: int, ctx: float, L=12, d=1024, F=4096, V=1025) -> float:
     return w + B * (ctx + 1) * kv_tok
 
 
+def timed_graph(fn, reps: int = 5) -> float:
+    """ms per fn(): captured once, replayed reps times between two events (no host launch overhead)."""
+    fn()
+    torch.cuda.synchronize()
+    gr = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(gr):
+        fn()
+    gr.replay()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        gr.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+# ------------------------------------------------------------------------------------------------------------
+@torch.inference_mode()
+def attention_roofline(eng, ops, ctx: int, pk: dict, step_ms: float | None) -> dict:
+    """The dominant kernel at the launch shape the engine really uses (first sub-batch): algorithmic bytes per launch over
+    the CUDA-event time of 12 launches on 12 distinct layer pools (> L2, no re-use between launches)."""
+    st = eng._state
+    sb = st['subs'][0]
+    Bs, H, Dh, d = sb['B'], eng.H, eng.Dh, eng.d
+    keep = st['seq_lens'].clone()
+    st['seq_lens'].fill_(ctx)
+    if eng._lean_ok(sb):
+        src, n_p, p_s = sb['r_qkv'], 1, 0
+    elif eng._tc_ok(sb):
+        src, n_p, p_s = sb['qkv32'], 1, 0
+    else:
+        src, n_p, p_s = sb['p_qkv'], sb['ns']['qkv'], Bs * 3 * d
+
+    def attn_all_layers():
+        for li in range(len(eng.weights.layers)):
+            ops.attn_decode_paged(src, n_p, p_s, st['pools'][li], sb['block_table'], sb['seq_lens'], sb['o'], Bs, H, Dh,
+                                  sb['n_tsplit'], sb['attn_ws'], eng.attn_flags)
+
+    L = len(eng.weights.layers)
+    att_ms = timed_graph(attn_all_layers) / L
+    st['seq_lens'].copy_(keep)
+    att_bytes = Bs * (ctx + 1) * 2 * d * 2               # K and V rows of every cached position, bf16
+    traffic = None
+    try:                                                 # DRAM bytes per launch from the committed ncu --set full capture
+        with open(os.path.join(ROOT, 'profiles', 'traffic.json')) as fh:
+            tr = json.load(fh)['attn_decode_mma_kernel<bf16>']
+        traffic = (tr['dram_bytes_read'] + tr['dram_bytes_write']) * att_bytes / tr['algorithmic_bytes']
+    except Exception:
+        pass
+    out = {'bound': 'hbm', 'kernel': 'attn_decode_mma_kernel<bf16>', 'achieved': att_bytes / (att_ms * 1e-3) / 1e9,
+           'peak': pk['hbm_gbs'], 'unit': 'GB/s', 'frac': att_bytes / (att_ms * 1e-3) / 1e9 / pk['hbm_gbs'], 'traffic': traffic,
+           'traffic_source': 'profiles/traffic.json (ncu --set full at B=32, ctx=750, scaled to this launch)',
+           'peak_source': pk['_source'] + ' (MEASURED_PEAKS.json hbm_gbs)', 'bytes_per_launch': att_bytes,
+           'us_per_launch': att_ms * 1e3, 'rows_per_launch': Bs, 'ctx': ctx, 'launches_per_step': L * len(st['subs'])}
+    if step_ms:
+        out['share_of_decode_step'] = att_ms * L * len(st['subs']) / step_ms
+    return out
+
+
+@torch.inference_mode()
+def ar_decode_steady(model, B: int, K: int, extra_prompt: int, dev, gen_seed: int, world: int = 1, warm: int = 8):
+    """BASELINE configs[1]: K CUDA-graph-replayed decode steps at batch B (device-resident), prompt lengthened by
+    extra_prompt so that the mean context over the K steps is the config's 750.5 when K < 750.  All ranks take part
+    (barrier + max over ranks).  Returns (tokens/s of B x world sequences, ms per step, mean ctx, engine)."""
+    eng = model._engine()
+    g = torch.Generator().manual_seed(gen_seed)
+    tokens = torch.randint(0, 256, (B, TX), generator=g).to(dev)
+    codes = torch.cat([torch.full((B, 1), 1025), torch.randint(0, 1024, (B, P0 + extra_prompt - 1), generator=g)], 1).to(dev)
+    samp = {'temperature': 1.0, 'top_k': 1, 'top_p': 1.0, 'seed': 0}
+    st = eng.prefill(tokens, codes, max_new=K + warm + 4)
+    eng.first_token(samp, None, -1)
+    eng.decode_step(samp, None, -1)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        eng.decode_step(samp, None, -1)
+    for _ in range(warm):
+        graph.replay()
+    ctx0 = int(st['seq_lens'][0].item())
+    if world > 1:
+        torch.distributed.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        graph.replay()
+    e1.record()
+    if world > 1:
+        torch.distributed.barrier()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        ms = float(t.item())
+    return B * world * K / (ms * 1e-3), ms / K, ctx0 + (K - 1) / 2.0, eng
+
+
 # ------------------------------------------------------------------------------------------------------------
 def run_ours(args, rank: int, world: int, local_rank: int):
     import valle2_b200
-    from valle2_b200 import ops
-    from valle2_b200.models import ValleAR
+    from valle2_b200 import _lib, ops, parallel
+    from valle2_b200.models import ValleAR, ValleNAR
+    from valle2_b200.tts import synthesize_batch
 
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
     valle2_b200.set_precision('bf16')
     tmp = f'/tmp/valle_bench_{os.getpid()}'
-    B, K, W = args.batch, args.steps, args.warmup
+    G, K, W = args.utterances, args.steps, args.warmup
+    pk = peaks()
     torch.manual_seed(0)
-    model = ValleAR(large_cfg('LayerNorm', tmp)).eval().to(dev)
-    eng = model._engine()
-    g = torch.Generator().manual_seed(100 + rank)
-    total_steps = K + W
-    # lengthen the prompt when fewer than 750 steps are timed so the mean context matches the config
-    extra = max(0, int(round(MEAN_CTX - (K - 1) / 2.0 - W)) - (TX + P0))
-    P = P0 + extra
-    tokens_h = torch.randint(0, 256, (B, TX), generator=g).pin_memory()
-    codes_h = torch.cat([torch.full((B, 1), 1025), torch.randint(0, 1024, (B, P - 1), generator=g)], 1).pin_memory()
-    samp = {'temperature': 1.0, 'top_k': 1, 'top_p': 1.0, 'seed': 0}
+    ar = ValleAR(large_cfg('LayerNorm', tmp)).eval().to(dev)
+    torch.manual_seed(1)
+    nar = ValleNAR(large_cfg('AdaptiveLayerNorm', tmp)).eval().to(dev)
+    g = torch.Generator().manual_seed(100)
+    host = {'pt': torch.randint(0, 256, (G, TP), generator=g).pin_memory(),
+            'tt': torch.randint(0, 256, (G, TT), generator=g).pin_memory(),
+            'pc': torch.randint(0, 1024, (G, TC, Q), generator=g).pin_memory()}
+    on_dev = {k: v.to(dev) for k, v in host.items()}
 
     def barrier():
         if world > 1:
             torch.distributed.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident measurement: prefill (untimed), W warm-up steps, K timed graph replays ----
-    st = eng.prefill(tokens_h.to(dev), codes_h.to(dev), max_new=total_steps + 2)
-    eng.first_token(samp, None, -1)
-    eng.decode_step(samp, None, -1)                        # eager warm-up launch (module load, func attributes)
-    torch.cuda.synchronize()
-    graph = torch.cuda.CUDAGraph()
-    with torch.cuda.graph(graph):
-        eng.decode_step(samp, None, -1)
-    for _ in range(max(W - 1, 0)):
-        graph.replay()
-    ctx0 = int(st['seq_lens'][0].item())
+    def decode_fn(src):
+        def fn(idx):
+            """This rank's shard -> (rows (n, 750 * 8) int32, lens): the public hand-off API, AR then NAR."""
+            sel = torch.as_tensor(idx, dtype=torch.long)
+            if src is on_dev:
+                sel = sel.to(dev)
+                pt, tt, pc = (src[k][sel] for k in ('pt', 'tt', 'pc'))
+            else:           # pinned host tensors: gather the shard on the host, one H2D copy per tensor
+                pt, tt, pc = (src[k][sel].pin_memory().to(dev, non_blocking=True) for k in ('pt', 'tt', 'pc'))
+            mats = synthesize_batch(ar, nar, pt, pc, tt, max_new=N_NEW, ignore_eos=True, nar_chunk=args.nar_chunk)
+            rows = torch.stack(mats).reshape(len(idx), -1).to(torch.int32)
+            return rows, torch.full((len(idx),), rows.shape[1], device=dev, dtype=torch.int32)
+        return fn
+
+    def job(src):
+        rows, lens = parallel.generate_sharded(decode_fn(src), G, pad_value=-1)
+        return rows
+
+    # ---- device-resident measurement: W warm-up jobs, K timed jobs, gather inside --------------------------------
+    for _ in range(W):
+        out = job(on_dev)
+    eng = ar._engine()
+    _lib.LAUNCHES = 0
+    replays0 = eng.replays
     sampler = ClockSampler(local_rank)
     barrier()
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(K):
-        graph.replay()
+        out = job(on_dev)
     e1.record()
     barrier()
     clocks = sampler.stop()
     ms = e0.elapsed_time(e1)
+    launches = _lib.LAUNCHES + (eng.replays - replays0) * eng.launches_per_step()
     if world > 1:
-        t = torch.tensor([ms], device=dev)
+        t = torch.tensor([ms, float(launches)], device=dev)
+        torch.distributed.all_reduce(t[:1], op=torch.distributed.ReduceOp.MAX)
+        torch.distributed.all_reduce(t[1:], op=torch.distributed.ReduceOp.SUM)
+        ms, launches = float(t[0].item()), int(t[1].item())
+    assert out.shape == (G, N_NEW * Q) and int(out.min()) >= 0
+    n_local = len(parallel.shard_indices(G, rank, world))
+    frames_s = G * N_NEW * K / (ms * 1e-3)
+    phases = dict(getattr(eng, 'last_phases', {}))
+
+    # ---- sharded == single: rank 0 decodes another rank's shard alone and compares with what the gather delivered ----
+    equal = None
+    if world > 1:
+        other = parallel.shard_indices(G, 1, world)
+        if rank == 0:
+            rows1, _ = decode_fn(on_dev)(other)
+            equal = bool(torch.equal(rows1, out[torch.as_tensor(other, device=dev)]))
+            assert equal, 'gathered codes of rank 1 differ from a single-GPU decode of the same utterances'
+        barrier()
+
+    # ---- end to end from pinned host tensors (H2D of the shard, job, gather, D2H of the gathered codes) ----------
+    ke = max(1, min(K, args.e2e_steps))
+    job(host)
+    barrier()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(ke):
+        out_h = job(host).to('cpu')
+    t1.record()
+    barrier()
+    e2e_ms = t0.elapsed_time(t1)
+    if world > 1:
+        t = torch.tensor([e2e_ms], device=dev)
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
-        ms = float(t.item())
-        # the only collective of the path: gather the generated codes once at the end (NCCL over NVLink)
-        gathered = [torch.empty_like(st['codes_out']) for _ in range(world)]
-        torch.distributed.all_gather(gathered, st['codes_out'])
-    mean_ctx = ctx0 + (K - 1) / 2.0
-    tok_s = B * world * K / (ms * 1e-3)
-    step_bytes = ar_step_bytes(B, mean_ctx)
-    pk = peaks()
-    launches_per_step = eng.launches_per_step()
-    n_sub = len(st['subs'])
+        e2e_ms = float(t.item())
+    assert torch.equal(out_h, out.cpu()), 'host-fed job differs from the device-resident one'
 
+    st = eng._state
+    sb = st['subs'][0]
     result = {
-        'metric': 'ar_decode_tokens_per_s', 'value': tok_s, 'unit': 'tokens/s', 'n_gpus': world, 'steps': K, 'warmup': W,
-        'ms_per_step': ms / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16',
+        'metric': 'tts_codec_frames_per_s', 'value': frames_s, 'unit': 'frames/s', 'n_gpus': world, 'steps': K, 'warmup': W,
+        'ms_per_step': ms / K, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'bf16',
         'data': 'synthetic',
-        'config': {'workload': f'AR decode, default VALL-E AR decoder 12L d1024 h16 F4096, KV-cached greedy, batch {B}/GPU '
-                               f'(BASELINE configs[1]); text {TX}, prompt {P}, ctx {ctx0}->{ctx0 + K} (mean {mean_ctx:.1f})',
-                   'batch_per_gpu': B, 'global_batch': B * world, 'parallelism': f'dp{world} (utterance sharding, '
-                   'one all-gather of the codes at the end)', 'kv_page': 64,
-                   'sub_batches': n_sub, 'decode_gemm': decode_form(eng, st['subs'][0]), 'launches_per_step': launches_per_step,
-                   'l2_policy': 'inputs larger than L2: every step streams 304 MB of weights + %.0f MB of KV' %
-                                ((step_bytes - ar_step_bytes(0, 0)) / 1e6),
-                   'step_hbm_bytes': step_bytes, 'step_hbm_frac_of_measured_peak':
-                       step_bytes / (ms / K * 1e-3) / (pk['hbm_gbs'] * 1e9)},
-        'clocks': clocks, 'gpu_launches': launches_per_step * K,
+        'config': {'workload': workload_string(G), 'utterances': G, 'utterances_per_gpu': n_local,
+                   'utterances_per_s': frames_s / N_NEW, 'audio_seconds_per_s': frames_s / 75.0,
+                   'parallelism': f'dp{world}: utterance sharding (round robin), one all-gather of the int32 codes + lengths at the end of '
+                                  'every job, inside the timed region', 'kv_page': 64,
+                   'decode_gemm': decode_form(eng, sb), 'launches_per_decode_step': eng.launches_per_step(),
+                   'nar_chunk': args.nar_chunk, 'sharded_equals_single_gpu': equal,
+                   'l2_policy': 'inputs larger than L2: every decode step streams 304 MB of weights + %.0f MB of KV per GPU' %
+                                ((ar_step_bytes(n_local, MEAN_CTX) - ar_step_bytes(0, 0)) / 1e6)},
+        'clocks': clocks, 'gpu_launches': launches,
+        'e2e': {'value': G * N_NEW * ke / (e2e_ms * 1e-3), 'unit': 'frames/s',
+                'h2d_bytes_per_step': sum(v.numel() for v in host.values()) * 8,
+                'd2h_bytes_per_step': out_h.numel() * 4, 'steps': ke, 'ms_per_step': e2e_ms / ke,
+                'includes': 'per job: H2D of every rank\'s shard from pinned host tensors, AR prefill, 750 decode steps, NAR stages, '
+                            'all-gather, D2H of the gathered codes (step graph and KV pools are reused between jobs)',
+                'phases_ms_rank0_last_job': phases},
     }
-
     if rank == 0:
-        # ---- roofline of the dominant kernel (paged decode attention), CUDA events on the launch stream ----
-        H, Dh, d = 16, 64, 1024
-        ctx_r = int(round(mean_ctx))
-        st['seq_lens'].fill_(ctx_r)
-        sb = st['subs'][0]                                   # the launch shape the step really uses (one sub-batch)
-        Bs = sb['B']
-        torch.cuda.synchronize()
-        reps = 5
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-        lean, tc = eng._lean_ok(sb), eng._tc_ok(sb)
-        if lean:
-            qkv_src, qkv_np, qkv_ps = sb['r_qkv'], 1, 0
-        elif tc:
-            qkv_src, qkv_np, qkv_ps = sb['qkv32'], 1, 0
-        else:
-            qkv_src, qkv_np, qkv_ps = sb['p_qkv'], sb['ns']['qkv'], Bs * 3 * d
+        result['roofline'] = attention_roofline(eng, ops, int(round(MEAN_CTX)), pk, None)
 
-        def attn_all_layers():
-            for li in range(12):                             # 12 layers x B x ctx KV = > L2, no re-use between launches
-                ops.attn_decode_paged(qkv_src, qkv_np, qkv_ps, st['pools'][li], sb['block_table'], sb['seq_lens'],
-                                      sb['o'], Bs, H, Dh, sb['n_tsplit'], sb['attn_ws'], eng.attn_flags)
-
-        def timed_graph(fn):
-            """Kernel time without host launch overhead: capture fn once, replay it reps times between two events."""
-            fn()
-            torch.cuda.synchronize()
-            gr = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(gr):
-                fn()
-            gr.replay()
-            torch.cuda.synchronize()
-            ev[0].record()
-            for _ in range(reps):
-                gr.replay()
-            ev[1].record()
-            torch.cuda.synchronize()
-            return ev[0].elapsed_time(ev[1]) / reps
-
-        att_ms = timed_graph(attn_all_layers) / 12
-        att_bytes = Bs * (ctx_r + 1) * 2 * d * 2           # K and V rows of every cached position, bf16
-        traffic = None
-        try:                                                 # DRAM bytes per launch from the committed ncu --set full capture
-            with open(os.path.join(ROOT, 'profiles', 'traffic.json')) as fh:
-                tr = json.load(fh)['attn_decode_kernel<bf16>' if eng.attn_flags else 'attn_decode_mma_kernel<bf16>']
-            # the capture is at B=32, ctx=750; scale linearly to this launch's algorithmic bytes
-            traffic = (tr['dram_bytes_read'] + tr['dram_bytes_write']) * att_bytes / tr['algorithmic_bytes']
-        except Exception:
-            pass
-        result['roofline'] = {'bound': 'hbm', 'kernel': 'attn_decode_kernel<bf16> (SIMT)' if eng.attn_flags else 'attn_decode_mma_kernel<bf16>', 'achieved': att_bytes / (att_ms * 1e-3) / 1e9,
-                              'peak': pk['hbm_gbs'], 'unit': 'GB/s', 'frac': att_bytes / (att_ms * 1e-3) / 1e9 / pk['hbm_gbs'],
-                              'traffic': traffic, 'traffic_source': 'profiles/traffic.json (ncu --set full, scaled to this launch)',
-                              'peak_source': pk['_source'] + ' (MEASURED_PEAKS.json hbm_gbs)',
-                              'bytes_per_launch': att_bytes, 'us_per_launch': att_ms * 1e3,
-                              'share_of_step': att_ms * 12 * n_sub / (ms / K), 'rows_per_launch': Bs,
-                              'launches_per_step': 12 * n_sub}
-        # weight-streaming GEMMs of one step (incl. their fused reductions / epilogues), same method
-        def gemms_all_layers():
-            for L in eng.weights.layers:
-                if lean:
-                    g1, b1, _ = L['norm1']
-                    g2, b2, _ = L['norm2']
-                    ops.linear_decode_rows_ln(sb['x'], L['wqkv'], sb['r_qkv'][0], gamma=g1[0], beta=b1[0])
-                    ops.linear_decode_rows(sb['o'], L['wo'], sb['x'], bias=L['bo'], residual=True)
-                    ops.linear_decode_rows_ln(sb['x'], L['w1'], sb['f'], gamma=g2[0], beta=b2[0], bias=L['b1'], gelu=True)
-                    ops.linear_decode_rows(sb['f'], L['w2'], sb['x'], bias=L['b2'], residual=True, want_split=0)
-                elif tc:
-                    dg = sb['dg']
-                    ch_o, ch_f2 = dg['o']['tiles'], dg['f2']['tiles']
-                    eng._dg(sb, 'qkv', sb['xb'], L['wqkv_s'], ops.DG_LN, bias=L['b_qkv'], colsum=L['c_qkv'], stats_in=sb['stats'],
-                            n_chunks_in=ch_f2, y32=sb['qkv32'])
-                    eng._dg(sb, 'o', sb['o'], L['wo'], ops.DG_RESIDUAL, bias=L['bo'], xres=sb['x'], y16=sb['xb'], stats_out=sb['stats'])
-                    eng._dg(sb, 'f1', sb['xb'], L['w1_s'], ops.DG_LN_GELU, bias=L['b_1'], colsum=L['c_1'], stats_in=sb['stats'],
-                            n_chunks_in=ch_o, y16=sb['f'])
-                    eng._dg(sb, 'f2', sb['f'], L['w2'], ops.DG_RESIDUAL, bias=L['b2'], xres=sb['x'], y16=sb['xb'], stats_out=sb['stats'])
-                else:
-                    ops.linear_decode(sb['h'], L['wqkv'], sb['p_qkv'], Bs * 3 * d, 32)
-                    ops.linear_decode(sb['o'], L['wo'], sb['p_o'], Bs * d, 32)
-                    ops.linear_decode(sb['h'], L['w1'], sb['p_f1'], Bs * 4096, 32)
-                    ops.linear_decode(sb['f'], L['w2'], sb['p_f2'], Bs * d, 32)
-
-        sb['x'].zero_()
-        gemm_ms = timed_graph(gemms_all_layers)
-        wbytes = 2 * 12 * (3 * d * d + d * d + 2 * d * 4096)
-        result['gemm_decode'] = {'ms_per_step': gemm_ms, 'achieved_gbs': wbytes / (gemm_ms * 1e-3) / 1e9,
-                                 'frac_of_hbm_peak': wbytes / (gemm_ms * 1e-3) / 1e9 / pk['hbm_gbs'], 'launches': 48,
-                                 'kernel': decode_form(eng, sb)}
-
-    # ---- end-to-end through the public API from pinned host tensors --------------------------------
-    # One untimed call first (allocates the KV pools and captures the step graph of this request shape -- the engine keeps
-    # both for later requests of the same shape), then three timed calls; the median is reported and all three are listed.
-    # Every timed call does the full job: H2D prompt, prefill, decode, D2H codes.
-    def e2e_once():
-        barrier()
-        t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
-        t0.record()
-        out, n = model.generate_batch(tokens_h.to(dev, non_blocking=True), codes_h.to(dev, non_blocking=True),
-                                      max_new=total_steps, ignore_eos=True)
-        out_h = out.to('cpu', non_blocking=False)
-        t1.record()
-        barrier()
-        t_ms = t0.elapsed_time(t1)
-        if world > 1:
-            t = torch.tensor([t_ms], device=dev)
-            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
-            t_ms = float(t.item())
-        return t_ms, out_h
-
-    e2e_once()
-    runs = [e2e_once() for _ in range(3)]
-    e2e_all = sorted(r[0] for r in runs)
-    e2e_ms, out_h = e2e_all[1], runs[0][1]
-    result['e2e'] = {'value': B * world * total_steps / (e2e_ms * 1e-3), 'unit': 'tokens/s',
-                     'h2d_bytes_per_step': (tokens_h.numel() + codes_h.numel()) * 8 / total_steps,
-                     'd2h_bytes_per_step': out_h.numel() * 4 / total_steps,
-                     'includes': f'H2D prompt, prefill of {TX + P} positions, {total_steps} decode steps (step graph and KV pools of this '
-                                 f'request shape are reused from the untimed first call), D2H codes',
-                     'ms_total': e2e_ms, 'ms_all_runs': e2e_all, 'runs': 'median of 3 after one untimed call'}
-
-    if rank == 0 and not args.no_extras:
-        result['extras'] = extras(args, dev, tmp)
-        result['cpu_baseline'] = cpu_baseline(model, B, budget_s=12.0)
+    # ---- BASELINE configs[1] on every rank: AR decode, batch 32 per GPU (weak scaling) --------------------------
+    if not args.no_extras:
+        extras = {}
+        Kw = 300
+        tok_s, step_ms, mctx, eng32 = ar_decode_steady(ar, 32, Kw, int(round(MEAN_CTX - (Kw - 1) / 2.0 - 8)) - (TX + P0), dev, 7, world)
+        if rank == 0:
+            bytes32 = ar_step_bytes(32, mctx)
+            roof32 = attention_roofline(eng32, ops, int(round(mctx)), pk, step_ms)
+            extras['ar_decode_weak'] = {
+                'workload': 'BASELINE configs[1]: AR decode, batch 32 per GPU, KV-cached greedy, CUDA-graph steps, device-resident',
+                'tokens_per_s': tok_s, 'ms_per_step': step_ms, 'mean_ctx': mctx, 'batch_per_gpu': 32, 'scaling': 'weak',
+                'step_hbm_bytes': bytes32, 'step_hbm_frac_of_measured_peak': bytes32 / (step_ms * 1e-3) / (pk['hbm_gbs'] * 1e9),
+                'launches_per_step': eng32.launches_per_step(), 'decode_gemm': decode_form(eng32, eng32._state['subs'][0]),
+                'roofline_attention': roof32}
+        if rank == 0 and world == 1:
+            extras.update(extras_single_gpu(args, dev, tmp, ar, nar, pk))
+            result['cpu_baseline'] = cpu_baseline(budget_s=args.cpu_budget)
+        if rank == 0:
+            result['extras'] = extras
     return result
 
 
-def extras(args, dev, tmp):
-    """Secondary numbers of BASELINE.json's metric: AR decode at batch 1, NAR frames/s (config 3, reduced batch if needed)."""
-    import valle2_b200
+def extras_single_gpu(args, dev, tmp, ar, nar, pk):
+    """One GPU only: AR decode at batch 1 (configs[1]), NAR configs[2], training steps of configs[4], torch-eager reference."""
     from valle2_b200.models import ValleAR, ValleNAR
     out = {}
-    pk = peaks()
-    torch.manual_seed(0)
-    model = ValleAR(large_cfg('LayerNorm', tmp)).eval().to(dev)
-    eng = model._engine()
-    g = torch.Generator().manual_seed(7)
-    samp = {'temperature': 1.0, 'top_k': 1, 'top_p': 1.0, 'seed': 0}
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    # batch 1 (BASELINE configs[1]) over the full 750 frames; batch 128 / 64 = one GPU's share of configs[3] (256 utterances
-    # over 2 / 4 GPUs), 150 steps around the same mean context
-    for Bx, K1, extra in ((1, N_NEW - 8, 0), (64, 150, 300), (128, 150, 300)):
-        tokens = torch.randint(0, 256, (Bx, TX), generator=g).to(dev)
-        codes = torch.cat([torch.full((Bx, 1), 1025), torch.randint(0, 1024, (Bx, P0 + extra - 1), generator=g)], 1).to(dev)
-        st = eng.prefill(tokens, codes, max_new=K1 + 10)
-        eng.first_token(samp, None, -1)
-        eng.decode_step(samp, None, -1)
-        torch.cuda.synchronize()
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
-            eng.decode_step(samp, None, -1)
-        for _ in range(4):
-            graph.replay()
-        torch.cuda.synchronize()
-        e0.record()
-        for _ in range(K1):
-            graph.replay()
-        e1.record()
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1)
-        mean_ctx = TX + P0 + extra + 6 + (K1 - 1) / 2
-        out[f'ar_decode_b{Bx}'] = {'tokens_per_s': Bx * K1 / (ms * 1e-3), 'us_per_step': ms * 1e3 / K1, 'mean_ctx': mean_ctx,
-                                   'launches_per_step': eng.launches_per_step(),
-                                   'hbm_frac_of_measured_peak': ar_step_bytes(Bx, mean_ctx) / (ms / K1 * 1e-3) / (pk['hbm_gbs'] * 1e9)}
-        del st, graph
-    del model, eng
-    torch.cuda.empty_cache()
-    # NAR config 3: 7 stages, S = 150 + 225 + 525 = 900, batch 64
+    g = torch.Generator().manual_seed(7)
+    K1 = N_NEW - 8
+    tok_s, step_ms, mctx, eng1 = ar_decode_steady(ar, 1, K1, 0, dev, 9)
+    b1 = ar_step_bytes(1, mctx)
+    out['ar_decode_b1'] = {'workload': 'BASELINE configs[1]: AR decode, batch 1', 'tokens_per_s': tok_s, 'us_per_step': step_ms * 1e3,
+                           'mean_ctx': mctx, 'launches_per_step': eng1.launches_per_step(),
+                           'step_hbm_frac_of_measured_peak': b1 / (step_ms * 1e-3) / (pk['hbm_gbs'] * 1e9),
+                           'roofline': {'bound': 'hbm', 'achieved': b1 / (step_ms * 1e-3) / 1e9, 'peak': pk['hbm_gbs'], 'unit': 'GB/s',
+                                        'frac': b1 / (step_ms * 1e-3) / (pk['hbm_gbs'] * 1e9), 'bytes_per_step': b1,
+                                        'note': 'whole step (all weights + KV once), not one kernel'}}
+    # NAR configs[2]: 7 stages, S = 150 + 225 + 525 = 900, batch 64
     try:
-        torch.manual_seed(1)
-        nar = ValleNAR(large_cfg('AdaptiveLayerNorm', tmp)).eval().to(dev)
-        Bn, Tc, Tt = args.nar_batch, 225, 525
-        pt = torch.randint(0, 256, (Bn, 50), generator=g).to(dev)
-        tt = torch.randint(0, 256, (Bn, 100), generator=g).to(dev)
-        pc = torch.randint(0, 1024, (Bn, Tc, 8), generator=g).to(dev)
-        fl = torch.randint(0, 1024, (Bn, Tt), generator=g).to(dev)
-        use_tc = bool(int(os.environ.get('VALLE_B200_TC_ATTN', '1')))
-        nar.generate_batch(pt[:2], pc[:2], tt[:2], fl[:2], use_tc_attention=use_tc)     # warm-up: kernels, func attributes
-        nar.generate_batch(pt, pc, tt, fl, use_tc_attention=use_tc)                     # warm-up: workspaces of this shape
+        Bn, Tt_ = args.nar_batch, 525
+        pt = torch.randint(0, 256, (Bn, TP), generator=g).to(dev)
+        tt = torch.randint(0, 256, (Bn, TT), generator=g).to(dev)
+        pc = torch.randint(0, 1024, (Bn, TC, Q), generator=g).to(dev)
+        fl = torch.randint(0, 1024, (Bn, Tt_), generator=g).to(dev)
+        nar.generate_batch(pt[:2], pc[:2], tt[:2], fl[:2])
+        nar.generate_batch(pt, pc, tt, fl)
         nar_ms = []
-        for _ in range(3):              # median of three full runs (the first call of a shape pays cudaMalloc for ~2 GB)
+        for _ in range(3):
             torch.cuda.synchronize()
             e0.record()
-            nar.generate_batch(pt, pc, tt, fl, use_tc_attention=use_tc)
+            nar.generate_batch(pt, pc, tt, fl)
             e1.record()
             torch.cuda.synchronize()
             nar_ms.append(e0.elapsed_time(e1))
         ms = sorted(nar_ms)[1]
         S, d, F, L = 900, 1024, 4096, 12
-        flops = 7 * Bn * (L * (S * 2 * (4 * d * d + 2 * d * F) + 4 * S * S * d) + 2 * Tt * d * 1024)
-        out['nar'] = {'batch': Bn, 'stage_frames_per_s': Bn * Tt * 7 / (ms * 1e-3), 'utterance_frames_per_s': Bn * Tt / (ms * 1e-3),
-                      'ms_total': ms, 'ms_all_runs': nar_ms, 'tflops': flops / (ms * 1e-3) / 1e12,
-                      'frac_of_bf16_sustained_peak': flops / (ms * 1e-3) / 1e12 / pk['bf16_tflops_sustained'],
-                      'attention': 'tcgen05' if use_tc else 'simt'}
+        flops = 7 * Bn * (L * (S * 2 * (4 * d * d + 2 * d * F) + 4 * S * S * d) + 2 * Tt_ * d * 1024)
+        out['nar'] = {'workload': 'BASELINE configs[2]', 'batch': Bn, 'stage_frames_per_s': Bn * Tt_ * 7 / (ms * 1e-3),
+                      'utterance_frames_per_s': Bn * Tt_ / (ms * 1e-3), 'ms_total': ms, 'ms_all_runs': nar_ms,
+                      'tflops': flops / (ms * 1e-3) / 1e12,
+                      'frac_of_bf16_sustained_peak': flops / (ms * 1e-3) / 1e12 / pk['bf16_tflops_sustained']}
     except Exception as e:  # report, do not hide
-        out['nar'] = {'error': repr(e)}
-    # Full TTS hand-off (BASELINE configs[3], one GPU's share of 256 utterances over 8 GPUs = 32): AR prefill + 750 decode
-    # steps + 7 NAR stages through valle2_b200.tts.synthesize_batch, from host tensors to host code matrices
+        out['nar'] = {'error': repr(e)[:300]}
+    # torch-eager reference on the same GPU (SURVEY 2.3: "the real bar on the box")
     try:
-        from valle2_b200.tts import synthesize_batch
-        torch.manual_seed(0)
-        ar_t = ValleAR(large_cfg('LayerNorm', tmp)).eval().to(dev)
-        Bt_ = 32
-        ptk = torch.randint(0, 256, (Bt_, 50), generator=g)
-        ttk = torch.randint(0, 256, (Bt_, 100), generator=g)
-        pcd = torch.randint(0, 1024, (Bt_, 225, 8), generator=g)
-        for it in range(3):             # first call allocates / captures for this shape, then two timed calls (the second is reported)
-            torch.cuda.synchronize()
-            e0.record()
-            res = synthesize_batch(ar_t, nar, ptk.to(dev), pcd.to(dev), ttk.to(dev), max_new=N_NEW, ignore_eos=True)
-            res_h = [r.cpu() for r in res]
-            e1.record()
-            torch.cuda.synchronize()
-            ms_t = e0.elapsed_time(e1)
-        out['tts'] = {'utterances': Bt_, 'frames_per_utterance': int(res_h[0].shape[0]), 'codebooks': int(res_h[0].shape[1]),
-                      'ms_total': ms_t, 'utterances_per_s': Bt_ / (ms_t * 1e-3),
-                      'audio_seconds_per_s': Bt_ * res_h[0].shape[0] / 75.0 / (ms_t * 1e-3),
-                      'note': 'AR (prefill 376 + 750 decode steps, greedy, EOS ignored) + NAR stages 2..8, batch 32 = one GPU of the '
-                              '8-GPU sharding of configs[3]; codes out on the host'}
-        del ar_t
-    except Exception as ex:  # noqa: BLE001
-        out['tts'] = {'error': repr(ex)[:300]}
-    # Training step (BASELINE config 5, per-GPU share): teacher-forced AR, 16 clips of 15 s (Ty = 1126, Tx = 225), bf16
-    # operands / fp32 accumulation, forward + backward on the CUDA stack (valle2_b200/train.py)
+        from oracle import ref_runner
+        if ref_runner.available():
+            torch.cuda.empty_cache()
+            prec = torch.get_float32_matmul_precision()
+            r = ref_runner.tts_rate('cuda', 32, 40, 4, warmup=4)
+            torch.set_float32_matmul_precision(prec)
+            out['gpu_eager_reference'] = {k: r[k] for k in ('frames_per_s', 'ar_tokens_per_s', 'nar_stage_frames_per_s', 'prefill_s',
+                                                            'step_s_mean', 'nar_stage_s', 'sample')}
+            out['gpu_eager_reference']['note'] = ('unmodified reference modules, torch eager on this GPU, fp32 parameters with the TF32 matmul '
+                                                  'mode the reference switches on (valle/utils.py:11)')
+        else:
+            out['gpu_eager_reference'] = {'unavailable': 'oracle/_ref not installed (python -m oracle.build_ref in the authoring container)'}
+    except Exception as e:  # noqa: BLE001
+        out['gpu_eager_reference'] = {'error': repr(e)[:300]}
+    # Training steps (BASELINE configs[4], per-GPU share): teacher-forced AR and NAR, 16 clips of 15 s, forward + backward
     try:
-        del nar
         torch.cuda.empty_cache()
         torch.manual_seed(2)
-        ar = ValleAR(large_cfg('LayerNorm', tmp)).train().to(dev)
+        ar_t = ValleAR(large_cfg('LayerNorm', tmp)).train().to(dev)
         Bt, Txt, Tyt = args.train_batch, 225, 1126
         batch = {'tokens': torch.randint(0, 256, (Bt, Txt), generator=g), 'tokens_lens': torch.full((Bt,), Txt),
                  'codes': torch.randint(0, 1024, (Bt, Tyt), generator=g), 'codes_lens': torch.full((Bt,), Tyt),
@@ -427,9 +447,9 @@ def extras(args, dev, tmp):
             if it == 3:
                 torch.cuda.synchronize()
                 e0.record()
-            for p_ in ar.parameters():
+            for p_ in ar_t.parameters():
                 p_.grad = None
-            loss = ar.training_step(batch)
+            loss = ar_t.training_step(batch)
             loss.backward()
         e1.record()
         torch.cuda.synchronize()
@@ -441,8 +461,7 @@ def extras(args, dev, tmp):
                              'frac_of_bf16_sustained_peak': 3 * fwd / (ms * 1e-3) / 1e12 / pk['bf16_tflops_sustained'],
                              'note': 'forward + backward, no optimizer step; flops = 3 x dense forward (no causal discount)',
                              'peak_mem_gb': torch.cuda.max_memory_allocated() / 1e9}
-        # the NAR half of configs[4]: same clips, all 8 codebooks, stage drawn by training_step (valle_nar.py:76)
-        del ar
+        del ar_t
         torch.cuda.empty_cache()
         torch.manual_seed(3)
         nar_t = ValleNAR(large_cfg('AdaptiveLayerNorm', tmp)).train().to(dev)
@@ -467,85 +486,88 @@ def extras(args, dev, tmp):
                                  'note': 'ValleNAR.training_step forward + backward (full attention, AdaLN), stage drawn per step'}
         del nar_t
     except Exception as e:  # report, do not hide
-        out['train_step'] = {'error': repr(e)}
+        out['train_step'] = {'error': repr(e)[:300]}
     return out
 
 
 # ------------------------------------------------------------------------------------------------------------
-def _cpu_decode_rate(sd, oc, B: int, n_steps: int, ctx: int, warm: int = 1):
-    """Oracle port (reference algorithm incl. its torch.cat cache growth) on the host cores: tokens/s of n_steps
-    KV-cached decode steps at batch B starting from a synthetic cache of `ctx` positions."""
-    from oracle import valle_oracle as vo
-    d, H, Dh, L = oc.d_model, oc.n_heads, oc.d_model // oc.n_heads, oc.num_layers
-    g = torch.Generator().manual_seed(0)
-    kv = tuple((torch.randn(B, H, ctx, Dh, generator=g), torch.randn(B, H, ctx, Dh, generator=g)) for _ in range(L))
-    x = torch.randn(B, 1, d, generator=g)
-    times = []
-    for s in range(warm + n_steps):
-        t0 = time.perf_counter()
-        h, kv = vo.transformer(x, sd, oc, kv_cache=kv, use_cache=True)
-        logits = (h @ sd['proj.weight'].t())[:, -1]
-        tok, _ = vo.topk_sampling(logits, 1, 1.0, 1.0)
-        x = sd['audio_emb.word_embeddings.weight'][tok] + 0.0
-        dt = time.perf_counter() - t0
-        if s >= warm:
-            times.append(dt)
-    return B * len(times) / sum(times), sum(times)
-
-
-def cpu_baseline(model, B: int, budget_s: float):
-    from oracle.valle_oracle import OracleConfig
+def _reference_rate(n_steps: int, warmup: int, B_ar: int, B_nar: int) -> tuple[dict, str]:
+    """Executed reference (oracle/_ref) on the host cores; falls back to the oracle port when it is not installed."""
+    from oracle import ref_runner
     torch.set_num_threads(os.cpu_count() or 1)
-    oc = OracleConfig.from_any(model.config)
-    sd = {k: v.detach().float().cpu() for k, v in model.state_dict().items()}
-    rate1, t1 = _cpu_decode_rate(sd, oc, B, 1, int(MEAN_CTX), warm=1)
-    n = max(2, min(160, int(budget_s / max(t1, 1e-3))))          # bounded sample: ~budget_s seconds of CPU work
-    ctx = int(MEAN_CTX - n / 2)                                   # centred on the GPU workload's mean context
-    rate, total = _cpu_decode_rate(sd, oc, B, n, ctx, warm=0)
-    return {'value': rate, 'unit': 'tokens/s', 'cores': torch.get_num_threads(), 'kind': 'port',
-            'sample': f'oracle port (fp32, torch CPU ops, reference algorithm incl. torch.cat KV growth): {n} decode steps at batch '
-                      f'{B}, ctx {ctx}->{ctx + n}, {total:.1f} s of CPU work; host has {os.cpu_count()} logical cores'}
+    if ref_runner.available():
+        return ref_runner.tts_rate('cpu', B_ar, n_steps, B_nar, warmup=warmup), 'reference'
+    return _port_rate(n_steps, B_ar), 'port'
+
+
+def _port_rate(n_steps: int, B_ar: int) -> dict:
+    """Oracle port (oracle/valle_oracle.py: the reference's algorithm restated) -- only used when oracle/_ref is absent."""
+    from oracle import synth
+    from oracle import valle_oracle as vo
+    oc = synth.large_config('LayerNorm', num_beams=B_ar, max_audio_len=n_steps + 1)
+    sd = synth.synth_state_dict(synth.ar_state_shapes(oc), 0)
+    g = torch.Generator().manual_seed(100)
+    pt, tt = torch.randint(0, 256, (TP,), generator=g), torch.randint(0, 256, (TT,), generator=g)
+    pc = torch.randint(0, 1024, (TC, Q), generator=g)
+    t0 = time.perf_counter()
+    vo.ar_generate(sd, oc, pt, pc, tt, max_steps=1)
+    t_pre = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    vo.ar_generate(sd, oc, pt, pc, tt, max_steps=n_steps + 1)
+    t_step = max(time.perf_counter() - t0 - t_pre, 1e-6) / n_steps
+    ocn = synth.large_config('AdaptiveLayerNorm')
+    sdn = synth.synth_state_dict(synth.nar_state_shapes(ocn), 1)
+    fl = torch.randint(0, 1024, (N_NEW,), generator=g)
+    t0 = time.perf_counter()
+    vo.nar_generate(sdn, ocn, pt, pc, tt, fl)
+    t_stage = (time.perf_counter() - t0) / 7
+    per_utt = t_pre / B_ar + N_NEW * t_step / B_ar + 7 * t_stage
+    return {'frames_per_s': N_NEW / per_utt, 'ar_tokens_per_s': B_ar / t_step, 'nar_stage_frames_per_s': N_NEW / t_stage,
+            'prefill_s': t_pre, 'step_s_mean': t_step, 'timed_steps': n_steps, 'nar_stage_s': t_stage, 'B_ar': B_ar, 'B_nar': 1,
+            'sample': f'oracle PORT (oracle/_ref not installed): ar_generate at num_beams={B_ar}, {n_steps} cached steps; nar_generate at batch 1'}
+
+
+def cpu_baseline(budget_s: float):
+    """The executed reference on this box's host cores, bounded sample (~budget_s seconds of CPU work)."""
+    n_steps = max(4, min(24, int(budget_s / 3 / 0.2)))      # ~0.2 s per step at num_beams=32; prefill + NAR stage take the rest
+    r, kind = _reference_rate(n_steps, 2, 32, 2)
+    return {'value': r['frames_per_s'], 'unit': 'frames/s', 'cores': torch.get_num_threads(), 'kind': kind, 'sample': r['sample'],
+            'ar_tokens_per_s': r['ar_tokens_per_s'], 'nar_stage_frames_per_s': r['nar_stage_frames_per_s'],
+            'host_logical_cores': os.cpu_count()}
 
 
 def run_reference(args, rank: int, world: int):
-    """--impl reference: the reference's own CPU implementation of the path.  The reference is Python/PyTorch and its
-    tree does not exist on the GPU box, so this times the oracle port (same algorithm, same ops) on all host threads."""
+    """--impl reference: the reference's own CPU implementation of the path on the host cores (rank 0 only)."""
     if rank != 0:
         return None
-    from oracle import synth
-    torch.set_num_threads(os.cpu_count() or 1)
-    oc = synth.large_config('LayerNorm')
-    sd = synth.synth_state_dict(synth.ar_state_shapes(oc), 0)
     K, W = args.steps, args.warmup
-    ctx = int(round(MEAN_CTX - (K - 1) / 2.0)) if K < N_NEW else TX + P0
-    B = args.batch
-    rate, t = _cpu_decode_rate(sd, oc, B, 1, ctx, warm=1)
-    while B > 1 and t * (K + W) > 150.0:       # bounded sample: shrink the batch until K steps fit in a few minutes
-        B = max(1, B // 4)
-        rate, t = _cpu_decode_rate(sd, oc, B, 1, ctx, warm=0)
-    k_eff = K if t * (K + W) <= 200.0 else max(1, int(200.0 / t) - W)
-    rate, total = _cpu_decode_rate(sd, oc, B, k_eff, ctx, warm=W)
-    sample = (f'oracle port on {torch.get_num_threads()} host threads: {k_eff} timed decode steps (of K={K}) at batch {B}, '
-              f'ctx {ctx}->{ctx + k_eff}, fp32')
-    return {'impl': 'reference', 'metric': 'ar_decode_tokens_per_s', 'value': rate, 'unit': 'tokens/s', 'n_gpus': world,
-            'steps': K, 'warmup': W, 'ms_per_step': total / k_eff * 1e3, 'higher_is_better': True, 'scaling': 'weak',
+    # bounded sample: one prefill, then W + K cached AR steps (capped so that the arm ends within a few minutes), one NAR stage
+    n = max(2, min(K + W, 400))
+    r, kind = _reference_rate(n, min(W, n - 1), 32, 2)
+    rate = r['frames_per_s']
+    return {'impl': 'reference', 'metric': 'tts_codec_frames_per_s', 'value': rate, 'unit': 'frames/s', 'n_gpus': world,
+            'steps': K, 'warmup': W, 'ms_per_step': args.utterances * N_NEW / rate * 1e3, 'higher_is_better': True, 'scaling': 'strong',
             'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': 'AR decode, default VALL-E AR decoder 12L d1024 h16 F4096, KV-cached greedy (BASELINE configs[1]); '
-                                   'CPU sample: ' + sample, 'batch_per_gpu': B},
-            'cpu_baseline': {'value': rate, 'unit': 'tokens/s', 'cores': torch.get_num_threads(), 'kind': 'port', 'sample': sample},
-            'e2e': {'value': rate, 'unit': 'tokens/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            'config': {'workload': workload_string(args.utterances), 'utterances': args.utterances,
+                       'utterances_per_s': rate / N_NEW, 'sample': r['sample']},
+            'cpu_baseline': {'value': rate, 'unit': 'frames/s', 'cores': torch.get_num_threads(), 'kind': kind, 'sample': r['sample'],
+                             'ar_tokens_per_s': r['ar_tokens_per_s'], 'nar_stage_frames_per_s': r['nar_stage_frames_per_s']},
+            'e2e': {'value': rate, 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'gpu_launches': 0}
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=N_NEW)
-    ap.add_argument('--warmup', type=int, default=8)
+    ap.add_argument('--steps', type=int, default=3)
+    ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--batch', type=int, default=32)
+    ap.add_argument('--utterances', type=int, default=256)
+    ap.add_argument('--e2e-steps', type=int, default=3)
+    ap.add_argument('--nar-chunk', type=int, default=64)
     ap.add_argument('--nar-batch', type=int, default=64)
     ap.add_argument('--train-batch', type=int, default=16)
+    ap.add_argument('--cpu-budget', type=float, default=15.0)
     ap.add_argument('--no-extras', action='store_true')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup

@@ -96,7 +96,14 @@ def load(build_if_missing: bool = True):
     return lib
 
 
+LAUNCHES = 0            # kernel-launching C calls made through check() (bench.py's gpu_launches claim; graph replays are
+_NO_LAUNCH = {'vb_device_info', 'vb_decode_gemm_plan'}    # counted separately by the engine)
+
+
 def check(rc: int, what: str = '') -> None:
+    global LAUNCHES
+    if what not in _NO_LAUNCH:
+        LAUNCHES += 1
     if rc != 0:
         msg = load().vb_last_error_string().decode(errors='replace')
         raise VBError(f'{what or "libvalle_b200"} failed with status {rc}: {msg}')

@@ -149,6 +149,8 @@ class ARDecoder:
         self._graph = None
         self._graph_key = None
         self._streams = []
+        self.replays = 0                       # CUDA-graph replays of the decode step so far (launch accounting)
+        self._phase_events = None
         self._seed_dev = torch.zeros(1, device=self.device, dtype=torch.int64)     # read by vb_ar_step_tail: graphs are seed-independent
         if precision == 'bf16':
             self._fold_layernorm(model)
@@ -480,6 +482,16 @@ class ARDecoder:
                 ops.linear(sub['f'], L['w2'], L['b2'], residual=x, out=x)
         self._logits_sample_book(sub, x, samp, uniforms, eos)
 
+    @property
+    def last_phases(self) -> dict:
+        """Device time of the last generate() call split into prefill (+ first token) and the decode loop, from CUDA events
+        recorded in stream order (synchronises on the last one)."""
+        if self._phase_events is None:
+            return {}
+        ev = self._phase_events
+        ev[2].synchronize()
+        return {'ar_prefill_ms': ev[0].elapsed_time(ev[1]), 'ar_decode_ms': ev[1].elapsed_time(ev[2])}
+
     def step_logits(self) -> torch.Tensor:
         """(B, V) fp32 logits of the most recent first_token / decode_step, for parity tests: where the logits GEMM leaves
         split-K slices they are summed in index order, exactly as the sampling kernel does."""
@@ -543,8 +555,11 @@ class ARDecoder:
         """Returns (codes_out (B,n_steps) int32, sum_logprobs (B,), n_steps).  Semantics: valle_ar.py:141-171."""
         samp = {'temperature': temperature, 'top_k': top_k, 'top_p': top_p, 'seed': seed}
         eos = -1 if ignore_eos else self.cfg.num_audio_tokens
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        ev[0].record()
         st = self.prefill(tokens, codes, code_lens=code_lens, max_new=max_new)
         self.first_token(samp, None if uniforms is None else uniforms[0], eos)
+        ev[1].record()
         graph = None
         step = 1
         if use_graph and uniforms is None and max_new > 2:
@@ -569,12 +584,15 @@ class ARDecoder:
         while step < max_new:
             if graph is not None:
                 graph.replay()
+                self.replays += 1
             else:
                 self.decode_step(samp, None if uniforms is None else uniforms[step], eos)
             step += 1
             if not ignore_eos and (step % poll_every == 0):
                 if int(st['state'][:, 1].min().item()) >= 0:      # every sub-batch has seen all of its rows stop
                     break
+        ev[2].record()
+        self._phase_events = ev
         state = st['state'].tolist()
         s_now = state[0][0]
         stops = [s[1] for s in state]
