@@ -369,12 +369,62 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                 'step_hbm_bytes': bytes32, 'step_hbm_frac_of_measured_peak': bytes32 / (step_ms * 1e-3) / (pk['hbm_gbs'] * 1e9),
                 'launches_per_step': eng32.launches_per_step(), 'decode_gemm': decode_form(eng32, eng32._state['subs'][0]),
                 'roofline_attention': roof32}
+        if world > 1:
+            del nar
+            td = train_step_dp(args, dev, tmp, world, pk)
+            if rank == 0:
+                extras['train_step_dp'] = td
         if rank == 0 and world == 1:
             extras.update(extras_single_gpu(args, dev, tmp, ar, nar, pk))
             result['cpu_baseline'] = cpu_baseline(budget_s=args.cpu_budget)
         if rank == 0:
             result['extras'] = extras
     return result
+
+
+def train_step_dp(args, dev, tmp, world: int, pk: dict) -> dict:
+    """BASELINE configs[4] across the ranks: teacher-forced AR step, 16 clips of 15 s PER GPU, forward + backward with the
+    gradient all-reduce overlapped with the backward pass (parallel.GradReducer), and the same step without any exchange."""
+    from valle2_b200 import parallel
+    from valle2_b200.models import ValleAR
+    torch.cuda.empty_cache()
+    torch.manual_seed(2)
+    model = ValleAR(large_cfg('LayerNorm', tmp)).train().to(dev)
+    g = torch.Generator().manual_seed(11 + int(os.environ.get('RANK', '0')))
+    Bt, Txt, Tyt = args.train_batch, 225, 1126
+    batch = {'tokens': torch.randint(0, 256, (Bt, Txt), generator=g), 'tokens_lens': torch.full((Bt,), Txt),
+             'codes': torch.randint(0, 1024, (Bt, Tyt), generator=g), 'codes_lens': torch.full((Bt,), Tyt),
+             'target': torch.randint(0, 1025, (Bt, Tyt), generator=g)}
+    red = parallel.GradReducer(model)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    out = {}
+    for label, reducer in (('local_ms_per_step', None), ('overlapped_allreduce_ms_per_step', red)):
+        for it in range(6):
+            if it == 3:
+                torch.distributed.barrier()
+                torch.cuda.synchronize()
+                e0.record()
+            for p_ in model.parameters():
+                p_.grad = None
+            with parallel.reducing(reducer):
+                loss = model.training_step(batch)
+            loss.backward()
+        e1.record()
+        torch.distributed.barrier()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / 3], device=dev)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        out[label] = float(t.item())
+    n_grad = sum(p.numel() for p in model.parameters())
+    out.update({'workload': 'BASELINE configs[4] per-GPU share: ValleAR.training_step, 16 clips x (225 + 1126) positions per GPU, forward + '
+                            'backward, no optimizer step', 'global_batch': Bt * world, 'gradient_bytes_fp32': n_grad * 4,
+                'clips_per_s': Bt * world / (out['overlapped_allreduce_ms_per_step'] * 1e-3),
+                'slowdown_vs_local': out['overlapped_allreduce_ms_per_step'] / out['local_ms_per_step'],
+                'exchange': 'one all_reduce (NCCL AVG) per transformer layer + one for the remaining parameters, enqueued as the backward '
+                            'pass finishes each layer'})
+    del model, red
+    torch.cuda.empty_cache()
+    return out
 
 
 def extras_single_gpu(args, dev, tmp, ar, nar, pk):

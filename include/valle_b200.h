@@ -256,6 +256,13 @@ int vb_colsum_blocks(const void* x, int dtype, int64_t R, int N, int64_t ldx, fl
 /* y = gelu_erf(pre);  dpre = dy * gelu_erf'(pre)   (modules.py:216) */
 int vb_gelu_fwd(const void* pre, int dtype, void* y, int64_t n, void* stream);
 int vb_gelu_bwd(const void* pre, const void* dy, int dtype, void* dpre, int64_t n, void* stream);
+/* nn.Dropout of the training step (modules.py:56/78 PositionalEncoding p = 0.1, :215/:221 FeedForward, :234-235/:277-278
+ * dropout1 / dropout2).  The keep mask is a counter-based hash of (seed, site, element index): the backward pass applies the
+ * SAME call to the gradient instead of reading a stored mask.
+ *   vb_dropout:      x[i] = keep(i) ? x[i] / (1 - p) : 0      in place, x fp32 or bf16
+ *   vb_dropout_add:  x[i] += keep(i) ? t[i] / (1 - p) : 0     x fp32 residual stream, t fp32 or bf16     (x + dropout(t)) */
+int vb_dropout(void* x, int dtype, int64_t n, float p, uint64_t seed, uint64_t site, void* stream);
+int vb_dropout_add(float* x, const void* t, int t_dtype, int64_t n, float p, uint64_t seed, uint64_t site, void* stream);
 /* LayerNorm backward: dx[R][d] (fp32) += d/dx of LN(x; gamma, beta) applied to dy; dgamma_part / dbeta_part receive
  * vb_layernorm_bwd_blocks(R) partial rows of d floats (reduce them with vb_colsum).  gamma == NULL: the forward was a plain
  * cast, dx += dy. */

@@ -13,6 +13,7 @@ import valle2_b200  # noqa: E402
 from oracle import synth  # noqa: E402
 from oracle import valle_oracle as vo  # noqa: E402
 from test_gpu_models import build, rel_err  # noqa: E402
+from valle2_b200.train import zero_pe_dropout  # noqa: E402
 
 
 @pytest.fixture(autouse=True)
@@ -56,6 +57,7 @@ def test_ar_training_step_gradients_vs_oracle_autograd(tmp_path, precision, tol,
     oc = synth.tiny_config('LayerNorm')
     model, sd = build('ValleAR', oc, tmp_path, 3)
     model.train()
+    zero_pe_dropout(model)          # parity against the dropout-free oracle (SURVEY K-3)
     batch = _ar_batch(oc, B, Tx, Ty, 5)
     ref_loss, ref = _oracle_grads(sd, lambda s: vo.ar_teacher_forced(s, oc, batch['tokens'], batch['codes'], batch['tokens_lens'],
                                                                      batch['codes_lens'], batch['target'])[1])
@@ -81,6 +83,7 @@ def test_nar_training_step_gradients_vs_oracle_autograd(tmp_path, precision, tol
     oc = synth.tiny_config('AdaptiveLayerNorm')
     model, sd = build('ValleNAR', oc, tmp_path, 4)
     model.train()
+    zero_pe_dropout(model)          # parity against the dropout-free oracle (SURVEY K-3)
     g = torch.Generator().manual_seed(6)
     B, Tx, T = 2, 6, 13
     batch = {'tokens': torch.randint(0, 256, (B, Tx), generator=g), 'codes': torch.randint(0, 1024, (B, T, 8), generator=g),
@@ -110,6 +113,7 @@ def test_training_step_drives_an_optimizer(tmp_path):
     oc = synth.tiny_config('LayerNorm')
     model, _ = build('ValleAR', oc, tmp_path, 8)
     model.train()
+    zero_pe_dropout(model)          # parity against the dropout-free oracle (SURVEY K-3)
     batch = _ar_batch(oc, 2, 6, 12, 9, ragged=False)
     opt = torch.optim.AdamW(model.parameters(), lr=1e-3)
     losses = []
@@ -264,6 +268,7 @@ def test_collated_batch_feeds_training_step(tmp_path):
     batch = ValleARCollate(oc)(items)
     model, sd = build('ValleAR', oc, tmp_path, 3)
     model.train()
+    zero_pe_dropout(model)          # parity against the dropout-free oracle (SURVEY K-3)
     ref = vo.ar_teacher_forced(sd, oc, batch['tokens'], batch['codes'], batch['tokens_lens'], batch['codes_lens'], batch['target'])[1]
     loss = model.training_step(batch)
     assert abs(loss.item() - ref.item()) < 1e-4
@@ -323,3 +328,105 @@ def test_train_model_driver_end_to_end(tmp_path):
         tm.train(fp, 'ValleAR')
     # the CLI parses the reference's flags
     tm.main(['-c', str(fp), '-m', 'ValleAR', '--synthetic', '8', '--max-steps', '1'])
+
+
+def test_dropout_kernel_statistics_and_determinism(ops):
+    """vb_dropout: keep fraction 1 - p, survivors scaled by 1 / (1 - p), the mask is a pure function of (seed, site, index)
+    (the backward pass recomputes it), different sites / seeds give different masks, both dtypes agree on the mask."""
+    n = 1 << 20
+    for p in (0.1, 0.5):
+        x = torch.ones(n, device='cuda')
+        ops.dropout_(x, p, 42, 7)
+        keep = (x != 0).float().mean().item()
+        assert abs(keep - (1 - p)) < 4 * math.sqrt(p * (1 - p) / n) + 1e-4
+        assert torch.allclose(x[x != 0], torch.full((1,), 1 / (1 - p), device='cuda'))
+        y = torch.ones(n, device='cuda')
+        ops.dropout_(y, p, 42, 7)
+        assert torch.equal(x, y)
+        z = torch.ones(n, device='cuda', dtype=torch.bfloat16)
+        ops.dropout_(z, p, 42, 7)
+        assert torch.equal(z != 0, x != 0)
+        for seed, site in ((43, 7), (42, 8)):
+            w = torch.ones(n, device='cuda')
+            ops.dropout_(w, p, seed, site)
+            agree = ((w != 0) == (x != 0)).float().mean().item()
+            assert abs(agree - ((1 - p) ** 2 + p ** 2)) < 0.01          # independent masks
+        r = torch.randn(n, device='cuda')
+        t = torch.randn(n, device='cuda')
+        want = r + t * x
+        ops.dropout_add_(r, t, p, 42, 7)
+        assert torch.allclose(r, want, atol=1e-6)
+    assert torch.equal(ops.dropout_(torch.ones(8, device='cuda'), 0.0, 1, 1), torch.ones(8, device='cuda'))
+
+
+class _MaskMul(torch.nn.Module):
+    def __init__(self, mask):
+        super().__init__()
+        self.mask = mask
+
+    def forward(self, x):
+        return x * self.mask
+
+
+@pytest.mark.parametrize('precision,tol', [('fp32', 1e-4), ('bf16', 3e-2)])
+def test_ar_training_step_with_dropout_equals_reference_with_the_same_masks(tmp_path, precision, tol):
+    """model.train() with config.dropout = 0.1 and the PositionalEncoding's hard-wired p = 0.1 (SURVEY K-3): torch's RNG
+    stream cannot be reproduced, so the EXECUTED reference gets this step's masks (generated by the same kernel,
+    train.dropout_masks) in place of its five nn.Dropout sites; loss and every parameter gradient must then agree."""
+    from oracle import ref_shims
+    if not ref_shims.reference_available():
+        pytest.skip('executed reference not installed (python -m oracle.build_ref)')
+    from valle2_b200 import train
+    from valle2_b200.config import ConfigValle
+    from valle2_b200.models import ValleAR
+    valle2_b200.set_precision(precision)
+    oc = synth.tiny_config('LayerNorm')
+    fields = {k: getattr(oc, k) for k in type(oc).__dataclass_fields__}
+    cfg = ConfigValle(dropout=0.1, ckpt_path=tmp_path / 'c', log_path=tmp_path / 'l', **fields)
+    sd = synth.synth_state_dict(synth.ar_state_shapes(oc), 3)
+    model = ValleAR(cfg)
+    model.load_state_dict(sd, strict=True)
+    model = model.cuda().train()
+    B, Tx, Ty = 3, 9, 21
+    batch = _ar_batch(oc, B, Tx, Ty, 5)
+    plan = train.dropout_plan(model, seed=1234)
+    assert plan == {'p': 0.1, 'pe_p': 0.1, 'seed': 1234}
+    loss = model.training_step(batch, dropout_seed=1234)
+    loss.backward()
+    loss_eval_mode = None
+    S = Tx + Ty
+    masks = {k: v.cpu() for k, v in train.dropout_masks(plan, oc.num_layers, B * S, oc.d_model, oc.dim_feedforward, 'cuda').items()}
+    assert 0.8 < (masks['pe'] != 0).float().mean().item() < 0.97
+    valle = ref_shims.import_reference()
+    try:
+        rcfg = valle.config.ConfigValle(dropout=0.1, ckpt_path=tmp_path / 'rc', log_path=tmp_path / 'rl', **fields)
+        ref = valle.models.ValleAR(rcfg)
+        ref.load_state_dict(sd, strict=True)
+        ref.train()
+        pe = masks['pe'].view(B, S, -1)
+        ref.tokens_position_emb.dropout = _MaskMul(pe[:, :Tx])
+        ref.audio_position_emb.dropout = _MaskMul(pe[:, Tx:])
+        for li, layer in enumerate(ref.transformer.layers):
+            layer.dropout1 = _MaskMul(masks[f'{li}.attn'].view(B, S, -1))
+            layer.ffn.dropout = _MaskMul(masks[f'{li}.ffn_inner'].view(B, S, -1))
+            layer.dropout2 = _MaskMul(masks[f'{li}.ffn'].view(B, S, -1))
+        ref_loss = ref.training_step(batch)
+        ref_loss.backward()
+        ref_grads = {n: p.grad.clone() for n, p in ref.named_parameters()}
+        ref.eval()
+        with torch.no_grad():
+            loss_eval_mode = float(ref.training_step(batch))
+    finally:
+        ref_shims.release_reference()
+    assert abs(float(ref_loss) - loss_eval_mode) > 1e-3                 # the masks do change the step
+    assert abs(loss.item() - float(ref_loss)) < (1e-4 if precision == 'fp32' else 5e-2)
+    for name, p in model.named_parameters():
+        scale = ref_grads[name].abs().max().item() + 1e-12
+        err = (p.grad.cpu().double() - ref_grads[name].double()).abs().max().item() / scale
+        assert err < tol, (name, err)
+    # eval mode drops nothing; a second training step draws new masks
+    model.eval()
+    assert train.dropout_plan(model) is None
+    model.train()
+    a, b = train.dropout_plan(model), train.dropout_plan(model)
+    assert a['seed'] != b['seed']

@@ -167,3 +167,107 @@ def test_train_model_host_side_sharding_and_items(tmp_path):
     expect = torch.tensor([items[i]['tokens'].numel() for i in range(bs * world)])
     assert torch.equal(step0, expect)
     assert per_rank[0][0]['codes'].shape[0] == bs and int(per_rank[0][0]['codes'][0, 0]) == cfg.bos_token
+
+
+def test_checkpoint_round_trip_and_reference_interchange(tmp_path):
+    """Checkpoints in Lightning's file format with the reference's state_dict keys: save -> load restores parameters, optimizer
+    and scheduler; our state_dict loads strictly into the EXECUTED reference's ValleAR / ValleNAR and theirs into ours."""
+    import torch
+    from valle2_b200 import checkpoint
+    from valle2_b200.config import ConfigValle
+    from valle2_b200.models import ValleAR, ValleNAR
+    kw = dict(num_layers=2, d_model=64, n_heads=4, dim_feedforward=128, ckpt_path=tmp_path / 'c', log_path=tmp_path / 'l')
+    for cls, norm in ((ValleAR, 'LayerNorm'), (ValleNAR, 'AdaptiveLayerNorm')):
+        torch.manual_seed(1)
+        model = cls(ConfigValle(norm=norm, **kw))
+        opt = model.configure_optimizers()
+        optimizer, scheduler = opt['optimizer'], opt['lr_scheduler']
+        for p in model.parameters():
+            p.grad = torch.ones_like(p) * 1e-3
+        optimizer.step(); scheduler.step()
+        path = checkpoint.save_checkpoint(tmp_path / f'{cls.__name__}.ckpt', model, optimizer, scheduler, global_step=7, epoch=2)
+        raw = torch.load(path, weights_only=False)
+        assert {'state_dict', 'optimizer_states', 'lr_schedulers', 'global_step', 'epoch', 'hyper_parameters'} <= set(raw)
+        torch.manual_seed(2)
+        other = cls(ConfigValle(norm=norm, **kw))
+        o2 = other.configure_optimizers()
+        meta = checkpoint.load_checkpoint(path, other, o2['optimizer'], o2['lr_scheduler'])
+        assert meta['global_step'] == 7 and meta['epoch'] == 2 and meta['model_class'] == cls.__name__
+        for (n, a), (_, b) in zip(model.state_dict().items(), other.state_dict().items()):
+            assert torch.equal(a, b), n
+        assert o2['lr_scheduler'].state_dict()['last_epoch'] == scheduler.state_dict()['last_epoch']
+        st_a, st_b = optimizer.state_dict()['state'], o2['optimizer'].state_dict()['state']
+        assert st_a.keys() == st_b.keys() and all(torch.equal(st_a[k]['exp_avg'], st_b[k]['exp_avg']) for k in st_a)
+    from oracle import ref_shims
+    if not ref_shims.reference_available():
+        return
+    torch.manual_seed(3)
+    ours = {'ValleAR': ValleAR(ConfigValle(norm='LayerNorm', **kw)), 'ValleNAR': ValleNAR(ConfigValle(norm='AdaptiveLayerNorm', **kw))}
+    paths = {k: checkpoint.save_checkpoint(tmp_path / f'x{k}.ckpt', m) for k, m in ours.items()}
+    valle = ref_shims.import_reference()
+    try:
+        ref_sd = {}
+        for k, norm in (('ValleAR', 'LayerNorm'), ('ValleNAR', 'AdaptiveLayerNorm')):
+            ref = getattr(valle.models, k)(valle.config.ConfigValle(norm=norm, **kw))
+            ref.load_state_dict(torch.load(paths[k], weights_only=False)['state_dict'], strict=True)      # ours -> reference
+            torch.manual_seed(4)
+            fresh = getattr(valle.models, k)(valle.config.ConfigValle(norm=norm, **kw))
+            ref_sd[k] = {n: v.clone() for n, v in fresh.state_dict().items()}
+    finally:
+        ref_shims.release_reference()
+    for k, m in ours.items():
+        m.load_state_dict(ref_sd[k], strict=True)                                                           # reference -> ours
+        assert all(torch.equal(v, ref_sd[k][n]) for n, v in m.state_dict().items())
+
+
+def test_encodec_pip_wire_format_with_a_stand_in_codec():
+    """The reference's tests/test_encodec_pip.py shapes (16 000 samples -> (8, 50) codes -> 16 000 samples, embeddings (128, T))
+    against EncodecPip driven by a stand-in codec with EnCodec-24 kHz's interface and hop (the real package is not available
+    offline), plus the (Q, T) <-> (T, Q) adapters between codec and decoders."""
+    import pytest
+    import torch
+    from valle.models import EncodecPip, MODEL_DICT
+
+    class FakeCodec:
+        sample_rate = 24000
+
+        def __init__(self):
+            self.bandwidth = None
+            self.encoder = lambda a: torch.zeros(a.shape[0], 128, a.shape[-1] // 320)
+
+        def set_target_bandwidth(self, bw):
+            self.bandwidth = bw
+
+        def encode(self, audio):                      # (B, 1, T) -> [(codes (B, Q, T / 320), scale)]
+            B, _, T = audio.shape
+            return [(torch.arange(B * 8 * (T // 320)).view(B, 8, T // 320) % 1024, None)]
+
+        def decode(self, frames):                     # [(codes (B, Q, F), scale)] -> (B, 1, F * 320)
+            codes = frames[0][0]
+            return torch.zeros(codes.shape[0], 1, codes.shape[-1] * 320)
+
+    assert MODEL_DICT['EncodecPip'] is EncodecPip
+    enc = EncodecPip(model=FakeCodec())
+    assert enc.model.bandwidth == 6.0 and enc.sampling_rate == 24000
+    for n, frames in ((16000, 50), (32000, 100), (48000, 150)):
+        assert enc.encode(torch.randn(n)).shape == (8, frames)
+        assert enc.batch_encode(torch.randn(4, n)).shape == (4, 8, frames)
+        assert enc.decode(torch.randint(0, 1024, (8, frames))).shape == (n,)
+        assert enc.batch_decode(torch.randint(0, 1024, (4, 8, frames))).shape == (4, n)
+        assert enc.encode_decode(torch.randn(n)).shape == (n,)
+        assert enc.get_embedding(torch.randn(n)).shape == (128, frames)
+        assert enc.batch_get_embedding(torch.randn(4, n)).shape == (4, 128, frames)
+    with pytest.raises(AssertionError, match='Expected 1D audio tensor'):
+        enc.encode(torch.randn(2, 100))
+    with pytest.raises(AssertionError, match='Expected 2D codes tensor'):
+        enc.decode(torch.zeros(8, dtype=torch.long))
+    qt = torch.randint(0, 1024, (8, 50))
+    tq = EncodecPip.to_model_layout(qt)
+    assert tq.shape == (50, 8) and tq.dtype == torch.int64 and torch.equal(EncodecPip.to_codec_layout(tq), qt)
+    assert EncodecPip.to_model_layout(qt[None]).shape == (1, 50, 8)
+    assert enc.prompt_from_audio(torch.randn(16000)).shape == (50, 8) and enc.audio_from_codes(tq).shape == (16000,)
+    try:
+        import encodec  # noqa: F401
+    except Exception:
+        with pytest.raises(RuntimeError, match='encodec'):
+            EncodecPip()

@@ -86,3 +86,75 @@ def test_gradient_allreduce_matches_full_batch(tmp_path):
     for n, p in model.named_parameters():
         assert torch.allclose(g0[n], p.grad, atol=1e-6), n
         assert torch.equal(g0[n], g1[n]), n
+
+
+class _Toy(torch.nn.Module):
+    """Parameter names shaped like the decoders': transformer.layers.{i}.* + a few others (one never used)."""
+
+    def __init__(self):
+        super().__init__()
+        self.emb = torch.nn.Linear(5, 6)
+        self.transformer = torch.nn.Module()
+        self.transformer.layers = torch.nn.ModuleList([torch.nn.Linear(6, 6) for _ in range(3)])
+        self.proj = torch.nn.Linear(6, 2)
+        self.unused = torch.nn.Linear(6, 2)          # no gradient on any rank
+        self.rank0_only = torch.nn.Linear(6, 1)      # gradient on rank 0 only
+
+    def forward(self, x, rank):
+        h = self.emb(x)
+        for layer in self.transformer.layers:
+            h = torch.tanh(layer(h))
+        out = self.proj(h).pow(2).mean()
+        return out + (self.rank0_only(h).sum() if rank == 0 else 0.0)
+
+
+def _reducer_worker(rank, world_size, port, out_dir):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world_size)
+    from valle2_b200 import parallel
+    torch.manual_seed(0)
+    model = _Toy()
+    x = torch.arange(20, dtype=torch.float32).view(4, 5) / 10
+    part = parallel.shard_batch({'x': x}, rank, world_size)['x']
+    loss = model(part, rank)
+    names = [n for n, _ in model.named_parameters()]
+    grads = dict(zip(names, torch.autograd.grad(loss, list(model.parameters()), allow_unused=True)))
+    red = parallel.GradReducer(model)
+    assert len(red.buckets) == 4 and [n for n, _ in red.buckets[1]] == ['transformer.layers.1.weight', 'transformer.layers.1.bias']
+    with parallel.reducing(red) as active:
+        assert parallel.active_reducer() is active
+        red.begin()
+        for li in (2, 1, 0):                         # the order the backward pass finishes the layers in
+            red.submit(li, {k: v for k, v in grads.items() if k.startswith(f'transformer.layers.{li}.')})
+        red.submit(3, grads)
+        avg = red.finish()
+    assert parallel.active_reducer() is None
+    for n, p in model.named_parameters():
+        p.grad = avg[n].clone()
+    dropped = red.drop_unused(model)
+    assert dropped == 2 and model.unused.weight.grad is None and model.rank0_only.weight.grad is not None
+    torch.save({n: (None if p.grad is None else p.grad.clone()) for n, p in model.named_parameters()}, os.path.join(out_dir, f'r{rank}.pt'))
+    dist.destroy_process_group()
+
+
+def test_overlapped_grad_reducer_matches_full_batch(tmp_path):
+    """World-size-2 gloo: GradReducer (per-layer buckets in one flat buffer, asynchronous all-reduce per bucket, has-gradient
+    flags) gives every rank the gradient of the mean loss over the whole batch; a parameter without a gradient on every rank
+    keeps grad = None, one with a gradient on one rank gets the average with zeros."""
+    with socket.socket() as s:
+        s.bind(('127.0.0.1', 0))
+        port = s.getsockname()[1]
+    mp.spawn(_reducer_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    torch.manual_seed(0)
+    model = _Toy()
+    x = torch.arange(20, dtype=torch.float32).view(4, 5) / 10
+    loss = 0.5 * model(x[:2], 0) + 0.5 * model(x[2:], 1)
+    loss.backward()
+    g0, g1 = torch.load(os.path.join(tmp_path, 'r0.pt')), torch.load(os.path.join(tmp_path, 'r1.pt'))
+    for n, p in model.named_parameters():
+        if p.grad is None:
+            assert g0[n] is None and g1[n] is None, n
+            continue
+        assert torch.allclose(g0[n], p.grad, atol=1e-6), n
+        assert torch.equal(g0[n], g1[n]), n

@@ -7,6 +7,7 @@ import valle2_b200
 import valle2_b200.collate
 import valle2_b200.config
 import valle2_b200.models
+import valle2_b200.models.encodec_pip
 import valle2_b200.models.modules
 import valle2_b200.models.utils
 import valle2_b200.models.valle_ar
@@ -16,6 +17,7 @@ _alias = {
     'valle.collate': valle2_b200.collate,
     'valle.config': valle2_b200.config,
     'valle.models': valle2_b200.models,
+    'valle.models.encodec_pip': valle2_b200.models.encodec_pip,
     'valle.models.modules': valle2_b200.models.modules,
     'valle.models.utils': valle2_b200.models.utils,
     'valle.models.valle_ar': valle2_b200.models.valle_ar,

@@ -44,6 +44,8 @@ SIGNATURES = {
     'vb_colsum_blocks': (_i, [_p, _i, _i64, _i, _i64, _p, _i, _p]),
     'vb_gelu_fwd': (_i, [_p, _i, _p, _i64, _p]),
     'vb_gelu_bwd': (_i, [_p, _p, _i, _p, _i64, _p]),
+    'vb_dropout': (_i, [_p, _i, _i64, _f, _u64, _u64, _p]),
+    'vb_dropout_add': (_i, [_p, _p, _i, _i64, _f, _u64, _u64, _p]),
     'vb_layernorm_bwd_blocks': (_i, [_i64]),
     'vb_layernorm_bwd': (_i, [_p, _p, _p, _i, _p, _p, _p, _i64, _i, _f, _p]),
     'vb_attention_bwd': (_i, [_p, _p, _p, _p, _i, _p, _p, _i, _i, _i, _i, _i, _p, _p, _i, _p]),

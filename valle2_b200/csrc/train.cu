@@ -860,6 +860,39 @@ __global__ void embed_bwd_kernel(const int32_t* __restrict__ ids, const float* _
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Dropout (nn.Dropout at modules.py:56/78 PositionalEncoding p=0.1, :215/:221 FeedForward, :234-235/:277-278 dropout1/2).
+// The keep mask is a pure function of (seed, site, element index) -- a counter-based hash -- so the backward pass
+// recomputes it instead of storing it: y = keep ? x / (1 - p) : 0 with keep = hash(seed, site, i) >= p * 2^32.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t dropout_bits(uint64_t key, uint64_t i) {
+    uint64_t z = key + 0x9E3779B97F4A7C15ull * (i + 1);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    return static_cast<uint32_t>(z >> 32);
+}
+__host__ __device__ __forceinline__ uint64_t dropout_key(uint64_t seed, uint64_t site) {
+    return seed * 0xD1342543DE82EF95ull + site * 0xA0761D6478BD642Full + 0x2545F4914F6CDD1Dull;
+}
+
+template <typename T>
+__global__ void dropout_kernel(T* __restrict__ x, int64_t n, uint32_t thr, float inv_keep, uint64_t key) {
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const bool keep = dropout_bits(key, static_cast<uint64_t>(i)) >= thr;
+        x[i] = from_f32<T>(keep ? to_f32<T>(x[i]) * inv_keep : 0.f);
+    }
+}
+
+template <typename T>
+__global__ void dropout_add_kernel(float* __restrict__ x, const T* __restrict__ t, int64_t n, uint32_t thr, float inv_keep, uint64_t key) {
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const bool keep = dropout_bits(key, static_cast<uint64_t>(i)) >= thr;
+        if (keep) x[i] += to_f32<T>(t[i]) * inv_keep;
+    }
+}
+
 }  // namespace
 
 // ==================================================================================================================
@@ -1055,6 +1088,39 @@ extern "C" int vb_embed_bwd(const int32_t* ids, const float* dx, float* grad_tab
     if (B == 0 || T == 0) return VB_OK;
     embed_bwd_kernel<<<dim3(T, B), 256, 0, static_cast<cudaStream_t>(stream)>>>(ids, dx, grad_tables, T, Q, V, d, t_split, nq_a, nq_b,
                                                                                  rows_per_batch, row_offset);
+    VB_LAUNCH_CHECK();
+    return VB_OK;
+}
+
+static uint32_t dropout_threshold(float p) {
+    const double t = static_cast<double>(p) * 4294967296.0;
+    return t >= 4294967295.0 ? 0xffffffffu : static_cast<uint32_t>(t);
+}
+
+/* x[i] = keep(i) ? x[i] / (1 - p) : 0, in place; the same (seed, site) gives the same mask (forward and backward). */
+extern "C" int vb_dropout(void* x, int dtype, int64_t n, float p, uint64_t seed, uint64_t site, void* stream) {
+    VB_REQUIRE(x && n >= 0 && p >= 0.f && p < 1.f, VB_ERR_BAD_ARG, "vb_dropout: bad args (p must be in [0, 1))");
+    if (n == 0 || p == 0.f) return VB_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int blocks = static_cast<int>(std::min<int64_t>((n + 255) / 256, 148 * 16));
+    const uint64_t key = dropout_key(seed, site);
+    if (dtype == VB_F32) dropout_kernel<float><<<blocks, 256, 0, st>>>(static_cast<float*>(x), n, dropout_threshold(p), 1.f / (1.f - p), key);
+    else if (dtype == VB_BF16) dropout_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(static_cast<__nv_bfloat16*>(x), n, dropout_threshold(p), 1.f / (1.f - p), key);
+    else VB_REQUIRE(false, VB_ERR_BAD_ARG, "vb_dropout: bad dtype");
+    VB_LAUNCH_CHECK();
+    return VB_OK;
+}
+
+/* x[i] += keep(i) ? t[i] / (1 - p) : 0   (x fp32 residual stream, t fp32 or bf16): x = x + dropout(t), modules.py:277-278. */
+extern "C" int vb_dropout_add(float* x, const void* t, int t_dtype, int64_t n, float p, uint64_t seed, uint64_t site, void* stream) {
+    VB_REQUIRE(x && t && n >= 0 && p >= 0.f && p < 1.f, VB_ERR_BAD_ARG, "vb_dropout_add: bad args (p must be in [0, 1))");
+    if (n == 0) return VB_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int blocks = static_cast<int>(std::min<int64_t>((n + 255) / 256, 148 * 16));
+    const uint64_t key = dropout_key(seed, site);
+    if (t_dtype == VB_F32) dropout_add_kernel<float><<<blocks, 256, 0, st>>>(x, static_cast<const float*>(t), n, dropout_threshold(p), 1.f / (1.f - p), key);
+    else if (t_dtype == VB_BF16) dropout_add_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(x, static_cast<const __nv_bfloat16*>(t), n, dropout_threshold(p), 1.f / (1.f - p), key);
+    else VB_REQUIRE(false, VB_ERR_BAD_ARG, "vb_dropout_add: bad dtype");
     VB_LAUNCH_CHECK();
     return VB_OK;
 }

@@ -1,21 +1,7 @@
 """Model registry -- same names as the reference's ``valle/models/__init__.py``."""
+from .encodec_pip import EncodecPip
 from .valle_ar import ValleAR
 from .valle_nar import ValleNAR
-
-
-class _EncodecUnavailable:
-    """EnCodec wrapper is outside the hot-path scope; the ``encodec`` package and its weights are
-    not available offline.  Constructing it says so instead of failing at import time."""
-
-    def __init__(self, *a, **k):
-        raise RuntimeError('EncodecPip is out of scope for valle2_b200 (needs the `encodec` package + weights)')
-
-
-try:  # pragma: no cover
-    from encodec import EncodecModel  # noqa: F401
-    EncodecPip = _EncodecUnavailable
-except Exception:
-    EncodecPip = _EncodecUnavailable
 
 MODEL_DICT = {'EncodecPip': EncodecPip, 'ValleAR': ValleAR, 'ValleNAR': ValleNAR}
 

@@ -89,7 +89,8 @@ class ValleAR(BaseModule):
         ``loss.backward()`` / Lightning's optimisation loop work as with the reference."""
         from .. import train
         precision = valle2_b200.get_precision()
-        loss = train.step_loss(self, lambda: train.ar_loss_and_grads(self, batch, precision))
+        drop = train.dropout_plan(self, kwargs.get('dropout_seed'))       # None in eval mode / at rate 0
+        loss = train.step_loss(self, lambda: train.ar_loss_and_grads(self, batch, precision, drop))
         self.log('train/loss', loss)
         return loss
 

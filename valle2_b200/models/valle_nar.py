@@ -9,6 +9,7 @@ import random
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
+from torch import optim
 
 import valle2_b200
 
@@ -79,7 +80,8 @@ class ValleNAR(BaseModule):
         from .. import train
         layer = kwargs.get('layer') or random.randint(1, self.config.num_quantizers - 1)   # :76
         precision = valle2_b200.get_precision()
-        return train.step_loss(self, lambda: train.nar_loss_and_grads(self, batch, layer, precision))
+        drop = train.dropout_plan(self, kwargs.get('dropout_seed'))
+        return train.step_loss(self, lambda: train.nar_loss_and_grads(self, batch, layer, precision, drop))
 
     @torch.inference_mode()
     def generate(self, prompt_tokens: torch.Tensor, prompt_codes: torch.Tensor, target_tokens: torch.Tensor,
@@ -98,6 +100,14 @@ class ValleNAR(BaseModule):
         return self._engine().generate(prompt_tokens, prompt_codes, target_tokens, first_layer, greedy=greedy,
                                        temperature=self.config.temperature, seed=seed,
                                        use_tc_attention=use_tc_attention, target_lens=target_lens)
+
+    def configure_optimizers(self):
+        """Upstream ``ValleNAR`` has no ``configure_optimizers`` (SURVEY A-11: ``-m ValleNAR`` cannot train there); this is
+        ``ValleAR.configure_optimizers`` (valle_ar.py:182-194) verbatim in behaviour: AdamW + CosineAnnealingWarmRestarts."""
+        optimizer = optim.AdamW(self.parameters(), lr=self.config.lr, betas=self.config.betas,
+                                weight_decay=self.config.weight_decay, fused=True)
+        scheduler = optim.lr_scheduler.CosineAnnealingWarmRestarts(optimizer, self.config.lr_warmup)
+        return {'optimizer': optimizer, 'lr_scheduler': scheduler}
 
     def _prepare_audio_codes(self, codes: torch.Tensor, nar_stage: int) -> tuple[torch.Tensor, int]:
         """(B, T, Q) codes -> (summed embeddings (B, T, d), prefix_len)  (valle_nar.py:167-188): the first

@@ -387,6 +387,22 @@ def gelu_bwd(pre: torch.Tensor, dy: torch.Tensor, dpre: torch.Tensor) -> torch.T
     return dpre
 
 
+def dropout_(x: torch.Tensor, p: float, seed: int, site: int) -> torch.Tensor:
+    """In place nn.Dropout(p) with the counter-based mask of (seed, site); the same call on a gradient is its backward."""
+    assert x.is_contiguous()
+    if p > 0.0:
+        check(_L().vb_dropout(_ptr(x), _code(x.dtype), x.numel(), float(p), seed & (2 ** 64 - 1), site, _stream()), 'vb_dropout')
+    return x
+
+
+def dropout_add_(x: torch.Tensor, t: torch.Tensor, p: float, seed: int, site: int) -> torch.Tensor:
+    """x (fp32) += dropout(t) with the mask of (seed, site)."""
+    assert x.dtype == torch.float32 and x.is_contiguous() and t.is_contiguous() and x.numel() == t.numel()
+    check(_L().vb_dropout_add(_ptr(x), _ptr(t), _code(t.dtype), x.numel(), float(p), seed & (2 ** 64 - 1), site, _stream()),
+          'vb_dropout_add')
+    return x
+
+
 def layernorm_bwd(x: torch.Tensor, gamma: torch.Tensor | None, dy: torch.Tensor, dx: torch.Tensor, eps: float = 1e-5):
     """dx (fp32, R x d) += LN backward of dy; returns (dgamma, dbeta) fp32 [d] (None, None when gamma is None = plain cast)."""
     R, d = x.shape

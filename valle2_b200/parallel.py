@@ -76,19 +76,143 @@ def generate_sharded(decode_fn: Callable[[list[int]], tuple[torch.Tensor, torch.
 
 
 # ---- training: batch-sharded data parallelism (BASELINE config 5) -------------------------------------------
-def allreduce_gradients(model: torch.nn.Module, bucket_bytes: int = 64 << 20) -> int:
-    """Average ``param.grad`` over the ranks: the ONE exchange step of the batch-sharded training step.
+def _buckets_of(model: torch.nn.Module) -> list[list[tuple[str, torch.nn.Parameter]]]:
+    """Parameters grouped the way the backward pass finishes them: one bucket per transformer layer (last layer first is the
+    order they complete in), everything else (embeddings, projections, stage embeddings) in a final bucket."""
+    layers: dict[int, list] = {}
+    rest = []
+    for name, p in model.named_parameters():
+        if not p.requires_grad:
+            continue
+        parts = name.split('.')
+        if len(parts) > 2 and parts[0] == 'transformer' and parts[1] == 'layers' and parts[2].isdigit():
+            layers.setdefault(int(parts[2]), []).append((name, p))
+        else:
+            rest.append((name, p))
+    return [layers[k] for k in sorted(layers)] + [rest]
 
-    Gradients are flattened into buckets of ~``bucket_bytes`` (fp32) and summed with ``all_reduce`` (NCCL over
-    NVLink/NVSwitch on GPUs -- bucket size picked for launch latency, not link count -- gloo in the CPU tests), then
-    divided by the world size; parameters without a gradient on this rank (e.g. other NAR stages) contribute zeros so that
-    every rank issues the same collectives.  Returns the number of buckets reduced."""
+
+class GradReducer:
+    """Gradient averaging of the batch-sharded training step that OVERLAPS the backward pass.
+
+    One persistent flat fp32 buffer holds every parameter's gradient (no per-step ``torch.cat`` / copy-back); it is cut into
+    one bucket per transformer layer + one for the remaining parameters.  The hand-written backward (valle2_b200/train.py)
+    hands each layer's gradients over as soon as that layer is done (``submit``): they are copied into the bucket and the
+    bucket's ``all_reduce`` is enqueued at once (``async_op``: NCCL runs it on its own stream, ordered after the copies), so the
+    exchange of layer l travels over NVLink while layers l-1 .. 0 are still being differentiated.  ``finish`` waits for the
+    outstanding reductions and returns views of the averaged gradients.  A has-gradient flag per parameter is summed along
+    with the last bucket: a parameter that received no gradient on ANY rank (e.g. the projections of the NAR stages that were
+    not drawn) keeps ``grad = None`` (``drop_unused``), exactly as in a single-process step."""
+
+    def __init__(self, model: torch.nn.Module):
+        self.rank, self.ws = world()
+        self.buckets = _buckets_of(model)
+        dev = next(model.parameters()).device
+        self.names = [n for b in self.buckets for n, _ in b]
+        n_total = sum(p.numel() for b in self.buckets for _, p in b)
+        self.flat = torch.zeros(n_total + len(self.names), device=dev, dtype=torch.float32)
+        self.views, self.ranges, self.bucket_of = {}, [], {}
+        off = 0
+        for bi, bucket in enumerate(self.buckets):
+            start = off
+            for name, p in bucket:
+                self.views[name] = self.flat[off:off + p.numel()].view_as(p)
+                self.bucket_of[name] = bi
+                off += p.numel()
+            self.ranges.append((start, off))
+        self.flags = self.flat[n_total:]
+        self.flag_index = {n: i for i, n in enumerate(self.names)}
+        self.ranges[-1] = (self.ranges[-1][0], self.flat.numel())       # the flags travel with the last bucket
+        self._work, self._submitted = [], set()
+        self.avg_op = dist.ReduceOp.AVG if (self.ws > 1 and dist.get_backend() == 'nccl') else None
+
+    def begin(self) -> None:
+        self.flags.zero_()
+        self._work, self._submitted = [], set()
+
+    def _reduce(self, bi: int) -> None:
+        lo, hi = self.ranges[bi]
+        if self.ws > 1:
+            self._work.append(dist.all_reduce(self.flat[lo:hi], op=self.avg_op or dist.ReduceOp.SUM, async_op=True))
+
+    def submit(self, bucket: int, grads: dict) -> None:
+        """Gradients of one finished bucket ({parameter name: tensor or None}); missing names count as 'no gradient'."""
+        assert bucket not in self._submitted, f'bucket {bucket} submitted twice'
+        for name, _ in self.buckets[bucket]:
+            g = grads.get(name)
+            if g is None:
+                self.views[name].zero_()
+            else:
+                self.views[name].copy_(g.reshape(self.views[name].shape))
+                self.flags[self.flag_index[name]] = 1.0
+        self._submitted.add(bucket)
+        self._reduce(bucket)
+
+    def finish(self) -> dict:
+        """Wait for every reduction; returns {name: averaged gradient (a view of the flat buffer)}."""
+        assert len(self._submitted) == len(self.buckets), 'not every bucket was submitted'
+        for w in self._work:
+            w.wait()
+        if self.ws > 1 and self.avg_op is None:         # gloo has no AVG: sum, then divide (the flags stay sums)
+            n_params = self.flat.numel() - len(self.names)
+            self.flat[:n_params].div_(self.ws)
+        self._work = []
+        return dict(self.views)
+
+    def drop_unused(self, model: torch.nn.Module) -> int:
+        """After ``loss.backward()``: parameters whose has-gradient flag is zero on every rank get ``grad = None`` (one host
+        read of the flag vector).  Returns how many were dropped."""
+        flags = self.flags.tolist()
+        dropped = 0
+        for name, p in model.named_parameters():
+            i = self.flag_index.get(name)
+            if i is not None and flags[i] == 0.0 and p.grad is not None:
+                p.grad = None
+                dropped += 1
+        return dropped
+
+
+_ACTIVE: list = []
+
+
+class reducing:
+    """``with parallel.reducing(reducer): loss = model.training_step(batch)`` -- the training step's backward hands its
+    gradients to ``reducer`` layer by layer (overlapped all-reduce); outside the context the step is purely local."""
+
+    def __init__(self, reducer: GradReducer | None):
+        self.reducer = reducer
+
+    def __enter__(self):
+        _ACTIVE.append(self.reducer)
+        return self.reducer
+
+    def __exit__(self, *exc):
+        _ACTIVE.pop()
+        return False
+
+
+def active_reducer() -> GradReducer | None:
+    return _ACTIVE[-1] if _ACTIVE else None
+
+
+def allreduce_gradients(model: torch.nn.Module, bucket_bytes: int = 64 << 20) -> int:
+    """Average ``param.grad`` over the ranks AFTER the backward pass (no overlap): used with gradient accumulation, where the
+    exchange belongs to the last micro-batch only.  Gradients are packed into fp32 buckets of ~``bucket_bytes`` and summed
+    with ``all_reduce``; a has-gradient flag per parameter travels along so that a parameter without a gradient on every rank
+    keeps ``grad = None`` (single-process behaviour) while one that has a gradient on some ranks gets zeros from the others.
+    Returns the number of buckets reduced."""
     rank, ws = world()
     params = [p for _, p in sorted(model.named_parameters(), key=lambda kv: kv[0]) if p.requires_grad]
     if ws == 1 or not params:
         return 0
+    dev = params[0].device
+    flags = torch.tensor([0.0 if p.grad is None else 1.0 for p in params], device=dev)
+    dist.all_reduce(flags, op=dist.ReduceOp.SUM)
+    has = flags.tolist()
     buckets, cur, cur_bytes = [], [], 0
-    for p in params:
+    for p, h in zip(params, has):
+        if h == 0.0:
+            continue                               # no rank has a gradient: leave grad = None
         cur.append(p)
         cur_bytes += p.numel() * 4
         if cur_bytes >= bucket_bytes:
@@ -97,15 +221,23 @@ def allreduce_gradients(model: torch.nn.Module, bucket_bytes: int = 64 << 20) ->
     if cur:
         buckets.append(cur)
     for bucket in buckets:
-        flat = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1).float() for p in bucket])
+        flat = torch.empty(sum(p.numel() for p in bucket), device=dev, dtype=torch.float32)
+        off = 0
+        for p in bucket:
+            n = p.numel()
+            if p.grad is None:
+                flat[off:off + n].zero_()
+            else:
+                flat[off:off + n].copy_(p.grad.reshape(-1))
+            off += n
         dist.all_reduce(flat, op=dist.ReduceOp.SUM)
         flat.div_(ws)
         off = 0
         for p in bucket:
             n = p.numel()
-            g = flat[off:off + n].view_as(p).to(p.dtype)
+            g = flat[off:off + n].view_as(p)
             if p.grad is None:
-                p.grad = g.clone()
+                p.grad = g.to(p.dtype).clone()
             else:
                 p.grad.copy_(g)
             off += n

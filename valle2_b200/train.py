@@ -16,7 +16,11 @@ Everything else (LayerNorm / GELU / attention backward, cross entropy, embedding
 
 Precision: 'bf16' = bf16 operands, fp32 accumulation, fp32 residual stream and fp32 gradients of the residual stream and
 of all parameters; 'fp32' = validation mode (gradients within 1e-4 of torch autograd on the CPU oracle).
-Dropout is not applied (the parity configuration: ``dropout=0`` and PE dropout zeroed, SURVEY K-3).
+Dropout (``model.train()`` with ``config.dropout`` > 0, and the PositionalEncoding's hard-wired p = 0.1, SURVEY K-3): applied at
+the reference's four sites -- after embedding + PE (modules.py:78), inside the FFN after GELU (:221), on the attention and FFN
+outputs before the residual adds (dropout1 / dropout2, :277-278) -- with counter-based masks (``vb_dropout``): the mask is a
+hash of (step seed, site, element), recomputed by the backward pass instead of being stored.  torch's own RNG stream cannot be
+reproduced, so parity is checked by giving the executed reference the SAME masks (tests/test_gpu_training.py).
 """
 from __future__ import annotations
 
@@ -24,7 +28,7 @@ import os
 
 import torch
 
-from . import ops
+from . import ops, parallel
 from .ops import MASK_NONE, MASK_PREFIX_LM
 
 
@@ -75,6 +79,44 @@ def _rows(Rp: int, n: int, R: int, device, dtype: torch.dtype) -> torch.Tensor:
     if Rp > R:
         t[R:].zero_()
     return t
+
+
+SITE_PE = 1 << 20            # dropout site ids: PE = SITE_PE, layer li: 3 * li + {0: attention out, 1: FFN inner, 2: FFN out}
+
+
+def dropout_plan(model, seed: int | None = None) -> dict | None:
+    """Dropout of this training step, or None when nothing is dropped (eval mode or all rates zero).  Every call advances the
+    model's step counter so that consecutive steps draw different masks; ``seed`` pins the masks (tests)."""
+    if not model.training:
+        return None
+    p = float(model.config.dropout)
+    pe_t, pe_a = float(model.tokens_position_emb.dropout.p), float(model.audio_position_emb.dropout.p)
+    assert pe_t == pe_a, 'text and audio PositionalEncoding dropout rates differ'
+    if p <= 0.0 and pe_t <= 0.0:
+        return None
+    if seed is None:
+        step = getattr(model, '_dropout_step', 0)
+        model._dropout_step = step + 1
+        seed = (torch.initial_seed() * 1000003 + step) & ((1 << 63) - 1)
+    return {'p': p, 'pe_p': pe_t, 'seed': int(seed)}
+
+
+def zero_pe_dropout(model) -> None:
+    """The PositionalEncoding dropout is hard-wired to p = 0.1 independently of config.dropout (modules.py:56, SURVEY K-3):
+    parity runs against a dropout-free oracle switch it off with this."""
+    model.tokens_position_emb.dropout.p = 0.0
+    model.audio_position_emb.dropout.p = 0.0
+
+
+def dropout_masks(plan: dict, n_layers: int, rows: int, d: int, F: int, device) -> dict:
+    """The step's keep masks (scaled by 1 / (1 - p)) as dense fp32 tensors, generated by the same kernel -- for tests that feed
+    them to the reference in place of nn.Dropout."""
+    out = {'pe': ops.dropout_(torch.ones(rows, d, device=device), plan['pe_p'], plan['seed'], SITE_PE)}
+    for li in range(n_layers):
+        out[f'{li}.attn'] = ops.dropout_(torch.ones(rows, d, device=device), plan['p'], plan['seed'], 3 * li)
+        out[f'{li}.ffn_inner'] = ops.dropout_(torch.ones(rows, F, device=device), plan['p'], plan['seed'], 3 * li + 1)
+        out[f'{li}.ffn'] = ops.dropout_(torch.ones(rows, d, device=device), plan['p'], plan['seed'], 3 * li + 2)
+    return out
 
 
 def _mn_ok(*ts: torch.Tensor) -> bool:
@@ -136,15 +178,17 @@ class StackTrainer:
         g0, b0 = nm.norm.weight.detach().float(), nm.norm.bias.detach().float()
         return (w * g0).contiguous(), (w * b0 + b).contiguous(), {'w': w, 'e': e, 'g0': g0, 'b0': b0}
 
-    def forward(self, x: torch.Tensor, B: int, S: int, *, mask_mode: int, x_lens, kv_lens, stage: int = 0):
-        """x (Rp, d) fp32 residual stream (rows >= B*S are zero padding), updated in place.  Returns the cache."""
+    def forward(self, x: torch.Tensor, B: int, S: int, *, mask_mode: int, x_lens, kv_lens, stage: int = 0, drop: dict | None = None):
+        """x (Rp, d) fp32 residual stream (rows >= B*S are zero padding), updated in place.  Returns the cache.
+        drop = dropout_plan(model): dropout1 / dropout2 / the FFN's inner dropout with rate drop['p'] (0: the fused epilogues)."""
+        p_drop, seed = (float(drop['p']), drop['seed']) if drop else (0.0, 0)
         Rp, d = x.shape
         R = B * S
         cd, H, F = self.cd, self.H, self.F
         dev = x.device
         use_tc = cd == torch.bfloat16 and d // H == 64
         cache = []
-        for L in self.layers:
+        for li, L in enumerate(self.layers):
             c = {}
             g1, b1, c['fold1'] = self._affine(L, 'norm1', stage)
             c['g1'] = g1
@@ -158,7 +202,12 @@ class StackTrainer:
             c['lse'] = torch.empty(B, H, S, device=dev, dtype=torch.float32) if (use_tc and self.save_lse) else None
             ops.attention_packed(c['qkv'][:R], c['o'][:R], B, S, H, mask_mode=mask_mode, x_lens=x_lens, kv_lens=kv_lens, use_tc=use_tc,
                                  lse=c['lse'])
-            _linear_fwd(c['o'][:R], L['o'], residual=x[:R], out=x[:R])
+            if p_drop > 0.0:        # x = x + dropout1(attn): the GEMM's residual epilogue cannot drop, so the add is its own kernel
+                t = _rows(Rp, d, R, dev, cd)
+                _linear_fwd(c['o'][:R], L['o'], out=t[:R])
+                ops.dropout_add_(x[:R], t[:R], p_drop, seed, 3 * li)
+            else:
+                _linear_fwd(c['o'][:R], L['o'], residual=x[:R], out=x[:R])
             g2, b2, c['fold2'] = self._affine(L, 'norm2', stage)
             c['g2'] = g2
             c['x_mid'] = x.clone()
@@ -168,13 +217,21 @@ class StackTrainer:
             _linear_fwd(c['h2'][:R], L['f1'], out=c['f_pre'][:R])
             c['f'] = _rows(Rp, F, R, dev, cd)
             ops.gelu_fwd(c['f_pre'], c['f'])
-            _linear_fwd(c['f'][:R], L['f2'], residual=x[:R], out=x[:R])
+            if p_drop > 0.0:
+                ops.dropout_(c['f'][:R], p_drop, seed, 3 * li + 1)          # the cached f is the dropped one: what linear_2 saw
+                t = _rows(Rp, d, R, dev, cd)
+                _linear_fwd(c['f'][:R], L['f2'], out=t[:R])
+                ops.dropout_add_(x[:R], t[:R], p_drop, seed, 3 * li + 2)
+            else:
+                _linear_fwd(c['f'][:R], L['f2'], residual=x[:R], out=x[:R])
             cache.append(c)
         return cache
 
-    def backward(self, dx: torch.Tensor, cache: list, B: int, S: int, *, mask_mode: int, x_lens, kv_lens) -> list[dict]:
+    def backward(self, dx: torch.Tensor, cache: list, B: int, S: int, *, mask_mode: int, x_lens, kv_lens,
+                 drop: dict | None = None, on_layer=None) -> list[dict]:
         """dx (Rp, d) fp32: gradient wrt the stack output, turned in place into the gradient wrt the stack input.
-        Returns per-layer parameter gradients (fp32)."""
+        Returns per-layer parameter gradients (fp32).  drop: the plan the forward ran with (same masks, recomputed)."""
+        p_drop, seed = (float(drop['p']), drop['seed']) if drop else (0.0, 0)
         Rp, d = dx.shape
         R = B * S
         cd, H = self.cd, self.H
@@ -184,21 +241,33 @@ class StackTrainer:
         for li in range(len(self.layers) - 1, -1, -1):
             L, c = self.layers[li], cache[li]
             g = {}
-            # ---- x_out = x_mid + f W2^T + b2 ----
-            ops.residual_layernorm(dx[:R], None, None, dxb[:R])                    # cast of the residual gradient
-            g['f2.b'] = ops.colsum(dx[:R])
+            # ---- x_out = x_mid + dropout2(f W2^T + b2) ----
+            if p_drop > 0.0:        # gradient of the dropped branch = dx through the same mask; dx itself flows on unchanged
+                dt = ops.dropout_(dx[:R].clone(), p_drop, seed, 3 * li + 2)
+                ops.residual_layernorm(dt, None, None, dxb[:R])
+                g['f2.b'] = ops.colsum(dt)
+            else:
+                ops.residual_layernorm(dx[:R], None, None, dxb[:R])                # cast of the residual gradient
+                g['f2.b'] = ops.colsum(dx[:R])
             g['f2.w'] = _wgrad(dxb, c['f'], R)                                     # (d, F)
             df = _rows(Rp, self.F, R, dev, cd)
             _dgrad(dxb[:R], L['f2'], df[:R])                                       # (R, F)
+            if p_drop > 0.0:
+                ops.dropout_(df[:R], p_drop, seed, 3 * li + 1)                     # through the FFN's inner dropout
             dpre = ops.gelu_bwd(c['f_pre'], df, df)                                # in place
             g['f1.b'] = ops.colsum(dpre[:R])
             g['f1.w'] = _wgrad(dpre, c['h2'], R)                                   # (F, d)
             dh = _rows(Rp, d, R, dev, cd)
             _dgrad(dpre[:R], L['f1'], dh[:R])
             g['n2.g'], g['n2.b'] = ops.layernorm_bwd(c['x_mid'][:R], c['g2'], dh[:R], dx[:R], L['norm2']['eps'])
-            # ---- x_mid = x_in + o Wo^T + bo ----
-            ops.residual_layernorm(dx[:R], None, None, dxb[:R])
-            g['o.b'] = ops.colsum(dx[:R])
+            # ---- x_mid = x_in + dropout1(o Wo^T + bo) ----
+            if p_drop > 0.0:
+                dt = ops.dropout_(dx[:R].clone(), p_drop, seed, 3 * li)
+                ops.residual_layernorm(dt, None, None, dxb[:R])
+                g['o.b'] = ops.colsum(dt)
+            else:
+                ops.residual_layernorm(dx[:R], None, None, dxb[:R])
+                g['o.b'] = ops.colsum(dx[:R])
             g['o.w'] = _wgrad(dxb, c['o'], R)                                      # (d, d)
             do = _rows(Rp, d, R, dev, cd)
             _dgrad(dxb[:R], L['o'], do[:R])
@@ -211,6 +280,8 @@ class StackTrainer:
             g['fold1'], g['fold2'] = c['fold1'], c['fold2']
             grads[li] = g
             cache[li] = None                                                        # release the layer's activations
+            if on_layer is not None:
+                on_layer(li, g)                                                     # e.g. start this layer's gradient all-reduce
         return grads
 
 
@@ -245,7 +316,7 @@ def _layer_param_grads(prefix: str, layer_mod, g: dict, norm: str, out: dict, st
 
 
 @torch.no_grad()
-def ar_loss_and_grads(model, batch: dict, precision: str):
+def ar_loss_and_grads(model, batch: dict, precision: str, drop: dict | None = None):
     """ValleAR.training_step (valle_ar.py:43-90): returns (loss scalar tensor, {param name: grad})."""
     cfg, dev = model.config, model.device
     cd = _cd(precision)
@@ -265,9 +336,11 @@ def ar_loss_and_grads(model, batch: dict, precision: str):
     x = torch.zeros(Rp, d, device=dev, dtype=torch.float32)
     ops.embed_sum_pe(tok_i, tok_table, pe_t, x, out_rows_per_batch=S)
     ops.embed_sum_pe(cod_i, aud_table, pe_a, x, out_rows_per_batch=S, out_row_offset=Tx)
+    if drop and drop['pe_p'] > 0.0:
+        ops.dropout_(x[:R], drop['pe_p'], drop['seed'], SITE_PE)                     # PositionalEncoding.dropout (modules.py:78)
     xl = torch.full((B,), Tx, device=dev, dtype=torch.int32)
     kv_lens = (xl + _i32(codes_lens, dev)).contiguous()
-    cache = tr.forward(x, B, S, mask_mode=MASK_PREFIX_LM, x_lens=xl, kv_lens=kv_lens)
+    cache = tr.forward(x, B, S, mask_mode=MASK_PREFIX_LM, x_lens=xl, kv_lens=kv_lens, drop=drop)
     # logits over the audio rows (valle_ar.py:80-83), mean CE over every position incl. padding (K-5)
     Ra, Rap = B * Ty, _pad8(B * Ty)
     rows = x[:R].view(B, S, d)[:, Tx:].reshape(Ra, d).contiguous()
@@ -289,20 +362,34 @@ def ar_loss_and_grads(model, batch: dict, precision: str):
     _dgrad(dl[:Ra], proj, dh[:Ra])
     dx = torch.zeros(Rp, d, device=dev, dtype=torch.float32)
     dx[:R].view(B, S, d)[:, Tx:] = dh[:Ra].view(B, Ty, d).float()                   # scatter into the audio rows (plumbing)
-    lg = tr.backward(dx, cache, B, S, mask_mode=MASK_PREFIX_LM, x_lens=xl, kv_lens=kv_lens)
-    for li, g in enumerate(lg):
-        _layer_param_grads(f'transformer.layers.{li}.', model.transformer.layers[li], g, cfg.norm, grads, None)
+    reducer = parallel.active_reducer()
+
+    def layer_done(li, g):
+        out = {}
+        _layer_param_grads(f'transformer.layers.{li}.', model.transformer.layers[li], g, cfg.norm, out, None)
+        grads.update(out)
+        if reducer is not None:
+            reducer.submit(li, out)          # the layer's all-reduce starts while the layers below are differentiated
+
+    if reducer is not None:
+        reducer.begin()
+    tr.backward(dx, cache, B, S, mask_mode=MASK_PREFIX_LM, x_lens=xl, kv_lens=kv_lens, drop=drop, on_layer=layer_done)
+    if drop and drop['pe_p'] > 0.0:
+        ops.dropout_(dx[:R], drop['pe_p'], drop['seed'], SITE_PE)
     gt = torch.zeros_like(tok_table)
     ga = torch.zeros_like(aud_table)
     ops.embed_bwd(tok_i, dx, gt, rows_per_batch=S)
     ops.embed_bwd(cod_i, dx, ga, rows_per_batch=S, row_offset=Tx)
     grads['tokens_emb.word_embeddings.weight'] = gt[0]
     grads['audio_emb.word_embeddings.weight'] = ga[0]
+    if reducer is not None:
+        reducer.submit(len(tr.layers), grads)      # the remaining parameters (embeddings, proj)
+        grads = reducer.finish()
     return loss, grads
 
 
 @torch.no_grad()
-def nar_loss_and_grads(model, batch: dict, layer: int, precision: str):
+def nar_loss_and_grads(model, batch: dict, layer: int, precision: str, drop: dict | None = None):
     """ValleNAR.training_step for a fixed stage ``layer`` (valle_nar.py:53-105 with repairs A-1..A-3, A-4 kept)."""
     cfg, dev = model.config, model.device
     cd = _cd(precision)
@@ -323,7 +410,9 @@ def nar_loss_and_grads(model, batch: dict, layer: int, precision: str):
     x = torch.zeros(Rp, d, device=dev, dtype=torch.float32)
     ops.embed_sum_pe(tok_i, tok_table, pe_t, x, out_rows_per_batch=S)
     ops.embed_sum_pe(cod_i, code_tables, pe_a, x, t_split=prefix_len, nq_a=Q, nq_b=layer, out_rows_per_batch=S, out_row_offset=Tx)
-    cache = tr.forward(x, B, S, mask_mode=MASK_NONE, x_lens=None, kv_lens=None, stage=layer - 1)   # padding ignored (A-4)
+    if drop and drop['pe_p'] > 0.0:
+        ops.dropout_(x[:R], drop['pe_p'], drop['seed'], SITE_PE)
+    cache = tr.forward(x, B, S, mask_mode=MASK_NONE, x_lens=None, kv_lens=None, stage=layer - 1, drop=drop)   # padding ignored (A-4)
     Tt = T - prefix_len
     Ra, Rap = B * Tt, _pad8(B * Tt)
     rows = x[:R].view(B, S, d)[:, Tx + prefix_len:].reshape(Ra, d).contiguous()
@@ -345,17 +434,36 @@ def nar_loss_and_grads(model, batch: dict, layer: int, precision: str):
     _dgrad(dl[:Ra], proj, dh[:Ra])
     dx = torch.zeros(Rp, d, device=dev, dtype=torch.float32)
     dx[:R].view(B, S, d)[:, Tx + prefix_len:] = dh[:Ra].view(B, Tt, d).float()
-    lg = tr.backward(dx, cache, B, S, mask_mode=MASK_NONE, x_lens=None, kv_lens=None)
     stage_key = f'stage_embs.{layer - 1}.word_embeddings.weight'
-    for li, g in enumerate(lg):
-        _layer_param_grads(f'transformer.layers.{li}.', model.transformer.layers[li], g, cfg.norm, grads, stage_key)
+    reducer = parallel.active_reducer()
+
+    def layer_done(li, g):
+        out = {}
+        _layer_param_grads(f'transformer.layers.{li}.', model.transformer.layers[li], g, cfg.norm, out, stage_key)
+        de = out.pop(stage_key, None)              # the stage embedding collects a term from every AdaLN: last bucket
+        if de is not None:
+            grads[stage_key] = grads.get(stage_key, 0) + de
+        grads.update(out)
+        if reducer is not None:
+            reducer.submit(li, out)
+
+    if reducer is not None:
+        reducer.begin()
+    tr.backward(dx, cache, B, S, mask_mode=MASK_NONE, x_lens=None, kv_lens=None, drop=drop, on_layer=layer_done)
+    if drop and drop['pe_p'] > 0.0:
+        ops.dropout_(dx[:R], drop['pe_p'], drop['seed'], SITE_PE)
     gt = torch.zeros_like(tok_table)
     gc = torch.zeros_like(code_tables)
     ops.embed_bwd(tok_i, dx, gt, rows_per_batch=S)
     ops.embed_bwd(cod_i, dx, gc, t_split=prefix_len, nq_a=Q, nq_b=layer, rows_per_batch=S, row_offset=Tx)
     grads['tokens_emb.word_embeddings.weight'] = gt[0]
     for q in range(Q):
-        grads[f'codes_embs.{q}.word_embeddings.weight'] = gc[q]
+        # a table contributes when its codebook is summed somewhere: all Q over the prompt prefix, the first `layer` over the rest
+        if q < layer or prefix_len > 0:
+            grads[f'codes_embs.{q}.word_embeddings.weight'] = gc[q]
+    if reducer is not None:
+        reducer.submit(len(tr.layers), grads)
+        grads = reducer.finish()
     return loss, grads
 
 
