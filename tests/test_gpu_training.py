@@ -402,10 +402,14 @@ def test_ar_training_step_with_dropout_equals_reference_with_the_same_masks(tmp_
         rcfg = valle.config.ConfigValle(dropout=0.1, ckpt_path=tmp_path / 'rc', log_path=tmp_path / 'rl', **fields)
         ref = valle.models.ValleAR(rcfg)
         ref.load_state_dict(sd, strict=True)
+        ref.eval()
+        with torch.no_grad():
+            loss_eval_mode = float(ref.training_step(batch))        # nothing dropped
         ref.train()
         pe = masks['pe'].view(B, S, -1)
-        ref.tokens_position_emb.dropout = _MaskMul(pe[:, :Tx])
-        ref.audio_position_emb.dropout = _MaskMul(pe[:, Tx:])
+        # the reference's PositionalEncoding drops in its (T, B, C) layout (modules.py:76-78)
+        ref.tokens_position_emb.dropout = _MaskMul(pe[:, :Tx].transpose(0, 1))
+        ref.audio_position_emb.dropout = _MaskMul(pe[:, Tx:].transpose(0, 1))
         for li, layer in enumerate(ref.transformer.layers):
             layer.dropout1 = _MaskMul(masks[f'{li}.attn'].view(B, S, -1))
             layer.ffn.dropout = _MaskMul(masks[f'{li}.ffn_inner'].view(B, S, -1))
@@ -413,9 +417,7 @@ def test_ar_training_step_with_dropout_equals_reference_with_the_same_masks(tmp_
         ref_loss = ref.training_step(batch)
         ref_loss.backward()
         ref_grads = {n: p.grad.clone() for n, p in ref.named_parameters()}
-        ref.eval()
-        with torch.no_grad():
-            loss_eval_mode = float(ref.training_step(batch))
+        ref_loss = float(ref_loss.detach())
     finally:
         ref_shims.release_reference()
     assert abs(float(ref_loss) - loss_eval_mode) > 1e-3                 # the masks do change the step
