@@ -398,7 +398,8 @@ def train_step_dp(args, dev, tmp, world: int, pk: dict) -> dict:
     red = parallel.GradReducer(model)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     out = {}
-    for label, reducer in (('local_ms_per_step', None), ('overlapped_allreduce_ms_per_step', red)):
+    # each variant twice, alternating (the first timed loop of a process also pays allocator growth); the smaller time counts
+    for label, reducer in (('local_ms_per_step', None), ('overlapped_allreduce_ms_per_step', red)) * 2:
         for it in range(6):
             if it == 3:
                 torch.distributed.barrier()
@@ -414,7 +415,7 @@ def train_step_dp(args, dev, tmp, world: int, pk: dict) -> dict:
         torch.cuda.synchronize()
         t = torch.tensor([e0.elapsed_time(e1) / 3], device=dev)
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
-        out[label] = float(t.item())
+        out[label] = min(out.get(label, 1e30), float(t.item()))
     n_grad = sum(p.numel() for p in model.parameters())
     out.update({'workload': 'BASELINE configs[4] per-GPU share: ValleAR.training_step, 16 clips x (225 + 1126) positions per GPU, forward + '
                             'backward, no optimizer step', 'global_batch': Bt * world, 'gradient_bytes_fp32': n_grad * 4,

@@ -110,6 +110,7 @@ class GradReducer:
         dev = next(model.parameters()).device
         self.names = [n for b in self.buckets for n, _ in b]
         n_total = sum(p.numel() for b in self.buckets for _, p in b)
+        n_total = (n_total + 3) // 4 * 4            # the flag vector starts 16-byte aligned
         self.flat = torch.zeros(n_total + len(self.names), device=dev, dtype=torch.float32)
         self.views, self.ranges, self.bucket_of = {}, [], {}
         off = 0
@@ -125,26 +126,33 @@ class GradReducer:
         self.ranges[-1] = (self.ranges[-1][0], self.flat.numel())       # the flags travel with the last bucket
         self._work, self._submitted = [], set()
         self.avg_op = dist.ReduceOp.AVG if (self.ws > 1 and dist.get_backend() == 'nccl') else None
+        self.no_comm = False                    # measurement aid (tools/train_dp_probe.py): bucket copies without the collectives
 
     def begin(self) -> None:
-        self.flags.zero_()
+        self._has = [0.0] * len(self.names)
         self._work, self._submitted = [], set()
 
     def _reduce(self, bi: int) -> None:
         lo, hi = self.ranges[bi]
-        if self.ws > 1:
+        if self.ws > 1 and not self.no_comm:
             self._work.append(dist.all_reduce(self.flat[lo:hi], op=self.avg_op or dist.ReduceOp.SUM, async_op=True))
 
     def submit(self, bucket: int, grads: dict) -> None:
         """Gradients of one finished bucket ({parameter name: tensor or None}); missing names count as 'no gradient'."""
         assert bucket not in self._submitted, f'bucket {bucket} submitted twice'
+        dst, src = [], []
         for name, _ in self.buckets[bucket]:
             g = grads.get(name)
             if g is None:
                 self.views[name].zero_()
             else:
-                self.views[name].copy_(g.reshape(self.views[name].shape))
-                self.flags[self.flag_index[name]] = 1.0
+                dst.append(self.views[name])
+                src.append(g.reshape(self.views[name].shape))
+                self._has[self.flag_index[name]] = 1.0
+        if dst:
+            torch._foreach_copy_(dst, src)          # one multi-tensor copy per bucket
+        if bucket == len(self.buckets) - 1:         # the flags travel with the last bucket (one small H2D copy per step)
+            self.flags.copy_(torch.tensor(self._has, dtype=torch.float32), non_blocking=True)
         self._submitted.add(bucket)
         self._reduce(bucket)
 
@@ -153,9 +161,8 @@ class GradReducer:
         assert len(self._submitted) == len(self.buckets), 'not every bucket was submitted'
         for w in self._work:
             w.wait()
-        if self.ws > 1 and self.avg_op is None:         # gloo has no AVG: sum, then divide (the flags stay sums)
-            n_params = self.flat.numel() - len(self.names)
-            self.flat[:n_params].div_(self.ws)
+        if self.ws > 1 and self.avg_op is None and not self.no_comm:    # gloo has no AVG: sum, then divide (the flags stay sums)
+            self.flat[:self.flat.numel() - len(self.names)].div_(self.ws)
         self._work = []
         return dict(self.views)
 
