@@ -120,7 +120,7 @@ enum { VB_FLAG_LATE_TRIGGER = 1, VB_FLAG_PREFETCH_KV = 2, VB_FLAG_ATTN_SIMT = 4,
 int vb_linear_decode(const void* x, int64_t ldx, const void* w, int64_t ldw, float* part, int64_t part_stride,
                      int64_t M, int64_t N, int64_t K, int max_split, int flags, int* n_split_out, void* stream);
 
-/* Decode-shape linear layer in "rows" form (csrc/gemm_decode_mma.cu), M <= 32, K % 256 == 0, x and w bf16:
+/* Decode-shape linear layer in "rows" form (csrc/gemm_decode_mma.cu), M <= 16, K % 256 == 0, x and w bf16:
  *   y[M][N] = epilogue(x[M][K] . w[N][K]^T)   -- the whole K of an output element stays inside one CTA when K <= 1024, so
  *   bias / erf-GELU / the residual add run in the epilogue and no reduce kernel follows (modules.py:146, :171+:274,
  *   :220-221, :278; valle_ar.py:158).  Weights stream HBM -> registers in mma.sync fragment order before the kernel waits

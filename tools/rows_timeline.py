@@ -9,7 +9,7 @@ sys.path.insert(0, '.')
 from valle2_b200 import _lib, ops  # noqa: E402
 
 dev, bf = 'cuda', torch.bfloat16
-B, d, F = int(sys.argv[1]) if len(sys.argv) > 1 else 32, 1024, 4096
+B, d, F = int(sys.argv[1]) if len(sys.argv) > 1 else 8, 1024, 4096      # rows kernels serve M <= 16
 
 lib = _lib.load()
 names = ['start', 'w requested', 'dep resolved', 'acts landed', 'mma done', 'summed', 'stored']

@@ -509,7 +509,7 @@ extern "C" int vb_linear_decode_rows(const void* x, int64_t ldx, const void* w, 
                                      int y_dtype, int64_t ldy, int64_t split_stride, int M, int64_t N, int64_t K, int epilogue,
                                      int want_split, int flags, int* n_split_out, void* stream) {
     VB_REQUIRE(x != nullptr && K > 0, VB_ERR_BAD_ARG, "vb_linear_decode_rows: bad args");
-    VB_REQUIRE(M <= 32, VB_ERR_UNSUPPORTED, "vb_linear_decode_rows: M = %d > 32 (use vb_linear_decode)", M);
+    VB_REQUIRE(M <= 16, VB_ERR_UNSUPPORTED, "vb_linear_decode_rows: M = %d > 16 (use vb_decode_gemm / vb_linear_decode)", M);
     VB_REQUIRE(K % 256 == 0, VB_ERR_UNSUPPORTED, "vb_linear_decode_rows: K = %lld is not a multiple of 256", (long long)K);
     VB_REQUIRE(ldx % 8 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0, VB_ERR_BAD_ARG,
                "vb_linear_decode_rows: x must be 16-byte aligned with a pitch that is a multiple of 8");
@@ -526,7 +526,7 @@ extern "C" int vb_linear_decode_rows(const void* x, int64_t ldx, const void* w, 
     p.ldx = ldx;
     const int nt = n8_tiles_per_cta(N, n_split, kc);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    return M <= 16 ? launch_rows_n<1, 0>(p, nt, n_split, st) : launch_rows_n<2, 0>(p, nt, n_split, st);
+    return launch_rows_n<1, 0>(p, nt, n_split, st);   // one m16 tile; 17..32 rows (a second m16 tile) measured slower than the tcgen05 forms
 }
 
 extern "C" int vb_linear_decode_rows_ln(const float* x, int64_t ldx, const float* gamma, const float* beta, float eps,

@@ -521,10 +521,12 @@ class ARDecoder:
 
     # ------------------------------------------------------------------------------------------
     @torch.no_grad()
-    def prefill(self, tokens: torch.Tensor, codes: torch.Tensor, *, x_lens=None, code_lens=None, max_new: int):
+    def prefill(self, tokens: torch.Tensor, codes: torch.Tensor, *, code_lens=None, max_new: int):
         """tokens (B,Tx), codes (B,P) incl. BOS.  Lays every sequence out as [text | audio] with the audio part
-        starting at column Tx (the reference's layout, valle_ar.py:147); ragged batches pass x_lens / code_lens
-        (then text padding between x_lens[b] and Tx is attended exactly like the reference does, K-4)."""
+        starting at column Tx (the reference's layout, valle_ar.py:147).  Ragged PROMPTS pass code_lens.  Ragged TEXT has no
+        length argument on purpose: the reference never masks text padding (SURVEY K-4: padded phoneme positions, token id 0,
+        are attended), so a batch of utterances with different text lengths is decoded with its padding attended, exactly as
+        the reference's teacher-forced step does; callers who want per-utterance text masking must batch equal lengths."""
         dev = self.device
         B, Tx = tokens.shape
         P = codes.shape[1]

@@ -5,7 +5,9 @@ Parameters are ordinary fp32 ``nn.Parameter`` s, so checkpoints interchange with
 run the CUDA kernels in the precision selected by ``valle2_b200.set_precision`` ('bf16' default, 'fp32' validation);
 inputs must live on a CUDA device -- there is no CPU path.  These module-level entry points keep the reference's
 materialised-mask API (``merge_masks`` etc.); the fast generation paths in ``engine.py`` never materialise a mask.
-Forward only: the kernels are not differentiable yet (training backward is the next scope row).
+These module-level forwards are INFERENCE entry points: they do not build an autograd graph (inputs are detached; an input
+that requires grad raises instead of silently yielding partial gradients).  Training goes through
+``ValleAR.training_step`` / ``ValleNAR.training_step``, whose forward AND backward run on the CUDA stack (valle2_b200/train.py).
 """
 from __future__ import annotations
 
@@ -18,6 +20,12 @@ import valle2_b200
 
 from .. import ops
 from ..config import ConfigValle
+
+
+def _inference_only(x: torch.Tensor, who: str) -> None:
+    if torch.is_grad_enabled() and x.requires_grad:
+        raise RuntimeError(f'{who}.forward is an inference entry point and does not back-propagate into its input; '
+                           'use ValleAR.training_step / ValleNAR.training_step (hand-written backward) for gradients')
 
 
 def _compute_dtype() -> torch.dtype:
@@ -124,6 +132,7 @@ class AdaptiveLayerNorm(nn.Module):
 
     def forward(self, x: torch.Tensor, embedding: torch.Tensor) -> torch.Tensor:
         d = self.d_model
+        _inference_only(x, type(self).__name__)
         e = embedding.detach().float().reshape(-1, d).contiguous()
         assert e.shape[0] == 1, 'stage embedding must be (1, d_model) (valle_nar.py:35,95,153)'
         wb = ops.linear(e, _cache.get(self.project_layer.weight, torch.float32),
@@ -163,6 +172,7 @@ class MultiHeadAttention(nn.Module):
         B, n, d = x.shape
         H, Dh = self.n_heads, self.head_dim
         cd = _compute_dtype()
+        _inference_only(x, type(self).__name__)
         xr = _rows(x.detach(), cd)
         qkv = ops.linear(xr, _cache.get(self.qkv.weight, cd)).view(B, n, 3, H, Dh)
         q = qkv[:, :, 0].permute(0, 2, 1, 3)
@@ -214,6 +224,7 @@ class FeedForward(nn.Module):
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         cd = _compute_dtype()
+        _inference_only(x, type(self).__name__)
         xr = _rows(x.detach(), cd)
         h = ops.linear(xr, _cache.get(self.linear_1.weight, cd), _cache.get(self.linear_1.bias, torch.float32), gelu=True)
         y = ops.linear(h, _cache.get(self.linear_2.weight, cd), _cache.get(self.linear_2.bias, torch.float32),
