@@ -354,6 +354,14 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     }
     if rank == 0:
         result['roofline'] = attention_roofline(eng, ops, int(round(MEAN_CTX)), pk, None)
+        if phases.get('ar_prefill_ms'):
+            # AR prompt prefill of this rank's shard (tensor-core bound): 2 x params x tokens + attention, SURVEY 8d (120.5 GFLOP / sequence)
+            S0, d_, F_, L_ = TX + P0, 1024, 4096, 12
+            fl = n_local * (L_ * (S0 * 2 * (4 * d_ * d_ + 2 * d_ * F_) + 4 * S0 * S0 * d_))
+            result['e2e']['ar_prefill'] = {'sequences': n_local, 'positions': S0, 'ms': phases['ar_prefill_ms'],
+                                           'tflops': fl / (phases['ar_prefill_ms'] * 1e-3) / 1e12,
+                                           'frac_of_bf16_sustained_peak': fl / (phases['ar_prefill_ms'] * 1e-3) / 1e12 / pk['bf16_tflops_sustained'],
+                                           'note': 'prefix-LM mask not discounted; includes KV scatter into the page pool and the first token'}
 
     # ---- BASELINE configs[1] on every rank: AR decode, batch 32 per GPU (weak scaling) --------------------------
     if not args.no_extras:

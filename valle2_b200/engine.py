@@ -22,6 +22,25 @@ from . import ops
 from .ops import MASK_NONE, MASK_PREFIX_LM, PAGE
 
 
+_NVTX = os.environ.get('VALLE_B200_NVTX', '0') != '0'
+
+
+class _nvtx:
+    """NVTX range around a phase of the path (VALLE_B200_NVTX=1; off by default: no overhead in the timed loops)."""
+
+    def __init__(self, name: str):
+        self.name = name
+
+    def __enter__(self):
+        if _NVTX:
+            torch.cuda.nvtx.range_push(self.name)
+
+    def __exit__(self, *exc):
+        if _NVTX:
+            torch.cuda.nvtx.range_pop()
+        return False
+
+
 def _cdtype(precision: str) -> torch.dtype:
     return torch.bfloat16 if precision == 'bf16' else torch.float32
 
@@ -559,8 +578,9 @@ class ARDecoder:
         eos = -1 if ignore_eos else self.cfg.num_audio_tokens
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
         ev[0].record()
-        st = self.prefill(tokens, codes, code_lens=code_lens, max_new=max_new)
-        self.first_token(samp, None if uniforms is None else uniforms[0], eos)
+        with _nvtx('valle_b200.ar.prefill'):
+            st = self.prefill(tokens, codes, code_lens=code_lens, max_new=max_new)
+            self.first_token(samp, None if uniforms is None else uniforms[0], eos)
         ev[1].record()
         graph = None
         step = 1
@@ -583,6 +603,8 @@ class ARDecoder:
                 self._graph, self._graph_key = graph, gkey
         else:
             self._graph, self._graph_key = None, None
+        if _NVTX:
+            torch.cuda.nvtx.range_push('valle_b200.ar.decode')
         while step < max_new:
             if graph is not None:
                 graph.replay()
@@ -593,6 +615,8 @@ class ARDecoder:
             if not ignore_eos and (step % poll_every == 0):
                 if int(st['state'][:, 1].min().item()) >= 0:      # every sub-batch has seen all of its rows stop
                     break
+        if _NVTX:
+            torch.cuda.nvtx.range_pop()
         ev[2].record()
         self._phase_events = ev
         state = st['state'].tolist()
@@ -648,6 +672,8 @@ class NARDecoder:
         if target_lens is not None:
             kv_lens = (_i32(target_lens, dev) + (Tx + Tc)).contiguous()
         for n in range(1, Q):
+            if _NVTX:
+                torch.cuda.nvtx.range_push(f'valle_b200.nar.stage{n}')
             ops.embed_sum_pe(tok_i, self.tok_table, self.pe_t, x, out_rows_per_batch=S, out_row_offset=0)
             ops.embed_sum_pe(ids, self.code_tables, self.pe_a, x, t_split=Tc, nq_a=Q, nq_b=n,
                              out_rows_per_batch=S, out_row_offset=Tx)
@@ -669,5 +695,7 @@ class NARDecoder:
                 ops.sample(logits, 1, 0, V, B * T, V, temperature=temperature, top_k=0, top_p=1.0, out_tok=sampled,
                            seed=seed, step_ptr=step)
             ids[:, Tc:, n] = sampled.view(B, T)
+            if _NVTX:
+                torch.cuda.nvtx.range_pop()
         out = ids[:, Tc:].long()
         return (out, trace) if return_logits else out
