@@ -84,6 +84,12 @@ __global__ void __launch_bounds__(THREADS, 1) decode_gemm_kernel(const __grid_co
     constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
     constexpr uint32_t IDESC = umma_idesc_bf16(BM, BN, 0, 0);
     constexpr int MAXI = 2;                     // epilogue work items per thread whose operands are prefetched
+    // ALIAS (BN >= 64): the receive buffer of the exchange lives INSIDE the operand ring, so that two CTAs fit per SM and the
+    // next kernel's CTAs (and their weight prefetch) can be resident while this one runs -- at batch 64 a separate buffer made
+    // every launch start 6 us late (tools/dg_timeline.py 64).  Price: nobody may push before EVERY CTA of the cluster has finished
+    // its MMAs (phase 1 of the cluster barrier moves behind the accumulator), a few 100 ns of skew; not worth it at BN <= 32.
+    constexpr bool ALIAS = CLUSTER && BN >= 64;
+    constexpr int STG_BYTES = 4 * 32 * 32 * 4;  // the epilogue warps' transpose staging at the start of the ring
     // ONE kernel serves the four epilogue modes (run-time switch): the GEMMs of a layer alternate between them, and a shared
     // function keeps its code in the instruction caches (one kernel per mode measured +0.4 us per launch, tools/dg_timeline.py)
     const bool IS_LN = (p.mode == VB_DG_LN || p.mode == VB_DG_LN_GELU), IS_RES = (p.mode == VB_DG_RESIDUAL);
@@ -98,7 +104,7 @@ __global__ void __launch_bounds__(THREADS, 1) decode_gemm_kernel(const __grid_co
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
     float* s_stage = reinterpret_cast<float*>(smem_al);                      // transpose staging: aliases the operand ring
-    float* s_recv = reinterpret_cast<float*>(smem_al + RING_BYTES);          // CLUSTER: [n_split][rows_per_split][128]
+    float* s_recv = reinterpret_cast<float*>(smem_al + (ALIAS ? STG_BYTES : RING_BYTES));   // CLUSTER: [n_split][rows_per_split][128]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tile = CLUSTER ? blockIdx.x / p.n_split : blockIdx.x % p.tiles;
     const int split = CLUSTER ? blockIdx.x % p.n_split : blockIdx.x / p.tiles;
@@ -122,7 +128,7 @@ __global__ void __launch_bounds__(THREADS, 1) decode_gemm_kernel(const __grid_co
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_slot;
     if (threadIdx.x == 0) DG_STAMP(0);
-    if constexpr (CLUSTER) cluster_arrive();     // phase 1: every CTA of the cluster is running (waited for before the pushes)
+    if constexpr (CLUSTER && !ALIAS) cluster_arrive();   // phase 1: every CTA of the cluster is running (waited for before the pushes)
 
     // the epilogue's share of the tile after the exchange: ALL 128 weight rows x batch rows [b_lo, b_hi)
     const int b_lo = min(p.M, split * p.rows_per_split), b_hi = min(p.M, b_lo + p.rows_per_split);
@@ -161,6 +167,7 @@ __global__ void __launch_bounds__(THREADS, 1) decode_gemm_kernel(const __grid_co
             }
         } else if (p.late_trigger) { pdl_wait(); pdl_trigger(); }
         __syncwarp();
+        if constexpr (ALIAS) cluster_arrive();
         if constexpr (CLUSTER) cluster_wait();                // phase 1 (every thread pairs each arrive with a wait)
     } else if (warp == 1) {
         if (p.late_trigger) { pdl_wait(); pdl_trigger(); }
@@ -185,6 +192,7 @@ __global__ void __launch_bounds__(THREADS, 1) decode_gemm_kernel(const __grid_co
             DG_STAMP(4);
         }
         __syncwarp();
+        if constexpr (ALIAS) cluster_arrive();
         if constexpr (CLUSTER) cluster_wait();                // phase 1
     } else {
         // ------------------------------------------------------------------ epilogue warps, part 1 -----
@@ -242,6 +250,7 @@ __global__ void __launch_bounds__(THREADS, 1) decode_gemm_kernel(const __grid_co
         mbar_wait(smem_u32(&tfull_bar), 0);
         if (et == 0) DG_STAMP(5);
         tc_fence_after();
+        if constexpr (ALIAS) cluster_arrive();                // ALIAS: phase 1 = every CTA's accumulator is complete, its ring is free
         if constexpr (CLUSTER) cluster_wait();                // phase 1 complete: remote shared memory may be written
         {
             const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
@@ -462,7 +471,9 @@ int cluster_max() { cluster_enabled(); const char* e = getenv("VALLE_B200_DG_CLU
 
 template <int BN, bool CLUSTER>
 int launch(const CUtensorMap& tw, const CUtensorMap& tx, const DecGemmParams& p, cudaStream_t st) {
-    constexpr int SMEM = STAGES * (BM * BK * 2 + BN * BK * 2) + 1024 + (CLUSTER ? recv_rows(BN) * BM * 4 : 0);
+    constexpr bool ALIAS = CLUSTER && BN >= 64;
+    static_assert(!ALIAS || 4 * 32 * 32 * 4 + recv_rows(BN) * BM * 4 <= STAGES * (BM * BK * 2 + BN * BK * 2), "receive buffer must fit in the ring");
+    constexpr int SMEM = STAGES * (BM * BK * 2 + BN * BK * 2) + 1024 + ((CLUSTER && !ALIAS) ? recv_rows(BN) * BM * 4 : 0);
     static bool configured = false;
     auto kern = decode_gemm_kernel<BN, CLUSTER>;
     if (!configured) {
