@@ -88,8 +88,36 @@ static PFN_encodeTiled get_encode() {
     return fn;
 }
 
+// Tensor maps are pure functions of (base, rows, cols, ld, box): the decode / NAR / training paths ask for the same few
+// hundred over and over (weights, fixed workspaces), so the encoded 128-byte descriptors are kept in a small direct-mapped
+// cache per thread instead of calling into the driver on every GEMM launch (~600 encodes per NAR request otherwise).
+namespace {
+struct TmapKey {
+    const void* base; int64_t rows, cols, ld; int box_rows, box_cols;
+    bool operator==(const TmapKey& o) const {
+        return base == o.base && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows && box_cols == o.box_cols;
+    }
+};
+struct TmapSlot { TmapKey key; CUtensorMap map; bool valid; };
+constexpr int kTmapSlots = 1024;
+thread_local TmapSlot g_tmap_cache[kTmapSlots];
+inline size_t tmap_hash(const TmapKey& k) {
+    uint64_t h = reinterpret_cast<uintptr_t>(k.base) * 0x9E3779B97F4A7C15ull;
+    h ^= (static_cast<uint64_t>(k.rows) * 0xBF58476D1CE4E5B9ull) ^ (static_cast<uint64_t>(k.cols) << 21) ^ (static_cast<uint64_t>(k.ld) << 42);
+    h ^= (static_cast<uint64_t>(k.box_rows) << 7) ^ static_cast<uint64_t>(k.box_cols);
+    h ^= h >> 29;
+    return static_cast<size_t>(h % kTmapSlots);
+}
+}  // namespace
+
 int vb_make_tmap_bf16_2d(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows,
                          int box_cols) {
+    const TmapKey key{base, rows, cols, ld, box_rows, box_cols};
+    TmapSlot& slot = g_tmap_cache[tmap_hash(key)];
+    if (slot.valid && slot.key == key) {
+        *map = slot.map;
+        return VB_OK;
+    }
     PFN_encodeTiled enc = get_encode();
     VB_REQUIRE(enc != nullptr, VB_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
     VB_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0 && (ld * 2) % 16 == 0, VB_ERR_BAD_ARG,
@@ -103,6 +131,9 @@ int vb_make_tmap_bf16_2d(CUtensorMap* map, const void* base, int64_t rows, int64
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     VB_REQUIRE(r == CUDA_SUCCESS, VB_ERR_CUDA, "cuTensorMapEncodeTiled(2d) failed: CUresult %d (rows=%lld cols=%lld ld=%lld box=%dx%d)",
                (int)r, (long long)rows, (long long)cols, (long long)ld, box_rows, box_cols);
+    slot.key = key;
+    slot.map = *map;
+    slot.valid = true;
     return VB_OK;
 }
 
