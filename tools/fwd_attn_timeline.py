@@ -13,7 +13,7 @@ lib = _lib.load()
 qkv = torch.randn(B * S, 3 * d, device='cuda').bfloat16()
 o = torch.empty(B * S, d, device='cuda', dtype=torch.bfloat16)
 n_cta = ((S + 127) // 128) * H * B
-dbg = torch.zeros(n_cta, 32, 4, device='cuda', dtype=torch.int64)
+dbg = torch.zeros(n_cta, 32, 8, device='cuda', dtype=torch.int64)
 for _ in range(2):
     ops.attention_packed(qkv, o, B, S, H, mask_mode=ops.MASK_NONE, x_lens=None, kv_lens=None, use_tc=True)
 _lib.check(lib.vb_attention_prefill_set_debug(dbg.data_ptr()), 'dbg')
@@ -24,17 +24,24 @@ t = dbg.cpu().numpy().astype(np.float64)
 nb = (S + 63) // 64
 extra = t[:, 31]
 t = t[:, :nb]
-keep = (t[:, :, 3] > 0).all(axis=1)
+keep = (t[:, :, 3] > 0).all(axis=1) & (t[:, :, 7] > 0).all(axis=1)
 full = t[keep]
 extra = extra[keep]
 print(f'{len(full)} CTAs with {nb} key blocks; cycles per phase (median over CTAs and blocks 2..{nb - 1}):')
 blk = full[:, 2:]
 prev = full[:, 1:-1, 3]
 print('  previous P written -> S ready      %6.0f' % np.median(blk[:, :, 0] - prev))
-print('  S ready -> row maximum known (pass 1) %6.0f' % np.median(blk[:, :, 1] - blk[:, :, 0]))
-print('  -> previous PV done (bar_o)         %6.0f' % np.median(blk[:, :, 2] - blk[:, :, 1]))
-print('  -> P written (pass 2 + stores)      %6.0f' % np.median(blk[:, :, 3] - blk[:, :, 2]))
+print('  S ready -> row maximum known       %6.0f' % np.median(blk[:, :, 1] - blk[:, :, 0]))
+print('  -> exp2 / pack done                 %6.0f' % np.median(blk[:, :, 2] - blk[:, :, 1]))
+print('  -> P written (buffer free + stores) %6.0f' % np.median(blk[:, :, 3] - blk[:, :, 2]))
 print('  whole block                         %6.0f' % np.median(blk[:, :, 3] - prev))
+print(' MMA warp (block j):')
+print('  P_j written (row thread) -> P_j seen by the MMA warp %6.0f' % np.median(blk[:, :, 6] - blk[:, :, 3]))
+print('  P_j seen -> P V_j issued + committed                 %6.0f' % np.median(blk[:, :, 7] - blk[:, :, 6]))
+print('  P V_{j-1} issued -> Q K_{j+1} operands/S buffer ready %6.0f' % np.median(full[:, 3:, 4] - full[:, 1:-2, 7]))
+print('  -> Q K_{j+1} issued + committed                       %6.0f' % np.median(full[:, 3:, 5] - full[:, 3:, 4]))
+print('  Q K_{j+1} issued -> S_{j+1} first read by the row thread %6.0f' % np.median(full[:, 3:, 0] - full[:, 3:, 5]))
+print('  MMA warp period per block (P V_j issued -> P V_{j+1} issued) %6.0f' % np.median(full[:, 2:, 7] - full[:, 1:-1, 7]))
 print('  CTA lifetime (first S ready -> last P written) median %.0f cycles' % np.median(full[:, -1, 3] - full[:, 0, 0]))
 print('  row-thread entry -> first S ready   %6.0f' % np.median(full[:, 0, 0] - extra[:, 0]))
 print('  last P written -> last PV done      %6.0f' % np.median(extra[:, 1] - full[:, -1, 3]))
