@@ -1,5 +1,6 @@
 """Per-key-block cycle timeline of the tcgen05 forward attention (one row thread per CTA), NAR shape B=64 S=900 H=16.
     python tools/fwd_attn_timeline.py"""
+import os
 import sys
 
 import numpy as np
@@ -22,29 +23,33 @@ _lib.check(lib.vb_attention_prefill_set_debug(None), 'dbg')
 torch.cuda.synchronize()
 t = dbg.cpu().numpy().astype(np.float64)
 nb = (S + 63) // 64
+thread = int(os.environ.get('VALLE_B200_FWD_DBG_THREAD', '64'))
+hh = (thread // 32 - 2) // 4            # which half stamped: 0 = even key blocks, 1 = odd
 extra = t[:, 31]
 t = t[:, :nb]
-keep = (t[:, :, 3] > 0).all(axis=1) & (t[:, :, 7] > 0).all(axis=1)
+mine = np.arange(hh, nb, 2)             # the stamping thread's blocks
+keep = (t[:, mine, 3] > 0).all(axis=1) & (t[:, :, 7] > 0).all(axis=1)
 full = t[keep]
 extra = extra[keep]
-print(f'{len(full)} CTAs with {nb} key blocks; cycles per phase (median over CTAs and blocks 2..{nb - 1}):')
-blk = full[:, 2:]
-prev = full[:, 1:-1, 3]
-print('  previous P written -> S ready      %6.0f' % np.median(blk[:, :, 0] - prev))
-print('  S ready -> row maximum known       %6.0f' % np.median(blk[:, :, 1] - blk[:, :, 0]))
-print('  -> exp2 / pack done                 %6.0f' % np.median(blk[:, :, 2] - blk[:, :, 1]))
-print('  -> P written (buffer free + stores) %6.0f' % np.median(blk[:, :, 3] - blk[:, :, 2]))
-print('  whole block                         %6.0f' % np.median(blk[:, :, 3] - prev))
-print(' MMA warp (block j):')
-print('  P_j written (row thread) -> P_j seen by the MMA warp %6.0f' % np.median(blk[:, :, 6] - blk[:, :, 3]))
-print('  P_j seen -> P V_j issued + committed                 %6.0f' % np.median(blk[:, :, 7] - blk[:, :, 6]))
-print('  P V_{j-1} issued -> Q K_{j+1} operands/S buffer ready %6.0f' % np.median(full[:, 3:, 4] - full[:, 1:-2, 7]))
-print('  -> Q K_{j+1} issued + committed                       %6.0f' % np.median(full[:, 3:, 5] - full[:, 3:, 4]))
-print('  Q K_{j+1} issued -> S_{j+1} first read by the row thread %6.0f' % np.median(full[:, 3:, 0] - full[:, 3:, 5]))
-print('  MMA warp period per block (P V_j issued -> P V_{j+1} issued) %6.0f' % np.median(full[:, 2:, 7] - full[:, 1:-1, 7]))
-print('  CTA lifetime (first S ready -> last P written) median %.0f cycles' % np.median(full[:, -1, 3] - full[:, 0, 0]))
-print('  row-thread entry -> first S ready   %6.0f' % np.median(full[:, 0, 0] - extra[:, 0]))
-print('  last P written -> last PV done      %6.0f' % np.median(extra[:, 1] - full[:, -1, 3]))
+row = full[:, mine]                      # [cta][own block][slot]
+print(f'{len(full)} CTAs with {nb} key blocks; row thread {thread} (half {hh}: blocks {hh}, {hh + 2}, ...); cycles, median over CTAs and its blocks 2..:')
+blk = row[:, 1:]
+prev = row[:, :-1, 3]
+print('  previous P written -> S ready                          %6.0f' % np.median(blk[:, :, 0] - prev))
+print('  S ready -> maximum known AND partner exponentials done %6.0f' % np.median(blk[:, :, 1] - blk[:, :, 0]))
+print('  -> exp2 / pack done                                    %6.0f' % np.median(blk[:, :, 2] - blk[:, :, 1]))
+print('  -> P written (tile free + stores + fence + arrive)     %6.0f' % np.median(blk[:, :, 3] - blk[:, :, 2]))
+print('  period of this half (two key blocks)                   %6.0f' % np.median(blk[:, :, 3] - prev))
+print(' MMA warp (block t):')
+pw = full[:, mine, 3]
+print('  P_t written (this row thread) -> P_t seen by the MMA warp %6.0f' % np.median(full[:, mine, 6][:, 1:] - pw[:, 1:]))
+print('  P_t seen -> P V_t issued + committed                      %6.0f' % np.median(full[:, 2:, 7] - full[:, 2:, 6]))
+print('  P V_{t-1} issued -> Q K_{t+2} operands + buffer ready     %6.0f' % np.median(full[:, 3:, 4] - full[:, :-3, 7]))
+print('  -> Q K_{t+2} issued + committed                           %6.0f' % np.median(full[:, 3:, 5] - full[:, 3:, 4]))
+print('  MMA warp period per block (P V_t issued -> P V_{t+1})     %6.0f' % np.median(full[:, 2:, 7] - full[:, 1:-1, 7]))
+print('  CTA lifetime (first S ready -> last P written) median %.0f cycles' % np.median(row[:, -1, 3] - row[:, 0, 0]))
+print('  row-thread entry -> first S ready   %6.0f' % np.median(row[:, 0, 0] - extra[:, 0]))
+print('  last P written -> last PV done      %6.0f' % np.median(extra[:, 1] - row[:, -1, 3]))
 print('  last PV done -> output stored       %6.0f' % np.median(extra[:, 2] - extra[:, 1]))
 print('  row-thread entry -> output stored   %6.0f cycles (%.1f us at 1.965 GHz)' % (np.median(extra[:, 2] - extra[:, 0]), np.median(extra[:, 2] - extra[:, 0]) / 1965))
 g = dbg.cpu().numpy()[:, 30].astype(np.int64)

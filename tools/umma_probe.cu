@@ -81,6 +81,84 @@ __global__ void __launch_bounds__(64) probe_kernel(int R, long long* out) {
     }
 }
 
+// TMEM read bandwidth: `active` warps (one per lane quadrant / SM sub-partition) each issue R x tcgen05.ld 32x32b.x32 (4 KB)
+__global__ void __launch_bounds__(128) ldtm_probe_kernel(int active, int R, long long* out, uint32_t* sink) {
+    __shared__ uint32_t tmem_slot;
+    const int warp = threadIdx.x >> 5;
+    if (warp == 0) tmem_alloc<512>(smem_u32(&tmem_slot));
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t t0 = tmem_slot + (static_cast<uint32_t>(warp * 32) << 16);
+    uint32_t acc = 0;
+    long long best = 1ll << 60;
+    if (warp < active) {
+        for (int rep = 0; rep < 5; ++rep) {
+            const long long c0 = clock64();
+            for (int i = 0; i < R; ++i) {
+                uint32_t v[32];
+                tmem_ld_32x32(t0 + (i & 7) * 32, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int k = 0; k < 32; ++k) acc ^= v[k];
+            }
+            const long long c1 = clock64();
+            if (c1 - c0 < best) best = c1 - c0;
+        }
+        if ((threadIdx.x & 31) == 0) out[blockIdx.x * 4 + warp] = best;
+        if (acc == 0x12345678u) sink[0] = acc;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        tmem_dealloc<512>(tmem_slot);
+    }
+}
+
+// MUFU.EX2 rate: `warps` warps per CTA (one CTA per SM), 8 independent chains of ex2 per thread
+__global__ void mufu_probe_kernel(int R, long long* out, float* sink) {
+    float x[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) x[k] = -0.001f * (threadIdx.x + k);
+    __syncthreads();
+    const long long c0 = clock64();
+    for (int i = 0; i < R; ++i) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(x[k]));
+    }
+    const long long c1 = clock64();
+    float a = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a += x[k];
+    if (a == 123.f) sink[0] = a;
+    if ((threadIdx.x & 31) == 0) out[blockIdx.x * 32 + (threadIdx.x >> 5)] = c1 - c0;
+}
+void run_mufu(int warps, long long* d_out, float* d_sink) {
+    const int R = 512;
+    mufu_probe_kernel<<<148, warps * 32>>>(R, d_out, d_sink);
+    cudaDeviceSynchronize();
+    std::vector<long long> h(148 * 32);
+    cudaMemcpy(h.data(), d_out, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+    long long mx = 0;
+    for (int i = 0; i < 148; ++i) for (int w = 0; w < warps; ++w) mx = h[i * 32 + w] > mx ? h[i * 32 + w] : mx;
+    printf("MUFU.EX2: %2d warps per SM: %.2f cycles per warp instruction per warp -> %.1f lanes/cycle/SM\n", warps,
+           static_cast<double>(mx) / (R * 8), warps * 32.0 * R * 8 / static_cast<double>(mx));
+}
+
+void run_ldtm(int active, long long* d_out, uint32_t* d_sink) {
+    const int R = 256;
+    ldtm_probe_kernel<<<148, 128>>>(active, R, d_out, d_sink);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { printf("ldtm probe: %s\n", cudaGetErrorString(e)); exit(1); }
+    std::vector<long long> h(148 * 4);
+    cudaMemcpy(h.data(), d_out, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+    long long mx = 0;
+    for (int i = 0; i < 148; ++i) for (int w = 0; w < active; ++w) mx = h[i * 4 + w] > mx ? h[i * 4 + w] : mx;
+    printf("tcgen05.ld 32x32b.x32 (4 KB per warp), %d warp(s) per SM: %.1f cycles per load (dependent: load, wait, consume) -> %.0f B/cycle/SM\n",
+           active, static_cast<double>(mx) / R, active * 4096.0 * R / static_cast<double>(mx));
+}
+
 template <int N, int MODE, int M = 128> void run(int grid, int R, long long* d_out) {
     const int smem = 16384 + 32768 + 1024;
     cudaFuncSetAttribute(probe_kernel<N, MODE, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -107,9 +185,13 @@ template <int MODE> void run_all(int grid, int R, long long* d_out) {
 
 int main() {
     long long* d_out;
-    cudaMalloc(&d_out, 1024 * sizeof(long long));
+    cudaMalloc(&d_out, 148 * 32 * sizeof(long long));
+    uint32_t* d_sink;
+    cudaMalloc(&d_sink, 64);
+    for (int active : {1, 2, 4}) run_ldtm(active, d_out, d_sink);
+    for (int warps : {1, 4, 8, 16}) run_mufu(warps, d_out, reinterpret_cast<float*>(d_sink));
     const int R = 512;
-    for (int grid : {1, 148}) {
+    for (int grid : {148}) {
         run_all<0>(grid, R, d_out);
         run_all<1>(grid, R, d_out);
         run_all<2>(grid, R, d_out);

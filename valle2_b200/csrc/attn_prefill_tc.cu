@@ -4,22 +4,21 @@
 // materialised (B,H,S,S) mask: the prefix-LM / padding predicate is evaluated from (x_len, kv_len) per element.
 //
 // CTA = 128 query rows of one (batch, head); key blocks of 64; 320 threads, two CTAs per SM.
-//   warp 0    TMA producer: Q tile once, then a 4-deep ring of K blocks and a 3-deep ring of V blocks (a block's operands must be
-//             requested > 1000 cycles ahead: with a 3-deep {K, V} ring the MMA warp waited ~500 cycles per block for them)
-//   warp 1    MMA issuer + TMEM allocator: QK_j (M128 N64 K64) into score buffer j%2, PV_j (M128 N64 K64; V is the MN-major
-//             B operand) accumulating into O in TMEM.  Issue order QK_0, QK_1, PV_0, QK_2, PV_1, ...
-//   warp 2-9  softmax, TWO threads per query row (warps w and w+4 share a TMEM lane quadrant; each takes 32 of the block's
-//             64 columns).  The kernel is bound by per-block latencies of the row threads (mbarrier wait ~90 cycles, TMEM
-//             load, proxy fence, arrive), not by any pipe -- twice the warps hide twice the latency, and a thread carries 32
-//             instead of 64 scores.  The halves exchange their row maxima through shared memory (one 64-thread named barrier).
-// Synchronisation per key block: the row threads wait for S_j and arrive once with P_j; everything else is implied by the
-// MMA issue order (tcgen05 operations of one thread complete in order):
-//   * S_j complete  =>  PV_{j-2} complete  =>  P buffer j%2 may be overwritten;
-//   * P_{j-1} seen by the MMA warp  =>  every row thread has read S_{j-1}  =>  QK_{j+1} may overwrite score buffer (j+1)%2.
-// O stays in TMEM: the softmax reference is raised lazily (only when a block maximum exceeds it by 2^8) and only then O is
-// rescaled.  exp2: in unmasked blocks POLY_OF_8 of every 8 score pairs take exp2 on the FMA pipe instead of MUFU (round-to-
-// nearest range reduction by the 1.5*2^23 trick, degree-3 minimax on [-0.5, 0.5]: 7.5e-5 relative error, far below the bf16
-// rounding of P).
+//   warp 0    TMA producer: Q tile once, then a 4-deep ring of K blocks and a 3-deep ring of V blocks
+//   warp 1    MMA issuer + TMEM allocator: QK_t (M128 N64 K64) into score buffer t%2, PV_t (M128 N64 K64; V is the MN-major B
+//             operand) accumulating into O in TMEM.  Issue order QK_0, QK_1, {QK_{t+2}, PV_t}.
+//   warp 2-5  softmax of the EVEN key blocks, one thread per query row (tcgen05.ld 32x32b gives a thread its whole row)
+//   warp 6-9  softmax of the ODD key blocks, same rows (warps w and w+4 share a TMEM lane quadrant and an SM sub-partition)
+// The kernel is bound by the MUFU pipe (64 exp2 per row and block = 512 pipe cycles against 256 tensor-pipe cycles) AND by the
+// per-block latencies of a row thread (mbarrier waits ~90 cycles each, TMEM load, proxy fence: ~800 cycles with the MUFU pipe
+// idle).  When all row warps of a sub-partition run their exponentials at the same time they queue on the pipe and then idle
+// together (measured: 45 % MUFU utilisation); so the two halves are kept in ANTI-PHASE by a ping-pong of named barriers: a warp
+// starts the exponentials of block t only when its partner has finished those of block t-1, and does its waits, loads, row
+// maximum and stores under the partner's exponentials.
+// The softmax reference m_ref is shared by the two halves and handed on in block order through shared memory (the ping-pong
+// barrier orders it); it is raised lazily -- only when a block maximum exceeds it by 2^8 -- and only then O (in TMEM) is rescaled
+// by the thread that raised it, so p = exp2(s - m_ref) <= 256 and no per-block traffic on O is needed.
+// exp2 offload (compile-time, off): POLY_OF_8 of every 8 score pairs on the FMA pipe (Cody-Waite + degree-3 minimax, 7.5e-5).
 // Replaces F.scaled_dot_product_attention + merge_masks on modules.py:160-167 for S > 1.
 #include <math.h>
 #include <stdlib.h>
@@ -35,15 +34,15 @@ namespace {
 constexpr int BQ = 128;    // query rows per CTA
 constexpr int BKV = 64;    // keys per block
 constexpr int DH = 64;
-constexpr int K_STAGES = 4;   // K blocks: a stage is free as soon as Q K_j^T has completed
-constexpr int V_STAGES = 3;   // V blocks: free after P_j V_j
+constexpr int K_STAGES = 4;   // K blocks: a stage is free as soon as Q K_t^T has completed
+constexpr int V_STAGES = 3;   // V blocks: free after P_t V_t
 constexpr int POLY_OF_8 = VB_FWD_POLY;
 constexpr int THREADS = 320;
 constexpr int Q_BYTES = BQ * DH * 2;          // 16 KB
 constexpr int KV_BYTES = BKV * DH * 2;        // 8 KB per K or V block
 constexpr int P_BYTES = BQ * BKV * 2;         // 16 KB
 constexpr int SMEM_BYTES = Q_BYTES + (K_STAGES + V_STAGES) * KV_BYTES + 2 * P_BYTES + 1024;
-constexpr int O_COL = 2 * BKV;                // score buffers: cols [0, 64), [64, 128); O: [128, 192)
+constexpr int O_COL = 2 * BKV;                // score buffers: cols [0, 64) even blocks, [64, 128) odd blocks; O: [128, 192)
 constexpr int TMEM_COLS = 256;
 
 // three-input maximum (FMNMX3 on sm_100)
@@ -75,21 +74,17 @@ __device__ __forceinline__ float2 poly_exp2(float2 x) {
                        __uint_as_float(__float_as_uint(p.y) + (__float_as_uint(r.y) << 23)));
 }
 
-// p = exp2(s * scale - m) for a thread's 32 scores, their sum, bf16 pack (pk[i] = columns 2i, 2i+1)
+// p = exp2(s * scale - m) for 32 scores of a row, their sum, bf16 pack (pk[i] = columns 2i, 2i+1)
 template <bool POLY>
-__device__ __forceinline__ float softmax_half_row(const uint32_t (&sv)[32], uint32_t (&pk)[16], float scale_log2e, float m_use) {
+__device__ __forceinline__ float softmax_32(const uint32_t (&sv)[32], uint32_t (&pk)[16], float scale_log2e, float m_use) {
     const float2 sc2 = make_float2(scale_log2e, scale_log2e), nm2 = make_float2(-m_use, -m_use);
     float2 rs_a = make_float2(0.f, 0.f), rs_b = make_float2(0.f, 0.f);
 #pragma unroll
     for (int c = 0; c < 32; c += 2) {
         const float2 t = __ffma2_rn(make_float2(__uint_as_float(sv[c]), __uint_as_float(sv[c + 1])), sc2, nm2);
         float2 pp;
-#ifdef VB_FWD_NOEXP      // timing experiment only: no exponential at all (wrong results)
-        pp = t;
-#else
         if (POLY && ((c >> 1) & 7) >= 8 - POLY_OF_8) pp = poly_exp2(t);
         else pp = make_float2(fast_exp2(t.x), fast_exp2(t.y));
-#endif
         if (c & 2) rs_b = __fadd2_rn(rs_b, pp);
         else rs_a = __fadd2_rn(rs_a, pp);
         pk[c >> 1] = pack_bf16x2(pp.x, pp.y);
@@ -98,9 +93,35 @@ __device__ __forceinline__ float softmax_half_row(const uint32_t (&sv)[32], uint
     return rs.x + rs.y;
 }
 
+__device__ __forceinline__ void tmem_ld_32x8(uint32_t taddr, uint32_t (&r)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_st_32x8(uint32_t taddr, const uint32_t (&r)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+}
 // shared-memory matrix descriptor (SWIZZLE_128B, SBO 1024) from its low word: start address >> 4 | LBO >> 4 << 16
 __device__ __forceinline__ uint64_t desc_from_lo(uint32_t lo) { return (static_cast<uint64_t>(0x40004040u) << 32) | lo; }
-__device__ __forceinline__ void pair_barrier(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+#ifdef VB_FWD_DEBUG_WAIT      // experiment build: a wait that does not complete reports where it is and traps
+#include <stdio.h>
+__device__ __forceinline__ void dbg_wait(uint32_t bar, uint32_t parity, int code, int t) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if (++spins > (1u << 17)) {
+            printf("attn_prefill wait %d stuck: cta (%d,%d,%d) thread %d block %d parity %u\n", code, blockIdx.x, blockIdx.y, blockIdx.z,
+                   threadIdx.x, t, parity);
+            __trap();
+        }
+    }
+}
+#define WAIT(bar, parity, code, t) dbg_wait(bar, parity, code, t)
+#else
+#define WAIT(bar, parity, code, t) mbar_wait(bar, parity)
+#endif
+// named barriers over the two warps of a pair (64 threads): full sync, or producer arrive / consumer sync
+__device__ __forceinline__ void pair_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ void pair_arrive(int id) { asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory"); }
 
 __global__ void __launch_bounds__(THREADS, 2) attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tm_q,
                                                                      const __grid_constant__ CUtensorMap tm_kv,
@@ -109,8 +130,9 @@ __global__ void __launch_bounds__(THREADS, 2) attn_prefill_tc_kernel(const __gri
                                                                      const int32_t* __restrict__ kv_lens, float scale_log2e,
                                                                      float* __restrict__ lse, long long* __restrict__ dbg, int dbg_thread) {
     extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t bar_q, bar_o, s_full[2], p_full[2], k_full[K_STAGES], k_empty[K_STAGES], v_full[V_STAGES], v_empty[V_STAGES];
-    __shared__ float xch[2][2][BQ];      // [block parity][column half][row]: the halves' row maxima (and, at the end, sums)
+    __shared__ __align__(8) uint64_t bar_q, bar_done, s_full[2], s_free[2], p_full[2], p_free[2];
+    __shared__ __align__(8) uint64_t k_full[K_STAGES], k_empty[K_STAGES], v_full[V_STAGES], v_empty[V_STAGES];
+    __shared__ float xch[2][BQ];      // [block parity][row]: softmax reference after that block (at the end: the halves' row sums)
     __shared__ uint32_t tmem_slot;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -138,10 +160,12 @@ __global__ void __launch_bounds__(THREADS, 2) attn_prefill_tc_kernel(const __gri
         tma_prefetch_desc(&tm_q);
         tma_prefetch_desc(&tm_kv);
         mbar_init(smem_u32(&bar_q), 1);
-        mbar_init(smem_u32(&bar_o), 1);
+        mbar_init(smem_u32(&bar_done), 1);
         for (int s = 0; s < 2; ++s) {
             mbar_init(smem_u32(&s_full[s]), 1);
-            mbar_init(smem_u32(&p_full[s]), 8);
+            mbar_init(smem_u32(&s_free[s]), 4);
+            mbar_init(smem_u32(&p_full[s]), 4);
+            mbar_init(smem_u32(&p_free[s]), 1);
         }
         for (int s = 0; s < K_STAGES; ++s) {
             mbar_init(smem_u32(&k_full[s]), 1);
@@ -199,95 +223,115 @@ __global__ void __launch_bounds__(THREADS, 2) attn_prefill_tc_kernel(const __gri
             const uint32_t k_lo = ((k_smem & 0x3ffffu) >> 4) | (1u << 16);
             const uint32_t v_lo = ((v_smem & 0x3ffffu) >> 4) | (64u << 16);
             const uint32_t p_lo = ((p_smem & 0x3ffffu) >> 4) | (1u << 16);
-            // MMA-warp stamps (debug buffer slots 4..7 of a block): {K/V stage ready, Q K^T issued, P ready, P V issued}
-            mbar_wait(smem_u32(&bar_q), 0);
-            int pv_stage = 0;
-            uint32_t pv_phase = 0;
-            auto issue_pv = [&](int jj) {
-                const int pb = jj & 1;
-                mbar_wait(smem_u32(&v_full[pv_stage]), pv_phase);
-                mbar_wait(smem_u32(&p_full[pb]), (jj >> 1) & 1);
+            // MMA-warp stamps (debug buffer slots 4..7 of block t): {operands + score buffer ready, Q K^T issued, P ready, P V issued}
+            WAIT(smem_u32(&bar_q), 0, 1, 0);
+            int stage = 0, pv_stage = 0;
+            uint32_t phase = 0, pv_phase = 0;
+            auto issue_qk = [&](int t) {
+                WAIT(smem_u32(&k_full[stage]), phase, 2, t);
+                // score buffer t%2 last held S_{t-2}: free once its four row warps have it in registers
+                if (t >= 2) WAIT(smem_u32(&s_free[t & 1]), ((t >> 1) - 1) & 1, 3, t);
                 tc_fence_after();
-                if (dbg_cta && jj < 30) dbg_cta[jj * 8 + 6] = clock64();
-                const uint32_t vl = v_lo + pv_stage * (KV_BYTES >> 4), pl = p_lo + pb * (P_BYTES >> 4);
-#pragma unroll
-                for (int kk = 0; kk < BKV / 16; ++kk)
-                    umma_f16(o_tmem, desc_from_lo(pl + kk * 2), desc_from_lo(vl + kk * 128), IDESC_PV, (jj > 0 || kk > 0) ? 1u : 0u);
-                umma_commit(smem_u32(&v_empty[pv_stage]));
-                umma_commit(smem_u32(&bar_o));
-                if (dbg_cta && jj < 30) dbg_cta[jj * 8 + 7] = clock64();
-                if (++pv_stage == V_STAGES) { pv_stage = 0; pv_phase ^= 1; }
-            };
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int j = 0; j < nb; ++j) {
-                mbar_wait(smem_u32(&k_full[stage]), phase);
-                tc_fence_after();
-                if (dbg_cta && j < 30) dbg_cta[j * 8 + 4] = clock64();
+                if (dbg_cta && t < 30) dbg_cta[t * 8 + 4] = clock64();
                 const uint32_t kl = k_lo + stage * (KV_BYTES >> 4);
-                const uint32_t s_tmem = tmem_base + (j & 1) * BKV;
+                const uint32_t s_tmem = tmem_base + (t & 1) * BKV;
 #pragma unroll
                 for (int kk = 0; kk < DH / 16; ++kk)
                     umma_f16(s_tmem, desc_from_lo(q_lo + kk * 2), desc_from_lo(kl + kk * 2), IDESC_QK, kk > 0 ? 1u : 0u);
-                umma_commit(smem_u32(&s_full[j & 1]));
+                umma_commit(smem_u32(&s_full[t & 1]));
                 umma_commit(smem_u32(&k_empty[stage]));
-                if (dbg_cta && j < 30) dbg_cta[j * 8 + 5] = clock64();
+                if (dbg_cta && t < 30) dbg_cta[t * 8 + 5] = clock64();
                 if (++stage == K_STAGES) { stage = 0; phase ^= 1; }
-                if (j > 0) issue_pv(j - 1);
+            };
+            auto issue_pv = [&](int t) {
+                const int pb = t & 1;
+                WAIT(smem_u32(&v_full[pv_stage]), pv_phase, 4, t);
+                WAIT(smem_u32(&p_full[pb]), (t >> 1) & 1, 5, t);
+                tc_fence_after();
+                if (dbg_cta && t < 30) dbg_cta[t * 8 + 6] = clock64();
+                const uint32_t vl = v_lo + pv_stage * (KV_BYTES >> 4), pl = p_lo + pb * (P_BYTES >> 4);
+#pragma unroll
+                for (int kk = 0; kk < BKV / 16; ++kk)
+                    umma_f16(o_tmem, desc_from_lo(pl + kk * 2), desc_from_lo(vl + kk * 128), IDESC_PV, (t > 0 || kk > 0) ? 1u : 0u);
+                umma_commit(smem_u32(&v_empty[pv_stage]));
+                umma_commit(smem_u32(&p_free[pb]));
+                if (t == nb - 1) umma_commit(smem_u32(&bar_done));
+                if (dbg_cta && t < 30) dbg_cta[t * 8 + 7] = clock64();
+                if (++pv_stage == V_STAGES) { pv_stage = 0; pv_phase ^= 1; }
+            };
+            issue_qk(0);
+            if (nb > 1) issue_qk(1);
+            for (int t = 0; t < nb; ++t) {
+                if (t + 2 < nb) issue_qk(t + 2);
+                issue_pv(t);
             }
-            issue_pv(nb - 1);
         }
     } else {
-        const int sw = warp - 2;              // 0..7
         const int q = warp & 3;               // TMEM lane quadrant this warp may access
-        const int half = sw >> 2;             // which 32 of a block's 64 columns
+        const int half = (warp - 2) >> 2;     // 0: even key blocks, 1: odd key blocks
         const int r = q * 32 + lane;          // row within the tile == TMEM lane
         const int i = i0 + r;                 // query index within the sequence
-        const int pair_id = 1 + q;            // named barrier of the two warps that share the quadrant
+        // ping-pong barriers of the pair (ids 1..8): `mine` = "my exponentials of this block are done (and my m_ref is
+        // published)", arrived by me, awaited by the partner before ITS exponentials; `theirs` the other way round
+        const int bar_mine = 1 + half * 4 + q, bar_theirs = 1 + (half ^ 1) * 4 + q;
         const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-        // O accumulates in TMEM across key blocks (PV MMAs with accumulate = 1).  The softmax reference m_ref is only
-        // raised when the block maximum exceeds it by more than 2^8 ("lazy rescaling"): then O and l are multiplied by
-        // exp2(m_ref - m_new) -- a TMEM load/scale/store done by both warps of a pair (32 columns of O each) if any of
-        // their rows needs it.  Otherwise p = exp2(s - m_ref) <= 256, which bf16 / fp32 hold comfortably.
-        float m_ref = -INFINITY, l_run = 0.f;      // l_run: this thread's 32 columns only
-        // optional per-block cycle stamps of ONE row thread of every CTA (vb_attention_prefill_set_debug): [cta][block][0..3] =
-        // {S ready, row maximum known, exp2 / pack done, P written}
+        float m_ref = -INFINITY, l_run = 0.f;      // l_run: this thread's blocks only, relative to m_ref
+        // optional per-block cycle stamps of ONE row thread of every CTA (vb_attention_prefill_set_debug), slots 0..3 of block t:
+        // {S ready, row maximum known + partner's exponentials done, exp2 / pack done, P written}
         const long long t_entry = clock64();
         const bool stamp = dbg != nullptr && threadIdx.x == dbg_thread;
-        for (int j = 0; j < nb; ++j) {
-            const int sb = j & 1;
-            mbar_wait(smem_u32(&s_full[sb]), (j >> 1) & 1);
+        const uint32_t p_row = p_smem + half * P_BYTES + r * 128;
+#pragma unroll 1
+        for (int t = half; t < nb; t += 2) {
+            const int u = t >> 1;                 // this half's block counter
+            WAIT(smem_u32(&s_full[half]), u & 1, 6, t);
             tc_fence_after();
-            if (stamp && j < 30) dbg_cta[j * 8 + 0] = clock64();
-            uint32_t sv[32];
-            tmem_ld_32x32(lane_addr + sb * BKV + half * 32, sv);
-            tmem_ld_wait();
-            const int kbase = j * BKV;
+            if (stamp && t < 30) dbg_cta[t * 8 + 0] = clock64();
+            uint32_t sv[64];
+            {
+                uint32_t (&lo)[32] = *reinterpret_cast<uint32_t (*)[32]>(&sv[0]);
+                uint32_t (&hi)[32] = *reinterpret_cast<uint32_t (*)[32]>(&sv[32]);
+                tmem_ld_32x32(lane_addr + half * BKV, lo);
+                tmem_ld_32x32(lane_addr + half * BKV + 32, hi);
+                tmem_ld_wait();
+            }
+            // S_t is in registers: the MMA warp may overwrite the buffer with S_{t+2}
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&s_free[half]));
+            const int kbase = t * BKV;
             bool need_mask = (kbase + BKV > kv_len);
             if (mask_mode == VB_MASK_PREFIX_LM)
                 need_mask = need_mask || !((kbase + BKV <= x_len) || (i0 >= x_len && kbase + BKV - 1 <= i0));
             if (need_mask) {
 #pragma unroll
-                for (int c = 0; c < 32; ++c) {
-                    const int kj = kbase + half * 32 + c;
+                for (int c = 0; c < 64; ++c) {
+                    const int kj = kbase + c;
                     bool ok = kj < kv_len;
                     if (mask_mode == VB_MASK_PREFIX_LM) ok = ok && ((kj < x_len) || (i >= x_len && kj <= i));
                     if (!ok) sv[c] = 0xff800000u;   // -inf -> p = 0
                 }
             }
-            // maximum of this half's raw scores (scale > 0 commutes with max), then the other half's through shared memory
-            float mx0 = -INFINITY, mx1 = -INFINITY;
+            // maximum of the block's raw scores (scale > 0 commutes with max)
+            float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
-            for (int c = 0; c < 32; c += 4) {
+            for (int c = 0; c < 64; c += 8) {
                 mx0 = fmax3(mx0, __uint_as_float(sv[c]), __uint_as_float(sv[c + 1]));
                 mx1 = fmax3(mx1, __uint_as_float(sv[c + 2]), __uint_as_float(sv[c + 3]));
+                mx2 = fmax3(mx2, __uint_as_float(sv[c + 4]), __uint_as_float(sv[c + 5]));
+                mx3 = fmax3(mx3, __uint_as_float(sv[c + 6]), __uint_as_float(sv[c + 7]));
             }
-            float mx = fmaxf(mx0, mx1);
-            xch[sb][half][r] = mx;
-            pair_barrier(pair_id);
-            mx = fmaxf(mx, xch[sb][half ^ 1][r]);
-            if (stamp && j < 30) dbg_cta[j * 8 + 1] = clock64();
-            const float m_blk = mx * scale_log2e;
+            const float m_blk = fmaxf(fmax3(mx0, mx1, mx2), mx3) * scale_log2e;
+            if (t > 0) {
+                // the partner has finished the exponentials of block t-1 and published the reference it used
+                pair_sync(bar_theirs);
+                const float m_prev = xch[(t - 1) & 1][r];
+                if (m_prev != m_ref) {              // references only grow: m_prev > m_ref
+                    l_run *= (m_ref == -INFINITY) ? 0.f : fast_exp2(m_ref - m_prev);
+                    m_ref = m_prev;
+                }
+            }
+            if (stamp && t < 30) dbg_cta[t * 8 + 1] = clock64();
             const bool grow = m_blk > m_ref + 8.0f;            // also true for the first finite block (m_ref = -inf)
             float alpha = 1.f;
             if (grow) {
@@ -295,49 +339,68 @@ __global__ void __launch_bounds__(THREADS, 2) attn_prefill_tc_kernel(const __gri
                 m_ref = m_blk;
                 l_run *= alpha;
             }
-            if (j > 0 && __any_sync(0xffffffffu, grow)) {
-                // O is about to be corrected: every P V issued so far must have completed.  bar_o completes one phase per
-                // P V; it is in phase j-1 (P V_{j-1} pending) or j, so the parity of phase j-1 is unambiguous.
-                mbar_wait(smem_u32(&bar_o), (j - 1) & 1);
+            xch[t & 1][r] = m_ref;
+            if (t > 0 && __any_sync(0xffffffffu, grow)) {
+                // O is about to be corrected: P V_{t-1} (and with it every earlier one) must have completed.  p_free of the
+                // partner's buffer is in phase (t-1)/2 (pending) or one later, never further: P V_{t+1} needs P V_t first.
+                WAIT(smem_u32(&p_free[half ^ 1]), ((t - 1) >> 1) & 1, 7, t);
                 tc_fence_after();
                 const float2 a2 = make_float2(alpha, alpha);
-                uint32_t ov[32];
-                tmem_ld_32x32(lane_addr + O_COL + half * 32, ov);
-                tmem_ld_wait();
+#pragma unroll 1
+                for (int part = 0; part < 8; ++part) {       // 8 columns at a time: the rare path must not cost registers
+                    uint32_t ov[8];
+                    tmem_ld_32x8(lane_addr + O_COL + part * 8, ov);
+                    tmem_ld_wait();
 #pragma unroll
-                for (int e = 0; e < 32; e += 2) {
-                    const float2 t = __fmul2_rn(make_float2(__uint_as_float(ov[e]), __uint_as_float(ov[e + 1])), a2);
-                    ov[e] = __float_as_uint(t.x);
-                    ov[e + 1] = __float_as_uint(t.y);
+                    for (int e = 0; e < 8; e += 2) {
+                        const float2 tt = __fmul2_rn(make_float2(__uint_as_float(ov[e]), __uint_as_float(ov[e + 1])), a2);
+                        ov[e] = __float_as_uint(tt.x);
+                        ov[e + 1] = __float_as_uint(tt.y);
+                    }
+                    tmem_st_32x8(lane_addr + O_COL + part * 8, ov);
                 }
-                tmem_st_32x32(lane_addr + O_COL + half * 32, ov);
                 tmem_st_wait();
             }
             const float m_use = (m_ref == -INFINITY) ? 0.f : m_ref;     // fully masked so far: p = 0, no NaN
-            uint32_t pk[16];
-            if (need_mask || POLY_OF_8 == 0) l_run += softmax_half_row<false>(sv, pk, scale_log2e, m_use);
-            else l_run += softmax_half_row<true>(sv, pk, scale_log2e, m_use);
-            if (stamp && j < 30) dbg_cta[j * 8 + 2] = clock64();
-            // P_j -> smem buffer j%2 as K-major 128B-swizzled rows (16-byte chunk c of row r lives at chunk c ^ (r & 7));
-            // the buffer is free: S_j complete implies P V_{j-2} complete (issue order of the MMA warp)
-            const uint32_t p_row = p_smem + sb * P_BYTES + r * 128;
+            // p = exp2(s * scale - m_ref), 32 columns at a time
+            uint32_t pk[32];
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                const uint32_t addr = p_row + (static_cast<uint32_t>((half * 4 + c) ^ (r & 7)) << 4);
+            for (int part = 0; part < 2; ++part) {
+                uint32_t (&svp)[32] = *reinterpret_cast<uint32_t (*)[32]>(&sv[part * 32]);
+                uint32_t (&pkp)[16] = *reinterpret_cast<uint32_t (*)[16]>(&pk[part * 16]);
+                if (need_mask || POLY_OF_8 == 0) l_run += softmax_32<false>(svp, pkp, scale_log2e, m_use);
+                else l_run += softmax_32<true>(svp, pkp, scale_log2e, m_use);
+            }
+            if (t + 1 < nb) pair_arrive(bar_mine);      // the partner may start the exponentials of block t+1
+            if (stamp && t < 30) dbg_cta[t * 8 + 2] = clock64();
+            // P_t -> this half's smem tile as K-major 128B-swizzled rows (16-byte chunk c of row r lives at chunk c ^ (r & 7));
+            // the tile is free once P V_{t-2} has completed
+            if (t >= 2) WAIT(smem_u32(&p_free[half]), (u - 1) & 1, 8, t);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const uint32_t addr = p_row + (static_cast<uint32_t>(c ^ (r & 7)) << 4);
                 asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[c * 4]), "r"(pk[c * 4 + 1]),
                              "r"(pk[c * 4 + 2]), "r"(pk[c * 4 + 3]) : "memory");
             }
             fence_proxy_async();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(&p_full[sb]));
-            if (stamp && j < 30) dbg_cta[j * 8 + 3] = clock64();
+            if (lane == 0) mbar_arrive(smem_u32(&p_full[half]));
+            if (stamp && t < 30) dbg_cta[t * 8 + 3] = clock64();
         }
-        // the other half's partial row sum (slot parity nb&1 was last used by block nb-2 or not at all)
-        xch[nb & 1][half][r] = l_run;
-        pair_barrier(pair_id);
-        const float l_tot = l_run + xch[nb & 1][half ^ 1][r];
-        mbar_wait(smem_u32(&bar_o), (nb - 1) & 1);
+        // final reference = the one published by block nb-1; bring this half's row sum to it, then add the halves
+        const int pair_id = 9 + q;            // own ids: a ping-pong arrival of this warp may still be waiting for its partner
+        pair_sync(pair_id);
+        const float m_fin = xch[(nb - 1) & 1][r];
+        if (m_fin != m_ref) {
+            l_run *= (m_ref == -INFINITY) ? 0.f : fast_exp2(m_ref - m_fin);
+            m_ref = m_fin;
+        }
+        pair_sync(pair_id);                   // both have read m_fin before its slot is reused for the sums
+        xch[half][r] = l_run;
+        pair_sync(pair_id);
+        const float l_tot = l_run + xch[half ^ 1][r];
+        WAIT(smem_u32(&bar_done), 0, 9, nb);
         tc_fence_after();
         if (stamp) { dbg_cta[31 * 8 + 0] = t_entry; dbg_cta[31 * 8 + 1] = clock64(); }     // row-thread entry, last PV done
         const float inv = (l_tot > 0.f) ? 1.f / l_tot : 0.f;
