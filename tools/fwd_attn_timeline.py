@@ -47,6 +47,9 @@ print('  P_t seen -> P V_t issued + committed                      %6.0f' % np.m
 print('  P V_{t-1} issued -> Q K_{t+2} operands + buffer ready     %6.0f' % np.median(full[:, 3:, 4] - full[:, :-3, 7]))
 print('  -> Q K_{t+2} issued + committed                           %6.0f' % np.median(full[:, 3:, 5] - full[:, 3:, 4]))
 print('  MMA warp period per block (P V_t issued -> P V_{t+1})     %6.0f' % np.median(full[:, 2:, 7] - full[:, 1:-1, 7]))
+print('  Q K_t issued -> S_t first read by its row thread          %6.0f' % np.median(row[:, 1:, 0] - full[:, mine, 5][:, 1:]))
+print('  row thread finished block t-2 -> Q K_t issued             %6.0f' % np.median(full[:, mine, 5][:, 1:] - row[:, :-1, 3]))
+print('  Q K_{t-1} issued -> Q K_t issued                          %6.0f' % np.median(full[:, 2:, 5] - full[:, 1:-1, 5]))
 print('  CTA lifetime (first S ready -> last P written) median %.0f cycles' % np.median(row[:, -1, 3] - row[:, 0, 0]))
 print('  row-thread entry -> first S ready   %6.0f' % np.median(row[:, 0, 0] - extra[:, 0]))
 print('  last P written -> last PV done      %6.0f' % np.median(extra[:, 1] - row[:, -1, 3]))

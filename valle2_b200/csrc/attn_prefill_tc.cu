@@ -4,9 +4,11 @@
 // materialised (B,H,S,S) mask: the prefix-LM / padding predicate is evaluated from (x_len, kv_len) per element.
 //
 // CTA = 128 query rows of one (batch, head); key blocks of 64; 320 threads, two CTAs per SM.
-//   warp 0    TMA producer: Q tile once, then a 4-deep ring of K blocks and a 3-deep ring of V blocks
-//   warp 1    MMA issuer + TMEM allocator: QK_t (M128 N64 K64) into score buffer t%2, PV_t (M128 N64 K64; V is the MN-major B
-//             operand) accumulating into O in TMEM.  Issue order QK_0, QK_1, {QK_{t+2}, PV_t}.
+//   warp 0    Q tile + 4-deep ring of K blocks by TMA, and the Q K^T issuer: QK_t (M128 N64 K64) into score buffer t%2 as soon as
+//             the row threads have S_{t-2} in registers -- the scores run up to two blocks ahead
+//   warp 1    3-deep ring of V blocks by TMA, the P V issuer (M128 N64 K64; V is the MN-major B operand; O accumulates in TMEM)
+//             and the TMEM allocator.  One control thread for both MMA streams needed ~1100 cycles per block (four mbarrier
+//             waits at ~90 cycles each plus a serial instruction stream on a busy sub-partition) and S_t arrived late.
 //   warp 2-5  softmax of the EVEN key blocks, one thread per query row (tcgen05.ld 32x32b gives a thread its whole row)
 //   warp 6-9  softmax of the ODD key blocks, same rows (warps w and w+4 share a TMEM lane quadrant and an SM sub-partition)
 // The kernel is bound by the MUFU pipe (64 exp2 per row and block = 512 pipe cycles against 256 tensor-pipe cycles) AND by the
@@ -37,6 +39,10 @@ constexpr int DH = 64;
 constexpr int K_STAGES = 4;   // K blocks: a stage is free as soon as Q K_t^T has completed
 constexpr int V_STAGES = 3;   // V blocks: free after P_t V_t
 constexpr int POLY_OF_8 = VB_FWD_POLY;
+#ifndef VB_FWD_RELEASE_PART
+#define VB_FWD_RELEASE_PART 1
+#endif
+constexpr int RELEASE_PART = VB_FWD_RELEASE_PART;   // after which 32-column part of its exponentials a row warp releases its partner
 constexpr int THREADS = 320;
 constexpr int Q_BYTES = BQ * DH * 2;          // 16 KB
 constexpr int KV_BYTES = BKV * DH * 2;        // 8 KB per K or V block
@@ -132,7 +138,8 @@ __global__ void __launch_bounds__(THREADS, 2) attn_prefill_tc_kernel(const __gri
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bar_q, bar_done, s_full[2], s_free[2], p_full[2], p_free[2];
     __shared__ __align__(8) uint64_t k_full[K_STAGES], k_empty[K_STAGES], v_full[V_STAGES], v_empty[V_STAGES];
-    __shared__ float xch[2][BQ];      // [block parity][row]: softmax reference after that block (at the end: the halves' row sums)
+    __shared__ float xch[2][BQ];      // [block parity][row]: softmax reference after that block
+    __shared__ float fin_m[2][BQ], fin_l[2][BQ];      // [half][row]: final reference and row sum of each half
     __shared__ uint32_t tmem_slot;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -184,6 +191,15 @@ __global__ void __launch_bounds__(THREADS, 2) attn_prefill_tc_kernel(const __gri
     const uint32_t tmem_base = tmem_slot;
     const int row0 = b * S;   // first row of this batch in the packed [B*S][3d] matrix
     pdl_wait();               // qkv / lens are produced by earlier kernels; the set-up above overlapped their tail
+    // block 0 is always needed: request Q, K_0 and V_0 before the sequence lengths are even read
+    if (threadIdx.x == 0) {
+        mbar_expect_tx(smem_u32(&bar_q), Q_BYTES);
+        tma_load_2d(q_smem, &tm_q, smem_u32(&bar_q), h * DH, row0 + i0);
+        mbar_expect_tx(smem_u32(&k_full[0]), KV_BYTES);
+        tma_load_2d(k_smem, &tm_kv, smem_u32(&k_full[0]), d + h * DH, row0);
+        mbar_expect_tx(smem_u32(&v_full[0]), KV_BYTES);
+        tma_load_2d(v_smem, &tm_kv, smem_u32(&v_full[0]), 2 * d + h * DH, row0);
+    }
     const int kv_len = kv_lens ? min(kv_lens[b], S) : S;
     const int x_len = (mask_mode == VB_MASK_PREFIX_LM) ? x_lens[b] : 0;
     // keys any row of this tile may attend: everything (no mask) or the text prefix plus the causal part
@@ -191,79 +207,73 @@ __global__ void __launch_bounds__(THREADS, 2) attn_prefill_tc_kernel(const __gri
     if (mask_mode == VB_MASK_PREFIX_LM) k_end = min(kv_len, max(x_len, i0 + BQ));
     const int nb = max(1, (k_end + BKV - 1) / BKV);
 
+    // descriptor low words; a step of 16 along K is +32 bytes (K-major) or +16 rows of 128 bytes (MN-major V)
+    const uint32_t q_lo = ((q_smem & 0x3ffffu) >> 4) | (1u << 16);
+    const uint32_t k_lo = ((k_smem & 0x3ffffu) >> 4) | (1u << 16);
+    const uint32_t v_lo = ((v_smem & 0x3ffffu) >> 4) | (64u << 16);
+    const uint32_t p_lo = ((p_smem & 0x3ffffu) >> 4) | (1u << 16);
     if (warp == 0) {
-        if (elect_one()) {
-            mbar_expect_tx(smem_u32(&bar_q), Q_BYTES);
-            tma_load_2d(q_smem, &tm_q, smem_u32(&bar_q), h * DH, row0 + i0);
-            // K runs one block ahead of V: K_t and V_{t-1} per iteration (a K stage is released earlier than a V stage)
-            int ks = 0, vs = 0;
-            uint32_t kph = 0, vph = 0;
-            for (int t = 0; t <= nb; ++t) {
-                if (t < nb) {
-                    mbar_wait_relaxed(smem_u32(&k_empty[ks]), kph ^ 1);
-                    mbar_expect_tx(smem_u32(&k_full[ks]), KV_BYTES);
-                    tma_load_2d(k_smem + ks * KV_BYTES, &tm_kv, smem_u32(&k_full[ks]), d + h * DH, row0 + t * BKV);
-                    if (++ks == K_STAGES) { ks = 0; kph ^= 1; }
-                }
-                if (t > 0) {
-                    mbar_wait_relaxed(smem_u32(&v_empty[vs]), vph ^ 1);
-                    mbar_expect_tx(smem_u32(&v_full[vs]), KV_BYTES);
-                    tma_load_2d(v_smem + vs * KV_BYTES, &tm_kv, smem_u32(&v_full[vs]), 2 * d + h * DH, row0 + (t - 1) * BKV);
-                    if (++vs == V_STAGES) { vs = 0; vph ^= 1; }
-                }
-            }
-        }
-    } else if (warp == 1) {
+        // K producer + Q K^T issuer.  MMA-warp stamps (debug slots 4, 5 of block t): {operands + score buffer ready, issued}
         if (elect_one()) {
             constexpr uint32_t IDESC_QK = umma_idesc_bf16(BQ, BKV, 0, 0);   // A = Q (K-major), B = K block (K-major)
-            constexpr uint32_t IDESC_PV = umma_idesc_bf16(BQ, DH, 0, 1);    // A = P (K-major), B = V block (MN-major)
-            const uint32_t o_tmem = tmem_base + O_COL;
-            // descriptor low words; a step of 16 along K is +32 bytes (K-major) or +16 rows of 128 bytes (MN-major V)
-            const uint32_t q_lo = ((q_smem & 0x3ffffu) >> 4) | (1u << 16);
-            const uint32_t k_lo = ((k_smem & 0x3ffffu) >> 4) | (1u << 16);
-            const uint32_t v_lo = ((v_smem & 0x3ffffu) >> 4) | (64u << 16);
-            const uint32_t p_lo = ((p_smem & 0x3ffffu) >> 4) | (1u << 16);
-            // MMA-warp stamps (debug buffer slots 4..7 of block t): {operands + score buffer ready, Q K^T issued, P ready, P V issued}
+            auto load_k = [&](int t) {
+                const int st = t % K_STAGES;
+                mbar_expect_tx(smem_u32(&k_full[st]), KV_BYTES);
+                tma_load_2d(k_smem + st * KV_BYTES, &tm_kv, smem_u32(&k_full[st]), d + h * DH, row0 + t * BKV);
+            };
+            for (int t = 1; t < min(nb, K_STAGES); ++t) load_k(t);
             WAIT(smem_u32(&bar_q), 0, 1, 0);
-            int stage = 0, pv_stage = 0;
-            uint32_t phase = 0, pv_phase = 0;
-            auto issue_qk = [&](int t) {
-                WAIT(smem_u32(&k_full[stage]), phase, 2, t);
+            for (int t = 0; t < nb; ++t) {
+                const int st = t % K_STAGES;
+                WAIT(smem_u32(&k_full[st]), (t / K_STAGES) & 1, 2, t);
                 // score buffer t%2 last held S_{t-2}: free once its four row warps have it in registers
                 if (t >= 2) WAIT(smem_u32(&s_free[t & 1]), ((t >> 1) - 1) & 1, 3, t);
                 tc_fence_after();
                 if (dbg_cta && t < 30) dbg_cta[t * 8 + 4] = clock64();
-                const uint32_t kl = k_lo + stage * (KV_BYTES >> 4);
+                const uint32_t kl = k_lo + st * (KV_BYTES >> 4);
                 const uint32_t s_tmem = tmem_base + (t & 1) * BKV;
 #pragma unroll
                 for (int kk = 0; kk < DH / 16; ++kk)
                     umma_f16(s_tmem, desc_from_lo(q_lo + kk * 2), desc_from_lo(kl + kk * 2), IDESC_QK, kk > 0 ? 1u : 0u);
                 umma_commit(smem_u32(&s_full[t & 1]));
-                umma_commit(smem_u32(&k_empty[stage]));
+                umma_commit(smem_u32(&k_empty[st]));
                 if (dbg_cta && t < 30) dbg_cta[t * 8 + 5] = clock64();
-                if (++stage == K_STAGES) { stage = 0; phase ^= 1; }
+                // refill the stage of the PREVIOUS block (its Q K^T was issued one iteration ago and has completed by now)
+                if (t >= 1 && t - 1 + K_STAGES < nb) {
+                    WAIT(smem_u32(&k_empty[(t - 1) % K_STAGES]), ((t - 1) / K_STAGES) & 1, 10, t);
+                    load_k(t - 1 + K_STAGES);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // V producer + P V issuer.  Stamps (debug slots 6, 7 of block t): {P ready, issued}
+        if (elect_one()) {
+            constexpr uint32_t IDESC_PV = umma_idesc_bf16(BQ, DH, 0, 1);    // A = P (K-major), B = V block (MN-major)
+            const uint32_t o_tmem = tmem_base + O_COL;
+            auto load_v = [&](int t) {
+                const int st = t % V_STAGES;
+                mbar_expect_tx(smem_u32(&v_full[st]), KV_BYTES);
+                tma_load_2d(v_smem + st * KV_BYTES, &tm_kv, smem_u32(&v_full[st]), 2 * d + h * DH, row0 + t * BKV);
             };
-            auto issue_pv = [&](int t) {
-                const int pb = t & 1;
-                WAIT(smem_u32(&v_full[pv_stage]), pv_phase, 4, t);
+            for (int t = 1; t < min(nb, V_STAGES); ++t) load_v(t);
+            for (int t = 0; t < nb; ++t) {
+                const int st = t % V_STAGES, pb = t & 1;
+                WAIT(smem_u32(&v_full[st]), (t / V_STAGES) & 1, 4, t);
                 WAIT(smem_u32(&p_full[pb]), (t >> 1) & 1, 5, t);
                 tc_fence_after();
                 if (dbg_cta && t < 30) dbg_cta[t * 8 + 6] = clock64();
-                const uint32_t vl = v_lo + pv_stage * (KV_BYTES >> 4), pl = p_lo + pb * (P_BYTES >> 4);
+                const uint32_t vl = v_lo + st * (KV_BYTES >> 4), pl = p_lo + pb * (P_BYTES >> 4);
 #pragma unroll
                 for (int kk = 0; kk < BKV / 16; ++kk)
                     umma_f16(o_tmem, desc_from_lo(pl + kk * 2), desc_from_lo(vl + kk * 128), IDESC_PV, (t > 0 || kk > 0) ? 1u : 0u);
-                umma_commit(smem_u32(&v_empty[pv_stage]));
+                umma_commit(smem_u32(&v_empty[st]));
                 umma_commit(smem_u32(&p_free[pb]));
                 if (t == nb - 1) umma_commit(smem_u32(&bar_done));
                 if (dbg_cta && t < 30) dbg_cta[t * 8 + 7] = clock64();
-                if (++pv_stage == V_STAGES) { pv_stage = 0; pv_phase ^= 1; }
-            };
-            issue_qk(0);
-            if (nb > 1) issue_qk(1);
-            for (int t = 0; t < nb; ++t) {
-                if (t + 2 < nb) issue_qk(t + 2);
-                issue_pv(t);
+                if (t >= 1 && t - 1 + V_STAGES < nb) {
+                    WAIT(smem_u32(&v_empty[(t - 1) % V_STAGES]), ((t - 1) / V_STAGES) & 1, 11, t);
+                    load_v(t - 1 + V_STAGES);
+                }
             }
         }
     } else {
@@ -322,6 +332,9 @@ __global__ void __launch_bounds__(THREADS, 2) attn_prefill_tc_kernel(const __gri
                 mx3 = fmax3(mx3, __uint_as_float(sv[c + 6]), __uint_as_float(sv[c + 7]));
             }
             const float m_blk = fmaxf(fmax3(mx0, mx1, mx2), mx3) * scale_log2e;
+            // P V_{t-2} complete: this half's P tile is free -- and P V_{t-3} is complete too (the P V issuer works in order),
+            // which the rescaling below relies on.  Waited for here, off the hand-over path between the halves.
+            if (t >= 2) WAIT(smem_u32(&p_free[half]), (u - 1) & 1, 8, t);
             if (t > 0) {
                 // the partner has finished the exponentials of block t-1 and published the reference it used
                 pair_sync(bar_theirs);
@@ -370,12 +383,12 @@ __global__ void __launch_bounds__(THREADS, 2) attn_prefill_tc_kernel(const __gri
                 uint32_t (&pkp)[16] = *reinterpret_cast<uint32_t (*)[16]>(&pk[part * 16]);
                 if (need_mask || POLY_OF_8 == 0) l_run += softmax_32<false>(svp, pkp, scale_log2e, m_use);
                 else l_run += softmax_32<true>(svp, pkp, scale_log2e, m_use);
+                // the partner may start the exponentials of block t+1 (RELEASE_PART 0: when half of mine are still to come --
+                // the overlap fills the hand-over bubble on the MUFU pipe)
+                if (part == RELEASE_PART && t + 1 < nb) pair_arrive(bar_mine);
             }
-            if (t + 1 < nb) pair_arrive(bar_mine);      // the partner may start the exponentials of block t+1
             if (stamp && t < 30) dbg_cta[t * 8 + 2] = clock64();
-            // P_t -> this half's smem tile as K-major 128B-swizzled rows (16-byte chunk c of row r lives at chunk c ^ (r & 7));
-            // the tile is free once P V_{t-2} has completed
-            if (t >= 2) WAIT(smem_u32(&p_free[half]), (u - 1) & 1, 8, t);
+            // P_t -> this half's smem tile as K-major 128B-swizzled rows (16-byte chunk c of row r lives at chunk c ^ (r & 7))
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
                 const uint32_t addr = p_row + (static_cast<uint32_t>(c ^ (r & 7)) << 4);
@@ -388,18 +401,16 @@ __global__ void __launch_bounds__(THREADS, 2) attn_prefill_tc_kernel(const __gri
             if (lane == 0) mbar_arrive(smem_u32(&p_full[half]));
             if (stamp && t < 30) dbg_cta[t * 8 + 3] = clock64();
         }
-        // final reference = the one published by block nb-1; bring this half's row sum to it, then add the halves
-        const int pair_id = 9 + q;            // own ids: a ping-pong arrival of this warp may still be waiting for its partner
-        pair_sync(pair_id);
-        const float m_fin = xch[(nb - 1) & 1][r];
-        if (m_fin != m_ref) {
-            l_run *= (m_ref == -INFINITY) ? 0.f : fast_exp2(m_ref - m_fin);
-            m_ref = m_fin;
-        }
-        pair_sync(pair_id);                   // both have read m_fin before its slot is reused for the sums
-        xch[half][r] = l_run;
-        pair_sync(pair_id);
-        const float l_tot = l_run + xch[half ^ 1][r];
+        // combine the halves: references only grow, so the final one is the larger of the two; one exchange of (m_ref, l) per row.
+        // Own barrier ids: a ping-pong arrival of this warp may still be waiting for its partner.
+        fin_m[half][r] = m_ref;
+        fin_l[half][r] = l_run;
+        pair_sync(9 + q);
+        const float m_oth = fin_m[half ^ 1][r], l_oth = fin_l[half ^ 1][r];
+        const float m_fin = fmaxf(m_ref, m_oth);
+        const float l_tot = ((m_ref == -INFINITY) ? 0.f : l_run * fast_exp2(m_ref - m_fin)) +
+                            ((m_oth == -INFINITY) ? 0.f : l_oth * fast_exp2(m_oth - m_fin));
+        m_ref = m_fin;
         WAIT(smem_u32(&bar_done), 0, 9, nb);
         tc_fence_after();
         if (stamp) { dbg_cta[31 * 8 + 0] = t_entry; dbg_cta[31 * 8 + 1] = clock64(); }     // row-thread entry, last PV done
