@@ -1,4 +1,6 @@
-"""Kernel breakdown of NAR config 3 (B=64, S=900, 7 stages) in situ.   python tools/nar_profile.py"""
+"""Kernel breakdown of NAR config 3 (B=64, S=900, 7 stages) in situ.   python tools/nar_profile.py
+NAR_TT=750 gives the bench job's shape (S = 150 + 225 + 750 = 1125)."""
+import os
 import sys
 import tempfile
 
@@ -14,7 +16,7 @@ dev = torch.device('cuda')
 torch.manual_seed(1)
 nar = ValleNAR(large_cfg('AdaptiveLayerNorm', tempfile.mkdtemp())).eval().to(dev)
 g = torch.Generator().manual_seed(7)
-Bn, Tc, Tt = 64, 225, 525
+Bn, Tc, Tt = 64, 225, int(os.environ.get('NAR_TT', '525'))
 pt = torch.randint(0, 256, (Bn, 50), generator=g).to(dev)
 tt = torch.randint(0, 256, (Bn, 100), generator=g).to(dev)
 pc = torch.randint(0, 1024, (Bn, Tc, 8), generator=g).to(dev)

@@ -6,12 +6,16 @@
 // CTA = 128 query rows of one (batch, head); key blocks of 64; 320 threads, two CTAs per SM.
 //   warp 0    Q tile + 4-deep ring of K blocks by TMA, and the Q K^T issuer: QK_t (M128 N64 K64) into score buffer t%2 as soon as
 //             the row threads have S_{t-2} in registers -- the scores run up to two blocks ahead
-//   warp 1    3-deep ring of V blocks by TMA, the P V issuer (M128 N64 K64; V is the MN-major B operand; O accumulates in TMEM)
-//             and the TMEM allocator.  One control thread for both MMA streams needed ~1100 cycles per block (four mbarrier
-//             waits at ~90 cycles each plus a serial instruction stream on a busy sub-partition) and S_t arrived late.
+//   warp 1    3-deep ring of V blocks by TMA, the P V issuer and the TMEM allocator.  P V_t reads its A operand P_t from TENSOR
+//             MEMORY (tcgen05.mma with [a_tmem]) and V_t from shared memory (MN-major B); O accumulates in TMEM.
+//             One control thread for both MMA streams needed ~1100 cycles per block (four mbarrier waits at ~90 cycles each
+//             plus a serial instruction stream on a busy sub-partition) and S_t arrived late.
 //   warp 2-5  softmax of the EVEN key blocks, one thread per query row (tcgen05.ld 32x32b gives a thread its whole row)
 //   warp 6-9  softmax of the ODD key blocks, same rows (warps w and w+4 share a TMEM lane quadrant and an SM sub-partition)
-// The kernel is bound by the MUFU pipe (64 exp2 per row and block = 512 pipe cycles against 256 tensor-pipe cycles) AND by the
+// Shared-memory bandwidth is what a tcgen05.mma with small N pays for: M128 N64 K16 reads 4 KB of A + 2 KB of B = 48 cycles at
+// 128 B/clk for 32 cycles of math (tools/umma_probe.cu).  With P staged in shared memory a key block moved 80 KB through that
+// pipe (48 KB operand reads + 16 KB P stores + 16 KB TMA writes = 640 of the 704 cycles a block took); P through TMEM leaves
+// 48 KB.  Beyond that the kernel is bound by the MUFU pipe (64 exp2 per row and block = 525 pipe cycles) AND by the
 // per-block latencies of a row thread (mbarrier waits ~90 cycles each, TMEM load, proxy fence: ~800 cycles with the MUFU pipe
 // idle).  When all row warps of a sub-partition run their exponentials at the same time they queue on the pipe and then idle
 // together (measured: 45 % MUFU utilisation); so the two halves are kept in ANTI-PHASE by a ping-pong of named barriers: a warp
@@ -46,9 +50,9 @@ constexpr int RELEASE_PART = VB_FWD_RELEASE_PART;   // after which 32-column par
 constexpr int THREADS = 320;
 constexpr int Q_BYTES = BQ * DH * 2;          // 16 KB
 constexpr int KV_BYTES = BKV * DH * 2;        // 8 KB per K or V block
-constexpr int P_BYTES = BQ * BKV * 2;         // 16 KB
-constexpr int SMEM_BYTES = Q_BYTES + (K_STAGES + V_STAGES) * KV_BYTES + 2 * P_BYTES + 1024;
+constexpr int SMEM_BYTES = Q_BYTES + (K_STAGES + V_STAGES) * KV_BYTES + 1024;
 constexpr int O_COL = 2 * BKV;                // score buffers: cols [0, 64) even blocks, [64, 128) odd blocks; O: [128, 192)
+constexpr int P_COL = O_COL + DH;             // P tiles (bf16 pairs, 32 columns per 64 keys): [192, 224) even, [224, 256) odd blocks
 constexpr int TMEM_COLS = 256;
 
 // three-input maximum (FMNMX3 on sm_100)
@@ -107,6 +111,14 @@ __device__ __forceinline__ void tmem_st_32x8(uint32_t taddr, const uint32_t (&r)
     asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
                  ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
 }
+// D[tmem] (+)= A[tmem] * B[smem]: the A operand (128 rows x 16 bf16 = 8 columns of bf16 pairs) is read from tensor memory
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n"
+        " tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 // shared-memory matrix descriptor (SWIZZLE_128B, SBO 1024) from its low word: start address >> 4 | LBO >> 4 << 16
 __device__ __forceinline__ uint64_t desc_from_lo(uint32_t lo) { return (static_cast<uint64_t>(0x40004040u) << 32) | lo; }
 #ifdef VB_FWD_DEBUG_WAIT      // experiment build: a wait that does not complete reports where it is and traps
@@ -161,7 +173,6 @@ __global__ void __launch_bounds__(THREADS, 2) attn_prefill_tc_kernel(const __gri
     const uint32_t q_smem = base;
     const uint32_t k_smem = base + Q_BYTES;
     const uint32_t v_smem = k_smem + K_STAGES * KV_BYTES;
-    const uint32_t p_smem = v_smem + V_STAGES * KV_BYTES;
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tm_q);
@@ -211,7 +222,6 @@ __global__ void __launch_bounds__(THREADS, 2) attn_prefill_tc_kernel(const __gri
     const uint32_t q_lo = ((q_smem & 0x3ffffu) >> 4) | (1u << 16);
     const uint32_t k_lo = ((k_smem & 0x3ffffu) >> 4) | (1u << 16);
     const uint32_t v_lo = ((v_smem & 0x3ffffu) >> 4) | (64u << 16);
-    const uint32_t p_lo = ((p_smem & 0x3ffffu) >> 4) | (1u << 16);
     if (warp == 0) {
         // K producer + Q K^T issuer.  MMA-warp stamps (debug slots 4, 5 of block t): {operands + score buffer ready, issued}
         if (elect_one()) {
@@ -262,10 +272,10 @@ __global__ void __launch_bounds__(THREADS, 2) attn_prefill_tc_kernel(const __gri
                 WAIT(smem_u32(&p_full[pb]), (t >> 1) & 1, 5, t);
                 tc_fence_after();
                 if (dbg_cta && t < 30) dbg_cta[t * 8 + 6] = clock64();
-                const uint32_t vl = v_lo + st * (KV_BYTES >> 4), pl = p_lo + pb * (P_BYTES >> 4);
+                const uint32_t vl = v_lo + st * (KV_BYTES >> 4), p_tmem = tmem_base + P_COL + pb * (BKV / 2);
 #pragma unroll
                 for (int kk = 0; kk < BKV / 16; ++kk)
-                    umma_f16(o_tmem, desc_from_lo(pl + kk * 2), desc_from_lo(vl + kk * 128), IDESC_PV, (t > 0 || kk > 0) ? 1u : 0u);
+                    umma_f16_ts(o_tmem, p_tmem + kk * 8, desc_from_lo(vl + kk * 128), IDESC_PV, (t > 0 || kk > 0) ? 1u : 0u);
                 umma_commit(smem_u32(&v_empty[st]));
                 umma_commit(smem_u32(&p_free[pb]));
                 if (t == nb - 1) umma_commit(smem_u32(&bar_done));
@@ -290,7 +300,6 @@ __global__ void __launch_bounds__(THREADS, 2) attn_prefill_tc_kernel(const __gri
         // {S ready, row maximum known + partner's exponentials done, exp2 / pack done, P written}
         const long long t_entry = clock64();
         const bool stamp = dbg != nullptr && threadIdx.x == dbg_thread;
-        const uint32_t p_row = p_smem + half * P_BYTES + r * 128;
 #pragma unroll 1
         for (int t = half; t < nb; t += 2) {
             const int u = t >> 1;                 // this half's block counter
@@ -388,14 +397,11 @@ __global__ void __launch_bounds__(THREADS, 2) attn_prefill_tc_kernel(const __gri
                 if (part == RELEASE_PART && t + 1 < nb) pair_arrive(bar_mine);
             }
             if (stamp && t < 30) dbg_cta[t * 8 + 2] = clock64();
-            // P_t -> this half's smem tile as K-major 128B-swizzled rows (16-byte chunk c of row r lives at chunk c ^ (r & 7))
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                const uint32_t addr = p_row + (static_cast<uint32_t>(c ^ (r & 7)) << 4);
-                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[c * 4]), "r"(pk[c * 4 + 1]),
-                             "r"(pk[c * 4 + 2]), "r"(pk[c * 4 + 3]) : "memory");
-            }
-            fence_proxy_async();
+            // P_t -> this half's TMEM tile: lane = query row, 32 columns of bf16 pairs = the A operand of P V_t, read by the
+            // tensor core straight from tensor memory.  (Through shared memory, P cost 16 KB of stores + 16 KB of operand reads
+            // per block on a shared-memory pipe that the MMA operand traffic already keeps 60 % busy.)
+            tmem_st_32x32(lane_addr + P_COL + half * (BKV / 2), pk);
+            tmem_st_wait();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&p_full[half]));
