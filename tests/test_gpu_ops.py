@@ -491,7 +491,8 @@ def test_attention_masks(ops, dt, Dh):
     assert rel_err(out.float(), ref) < tol
 
 
-@pytest.mark.parametrize('B,S,H', [(2, 300, 4), (3, 128, 2), (2, 77, 16), (2, 900, 3), (1, 1, 1), (4, 129, 2)])
+@pytest.mark.parametrize('B,S,H', [(2, 300, 4), (3, 128, 2), (2, 77, 16), (2, 900, 3), (1, 1, 1), (4, 129, 2), (2, 1125, 2), (1, 64, 1),
+                                   (1, 65, 1), (1, 192, 1)])
 @pytest.mark.parametrize('mode', ['none', 'prefix', 'ragged'])
 def test_attention_prefill_tc(ops, B, S, H, mode):
     """tcgen05 flash attention vs a float64 dense softmax on the same bf16 qkv."""

@@ -134,6 +134,40 @@ __global__ void mufu_probe_kernel(int R, long long* out, float* sink) {
     if (a == 123.f) sink[0] = a;
     if ((threadIdx.x & 31) == 0) out[blockIdx.x * 32 + (threadIdx.x >> 5)] = c1 - c0;
 }
+// packed ex2: two exponentials per instruction (bf16x2 / f16x2)
+template <int KIND>
+__global__ void mufu2_probe_kernel(int R, long long* out, uint32_t* sink) {
+    uint32_t x[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) x[k] = (KIND == 0 ? 0xbc00bc00u : 0xa000a000u) + threadIdx.x + k;
+    __syncthreads();
+    const long long c0 = clock64();
+    for (int i = 0; i < R; ++i) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            if (KIND == 0) asm volatile("ex2.approx.ftz.bf16x2 %0, %0;" : "+r"(x[k]));
+            else asm volatile("ex2.approx.f16x2 %0, %0;" : "+r"(x[k]));
+        }
+    }
+    const long long c1 = clock64();
+    uint32_t a = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a ^= x[k];
+    if (a == 0x12345u) sink[0] = a;
+    if ((threadIdx.x & 31) == 0) out[blockIdx.x * 32 + (threadIdx.x >> 5)] = c1 - c0;
+}
+template <int KIND> void run_mufu2(int warps, long long* d_out, uint32_t* d_sink) {
+    const int R = 512;
+    mufu2_probe_kernel<KIND><<<148, warps * 32>>>(R, d_out, d_sink);
+    cudaDeviceSynchronize();
+    std::vector<long long> h(148 * 32);
+    cudaMemcpy(h.data(), d_out, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+    long long mx = 0;
+    for (int i = 0; i < 148; ++i) for (int w = 0; w < warps; ++w) mx = h[i * 32 + w] > mx ? h[i * 32 + w] : mx;
+    printf("ex2 %s: %2d warps per SM: %.2f cycles per warp instruction per warp -> %.1f exponentials/cycle/SM\n", KIND == 0 ? "bf16x2" : "f16x2 ",
+           warps, static_cast<double>(mx) / (R * 8), 2 * warps * 32.0 * R * 8 / static_cast<double>(mx));
+}
+
 void run_mufu(int warps, long long* d_out, float* d_sink) {
     const int R = 512;
     mufu_probe_kernel<<<148, warps * 32>>>(R, d_out, d_sink);
@@ -190,6 +224,7 @@ int main() {
     cudaMalloc(&d_sink, 64);
     for (int active : {1, 2, 4}) run_ldtm(active, d_out, d_sink);
     for (int warps : {1, 4, 8, 16}) run_mufu(warps, d_out, reinterpret_cast<float*>(d_sink));
+    for (int warps : {4, 8}) { run_mufu2<0>(warps, d_out, d_sink); run_mufu2<1>(warps, d_out, d_sink); }
     const int R = 512;
     for (int grid : {148}) {
         run_all<0>(grid, R, d_out);
