@@ -148,7 +148,7 @@ def test_linear_bf16_inplace_residual(ops):
     assert rel_err(res, ref) < 1e-4
 
 
-@pytest.mark.parametrize('M', [1, 5, 16, 32, 33, 64, 200, 256])
+@pytest.mark.parametrize('M', [1, 5, 16, 32, 33, 64, 128, 129, 192, 193, 200, 256])
 @pytest.mark.parametrize('N,K', [(1025, 1024), (3072, 1024), (1024, 4096), (256, 256), (768, 64)])
 def test_linear_decode(ops, M, N, K):
     torch.manual_seed(6)
@@ -157,7 +157,9 @@ def test_linear_decode(ops, M, N, K):
     ns_max = 32
     part = torch.full((ns_max, M, N), float('nan'), device='cuda')
     ns = ops.linear_decode(x, w, part, M * N, ns_max, flags=(M % 2))     # odd M also exercises the late PDL trigger
-    assert ns == ops.linear_decode_splits(N, K, ns_max) and 1 <= ns <= ns_max
+    assert ns == ops.linear_decode_splits(N, K, ns_max, M) and 1 <= ns <= ns_max       # above 192 rows: batch tiles, fewer slices
+    if M <= 128:
+        assert ns == ops.linear_decode_splits(N, K, ns_max)
     torch.cuda.synchronize()
     y = part[:ns].sum(0)
     assert not torch.isnan(y).any()

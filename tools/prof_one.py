@@ -22,8 +22,8 @@ if what == 'attn_decode':            # BASELINE config 2 at the mean context: B=
     ws = torch.zeros(ops.attn_decode_ws_bytes(B, H, 1) // 4 + 64, device='cuda', dtype=torch.int32)
     for li in range(12):
         ops.attn_decode_paged(part, 6, B * 3 * d, pools[li], bt, seq, o, B, H, 64, 1, ws)
-elif what == 'gemm_decode':          # the four weight-streaming GEMMs of one decode layer at B=32
-    B = 32
+elif what == 'gemm_decode':          # the four weight-streaming GEMMs of one decode layer at B = argv[2] (default 32)
+    B = int(sys.argv[2]) if len(sys.argv) > 2 else 32
     h = torch.randn(B, d, device='cuda').bfloat16()
     f = torch.randn(B, F, device='cuda').bfloat16()
     for rep in range(3):

@@ -57,3 +57,11 @@ for B in [int(a) for a in sys.argv[1:]] or [1, 32]:
         setattr(ops, k, v)
     print(f'B={B:3d}  step {full:7.1f} us | without attention {no_attn:7.1f} | attention only (+embed, sample) {only_attn:7.1f} '
           f'| sum of parts {no_attn + only_attn:7.1f}  launches {eng.launches_per_step()}')
+    if os.environ.get('BREAKDOWN_FAMILIES'):       # leave out one kernel family of the chain at a time
+        for fam in (('linear_decode',), ('residual_layernorm',), ('reduce_bias_act',), ('residual_layernorm', 'reduce_bias_act')):
+            for k in fam:
+                setattr(ops, k, lambda *a, **kw: 1)
+            t = timed_step()
+            for k, v in real.items():
+                setattr(ops, k, v)
+            print(f'        without {"+".join(fam):40s} {t:7.1f} us  (-{full - t:6.1f})')

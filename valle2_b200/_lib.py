@@ -28,6 +28,7 @@ SIGNATURES = {
     'vb_linear': (_i, [_p, _i, _i64, _p, _i, _i64, _p, _p, _i64, _p, _i, _i64, _i64, _i64, _i64, _i, _p]),
     'vb_linear_t': (_i, [_p, _i64, _i, _p, _i64, _i, _p, _p, _i64, _p, _i, _i64, _i64, _i64, _i64, _i, _p]),
     'vb_linear_decode_splits': (_i, [_i64, _i64, _i]),
+    'vb_linear_decode_splits_m': (_i, [_i64, _i64, _i64, _i]),
     'vb_linear_decode': (_i, [_p, _i64, _p, _i64, _p, _i64, _i64, _i64, _i64, _i, _i, _p, _p]),
     'vb_linear_decode_rows_splits': (_i, [_i, _i64, _i]),
     'vb_linear_decode_rows_ln': (_i, [_p, _i64, _p, _p, _f, _p, _i64, _p, _p, _i, _i64, _i, _i64, _i64, _i, _i, _p]),

@@ -9,6 +9,8 @@
 //   swap-AB: A = w [N][K], B = x [M<=256][K] -> part[s][m][n]  (decode: weight rows fill the 128-row MMA-M, the batch
 //            sits on MMA-N, split-K slices are written as deterministic fp32 partials)
 // Replaces the nn.Linear call sites modules.py:146,171,220-221 and valle_ar.py:158 / valle_nar.py:157.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace {
@@ -107,7 +109,7 @@ __global__ void __launch_bounds__(num_threads(SWAP), 1) gemm_tc_kernel(const __g
             // expects the bytes of both tiles.
             auto tile_of = [&](int t, int& ta, int& tb, int& kb0, int& kb1) {
                 int split;
-                if (SWAP) { ta = t % p.tiles_a; split = t / p.tiles_a; tb = 0; }
+                if (SWAP) { ta = t % p.tiles_a; const int r = t / p.tiles_a; tb = r % p.tiles_b; split = r / p.tiles_b; }
                 else      { tb = t % p.tiles_b; ta = t / p.tiles_b; split = 0; }
                 kb0 = split * p.kb_per_split;
                 kb1 = min(kb0 + p.kb_per_split, p.kb_total);
@@ -174,7 +176,7 @@ __global__ void __launch_bounds__(num_threads(SWAP), 1) gemm_tc_kernel(const __g
             uint32_t phase = 0;
             int local = 0;
             for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++local) {
-                const int split = SWAP ? t / p.tiles_a : 0;
+                const int split = SWAP ? t / (p.tiles_a * p.tiles_b) : 0;
                 const int kb0 = split * p.kb_per_split;
                 const int kb1 = min(kb0 + p.kb_per_split, p.kb_total);
                 const int acc = local & 1;
@@ -211,7 +213,7 @@ __global__ void __launch_bounds__(num_threads(SWAP), 1) gemm_tc_kernel(const __g
         if (p.late_trigger) pdl_trigger();
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++local) {
             int ta, tb, split;
-            if (SWAP) { ta = t % p.tiles_a; split = t / p.tiles_a; tb = 0; }
+            if (SWAP) { ta = t % p.tiles_a; const int r = t / p.tiles_a; tb = r % p.tiles_b; split = r / p.tiles_b; }
             else      { tb = t % p.tiles_b; ta = t / p.tiles_b; split = 0; }
             const int kb0 = split * p.kb_per_split;
             const bool empty_slice = kb0 >= p.kb_total;   // a split past the end of K: contributes zeros
@@ -246,7 +248,8 @@ __global__ void __launch_bounds__(num_threads(SWAP), 1) gemm_tc_kernel(const __g
             const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * ACC_COLS;
             const int row = ta * BM + q * 32 + lane;  // row of the A operand owned by this thread
             if (SWAP) {
-                // D[n][m]: this thread owns weight row n; columns are batch rows m.
+                // D[n][m]: this thread owns weight row n; columns are batch rows m0 + m of batch tile tb.
+                const int m0 = tb * BN;
                 float* dst = p.part + split * p.part_stride + row;
                 constexpr int CH = (BN >= 32) ? 32 : 16;
                 const int ew = warp - 2;
@@ -257,7 +260,7 @@ __global__ void __launch_bounds__(num_threads(SWAP), 1) gemm_tc_kernel(const __g
                 const bool vec = ((p.part_ld & 3) == 0) && ((p.part_stride & 3) == 0) && (ta * BM + q * 32 + 32 <= p.rows_a);
 #pragma unroll 1
                 for (int c0 = 0; c0 < BN; c0 += CH) {
-                    if (c0 >= p.rows_b) break;
+                    if (m0 + c0 >= p.rows_b) break;
                     uint32_t v[CH];
                     if constexpr (CH == 32) tmem_ld_32x32(t_addr + c0, reinterpret_cast<uint32_t(&)[32]>(v));
                     else tmem_ld_32x16(t_addr + c0, reinterpret_cast<uint32_t(&)[16]>(v));
@@ -282,7 +285,7 @@ __global__ void __launch_bounds__(num_threads(SWAP), 1) gemm_tc_kernel(const __g
                         const int n4 = (lane & 7) * 4, msub = lane >> 3;
 #pragma unroll
                         for (int it = 0; it < CH / 4; ++it) {
-                            const int mm = it * 4 + msub, m = c0 + mm;
+                            const int mm = it * 4 + msub, m = m0 + c0 + mm;
                             if (m < p.rows_b) {
                                 const float4 val = *reinterpret_cast<const float4*>(stg + mm * 32 + n4);
                                 *reinterpret_cast<float4*>(p.part + split * p.part_stride + static_cast<int64_t>(m) * p.part_ld + ta * BM + q * 32 + n4) = val;
@@ -292,7 +295,7 @@ __global__ void __launch_bounds__(num_threads(SWAP), 1) gemm_tc_kernel(const __g
                     } else if (row < p.rows_a) {
 #pragma unroll
                         for (int j = 0; j < CH; ++j) {
-                            const int m = c0 + j;
+                            const int m = m0 + c0 + j;
                             if (m < p.rows_b) dst[m * p.part_ld] = empty_slice ? 0.f : __uint_as_float(v[j]);
                         }
                     }
@@ -469,7 +472,21 @@ int vb_linear_tc_t(const void* x, int64_t ldx, int x_mn, const void* w, int64_t 
 }
 
 // split K so that (N/128 slabs) x splits fills the SMs, with at least 2 k-blocks (128 columns of K) per slice
-extern "C" int vb_linear_decode_splits(int64_t N, int64_t K, int max_split) {
+// Above 192 batch rows the batch is tiled too (128 rows per tile, MMA-N = 128): twice the CTAs per split, so half the splits --
+// half the slice bytes to write and re-read, and a 64 KB instead of a 128 KB epilogue per CTA.  Measured (decode step, batch
+// 256 / 160): 2.142 / 1.487 ms tiled against 2.171 / 1.471 ms with one 256-row tile, so 129..192 rows keep the single tile.
+static int decode_batch_tiles(int64_t M) {
+    static const bool wide = getenv("VALLE_B200_SWAP_BN256") != nullptr;      // experiment: one 256-row batch tile as in round 1
+    return (M > 192 && !wide) ? (int)vb_ceil_div(M, 128) : 1;
+}
+extern "C" int vb_linear_decode_splits_m(int64_t M, int64_t N, int64_t K, int max_split) {
+    const int tiles_a = (int)vb_ceil_div(N, BM) * decode_batch_tiles(M), kb_total = (int)vb_ceil_div(K, BK);
+    const int want = (int)vb_ceil_div(vb_sm_count(), tiles_a);
+    int n_split = max(1, min(min(want, max_split), max(1, kb_total / 2)));
+    const int kb_per_split = (int)vb_ceil_div(kb_total, n_split);
+    return (int)vb_ceil_div(kb_total, kb_per_split);
+}
+extern "C" int vb_linear_decode_splits(int64_t N, int64_t K, int max_split) {      // batch <= 128
     const int tiles_a = (int)vb_ceil_div(N, BM), kb_total = (int)vb_ceil_div(K, BK);
     const int want = (int)vb_ceil_div(vb_sm_count(), tiles_a);
     int n_split = max(1, min(min(want, max_split), max(1, kb_total / 2)));
@@ -492,9 +509,9 @@ extern "C" int vb_linear_decode(const void* x, int64_t ldx, const void* w, int64
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     GemmParams p{};
     p.rows_a = (int)N; p.rows_b = (int)M; p.K = (int)K;
-    p.tiles_a = (int)vb_ceil_div(N, BM); p.tiles_b = 1;
+    p.tiles_a = (int)vb_ceil_div(N, BM); p.tiles_b = decode_batch_tiles(M);
     p.kb_total = (int)vb_ceil_div(K, BK);
-    const int n_split = vb_linear_decode_splits(N, K, max_split);
+    const int n_split = vb_linear_decode_splits_m(M, N, K, max_split);
     p.kb_per_split = (int)vb_ceil_div(p.kb_total, n_split);
     p.n_split = n_split;
     p.part = part; p.part_stride = part_stride; p.part_ld = N;
@@ -514,7 +531,7 @@ extern "C" int vb_linear_decode(const void* x, int64_t ldx, const void* w, int64
     if (M <= 16) DECODE_CASE(16, 4)
     if (M <= 32) DECODE_CASE(32, 4)
     if (M <= 64) DECODE_CASE(64, 4)
-    if (M <= 128) DECODE_CASE(128, 4)
+    if (M <= 128 || p.tiles_b > 1) DECODE_CASE(128, 4)      /* p.tiles_b > 1: two 128-row batch tiles */
     DECODE_CASE(256, 4)
 #undef DECODE_CASE
 }

@@ -258,7 +258,7 @@ class ARDecoder:
             sub['qkv32'] = torch.zeros(B, 3 * d, device=dev, dtype=torch.float32)
             if self.decode_gemm == 'splitk' or (self.decode_gemm == 'auto' and B > 32) or B > 256:
                 ms = 32
-                ns = {k: ops.linear_decode_splits(n, kk, ms) for k, (n, kk) in
+                ns = {k: ops.linear_decode_splits(n, kk, ms, B) for k, (n, kk) in
                       {'qkv': (3 * d, d), 'o': (d, d), 'f1': (F, d), 'f2': (d, F), 'lg': (V, d)}.items()}
                 sub['ns'] = ns
                 sub['p_qkv'] = torch.zeros(ns['qkv'], B, 3 * d, device=dev, dtype=torch.float32)

@@ -131,8 +131,11 @@ def linear_t(x: torch.Tensor, w: torch.Tensor, *, x_t: bool = False, w_t: bool =
     return out
 
 
-def linear_decode_splits(N: int, K: int, max_split: int) -> int:
-    return int(_L().vb_linear_decode_splits(N, K, max_split))
+def linear_decode_splits(N: int, K: int, max_split: int, M: int | None = None) -> int:
+    """Split-K slice count vb_linear_decode uses for an (M, K) x (N, K)^T product (M = None: any batch up to 128 rows)."""
+    if M is None:
+        return int(_L().vb_linear_decode_splits(N, K, max_split))
+    return int(_L().vb_linear_decode_splits_m(M, N, K, max_split))
 
 
 def linear_decode(x: torch.Tensor, w: torch.Tensor, part: torch.Tensor, part_stride: int, max_split: int,
