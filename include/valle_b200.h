@@ -113,7 +113,7 @@ int vb_linear_t(const void* x, int64_t ldx, int x_transposed, const void* w, int
  * Deterministic: consumers (vb_residual_layernorm / vb_reduce_bias_act / vb_attn_decode_paged / vb_sample) add the
  * slices in index order.  x,w bf16.  Returns the split count actually used in *n_split_out (<= max_split). */
 int vb_linear_decode_splits(int64_t N, int64_t K, int max_split);   /* pure query: the split count vb_linear_decode uses */
-int vb_linear_decode_splits_m(int64_t M, int64_t N, int64_t K, int max_split);   /* the same for M batch rows: above 192 rows the
+int vb_linear_decode_splits_m(int64_t M, int64_t N, int64_t K, int max_split);   /* the same for M batch rows: above 128 rows the
                                                                                     batch is tiled as well and fewer splits are used */
 /* flags: VB_FLAG_LATE_TRIGGER -- programmatic dependent launch: the kernel lets its successor start only after it has
  * itself waited for its predecessor, so the successor's pre-wait code may read anything written before this kernel

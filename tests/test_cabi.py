@@ -31,7 +31,7 @@ def test_pure_queries_need_no_gpu():
     assert lib.vb_attn_decode_ws_bytes(32, 16, 4) > 32 * 16 * 4 * 64 * 4
     ns = lib.vb_linear_decode_splits(3072, 1024, 32)
     assert 1 <= ns <= 8
-    assert lib.vb_linear_decode_splits_m(64, 3072, 1024, 32) == ns                 # up to 192 batch rows: the same
+    assert lib.vb_linear_decode_splits_m(64, 3072, 1024, 32) == ns                 # up to 128 batch rows: the same
     assert 1 <= lib.vb_linear_decode_splits_m(256, 3072, 1024, 32) <= ns           # above: batch tiles, never more slices
 
 

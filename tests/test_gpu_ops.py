@@ -157,9 +157,11 @@ def test_linear_decode(ops, M, N, K):
     ns_max = 32
     part = torch.full((ns_max, M, N), float('nan'), device='cuda')
     ns = ops.linear_decode(x, w, part, M * N, ns_max, flags=(M % 2))     # odd M also exercises the late PDL trigger
-    assert ns == ops.linear_decode_splits(N, K, ns_max, M) and 1 <= ns <= ns_max       # above 192 rows: batch tiles, fewer slices
+    assert ns == ops.linear_decode_splits(N, K, ns_max, M) and 1 <= ns <= ns_max       # above 128 rows: batch tiles, fewer slices
     if M <= 128:
         assert ns == ops.linear_decode_splits(N, K, ns_max)
+    else:
+        assert ns * -(-N // 128) * -(-M // 128) <= ops.device_info()['sm_count'] or ns == 1          # one wave
     torch.cuda.synchronize()
     y = part[:ns].sum(0)
     assert not torch.isnan(y).any()

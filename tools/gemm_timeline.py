@@ -1,5 +1,5 @@
 """In-kernel timeline of the decode GEMM (split-K slices) inside a PDL chain: %globaltimer stamps per CTA.
-    python tools/gemm_timeline.py"""
+    python tools/gemm_timeline.py [B]"""
 import sys
 
 import numpy as np
@@ -9,14 +9,14 @@ sys.path.insert(0, '.')
 from valle2_b200 import _lib, ops  # noqa: E402
 
 dev, bf = 'cuda', torch.bfloat16
-B, d, F = 32, 1024, 4096
+B, d, F = (int(sys.argv[1]) if len(sys.argv) > 1 else 32), 1024, 4096
 lib = _lib.load()
 sm = ops.device_info()['sm_count']
 names = ['prologue', 'w requested', 'dep resolved', '1st kblock', 'mma issued', 'acc done', 'acc in regs', 'epi done']
 for k, (n, kk) in {'qkv': (3 * d, d), 'o': (d, d), 'f1': (F, d), 'f2': (d, F)}.items():
     ws = [(torch.randn(n, kk, device=dev) / 32).to(bf) for _ in range(6)]
     a = torch.randn(B, kk, device=dev).to(bf)
-    ns = ops.linear_decode_splits(n, kk, 32)
+    ns = ops.linear_decode_splits(n, kk, 32, B)
     part = torch.zeros(ns, B, n, device=dev)
     dbgs = [torch.zeros(sm, 16, device=dev, dtype=torch.int64) for _ in range(6)]
 

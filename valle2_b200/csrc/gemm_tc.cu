@@ -472,19 +472,28 @@ int vb_linear_tc_t(const void* x, int64_t ldx, int x_mn, const void* w, int64_t 
 }
 
 // split K so that (N/128 slabs) x splits fills the SMs, with at least 2 k-blocks (128 columns of K) per slice
-// Above 192 batch rows the batch is tiled too (128 rows per tile, MMA-N = 128): twice the CTAs per split, so half the splits --
-// half the slice bytes to write and re-read, and a 64 KB instead of a 128 KB epilogue per CTA.  Measured (decode step, batch
-// 256 / 160): 2.142 / 1.487 ms tiled against 2.171 / 1.471 ms with one 256-row tile, so 129..192 rows keep the single tile.
+// Above 128 batch rows the batch is tiled too (128 rows per tile, MMA-N = 128) and the split count is the largest whose
+// (weight tile x batch tile x split) grid still fits on the SMs in ONE wave: half the slice bytes to write and re-read, a 64 KB
+// instead of a 128 KB epilogue per CTA, no CTA with two tiles.  Decode step at batch 136 / 160 / 192 / 224 / 256: 1.254 / 1.410 /
+// 1.667 / 1.865 / 2.058 ms against 1.303 / 1.471 / 1.735 / 1.956 / 2.179 ms with one 256-row tile (profiles/r02c_ab_decode_batch_tiles.jsonl).
 static int decode_batch_tiles(int64_t M) {
     static const bool wide = getenv("VALLE_B200_SWAP_BN256") != nullptr;      // experiment: one 256-row batch tile as in round 1
-    return (M > 192 && !wide) ? (int)vb_ceil_div(M, 128) : 1;
+    static const int tile_min = getenv("VALLE_B200_SWAP_TILE_MIN") ? atoi(getenv("VALLE_B200_SWAP_TILE_MIN")) : 129;
+    return (M >= tile_min && !wide) ? (int)vb_ceil_div(M, 128) : 1;
 }
 extern "C" int vb_linear_decode_splits_m(int64_t M, int64_t N, int64_t K, int max_split) {
-    const int tiles_a = (int)vb_ceil_div(N, BM) * decode_batch_tiles(M), kb_total = (int)vb_ceil_div(K, BK);
-    const int want = (int)vb_ceil_div(vb_sm_count(), tiles_a);
-    int n_split = max(1, min(min(want, max_split), max(1, kb_total / 2)));
-    const int kb_per_split = (int)vb_ceil_div(kb_total, n_split);
-    return (int)vb_ceil_div(kb_total, kb_per_split);
+    const int tb = decode_batch_tiles(M);
+    if (tb == 1) return vb_linear_decode_splits(N, K, max_split);
+    // tiled batch: every (weight tile, batch tile, split) must get its own CTA -- with 1.3 waves the last epilogue ends 2 us
+    // after the median one (tools/gemm_timeline.py 256) -- so the largest split count whose tiles still fit on the SMs
+    const int tiles = (int)vb_ceil_div(N, BM) * tb, kb_total = (int)vb_ceil_div(K, BK);
+    int n_split = max(1, min(min(vb_sm_count() / tiles, max_split), max(1, kb_total / 2)));
+    for (;;) {
+        const int kb_per_split = (int)vb_ceil_div(kb_total, n_split);
+        const int eff = (int)vb_ceil_div(kb_total, kb_per_split);
+        if (eff * tiles <= vb_sm_count() || n_split == 1) return eff;
+        --n_split;
+    }
 }
 extern "C" int vb_linear_decode_splits(int64_t N, int64_t K, int max_split) {      // batch <= 128
     const int tiles_a = (int)vb_ceil_div(N, BM), kb_total = (int)vb_ceil_div(K, BK);
