@@ -153,3 +153,21 @@ int vb_make_tmap_bf16_3d(CUtensorMap* map, const void* base, int64_t d0, int64_t
     VB_REQUIRE(r == CUDA_SUCCESS, VB_ERR_CUDA, "cuTensorMapEncodeTiled(3d) failed: CUresult %d", (int)r);
     return VB_OK;
 }
+
+// 3D fp32 [d2][d1][d0] (d0 contiguous), strides in elements; box = [1][box1][box0], no swizzle: the destination of TMA stores
+int vb_make_tmap_f32_3d(CUtensorMap* map, const void* base, int64_t d0, int64_t d1, int64_t d2, int64_t s1, int64_t s2, int box0,
+                        int box1) {
+    PFN_encodeTiled enc = get_encode();
+    VB_REQUIRE(enc != nullptr, VB_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    VB_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0 && (s1 * 4) % 16 == 0 && (s2 * 4) % 16 == 0, VB_ERR_BAD_ARG,
+               "TMA operand must be 16-byte aligned with 16-byte multiple strides");
+    cuuint64_t dims[3] = {static_cast<cuuint64_t>(d0), static_cast<cuuint64_t>(d1), static_cast<cuuint64_t>(d2)};
+    cuuint64_t strides[2] = {static_cast<cuuint64_t>(s1) * 4, static_cast<cuuint64_t>(s2) * 4};
+    cuuint32_t box[3] = {static_cast<cuuint32_t>(box0), static_cast<cuuint32_t>(box1), 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    VB_REQUIRE(r == CUDA_SUCCESS, VB_ERR_CUDA, "cuTensorMapEncodeTiled(f32 3d) failed: CUresult %d", (int)r);
+    return VB_OK;
+}

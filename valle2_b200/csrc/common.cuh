@@ -214,6 +214,17 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
         ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
 }
+// TMA store shared -> global (bulk-group completion): the box of `map` at coordinates (c0, c1, c2) is written from dense smem rows
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                 ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all but the newest N bulk groups of this thread have finished READING their shared-memory source
+template <int N> __device__ __forceinline__ void bulk_wait_group_read() {
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -312,3 +323,6 @@ int vb_make_tmap_bf16_2d(CUtensorMap* map, const void* base, int64_t rows, int64
 // 3D bf16 [d2][d1][d0] (d0 contiguous), strides in elements; box = [1][box1][box0]
 int vb_make_tmap_bf16_3d(CUtensorMap* map, const void* base, int64_t d0, int64_t d1, int64_t d2, int64_t s1, int64_t s2,
                          int box0, int box1);
+// 3D fp32 [d2][d1][d0], strides in elements; box = [1][box1][box0], no swizzle (TMA store destination)
+int vb_make_tmap_f32_3d(CUtensorMap* map, const void* base, int64_t d0, int64_t d1, int64_t d2, int64_t s1, int64_t s2, int box0,
+                        int box1);

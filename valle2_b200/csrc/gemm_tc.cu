@@ -21,6 +21,7 @@ constexpr int UMMA_K = 16;
 constexpr int epi_warps(bool swap) { return swap ? 4 : 8; }
 constexpr int num_threads(bool swap) { return 64 + 32 * epi_warps(swap); }
 constexpr int STG_BYTES_PER_WARP = 32 * 128;   // epilogue staging: 32 rows x 32 fp32, 128B-swizzled
+constexpr int stg_bufs(bool swap) { return swap ? 2 : 1; }   // the split-K slices leave by TMA store: two staging tiles in flight
 
 struct GemmParams {
     int rows_a, rows_b, K;
@@ -37,6 +38,7 @@ struct GemmParams {
     int64_t part_stride;
     int64_t part_ld;           // N (row pitch of a partial slice)
     int late_trigger;          // release the dependent kernel only after our own pdl_wait (see vb_linear_decode flags)
+    int tma_store;             // swap-AB: the slices are written by TMA stores through tm_p (needs 16-byte aligned slice rows)
     unsigned long long* dbg;   // optional %globaltimer stamps [cta][8] (vb_linear_decode_set_debug)
 };
 
@@ -55,7 +57,8 @@ __device__ __forceinline__ unsigned long long gtimer() {
 // TMA; UMMA descriptor: start advances 2 KB per 16 k rows, LBO = atom pitch (8 KB), SBO = 8-row group pitch (1 KB).
 template <int BN, int STAGES, bool SWAP, bool A_MN = false, bool B_MN = false>
 __global__ void __launch_bounds__(num_threads(SWAP), 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a,
-                                                                 const __grid_constant__ CUtensorMap tm_b, GemmParams p) {
+                                                                 const __grid_constant__ CUtensorMap tm_b,
+                                                                 const __grid_constant__ CUtensorMap tm_p, GemmParams p) {
     constexpr int A_BYTES = BM * BK * 2;
     constexpr int B_BYTES = BN * BK * 2;
     constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
@@ -253,7 +256,39 @@ __global__ void __launch_bounds__(num_threads(SWAP), 1) gemm_tc_kernel(const __g
                 float* dst = p.part + split * p.part_stride + row;
                 constexpr int CH = (BN >= 32) ? 32 : 16;
                 const int ew = warp - 2;
-                float* stg = reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw)) + STAGES * STAGE_BYTES) + ew * (32 * 32);
+                float* stg = reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw)) + STAGES * STAGE_BYTES) + ew * (stg_bufs(SWAP) * 32 * 32);
+                if (p.tma_store) {
+                    // The warp's 32 weight rows x 32 batch rows of a chunk are transposed into a dense [m][n] staging tile and
+                    // leave as ONE TMA store (box 32 x 32 of the [split][m][n] slice tensor, rows / columns past the end clipped
+                    // by the tensor map): with 16-byte stores from the lanes the epilogue of a 128 x 128 tile took 3 530 cycles,
+                    // ~50 cycles per store instruction (tools/gemm_timeline.py 256).  Two staging tiles per warp alternate.
+                    int buf = 0, issued = 0;
+#pragma unroll 1
+                    for (int c0 = 0; c0 < BN; c0 += 32) {
+                        if (m0 + c0 >= p.rows_b) break;
+                        uint32_t v[32];
+                        tmem_ld_32x32(t_addr + c0, v);
+                        tmem_ld_wait();
+                        if (threadIdx.x == 64 && c0 == 0) DBG_STAMP(6);           // accumulator in registers
+                        float* sb = stg + buf * (32 * 32);
+                        if (issued >= 2) {      // the store that last read this staging tile must have finished reading it
+                            if (lane == 0) bulk_wait_group_read<1>();
+                            __syncwarp();
+                        }
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) sb[j * 32 + lane] = empty_slice ? 0.f : __uint_as_float(v[j]);
+                        fence_proxy_async();
+                        __syncwarp();
+                        if (lane == 0) {
+                            tma_store_3d(&tm_p, smem_u32(sb), ta * BM + q * 32, m0 + c0, split);
+                            bulk_commit_group();
+                        }
+                        ++issued;
+                        buf ^= 1;
+                    }
+                    if (lane == 0) bulk_wait_group_read<0>();
+                    __syncwarp();
+                } else {
                 // vector path: the warp's 32 weight rows x 32 batch rows go through a shared-memory transpose so that each
                 // store instruction writes 16 bytes per lane along n (8 lanes = one 128-byte row segment) -- four times fewer
                 // store instructions than one 4-byte store per (n, m) (measured: ~50 cycles per store instruction)
@@ -299,6 +334,7 @@ __global__ void __launch_bounds__(num_threads(SWAP), 1) gemm_tc_kernel(const __g
                             if (m < p.rows_b) dst[m * p.part_ld] = empty_slice ? 0.f : __uint_as_float(v[j]);
                         }
                     }
+                }
                 }
             } else {
                 // Normal orientation.  Each quadrant is served by two warps (column halves).  A 32-column chunk goes
@@ -399,8 +435,8 @@ __global__ void __launch_bounds__(num_threads(SWAP), 1) gemm_tc_kernel(const __g
 }
 
 template <int BN, int STAGES, bool SWAP, bool A_MN = false, bool B_MN = false>
-int launch_gemm_tc(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
-    constexpr int SMEM = STAGES * (BM * BK * 2 + BN * BK * 2) + 1024 + epi_warps(SWAP) * STG_BYTES_PER_WARP;
+int launch_gemm_tc(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st, const CUtensorMap* tp = nullptr) {
+    constexpr int SMEM = STAGES * (BM * BK * 2 + BN * BK * 2) + 1024 + epi_warps(SWAP) * stg_bufs(SWAP) * STG_BYTES_PER_WARP;
     static bool configured = false;
     auto kern = gemm_tc_kernel<BN, STAGES, SWAP, A_MN, B_MN>;
     if (!configured) {
@@ -409,7 +445,8 @@ int launch_gemm_tc(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParam
     }
     const int total = p.tiles_a * p.tiles_b * p.n_split;
     const int grid = min(total, vb_sm_count());
-    VB_CUDA(vb_launch(SWAP, kern, dim3(grid), dim3(num_threads(SWAP)), SMEM, st, ta, tb, p));
+    static const CUtensorMap no_map{};
+    VB_CUDA(vb_launch(SWAP, kern, dim3(grid), dim3(num_threads(SWAP)), SMEM, st, ta, tb, tp ? *tp : no_map, p));
     return VB_OK;
 }
 
@@ -529,13 +566,17 @@ extern "C" int vb_linear_decode(const void* x, int64_t ldx, const void* w, int64
 
     VB_REQUIRE(n_split == 1 || part_stride >= M * N, VB_ERR_BAD_ARG, "vb_linear_decode: part_stride too small");
     if (n_split_out) *n_split_out = n_split;
-    CUtensorMap ta, tb;
+    CUtensorMap ta, tb, tp;
     int rc;
     if ((rc = vb_make_tmap_bf16_2d(&ta, w, N, K, ldw, BM, BK)) != VB_OK) return rc;
+    // slices [split][m][n] as a TMA store destination (32 x 32 boxes) when their rows are 16-byte aligned
+    static const bool no_tma_store = getenv("VALLE_B200_NO_TMA_STORE") != nullptr;      // experiment: 16-byte stores from the lanes
+    p.tma_store = (!no_tma_store && M > 16 && (N & 3) == 0 && (part_stride & 3) == 0 && (reinterpret_cast<uintptr_t>(part) & 15) == 0) ? 1 : 0;
+    if (p.tma_store && (rc = vb_make_tmap_f32_3d(&tp, part, N, M, n_split, N, n_split > 1 ? part_stride : M * N, 32, 32)) != VB_OK) return rc;
 #define DECODE_CASE(BNV, ST)                                                             \
     {                                                                                    \
         if ((rc = vb_make_tmap_bf16_2d(&tb, x, M, K, ldx, BNV, BK)) != VB_OK) return rc; \
-        return launch_gemm_tc<BNV, ST, true>(ta, tb, p, st);                             \
+        return launch_gemm_tc<BNV, ST, true>(ta, tb, p, st, p.tma_store ? &tp : nullptr); \
     }
     if (M <= 16) DECODE_CASE(16, 4)
     if (M <= 32) DECODE_CASE(32, 4)
