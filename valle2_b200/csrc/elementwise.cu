@@ -416,7 +416,10 @@ template <typename TY>
 static int launch_rln(float* x, const float* part, int n_part, int64_t part_stride, const float* bias, const float* gamma,
                       const float* beta, TY* y, int64_t R, int d, float eps, cudaStream_t st) {
     static const bool ln_cluster = !(getenv("VALLE_B200_LN_CLUSTER") != nullptr && getenv("VALLE_B200_LN_CLUSTER")[0] == '0');
-    if (ln_cluster && g_ln_dbg == nullptr && R <= 1024 && n_part >= 4 && (d == 256 || d == 512 || d == 1024)) {
+    // The 4-CTA cluster per row is a latency form (one column per thread, the row statistics meet in DSMEM); above 160 rows
+    // the CTA-per-row form with float4 loads moves the slices faster: decode step at batch 256 / 192 1.976 / 1.593 vs 2.034 /
+    // 1.647 ms, at batch 160 / 128 1.397 / 1.209 vs 1.386 / 1.199 (profiles/r02d_ab_ln_cluster.jsonl)
+    if (ln_cluster && g_ln_dbg == nullptr && R <= 160 && n_part >= 4 && (d == 256 || d == 512 || d == 1024)) {
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(4, static_cast<unsigned>(R));
         cfg.blockDim = dim3(256);
