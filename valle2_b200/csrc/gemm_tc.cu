@@ -395,7 +395,11 @@ __global__ void __launch_bounds__(num_threads(SWAP), 1) gemm_tc_kernel(const __g
                         float4 v4 = f[it];
                         v4.x += b4.x; v4.y += b4.y; v4.z += b4.z; v4.w += b4.w;
                         if (p.epilogue == VB_EPI_BIAS_GELU) {
+                            #ifdef VB_GELU_MUFU      // experiment: the Abramowitz-Stegun form with two MUFU ops per value
                             const float2 g01 = gelu_erf_fast2(make_float2(v4.x, v4.y)), g23 = gelu_erf_fast2(make_float2(v4.z, v4.w));
+#else
+                            const float2 g01 = gelu_erf_poly2(make_float2(v4.x, v4.y)), g23 = gelu_erf_poly2(make_float2(v4.z, v4.w));
+#endif
                             v4 = make_float4(g01.x, g01.y, g23.x, g23.y);
                         }
                         if (vec_ok) {
