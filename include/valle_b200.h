@@ -108,7 +108,7 @@ int vb_linear_t(const void* x, int64_t ldx, int x_transposed, const void* w, int
                 const float* residual, int64_t ldr, void* y, int y_dtype, int64_t ldy, int64_t M, int64_t N, int64_t K,
                 int epilogue, void* stream);
 
-/* Decode-shape (M <= 256) weight-streaming GEMM, swap-AB on tcgen05 with split-K:
+/* Decode-shape (M <= 1024; above 128 rows the batch is tiled) weight-streaming GEMM, swap-AB on tcgen05 with split-K:
  *   part[s][m][n] = sum_{k in slice s} x[m,k] w[n,k]      s < n_split, fp32, part_stride = elements between slices.
  * Deterministic: consumers (vb_residual_layernorm / vb_reduce_bias_act / vb_attn_decode_paged / vb_sample) add the
  * slices in index order.  x,w bf16.  Returns the split count actually used in *n_split_out (<= max_split). */

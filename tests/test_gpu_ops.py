@@ -148,7 +148,7 @@ def test_linear_bf16_inplace_residual(ops):
     assert rel_err(res, ref) < 1e-4
 
 
-@pytest.mark.parametrize('M', [1, 5, 16, 32, 33, 64, 128, 129, 192, 193, 200, 256])
+@pytest.mark.parametrize('M', [1, 5, 16, 32, 33, 64, 128, 129, 192, 193, 200, 256, 300, 512])
 @pytest.mark.parametrize('N,K', [(1025, 1024), (3072, 1024), (1024, 4096), (256, 256), (768, 64)])
 def test_linear_decode(ops, M, N, K):
     torch.manual_seed(6)

@@ -517,11 +517,7 @@ int vb_linear_tc_t(const void* x, int64_t ldx, int x_mn, const void* w, int64_t 
 // (weight tile x batch tile x split) grid still fits on the SMs in ONE wave: half the slice bytes to write and re-read, a 64 KB
 // instead of a 128 KB epilogue per CTA, no CTA with two tiles.  Decode step at batch 136 / 160 / 192 / 224 / 256: 1.254 / 1.410 /
 // 1.667 / 1.865 / 2.058 ms against 1.303 / 1.471 / 1.735 / 1.956 / 2.179 ms with one 256-row tile (profiles/r02c_ab_decode_batch_tiles.jsonl).
-static int decode_batch_tiles(int64_t M) {
-    static const bool wide = getenv("VALLE_B200_SWAP_BN256") != nullptr;      // experiment: one 256-row batch tile as in round 1
-    static const int tile_min = getenv("VALLE_B200_SWAP_TILE_MIN") ? atoi(getenv("VALLE_B200_SWAP_TILE_MIN")) : 129;
-    return (M >= tile_min && !wide) ? (int)vb_ceil_div(M, 128) : 1;
-}
+static int decode_batch_tiles(int64_t M) { return M > 128 ? (int)vb_ceil_div(M, 128) : 1; }
 extern "C" int vb_linear_decode_splits_m(int64_t M, int64_t N, int64_t K, int max_split) {
     const int tb = decode_batch_tiles(M);
     if (tb == 1) return vb_linear_decode_splits(N, K, max_split);
@@ -553,7 +549,7 @@ extern "C" int vb_linear_decode_set_debug(void* buf) {   /* device buffer of #SM
 extern "C" int vb_linear_decode(const void* x, int64_t ldx, const void* w, int64_t ldw, float* part, int64_t part_stride,
                                 int64_t M, int64_t N, int64_t K, int max_split, int flags, int* n_split_out, void* stream) {
     VB_REQUIRE(x && w && part, VB_ERR_BAD_ARG, "vb_linear_decode: null pointer");
-    VB_REQUIRE(M >= 1 && M <= 256, VB_ERR_UNSUPPORTED, "vb_linear_decode: M must be in [1,256] (got %lld)", (long long)M);
+    VB_REQUIRE(M >= 1 && M <= 1024, VB_ERR_UNSUPPORTED, "vb_linear_decode: M must be in [1,1024] (got %lld)", (long long)M);
     VB_REQUIRE(K % 8 == 0 && N >= 1, VB_ERR_UNSUPPORTED, "vb_linear_decode: K %% 8 != 0 or N < 1");
     VB_REQUIRE(max_split >= 1, VB_ERR_BAD_ARG, "vb_linear_decode: max_split must be >= 1");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -574,8 +570,7 @@ extern "C" int vb_linear_decode(const void* x, int64_t ldx, const void* w, int64
     int rc;
     if ((rc = vb_make_tmap_bf16_2d(&ta, w, N, K, ldw, BM, BK)) != VB_OK) return rc;
     // slices [split][m][n] as a TMA store destination (32 x 32 boxes) when their rows are 16-byte aligned
-    static const bool no_tma_store = getenv("VALLE_B200_NO_TMA_STORE") != nullptr;      // experiment: 16-byte stores from the lanes
-    p.tma_store = (!no_tma_store && M > 16 && (N & 3) == 0 && (part_stride & 3) == 0 && (reinterpret_cast<uintptr_t>(part) & 15) == 0) ? 1 : 0;
+    p.tma_store = (M > 16 && (N & 3) == 0 && (part_stride & 3) == 0 && (reinterpret_cast<uintptr_t>(part) & 15) == 0) ? 1 : 0;
     if (p.tma_store && (rc = vb_make_tmap_f32_3d(&tp, part, N, M, n_split, N, n_split > 1 ? part_stride : M * N, 32, 32)) != VB_OK) return rc;
 #define DECODE_CASE(BNV, ST)                                                             \
     {                                                                                    \
@@ -585,7 +580,6 @@ extern "C" int vb_linear_decode(const void* x, int64_t ldx, const void* w, int64
     if (M <= 16) DECODE_CASE(16, 4)
     if (M <= 32) DECODE_CASE(32, 4)
     if (M <= 64) DECODE_CASE(64, 4)
-    if (M <= 128 || p.tiles_b > 1) DECODE_CASE(128, 4)      /* p.tiles_b > 1: two 128-row batch tiles */
-    DECODE_CASE(256, 4)
+    DECODE_CASE(128, 4)      /* M <= 128, or two 128-row batch tiles */
 #undef DECODE_CASE
 }

@@ -140,7 +140,7 @@ def linear_decode_splits(N: int, K: int, max_split: int, M: int | None = None) -
 
 def linear_decode(x: torch.Tensor, w: torch.Tensor, part: torch.Tensor, part_stride: int, max_split: int,
                   flags: int = 0) -> int:
-    """part[s][m][n] (fp32) = split-K slices of x @ w.T; x (M<=256,K) bf16, w (N,K) bf16.  Returns n_split."""
+    """part[s][m][n] (fp32) = split-K slices of x @ w.T; x (M<=1024,K) bf16, w (N,K) bf16.  Returns n_split."""
     assert x.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and part.dtype == torch.float32
     M, K = x.shape
     N = w.shape[0]
