@@ -55,12 +55,18 @@ __device__ __forceinline__ unsigned long long gtimer() {
 // GEMMs: dgrad reads W (N,K) as the MN-major B operand of dy.W, wgrad reads dy and x as MN-major A and B of dy^T.x, so no
 // operand is transposed in HBM first).  Tile = 64-wide MN atoms of [64 k rows][64 columns], 8 KB each, 128B-swizzled by
 // TMA; UMMA descriptor: start advances 2 KB per 16 k rows, LBO = atom pitch (8 KB), SBO = 8-row group pitch (1 KB).
-template <int BN, int STAGES, bool SWAP, bool A_MN = false, bool B_MN = false>
+// TWO: CTA pair (`cta_group::2`, cluster of two CTAs on one TPC).  The pair owns a 256 x BN output tile: each CTA loads its 128
+// rows of A and HALF of the B tile (BN/2 rows) per k-block, the leader CTA issues ONE tcgen05.mma of M = 256 that reads both
+// halves of B out of both CTAs' shared memory, and each CTA's tensor core accumulates its own 128 x BN rows in its own TMEM.
+// Per SM and k-block that is 32 KB of TMA writes and operand reads instead of 48 KB -- the single-CTA kernel streams
+// 94 B/clk/SM of operands at full MMA rate.  TMA loads of both CTAs complete on the LEADER's mbarrier, the MMA commits are
+// multicast to both CTAs' barriers, the accumulator-empty barrier collects the epilogue warps of both CTAs.
+template <int BN, int STAGES, bool SWAP, bool A_MN = false, bool B_MN = false, bool TWO = false>
 __global__ void __launch_bounds__(num_threads(SWAP), 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a,
                                                                  const __grid_constant__ CUtensorMap tm_b,
                                                                  const __grid_constant__ CUtensorMap tm_p, GemmParams p) {
     constexpr int A_BYTES = BM * BK * 2;
-    constexpr int B_BYTES = BN * BK * 2;
+    constexpr int B_BYTES = (TWO ? BN / 2 : BN) * BK * 2;
     constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     // NACC independent accumulators per tile (summed by the epilogue) were tried for the narrow decode tiles, on the theory
     // that four MMAs of a k-block accumulating into ONE TMEM tile run at MMA latency: measured no change (~400 cycles per
@@ -69,7 +75,11 @@ __global__ void __launch_bounds__(num_threads(SWAP), 1) gemm_tc_kernel(const __g
     constexpr int ACC_COLS = NACC * BN;             // TMEM columns of one (multi-)accumulator; two of them are in flight
     constexpr int TMEM_COLS = (2 * ACC_COLS <= 32) ? 32 : (2 * ACC_COLS <= 64) ? 64 : (2 * ACC_COLS <= 128) ? 128 : (2 * ACC_COLS <= 256) ? 256 : 512;
     static_assert(!(SWAP && (A_MN || B_MN)), "MN-major operands are for the large-M orientation");
-    constexpr uint32_t IDESC = umma_idesc_bf16(BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+    static_assert(!TWO || (!SWAP && !A_MN && !B_MN), "the CTA-pair form exists for the plain large-M orientation");
+    constexpr uint32_t IDESC = umma_idesc_bf16(TWO ? 2 * BM : BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+    constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;      // clears the CTA-rank bit of a shared::cluster address: the leader's copy
+    uint32_t cta_rank = 0;
+    if constexpr (TWO) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(cta_rank));
 
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[STAGES];
@@ -90,17 +100,32 @@ __global__ void __launch_bounds__(num_threads(SWAP), 1) gemm_tc_kernel(const __g
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(smem_u32(&tfull_bar[a]), 1);
-            mbar_init(smem_u32(&tempty_bar[a]), epi_warps(SWAP));
+            mbar_init(smem_u32(&tempty_bar[a]), (TWO ? 2 : 1) * epi_warps(SWAP));
         }
         fence_mbar_init();
     }
-    if (warp == 1) tmem_alloc<TMEM_COLS>(smem_u32(&tmem_base_slot));
+    if (warp == 1) {
+        if constexpr (TWO) {      // the same warp of both CTAs allocates the same columns in both tensor memories
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "n"(TMEM_COLS));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+        } else {
+            tmem_alloc<TMEM_COLS>(smem_u32(&tmem_base_slot));
+        }
+    }
     tc_fence_before();
-    __syncthreads();
+    if constexpr (TWO) {          // barrier inits and the allocation must be visible to the peer CTA before anything remote happens
+        asm volatile("barrier.cluster.arrive.release;" ::: "memory");
+        asm volatile("barrier.cluster.wait.acquire;" ::: "memory");
+    } else {
+        __syncthreads();
+    }
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_slot;
 
     const int total_tiles = p.tiles_a * p.tiles_b * p.n_split;
+    // work distribution: a CTA (a CTA pair when TWO) takes every tile_step-th tile starting at tile_first
+    const int tile_first = TWO ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+    const int tile_step = TWO ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
     if (threadIdx.x == 0) DBG_STAMP(0);                                   // prologue done
 
     if (!p.late_trigger) pdl_trigger();
@@ -114,13 +139,25 @@ __global__ void __launch_bounds__(num_threads(SWAP), 1) gemm_tc_kernel(const __g
                 int split;
                 if (SWAP) { ta = t % p.tiles_a; const int r = t / p.tiles_a; tb = r % p.tiles_b; split = r / p.tiles_b; }
                 else      { tb = t % p.tiles_b; ta = t / p.tiles_b; split = 0; }
+                if constexpr (TWO) ta = ta * 2 + static_cast<int>(cta_rank);      // this CTA's 128-row block of the pair's 256 rows
                 kb0 = split * p.kb_per_split;
                 kb1 = min(kb0 + p.kb_per_split, p.kb_total);
+            };
+            // CTA pair: both CTAs' loads complete on the leader's barrier, which expects the bytes of both
+            auto tma2 = [&](uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+                asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                             ::"r"(dst), "l"(map), "r"(bar & PEER_MASK), "r"(c0), "r"(c1) : "memory");
+            };
+            auto expect = [&](uint32_t bar) {
+                if constexpr (TWO) { if (cta_rank == 0) mbar_expect_tx(bar, 2 * STAGE_BYTES); }
+                else mbar_expect_tx(bar, STAGE_BYTES);
             };
             auto load_a = [&](uint32_t dst, uint32_t fb, int kb, int ta) {
                 if constexpr (A_MN) {
 #pragma unroll
                     for (int i = 0; i < BM / 64; ++i) tma_load_2d(dst + i * 8192, &tm_a, fb, ta * BM + i * 64, kb * BK);
+                } else if constexpr (TWO) {
+                    tma2(dst, &tm_a, fb, kb * BK, ta * BM);
                 } else {
                     tma_load_2d(dst, &tm_a, fb, kb * BK, ta * BM);
                 }
@@ -129,17 +166,19 @@ __global__ void __launch_bounds__(num_threads(SWAP), 1) gemm_tc_kernel(const __g
                 if constexpr (B_MN) {
 #pragma unroll
                     for (int i = 0; i < BN / 64; ++i) tma_load_2d(dst + i * 8192, &tm_b, fb, tb * BN + i * 64, kb * BK);
+                } else if constexpr (TWO) {
+                    tma2(dst, &tm_b, fb, kb * BK, tb * BN + static_cast<int>(cta_rank) * (BN / 2));      // this CTA's half of the B tile
                 } else {
                     tma_load_2d(dst, &tm_b, fb, kb * BK, tb * BN);
                 }
             };
             int pre = 0;   // ring slots already armed with their weight tile
-            for (int t = blockIdx.x; t < total_tiles && pre < STAGES; t += gridDim.x) {
+            for (int t = tile_first; t < total_tiles && pre < STAGES; t += tile_step) {
                 int ta, tb, kb0, kb1;
                 tile_of(t, ta, tb, kb0, kb1);
                 for (int kb = kb0; kb < kb1 && pre < STAGES; ++kb, ++pre) {
                     const uint32_t fb = smem_u32(&full_bar[pre]);
-                    mbar_expect_tx(fb, STAGE_BYTES);
+                    expect(fb);
                     const uint32_t sa = smem_base + pre * STAGE_BYTES;
                     if (SWAP) load_a(sa, fb, kb, ta);
                     else      load_b(sa + A_BYTES, fb, kb, tb);
@@ -151,7 +190,7 @@ __global__ void __launch_bounds__(num_threads(SWAP), 1) gemm_tc_kernel(const __g
             if (p.late_trigger) pdl_trigger();
             int stage = 0, n = 0;
             uint32_t phase = 0;
-            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+            for (int t = tile_first; t < total_tiles; t += tile_step) {
                 int ta, tb, kb0, kb1;
                 tile_of(t, ta, tb, kb0, kb1);
                 for (int kb = kb0; kb < kb1; ++kb, ++n) {
@@ -163,7 +202,7 @@ __global__ void __launch_bounds__(num_threads(SWAP), 1) gemm_tc_kernel(const __g
                     } else {
                         if (SWAP) mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
                         else mbar_wait_relaxed(smem_u32(&empty_bar[stage]), phase ^ 1);
-                        mbar_expect_tx(fb, STAGE_BYTES);
+                        expect(fb);
                         load_a(sa, fb, kb, ta);
                         load_b(sa + A_BYTES, fb, kb, tb);
                     }
@@ -174,11 +213,20 @@ __global__ void __launch_bounds__(num_threads(SWAP), 1) gemm_tc_kernel(const __g
         else if (p.late_trigger) { pdl_wait(); pdl_trigger(); }
     } else if (warp == 1) {
         if (p.late_trigger) { pdl_wait(); pdl_trigger(); }
-        if (elect_one()) {
+        if (elect_one() && (!TWO || cta_rank == 0)) {      // CTA pair: only the leader issues
             int stage = 0;
             uint32_t phase = 0;
             int local = 0;
-            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++local) {
+            // commits: to this CTA's barrier, or (CTA pair) multicast to the barrier at the same offset in both CTAs
+            auto commit = [&](uint32_t bar) {
+                if constexpr (TWO) {
+                    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                                 ::"r"(bar), "h"(static_cast<uint16_t>(3)) : "memory");
+                } else {
+                    umma_commit(bar);
+                }
+            };
+            for (int t = tile_first; t < total_tiles; t += tile_step, ++local) {
                 const int split = SWAP ? t / (p.tiles_a * p.tiles_b) : 0;
                 const int kb0 = split * p.kb_per_split;
                 const int kb1 = min(kb0 + p.kb_per_split, p.kb_total);
@@ -200,12 +248,18 @@ __global__ void __launch_bounds__(num_threads(SWAP), 1) gemm_tc_kernel(const __g
                                                  : umma_desc_sw128(sa + kk * UMMA_K * 2, 16, 1024);
                         const uint64_t db = B_MN ? umma_desc_sw128(sa + A_BYTES + kk * UMMA_K * 128, 8192, 1024)
                                                  : umma_desc_sw128(sa + A_BYTES + kk * UMMA_K * 2, 16, 1024);
-                        umma_f16(d_tmem + (kk % NACC) * BN, da, db, IDESC, (kb > kb0 || kk >= NACC) ? 1u : 0u);
+                        if constexpr (TWO) {
+                            asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n"
+                                         " tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n}"
+                                         ::"r"(d_tmem), "l"(da), "l"(db), "r"(IDESC), "r"((kb > kb0 || kk > 0) ? 1u : 0u) : "memory");
+                        } else {
+                            umma_f16(d_tmem + (kk % NACC) * BN, da, db, IDESC, (kb > kb0 || kk >= NACC) ? 1u : 0u);
+                        }
                     }
-                    umma_commit(smem_u32(&empty_bar[stage]));
+                    commit(smem_u32(&empty_bar[stage]));
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(smem_u32(&tfull_bar[acc]));
+                commit(smem_u32(&tfull_bar[acc]));
                 DBG_STAMP(4);                                                 // last MMA of the tile issued
             }
         }
@@ -214,10 +268,11 @@ __global__ void __launch_bounds__(num_threads(SWAP), 1) gemm_tc_kernel(const __g
         int local = 0;
         pdl_wait();              // residual reads / output writes must not overtake the predecessor kernel
         if (p.late_trigger) pdl_trigger();
-        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++local) {
+        for (int t = tile_first; t < total_tiles; t += tile_step, ++local) {
             int ta, tb, split;
             if (SWAP) { ta = t % p.tiles_a; const int r = t / p.tiles_a; tb = r % p.tiles_b; split = r / p.tiles_b; }
             else      { tb = t % p.tiles_b; ta = t / p.tiles_b; split = 0; }
+            if constexpr (TWO) ta = ta * 2 + static_cast<int>(cta_rank);
             const int kb0 = split * p.kb_per_split;
             const bool empty_slice = kb0 >= p.kb_total;   // a split past the end of K: contributes zeros
             const int acc = local & 1;
@@ -426,15 +481,27 @@ __global__ void __launch_bounds__(num_threads(SWAP), 1) gemm_tc_kernel(const __g
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[acc]));
+            if (lane == 0) {
+                if constexpr (TWO) {      // the leader's barrier collects the epilogue warps of both CTAs
+                    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(&tempty_bar[acc]) & PEER_MASK) : "memory");
+                } else {
+                    mbar_arrive(smem_u32(&tempty_bar[acc]));
+                }
+            }
             if (threadIdx.x == 64) DBG_STAMP(7);                              // epilogue stores issued, TMEM released
         }
     }
     tc_fence_before();
-    __syncthreads();
+    if constexpr (TWO) {          // the peer may still be reading its accumulators / receiving multicast arrivals
+        asm volatile("barrier.cluster.arrive.release;" ::: "memory");
+        asm volatile("barrier.cluster.wait.acquire;" ::: "memory");
+    } else {
+        __syncthreads();
+    }
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc<TMEM_COLS>(tmem_base);
+        if constexpr (TWO) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
+        else tmem_dealloc<TMEM_COLS>(tmem_base);
     }
 }
 
@@ -451,6 +518,33 @@ int launch_gemm_tc(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParam
     const int grid = min(total, vb_sm_count());
     static const CUtensorMap no_map{};
     VB_CUDA(vb_launch(SWAP, kern, dim3(grid), dim3(num_threads(SWAP)), SMEM, st, ta, tb, tp ? *tp : no_map, p));
+    return VB_OK;
+}
+
+// CTA-pair launch: cluster of two CTAs per 256 x BN tile, one pair per SM pair
+template <int BN, int STAGES>
+int launch_gemm_tc_pair(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
+    constexpr int SMEM = STAGES * (BM * BK * 2 + (BN / 2) * BK * 2) + 1024 + epi_warps(false) * STG_BYTES_PER_WARP;
+    static bool configured = false;
+    auto kern = gemm_tc_kernel<BN, STAGES, false, false, false, true>;
+    if (!configured) {
+        VB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+        configured = true;
+    }
+    const int total = p.tiles_a * p.tiles_b;
+    const int pairs = min(total, vb_sm_count() / 2);
+    static const CUtensorMap no_map{};
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * pairs);
+    cfg.blockDim = dim3(num_threads(false));
+    cfg.dynamicSmemBytes = SMEM;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    VB_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, no_map, p));
     return VB_OK;
 }
 
@@ -472,6 +566,13 @@ int vb_linear_tc(const void* x, int64_t ldx, const void* w, int64_t ldw, const f
     if ((rc = vb_make_tmap_bf16_2d(&ta, x, M, K, ldx, BM, BK)) != VB_OK) return rc;
     if (N > 128) {
         p.tiles_b = (int)vb_ceil_div(N, 256);
+        // CTA pairs (cta_group::2) for the large products: 256 x 256 tiles, each CTA of a pair loads half of the weight tile
+        static const bool pair_on = !(getenv("VALLE_B200_GEMM_PAIR") != nullptr && getenv("VALLE_B200_GEMM_PAIR")[0] == '0');
+        if (pair_on && M >= 1024) {
+            p.tiles_a = (int)vb_ceil_div(M, 2 * BM);
+            if ((rc = vb_make_tmap_bf16_2d(&tb, w, N, K, ldw, 128, BK)) != VB_OK) return rc;
+            return launch_gemm_tc_pair<256, 6>(ta, tb, p, st);
+        }
         if ((rc = vb_make_tmap_bf16_2d(&tb, w, N, K, ldw, 256, BK)) != VB_OK) return rc;
         return launch_gemm_tc<256, 4, false>(ta, tb, p, st);
     }
