@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(num_threads(SWAP), 1) gemm_tc_kernel(const __g
     constexpr int ACC_COLS = NACC * BN;             // TMEM columns of one (multi-)accumulator; two of them are in flight
     constexpr int TMEM_COLS = (2 * ACC_COLS <= 32) ? 32 : (2 * ACC_COLS <= 64) ? 64 : (2 * ACC_COLS <= 128) ? 128 : (2 * ACC_COLS <= 256) ? 256 : 512;
     static_assert(!(SWAP && (A_MN || B_MN)), "MN-major operands are for the large-M orientation");
-    static_assert(!TWO || (!SWAP && !A_MN && !B_MN), "the CTA-pair form exists for the plain large-M orientation");
+    static_assert(!TWO || !SWAP, "the CTA-pair form exists for the large-M orientation");
     constexpr uint32_t IDESC = umma_idesc_bf16(TWO ? 2 * BM : BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
     constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;      // clears the CTA-rank bit of a shared::cluster address: the leader's copy
     uint32_t cta_rank = 0;
@@ -155,7 +155,10 @@ __global__ void __launch_bounds__(num_threads(SWAP), 1) gemm_tc_kernel(const __g
             auto load_a = [&](uint32_t dst, uint32_t fb, int kb, int ta) {
                 if constexpr (A_MN) {
 #pragma unroll
-                    for (int i = 0; i < BM / 64; ++i) tma_load_2d(dst + i * 8192, &tm_a, fb, ta * BM + i * 64, kb * BK);
+                    for (int i = 0; i < BM / 64; ++i) {
+                        if constexpr (TWO) tma2(dst + i * 8192, &tm_a, fb, ta * BM + i * 64, kb * BK);
+                        else tma_load_2d(dst + i * 8192, &tm_a, fb, ta * BM + i * 64, kb * BK);
+                    }
                 } else if constexpr (TWO) {
                     tma2(dst, &tm_a, fb, kb * BK, ta * BM);
                 } else {
@@ -164,8 +167,12 @@ __global__ void __launch_bounds__(num_threads(SWAP), 1) gemm_tc_kernel(const __g
             };
             auto load_b = [&](uint32_t dst, uint32_t fb, int kb, int tb) {
                 if constexpr (B_MN) {
+                    constexpr int COLS = TWO ? BN / 2 : BN;      // CTA pair: this CTA's half of the tile's columns
 #pragma unroll
-                    for (int i = 0; i < BN / 64; ++i) tma_load_2d(dst + i * 8192, &tm_b, fb, tb * BN + i * 64, kb * BK);
+                    for (int i = 0; i < COLS / 64; ++i) {
+                        if constexpr (TWO) tma2(dst + i * 8192, &tm_b, fb, tb * BN + static_cast<int>(cta_rank) * COLS + i * 64, kb * BK);
+                        else tma_load_2d(dst + i * 8192, &tm_b, fb, tb * BN + i * 64, kb * BK);
+                    }
                 } else if constexpr (TWO) {
                     tma2(dst, &tm_b, fb, kb * BK, tb * BN + static_cast<int>(cta_rank) * (BN / 2));      // this CTA's half of the B tile
                 } else {
@@ -522,11 +529,11 @@ int launch_gemm_tc(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParam
 }
 
 // CTA-pair launch: cluster of two CTAs per 256 x BN tile, one pair per SM pair
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool A_MN = false, bool B_MN = false>
 int launch_gemm_tc_pair(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
     constexpr int SMEM = STAGES * (BM * BK * 2 + (BN / 2) * BK * 2) + 1024 + epi_warps(false) * STG_BYTES_PER_WARP;
     static bool configured = false;
-    auto kern = gemm_tc_kernel<BN, STAGES, false, false, false, true>;
+    auto kern = gemm_tc_kernel<BN, STAGES, false, A_MN, B_MN, true>;
     if (!configured) {
         VB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
         configured = true;
@@ -608,6 +615,14 @@ int vb_linear_tc_t(const void* x, int64_t ldx, int x_mn, const void* w, int64_t 
     if (w_mn) rc = vb_make_tmap_bf16_2d(&tb, w, K, N, ldw, BK, 64);
     else rc = vb_make_tmap_bf16_2d(&tb, w, N, K, ldw, 256, BK);
     if (rc != VB_OK) return rc;
+    static const bool pair_on = !(getenv("VALLE_B200_GEMM_PAIR") != nullptr && getenv("VALLE_B200_GEMM_PAIR")[0] == '0');
+    if (pair_on && M >= 1024) {      // CTA pairs: 256 x 256 tiles, half of the B tile per CTA (K-major B: 128-row boxes)
+        p.tiles_a = (int)vb_ceil_div(M, 2 * BM);
+        if (!w_mn && (rc = vb_make_tmap_bf16_2d(&tb, w, N, K, ldw, 128, BK)) != VB_OK) return rc;
+        if (x_mn && w_mn) return launch_gemm_tc_pair<256, 6, true, true>(ta, tb, p, st);
+        if (w_mn) return launch_gemm_tc_pair<256, 6, false, true>(ta, tb, p, st);
+        return launch_gemm_tc_pair<256, 6, true, false>(ta, tb, p, st);
+    }
     if (x_mn && w_mn) return launch_gemm_tc<256, 4, false, true, true>(ta, tb, p, st);
     if (w_mn) return launch_gemm_tc<256, 4, false, false, true>(ta, tb, p, st);
     return launch_gemm_tc<256, 4, false, true, false>(ta, tb, p, st);
