@@ -122,7 +122,9 @@ def test_linear_fp32(ops, M, N, K, epi):
 
 
 @pytest.mark.parametrize('M,N,K', [(128, 256, 64), (256, 512, 128), (300, 1024, 1024), (57, 192, 64),
-                                   (1000, 3072, 1024), (129, 100, 256), (4096, 1024, 4096), (64, 1025, 1024)])
+                                   (1000, 3072, 1024), (129, 100, 256), (4096, 1024, 4096), (64, 1025, 1024),
+                                   # M >= 1024: CTA pairs (256 x 256 tiles): ragged M, ragged N, N with an empty second half
+                                   (1300, 1025, 512), (2048, 384, 256), (1024, 3072, 1024)])
 @pytest.mark.parametrize('epi', EPIS)
 @pytest.mark.parametrize('ydt', [torch.bfloat16, torch.float32])
 def test_linear_bf16_tc(ops, M, N, K, epi, ydt):
