@@ -18,8 +18,11 @@ namespace {
 constexpr int BM = 128;      // UMMA M (rows of the A operand per tile)
 constexpr int BK = 64;       // k-block: 64 bf16 = one 128-byte swizzle atom row
 constexpr int UMMA_K = 16;
-constexpr int epi_warps(bool swap) { return swap ? 4 : 8; }
-constexpr int num_threads(bool swap) { return 64 + 32 * epi_warps(swap); }
+// Epilogue warps: 4 (swap-AB), 8 (large-M), 12 for the CTA-pair kernel when it is compiled for ONE non-residual epilogue: without the
+// residual prefetch registers the epilogue fits the 128 registers that 448 threads leave, and three warps per sub-partition instead
+// of two lift the ~0.45 IPC that bounds the GELU epilogue.
+constexpr int epi_warps(bool swap, bool wide = false) { return swap ? 4 : (wide ? 12 : 8); }
+constexpr int num_threads(bool swap, bool wide = false) { return 64 + 32 * epi_warps(swap, wide); }
 constexpr int STG_BYTES_PER_WARP = 32 * 128;   // epilogue staging: 32 rows x 32 fp32, 128B-swizzled
 constexpr int stg_bufs(bool swap) { return swap ? 2 : 1; }   // the split-K slices leave by TMA store: two staging tiles in flight
 
@@ -61,10 +64,11 @@ __device__ __forceinline__ unsigned long long gtimer() {
 // Per SM and k-block that is 32 KB of TMA writes and operand reads instead of 48 KB -- the single-CTA kernel streams
 // 94 B/clk/SM of operands at full MMA rate.  TMA loads of both CTAs complete on the LEADER's mbarrier, the MMA commits are
 // multicast to both CTAs' barriers, the accumulator-empty barrier collects the epilogue warps of both CTAs.
-template <int BN, int STAGES, bool SWAP, bool A_MN = false, bool B_MN = false, bool TWO = false>
-__global__ void __launch_bounds__(num_threads(SWAP), 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a,
+template <int BN, int STAGES, bool SWAP, bool A_MN = false, bool B_MN = false, bool TWO = false, int EPI = -1>
+__global__ void __launch_bounds__(num_threads(SWAP, TWO && EPI >= 0 && EPI != VB_EPI_BIAS_RESIDUAL), 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a,
                                                                  const __grid_constant__ CUtensorMap tm_b,
                                                                  const __grid_constant__ CUtensorMap tm_p, GemmParams p) {
+    constexpr bool WIDE = TWO && EPI >= 0 && EPI != VB_EPI_BIAS_RESIDUAL;      // 12 epilogue warps (see epi_warps)
     constexpr int A_BYTES = BM * BK * 2;
     constexpr int B_BYTES = (TWO ? BN / 2 : BN) * BK * 2;
     constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
@@ -100,7 +104,7 @@ __global__ void __launch_bounds__(num_threads(SWAP), 1) gemm_tc_kernel(const __g
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(smem_u32(&tfull_bar[a]), 1);
-            mbar_init(smem_u32(&tempty_bar[a]), (TWO ? 2 : 1) * epi_warps(SWAP));
+            mbar_init(smem_u32(&tempty_bar[a]), (TWO ? 2 : 1) * epi_warps(SWAP, WIDE));
         }
         fence_mbar_init();
     }
@@ -122,6 +126,7 @@ __global__ void __launch_bounds__(num_threads(SWAP), 1) gemm_tc_kernel(const __g
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_slot;
 
+    const int epilogue = (EPI >= 0) ? EPI : p.epilogue;      // EPI >= 0: compiled for one epilogue (dead code and its registers go)
     const int total_tiles = p.tiles_a * p.tiles_b * p.n_split;
     // work distribution: a CTA (a CTA pair when TWO) takes every tile_step-th tile starting at tile_first
     const int tile_first = TWO ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
@@ -290,10 +295,14 @@ __global__ void __launch_bounds__(num_threads(SWAP), 1) gemm_tc_kernel(const __g
             // (out-proj at M = 57 600: 532 TFLOP/s with the loads issued per chunk).
             float4 r_next[8];
             bool res_vec = false;
-            int e_half = 0, e_c4 = 0, e_rsub = 0;
+            // large-M orientation: a quadrant's warps split the tile's 32-column chunks among them (2 warps: 4 + 4, 3 warps: 2 + 3 + 3)
+            constexpr int E_PARTS = epi_warps(SWAP, WIDE) / 4, E_CHUNKS = BN / 32;
+            int e_c_begin = 0, e_c_end = 0, e_c4 = 0, e_rsub = 0;
             if (!SWAP) {
-                e_half = (warp - 2) >> 2; e_c4 = lane & 7; e_rsub = lane >> 3;
-                res_vec = (p.epilogue == VB_EPI_BIAS_RESIDUAL) && ((p.rows_b & 3) == 0) && ((p.ldy & 3) == 0) && ((p.ldr & 3) == 0);
+                const int part = (warp - 2) >> 2;
+                e_c_begin = (part * E_CHUNKS / E_PARTS) * 32; e_c_end = ((part + 1) * E_CHUNKS / E_PARTS) * 32;
+                e_c4 = lane & 7; e_rsub = lane >> 3;
+                res_vec = (epilogue == VB_EPI_BIAS_RESIDUAL) && ((p.rows_b & 3) == 0) && ((p.ldy & 3) == 0) && ((p.ldr & 3) == 0);
             }
             auto load_res = [&](int c0, float4 (&r)[8]) {
                 const int gcol = tb * BN + c0 + e_c4 * 4;
@@ -306,7 +315,7 @@ __global__ void __launch_bounds__(num_threads(SWAP), 1) gemm_tc_kernel(const __g
                                 : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
             };
-            if (res_vec) load_res(e_half * (BN / 2), r_next);
+            if (res_vec) load_res(e_c_begin, r_next);
             mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase);
             if (threadIdx.x == 64) DBG_STAMP(5);                              // accumulator complete
             tc_fence_after();
@@ -403,14 +412,14 @@ __global__ void __launch_bounds__(num_threads(SWAP), 1) gemm_tc_kernel(const __g
                 // TMEM -> registers (thread = row) -> a warp-private 128B-swizzled smem tile -> registers again with
                 // lane = (row, 16-byte column group), so that residual loads and output stores are coalesced
                 // (8 lanes cover one 128-byte row segment) instead of 32 scattered rows per instruction.
-                const int ew = warp - 2, half = ew >> 2;
+                const int ew = warp - 2;
                 const uint32_t stg = smem_base + STAGES * STAGE_BYTES + ew * STG_BYTES_PER_WARP;
                 const int n_base = tb * BN;
                 const int row_base = ta * BM + q * 32;
-                const bool vec_ok = ((p.rows_b & 3) == 0) && ((p.ldy & 3) == 0) && (p.epilogue != VB_EPI_BIAS_RESIDUAL || (p.ldr & 3) == 0);
+                const bool vec_ok = ((p.rows_b & 3) == 0) && ((p.ldy & 3) == 0) && (epilogue != VB_EPI_BIAS_RESIDUAL || (p.ldr & 3) == 0);
                 const int c4 = lane & 7, rsub = lane >> 3;
 #pragma unroll 1
-                for (int c0 = half * (BN / 2); c0 < (half + 1) * (BN / 2); c0 += 32) {
+                for (int c0 = e_c_begin; c0 < e_c_end; c0 += 32) {
                     const int n0 = n_base + c0;
                     if (n0 >= p.rows_b) break;
                     uint32_t v[32];
@@ -425,7 +434,7 @@ __global__ void __launch_bounds__(num_threads(SWAP), 1) gemm_tc_kernel(const __g
                     __syncwarp();
                     const int gcol = n0 + c4 * 4;
                     float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (p.epilogue != VB_EPI_NONE) {
+                    if (epilogue != VB_EPI_NONE) {
                         if (gcol + 3 < p.rows_b) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + gcol));
                         else {
                             if (gcol < p.rows_b) b4.x = p.bias[gcol];
@@ -447,7 +456,7 @@ __global__ void __launch_bounds__(num_threads(SWAP), 1) gemm_tc_kernel(const __g
 #pragma unroll
                         for (int it = 0; it < 8; ++it) r4[it] = r_next[it];
                         // next chunk of this warp's column half (different columns: no overlap with the stores below)
-                        if (c0 + 32 < (half + 1) * (BN / 2) && n0 + 32 < p.rows_b) load_res(c0 + 32, r_next);
+                        if (c0 + 32 < e_c_end && n0 + 32 < p.rows_b) load_res(c0 + 32, r_next);
                     }
                     // phase B: epilogue math + stores
 #pragma unroll
@@ -456,7 +465,7 @@ __global__ void __launch_bounds__(num_threads(SWAP), 1) gemm_tc_kernel(const __g
                         if (grow >= p.rows_a || !col_ok) continue;
                         float4 v4 = f[it];
                         v4.x += b4.x; v4.y += b4.y; v4.z += b4.z; v4.w += b4.w;
-                        if (p.epilogue == VB_EPI_BIAS_GELU) {
+                        if (epilogue == VB_EPI_BIAS_GELU) {
                             #ifdef VB_GELU_MUFU      // experiment: the Abramowitz-Stegun form with two MUFU ops per value
                             const float2 g01 = gelu_erf_fast2(make_float2(v4.x, v4.y)), g23 = gelu_erf_fast2(make_float2(v4.z, v4.w));
 #else
@@ -465,7 +474,7 @@ __global__ void __launch_bounds__(num_threads(SWAP), 1) gemm_tc_kernel(const __g
                             v4 = make_float4(g01.x, g01.y, g23.x, g23.y);
                         }
                         if (vec_ok) {
-                            if (p.epilogue == VB_EPI_BIAS_RESIDUAL) { v4.x += r4[it].x; v4.y += r4[it].y; v4.z += r4[it].z; v4.w += r4[it].w; }
+                            if (epilogue == VB_EPI_BIAS_RESIDUAL) { v4.x += r4[it].x; v4.y += r4[it].y; v4.z += r4[it].z; v4.w += r4[it].w; }
                             if (p.y_bf16) {
                                 *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(p.y) + static_cast<int64_t>(grow) * p.ldy + gcol) =
                                     make_uint2(pack_bf16x2(v4.x, v4.y), pack_bf16x2(v4.z, v4.w));
@@ -477,7 +486,7 @@ __global__ void __launch_bounds__(num_threads(SWAP), 1) gemm_tc_kernel(const __g
                             for (int e = 0; e < 4; ++e) {
                                 if (gcol + e >= p.rows_b) break;
                                 float val = fv[e];
-                                if (p.epilogue == VB_EPI_BIAS_RESIDUAL) val += p.residual[static_cast<int64_t>(grow) * p.ldr + gcol + e];
+                                if (epilogue == VB_EPI_BIAS_RESIDUAL) val += p.residual[static_cast<int64_t>(grow) * p.ldr + gcol + e];
                                 if (p.y_bf16) static_cast<__nv_bfloat16*>(p.y)[static_cast<int64_t>(grow) * p.ldy + gcol + e] = __float2bfloat16_rn(val);
                                 else static_cast<float*>(p.y)[static_cast<int64_t>(grow) * p.ldy + gcol + e] = val;
                             }
@@ -529,11 +538,13 @@ int launch_gemm_tc(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParam
 }
 
 // CTA-pair launch: cluster of two CTAs per 256 x BN tile, one pair per SM pair
-template <int BN, int STAGES, bool A_MN = false, bool B_MN = false>
+template <int BN, int STAGES, bool A_MN = false, bool B_MN = false, int EPI = -1>
 int launch_gemm_tc_pair(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
-    constexpr int SMEM = STAGES * (BM * BK * 2 + (BN / 2) * BK * 2) + 1024 + epi_warps(false) * STG_BYTES_PER_WARP;
+    constexpr bool WIDE = EPI >= 0 && EPI != VB_EPI_BIAS_RESIDUAL;
+    constexpr int SMEM = STAGES * (BM * BK * 2 + (BN / 2) * BK * 2) + 1024 + epi_warps(false, WIDE) * STG_BYTES_PER_WARP;
+    static_assert(SMEM <= 232448 - 1024, "CTA-pair GEMM: ring + staging exceed the shared memory of an SM");
     static bool configured = false;
-    auto kern = gemm_tc_kernel<BN, STAGES, false, A_MN, B_MN, true>;
+    auto kern = gemm_tc_kernel<BN, STAGES, false, A_MN, B_MN, true, EPI>;
     if (!configured) {
         VB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
         configured = true;
@@ -543,7 +554,7 @@ int launch_gemm_tc_pair(const CUtensorMap& ta, const CUtensorMap& tb, const Gemm
     static const CUtensorMap no_map{};
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2 * pairs);
-    cfg.blockDim = dim3(num_threads(false));
+    cfg.blockDim = dim3(num_threads(false, WIDE));
     cfg.dynamicSmemBytes = SMEM;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
@@ -578,7 +589,11 @@ int vb_linear_tc(const void* x, int64_t ldx, const void* w, int64_t ldw, const f
         if (pair_on && M >= 1024) {
             p.tiles_a = (int)vb_ceil_div(M, 2 * BM);
             if ((rc = vb_make_tmap_bf16_2d(&tb, w, N, K, ldw, 128, BK)) != VB_OK) return rc;
-            return launch_gemm_tc_pair<256, 6>(ta, tb, p, st);
+            // one instantiation per non-residual epilogue with 12 epilogue warps (5-stage ring pays for their staging tiles)
+            if (epilogue == VB_EPI_NONE) return launch_gemm_tc_pair<256, 5, false, false, VB_EPI_NONE>(ta, tb, p, st);
+            if (epilogue == VB_EPI_BIAS) return launch_gemm_tc_pair<256, 5, false, false, VB_EPI_BIAS>(ta, tb, p, st);
+            if (epilogue == VB_EPI_BIAS_GELU) return launch_gemm_tc_pair<256, 5, false, false, VB_EPI_BIAS_GELU>(ta, tb, p, st);
+            return launch_gemm_tc_pair<256, 6, false, false, VB_EPI_BIAS_RESIDUAL>(ta, tb, p, st);
         }
         if ((rc = vb_make_tmap_bf16_2d(&tb, w, N, K, ldw, 256, BK)) != VB_OK) return rc;
         return launch_gemm_tc<256, 4, false>(ta, tb, p, st);
@@ -619,6 +634,11 @@ int vb_linear_tc_t(const void* x, int64_t ldx, int x_mn, const void* w, int64_t 
     if (pair_on && M >= 1024) {      // CTA pairs: 256 x 256 tiles, half of the B tile per CTA (K-major B: 128-row boxes)
         p.tiles_a = (int)vb_ceil_div(M, 2 * BM);
         if (!w_mn && (rc = vb_make_tmap_bf16_2d(&tb, w, N, K, ldw, 128, BK)) != VB_OK) return rc;
+        if (epilogue == VB_EPI_NONE) {      // the backward GEMMs: compiled for the plain epilogue, 12 epilogue warps
+            if (x_mn && w_mn) return launch_gemm_tc_pair<256, 5, true, true, VB_EPI_NONE>(ta, tb, p, st);
+            if (w_mn) return launch_gemm_tc_pair<256, 5, false, true, VB_EPI_NONE>(ta, tb, p, st);
+            return launch_gemm_tc_pair<256, 5, true, false, VB_EPI_NONE>(ta, tb, p, st);
+        }
         if (x_mn && w_mn) return launch_gemm_tc_pair<256, 6, true, true>(ta, tb, p, st);
         if (w_mn) return launch_gemm_tc_pair<256, 6, false, true>(ta, tb, p, st);
         return launch_gemm_tc_pair<256, 6, true, false>(ta, tb, p, st);
