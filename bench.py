@@ -49,6 +49,17 @@ def workload_string(G: int) -> str:
             f'KV-cached greedy decode + NAR stages 2-{Q}; utterances sharded over the GPUs, codes all-gathered at the end')
 
 
+def workload_config(G: int, world: int) -> dict:
+    """`config` of the JSON line: the WORKLOAD only, built by one function so that both arms (ours / --impl reference) print the
+    same object; what an arm did with it (launch counts, kernels, samples, derived rates) goes to the line's `run` object."""
+    n_local = (G + world - 1) // world
+    return {'workload': workload_string(G), 'utterances': G, 'utterances_per_gpu': n_local,
+            'parallelism': f'dp{world}: utterance sharding (round robin), one all-gather of the int32 codes + lengths at the end of '
+                           'every job, inside the timed region',
+            'l2_policy': 'inputs larger than L2: every decode step streams 304 MB of weights + %.0f MB of KV per GPU' %
+                         ((ar_step_bytes(n_local, MEAN_CTX) - ar_step_bytes(0, 0)) / 1e6)}
+
+
 def peaks() -> dict:
     path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(path):
@@ -336,14 +347,10 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         'metric': 'tts_codec_frames_per_s', 'value': frames_s, 'unit': 'frames/s', 'n_gpus': world, 'steps': K, 'warmup': W,
         'ms_per_step': ms / K, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'bf16',
         'data': 'synthetic',
-        'config': {'workload': workload_string(G), 'utterances': G, 'utterances_per_gpu': n_local,
-                   'utterances_per_s': frames_s / N_NEW, 'audio_seconds_per_s': frames_s / 75.0,
-                   'parallelism': f'dp{world}: utterance sharding (round robin), one all-gather of the int32 codes + lengths at the end of '
-                                  'every job, inside the timed region', 'kv_page': 64,
-                   'decode_gemm': decode_form(eng, sb), 'launches_per_decode_step': eng.launches_per_step(),
-                   'nar_chunk': args.nar_chunk, 'sharded_equals_single_gpu': equal,
-                   'l2_policy': 'inputs larger than L2: every decode step streams 304 MB of weights + %.0f MB of KV per GPU' %
-                                ((ar_step_bytes(n_local, MEAN_CTX) - ar_step_bytes(0, 0)) / 1e6)},
+        'config': workload_config(G, world),
+        'run': {'utterances_per_s': frames_s / N_NEW, 'audio_seconds_per_s': frames_s / 75.0, 'kv_page': 64,
+                'decode_gemm': decode_form(eng, sb), 'launches_per_decode_step': eng.launches_per_step(),
+                'nar_chunk': args.nar_chunk, 'sharded_equals_single_gpu': equal},
         'clocks': clocks, 'gpu_launches': launches,
         'e2e': {'value': G * N_NEW * ke / (e2e_ms * 1e-3), 'unit': 'frames/s',
                 'h2d_bytes_per_step': sum(v.numel() for v in host.values()) * 8,
@@ -607,8 +614,8 @@ def run_reference(args, rank: int, world: int):
     return {'impl': 'reference', 'metric': 'tts_codec_frames_per_s', 'value': rate, 'unit': 'frames/s', 'n_gpus': world,
             'steps': K, 'warmup': W, 'ms_per_step': args.utterances * N_NEW / rate * 1e3, 'higher_is_better': True, 'scaling': 'strong',
             'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': workload_string(args.utterances), 'utterances': args.utterances,
-                       'utterances_per_s': rate / N_NEW, 'sample': r['sample']},
+            'config': workload_config(args.utterances, world),
+            'run': {'utterances_per_s': rate / N_NEW, 'audio_seconds_per_s': rate / 75.0, 'sample': r['sample']},
             'cpu_baseline': {'value': rate, 'unit': 'frames/s', 'cores': torch.get_num_threads(), 'kind': kind, 'sample': r['sample'],
                              'ar_tokens_per_s': r['ar_tokens_per_s'], 'nar_stage_frames_per_s': r['nar_stage_frames_per_s']},
             'e2e': {'value': rate, 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},

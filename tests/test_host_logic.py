@@ -271,3 +271,15 @@ def test_encodec_pip_wire_format_with_a_stand_in_codec():
     except Exception:
         with pytest.raises(RuntimeError, match='encodec'):
             EncodecPip()
+
+
+def test_training_ids_are_range_checked():
+    """The reference's nn.Embedding / F.cross_entropy refuse an id outside the table (modules.py:34, valle_ar.py:85); the CUDA
+    kernels clamp, so train.py checks first (asynchronously on the device; synchronously on a CPU tensor as here)."""
+    import torch
+    from valle2_b200.train import _ids_in_range
+    _ids_in_range(torch.tensor([[0, 5, 1023]]), 1024, 'codes')
+    with pytest.raises(RuntimeError, match='outside'):
+        _ids_in_range(torch.tensor([[0, 5, 1024]]), 1024, 'codes')
+    with pytest.raises(RuntimeError, match='outside'):
+        _ids_in_range(torch.tensor([-1]), 1025, 'target')

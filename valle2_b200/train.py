@@ -44,6 +44,13 @@ def _i32(t: torch.Tensor, device) -> torch.Tensor:
     return t.to(device=device, dtype=torch.int32).contiguous()
 
 
+def _ids_in_range(t: torch.Tensor, hi: int, what: str) -> None:
+    """The reference's nn.Embedding / F.cross_entropy fail on an id outside [0, hi) (a device-side assert on CUDA); the
+    kernels in csrc/train.cu clamp instead, which would hide a data bug -- so the same check is made here, asynchronously
+    (two tiny launches, no host synchronisation; a violation surfaces as a CUDA device-side assert, like the reference's)."""
+    torch._assert_async(((t >= 0) & (t < hi)).all(), f'{what}: id outside [0, {hi})')
+
+
 class _Lin:
     """One nn.Linear in the compute dtype: W (N,K), its transpose for dgrad, fp32 bias."""
 
@@ -333,6 +340,8 @@ def ar_loss_and_grads(model, batch: dict, precision: str, drop: dict | None = No
     pe_t = model.tokens_position_emb.pe.detach().float().reshape(-1, d).contiguous()
     pe_a = model.audio_position_emb.pe.detach().float().reshape(-1, d).contiguous()
     tok_i, cod_i = _i32(tokens, dev).view(B, Tx, 1), _i32(codes, dev).view(B, Ty, 1)
+    _ids_in_range(tok_i, tok_table.shape[1], 'ValleAR.training_step tokens')
+    _ids_in_range(cod_i, aud_table.shape[1], 'ValleAR.training_step codes')
     x = torch.zeros(Rp, d, device=dev, dtype=torch.float32)
     ops.embed_sum_pe(tok_i, tok_table, pe_t, x, out_rows_per_batch=S)
     ops.embed_sum_pe(cod_i, aud_table, pe_a, x, out_rows_per_batch=S, out_row_offset=Tx)
@@ -351,6 +360,7 @@ def ar_loss_and_grads(model, batch: dict, precision: str, drop: dict | None = No
     logits = torch.zeros(Rap, Vp, device=dev, dtype=torch.float32)
     ops.linear(hb[:Ra], proj.w, out=logits[:Ra])
     target = _i32(batch['target'].to(dev)[:, :Ty], dev).reshape(-1)
+    _ids_in_range(target, V, 'ValleAR.training_step target')
     dlogits = torch.zeros(Rap, Vp, device=dev, dtype=torch.float32)
     loss_rows = ops.cross_entropy(logits[:Ra], target, V, dlogits=dlogits[:Ra], scale=1.0 / Ra)
     loss = ops.colsum(loss_rows.view(Ra, 1), scale=1.0 / Ra)[0]
@@ -407,6 +417,8 @@ def nar_loss_and_grads(model, batch: dict, layer: int, precision: str, drop: dic
     pe_t = model.tokens_position_emb.pe.detach().float().reshape(-1, d).contiguous()
     pe_a = model.audio_position_emb.pe.detach().float().reshape(-1, d).contiguous()
     tok_i, cod_i = _i32(tokens, dev).view(B, Tx, 1), _i32(codes, dev)
+    _ids_in_range(tok_i, tok_table.shape[1], 'ValleNAR.training_step tokens')
+    _ids_in_range(cod_i, V, 'ValleNAR.training_step codes')            # embedding ids and the stage's targets alike
     x = torch.zeros(Rp, d, device=dev, dtype=torch.float32)
     ops.embed_sum_pe(tok_i, tok_table, pe_t, x, out_rows_per_batch=S)
     ops.embed_sum_pe(cod_i, code_tables, pe_a, x, t_split=prefix_len, nq_a=Q, nq_b=layer, out_rows_per_batch=S, out_row_offset=Tx)
