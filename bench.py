@@ -509,23 +509,35 @@ def extras_single_gpu(args, dev, tmp, ar, nar, pk):
         batch = {'tokens': torch.randint(0, 256, (Bt, Txt), generator=g), 'tokens_lens': torch.full((Bt,), Txt),
                  'codes': torch.randint(0, 1024, (Bt, Tyt), generator=g), 'codes_lens': torch.full((Bt,), Tyt),
                  'target': torch.randint(0, 1025, (Bt, Tyt), generator=g)}
-        for it in range(6):             # three warm-up steps (allocator growth, first-use kernel loads), three timed
-            if it == 3:
-                torch.cuda.synchronize()
-                e0.record()
-            for p_ in ar_t.parameters():
-                p_.grad = None
-            loss = ar_t.training_step(batch)
-            loss.backward()
-        e1.record()
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / 3
+        def timed_steps(model_, batch_, n_warm=3, n_timed=5):
+            """Per-step CUDA-event times after warm-up (allocator growth, first-use kernel loads); the median is reported, all are listed."""
+            import random as _random
+            _random.seed(3)             # ValleNAR.training_step draws its stage with random.randint
+            evs, loss_ = [], None
+            for it in range(n_warm + n_timed):
+                for p_ in model_.parameters():
+                    p_.grad = None
+                if it == n_warm:
+                    torch.cuda.synchronize()
+                a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a_.record()
+                loss_ = model_.training_step(batch_)
+                loss_.backward()
+                b_.record()
+                if it >= n_warm:
+                    evs.append((a_, b_))
+            torch.cuda.synchronize()
+            times = sorted(a_.elapsed_time(b_) for a_, b_ in evs)
+            return times[len(times) // 2], times, loss_
+
+        ms, ms_all, loss = timed_steps(ar_t, batch)
         S, d, F, L = Txt + Tyt, 1024, 4096, 12
         fwd = Bt * (L * (S * 2 * (4 * d * d + 2 * d * F) + 4 * S * S * d) + 2 * Tyt * d * 1025)
         out['train_step'] = {'batch': Bt, 'seq': S, 'ms_per_step': ms, 'clips_per_s': Bt / (ms * 1e-3), 'loss': float(loss.detach()),
                              'model_tflops': 3 * fwd / (ms * 1e-3) / 1e12,
                              'frac_of_bf16_sustained_peak': 3 * fwd / (ms * 1e-3) / 1e12 / pk['bf16_tflops_sustained'],
-                             'note': 'forward + backward, no optimizer step; flops = 3 x dense forward (no causal discount)',
+                             'ms_all_steps': ms_all,
+                             'note': 'forward + backward, no optimizer step; median of 5 steps; flops = 3 x dense forward (no causal discount)',
                              'peak_mem_gb': torch.cuda.max_memory_allocated() / 1e9}
         del ar_t
         torch.cuda.empty_cache()
@@ -533,23 +545,14 @@ def extras_single_gpu(args, dev, tmp, ar, nar, pk):
         nar_t = ValleNAR(large_cfg('AdaptiveLayerNorm', tmp)).train().to(dev)
         nbatch = {'tokens': batch['tokens'], 'tokens_lens': batch['tokens_lens'],
                   'codes': torch.randint(0, 1024, (Bt, Tyt - 1, 8), generator=g), 'codes_lens': torch.full((Bt,), Tyt - 1)}
-        for it in range(6):
-            if it == 3:
-                torch.cuda.synchronize()
-                e0.record()
-            for p_ in nar_t.parameters():
-                p_.grad = None
-            nloss = nar_t.training_step(nbatch)
-            nloss.backward()
-        e1.record()
-        torch.cuda.synchronize()
-        nms = e0.elapsed_time(e1) / 3
+        nms, nms_all, nloss = timed_steps(nar_t, nbatch)
         Sn = Txt + Tyt - 1
         nfwd = Bt * (L * (Sn * 2 * (4 * d * d + 2 * d * F) + 4 * Sn * Sn * d))
         out['train_step_nar'] = {'batch': Bt, 'seq': Sn, 'ms_per_step': nms, 'clips_per_s': Bt / (nms * 1e-3), 'loss': float(nloss.detach()),
                                  'model_tflops': 3 * nfwd / (nms * 1e-3) / 1e12,
                                  'frac_of_bf16_sustained_peak': 3 * nfwd / (nms * 1e-3) / 1e12 / pk['bf16_tflops_sustained'],
-                                 'note': 'ValleNAR.training_step forward + backward (full attention, AdaLN), stage drawn per step'}
+                                 'ms_all_steps': nms_all,
+                                 'note': 'ValleNAR.training_step forward + backward (full attention, AdaLN), stage drawn per step; median of 5 steps'}
         del nar_t
     except Exception as e:  # report, do not hide
         out['train_step'] = {'error': repr(e)[:300]}
