@@ -432,3 +432,43 @@ def test_ar_training_step_with_dropout_equals_reference_with_the_same_masks(tmp_
     model.train()
     a, b = train.dropout_plan(model), train.dropout_plan(model)
     assert a['seed'] != b['seed']
+
+
+def test_out_of_range_training_ids_fail_like_the_reference(tmp_path):
+    """An id outside the embedding table / class range makes the reference's nn.Embedding / F.cross_entropy fail (a device-side
+    assert on CUDA, modules.py:34, valle_ar.py:85); csrc/train.cu clamps, so train.py asserts first.  A device-side assert
+    poisons the CUDA context, hence the child process: the good batch must pass, the bad one must not."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = f'''
+import sys, torch
+sys.path.insert(0, {root!r}); sys.path.insert(0, {os.path.join(root, "tests")!r})
+from oracle import synth
+from test_gpu_models import build
+import pathlib
+oc = synth.tiny_config('LayerNorm')
+model, sd = build('ValleAR', oc, pathlib.Path({str(tmp_path)!r}), 3)
+model.train()
+g = torch.Generator().manual_seed(0)
+batch = {{'tokens': torch.randint(0, 256, (2, 6), generator=g), 'tokens_lens': torch.tensor([6, 4]),
+         'codes': torch.randint(0, 1024, (2, 9), generator=g), 'codes_lens': torch.tensor([9, 7]),
+         'target': torch.randint(0, 1025, (2, 9), generator=g)}}
+loss = model.training_step(batch); loss.backward(); torch.cuda.synchronize()
+print('GOOD_OK', flush=True)
+batch['target'][0, 3] = 1025 if sys.argv[1] == 'target' else batch['target'][0, 3]
+if sys.argv[1] == 'codes':
+    batch['codes'][1, 2] = 5000
+try:
+    loss = model.training_step(batch); loss.backward(); torch.cuda.synchronize()
+except Exception as e:
+    print('BAD_RAISED', type(e).__name__, flush=True)
+    sys.exit(0)
+print('BAD_PASSED', flush=True)
+'''
+    for which in ('target', 'codes'):
+        r = subprocess.run([sys.executable, '-c', code, which], capture_output=True, text=True, timeout=300)
+        assert 'GOOD_OK' in r.stdout, (r.stdout[-500:], r.stderr[-1500:])
+        assert 'BAD_PASSED' not in r.stdout, which
+        assert 'BAD_RAISED' in r.stdout or r.returncode != 0, (which, r.stdout[-500:], r.stderr[-500:])

@@ -283,3 +283,16 @@ def test_training_ids_are_range_checked():
         _ids_in_range(torch.tensor([[0, 5, 1024]]), 1024, 'codes')
     with pytest.raises(RuntimeError, match='outside'):
         _ids_in_range(torch.tensor([-1]), 1025, 'target')
+
+
+def test_generation_rejects_head_dims_other_than_64(tmp_path):
+    """KV-cached generation is built for 64-wide heads: any other d_model / n_heads says so up front."""
+    import torch
+    from valle2_b200.config import ConfigValle
+    from valle2_b200.engine import ARDecoder
+    from valle2_b200.models import ValleAR
+    cfg = ConfigValle(d_model=96, n_heads=3, dim_feedforward=128, num_layers=1, norm='LayerNorm', dropout=0.0,
+                      ckpt_path=str(tmp_path / 'c'), log_path=str(tmp_path / 'l'))
+    model = ValleAR(cfg).eval()
+    with pytest.raises(ValueError, match='== 64'):
+        ARDecoder(model, 'fp32')

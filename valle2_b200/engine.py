@@ -156,6 +156,12 @@ class ARDecoder:
         self.H = cfg.n_heads
         self.d = cfg.d_model
         self.Dh = self.d // self.H
+        if self.Dh != 64:
+            # the paged decode attention (csrc/attn_decode.cu) is built for 64-wide heads: one KV page row = one 128-byte line.
+            # The default VALL-E (1024 / 16) and the tiny test config (256 / 4) both have them; the module-level forwards
+            # (MultiHeadAttention.forward, csrc/attn_simt.cu) take any head_dim <= 256.
+            raise ValueError(f'KV-cached generation needs d_model / n_heads == 64 (got {self.d} / {self.H} = {self.Dh}); '
+                             'see DESIGN.md section 7')
         self.V = cfg.num_audio_tokens + 1
         self.weights = StackWeights(model.transformer, cfg.norm, precision)
         self.runner = StackRunner(self.weights, self.H)
