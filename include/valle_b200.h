@@ -40,7 +40,8 @@ enum {
     VB_EPI_NONE = 0,          /* y = x W^T                                  modules.py:146 (qkv), valle_ar.py:158 (proj) */
     VB_EPI_BIAS = 1,          /* y = x W^T + b                              modules.py:171 (out), :94-99 (AdaLN project) */
     VB_EPI_BIAS_GELU = 2,     /* y = gelu_erf(x W^T + b)                    modules.py:220-221 (linear_1 + nn.GELU)      */
-    VB_EPI_BIAS_RESIDUAL = 3  /* y = res + x W^T + b                        modules.py:277-278 (residual adds)           */
+    VB_EPI_BIAS_RESIDUAL = 3, /* y = res + x W^T + b                        modules.py:277-278 (residual adds)           */
+    VB_EPI_ARGMAX = 4         /* internal to vb_linear_argmax: y is never written, the epilogue keeps the row maxima      */
 };
 
 /* Attention mask modes (vb_attention). */
@@ -70,6 +71,17 @@ int vb_embed_sum_pe(const int32_t* ids, const float* tables, const float* pe, fl
                     int pos_offset, const int32_t* pos_b, int max_len,
                     int64_t out_rows_per_batch, int64_t out_row_offset, void* stream);
 
+/* vb_embed_sum_pe + the first (Ada)LayerNorm of the stack in one kernel (valle_nar.py:140-152 into modules.py:271 with the folded
+ * AdaLN of modules.py:93-99; valle_ar.py:127-139 likewise): out row as above AND
+ *   y[row][:] = (out[row] - mean) * rsqrt(var + eps) * gamma + beta      (gamma = beta = NULL: y = cast(out))
+ * with the row kept in registers in between (one warp per row), so layer 0's norm1 never re-reads the residual stream.
+ * y: y_dtype [rows][d], indexed like out.  d in {256, 512, 1024}.  Bit-identical to vb_embed_sum_pe + vb_residual_layernorm. */
+int vb_embed_sum_pe_norm(const int32_t* ids, const float* tables, const float* pe, float* out,
+                         int B, int T, int Q, int V, int d, int t_split, int nq_a, int nq_b,
+                         int pos_offset, const int32_t* pos_b, int max_len,
+                         int64_t out_rows_per_batch, int64_t out_row_offset,
+                         const float* gamma, const float* beta, float eps, void* y, int y_dtype, void* stream);
+
 /* ---- K3: LayerNorm / folded AdaLN, optionally fused with the split-K reduction + bias + residual ----------------- */
 /* if (n_part > 0)  x[r,:] += bias[:] + sum_{s<n_part} part[s*part_stride + r*d + :]   (fixed order, x updated in place)
  * y[r,:] = (x[r,:] - mean) * rsqrt(var + eps) * gamma + beta           (y may be NULL: residual update only;
@@ -98,6 +110,20 @@ int vb_reduce_bias_act(const float* part, int n_part, int64_t part_stride, const
 int vb_linear(const void* x, int x_dtype, int64_t ldx, const void* w, int w_dtype, int64_t ldw,
               const float* bias, const float* residual, int64_t ldr, void* y, int y_dtype, int64_t ldy,
               int64_t M, int64_t N, int64_t K, int epilogue, void* stream);
+
+/* Fused logits + greedy pick (valle_nar.py:157-160 with argmax sampling; the `logits.argmax(-1)` of a greedy stage):
+ *   tok[m] = argmin{ n : (x W^T)[m][n] is the row maximum }      x bf16 [M][K], w bf16 [N][K], fp32 accumulate.
+ * The tcgen05 CTA-pair GEMM of vb_linear runs with an epilogue that reads each accumulator row out of tensor memory, keeps its
+ * running (value, column) maximum in registers and merges the four 256-column tiles of a row with ONE 64-bit atomicMax on
+ * keys[m] = order-preserving bits of the value << 32 | ~column (ties -> lowest column, as vb_sample with top_k == 1): the
+ * (M x N) fp32 logits are never written to or read back from HBM.  A second tiny kernel unpacks keys[m] into
+ * out_tok[(m / rows_per_batch) * batch_stride + (m % rows_per_batch) * row_stride] (int32; e.g. straight into column n of the
+ * (B, T, Q) code tensor) and resets keys[m] to zero for the next call.  keys: M uint64, ZERO before the first call.
+ * Needs M >= 1024 and N > 128 (the CTA-pair GEMM); a row whose logits are all -inf / NaN yields token 0.
+ * Bit-identical to vb_linear(VB_EPI_NONE, fp32 y) followed by vb_sample(top_k = 1). */
+int vb_linear_argmax(const void* x, int64_t ldx, const void* w, int64_t ldw, unsigned long long* keys, int32_t* out_tok,
+                     int64_t rows_per_batch, int64_t batch_stride, int64_t row_stride, int64_t M, int64_t N, int64_t K,
+                     void* stream);
 
 /* The same bf16 tcgen05 GEMM with operands optionally given TRANSPOSED in memory (MN-major MMA operands, no copy):
  *   x_transposed: x is [K][M] row-major (pitch ldx) instead of [M][K];  w_transposed: w is [K][N] (pitch ldw) instead of [N][K].

@@ -288,3 +288,31 @@ def test_ar_large_short_decode_vs_oracle(precision, tmp_path):
     # the last len(ref) rows of the teacher-forced logits are the decode-step logits (cached == uncached invariant)
     for s in range(len(ref)):
         assert rel_err(logits[70 + s], trace[s][0]) < (2e-5 if precision == 'fp32' else 1e-2)
+
+
+def test_nar_fused_logits_argmax_equals_unfused_stages(tmp_path):
+    """Greedy bf16 NAR stages of >= 1024 target rows run the logits projection and the pick in ONE kernel (vb_linear_argmax,
+    valle_nar.py:157-160); the codes must be bit-identical to the stages that write fp32 logits and pick with vb_sample
+    (same GEMM, same accumulation order; 7 dependent stages, so a single different pick would change every later stage).
+    Ragged targets included (rows past a target's length are padding in both)."""
+    valle2_b200.set_precision('bf16')
+    oc = synth.tiny_config('AdaptiveLayerNorm')
+    model, sd = build('ValleNAR', oc, tmp_path, 4)
+    g = torch.Generator().manual_seed(11)
+    B, Tp, Tt, Tc, T = 3, 6, 9, 20, 400                      # B T = 1200 target rows
+    pt, tt = torch.randint(0, 256, (B, Tp), generator=g).cuda(), torch.randint(0, 256, (B, Tt), generator=g).cuda()
+    pc = torch.randint(0, 1024, (B, Tc, 8), generator=g).cuda()
+    first = torch.randint(0, 1024, (B, T), generator=g).cuda()
+    lens = torch.tensor([400, 333, 250])
+    eng = model._engine()
+    assert eng.fused_argmax and eng.fused_embed_norm
+    for tl in (None, lens):
+        fused = eng.generate(pt, pc, tt, first, greedy=True, target_lens=tl)
+        eng.fused_argmax = eng.fused_embed_norm = False          # also: embedding-sum + PE + first AdaLN in one kernel
+        try:
+            plain = eng.generate(pt, pc, tt, first, greedy=True, target_lens=tl)
+        finally:
+            eng.fused_argmax = eng.fused_embed_norm = True
+        assert fused.shape == (B, T, 8) and fused.dtype == torch.int64
+        assert torch.equal(fused, plain)
+        assert torch.equal(fused[:, :, 0], first)

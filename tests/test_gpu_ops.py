@@ -684,3 +684,94 @@ def test_linear_transposed_operands(ops, x_t, w_t, M, N, K):
     y = ops.linear_t(x, w, x_t=x_t, w_t=w_t, out_dtype=torch.float32)
     torch.cuda.synchronize()
     assert rel_err(y, X.double() @ W.double().t()) < 1e-4
+
+
+@pytest.mark.parametrize('M,N,K', [(1024, 1024, 256), (1300, 1024, 1024), (2500, 1000, 512), (1025, 300, 64), (4096, 1024, 1024)])
+def test_linear_argmax_equals_logits_then_greedy_pick(ops, M, N, K):
+    """vb_linear_argmax (logits GEMM + greedy pick in one kernel, valle_nar.py:157-160 with argmax sampling) against the
+    unfused pair it replaces -- vb_linear (fp32 logits) followed by vb_sample(top_k=1) -- and against torch.argmax over the
+    same logits: integer work, bit-exact.  Ragged M / N (partial last tiles), dense and strided destinations; the key
+    scratch is left zero."""
+    torch.manual_seed(M + N + K)
+    x = torch.randn(M, K, device='cuda').bfloat16()
+    w = (torch.randn(N, K, device='cuda') / math.sqrt(K)).bfloat16()
+    logits = ops.linear(x, w, out_dtype=torch.float32)
+    want = torch.empty(M, device='cuda', dtype=torch.int32)
+    ops.sample(logits, 1, 0, N, M, N, temperature=1.0, top_k=1, top_p=1.0, out_tok=want)
+    assert torch.equal(want.long(), logits.argmax(-1))
+    keys = torch.zeros(M, device='cuda', dtype=torch.int64)
+    got = torch.full((M,), -1, device='cuda', dtype=torch.int32)
+    ops.linear_argmax(x, w, keys, got)
+    assert torch.equal(got, want)
+    assert int(keys.abs().max()) == 0
+    # second call on the same scratch, strided destination: column 3 of a (B, T0 + T, 8) code tensor, rows from T0 on
+    Bb = 4 if M % 4 == 0 else 1
+    T, T0, Q = M // Bb, 5, 8
+    ids = torch.full((Bb, T0 + T, Q), -7, device='cuda', dtype=torch.int32)
+    ops.linear_argmax(x, w, keys, ids[:, T0:, 3], rows_per_batch=T, batch_stride=(T0 + T) * Q, row_stride=Q)
+    assert torch.equal(ids[:, T0:, 3].reshape(-1), want)
+    ids[:, T0:, 3] = -7
+    assert int((ids != -7).sum()) == 0          # nothing else was touched
+
+
+def test_linear_argmax_ties_and_degenerate_rows(ops):
+    """Ties go to the lowest column (vb_sample's greedy rule, torch.argmax's too): duplicated weight rows give bit-identical
+    logits in several columns, also across the 256-column tiles that meet in the atomic.  All-zero activations make every
+    logit of a row equal (0.0): token 0."""
+    torch.manual_seed(5)
+    M, N, K = 1100, 1024, 128
+    x = torch.randn(M, K, device='cuda').bfloat16()
+    w = (torch.randn(N, K, device='cuda') * 0.1).bfloat16()
+    big = (torch.randn(K, device='cuda')).bfloat16()
+    x[:, :] = x * 0.01
+    x[::3] = big * 0.5                         # rows whose best column is one of the duplicates below
+    for c in (7, 300, 301, 700, 1023):         # the same weight row in five columns spread over the four tiles
+        w[c] = big
+    x[10] = 0
+    logits = ops.linear(x, w, out_dtype=torch.float32)
+    assert torch.equal(logits[0, 7], logits[0, 1023])
+    keys = torch.zeros(M, device='cuda', dtype=torch.int64)
+    got = torch.empty(M, device='cuda', dtype=torch.int32)
+    ops.linear_argmax(x, w, keys, got)
+    want = torch.empty(M, device='cuda', dtype=torch.int32)
+    ops.sample(logits, 1, 0, N, M, N, temperature=1.0, top_k=1, top_p=1.0, out_tok=want)
+    assert torch.equal(got, want)
+    assert int(got[0]) == 7 and int(got[10]) == 0
+    from valle2_b200 import _lib
+    with pytest.raises(_lib.VBError):          # below the CTA-pair GEMM's shapes: refused, never a silent other path
+        ops.linear_argmax(x[:512], w, keys, got)
+
+
+@pytest.mark.parametrize('ydt', [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize('d', [256, 512, 1024])
+@pytest.mark.parametrize('affine', [True, False])
+def test_embed_sum_pe_norm_equals_embed_then_layernorm(ops, ydt, d, affine):
+    """vb_embed_sum_pe_norm (embedding sum + PE + the first (Ada)LayerNorm in one kernel; valle_nar.py:140-152 into
+    modules.py:271) against the two kernels it replaces: same residual rows and same normalised rows, bit for bit (same order
+    of operations), for both segments of a stage's input (text rows; prompt rows with all codebooks + target rows with the
+    first n) written at their row offsets of one (B, S, d) buffer."""
+    torch.manual_seed(d)
+    B, Tx, Tc, T, Q, V = 3, 5, 7, 9, 8, 50
+    S = Tx + Tc + T
+    tok = torch.randint(0, 256, (B, Tx, 1), dtype=torch.int32, device='cuda')
+    ids = torch.randint(0, V, (B, Tc + T, Q), dtype=torch.int32, device='cuda')
+    tok_table = torch.randn(1, 256, d, device='cuda')
+    tables = torch.randn(Q, V, d, device='cuda')
+    pe = torch.randn(64, d, device='cuda')
+    gamma = torch.randn(d, device='cuda') if affine else None
+    beta = torch.randn(d, device='cuda') if affine else None
+    x0 = torch.full((B * S, d), 7.0, device='cuda')
+    ops.embed_sum_pe(tok, tok_table, pe, x0, out_rows_per_batch=S, out_row_offset=0)
+    ops.embed_sum_pe(ids, tables, pe, x0, t_split=Tc, nq_a=Q, nq_b=3, out_rows_per_batch=S, out_row_offset=Tx)
+    y0 = torch.empty(B * S, d, device='cuda', dtype=ydt)
+    ops.residual_layernorm(x0, gamma, beta, y0, eps=1e-5)
+    x1 = torch.full((B * S, d), -3.0, device='cuda')
+    y1 = torch.zeros(B * S, d, device='cuda', dtype=ydt)
+    ops.embed_sum_pe(tok, tok_table, pe, x1, out_rows_per_batch=S, out_row_offset=0, norm_y=y1, gamma=gamma, beta=beta, eps=1e-5)
+    ops.embed_sum_pe(ids, tables, pe, x1, t_split=Tc, nq_a=Q, nq_b=3, out_rows_per_batch=S, out_row_offset=Tx, norm_y=y1,
+                     gamma=gamma, beta=beta, eps=1e-5)
+    assert torch.equal(x0, x1)
+    assert torch.equal(y0, y1)
+    # and against torch on the same rows
+    ref = torch.nn.functional.layer_norm(x0, (d,), gamma, beta, 1e-5) if affine else x0
+    assert rel_err(y1.float(), ref) < (1e-2 if ydt == torch.bfloat16 else 1e-5)

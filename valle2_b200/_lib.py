@@ -22,10 +22,12 @@ SIGNATURES = {
     'vb_version': (_i, []),
     'vb_last_error_string': (C.c_char_p, []),
     'vb_device_info': (_i, [_p, _p, _p, _p]),
+    'vb_embed_sum_pe_norm': (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _i, _i64, _i64, _p, _p, _f, _p, _i, _p]),
     'vb_embed_sum_pe': (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _i, _i64, _i64, _p]),
     'vb_residual_layernorm': (_i, [_p, _p, _i, _i64, _p, _p, _p, _p, _i, _i64, _i, _f, _p]),
     'vb_reduce_bias_act': (_i, [_p, _i, _i64, _p, _i, _p, _i, _i64, _i, _p]),
     'vb_linear': (_i, [_p, _i, _i64, _p, _i, _i64, _p, _p, _i64, _p, _i, _i64, _i64, _i64, _i64, _i, _p]),
+    'vb_linear_argmax': (_i, [_p, _i64, _p, _i64, _p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _p]),
     'vb_linear_t': (_i, [_p, _i64, _i, _p, _i64, _i, _p, _p, _i64, _p, _i, _i64, _i64, _i64, _i64, _i, _p]),
     'vb_linear_decode_splits': (_i, [_i64, _i64, _i]),
     'vb_linear_decode_splits_m': (_i, [_i64, _i64, _i64, _i]),

@@ -49,6 +49,109 @@ extern "C" int vb_embed_sum_pe(const int32_t* ids, const float* tables, const fl
     return VB_OK;
 }
 
+// Fused embedding-sum + PE + first (Ada)LayerNorm: one warp per row, the row stays in registers between the sum and the
+// normalisation, so the fp32 residual row is written once and never read back for layer 0's norm1.  Same lane layout and the same
+// order of operations as residual_layernorm_kernel below, hence bit-identical to vb_embed_sum_pe followed by vb_residual_layernorm.
+template <typename TY, int NV>  // NV = d / 128 float4 chunks per lane
+__global__ void __launch_bounds__(256) embed_sum_pe_norm_kernel(const int32_t* __restrict__ ids, const float* __restrict__ tables,
+                                                                const float* __restrict__ pe, float* __restrict__ out, int B, int T, int Q,
+                                                                int V, int d, int t_split, int nq_a, int nq_b, int pos_offset,
+                                                                const int32_t* __restrict__ pos_b, int max_len,
+                                                                int64_t out_rows_per_batch, int64_t out_row_offset,
+                                                                const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                float eps, TY* __restrict__ y) {
+    const int lane = threadIdx.x & 31;
+    const int64_t r = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (r >= static_cast<int64_t>(B) * T) return;
+    const int b = static_cast<int>(r / T), t = static_cast<int>(r % T);
+    const int nq = (t < t_split) ? nq_a : nq_b;
+    int pos = (pos_b ? pos_b[b] : pos_offset) + t;
+    pos = min(max(pos, 0), max_len - 1);
+    const int32_t* id_row = ids + (static_cast<int64_t>(b) * T + t) * Q;
+    const int64_t orow = static_cast<int64_t>(b) * out_rows_per_batch + out_row_offset + t;
+    const float* pe_row = pe + static_cast<int64_t>(pos) * d;
+    float4 v[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int j = 0; j < nq; ++j) {  // left-to-right, same order as the reference's += loop
+        int id = id_row[j];
+        id = min(max(id, 0), V - 1);
+        const float* e_row = tables + (static_cast<int64_t>(j) * V + id) * d;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const float4 e = *reinterpret_cast<const float4*>(e_row + (i * 32 + lane) * 4);
+            v[i].x += e.x; v[i].y += e.y; v[i].z += e.z; v[i].w += e.w;
+        }
+    }
+    float* o = out + orow * d;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int c = (i * 32 + lane) * 4;
+        const float4 p = *reinterpret_cast<const float4*>(pe_row + c);
+        v[i].x += p.x; v[i].y += p.y; v[i].z += p.z; v[i].w += p.w;
+        *reinterpret_cast<float4*>(o + c) = v[i];
+    }
+    TY* yr = y + orow * d;
+    if (gamma == nullptr) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int c = (i * 32 + lane) * 4;
+            if constexpr (sizeof(TY) == 4) *reinterpret_cast<float4*>(yr + c) = v[i];
+            else *reinterpret_cast<uint2*>(yr + c) = make_uint2(pack_bf16x2(v[i].x, v[i].y), pack_bf16x2(v[i].z, v[i].w));
+        }
+        return;
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    const float mean = warp_sum(s) / d;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const float a = v[i].x - mean, b2 = v[i].y - mean, c2 = v[i].z - mean, e2 = v[i].w - mean;
+        q += (a * a + b2 * b2) + (c2 * c2 + e2 * e2);
+    }
+    const float rstd = rsqrtf(warp_sum(q) / d + eps);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int c = (i * 32 + lane) * 4;
+        const float4 g = *reinterpret_cast<const float4*>(gamma + c);
+        const float4 bt = *reinterpret_cast<const float4*>(beta + c);
+        const float o0 = (v[i].x - mean) * rstd * g.x + bt.x, o1 = (v[i].y - mean) * rstd * g.y + bt.y;
+        const float o2 = (v[i].z - mean) * rstd * g.z + bt.z, o3 = (v[i].w - mean) * rstd * g.w + bt.w;
+        if constexpr (sizeof(TY) == 4) *reinterpret_cast<float4*>(yr + c) = make_float4(o0, o1, o2, o3);
+        else *reinterpret_cast<uint2*>(yr + c) = make_uint2(pack_bf16x2(o0, o1), pack_bf16x2(o2, o3));
+    }
+}
+
+extern "C" int vb_embed_sum_pe_norm(const int32_t* ids, const float* tables, const float* pe, float* out, int B, int T, int Q,
+                                    int V, int d, int t_split, int nq_a, int nq_b, int pos_offset, const int32_t* pos_b,
+                                    int max_len, int64_t out_rows_per_batch, int64_t out_row_offset, const float* gamma,
+                                    const float* beta, float eps, void* y, int y_dtype, void* stream) {
+    VB_REQUIRE(ids && tables && pe && out && y, VB_ERR_BAD_ARG, "vb_embed_sum_pe_norm: null pointer");
+    VB_REQUIRE((gamma == nullptr) == (beta == nullptr), VB_ERR_BAD_ARG, "vb_embed_sum_pe_norm: gamma and beta go together");
+    VB_REQUIRE(B >= 0 && T >= 0 && Q >= 1, VB_ERR_BAD_ARG, "vb_embed_sum_pe_norm: bad shape B=%d T=%d Q=%d", B, T, Q);
+    VB_REQUIRE(d == 256 || d == 512 || d == 1024, VB_ERR_UNSUPPORTED, "vb_embed_sum_pe_norm: d must be 256, 512 or 1024 (got %d)", d);
+    VB_REQUIRE(nq_a >= 0 && nq_a <= Q && nq_b >= 0 && nq_b <= Q, VB_ERR_BAD_ARG, "vb_embed_sum_pe_norm: nq out of range");
+    VB_REQUIRE(y_dtype == VB_F32 || y_dtype == VB_BF16, VB_ERR_BAD_ARG, "vb_embed_sum_pe_norm: bad y_dtype");
+    if (B == 0 || T == 0) return VB_OK;
+    const int64_t rows = static_cast<int64_t>(B) * T;
+    const unsigned grid = static_cast<unsigned>((rows + 7) / 8);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+#define EPN(TY, NV)                                                                                                          \
+    embed_sum_pe_norm_kernel<TY, NV><<<grid, 256, 0, st>>>(ids, tables, pe, out, B, T, Q, V, d, t_split, nq_a, nq_b, pos_offset, \
+                                                           pos_b, max_len, out_rows_per_batch, out_row_offset, gamma, beta, eps, \
+                                                           static_cast<TY*>(y))
+    if (y_dtype == VB_BF16) {
+        if (d == 256) EPN(__nv_bfloat16, 2); else if (d == 512) EPN(__nv_bfloat16, 4); else EPN(__nv_bfloat16, 8);
+    } else {
+        if (d == 256) EPN(float, 2); else if (d == 512) EPN(float, 4); else EPN(float, 8);
+    }
+#undef EPN
+    VB_CUDA(cudaGetLastError());
+    return VB_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // K3  [split-K reduce + bias + residual] + LayerNorm;  one warp per row, row kept in registers
 // ------------------------------------------------------------------------------------------------

@@ -407,6 +407,34 @@ __global__ void __launch_bounds__(num_threads(SWAP, TWO && EPI >= 0 && EPI != VB
                     }
                 }
                 }
+            } else if constexpr (EPI == VB_EPI_ARGMAX) {
+                // Fused logits + greedy pick (vb_linear_argmax): thread = accumulator row; its warp's share of the tile's columns is
+                // scanned straight out of tensor memory (ascending columns, strict '>' keeps the lowest column of a tie) and the
+                // row's (value, column) maximum joins the other warps / tiles of the row through one 64-bit atomicMax.  Nothing
+                // is staged and no logit is stored.
+                float best = 0.f;
+                int best_col = -1;
+                const int n_base = tb * BN;
+#pragma unroll 1
+                for (int c0 = e_c_begin; c0 < e_c_end; c0 += 32) {
+                    const int n0 = n_base + c0;
+                    if (n0 >= p.rows_b) break;
+                    uint32_t v[32];
+                    tmem_ld_32x32(t_addr + c0, v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float val = __uint_as_float(v[j]);
+                        if (n0 + j < p.rows_b && val > -INFINITY && (best_col < 0 || val > best)) { best = val; best_col = n0 + j; }
+                    }
+                }
+                if (row < p.rows_a && best_col >= 0) {
+                    uint32_t u = __float_as_uint(best);
+                    if ((u << 1) == 0u) u = 0u;                           // -0.0 and +0.0 compare equal: one key for both
+                    u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);      // order-preserving map float -> unsigned
+                    const unsigned long long key = (static_cast<unsigned long long>(u) << 32) | (0xFFFFFFFFu - static_cast<uint32_t>(best_col));
+                    atomicMax(static_cast<unsigned long long*>(p.y) + row, key);
+                }
             } else {
                 // Normal orientation.  Each quadrant is served by two warps (column halves).  A 32-column chunk goes
                 // TMEM -> registers (thread = row) -> a warp-private 128B-swizzled smem tile -> registers again with
@@ -593,11 +621,14 @@ int vb_linear_tc(const void* x, int64_t ldx, const void* w, int64_t ldw, const f
             if (epilogue == VB_EPI_NONE) return launch_gemm_tc_pair<256, 5, false, false, VB_EPI_NONE>(ta, tb, p, st);
             if (epilogue == VB_EPI_BIAS) return launch_gemm_tc_pair<256, 5, false, false, VB_EPI_BIAS>(ta, tb, p, st);
             if (epilogue == VB_EPI_BIAS_GELU) return launch_gemm_tc_pair<256, 5, false, false, VB_EPI_BIAS_GELU>(ta, tb, p, st);
+            if (epilogue == VB_EPI_ARGMAX) return launch_gemm_tc_pair<256, 5, false, false, VB_EPI_ARGMAX>(ta, tb, p, st);
             return launch_gemm_tc_pair<256, 6, false, false, VB_EPI_BIAS_RESIDUAL>(ta, tb, p, st);
         }
+        VB_REQUIRE(epilogue != VB_EPI_ARGMAX, VB_ERR_UNSUPPORTED, "vb_linear_argmax: needs M >= 1024 (got %lld)", (long long)M);
         if ((rc = vb_make_tmap_bf16_2d(&tb, w, N, K, ldw, 256, BK)) != VB_OK) return rc;
         return launch_gemm_tc<256, 4, false>(ta, tb, p, st);
     }
+    VB_REQUIRE(epilogue != VB_EPI_ARGMAX, VB_ERR_UNSUPPORTED, "vb_linear_argmax: needs N > 128 (got %lld)", (long long)N);
     if (N > 64) {
         p.tiles_b = 1;
         if ((rc = vb_make_tmap_bf16_2d(&tb, w, N, K, ldw, 128, BK)) != VB_OK) return rc;

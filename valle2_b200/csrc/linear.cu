@@ -45,3 +45,31 @@ extern "C" int vb_linear(const void* x, int x_dtype, int64_t ldx, const void* w,
         return vb_linear_tc(x, ldx, w, ldw, bias, residual, ldr, y, y_dtype, ldy, M, N, K, epilogue, st);
     VB_REQUIRE(false, VB_ERR_UNSUPPORTED, "vb_linear: dtype combination x=%d w=%d", x_dtype, w_dtype);
 }
+
+namespace {
+// keys[m] = order-preserving value bits << 32 | ~column (gemm_tc.cu, VB_EPI_ARGMAX) -> token; the key is reset for the next call
+__global__ void argmax_unpack_kernel(unsigned long long* __restrict__ keys, int32_t* __restrict__ out_tok, int64_t rows_per_batch,
+                                     int64_t batch_stride, int64_t row_stride, int64_t M) {
+    const int64_t m = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (m >= M) return;
+    const unsigned long long key = keys[m];
+    keys[m] = 0ull;
+    const int32_t tok = key ? static_cast<int32_t>(0xFFFFFFFFu - static_cast<uint32_t>(key & 0xFFFFFFFFull)) : 0;
+    out_tok[(m / rows_per_batch) * batch_stride + (m % rows_per_batch) * row_stride] = tok;
+}
+}  // namespace
+
+extern "C" int vb_linear_argmax(const void* x, int64_t ldx, const void* w, int64_t ldw, unsigned long long* keys, int32_t* out_tok,
+                                int64_t rows_per_batch, int64_t batch_stride, int64_t row_stride, int64_t M, int64_t N, int64_t K,
+                                void* stream) {
+    VB_REQUIRE(x && w && keys && out_tok, VB_ERR_BAD_ARG, "vb_linear_argmax: null pointer");
+    VB_REQUIRE(M >= 0 && N >= 1 && K >= 1 && rows_per_batch >= 1, VB_ERR_BAD_ARG, "vb_linear_argmax: bad shape M=%lld N=%lld K=%lld rows_per_batch=%lld",
+               (long long)M, (long long)N, (long long)K, (long long)rows_per_batch);
+    if (M == 0) return VB_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int rc = vb_linear_tc(x, ldx, w, ldw, nullptr, nullptr, 0, keys, VB_F32, N, M, N, K, VB_EPI_ARGMAX, st);
+    if (rc != VB_OK) return rc;
+    argmax_unpack_kernel<<<static_cast<unsigned>((M + 255) / 256), 256, 0, st>>>(keys, out_tok, rows_per_batch, batch_stride, row_stride, M);
+    VB_CUDA(cudaGetLastError());
+    return VB_OK;
+}

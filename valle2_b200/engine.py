@@ -103,9 +103,22 @@ class StackRunner:
             }}
         return self._ws[key]
 
+    def fused_first_norm_ok(self) -> bool:
+        return self.w.d in (256, 512, 1024)
+
+    def first_norm_buffer(self, R: int, device) -> torch.Tensor:
+        return self._buffers(R, device)['h']
+
+    def first_norm_args(self, stage: int = 0) -> dict:
+        """gamma / beta / eps of layer 0's norm1 (the stage's folded AdaLN affine), as keyword arguments of ops.embed_sum_pe."""
+        g, b, eps = self.w.layers[0]['norm1']
+        return {'gamma': g[min(stage, g.shape[0] - 1)], 'beta': b[min(stage, b.shape[0] - 1)], 'eps': eps}
+
     def forward(self, x: torch.Tensor, B: int, S: int, *, mask_mode: int, x_lens=None, kv_lens=None, stage: int = 0,
                 kv_pools: torch.Tensor | None = None, block_table: torch.Tensor | None = None,
-                use_tc_attention: bool | None = None) -> torch.Tensor:
+                use_tc_attention: bool | None = None, first_norm_done: bool = False) -> torch.Tensor:
+        """``first_norm_done``: layer 0's norm1 output already sits in ``first_norm_buffer(R)`` (written by the fused
+        embedding-sum + PE + LayerNorm kernel, ``first_norm_args``), so its LayerNorm launch is skipped."""
         R, d = x.shape
         if use_tc_attention is None:    # tcgen05 flash attention whenever the shape allows (bf16, head_dim 64)
             use_tc_attention = (self.cd == torch.bfloat16 and d // self.H == 64
@@ -116,7 +129,8 @@ class StackRunner:
         H, Dh = self.H, d // self.H
         for li, L in enumerate(self.w.layers):
             g, b, eps = L['norm1']
-            ops.residual_layernorm(x, g[min(stage, g.shape[0] - 1)], b[min(stage, b.shape[0] - 1)], h, eps=eps)
+            if not (li == 0 and first_norm_done):
+                ops.residual_layernorm(x, g[min(stage, g.shape[0] - 1)], b[min(stage, b.shape[0] - 1)], h, eps=eps)
             ops.linear(h, L['wqkv'], out=qkv)
             if kv_pools is not None:
                 ops.kv_scatter_paged(qkv, kv_pools[li], block_table, kv_lens, B, S, H, Dh)
@@ -650,6 +664,8 @@ class NARDecoder:
         self.pe_t = model.tokens_position_emb.pe.detach().float().reshape(-1, self.d).contiguous()
         self.pe_a = model.audio_position_emb.pe.detach().float().reshape(-1, self.d).contiguous()
         self.wproj = [m.weight.detach().to(self.cd).contiguous() for m in model.proj_layers]
+        self.fused_embed_norm = True   # embedding-sum + PE + the stage's first AdaLN in one kernel (tests: A/B)
+        self.fused_argmax = True       # greedy bf16 stages of >= 1024 target rows: logits GEMM + pick in one kernel (tests: A/B)
 
     @torch.no_grad()
     def generate(self, prompt_tokens: torch.Tensor, prompt_codes: torch.Tensor, target_tokens: torch.Tensor,
@@ -675,17 +691,34 @@ class NARDecoder:
         step = torch.zeros(1, device=dev, dtype=torch.int32)
         trace = []
         kv_lens = None
+        keys = None
         if target_lens is not None:
             kv_lens = (_i32(target_lens, dev) + (Tx + Tc)).contiguous()
         for n in range(1, Q):
             if _NVTX:
                 torch.cuda.nvtx.range_push(f'valle_b200.nar.stage{n}')
-            ops.embed_sum_pe(tok_i, self.tok_table, self.pe_t, x, out_rows_per_batch=S, out_row_offset=0)
+            # embedding sums + PE (valle_nar.py:140-152) and the stage's first AdaLN (modules.py:93-99, :271) in one kernel per
+            # segment: the residual rows are written once, layer 0's norm1 comes out of the same registers
+            fuse = self.fused_embed_norm and self.runner.fused_first_norm_ok()
+            nrm = dict(norm_y=self.runner.first_norm_buffer(B * S, dev), **self.runner.first_norm_args(n - 1)) if fuse else {}
+            ops.embed_sum_pe(tok_i, self.tok_table, self.pe_t, x, out_rows_per_batch=S, out_row_offset=0, **nrm)
             ops.embed_sum_pe(ids, self.code_tables, self.pe_a, x, t_split=Tc, nq_a=Q, nq_b=n,
-                             out_rows_per_batch=S, out_row_offset=Tx)
+                             out_rows_per_batch=S, out_row_offset=Tx, **nrm)
             self.runner.forward(x, B, S, mask_mode=MASK_NONE, kv_lens=kv_lens, stage=n - 1,
-                                use_tc_attention=use_tc_attention)
+                                use_tc_attention=use_tc_attention, first_norm_done=fuse)
             tgt = x.view(B, S, d)[:, Tx + Tc:].reshape(B * T, d)          # strided gather (memory plumbing)
+            if self.fused_argmax and self.precision == 'bf16' and greedy and not return_logits and ops.linear_argmax_ok(B * T, V):
+                # fused logits + greedy pick (valle_nar.py:157-160): the (B T x 1024) fp32 logits are never written; the row
+                # maxima leave the GEMM epilogue as packed keys and land in column n of the code tensor
+                hb = torch.empty(B * T, d, device=dev, dtype=self.cd)
+                ops.residual_layernorm(tgt, None, None, hb)
+                if keys is None:
+                    keys = torch.zeros(B * T, device=dev, dtype=torch.int64)
+                ops.linear_argmax(hb, self.wproj[n - 1], keys, ids[:, Tc:, n], rows_per_batch=T, batch_stride=(Tc + T) * Q,
+                                  row_stride=Q)
+                if _NVTX:
+                    torch.cuda.nvtx.range_pop()
+                continue
             if self.precision == 'bf16':
                 hb = torch.empty(B * T, d, device=dev, dtype=self.cd)
                 ops.residual_layernorm(tgt, None, None, hb)

@@ -53,8 +53,11 @@ def device_info() -> dict:
 def embed_sum_pe(ids: torch.Tensor, tables: torch.Tensor, pe: torch.Tensor, out: torch.Tensor, *,
                  t_split: int = 0, nq_a: int | None = None, nq_b: int | None = None, pos_offset: int = 0,
                  pos_b: torch.Tensor | None = None, out_rows_per_batch: int | None = None,
-                 out_row_offset: int = 0) -> None:
-    """ids int32 (B,T,Q); tables fp32 (Q,V,d); pe fp32 (max_len,d); out fp32 rows of d."""
+                 out_row_offset: int = 0, norm_y: torch.Tensor | None = None, gamma: torch.Tensor | None = None,
+                 beta: torch.Tensor | None = None, eps: float = 1e-5) -> None:
+    """ids int32 (B,T,Q); tables fp32 (Q,V,d); pe fp32 (max_len,d); out fp32 rows of d.  With ``norm_y`` (rows of d, bf16 or
+    fp32, indexed like out) the same kernel also writes LayerNorm(out row; gamma, beta, eps) -- a plain cast when gamma is
+    None -- from registers (vb_embed_sum_pe_norm, d in {256, 512, 1024})."""
     B, T, Q = ids.shape
     Qt, V, d = tables.shape
     assert Qt == Q and ids.dtype == torch.int32 and ids.is_contiguous() and tables.is_contiguous()
@@ -62,6 +65,14 @@ def embed_sum_pe(ids: torch.Tensor, tables: torch.Tensor, pe: torch.Tensor, out:
     nq_b = Q if nq_b is None else nq_b
     nq_a = nq_b if nq_a is None else nq_a
     rows = T if out_rows_per_batch is None else out_rows_per_batch
+    if norm_y is not None:
+        assert norm_y.is_contiguous() and norm_y.shape[-1] == d and norm_y.numel() == out.numel()
+        for t_ in (gamma, beta):
+            assert t_ is None or (t_.dtype == torch.float32 and t_.is_contiguous() and t_.numel() == d)
+        check(_L().vb_embed_sum_pe_norm(_ptr(ids), _ptr(tables), _ptr(pe), _ptr(out), B, T, Q, V, d, t_split, nq_a, nq_b,
+                                        pos_offset, _ptr(pos_b), pe.shape[0], rows, out_row_offset, _ptr(gamma), _ptr(beta),
+                                        eps, _ptr(norm_y), _code(norm_y.dtype), _stream()), 'vb_embed_sum_pe_norm')
+        return
     check(_L().vb_embed_sum_pe(_ptr(ids), _ptr(tables), _ptr(pe), _ptr(out), B, T, Q, V, d, t_split, nq_a, nq_b,
                                pos_offset, _ptr(pos_b), pe.shape[0], rows, out_row_offset, _stream()),
           'vb_embed_sum_pe')
@@ -112,6 +123,27 @@ def linear(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None = None, *
                          _ptr(residual), residual.stride(0) if residual is not None else 0, _ptr(out),
                          _code(out.dtype), out.stride(0), M, N, K, epi, _stream()), 'vb_linear')
     return out
+
+
+def linear_argmax_ok(M: int, N: int) -> bool:
+    """Shapes the fused logits + greedy-pick GEMM takes (the CTA-pair kernel: M >= 1024, N > 128)."""
+    return M >= 1024 and N > 128
+
+
+def linear_argmax(x: torch.Tensor, w: torch.Tensor, keys: torch.Tensor, out_tok: torch.Tensor, *, rows_per_batch: int | None = None,
+                  batch_stride: int | None = None, row_stride: int = 1) -> None:
+    """out_tok[...] = argmax_n (x @ w.T)[m, n] (lowest index on ties) without materialising the logits (vb_linear_argmax):
+    x (M,K), w (N,K) bf16; keys (M,) int64 scratch, zero before the first call (the call leaves it zero again); out_tok int32,
+    row m = b * rows_per_batch + t goes to element b * batch_stride + t * row_stride (default: dense (M,))."""
+    assert x.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and x.stride(1) == 1 and w.stride(1) == 1
+    assert x.shape[1] == w.shape[1], (x.shape, w.shape)
+    M, K = x.shape
+    N = w.shape[0]
+    assert keys.dtype == torch.int64 and keys.is_contiguous() and keys.numel() >= M and out_tok.dtype == torch.int32
+    rpb = rows_per_batch or max(M, 1)
+    bs = batch_stride if batch_stride is not None else rpb * row_stride
+    check(_L().vb_linear_argmax(_ptr(x), x.stride(0), _ptr(w), w.stride(0), _ptr(keys), _ptr(out_tok), rpb, bs, row_stride,
+                                M, N, K, _stream()), 'vb_linear_argmax')
 
 
 def linear_t(x: torch.Tensor, w: torch.Tensor, *, x_t: bool = False, w_t: bool = False, bias: torch.Tensor | None = None,
