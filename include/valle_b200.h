@@ -75,7 +75,8 @@ int vb_embed_sum_pe(const int32_t* ids, const float* tables, const float* pe, fl
  * AdaLN of modules.py:93-99; valle_ar.py:127-139 likewise): out row as above AND
  *   y[row][:] = (out[row] - mean) * rsqrt(var + eps) * gamma + beta      (gamma = beta = NULL: y = cast(out))
  * with the row kept in registers in between (one warp per row), so layer 0's norm1 never re-reads the residual stream.
- * y: y_dtype [rows][d], indexed like out.  d in {256, 512, 1024}.  Bit-identical to vb_embed_sum_pe + vb_residual_layernorm. */
+ * y: y_dtype [rows][d], indexed like out.  d in {256, 512, 1024}.  Bit-identical to vb_embed_sum_pe + vb_residual_layernorm for
+ * more than 1024 rows (the warp-per-row LayerNorm kernel, same lane layout); equal to fp32 rounding below (CTA-per-row kernel). */
 int vb_embed_sum_pe_norm(const int32_t* ids, const float* tables, const float* pe, float* out,
                          int B, int T, int Q, int V, int d, int t_split, int nq_a, int nq_b,
                          int pos_offset, const int32_t* pos_b, int max_len,

@@ -316,3 +316,28 @@ def test_nar_fused_logits_argmax_equals_unfused_stages(tmp_path):
         assert fused.shape == (B, T, 8) and fused.dtype == torch.int64
         assert torch.equal(fused, plain)
         assert torch.equal(fused[:, :, 0], first)
+
+
+@pytest.mark.parametrize('precision', ['fp32', 'bf16'])
+def test_ar_prefill_fused_embed_norm_equals_unfused(tmp_path, precision):
+    """AR prefill with the embedding + PE + layer-0 norm1 kernel (vb_embed_sum_pe_norm) against the two-kernel form: the
+    kernels agree bit for bit (above 1024 rows, where the unfused side runs the warp-per-row LayerNorm), so the continuation
+    (prefill state + KV pools + 24 cached steps) must be identical, ragged prompts included."""
+    valle2_b200.set_precision(precision)
+    oc = synth.tiny_config('LayerNorm')
+    model, sd = build('ValleAR', oc, tmp_path, 2)
+    g = torch.Generator().manual_seed(3)
+    B = 5
+    tok = torch.randint(0, 256, (B, 13), generator=g).cuda()
+    cod = torch.randint(0, 1024, (B, 220), generator=g)          # 5 x 233 rows: the large-M LayerNorm kernel on the unfused side
+    cod[:, 0] = oc.bos_token
+    lens = torch.tensor([220, 90, 120, 220, 30])
+    eng = model._engine()
+    assert eng.fused_embed_norm
+    fused, n1 = model.generate_batch(tok, cod.cuda(), code_lens=lens, max_new=24, ignore_eos=True)
+    eng.fused_embed_norm = False
+    try:
+        plain, n2 = model.generate_batch(tok, cod.cuda(), code_lens=lens, max_new=24, ignore_eos=True)
+    finally:
+        eng.fused_embed_norm = True
+    assert torch.equal(fused, plain) and torch.equal(torch.as_tensor(n1).cpu(), torch.as_tensor(n2).cpu())

@@ -749,15 +749,17 @@ def test_embed_sum_pe_norm_equals_embed_then_layernorm(ops, ydt, d, affine):
     """vb_embed_sum_pe_norm (embedding sum + PE + the first (Ada)LayerNorm in one kernel; valle_nar.py:140-152 into
     modules.py:271) against the two kernels it replaces: same residual rows and same normalised rows, bit for bit (same order
     of operations), for both segments of a stage's input (text rows; prompt rows with all codebooks + target rows with the
-    first n) written at their row offsets of one (B, S, d) buffer."""
+    first n) written at their row offsets of one (B, S, d) buffer.  (More than 1024 rows: vb_residual_layernorm then runs its
+    warp-per-row kernel, whose lane layout the fused kernel shares; at decode-shape row counts it runs a CTA-per-row kernel that
+    sums in another order, equal only to fp32 rounding -- second half of the test.)"""
     torch.manual_seed(d)
-    B, Tx, Tc, T, Q, V = 3, 5, 7, 9, 8, 50
+    B, Tx, Tc, T, Q, V = 3, 5, 7, 400, 8, 50
     S = Tx + Tc + T
     tok = torch.randint(0, 256, (B, Tx, 1), dtype=torch.int32, device='cuda')
     ids = torch.randint(0, V, (B, Tc + T, Q), dtype=torch.int32, device='cuda')
     tok_table = torch.randn(1, 256, d, device='cuda')
     tables = torch.randn(Q, V, d, device='cuda')
-    pe = torch.randn(64, d, device='cuda')
+    pe = torch.randn(512, d, device='cuda')
     gamma = torch.randn(d, device='cuda') if affine else None
     beta = torch.randn(d, device='cuda') if affine else None
     x0 = torch.full((B * S, d), 7.0, device='cuda')
@@ -775,3 +777,12 @@ def test_embed_sum_pe_norm_equals_embed_then_layernorm(ops, ydt, d, affine):
     # and against torch on the same rows
     ref = torch.nn.functional.layer_norm(x0, (d,), gamma, beta, 1e-5) if affine else x0
     assert rel_err(y1.float(), ref) < (1e-2 if ydt == torch.bfloat16 else 1e-5)
+    # a decode-shape row count (CTA-per-row LayerNorm on the unfused side): same rows, normalised rows equal to rounding
+    Bs, Ts = 2, 9
+    xs0, xs1 = torch.empty(Bs * Ts, d, device='cuda'), torch.empty(Bs * Ts, d, device='cuda')
+    ys0, ys1 = torch.empty(Bs * Ts, d, device='cuda', dtype=ydt), torch.empty(Bs * Ts, d, device='cuda', dtype=ydt)
+    ops.embed_sum_pe(ids[:Bs, :Ts].contiguous(), tables, pe, xs0, nq_b=5)
+    ops.residual_layernorm(xs0, gamma, beta, ys0, eps=1e-5)
+    ops.embed_sum_pe(ids[:Bs, :Ts].contiguous(), tables, pe, xs1, nq_b=5, norm_y=ys1, gamma=gamma, beta=beta, eps=1e-5)
+    assert torch.equal(xs0, xs1)
+    assert rel_err(ys1.float(), ys0.float()) < (8e-3 if ydt == torch.bfloat16 else 2e-6)

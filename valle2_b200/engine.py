@@ -199,6 +199,7 @@ class ARDecoder:
         # sequences), 'tc' = tcgen05 swap-AB GEMMs with the split-K reduction + folded LayerNorm + epilogues inside the launch
         # (csrc/gemm_decode_tc.cu, 5 launches per layer), 'splitk' = the round-1 form: tcgen05 split-K slices + LayerNorm /
         # GELU-reduce kernels (8 launches per layer; kept as the A/B reference), 'auto' = lean up to 8 sequences, tc above.
+        self.fused_embed_norm = True   # prefill: embedding + PE + layer 0's norm1 in one kernel (tests: A/B)
         self.decode_gemm = os.environ.get('VALLE_B200_DECODE_GEMM', 'auto')
         # lean path, >= 4 sequences: the attention kernel releases its successors only after its own wait (see
         # csrc/attn_decode.cu; measured -2 % step time at B = 4..8, +2 % at B = 1, tools/step_breakdown.py)
@@ -574,13 +575,16 @@ class ARDecoder:
         tok_i = _i32(tokens, dev).view(B, Tx, 1)
         cod_i = _i32(codes, dev).view(B, P, 1)
         x = torch.empty(B * S, self.d, device=dev, dtype=torch.float32)
-        ops.embed_sum_pe(tok_i, self.tok_table, self.pe_t, x, out_rows_per_batch=S, out_row_offset=0)
-        ops.embed_sum_pe(cod_i, self.aud_table, self.pe_a, x, out_rows_per_batch=S, out_row_offset=Tx)
+        # embedding + PE (valle_ar.py:127-139) and layer 0's norm1 (modules.py:271) in one kernel per segment
+        fuse = self.fused_embed_norm and self.runner.fused_first_norm_ok()
+        nrm = dict(norm_y=self.runner.first_norm_buffer(B * S, dev), **self.runner.first_norm_args(0)) if fuse else {}
+        ops.embed_sum_pe(tok_i, self.tok_table, self.pe_t, x, out_rows_per_batch=S, out_row_offset=0, **nrm)
+        ops.embed_sum_pe(cod_i, self.aud_table, self.pe_a, x, out_rows_per_batch=S, out_row_offset=Tx, **nrm)
         xl = torch.full((B,), Tx, device=dev, dtype=torch.int32)
         cl = torch.full((B,), P, device=dev, dtype=torch.int32) if code_lens is None else _i32(code_lens, dev)
         kv_lens = (xl + cl).contiguous()
         self.runner.forward(x, B, S, mask_mode=MASK_PREFIX_LM, x_lens=xl, kv_lens=kv_lens, kv_pools=st['pools'],
-                            block_table=st['block_table'])
+                            block_table=st['block_table'], first_norm_done=fuse)
         st['seq_lens'].copy_(kv_lens - 1)
         st['audio_pos'].copy_(cl - 1)
         rows = x.view(B, S, self.d)
