@@ -28,10 +28,14 @@ def _worker(rank, world_size, port, n_items, out_dir):
     dist.destroy_process_group()
 
 
-def test_sharded_generation_matches_single_process(tmp_path):
+import pytest
+
+
+@pytest.mark.parametrize('n_items', [7, 1, 0])      # odd count; fewer items than ranks (rank 1's shard is empty); nothing at all
+def test_sharded_generation_matches_single_process(tmp_path, n_items):
     from valle2_b200 import parallel
-    n_items = 7
     assert parallel.shard_indices(7, 0, 2) == [0, 2, 4, 6] and parallel.shard_indices(7, 1, 2) == [1, 3, 5]
+    assert parallel.shard_indices(1, 1, 2) == [] and parallel.shard_indices(0, 0, 2) == []
     ref_rows, ref_lens = _fake_decode(list(range(n_items)))
     single_rows, single_lens = parallel.generate_sharded(_fake_decode, n_items, pad_value=-1)
     assert torch.equal(single_lens, ref_lens)
