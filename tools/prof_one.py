@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Launch ONE kernel configuration a few times (no graphs) -- the target of `ncu --set full` captures.
-usage: python tools/prof_one.py {attn_decode|gemm_decode|rows_decode [B]|gemm_large|attn_prefill}"""
+usage: python tools/prof_one.py {attn_decode|gemm_decode|rows_decode [B]|gemm_large|gemm_argmax|attn_prefill}"""
 import os
 import sys
 
@@ -59,6 +59,18 @@ elif what == 'gemm_large':           # NAR config 3 shapes (M = 64 x 900)
             ops.linear(x, w, bias, gelu=True)
         else:
             ops.linear(x, w)
+elif what == 'gemm_argmax':          # a greedy NAR stage's logits projection + pick (batch 64, 750 target frames): unfused, then fused
+    M, N, K = 48000, 1024, 1024
+    x = torch.randn(M, K, device='cuda').bfloat16()
+    w = (torch.randn(N, K, device='cuda') / 32).bfloat16()
+    tok0 = torch.empty(M, device='cuda', dtype=torch.int32)
+    tok1 = torch.empty(M, device='cuda', dtype=torch.int32)
+    keys = torch.zeros(M, device='cuda', dtype=torch.int64)
+    logits = ops.linear(x, w, out_dtype=torch.float32)                                        # gemm_tc_kernel<..., EPI_NONE>: 197 MB of logits out
+    ops.sample(logits, 1, 0, N, M, N, temperature=1.0, top_k=1, top_p=1.0, out_tok=tok0)     # sample_kernel: 197 MB back in
+    ops.linear_argmax(x, w, keys, tok1)                                                       # gemm_tc_kernel<..., EPI_ARGMAX> + argmax_unpack_kernel
+    torch.cuda.synchronize()
+    assert torch.equal(tok0, tok1)
 elif what == 'attn_prefill':         # NAR config 3 attention: B=64, S=900, 16 heads
     B, S = 64, 900
     qkv = torch.randn(B * S, 3 * d, device='cuda').bfloat16()
