@@ -126,6 +126,16 @@ int vb_linear_argmax(const void* x, int64_t ldx, const void* w, int64_t ldw, uns
                      int64_t rows_per_batch, int64_t batch_stride, int64_t row_stride, int64_t M, int64_t N, int64_t K,
                      void* stream);
 
+/* Fused logits + Categorical draw (valle_nar.py:160: `Categorical(logits = logits / temperature).sample()`), same kernel and same
+ * arguments as vb_linear_argmax: the epilogue scans logit / temperature + Gumbel noise, and the arg-max of that IS a draw from
+ * softmax(logits / temperature) (Gumbel-max trick).  Noise = -log(-log(u)), u = a counter-based hash of (seed, step, row, column),
+ * so a call is a pure function of its arguments (step: the stage, so that stages draw independently).  The draws differ from
+ * vb_sample's inverse-CDF draws for the same seed (as both differ from torch.multinomial's stream: sampling is compared by
+ * distribution); temperature > 0. */
+int vb_linear_categorical(const void* x, int64_t ldx, const void* w, int64_t ldw, unsigned long long* keys, int32_t* out_tok,
+                          int64_t rows_per_batch, int64_t batch_stride, int64_t row_stride, int64_t M, int64_t N, int64_t K,
+                          float temperature, uint64_t seed, int step, void* stream);
+
 /* The same bf16 tcgen05 GEMM with operands optionally given TRANSPOSED in memory (MN-major MMA operands, no copy):
  *   x_transposed: x is [K][M] row-major (pitch ldx) instead of [M][K];  w_transposed: w is [K][N] (pitch ldw) instead of [N][K].
  *   y[M,N] = epilogue(X . W^T) as for vb_linear.  Serves the backward pass of every nn.Linear of the path without a

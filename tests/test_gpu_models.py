@@ -4,6 +4,8 @@
   - bf16 mode: logits within 1e-2 relative; tokens compared up to the first step whose reference top-1/top-2
     margin is below the bf16 noise (random-init margins go down to 1e-3).
 """
+import math
+
 import numpy as np
 import pytest
 import torch
@@ -341,3 +343,35 @@ def test_ar_prefill_fused_embed_norm_equals_unfused(tmp_path, precision):
     finally:
         eng.fused_embed_norm = True
     assert torch.equal(fused, plain) and torch.equal(torch.as_tensor(n1).cpu(), torch.as_tensor(n2).cpu())
+
+
+def test_nar_sampled_stages_fused_categorical(tmp_path):
+    """ValleNAR.generate as the reference runs it (valle_nar.py:160: a Categorical draw per stage, greedy=False) on the fused
+    logits + draw kernel: codes in range, first codebook untouched, reproducible by seed, different for another seed, and --
+    because every stage conditions on the previous stages' draws -- statistically indistinguishable from the unfused path
+    (vb_linear + vb_sample, other random stream): per-stage agreement with the greedy codes is the same within noise."""
+    valle2_b200.set_precision('bf16')
+    oc = synth.tiny_config('AdaptiveLayerNorm')
+    model, sd = build('ValleNAR', oc, tmp_path, 4)
+    g = torch.Generator().manual_seed(12)
+    B, Tp, Tt, Tc, T = 4, 6, 9, 20, 512                      # B T = 2048 target rows
+    pt, tt = torch.randint(0, 256, (B, Tp), generator=g).cuda(), torch.randint(0, 256, (B, Tt), generator=g).cuda()
+    pc = torch.randint(0, 1024, (B, Tc, 8), generator=g).cuda()
+    first = torch.randint(0, 1024, (B, T), generator=g).cuda()
+    eng = model._engine()
+    a = eng.generate(pt, pc, tt, first, greedy=False, temperature=1.0, seed=5)
+    assert a.shape == (B, T, 8) and int(a.min()) >= 0 and int(a.max()) < 1024
+    assert torch.equal(a[:, :, 0], first)
+    assert torch.equal(a, eng.generate(pt, pc, tt, first, greedy=False, temperature=1.0, seed=5))
+    b = eng.generate(pt, pc, tt, first, greedy=False, temperature=1.0, seed=6)
+    assert (a[:, :, 1:] != b[:, :, 1:]).double().mean().item() > 0.3
+    greedy = eng.generate(pt, pc, tt, first, greedy=True)
+    eng.fused_argmax = False
+    try:
+        c = eng.generate(pt, pc, tt, first, greedy=False, temperature=1.0, seed=5)
+    finally:
+        eng.fused_argmax = True
+    # stage 2 (column 1) sees identical inputs in all runs: P(draw == arg-max) must agree between the two samplers
+    hit_fused = (a[:, :, 1] == greedy[:, :, 1]).double().mean().item()
+    hit_plain = (c[:, :, 1] == greedy[:, :, 1]).double().mean().item()
+    assert abs(hit_fused - hit_plain) < 5 * math.sqrt(0.25 / (B * T)) + 0.01, (hit_fused, hit_plain)

@@ -786,3 +786,44 @@ def test_embed_sum_pe_norm_equals_embed_then_layernorm(ops, ydt, d, affine):
     ops.embed_sum_pe(ids[:Bs, :Ts].contiguous(), tables, pe, xs1, nq_b=5, norm_y=ys1, gamma=gamma, beta=beta, eps=1e-5)
     assert torch.equal(xs0, xs1)
     assert rel_err(ys1.float(), ys0.float()) < (8e-3 if ydt == torch.bfloat16 else 2e-6)
+
+
+def test_linear_categorical_draws_from_the_softmax(ops):
+    """vb_linear_categorical (valle_nar.py:160, `Categorical(logits / temperature).sample()`, fused into the logits GEMM by the
+    Gumbel-max trick): 65 536 rows with IDENTICAL activations are 65 536 independent draws from one known distribution.
+    Empirical frequencies against softmax(logits / T): the 20 likeliest classes within 5 sigma, total variation small,
+    chi-square per degree of freedom near 1 (would expose correlated noise across rows or columns).  Also: a call is a pure
+    function of (seed, step); another step or seed gives other draws; T -> 0 degenerates to the arg-max."""
+    torch.manual_seed(3)
+    M, N, K, T = 65536, 1024, 64, 0.8
+    x1 = torch.randn(1, K, device='cuda').bfloat16()
+    x = x1.expand(M, K).contiguous()
+    w = (torch.randn(N, K, device='cuda') * 0.3).bfloat16()
+    logits = ops.linear(x[:1024], w, out_dtype=torch.float32)[0].double()
+    p = torch.softmax(logits / T, -1)
+    keys = torch.zeros(M, device='cuda', dtype=torch.int64)
+
+    def draw(seed, step, temperature=T):
+        out = torch.full((M,), -1, device='cuda', dtype=torch.int32)
+        ops.linear_argmax(x, w, keys, out, temperature=temperature, seed=seed, step=step)
+        assert int(keys.abs().max()) == 0
+        assert int(out.min()) >= 0 and int(out.max()) < N
+        return out.long()
+
+    a = draw(11, 3)
+    f = torch.bincount(a, minlength=N).double() / M
+    top = p.topk(20).indices
+    sigma = (p[top] * (1 - p[top]) / M).sqrt()
+    assert ((f[top] - p[top]).abs() < 5 * sigma + 1e-4).all(), (f[top], p[top])
+    assert 0.5 * (f - p).abs().sum().item() < 0.06
+    big = p * M >= 20
+    chi2 = (((f[big] - p[big]) * M) ** 2 / (p[big] * M)).sum().item() / int(big.sum())
+    assert 0.6 < chi2 < 1.4, chi2
+    # rows are independent of each other: neighbouring rows agree about as often as two independent draws would
+    agree = (a[1:] == a[:-1]).double().mean().item()
+    assert abs(agree - (p * p).sum().item()) < 5 * math.sqrt((p * p).sum().item() / M) + 1e-3
+    assert torch.equal(a, draw(11, 3))                      # pure function of its arguments
+    assert (a != draw(11, 4)).double().mean().item() > 0.5  # another stage: other draws
+    assert (a != draw(12, 3)).double().mean().item() > 0.5  # another seed: other draws
+    cold = draw(11, 3, temperature=1e-4)                    # T -> 0: the arg-max (noise / logit-gap ~ 1e-3)
+    assert (cold == logits.argmax().item()).double().mean().item() > 0.999

@@ -27,6 +27,7 @@ SIGNATURES = {
     'vb_residual_layernorm': (_i, [_p, _p, _i, _i64, _p, _p, _p, _p, _i, _i64, _i, _f, _p]),
     'vb_reduce_bias_act': (_i, [_p, _i, _i64, _p, _i, _p, _i, _i64, _i, _p]),
     'vb_linear': (_i, [_p, _i, _i64, _p, _i, _i64, _p, _p, _i64, _p, _i, _i64, _i64, _i64, _i64, _i, _p]),
+    'vb_linear_categorical': (_i, [_p, _i64, _p, _i64, _p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _f, _u64, _i, _p]),
     'vb_linear_argmax': (_i, [_p, _i64, _p, _i64, _p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _p]),
     'vb_linear_t': (_i, [_p, _i64, _i, _p, _i64, _i, _p, _p, _i64, _p, _i, _i64, _i64, _i64, _i64, _i, _p]),
     'vb_linear_decode_splits': (_i, [_i64, _i64, _i]),

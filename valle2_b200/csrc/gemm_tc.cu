@@ -43,6 +43,11 @@ struct GemmParams {
     int late_trigger;          // release the dependent kernel only after our own pdl_wait (see vb_linear_decode flags)
     int tma_store;             // swap-AB: the slices are written by TMA stores through tm_p (needs 16-byte aligned slice rows)
     unsigned long long* dbg;   // optional %globaltimer stamps [cta][8] (vb_linear_decode_set_debug)
+    // VB_EPI_ARGMAX only: rng_on != 0 turns the pick into a Categorical draw (Gumbel-max): score = logit * inv_temp + Gumbel noise
+    // from a counter-based hash of (rng_key, row, column)
+    float inv_temp;
+    int rng_on;
+    unsigned long long rng_key;
 };
 
 __device__ __forceinline__ unsigned long long gtimer() {
@@ -412,9 +417,22 @@ __global__ void __launch_bounds__(num_threads(SWAP, TWO && EPI >= 0 && EPI != VB
                 // scanned straight out of tensor memory (ascending columns, strict '>' keeps the lowest column of a tie) and the
                 // row's (value, column) maximum joins the other warps / tiles of the row through one 64-bit atomicMax.  Nothing
                 // is staged and no logit is stored.
+                // rng_on (vb_linear_categorical, valle_nar.py:160): the same scan over logit / temperature + Gumbel noise -- the arg-max
+                // of that is an exact draw from Categorical(softmax(logits / temperature)) (Gumbel-max), so the sampled stage needs
+                // no logits in HBM either.  Noise = -log(-log(u)), u from a counter-based hash of (key, row, column): a 64-bit
+                // splitmix round per row, one 32-bit finaliser per logit; 24-bit uniforms strictly inside (0, 1).
                 float best = 0.f;
                 int best_col = -1;
                 const int n_base = tb * BN;
+                const bool noisy = p.rng_on != 0;
+                uint32_t row_key = 0;
+                if (noisy) {
+                    unsigned long long z = p.rng_key + 0x9E3779B97F4A7C15ull * (static_cast<unsigned long long>(row) + 1ull);
+                    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+                    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+                    z ^= z >> 31;
+                    row_key = static_cast<uint32_t>(z >> 32) ^ static_cast<uint32_t>(z);
+                }
 #pragma unroll 1
                 for (int c0 = e_c_begin; c0 < e_c_end; c0 += 32) {
                     const int n0 = n_base + c0;
@@ -424,7 +442,17 @@ __global__ void __launch_bounds__(num_threads(SWAP, TWO && EPI >= 0 && EPI != VB
                     tmem_ld_wait();
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
-                        const float val = __uint_as_float(v[j]);
+                        float val = __uint_as_float(v[j]);
+                        if (noisy) {
+                            uint32_t h = row_key ^ (static_cast<uint32_t>(n0 + j) * 0x9E3779B9u);
+                            h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
+                            const float u = (static_cast<float>(h >> 8) + 0.5f) * (1.f / 16777216.f);
+                            // E = -log(u) ~ Exp(1).  The largest noise values (the winners) come from u next to 1, where the fast
+                            // logarithm's ABSOLUTE error (2^-22) would swamp E: there E = -log1p(-w), w = 1 - u exact, by its series
+                            const float w1 = 1.f - u;
+                            const float e = (w1 < 0.015625f) ? w1 * (1.f + w1 * (0.5f + w1 * 0.33333334f)) : -__logf(u);
+                            val = fmaf(val, p.inv_temp, -__logf(e));
+                        }
                         if (n0 + j < p.rows_b && val > -INFINITY && (best_col < 0 || val > best)) { best = val; best_col = n0 + j; }
                     }
                 }
@@ -599,7 +627,7 @@ int launch_gemm_tc_pair(const CUtensorMap& ta, const CUtensorMap& tb, const Gemm
 // y[M,N] = epi(x . w^T), bf16 operands
 int vb_linear_tc(const void* x, int64_t ldx, const void* w, int64_t ldw, const float* bias, const float* residual,
                  int64_t ldr, void* y, int y_dtype, int64_t ldy, int64_t M, int64_t N, int64_t K, int epilogue,
-                 cudaStream_t st) {
+                 cudaStream_t st, float inv_temp, int rng_on, unsigned long long rng_key) {
     VB_REQUIRE(K % 8 == 0, VB_ERR_UNSUPPORTED, "vb_linear(bf16): K must be a multiple of 8 (got %lld)", (long long)K);
     CUtensorMap ta, tb;
     int rc;
@@ -609,6 +637,7 @@ int vb_linear_tc(const void* x, int64_t ldx, const void* w, int64_t ldw, const f
     p.kb_total = (int)vb_ceil_div(K, BK); p.kb_per_split = p.kb_total; p.n_split = 1;
     p.epilogue = epilogue; p.bias = bias; p.residual = residual; p.ldr = ldr;
     p.y = y; p.y_bf16 = (y_dtype == VB_BF16); p.ldy = ldy;
+    p.inv_temp = inv_temp; p.rng_on = rng_on; p.rng_key = rng_key;
     if ((rc = vb_make_tmap_bf16_2d(&ta, x, M, K, ldx, BM, BK)) != VB_OK) return rc;
     if (N > 128) {
         p.tiles_b = (int)vb_ceil_div(N, 256);
@@ -643,7 +672,7 @@ int vb_linear_tc(const void* x, int64_t ldx, const void* w, int64_t ldw, const f
 int vb_linear_tc_t(const void* x, int64_t ldx, int x_mn, const void* w, int64_t ldw, int w_mn, const float* bias,
                    const float* residual, int64_t ldr, void* y, int y_dtype, int64_t ldy, int64_t M, int64_t N, int64_t K,
                    int epilogue, cudaStream_t st) {
-    if (!x_mn && !w_mn) return vb_linear_tc(x, ldx, w, ldw, bias, residual, ldr, y, y_dtype, ldy, M, N, K, epilogue, st);
+    if (!x_mn && !w_mn) return vb_linear_tc(x, ldx, w, ldw, bias, residual, ldr, y, y_dtype, ldy, M, N, K, epilogue, st, 1.f, 0, 0ull);
     VB_REQUIRE(ldx % 8 == 0 && ldw % 8 == 0, VB_ERR_UNSUPPORTED, "vb_linear_t: operand pitches must be multiples of 8");
     CUtensorMap ta, tb;
     int rc;

@@ -6,7 +6,7 @@ int vb_linear_simt(const float* x, int64_t ldx, const float* w, int64_t ldw, con
                    cudaStream_t st);
 int vb_linear_tc(const void* x, int64_t ldx, const void* w, int64_t ldw, const float* bias, const float* residual,
                  int64_t ldr, void* y, int y_dtype, int64_t ldy, int64_t M, int64_t N, int64_t K, int epilogue,
-                 cudaStream_t st);
+                 cudaStream_t st, float inv_temp = 1.f, int rng_on = 0, unsigned long long rng_key = 0ull);
 
 int vb_linear_tc_t(const void* x, int64_t ldx, int x_mn, const void* w, int64_t ldw, int w_mn, const float* bias,
                    const float* residual, int64_t ldr, void* y, int y_dtype, int64_t ldy, int64_t M, int64_t N, int64_t K,
@@ -59,17 +59,32 @@ __global__ void argmax_unpack_kernel(unsigned long long* __restrict__ keys, int3
 }
 }  // namespace
 
-extern "C" int vb_linear_argmax(const void* x, int64_t ldx, const void* w, int64_t ldw, unsigned long long* keys, int32_t* out_tok,
-                                int64_t rows_per_batch, int64_t batch_stride, int64_t row_stride, int64_t M, int64_t N, int64_t K,
-                                void* stream) {
-    VB_REQUIRE(x && w && keys && out_tok, VB_ERR_BAD_ARG, "vb_linear_argmax: null pointer");
-    VB_REQUIRE(M >= 0 && N >= 1 && K >= 1 && rows_per_batch >= 1, VB_ERR_BAD_ARG, "vb_linear_argmax: bad shape M=%lld N=%lld K=%lld rows_per_batch=%lld",
+static int linear_pick(const void* x, int64_t ldx, const void* w, int64_t ldw, unsigned long long* keys, int32_t* out_tok,
+                       int64_t rows_per_batch, int64_t batch_stride, int64_t row_stride, int64_t M, int64_t N, int64_t K,
+                       float inv_temp, int rng_on, unsigned long long rng_key, void* stream) {
+    VB_REQUIRE(x && w && keys && out_tok, VB_ERR_BAD_ARG, "vb_linear_argmax / vb_linear_categorical: null pointer");
+    VB_REQUIRE(M >= 0 && N >= 1 && K >= 1 && rows_per_batch >= 1, VB_ERR_BAD_ARG, "vb_linear_argmax / vb_linear_categorical: bad shape M=%lld N=%lld K=%lld rows_per_batch=%lld",
                (long long)M, (long long)N, (long long)K, (long long)rows_per_batch);
     if (M == 0) return VB_OK;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const int rc = vb_linear_tc(x, ldx, w, ldw, nullptr, nullptr, 0, keys, VB_F32, N, M, N, K, VB_EPI_ARGMAX, st);
+    const int rc = vb_linear_tc(x, ldx, w, ldw, nullptr, nullptr, 0, keys, VB_F32, N, M, N, K, VB_EPI_ARGMAX, st, inv_temp, rng_on, rng_key);
     if (rc != VB_OK) return rc;
     argmax_unpack_kernel<<<static_cast<unsigned>((M + 255) / 256), 256, 0, st>>>(keys, out_tok, rows_per_batch, batch_stride, row_stride, M);
     VB_CUDA(cudaGetLastError());
     return VB_OK;
+}
+
+extern "C" int vb_linear_argmax(const void* x, int64_t ldx, const void* w, int64_t ldw, unsigned long long* keys, int32_t* out_tok,
+                                int64_t rows_per_batch, int64_t batch_stride, int64_t row_stride, int64_t M, int64_t N, int64_t K,
+                                void* stream) {
+    return linear_pick(x, ldx, w, ldw, keys, out_tok, rows_per_batch, batch_stride, row_stride, M, N, K, 1.f, 0, 0ull, stream);
+}
+
+extern "C" int vb_linear_categorical(const void* x, int64_t ldx, const void* w, int64_t ldw, unsigned long long* keys, int32_t* out_tok,
+                                     int64_t rows_per_batch, int64_t batch_stride, int64_t row_stride, int64_t M, int64_t N, int64_t K,
+                                     float temperature, uint64_t seed, int step, void* stream) {
+    VB_REQUIRE(temperature > 0.f, VB_ERR_BAD_ARG, "vb_linear_categorical: temperature must be positive (got %f)", (double)temperature);
+    const unsigned long long key = static_cast<unsigned long long>(seed) * 0xD1342543DE82EF95ull +
+                                   static_cast<unsigned long long>(static_cast<unsigned>(step)) * 0xA0761D6478BD642Full + 0x2545F4914F6CDD1Dull;
+    return linear_pick(x, ldx, w, ldw, keys, out_tok, rows_per_batch, batch_stride, row_stride, M, N, K, 1.f / temperature, 1, key, stream);
 }

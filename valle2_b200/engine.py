@@ -669,7 +669,7 @@ class NARDecoder:
         self.pe_a = model.audio_position_emb.pe.detach().float().reshape(-1, self.d).contiguous()
         self.wproj = [m.weight.detach().to(self.cd).contiguous() for m in model.proj_layers]
         self.fused_embed_norm = True   # embedding-sum + PE + the stage's first AdaLN in one kernel (tests: A/B)
-        self.fused_argmax = True       # greedy bf16 stages of >= 1024 target rows: logits GEMM + pick in one kernel (tests: A/B)
+        self.fused_argmax = True       # bf16 stages of >= 1024 target rows: logits GEMM + pick / draw in one kernel (tests: A/B)
 
     @torch.no_grad()
     def generate(self, prompt_tokens: torch.Tensor, prompt_codes: torch.Tensor, target_tokens: torch.Tensor,
@@ -711,15 +711,16 @@ class NARDecoder:
             self.runner.forward(x, B, S, mask_mode=MASK_NONE, kv_lens=kv_lens, stage=n - 1,
                                 use_tc_attention=use_tc_attention, first_norm_done=fuse)
             tgt = x.view(B, S, d)[:, Tx + Tc:].reshape(B * T, d)          # strided gather (memory plumbing)
-            if self.fused_argmax and self.precision == 'bf16' and greedy and not return_logits and ops.linear_argmax_ok(B * T, V):
-                # fused logits + greedy pick (valle_nar.py:157-160): the (B T x 1024) fp32 logits are never written; the row
-                # maxima leave the GEMM epilogue as packed keys and land in column n of the code tensor
+            if self.fused_argmax and self.precision == 'bf16' and not return_logits and ops.linear_argmax_ok(B * T, V):
+                # fused logits + pick (valle_nar.py:157-160): the (B T x 1024) fp32 logits are never written; the row maxima --
+                # of the logits (greedy) or of logits / temperature + Gumbel noise (the reference's Categorical draw) -- leave
+                # the GEMM epilogue as packed keys and land in column n of the code tensor
                 hb = torch.empty(B * T, d, device=dev, dtype=self.cd)
                 ops.residual_layernorm(tgt, None, None, hb)
                 if keys is None:
                     keys = torch.zeros(B * T, device=dev, dtype=torch.int64)
                 ops.linear_argmax(hb, self.wproj[n - 1], keys, ids[:, Tc:, n], rows_per_batch=T, batch_stride=(Tc + T) * Q,
-                                  row_stride=Q)
+                                  row_stride=Q, temperature=None if greedy else temperature, seed=seed, step=n)
                 if _NVTX:
                     torch.cuda.nvtx.range_pop()
                 continue

@@ -131,8 +131,11 @@ def linear_argmax_ok(M: int, N: int) -> bool:
 
 
 def linear_argmax(x: torch.Tensor, w: torch.Tensor, keys: torch.Tensor, out_tok: torch.Tensor, *, rows_per_batch: int | None = None,
-                  batch_stride: int | None = None, row_stride: int = 1) -> None:
-    """out_tok[...] = argmax_n (x @ w.T)[m, n] (lowest index on ties) without materialising the logits (vb_linear_argmax):
+                  batch_stride: int | None = None, row_stride: int = 1, temperature: float | None = None, seed: int = 0,
+                  step: int = 0) -> None:
+    """out_tok[...] = argmax_n (x @ w.T)[m, n] (lowest index on ties) without materialising the logits (vb_linear_argmax);
+    with ``temperature`` a draw from Categorical(softmax(logits / temperature)) instead (vb_linear_categorical: Gumbel-max in the
+    same epilogue, noise a pure function of (seed, step, row, column)):
     x (M,K), w (N,K) bf16; keys (M,) int64 scratch, zero before the first call (the call leaves it zero again); out_tok int32,
     row m = b * rows_per_batch + t goes to element b * batch_stride + t * row_stride (default: dense (M,))."""
     assert x.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and x.stride(1) == 1 and w.stride(1) == 1
@@ -142,8 +145,13 @@ def linear_argmax(x: torch.Tensor, w: torch.Tensor, keys: torch.Tensor, out_tok:
     assert keys.dtype == torch.int64 and keys.is_contiguous() and keys.numel() >= M and out_tok.dtype == torch.int32
     rpb = rows_per_batch or max(M, 1)
     bs = batch_stride if batch_stride is not None else rpb * row_stride
-    check(_L().vb_linear_argmax(_ptr(x), x.stride(0), _ptr(w), w.stride(0), _ptr(keys), _ptr(out_tok), rpb, bs, row_stride,
-                                M, N, K, _stream()), 'vb_linear_argmax')
+    if temperature is None:
+        check(_L().vb_linear_argmax(_ptr(x), x.stride(0), _ptr(w), w.stride(0), _ptr(keys), _ptr(out_tok), rpb, bs, row_stride,
+                                    M, N, K, _stream()), 'vb_linear_argmax')
+    else:
+        check(_L().vb_linear_categorical(_ptr(x), x.stride(0), _ptr(w), w.stride(0), _ptr(keys), _ptr(out_tok), rpb, bs, row_stride,
+                                         M, N, K, float(temperature), int(seed) & ((1 << 64) - 1), int(step), _stream()),
+              'vb_linear_categorical')
 
 
 def linear_t(x: torch.Tensor, w: torch.Tensor, *, x_t: bool = False, w_t: bool = False, bias: torch.Tensor | None = None,
