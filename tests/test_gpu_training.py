@@ -441,7 +441,7 @@ def test_ar_training_step_with_dropout_equals_reference_with_the_same_masks(tmp_
 
 @pytest.mark.skipif(__import__('os').environ.get('VALLE_B200_TEST_DEVICE_ASSERT', '0') != '1',
                     reason='provokes a CUDA device-side assert in a child process on purpose; opt in with VALLE_B200_TEST_DEVICE_ASSERT=1 '
-                           '(ran green twice on a B200 this round: profiles/r02g_pytest_gpu.log counts it among its 600 passes)')
+                           '(ran green twice on a B200 this round: it was among the 600 passes of the two full runs before it became opt-in)')
 def test_out_of_range_training_ids_fail_like_the_reference(tmp_path):
     """An id outside the embedding table / class range makes the reference's nn.Embedding / F.cross_entropy fail (a device-side
     assert on CUDA, modules.py:34, valle_ar.py:85); csrc/train.cu clamps, so train.py asserts first.  A device-side assert
