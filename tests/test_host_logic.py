@@ -296,3 +296,39 @@ def test_generation_rejects_head_dims_other_than_64(tmp_path):
     model = ValleAR(cfg).eval()
     with pytest.raises(ValueError, match='== 64'):
         ARDecoder(model, 'fp32')
+
+
+def test_ar_collate_equals_the_executed_reference_on_random_batches(tmp_path):
+    """ValleARCollate (collate.py:19-46) against the executed reference (oracle/_ref, unmodified) on 40 random batches: ragged
+    clip lengths, batch sizes 1-6, the BOS / EOS shift, zero padding, int64 lengths -- every field bit-equal.  (The NAR collate
+    cannot be compared this way: upstream's raises on ragged items, SURVEY A-13.)"""
+    from oracle import ref_shims
+    if not ref_shims.reference_available():
+        pytest.skip('oracle/_ref not installed')
+    import random
+    from valle.collate import ValleARCollate
+    from valle.config import ConfigValle
+    kw = dict(ckpt_path=str(tmp_path / 'c'), log_path=str(tmp_path / 'l'))
+    ours = ValleARCollate(ConfigValle(norm='LayerNorm', **kw))
+    rng = random.Random(7)
+    g = torch.Generator().manual_seed(7)
+    batches = []
+    for _ in range(40):
+        items = []
+        for _ in range(rng.randint(1, 6)):
+            Tx = rng.randint(1, 12)
+            T = Tx + rng.randint(0, 30)                 # T + 1 (BOS) frames > Tx phonemes: the collate's own assertion holds
+            items.append({'codes': torch.randint(0, 1024, (8, T), generator=g), 'tokens': torch.randint(0, 256, (Tx,), generator=g)})
+        batches.append(items)
+    got = [ours(items) for items in batches]
+    valle = ref_shims.import_reference()
+    try:
+        import importlib
+        ref_collate = importlib.import_module('valle.collate').ValleARCollate(valle.config.ConfigValle(norm='LayerNorm', **kw))
+        want = [ref_collate(items) for items in batches]
+    finally:
+        ref_shims.release_reference()
+    for a, b in zip(got, want):
+        assert set(a) == set(b)
+        for k in b:
+            assert a[k].dtype == b[k].dtype and torch.equal(a[k], b[k]), k
