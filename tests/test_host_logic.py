@@ -332,3 +332,40 @@ def test_ar_collate_equals_the_executed_reference_on_random_batches(tmp_path):
         assert set(a) == set(b)
         for k in b:
             assert a[k].dtype == b[k].dtype and torch.equal(a[k], b[k]), k
+
+
+def test_masks_and_best_beam_equal_the_executed_reference_on_random_inputs():
+    """build_pad_mask / build_attn_mask / get_best_beam (utils.py:8-43, :71-88) against the executed reference (oracle/_ref) on
+    random inputs: every prefix-LM mask for x_len, y_len in 0..6 (the empty segments included), 30 random length vectors, 60
+    random beam sets (ragged stop-token tails, ties in the score broken as torch.argmax breaks them, three length penalties)."""
+    from oracle import ref_shims
+    if not ref_shims.reference_available():
+        pytest.skip('oracle/_ref not installed')
+    from valle.models.utils import build_attn_mask, build_pad_mask, get_best_beam
+    g = torch.Generator().manual_seed(9)
+    shapes = [(x, y) for x in range(7) for y in range(7) if x + y > 0]
+    lens_cases = [torch.randint(1, 12, (int(torch.randint(1, 7, (1,), generator=g)),), generator=g) for _ in range(30)]
+    beams = []
+    for _ in range(60):
+        nb, L = int(torch.randint(1, 6, (1,), generator=g)), int(torch.randint(3, 12, (1,), generator=g))
+        x = torch.randint(0, 1024, (nb, L), generator=g)
+        for b in range(nb):                                   # ragged tails of stop tokens (a beam that ended early)
+            tail = int(torch.randint(0, L - 1, (1,), generator=g))
+            if tail:
+                x[b, L - tail:] = 1024
+        slp = -torch.rand(nb, generator=g) * 10
+        if nb > 1 and torch.rand(1, generator=g).item() < 0.3:
+            x[1], slp[1] = x[0], slp[0]                       # an exact tie
+        beams.append((x, slp, [1.0, 0.0, 2.0][len(beams) % 3]))
+    ours = ([build_attn_mask(x, y, 'cpu') for x, y in shapes], [build_pad_mask(l, 'cpu') for l in lens_cases],
+            [get_best_beam(x, s, 1024, lp) for x, s, lp in beams])
+    valle = ref_shims.import_reference()
+    try:
+        U = valle.models.utils
+        ref = ([U.build_attn_mask(x, y, 'cpu') for x, y in shapes], [U.build_pad_mask(l, 'cpu') for l in lens_cases],
+               [U.get_best_beam(x, s, 1024, lp) for x, s, lp in beams])
+    finally:
+        ref_shims.release_reference()
+    for kind, (a_list, b_list) in zip(('attn', 'pad', 'beam'), zip(ours, ref)):
+        for i, (a, b) in enumerate(zip(a_list, b_list)):
+            assert a.shape == b.shape and a.dtype == b.dtype and torch.equal(a, b), (kind, i)
