@@ -1,6 +1,7 @@
 """Pins the CPU oracle (oracle/valle_oracle.py) against vectors frozen from the EXECUTED reference
 (oracle/make_golden.py -> tests/golden/*.npz).  CPU only."""
 import numpy as np
+import pytest
 import torch
 
 from oracle import synth
@@ -163,3 +164,95 @@ def test_ar_training_gradients_match_the_executed_reference(golden):
         scale = gg['stats.' + name][2] + 1e-12
         assert np.abs(stats - gg['stats.' + name]).max() / max(scale, gg['stats.' + name][0]) < 1e-4, name
         assert np.abs(gr[:16].numpy() - gg['head.' + name]).max() / scale < 1e-4, name
+
+
+@pytest.mark.parametrize('case', [
+    dict(seed=1, beams=1, layers=2, d=256, heads=4, F=1024, Tp=7, Tc=9, Tt=5, steps=12),
+    dict(seed=2, beams=3, layers=1, d=128, heads=2, F=256, Tp=3, Tc=4, Tt=0, steps=9),
+    dict(seed=3, beams=2, layers=3, d=192, heads=3, F=384, Tp=11, Tc=1, Tt=8, steps=7),
+])
+def test_oracle_ar_equals_the_executed_reference_live(tmp_path, case):
+    """Beyond the frozen fixtures: the oracle against the executed reference itself (oracle/_ref, unmodified source) on OTHER
+    shapes than the golden files hold -- other depths / widths / head counts, 1-3 beams, a one-frame prompt, no target text --
+    greedy tokens equal, per-step logits of every beam within 1e-5, and the teacher-forced logits + loss of a ragged batch
+    (valle_ar.py:43-90, :92-180).  Skipped where the reference is not installed."""
+    from oracle import ref_shims, synth
+    if not ref_shims.reference_available():
+        pytest.skip('oracle/_ref not installed')
+    c = case
+    oc = synth.tiny_config('LayerNorm', num_layers=c['layers'], d_model=c['d'], n_heads=c['heads'], dim_feedforward=c['F'],
+                           num_beams=c['beams'], max_audio_len=c['steps'])
+    sd = synth.synth_state_dict(synth.ar_state_shapes(oc), c['seed'])
+    g = torch.Generator().manual_seed(100 + c['seed'])
+    pt = torch.randint(0, 256, (c['Tp'],), generator=g)
+    pc = torch.randint(0, 1024, (c['Tc'], 8), generator=g)
+    tt = torch.randint(0, 256, (c['Tt'],), generator=g) if c['Tt'] else None
+    B, Tx, Ty = 3, 6, 10
+    batch = {'tokens': torch.randint(0, 256, (B, Tx), generator=g), 'tokens_lens': torch.tensor([6, 4, 5]),
+             'codes': torch.randint(0, 1024, (B, Ty), generator=g), 'codes_lens': torch.tensor([10, 7, 9]),
+             'target': torch.randint(0, 1025, (B, Ty), generator=g)}
+    out, trace, _, _ = vo.ar_generate(sd, oc, pt, pc, tt, return_trace=True)
+    tf_logits, tf_loss = vo.ar_teacher_forced(sd, oc, batch['tokens'], batch['codes'], batch['tokens_lens'], batch['codes_lens'],
+                                              batch['target'])
+    valle = ref_shims.import_reference()
+    try:
+        kw = {k: getattr(oc, k) for k in type(oc).__dataclass_fields__}
+        cfg = valle.config.ConfigValle(dropout=0.0, ckpt_path=str(tmp_path / 'c'), log_path=str(tmp_path / 'l'), **kw)
+        model = valle.models.ValleAR(cfg).eval()
+        model.load_state_dict(sd, strict=True)
+        ref_trace, ref_tf = [], []
+        hook = model.proj.register_forward_hook(lambda m, i, o: ref_trace.append(o[:, -1].clone()))
+        with torch.no_grad():
+            ref_out = model.generate(pt, pc, tt)
+        hook.remove()
+        hook = model.proj.register_forward_hook(lambda m, i, o: ref_tf.append(o.clone()))
+        with torch.no_grad():
+            ref_loss = model.training_step({k: v.clone() for k, v in batch.items()})
+        hook.remove()
+    finally:
+        ref_shims.release_reference()
+    assert torch.equal(out, ref_out)
+    assert len(trace) == len(ref_trace)
+    for a, b in zip(trace, ref_trace):
+        close(a, b.numpy(), tol=1e-5)
+    close(tf_logits, ref_tf[0].numpy(), tol=1e-5)
+    assert abs(float(tf_loss) - float(ref_loss)) < 1e-5
+
+
+@pytest.mark.parametrize('norm', ['AdaptiveLayerNorm', 'LayerNorm'])
+@pytest.mark.parametrize('L,d,H,B,S', [(1, 96, 3, 2, 7), (3, 128, 8, 4, 13)])
+def test_oracle_transformer_equals_the_executed_reference_live(tmp_path, norm, L, d, H, B, S):
+    """The oracle's Transformer / EncoderLayer / (Adaptive)LayerNorm / MHA / FFN stack (modules.py:84-352) against the executed
+    reference modules on other shapes than the fixtures: odd head counts, key-padding masks, the stage embedding of AdaLN, and a
+    KV-cached continuation of two more positions (what the NAR stages and the AR loop are made of)."""
+    from oracle import ref_shims
+    if not ref_shims.reference_available():
+        pytest.skip('oracle/_ref not installed')
+    oc = OracleConfig(num_layers=L, d_model=d, n_heads=H, dim_feedforward=2 * d, norm=norm)
+    shapes = {}
+    for i in range(L):
+        shapes.update(synth._layer_shapes(oc, f'layers.{i}.'))
+    sd = synth.synth_state_dict(shapes, 20 + L)
+    g = torch.Generator().manual_seed(d + S)
+    x = torch.randn(B, S, d, generator=g)
+    x2 = torch.randn(B, 2, d, generator=g)
+    emb = torch.randn(1, d, generator=g) if norm == 'AdaptiveLayerNorm' else None
+    lens = torch.randint(S // 2, S + 1, (B,), generator=g)
+    lens[0] = S
+    pad = vo.build_pad_mask(lens)
+    y, kv = vo.transformer(x, sd, oc, prefix='', padding_mask=pad, embedding=emb, use_cache=True)
+    y2, _ = vo.transformer(torch.cat([x, x2], 1), sd, oc, prefix='', embedding=emb, kv_cache=kv, use_cache=True)
+    valle = ref_shims.import_reference()
+    try:
+        kw = {k: getattr(oc, k) for k in type(oc).__dataclass_fields__}
+        cfg = valle.config.ConfigValle(dropout=0.0, ckpt_path=str(tmp_path / 'c'), log_path=str(tmp_path / 'l'), **kw)
+        tr = valle.models.modules.Transformer(cfg).eval()
+        tr.load_state_dict(sd, strict=True)
+        with torch.no_grad():
+            ry, rkv = tr(x, padding_mask=pad, embedding=emb, use_cache=True)
+            ry2, _ = tr(torch.cat([x, x2], 1), embedding=emb, kv_cache=rkv, use_cache=True)
+    finally:
+        ref_shims.release_reference()
+    close(y, ry.numpy(), tol=1e-5)
+    close(y2, ry2.numpy(), tol=1e-5)
+    close(kv[-1][0], rkv[-1][0].numpy(), tol=1e-5)
