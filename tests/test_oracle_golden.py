@@ -256,3 +256,31 @@ def test_oracle_transformer_equals_the_executed_reference_live(tmp_path, norm, L
     close(y, ry.numpy(), tol=1e-5)
     close(y2, ry2.numpy(), tol=1e-5)
     close(kv[-1][0], rkv[-1][0].numpy(), tol=1e-5)
+
+
+def test_oracle_sampling_filter_equals_the_transformers_warpers_live():
+    """The third-party arithmetic of the path (transformers' top-k / top-p warpers behind `top_k_top_p_filtering`, utils.py:63):
+    the oracle's restatement against the installed library's own warper classes on 60 random (k, p) pairs and three logit
+    tables -- smooth, heavy ties (logits rounded to halves) and one dominant class -- the kept SET and the kept values equal."""
+    from oracle.ref_shims import _top_k_top_p_filtering
+    pytest.importorskip('transformers')
+    g = torch.Generator().manual_seed(17)
+    smooth = torch.randn(5, 1025, generator=g) * 3
+    ties = (torch.randn(5, 1025, generator=g) * 2).mul(2).round().div(2)
+    peaked = torch.randn(5, 1025, generator=g)
+    peaked[:, 77] += 25.0
+    ks = [0, 1, 2, 5, 50, 1024, 1025, 4000]
+    for i in range(60):
+        k = ks[i % len(ks)]
+        p = [1.0, 0.0, 0.999, 0.5][i % 4] if i < 16 else float(torch.rand(1, generator=g))
+        for name, lg in (('smooth', smooth), ('ties', ties), ('peaked', peaked)):
+            mine = vo.top_k_top_p_filter(lg, k, p)
+            ref = _top_k_top_p_filtering(lg.clone(), top_k=k, top_p=p)
+            if name == 'ties' and p < 1:
+                # the order of equal logits inside torch.sort is the only freedom (the oracle sorts stably, the library does
+                # not promise to): the kept COUNT per row and the multiset of kept values must still agree
+                assert torch.equal(torch.isinf(mine).sum(-1), torch.isinf(ref).sum(-1)), (name, k, p)
+                assert torch.equal(mine.sort(-1).values, ref.sort(-1).values), (name, k, p)
+            else:
+                assert torch.equal(torch.isinf(mine), torch.isinf(ref)), (name, k, p)
+                assert torch.equal(mine[~torch.isinf(mine)], ref[~torch.isinf(ref)]), (name, k, p)
