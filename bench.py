@@ -19,7 +19,9 @@ Prints ONE JSON line on rank 0:
             step's HBM roofline fraction); on one GPU also batch 1, NAR configs[2], the training steps of configs[4] and the
             torch-eager reference on the same GPU
   cpu_baseline  the EXECUTED reference (oracle/_ref, unmodified) on the host cores, bounded sample (N = 1 only)
-`--impl reference` times that executed reference alone (rank 0), same metric / unit / config.workload.
+  config    the WORKLOAD only (built by workload_config(): both arms print the identical object)
+  run       what this arm did with it: launches per decode step, decode GEMM form, sharded_equals_single_gpu, derived rates
+`--impl reference` times that executed reference alone (rank 0), same metric / unit / config.
 """
 from __future__ import annotations
 
