@@ -4,7 +4,7 @@
  * The reference (KubiakJakub01/Valle2) has no FFI: its "operator interface" for this path is the
  * set of ATen call sites inside valle/models/{modules,utils,valle_ar,valle_nar}.py.  Each entry
  * point below replaces one (or a fused group) of those call sites; the reference file:line it
- * stands in for is cited next to it.  The Python host mirror (valle2_b200/models/*.py) binds these
+ * stands in for is cited next to it.  The Python host mirror (the modules under valle2_b200/models) binds these
  * symbols with ctypes (valle2_b200/_lib.py) -- see INTEGRATION.md for the binding stub.
  *
  * Conventions

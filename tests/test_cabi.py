@@ -48,3 +48,34 @@ def test_no_cpu_fallback():
     from valle2_b200 import ops
     with pytest.raises(Exception):
         ops.linear(torch.zeros(4, 64), torch.zeros(8, 64))
+
+
+def test_header_is_plain_c_and_a_c_program_links_through_it(tmp_path):
+    """The boundary is a C ABI: include/valle_b200.h must compile as C99 (no C++ in the signatures), and a C translation unit
+    that includes it must link against libvalle_b200.so and call into it (pure queries and an argument check only: no GPU here)."""
+    import os
+    import shutil
+    import subprocess
+    import pytest
+    from valle2_b200 import _lib
+    if shutil.which('gcc') is None:
+        pytest.skip('gcc not available')
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / 'use_abi.c'
+    src.write_text('''
+#include <stdio.h>
+#include <string.h>
+#include "valle_b200.h"
+int main(void) {
+    int splits = vb_linear_decode_splits(3072, 1024, 32);
+    int rc = vb_linear_argmax(NULL, 0, NULL, 0, NULL, NULL, 1, 1, 1, 2048, 1024, 1024, NULL);
+    printf("%d %d %d %d\\n", vb_version(), splits, rc, (int)(strstr(vb_last_error_string(), "null") != NULL));
+    return 0;
+}
+''')
+    exe = tmp_path / 'use_abi'
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    subprocess.run(['gcc', '-std=c99', '-Wall', '-Werror', '-pedantic', '-I', os.path.join(root, 'include'), str(src), '-o', str(exe),
+                    '-L', libdir, '-lvalle_b200', f'-Wl,-rpath,{libdir}'], check=True, capture_output=True, text=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
+    assert int(out[0]) >= 100 and 1 <= int(out[1]) <= 8 and int(out[2]) == -1 and int(out[3]) == 1
