@@ -369,3 +369,37 @@ def test_masks_and_best_beam_equal_the_executed_reference_on_random_inputs():
     for kind, (a_list, b_list) in zip(('attn', 'pad', 'beam'), zip(ours, ref)):
         for i, (a, b) in enumerate(zip(a_list, b_list)):
             assert a.shape == b.shape and a.dtype == b.dtype and torch.equal(a, b), (kind, i)
+
+
+def test_product_never_imports_the_oracle_or_the_reference():
+    """The oracle (and the executed reference under oracle/_ref) is test infrastructure: no module of the product packages may
+    import it, and importing the product must not pull it in -- a product path through the checker would void every parity
+    claim.  Static: no import statement naming `oracle` in valle2_b200/ or valle/.  Dynamic: a fresh interpreter that imports the
+    whole product surface has no `oracle*` module loaded."""
+    import ast
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    offenders = []
+    for pkg in ('valle2_b200', 'valle'):
+        for dirpath, _, files in os.walk(os.path.join(root, pkg)):
+            for f in files:
+                if not f.endswith('.py'):
+                    continue
+                path = os.path.join(dirpath, f)
+                for node in ast.walk(ast.parse(open(path, encoding='utf-8').read())):
+                    names = []
+                    if isinstance(node, ast.Import):
+                        names = [a.name for a in node.names]
+                    elif isinstance(node, ast.ImportFrom):
+                        names = [node.module or '']
+                    if any(n == 'oracle' or n.startswith('oracle.') for n in names):
+                        offenders.append(path)
+    assert not offenders, offenders
+    code = ('import sys; sys.path.insert(0, %r); import valle2_b200, valle; from valle2_b200 import engine, ops, train, tts, parallel, '
+            'collate, checkpoint, train_model; from valle.models import ValleAR, ValleNAR, modules, utils; '
+            'bad = [m for m in sys.modules if m == "oracle" or m.startswith("oracle.")]; print("BAD", bad)') % root
+    out = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-800:]
+    assert 'BAD []' in out.stdout, out.stdout
