@@ -79,3 +79,23 @@ int main(void) {
                     '-L', libdir, '-lvalle_b200', f'-Wl,-rpath,{libdir}'], check=True, capture_output=True, text=True)
     out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
     assert int(out[0]) >= 100 and 1 <= int(out[1]) <= 8 and int(out[2]) == -1 and int(out[3]) == 1
+
+
+def test_a_missing_library_fails_loudly():
+    """No CPU fallback: with the extension absent (VALLE_B200_LIB pointing at a file that does not exist) the first op raises --
+    a fresh interpreter, so the already-loaded handle of this process is not in the way."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ('import sys; sys.path.insert(0, %r)\n'
+            'from valle2_b200 import _lib\n'
+            'try:\n'
+            '    _lib.load()\n'
+            'except OSError as e:\n'
+            '    print("LOUD", type(e).__name__)\n'
+            'else:\n'
+            '    print("SILENT")\n') % root
+    env = dict(os.environ, VALLE_B200_LIB='/nonexistent/libvalle_b200.so')
+    out = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, timeout=300, env=env)
+    assert 'LOUD' in out.stdout and 'SILENT' not in out.stdout, (out.stdout, out.stderr[-500:])
